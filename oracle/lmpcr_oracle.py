@@ -1,0 +1,485 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (numpy) of the reference's pairwise-registration hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module, and only as the checker.  The product (3d_multiview_reg_b200) never imports anything from oracle/.
+
+Parity status: PINNED by execution of the unmodified reference.  The reference has no tests, golden
+vectors or fixtures of its own, so this restatement is pinned against outputs of the
+reference itself, generated in the build container by tests/golden/make_golden.py (which imports
+/root/reference through oracle/refimport.py) and committed under tests/golden/*.npz;
+tests/test_oracle_golden.py re-checks the restatement against those files on every run.
+
+Every function cites the reference file:line (relative to the reference root) that it follows.
+Arithmetic is carried out in `dtype` (float32 = the reference's precision; float64 = truth witness).
+"""
+import itertools
+import math
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------------------
+# Stage 1: feature-space nearest neighbours  (lib/utils.py:968-992, lib/layers.py:57,81-86)
+# --------------------------------------------------------------------------------------------------
+
+
+def sqnorm_rows_f32(f):
+    """torch.sum(f ** 2, dim=-1) in float32 as the reference evaluates it (lib/utils.py:989-990).
+
+    Summation order probed against torch 2.11 CPU (see DESIGN.md "fp32 evaluation order"): eight lane
+    accumulators t[l] = ((q[l] + q[8+l]) + q[16+l]) + ... over chunks of 8, then t[0] + t[1] + ... + t[7]
+    sequentially, q = fl(f*f).  Bit-exact versus torch for D = 32 (the FCGF dimension).
+    """
+    f = np.ascontiguousarray(f, dtype=np.float32)
+    n, d = f.shape
+    assert d % 8 == 0
+    q = (f * f).astype(np.float32)
+    t = q[:, 0:8].copy()
+    for c in range(1, d // 8):
+        t = (t + q[:, 8 * c:8 * c + 8]).astype(np.float32)
+    s = t[:, 0].copy()
+    for l in range(1, 8):
+        s = (s + t[:, l]).astype(np.float32)
+    return s
+
+
+def _dot_seq_fma_f32(a, b):
+    """fp32 a @ b.T with a sequential fused-multiply-add chain over k (k = 0..D-1, accumulator starts at
+    0), which is what torch.matmul (MKL sgemm, K = 32) produces bit-for-bit (lib/utils.py:984; probed).
+    float64 emulation of fmaf: the product of two fp32 numbers is exact in fp64; the fp64 add followed
+    by the fp32 rounding can differ from a true fma only on double-rounding ties (probability ~2^-29
+    per op); oracle/nn_oracle.c holds the exact fmaf version used for large cases."""
+    a64 = np.asarray(a, dtype=np.float64)
+    b64 = np.asarray(b, dtype=np.float64)
+    acc = np.zeros((a.shape[0], b.shape[0]), dtype=np.float32)
+    for k in range(a.shape[1]):
+        acc = (a64[:, k:k + 1] * b64[None, :, k] + acc.astype(np.float64)).astype(np.float32)
+    return acc
+
+
+def pairwise_distance_f32(src, dst):
+    """lib/utils.py:968-992 with normalized_feature=False (the only mode its callers use,
+    lib/layers.py:57):  dist = -(src @ dst^T); dist = 2*dist; dist += |src|^2[:,None]; dist += |dst|^2[None,:]
+    each step rounded to fp32."""
+    c = _dot_seq_fma_f32(src, dst)
+    dist = (np.float32(2.0) * (-c)).astype(np.float32)
+    dist = (dist + sqnorm_rows_f32(src)[:, None]).astype(np.float32)
+    dist = (dist + sqnorm_rows_f32(dst)[None, :]).astype(np.float32)
+    return dist
+
+
+def nn_argmin_f32(src, dst):
+    """Hard nearest neighbour of every src row among dst rows: lib/layers.py:81 `dist.min(dim=2)[1]`
+    (first minimum wins ties, probed on torch CPU).  Returns (idx int32 [n], dist fp32 [n])."""
+    dist = pairwise_distance_f32(src, dst)
+    idx = np.argmin(dist, axis=1).astype(np.int32)
+    return idx, dist[np.arange(dist.shape[0]), idx]
+
+
+def hard_correspondences(x_f, y_f, y_c):
+    """Soft_NN(corr_type='hard').forward (lib/layers.py:44-88): one-hot(argmin) @ y_c == y_c[argmin]."""
+    idx, _ = nn_argmin_f32(x_f, y_f)
+    return np.asarray(y_c, dtype=np.float32)[idx], idx
+
+
+def mutual_index(idx_st, idx_ts):
+    """Index definition of a mutual nearest neighbour, scripts/extract_data.py:186-190, expressed for
+    source points:  i is mutual iff idx_ts[idx_st[i]] == i."""
+    idx_st = np.asarray(idx_st)
+    idx_ts = np.asarray(idx_ts)
+    return (idx_ts[idx_st] == np.arange(idx_st.shape[0])).astype(np.uint8)
+
+
+def knn_point_1(pos1, pos2):
+    """lib/utils.py:274-299 with k=1: for every row of pos2 the index of the closest row of pos1 under
+    sum(-(p1-p2)^2) (fp32, direct differences), torch.topk -> first maximum."""
+    p1 = np.asarray(pos1, dtype=np.float32)
+    p2 = np.asarray(pos2, dtype=np.float32)
+    out = np.empty(p2.shape[0], dtype=np.int64)
+    for s in range(0, p2.shape[0], 1024):
+        d = p1[None, :, :] - p2[s:s + 1024, None, :]
+        d = (d * d).astype(np.float32)
+        dist = -((d[..., 0] + d[..., 1]).astype(np.float32) + d[..., 2]).astype(np.float32)
+        out[s:s + 1024] = np.argmax(dist, axis=1)
+    return out
+
+
+def extract_mutuals(x1, x2, x1_soft_matches, x2_soft_matches, threshold=0.05):
+    """Geometric mutual test, lib/utils.py:822-848 (single pair, no batch axis)."""
+    idx = knn_point_1(x2, x1_soft_matches)
+    delta = np.asarray(x1, np.float32) - np.asarray(x2_soft_matches, np.float32)[idx]
+    d2 = (delta * delta).astype(np.float32)
+    dist = ((d2[:, 0] + d2[:, 1]).astype(np.float32) + d2[:, 2]).astype(np.float32)
+    return (dist < np.float32(threshold ** 2)).astype(np.float32)
+
+
+def enumerate_pairs(n_scans):
+    """lib/utils.py:873-876: itertools.combinations(range(S), 2), lexicographic."""
+    return np.array(list(itertools.combinations(range(n_scans), 2)), dtype=np.int32).reshape(-1, 2)
+
+
+def construct_xs(xyz_s, xyz_t_corr, mutuals=None):
+    """lib/utils.py:915-926: xs = cat(xyz_s, xyz_t_corr [, mutuals]) -> [1, n, 6(7)] (batch axis added by caller)."""
+    xs = np.concatenate([np.asarray(xyz_s, np.float32), np.asarray(xyz_t_corr, np.float32)], axis=-1)
+    if mutuals is not None:
+        xs = np.concatenate([xs, np.asarray(mutuals, np.float32).reshape(-1, 1)], axis=-1)
+    return xs[None]
+
+
+def register_pair_stage1(feat_s, feat_t, xyz_s, xyz_t, mutual_mode="index", mutual_thresh=0.05):
+    """Stage 1 for one scan pair, hard NN both ways (lib/pairwise/__init__.py:110-120)."""
+    idx_st, _ = nn_argmin_f32(feat_s, feat_t)
+    idx_ts, _ = nn_argmin_f32(feat_t, feat_s)
+    xyz_s = np.asarray(xyz_s, np.float32)
+    xyz_t = np.asarray(xyz_t, np.float32)
+    if mutual_mode == "index":
+        mutual = mutual_index(idx_st, idx_ts)
+    else:  # geometric definition evaluated through the index chase (hard NN: soft match == a target point)
+        back = xyz_s[idx_ts[idx_st]]
+        delta = xyz_s - back
+        d2 = (delta * delta).astype(np.float32)
+        dist = ((d2[:, 0] + d2[:, 1]).astype(np.float32) + d2[:, 2]).astype(np.float32)
+        mutual = (dist < np.float32(mutual_thresh ** 2)).astype(np.uint8)
+    xs = construct_xs(xyz_s, xyz_t[idx_st])
+    return idx_st, idx_ts, mutual, xs
+
+
+# --------------------------------------------------------------------------------------------------
+# Stage 3: weighted Kabsch + residuals  (lib/utils.py:164-256)
+# --------------------------------------------------------------------------------------------------
+
+
+def transformation_residuals(x1, x2, R, t, dtype=np.float32):
+    """lib/utils.py:240-256:  || (R x1^T + t)^T - x2 ||_2 per correspondence.  x1,x2 [P,n,3], R [P,3,3], t [P,3,1]."""
+    x1 = np.asarray(x1, dtype)
+    x2 = np.asarray(x2, dtype)
+    rec = np.matmul(np.asarray(R, dtype), x1.transpose(0, 2, 1)) + np.asarray(t, dtype)
+    return np.linalg.norm(rec.transpose(0, 2, 1) - x2, axis=2).astype(dtype)
+
+
+def kabsch(x1, x2, weights, eps=1e-7, dtype=np.float32):
+    """lib/utils.py:164-237 (normalize_w=True, best_k=0, w_threshold=0 -- the only mode its callers use).
+    Returns R [P,3,3], t [P,3,1], res [P,n], flag."""
+    x1 = np.asarray(x1, dtype)
+    x2 = np.asarray(x2, dtype)
+    w = np.asarray(weights, dtype)
+    eps = dtype(eps)
+    w = w / (w.sum(axis=1, keepdims=True) + eps)              # :187-189
+    w = w[:, :, None]
+    wsum = w.sum(axis=1)[:, None] + eps                       # :203-204
+    x1_mean = np.matmul(w.transpose(0, 2, 1), x1) / wsum
+    x2_mean = np.matmul(w.transpose(0, 2, 1), x2) / wsum
+    x1c = x1 - x1_mean
+    x2c = x2 - x2_mean
+    cov = np.matmul(x1c.transpose(0, 2, 1), w * x2c)          # :209-212 (diag_embed matmul)
+    try:
+        u, s, vh = np.linalg.svd(cov)                         # :215
+    except np.linalg.LinAlgError:                             # :216-223
+        P = x1.shape[0]
+        R = np.tile(np.eye(3, dtype=dtype), (P, 1, 1))
+        t = np.zeros((P, 3, 1), dtype)
+        return R, t, transformation_residuals(x1, x2, R, t, dtype), True
+    v = vh.transpose(0, 2, 1)
+    det = np.linalg.det(np.matmul(vh, u.transpose(0, 2, 1)))  # :225  det(V^T U^T)
+    D = np.tile(np.eye(3, dtype=dtype), (x1.shape[0], 1, 1))
+    D[:, 2, 2] = det.astype(dtype)
+    R = np.matmul(v, np.matmul(D, u.transpose(0, 2, 1))).astype(dtype)       # :229
+    t = (x2_mean.transpose(0, 2, 1) - np.matmul(R, x1_mean.transpose(0, 2, 1))).astype(dtype)  # :232
+    return R, t, transformation_residuals(x1, x2, R, t, dtype), False
+
+
+def pair_confidence(weights, residuals, eps=1e-7, inlier_w=0.5, inlier_res=0.05):
+    """Per-pair confidence record.  The released reference code has no per-pair confidence (SURVEY.md
+    8a row a15); the build defines it from the quantities its callers threshold:
+    [ #(w > 0.5)  (scripts/benchmark_pairwise_registration.py:211),  sum(w),
+      sqrt(sum(w_norm * res^2))  with w_norm as in lib/utils.py:187-189,
+      #(res < 5 cm)  (lib/utils.py:888 dist_th) ]."""
+    w = np.asarray(weights, np.float64)
+    r = np.asarray(residuals, np.float64)
+    wn = w / (w.sum(axis=1, keepdims=True) + eps)
+    return np.stack([(w > inlier_w).sum(axis=1).astype(np.float64), w.sum(axis=1),
+                     np.sqrt((wn * r * r).sum(axis=1)), (r < inlier_res).sum(axis=1).astype(np.float64)], axis=1)
+
+
+def chordal_angle(Ra, Rb):
+    """2*asin(|Ra-Rb|_F / (2*sqrt(2))) in fp64 -- the rotation metric used for every pose gate (the
+    reference's acos((tr-1)/2), lib/utils.py:135-143, has a 5e-4 rad noise floor in fp32)."""
+    d = np.linalg.norm(np.asarray(Ra, np.float64) - np.asarray(Rb, np.float64), axis=(-2, -1))
+    return 2.0 * np.arcsin(np.clip(d / (2.0 * math.sqrt(2.0)), 0.0, 1.0))
+
+
+# --------------------------------------------------------------------------------------------------
+# Stage 2: correspondence-weighting network  (lib/filtering/oanet.py)
+# --------------------------------------------------------------------------------------------------
+
+
+class _SD:
+    """state_dict view with a key prefix; values as numpy arrays of the working dtype."""
+
+    def __init__(self, sd, prefix, dtype):
+        self.sd, self.prefix, self.dtype = sd, prefix, dtype
+
+    def sub(self, name):
+        return _SD(self.sd, self.prefix + name + ".", self.dtype)
+
+    def __getitem__(self, name):
+        v = self.sd[self.prefix + name]
+        if hasattr(v, "detach"):
+            v = v.detach().cpu().numpy()
+        return np.asarray(v, self.dtype)
+
+    def has(self, name):
+        return (self.prefix + name) in self.sd
+
+
+def _inorm(x, eps):
+    """nn.InstanceNorm2d(affine=False, track_running_stats=False): per (pair, channel) over the point axis,
+    biased variance (oanet.py:27,31,65,79,101,118).  x [P,C,L]."""
+    mean = x.mean(axis=2, keepdims=True)
+    var = ((x - mean) ** 2).mean(axis=2, keepdims=True)
+    return (x - mean) / np.sqrt(var + x.dtype.type(eps))
+
+
+def _bn_eval(x, sd, eps=1e-5):
+    """nn.BatchNorm2d in eval mode (running statistics), channel axis = 1 (oanet.py:28,32,66,73,80,102,119)."""
+    s = sd["weight"] / np.sqrt(sd["running_var"] + x.dtype.type(eps))
+    return (x - sd["running_mean"][None, :, None]) * s[None, :, None] + sd["bias"][None, :, None]
+
+
+def _conv1x1(x, sd):
+    """nn.Conv2d(kernel_size=1): W [Co,Ci,1,1] applied per point."""
+    W = sd["weight"].reshape(sd["weight"].shape[0], -1)
+    return np.einsum("oc,pcl->pol", W, x, optimize=True).astype(x.dtype) + sd["bias"][None, :, None]
+
+
+def _relu(x):
+    return np.maximum(x, 0)
+
+
+def _pointcn(x, sd):
+    """PointCN, oanet.py:18-43."""
+    h = _relu(_bn_eval(_inorm(x, 1e-5), sd.sub("conv.1")))
+    h = _conv1x1(h, sd.sub("conv.3"))
+    h = _relu(_bn_eval(_inorm(h, 1e-5), sd.sub("conv.5")))
+    h = _conv1x1(h, sd.sub("conv.7"))
+    if sd.has("shot_cut.weight"):
+        return h + _conv1x1(x, sd.sub("shot_cut"))
+    return h + x
+
+
+def _oafilter(x, sd):
+    """OAFilter, oanet.py:56-93 (x [P,C,K])."""
+    out = _conv1x1(_relu(_bn_eval(_inorm(x, 1e-3), sd.sub("conv1.1"))), sd.sub("conv1.3"))
+    out = out.transpose(0, 2, 1)                                   # trans(1,2): [P,K,C]
+    out = out + _conv1x1(_relu(_bn_eval(out, sd.sub("conv2.0"))), sd.sub("conv2.2"))
+    out = out.transpose(0, 2, 1)
+    out = _conv1x1(_relu(_bn_eval(_inorm(out, 1e-3), sd.sub("conv3.2"))), sd.sub("conv3.4"))
+    return out + x
+
+
+def _softmax(x, axis):
+    m = x.max(axis=axis, keepdims=True)
+    e = np.exp(x - m)
+    return e / e.sum(axis=axis, keepdims=True)
+
+
+def _diff_pool(x, sd):
+    """diff_pool, oanet.py:96-110: softmax over the POINT axis."""
+    embed = _conv1x1(_relu(_bn_eval(_inorm(x, 1e-3), sd.sub("conv.1"))), sd.sub("conv.3"))   # [P,K,N]
+    S = _softmax(embed, axis=2)
+    return np.matmul(x, S.transpose(0, 2, 1))                       # [P,C,K]
+
+
+def _diff_unpool(x_up, x_down, sd):
+    """diff_unpool, oanet.py:113-129: softmax over the CLUSTER axis."""
+    embed = _conv1x1(_relu(_bn_eval(_inorm(x_up, 1e-3), sd.sub("conv.1"))), sd.sub("conv.3"))  # [P,K,N]
+    S = _softmax(embed, axis=1)
+    return np.matmul(x_down, S)                                     # [P,C,N]
+
+
+def oan_block(data, xs, sd, depth, dtype, guard="batch"):
+    """OANBlock.forward, oanet.py:165-185.  data [P,Cin,N]; xs [P,1,N,>=6]."""
+    half = depth // 2
+    x = _conv1x1(data, sd.sub("conv1"))
+    for i in range(half):
+        x = _pointcn(x, sd.sub("l1_1.%d" % i))
+    x1_1 = x
+    x_down = _diff_pool(x1_1, sd.sub("down1"))
+    x2 = x_down
+    for i in range(half):
+        x2 = _oafilter(x2, sd.sub("l2.%d" % i))
+    x_up = _diff_unpool(x1_1, x2, sd.sub("up1"))
+    out = np.concatenate([x1_1, x_up], axis=1)
+    for i in range(half):
+        out = _pointcn(out, sd.sub("l1_2.%d" % i))
+    logits = _conv1x1(out, sd.sub("output"))[:, 0, :]
+    weights = _relu(np.tanh(logits))
+    zero = weights.sum(axis=1) == 0.0
+    if guard == "batch":                                            # oanet.py:177-178 (batch-coupled, Q6)
+        if np.any(zero):
+            weights = weights + dtype(1.0 / weights.shape[1])
+    else:                                                           # per-pair guard (scene / multi-GPU mode)
+        weights = weights + zero[:, None].astype(dtype) * dtype(1.0 / weights.shape[1])
+    x1, x2c = xs[:, 0, :, :3], xs[:, 0, :, 3:6]
+    R, t, res, flag = kabsch(x1, x2c, weights, dtype=dtype)
+    return logits, weights, R, t, res, out, flag
+
+
+def oanet_forward(xs, state_dict, net_depth=12, iter_num=1, prefix="", dtype=np.float32, guard="batch"):
+    """OANet.forward, oanet.py:218-265, eval mode.  xs [P,1,N,6(+1)].  state_dict: reference key names
+    (optionally with `prefix`, e.g. 'filtering_module.')."""
+    xs = np.asarray(xs, dtype)
+    assert xs.ndim == 4 and xs.shape[1] == 1
+    depth = net_depth // (iter_num + 1)
+    sd = _SD(state_dict, prefix, dtype)
+    inp = xs.transpose(0, 3, 2, 1)[:, :, :, 0]                       # [P,Cx,N]
+    out = {"logits": [], "scores": [], "rot_est": [], "trans_est": [], "residuals": []}
+    logits, w, R, t, res, lat, flag = oan_block(inp, xs, sd.sub("reg_init"), depth, dtype, guard)
+    for k, v in zip(("logits", "scores", "rot_est", "trans_est", "residuals"), (logits, w, R, t, res)):
+        out[k].append(v)
+    for i in range(iter_num):
+        data = np.concatenate([inp, res[:, None, :], w[:, None, :]], axis=1)
+        logits, w, R, t, res, lat, f2 = oan_block(data, xs, sd.sub("reg_iter.%d" % i), depth, dtype, guard)
+        flag = flag or f2
+        for k, v in zip(("logits", "scores", "rot_est", "trans_est", "residuals"), (logits, w, R, t, res)):
+            out[k].append(v)
+    out["latent features"] = lat[:, :, :, None]
+    out["gradient_flag"] = flag
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Synthetic 3DMatch-shaped data -- shared by tests, smoke() and bench.py
+# --------------------------------------------------------------------------------------------------
+
+
+def random_rotation(rng):
+    axis = rng.standard_normal(3)
+    axis /= np.linalg.norm(axis)
+    ang = rng.uniform(0, math.pi)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + math.sin(ang) * K + (1 - math.cos(ang)) * (K @ K)
+
+
+def synth_scene(n_scans, n_pts, dim=32, overlap=0.3, sigma=0.3, seed=41):
+    """Unit-norm `dim`-d features + 2.5 cm-grid coordinates; every scan shares `overlap`*n_pts world points
+    (noise-perturbed features, 1 cm coordinate noise) with a common pool; per-scan random rigid pose."""
+    rng = np.random.default_rng(seed)
+    n_ov = int(round(overlap * n_pts))
+    pool_xyz = np.round(rng.uniform(0, 3, size=(n_ov, 3)) / 0.025) * 0.025
+    pool_f = rng.standard_normal((n_ov, dim))
+    pool_f /= np.linalg.norm(pool_f, axis=1, keepdims=True)
+    feats = np.empty((n_scans, n_pts, dim), np.float32)
+    xyz = np.empty((n_scans, n_pts, 3), np.float32)
+    poses = []
+    for s in range(n_scans):
+        R, t = random_rotation(rng), rng.standard_normal(3)
+        poses.append((R, t))
+        own_xyz = np.round(rng.uniform(0, 3, size=(n_pts - n_ov, 3)) / 0.025) * 0.025
+        own_f = rng.standard_normal((n_pts - n_ov, dim))
+        f = np.concatenate([pool_f + sigma * rng.standard_normal((n_ov, dim)) / math.sqrt(dim), own_f], axis=0)
+        f /= np.linalg.norm(f, axis=1, keepdims=True)
+        world = np.concatenate([pool_xyz + 0.01 * rng.standard_normal((n_ov, 3)), own_xyz], axis=0)
+        local = (world - t) @ R                                      # world = R local + t
+        perm = rng.permutation(n_pts)
+        feats[s] = f[perm].astype(np.float32)
+        xyz[s] = local[perm].astype(np.float32)
+    return feats, xyz, poses
+
+
+def synth_xs(n_pairs, n_pts, inlier_frac=0.3, seed=41, noise=0.01):
+    """Filter-only inputs xs [P,1,N,6] with a planted rigid motion on `inlier_frac` of the correspondences."""
+    rng = np.random.default_rng(seed)
+    xs = np.empty((n_pairs, 1, n_pts, 6), np.float32)
+    Rs = np.empty((n_pairs, 3, 3))
+    ts = np.empty((n_pairs, 3))
+    for p in range(n_pairs):
+        R, t = random_rotation(rng), rng.standard_normal(3)
+        x1 = rng.uniform(0, 3, size=(n_pts, 3))
+        x2 = x1 @ R.T + t + noise * rng.standard_normal((n_pts, 3))
+        n_out = n_pts - int(round(inlier_frac * n_pts))
+        out_idx = rng.permutation(n_pts)[:n_out]
+        x2[out_idx] = rng.uniform(-1, 4, size=(n_out, 3))
+        xs[p, 0, :, :3] = x1
+        xs[p, 0, :, 3:] = x2
+        Rs[p], ts[p] = R, t
+    return xs, Rs, ts
+
+
+# --------------------------------------------------------------------------------------------------
+# Parameter schema of the filtering network + seeded synthetic weights
+# --------------------------------------------------------------------------------------------------
+
+
+def oanet_param_schema(net_channel=128, clusters=500, net_depth=12, iter_num=1, side_channel=0):
+    """[(name, shape)] in the order of OANet(cfg).state_dict() (oanet.py:133-163,199-215), including the
+    BatchNorm buffers (`num_batches_tracked` has shape ())."""
+    C, K = net_channel, clusters
+    half = (net_depth // (iter_num + 1)) // 2
+    out = []
+
+    def conv(p, co, ci):
+        out.append((p + ".weight", (co, ci, 1, 1)))
+        out.append((p + ".bias", (co,)))
+
+    def bn(p, c):
+        for n in ("weight", "bias", "running_mean", "running_var"):
+            out.append((p + "." + n, (c,)))
+        out.append((p + ".num_batches_tracked", ()))
+
+    def pointcn(p, ci, co):
+        if ci != co:
+            conv(p + ".shot_cut", co, ci)
+        bn(p + ".conv.1", ci)
+        conv(p + ".conv.3", co, ci)
+        bn(p + ".conv.5", co)
+        conv(p + ".conv.7", co, co)
+
+    def block(p, cin):
+        conv(p + ".conv1", C, cin)
+        bn(p + ".down1.conv.1", C)
+        conv(p + ".down1.conv.3", K, C)
+        bn(p + ".up1.conv.1", C)
+        conv(p + ".up1.conv.3", K, C)
+        for i in range(half):
+            pointcn(p + ".l1_1.%d" % i, C, C)
+        pointcn(p + ".l1_2.0", 2 * C, C)
+        for i in range(1, half):
+            pointcn(p + ".l1_2.%d" % i, C, C)
+        for i in range(half):
+            q = p + ".l2.%d" % i
+            bn(q + ".conv1.1", C)
+            conv(q + ".conv1.3", C, C)
+            bn(q + ".conv2.0", K)
+            conv(q + ".conv2.2", K, K)
+            bn(q + ".conv3.2", C)
+            conv(q + ".conv3.4", C, C)
+        conv(p + ".output", 1, C)
+
+    block("reg_init", 6 + side_channel)
+    for i in range(iter_num):
+        block("reg_iter.%d" % i, 8 + side_channel)
+    return out
+
+
+def synth_state_dict(seed=41, **cfg):
+    """Seeded weights for the filtering network (numpy PCG64: identical on every machine).  Conv weights
+    ~ U(+-1/sqrt(fan_in)) like torch's default init; BatchNorm affine AND running statistics are
+    randomised (default init leaves running_mean=0 / running_var=1, which would hide BN-folding bugs)."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for name, shape in oanet_param_schema(**cfg):
+        leaf = name.rsplit(".", 1)[1]
+        if leaf == "num_batches_tracked":
+            sd[name] = np.array(0, np.int64)
+        elif len(shape) == 4:
+            b = 1.0 / math.sqrt(shape[1])
+            sd[name] = rng.uniform(-b, b, size=shape).astype(np.float32)
+        elif leaf == "running_var":
+            sd[name] = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        elif leaf == "running_mean":
+            sd[name] = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+        elif leaf == "weight":                                   # BN gamma
+            sd[name] = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        else:                                                     # conv bias / BN beta
+            sd[name] = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+    return sd
