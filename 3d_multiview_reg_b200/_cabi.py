@@ -1,0 +1,270 @@
+"""ctypes binding of liblmpcr_b200.so (include/lmpcr_b200.h).
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed only: every function here takes
+CUDA tensors, hands their raw device pointers and the current CUDA stream to the C ABI, and returns fresh
+tensors.  There is NO CPU fallback: if the shared library is missing, or the tensors are not on a CUDA (sm_100)
+device, the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblmpcr_b200.so")
+
+NN_EXACT_SIMT, NN_TENSOR = 0, 1
+MUTUAL_INDEX, MUTUAL_GEOMETRIC = 0, 1
+GUARD_BATCH, GUARD_PAIR = 0, 1
+STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
+
+EXPORTS = [
+    "lmpcr_abi_version", "lmpcr_last_error", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
+    "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
+]
+
+
+class LmpcrError(RuntimeError):
+    pass
+
+
+class FilterCfg(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("net_channel", "clusters", "net_depth", "iter_num", "side_channel", "guard_mode", "gemm_algo", "reserved")]
+
+
+_lib = None
+_vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+
+def load():
+    """Loads the C-ABI library (once).  Raises LmpcrError when it has not been built -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LmpcrError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.lmpcr_abi_version.restype = _i
+    lib.lmpcr_last_error.restype = ctypes.c_char_p
+    lib.lmpcr_device_info.argtypes = [ctypes.POINTER(_i)] * 4
+    lib.lmpcr_nn_workspace_bytes.restype = _sz
+    lib.lmpcr_nn_workspace_bytes.argtypes = [_i] * 7
+    lib.lmpcr_nn_argmin.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]
+    lib.lmpcr_pairwise_distance.argtypes = [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]
+    lib.lmpcr_gather_xyz.argtypes = [_vp, _i, _vp, _i, _vp, _i, _vp, _vp]
+    lib.lmpcr_mutual_xs.argtypes = [_vp, _i, _vp, _i, _vp, _vp, _i, _f, _vp, _vp, _i, _vp]
+    lib.lmpcr_knn3d_1.argtypes = [_vp, _i, _vp, _i, _i, _vp, _vp, _vp]
+    lib.lmpcr_kabsch.argtypes = [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.lmpcr_residuals.argtypes = [_vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]
+    lib.lmpcr_filter_num_params.argtypes = [ctypes.POINTER(FilterCfg)]
+    lib.lmpcr_filter_workspace_bytes.restype = _sz
+    lib.lmpcr_filter_workspace_bytes.argtypes = [ctypes.POINTER(FilterCfg), _i, _i]
+    lib.lmpcr_filter_forward.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), _i, ctypes.POINTER(FilterCfg),
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
+    lib.lmpcr_pack_pose_records.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _vp]
+    if lib.lmpcr_abi_version() != 1:
+        raise LmpcrError("liblmpcr_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise LmpcrError("lmpcr error %d: %s" % (rc, load().lmpcr_last_error().decode()))
+
+
+def _dev(t, dtype=torch.float32, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise LmpcrError("%s must be a CUDA tensor (the B200 path has no CPU fallback)" % name)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def device_info():
+    v = [ctypes.c_int(0) for _ in range(4)]
+    _check(load().lmpcr_device_info(*[ctypes.byref(x) for x in v]))
+    return {"sm_count": v[0].value, "l2_bytes": v[1].value, "cc": (v[2].value, v[3].value)}
+
+
+# ---------------------------------------------------------------------------------------------- stage 1
+def nn_argmin(q_feat, b_feat, jobs, algo=NN_EXACT_SIMT, return_dist=False):
+    """q_feat [Sq,n,D], b_feat [Sb,m,D] fp32 CUDA; jobs [J,2] int32 (query set, target set) -> idx [J,n] int32."""
+    lib = load()
+    q = _dev(q_feat, name="q_feat")
+    b = q if b_feat is q_feat else _dev(b_feat, name="b_feat")
+    jobs = _dev(jobs, torch.int32, "jobs")
+    assert q.dim() == 3 and b.dim() == 3 and q.shape[2] == b.shape[2] and jobs.dim() == 2 and jobs.shape[1] == 2
+    J, n = jobs.shape[0], q.shape[1]
+    with torch.cuda.device(q.device):
+        idx = torch.empty((J, n), dtype=torch.int32, device=q.device)
+        dist = torch.empty((J, n), dtype=torch.float32, device=q.device) if return_dist else None
+        nbytes = lib.lmpcr_nn_workspace_bytes(q.shape[0], n, b.shape[0], b.shape[1], q.shape[2], J, algo)
+        ws = _ws(nbytes, q.device)
+        _check(lib.lmpcr_nn_argmin(_p(q), q.shape[0], n, _p(b), b.shape[0], b.shape[1], q.shape[2], _p(jobs), J, _p(idx), _p(dist),
+                                   algo, _p(ws), ws.numel(), _stream(q)))
+    return (idx, dist) if return_dist else idx
+
+
+def pairwise_distance(src, dst):
+    lib = load()
+    s, d = _dev(src, name="src"), _dev(dst, name="dst")
+    B, n, dim = s.shape
+    m = d.shape[1]
+    with torch.cuda.device(s.device):
+        out = torch.empty((B, n, m), dtype=torch.float32, device=s.device)
+        ws = _ws(4 * (B * n + B * m) + 1024, s.device)
+        _check(lib.lmpcr_pairwise_distance(_p(s), n, _p(d), m, dim, B, _p(out), _p(ws), ws.numel(), _stream(s)))
+    return out
+
+
+def gather_xyz(b_xyz, jobs, idx):
+    lib = load()
+    x = _dev(b_xyz, name="b_xyz")
+    jobs = _dev(jobs, torch.int32, "jobs")
+    idx = _dev(idx, torch.int32, "idx")
+    with torch.cuda.device(x.device):
+        out = torch.empty((idx.shape[0], idx.shape[1], 3), dtype=torch.float32, device=x.device)
+        _check(lib.lmpcr_gather_xyz(_p(x), x.shape[1], _p(jobs), jobs.shape[0], _p(idx), idx.shape[1], _p(out), _stream(x)))
+    return out
+
+
+def mutual_xs(xyz, pairs, idx_st, idx_ts, mutual_mode=MUTUAL_INDEX, mutual_thresh=0.05, xs_channels=6, want_mutual=True):
+    """xyz [S,n,3]; pairs [P,2]; idx_st/idx_ts [P,n] -> (mutual uint8 [P,n] | None, xs [P,1,n,C])."""
+    lib = load()
+    x = _dev(xyz, name="xyz")
+    pairs = _dev(pairs, torch.int32, "pairs")
+    idx_st = _dev(idx_st, torch.int32, "idx_st")
+    idx_ts = _dev(idx_ts, torch.int32, "idx_ts") if idx_ts is not None else None
+    P, n = idx_st.shape
+    with torch.cuda.device(x.device):
+        mutual = torch.empty((P, n), dtype=torch.uint8, device=x.device) if want_mutual else None
+        xs = torch.empty((P, 1, n, xs_channels), dtype=torch.float32, device=x.device)
+        _check(lib.lmpcr_mutual_xs(_p(x), n, _p(pairs), P, _p(idx_st), _p(idx_ts), mutual_mode, float(mutual_thresh), _p(mutual), _p(xs),
+                                   xs_channels, _stream(x)))
+    return mutual, xs
+
+
+def knn3d_1(pos1, pos2):
+    lib = load()
+    a, b = _dev(pos1, name="pos1"), _dev(pos2, name="pos2")
+    B, n, _ = a.shape
+    m = b.shape[1]
+    with torch.cuda.device(a.device):
+        idx = torch.empty((B, m), dtype=torch.int32, device=a.device)
+        sq = torch.empty((B, m), dtype=torch.float32, device=a.device)
+        _check(lib.lmpcr_knn3d_1(_p(a), n, _p(b), m, B, _p(idx), _p(sq), _stream(a)))
+    return sq, idx
+
+
+# ---------------------------------------------------------------------------------------------- stage 3
+def kabsch_xs(xs, w, guard_mode=GUARD_PAIR, want_conf=False):
+    """xs [P,1,N,C>=6] or [P,N,C]; w [P,N] -> R [P,3,3], t [P,3,1], res [P,N], status [P] (, conf [P,4])."""
+    lib = load()
+    x = _dev(xs, name="xs")
+    w = _dev(w, name="weights")
+    C = x.shape[-1]
+    P, N = w.shape
+    assert x.numel() == P * N * C and C >= 6
+    with torch.cuda.device(x.device):
+        R = torch.empty((P, 3, 3), dtype=torch.float32, device=x.device)
+        t = torch.empty((P, 3, 1), dtype=torch.float32, device=x.device)
+        res = torch.empty((P, N), dtype=torch.float32, device=x.device)
+        conf = torch.empty((P, 4), dtype=torch.float32, device=x.device) if want_conf else None
+        status = torch.zeros((P,), dtype=torch.int32, device=x.device)
+        wout = torch.empty_like(w)
+        wout.copy_(w)
+        _check(lib.lmpcr_kabsch(_p(x), ctypes.c_void_p(x.data_ptr() + 12), C, _p(w), P, N, guard_mode, None, _p(wout), _p(R), _p(t),
+                                _p(res), _p(conf), _p(status), _stream(x)))
+    return (R, t, res, status, conf) if want_conf else (R, t, res, status)
+
+
+def kabsch_points(x1, x2, w):
+    """x1, x2 [P,N,3]; w [P,N].  No zero-weight guard (as lib/utils.py:164 itself has none)."""
+    lib = load()
+    a, b, w = _dev(x1, name="x1"), _dev(x2, name="x2"), _dev(w, name="weights")
+    P, N = w.shape
+    with torch.cuda.device(a.device):
+        R = torch.empty((P, 3, 3), dtype=torch.float32, device=a.device)
+        t = torch.empty((P, 3, 1), dtype=torch.float32, device=a.device)
+        res = torch.empty((P, N), dtype=torch.float32, device=a.device)
+        status = torch.zeros((P,), dtype=torch.int32, device=a.device)
+        _check(lib.lmpcr_kabsch(_p(a), _p(b), 3, _p(w), P, N, GUARD_BATCH, None, None, _p(R), _p(t), _p(res), None, _p(status), _stream(a)))
+    return R, t, res, status
+
+
+def residuals(x1, x2, R, t):
+    lib = load()
+    a, b = _dev(x1, name="x1"), _dev(x2, name="x2")
+    R, t = _dev(R, name="R"), _dev(t, name="t")
+    P, N, _ = a.shape
+    with torch.cuda.device(a.device):
+        res = torch.empty((P, N), dtype=torch.float32, device=a.device)
+        _check(lib.lmpcr_residuals(_p(a), _p(b), 3, _p(R), _p(t), P, N, _p(res), _stream(a)))
+    return res
+
+
+# ---------------------------------------------------------------------------------------------- stage 2
+def filter_forward(xs, params, cfg, want_latent=True, want_conf=True, workspace=None):
+    """xs [P,1,N,6+side] CUDA fp32; params: list of CUDA fp32 tensors in state_dict order (no num_batches_tracked);
+    cfg: FilterCfg.  Returns dict(logits [I,P,N], scores [I,P,N], R [I,P,3,3], t [I,P,3,1], residuals [P,N],
+    latent [P,C,N] | None, conf [P,4] | None, status [P])."""
+    lib = load()
+    x = _dev(xs, name="xs")
+    assert x.dim() == 4 and x.shape[1] == 1 and x.shape[3] == 6 + cfg.side_channel
+    P, N = x.shape[0], x.shape[2]
+    n_par = lib.lmpcr_filter_num_params(ctypes.byref(cfg))
+    if len(params) != n_par:
+        raise LmpcrError("expected %d parameter tensors, got %d" % (n_par, len(params)))
+    keep = [_dev(p, name="parameter") for p in params]
+    table = (ctypes.c_void_p * n_par)(*[p.data_ptr() for p in keep])
+    I = cfg.iter_num + 1
+    dev = x.device
+    with torch.cuda.device(dev):
+        out = {
+            "logits": torch.empty((I, P, N), dtype=torch.float32, device=dev),
+            "scores": torch.empty((I, P, N), dtype=torch.float32, device=dev),
+            "R": torch.empty((I, P, 3, 3), dtype=torch.float32, device=dev),
+            "t": torch.empty((I, P, 3, 1), dtype=torch.float32, device=dev),
+            "residuals": torch.empty((P, N), dtype=torch.float32, device=dev),
+            "latent": torch.empty((P, cfg.net_channel, N), dtype=torch.float32, device=dev) if want_latent else None,
+            "conf": torch.empty((P, 4), dtype=torch.float32, device=dev) if want_conf else None,
+            "status": torch.empty((P,), dtype=torch.int32, device=dev),
+        }
+        if P == 0:
+            return out
+        if workspace is None:
+            workspace = _ws(lib.lmpcr_filter_workspace_bytes(ctypes.byref(cfg), P, N), dev)
+        _check(lib.lmpcr_filter_forward(_p(x), P, N, table, n_par, ctypes.byref(cfg), _p(out["logits"]), _p(out["scores"]), _p(out["R"]),
+                                        _p(out["t"]), _p(out["residuals"]), _p(out["latent"]), _p(out["conf"]), _p(out["status"]),
+                                        _p(workspace), workspace.numel(), _stream(x)))
+    return out
+
+
+def filter_workspace_bytes(cfg, P, N):
+    return int(load().lmpcr_filter_workspace_bytes(ctypes.byref(cfg), P, N))
+
+
+def pack_pose_records(R, t, conf, status):
+    lib = load()
+    R, t = _dev(R, name="R"), _dev(t, name="t")
+    P = R.shape[0]
+    with torch.cuda.device(R.device):
+        rec = torch.empty((P, 16), dtype=torch.float32, device=R.device)
+        _check(lib.lmpcr_pack_pose_records(_p(R), _p(t), _p(conf), _p(status), P, _p(rec), _stream(R)))
+    return rec

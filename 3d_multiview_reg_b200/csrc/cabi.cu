@@ -1,0 +1,158 @@
+// extern "C" surface of liblmpcr_b200.so (declared in include/lmpcr_b200.h).  Plain pointers and sizes only.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace lmpcr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return LMPCR_ERR_LAUNCH;
+  }
+  return LMPCR_OK;
+}
+
+static int g_cc_major[64], g_sms[64];
+static bool g_seen[64];
+
+int check_device() {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); this library has no CPU fallback", e == cudaSuccess ? "bad ordinal" : cudaGetErrorString(e));
+    return LMPCR_ERR_DEVICE;
+  }
+  if (!g_seen[dev]) {
+    int maj = 0, sms = 0;
+    cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    g_cc_major[dev] = maj;
+    g_sms[dev] = sms;
+    g_seen[dev] = true;
+  }
+  if (g_cc_major[dev] != 10) {
+    set_error("device %d has compute capability %d.x; liblmpcr_b200 is built for sm_100a (B200) only", dev, g_cc_major[dev]);
+    return LMPCR_ERR_DEVICE;
+  }
+  return LMPCR_OK;
+}
+
+int sm_count() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 64 && g_seen[dev]) ? g_sms[dev] : 148;
+}
+
+}  // namespace lmpcr
+
+using namespace lmpcr;
+
+extern "C" {
+
+int lmpcr_abi_version(void) { return LMPCR_ABI_VERSION; }
+const char* lmpcr_last_error(void) { return g_err; }
+
+int lmpcr_device_info(int* sms, int* l2_bytes, int* cc_major, int* cc_minor) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("no CUDA device available");
+    return LMPCR_ERR_DEVICE;
+  }
+  int v = 0;
+  if (sms) { cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); *sms = v; }
+  if (l2_bytes) { cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev); *l2_bytes = v; }
+  if (cc_major) { cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev); *cc_major = v; }
+  if (cc_minor) { cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev); *cc_minor = v; }
+  return LMPCR_OK;
+}
+
+size_t lmpcr_nn_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, int dim, int n_jobs, int algo) {
+  return nn_workspace_bytes(n_q_sets, n_q, n_b_sets, n_b, dim, n_jobs, algo);
+}
+
+int lmpcr_nn_argmin(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
+                    const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, int algo, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_nn_argmin(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, dim, jobs, n_jobs, idx_out, dist_out, algo, workspace,
+                          workspace_bytes, (cudaStream_t)stream);
+}
+
+int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, int dim, int batch, float* out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_pairwise_distance(src, n, dst, m, dim, batch, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int lmpcr_gather_xyz(const float* b_xyz, int n_b, const int32_t* jobs, int n_jobs, const int32_t* idx, int n_q, float* out,
+                     void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_gather_xyz(b_xyz, n_b, jobs, n_jobs, idx, n_q, out, (cudaStream_t)stream);
+}
+
+int lmpcr_mutual_xs(const float* xyz, int n_pts, const int32_t* pairs, int n_pairs, const int32_t* idx_st,
+                    const int32_t* idx_ts, int mutual_mode, float mutual_thresh, uint8_t* mutual, float* xs, int xs_channels,
+                    void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_mutual_xs(xyz, n_pts, pairs, n_pairs, idx_st, idx_ts, mutual_mode, mutual_thresh, mutual, xs, xs_channels,
+                          (cudaStream_t)stream);
+}
+
+int lmpcr_knn3d_1(const float* pos1, int n, const float* pos2, int m, int batch, int32_t* idx_out, float* sqdist_out,
+                  void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_knn3d(pos1, n, pos2, m, batch, idx_out, sqdist_out, (cudaStream_t)stream);
+}
+
+int lmpcr_kabsch(const float* x1, const float* x2, int ld, const float* w, int n_pairs, int n_pts, int guard_mode,
+                 const int32_t* guard_flag, float* w_out, float* R, float* t, float* res, float* conf, uint32_t* status,
+                 void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_kabsch(x1, x2, ld, w, n_pairs, n_pts, guard_mode, guard_flag, w_out, R, t, res, conf, status, (cudaStream_t)stream);
+}
+
+int lmpcr_residuals(const float* x1, const float* x2, int ld, const float* R, const float* t, int n_pairs, int n_pts,
+                    float* res, void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_residuals(x1, x2, ld, R, t, n_pairs, n_pts, res, (cudaStream_t)stream);
+}
+
+int lmpcr_filter_num_params(const lmpcr_filter_cfg* cfg) {
+  if (!cfg) return LMPCR_ERR_ARG;
+  return filter_num_params(cfg);
+}
+
+size_t lmpcr_filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int n_pairs, int n_pts) {
+  return filter_workspace_bytes(cfg, n_pairs, n_pts);
+}
+
+int lmpcr_filter_forward(const float* xs, int n_pairs, int n_pts, const float* const* params, int n_params,
+                         const lmpcr_filter_cfg* cfg, float* logits, float* scores, float* R, float* t, float* residuals,
+                         float* latent, float* conf, uint32_t* status, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_filter_forward(xs, n_pairs, n_pts, params, n_params, cfg, logits, scores, R, t, residuals, latent, conf, status,
+                               workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int lmpcr_pack_pose_records(const float* R, const float* t, const float* conf, const uint32_t* status, int n_pairs, float* rec,
+                            void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_pack_records(R, t, conf, status, n_pairs, rec, (cudaStream_t)stream);
+}
+
+}  // extern "C"

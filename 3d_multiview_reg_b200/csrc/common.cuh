@@ -1,0 +1,85 @@
+// Shared helpers for the lmpcr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/lmpcr_b200.h"
+
+namespace lmpcr {
+
+// thread-local error string behind lmpcr_last_error()
+void set_error(const char* fmt, ...);
+int check_device();          // LMPCR_OK iff the current device is sm_100 (B200)
+int check_launch(const char* what);
+int sm_count();
+
+#define LMPCR_REQUIRE(cond, code, ...)   \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::lmpcr::set_error(__VA_ARGS__);   \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define LMPCR_TRY(expr)          \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != LMPCR_OK) return _rc; \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- internal launchers (one per .cu file) ----
+// kabsch.cu
+int launch_kabsch(const float* x1, const float* x2, int ld, const float* w, int P, int N, int guard_mode,
+                  const int32_t* guard_flag, float* w_out, float* R, float* t, float* res, float* conf,
+                  uint32_t* status, cudaStream_t st);
+int launch_residuals(const float* x1, const float* x2, int ld, const float* R, const float* t, int P, int N, float* res,
+                     cudaStream_t st);
+int launch_pack_records(const float* R, const float* t, const float* conf, const uint32_t* status, int P, float* rec,
+                        cudaStream_t st);
+
+// nn_search.cu
+size_t nn_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, int dim, int n_jobs, int algo);
+int launch_nn_argmin(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
+                     const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, int algo, void* ws,
+                     size_t ws_bytes, cudaStream_t st);
+int launch_pairwise_distance(const float* src, int n, const float* dst, int m, int dim, int batch, float* out, void* ws,
+                             size_t ws_bytes, cudaStream_t st);
+int launch_gather_xyz(const float* b_xyz, int n_b, const int32_t* jobs, int n_jobs, const int32_t* idx, int n_q,
+                      float* out, cudaStream_t st);
+int launch_mutual_xs(const float* xyz, int n_pts, const int32_t* pairs, int n_pairs, const int32_t* idx_st,
+                     const int32_t* idx_ts, int mode, float thresh, uint8_t* mutual, float* xs, int xs_channels,
+                     cudaStream_t st);
+int launch_knn3d(const float* pos1, int n, const float* pos2, int m, int batch, int32_t* idx, float* sq, cudaStream_t st);
+// nn_tensor.cu (tcgen05 path)
+size_t nn_tensor_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, int dim, int n_jobs);
+int launch_nn_tensor(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
+                     const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+
+// filter_net.cu
+int filter_num_params(const lmpcr_filter_cfg* cfg);
+size_t filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int P, int N);
+int launch_filter_forward(const float* xs, int P, int N, const float* const* params, int n_params,
+                          const lmpcr_filter_cfg* cfg, float* logits, float* scores, float* R, float* t, float* residuals,
+                          float* latent, float* conf, uint32_t* status, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace lmpcr

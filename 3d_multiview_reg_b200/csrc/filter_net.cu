@@ -1,0 +1,560 @@
+// Stage 2: correspondence-weighting network (OANet extension, eval mode) -- fp32 CUDA-core path.
+//
+// Replaces lib/filtering/oanet.py:18-265.  Every 1x1 convolution, the cluster-mixing convolution of OAFilter,
+// diff_pool and diff_unpool are instances of ONE batched strided GEMM
+//        C[p,i,j] = sum_k A[p,i,k] * f(B[p,k,j]) + bias[i] + Res[p,i,j]
+// whose B-operand prologue f(x) = relu(x * scale[p,k] + shift[p,k]) applies InstanceNorm (context
+// normalisation) + eval-mode BatchNorm + ReLU while the tile is staged into shared memory, so normalised
+// activations are never written back to HBM.  scale/shift come from in_affine_kernel (one warp per
+// (pair, channel) row: two-pass mean / biased variance with shuffle reductions, folded with the BN constants).
+// Activations keep the reference layout [P, C, N] (point axis contiguous); nothing is transposed in memory --
+// OAFilter's trans(1,2) (oanet.py:46-53) is expressed through the GEMM strides.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace lmpcr {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// batched strided SGEMM with fused prologue / epilogue
+// ------------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 128, BK = 8, GT = 256;
+
+struct GemmArgs {
+  const float* A; long long a_batch; int a_i;          // A[p,i,k] at A + p*a_batch + i*a_i + k   (k contiguous)
+  const float* B; long long b_batch; int b_k, b_j;     // B[p,k,j]
+  float* C; long long c_batch; int c_i, c_j;           // C[p,i,j]
+  const float* Res; long long r_batch;                 // same i/j strides as C (optional)
+  const float* bias;                                   // [M] (optional)
+  const float* scale; const float* shift; int aff_batch;  // prologue affine, index p*aff_batch + k (optional)
+  int M, N, K;
+};
+
+__global__ void __launch_bounds__(GT)
+gemm_fused_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int p = blockIdx.z;
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float* A = g.A + (long long)p * g.a_batch;
+  const float* B = g.B + (long long)p * g.b_batch;
+  const bool has_aff = g.scale != nullptr;
+  const float* sc = has_aff ? g.scale + (long long)p * g.aff_batch : nullptr;
+  const float* sh = has_aff ? g.shift + (long long)p * g.aff_batch : nullptr;
+  const bool b_vec = (g.b_j == 1) && ((g.b_k & 3) == 0) && ((g.b_batch & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
+
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+  // per-thread staging registers
+  float a_reg[4], b_reg[4];
+  const int a_i = tid >> 1, a_k = (tid & 1) * 4;     // A tile: 128 rows x 8 k -> 4 consecutive k per thread
+  const int bv_k = tid >> 5, bv_j = (tid & 31) * 4;  // B tile (j contiguous): 8 k x 128 j -> one float4 per thread
+  const int bs_j = tid & 127, bs_k = (tid >> 7) * 4; // B tile (generic / k contiguous): 4 consecutive k per thread
+
+  auto load_tiles = [&](int k0) {
+    {
+      const int gi = i0 + a_i;
+      const float* src = A + (long long)gi * g.a_i + k0 + a_k;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a_reg[c] = (gi < g.M && k0 + a_k + c < g.K) ? __ldg(src + c) : 0.f;
+    }
+    if (b_vec) {
+      const int gk = k0 + bv_k, gj = j0 + bv_j;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gk < g.K) {
+        const float* src = B + (long long)gk * g.b_k + gj;
+        if (gj + 3 < g.N) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (gj < g.N) v.x = __ldg(src);
+          if (gj + 1 < g.N) v.y = __ldg(src + 1);
+          if (gj + 2 < g.N) v.z = __ldg(src + 2);
+        }
+        if (has_aff) {
+          const float s = __ldg(sc + gk), t = __ldg(sh + gk);
+          v.x = fmaxf(fmaf(v.x, s, t), 0.f); v.y = fmaxf(fmaf(v.y, s, t), 0.f);
+          v.z = fmaxf(fmaf(v.z, s, t), 0.f); v.w = fmaxf(fmaf(v.w, s, t), 0.f);
+        }
+      }
+      b_reg[0] = v.x; b_reg[1] = v.y; b_reg[2] = v.z; b_reg[3] = v.w;
+    } else {
+      const int gj = j0 + bs_j;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int gk = k0 + bs_k + c;
+        float v = 0.f;
+        if (gk < g.K && gj < g.N) {
+          v = __ldg(B + (long long)gk * g.b_k + (long long)gj * g.b_j);
+          if (has_aff) v = fmaxf(fmaf(v, __ldg(sc + gk), __ldg(sh + gk)), 0.f);
+        }
+        b_reg[c] = v;
+      }
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) As[buf][a_k + c][a_i] = a_reg[c];
+    if (b_vec) {
+      *reinterpret_cast<float4*>(&Bs[buf][bv_k][bv_j]) = make_float4(b_reg[0], b_reg[1], b_reg[2], b_reg[3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Bs[buf][bs_k + c][bs_j] = b_reg[c];
+    }
+  };
+
+  const int nk = (g.K + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue: bias + residual, strided store
+  float* C = g.C + (long long)p * g.c_batch;
+  const float* R = g.Res ? g.Res + (long long)p * g.r_batch : nullptr;
+  const bool c_vec = (g.c_j == 1) && ((g.c_i & 3) == 0) && ((g.c_batch & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                     (!R || (((g.r_batch & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Res) & 15) == 0)));
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int gi = i0 + (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
+    if (gi >= g.M) continue;
+    const float bi = g.bias ? __ldg(g.bias + gi) : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int gj = j0 + h * 64 + tx * 4;
+      if (c_vec && gj + 3 < g.N) {
+        float4 v = make_float4(acc[r][4 * h] + bi, acc[r][4 * h + 1] + bi, acc[r][4 * h + 2] + bi, acc[r][4 * h + 3] + bi);
+        const long long off = (long long)gi * g.c_i + gj;
+        if (R) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(R + off));
+          v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        }
+        *reinterpret_cast<float4*>(C + off) = v;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (gj + c < g.N) {
+            const long long off = (long long)gi * g.c_i + (long long)(gj + c) * g.c_j;
+            float v = acc[r][4 * h + c] + bi;
+            if (R) v += __ldg(R + off);
+            C[off] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+int gemm(const GemmArgs& g, int batch, cudaStream_t st) {
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batch);
+  gemm_fused_kernel<<<grid, GT, 0, st>>>(g);
+  return check_launch("gemm_fused_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// InstanceNorm (+ eval BatchNorm) statistics -> per-(pair, channel) affine for the GEMM prologue
+//   y = relu( ((x - mean) / sqrt(var + eps_in) - rm) * gamma / sqrt(rv + 1e-5) + beta ) = relu(x*scale + shift)
+// One warp per (pair, channel) row; two-pass mean / biased variance (oanet.py:27-28 etc.).
+// use_in == 0: BatchNorm only (OAFilter.conv2, oanet.py:73), per-channel constants, batch-independent.
+// ------------------------------------------------------------------------------------------------
+__global__ void in_affine_kernel(const float* __restrict__ x, long long x_batch, int C, int L, int use_in, float eps_in,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                 float* __restrict__ scale, float* __restrict__ shift, int n_rows) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int p = row / C, c = row - p * C;
+  const float gsc = __ldg(gamma + c) / sqrtf(__ldg(rvar + c) + 1e-5f);
+  float mean = 0.f, rstd = 1.f;
+  if (use_in) {
+    const float* r = x + (long long)p * x_batch + (long long)c * L;
+    float s = 0.f;
+    for (int i = lane; i < L; i += 32) s += __ldg(r + i);
+    mean = warp_sum(s) / (float)L;
+    float v = 0.f;
+    for (int i = lane; i < L; i += 32) {
+      const float d = __ldg(r + i) - mean;
+      v = fmaf(d, d, v);
+    }
+    rstd = 1.0f / sqrtf(warp_sum(v) / (float)L + eps_in);
+  }
+  if (lane == 0) {
+    scale[row] = rstd * gsc;
+    shift[row] = (-mean * rstd - __ldg(rmean + c)) * gsc + __ldg(beta + c);
+  }
+}
+
+// xs [P,1,N,Cx] (+ residuals, scores of the previous block) -> in0 [P, Cin, N]   (oanet.py:233, 245-248)
+__global__ void pack_input_kernel(const float* __restrict__ xs, int Cx, const float* __restrict__ res,
+                                  const float* __restrict__ scores, int P, int N, float* __restrict__ out, int Cin) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)P * N) return;
+  const int p = (int)(gid / N), n = (int)(gid - (size_t)p * N);
+  const float* src = xs + gid * Cx;
+  float* o = out + (size_t)p * Cin * N + n;
+  for (int c = 0; c < Cx; ++c) o[(size_t)c * N] = __ldg(src + c);
+  if (res) {
+    o[(size_t)Cx * N] = __ldg(res + gid);
+    o[(size_t)(Cx + 1) * N] = __ldg(scores + gid);
+  }
+}
+
+// softmax over the point axis of every row of embed [rows, L], in place (diff_pool, oanet.py:108)
+__global__ void softmax_rows_kernel(float* __restrict__ e, int L, int n_rows) {
+  const int row = blockIdx.x;
+  if (row >= n_rows) return;
+  float* r = e + (size_t)row * L;
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, r[i]);
+  m = warp_max(m);
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < nw; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const float v = expf(r[i] - m);
+    r[i] = v;
+    s += v;
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < nw; ++w) s += red[w];
+  const float inv = 1.0f / s;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) r[i] *= inv;
+}
+
+// softmax over the cluster axis of embed [P, K, N] for every (pair, point), in place (diff_unpool, oanet.py:127)
+__global__ void softmax_cols_kernel(float* __restrict__ e, int K, int N, int P) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)P * N) return;
+  const int p = (int)(gid / N), n = (int)(gid - (size_t)p * N);
+  float* col = e + (size_t)p * K * N + n;
+  float m = -INFINITY;
+  for (int k = 0; k < K; ++k) m = fmaxf(m, col[(size_t)k * N]);
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float v = expf(col[(size_t)k * N] - m);
+    col[(size_t)k * N] = v;
+    s += v;
+  }
+  const float inv = 1.0f / s;
+  for (int k = 0; k < K; ++k) col[(size_t)k * N] *= inv;
+}
+
+// output conv (C -> 1) + tanh/relu weights (oanet.py:174-175) + "any positive weight" flag per pair
+__global__ void logits_kernel(const float* __restrict__ x, long long x_batch, int C, int N, int P,
+                              const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ logits,
+                              float* __restrict__ scores, int32_t* __restrict__ anypos) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)P * N) return;
+  const int p = (int)(gid / N), n = (int)(gid - (size_t)p * N);
+  const float* col = x + (long long)p * x_batch + n;
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) acc = fmaf(__ldg(w + c), __ldg(col + (size_t)c * N), acc);
+  acc += __ldg(b);
+  logits[gid] = acc;
+  const float s = fmaxf(tanhf(acc), 0.f);
+  scores[gid] = s;
+  if (s > 0.f) anypos[p] = 1;
+}
+
+__global__ void guard_flag_kernel(const int32_t* __restrict__ anypos, int P, int32_t* __restrict__ flag) {
+  // flag = any pair whose weights are all zero (oanet.py:177)
+  int f = 0;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) f |= (anypos[p] == 0);
+  f = __syncthreads_or(f);
+  if (threadIdx.x == 0) *flag = f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameter table (state_dict order)
+// ------------------------------------------------------------------------------------------------
+struct ConvP { const float* w; const float* b; };
+struct BNP { const float* g; const float* b; const float* rm; const float* rv; };
+struct PointCNP { bool has_sc; ConvP sc; BNP bn1; ConvP c1; BNP bn2; ConvP c2; };
+struct OAFilterP { BNP bn1; ConvP c1; BNP bn2; ConvP c2; BNP bn3; ConvP c3; };
+constexpr int MAX_HALF = 8;
+struct BlockP {
+  ConvP conv1; BNP down_bn; ConvP down_conv; BNP up_bn; ConvP up_conv;
+  PointCNP l1_1[MAX_HALF], l1_2[MAX_HALF]; OAFilterP l2[MAX_HALF]; ConvP output;
+};
+
+struct Cursor {
+  const float* const* p; int i, n;
+  const float* next() { return (i < n) ? p[i++] : (i++, nullptr); }
+  ConvP conv() { ConvP c; c.w = next(); c.b = next(); return c; }
+  BNP bn() { BNP b; b.g = next(); b.b = next(); b.rm = next(); b.rv = next(); return b; }
+  PointCNP pointcn(bool sc) { PointCNP q; q.has_sc = sc; if (sc) q.sc = conv(); else q.sc = ConvP{nullptr, nullptr}; q.bn1 = bn(); q.c1 = conv(); q.bn2 = bn(); q.c2 = conv(); return q; }
+};
+
+void parse_block(Cursor& cur, int half, BlockP& b) {
+  b.conv1 = cur.conv();
+  b.down_bn = cur.bn(); b.down_conv = cur.conv();
+  b.up_bn = cur.bn(); b.up_conv = cur.conv();
+  for (int i = 0; i < half; ++i) b.l1_1[i] = cur.pointcn(false);
+  b.l1_2[0] = cur.pointcn(true);
+  for (int i = 1; i < half; ++i) b.l1_2[i] = cur.pointcn(false);
+  for (int i = 0; i < half; ++i) {
+    OAFilterP& f = b.l2[i];
+    f.bn1 = cur.bn(); f.c1 = cur.conv(); f.bn2 = cur.bn(); f.c2 = cur.conv(); f.bn3 = cur.bn(); f.c3 = cur.conv();
+  }
+  b.output = cur.conv();
+}
+
+int block_num_params(int half) {
+  // conv1 2 + down 6 + up 6 + l1_1 half*12 + l1_2 (14 + (half-1)*12) + l2 half*18 + output 2
+  return 2 + 6 + 6 + half * 12 + 14 + (half - 1) * 12 + half * 18 + 2;
+}
+
+struct Work {   // per-group scratch, all fp32
+  float *in0, *T0, *T1, *T2, *CAT, *E, *XD0, *XD1, *Y, *Z, *scale, *shift;
+};
+
+size_t per_pair_floats(int C, int K, int N) {
+  return (size_t)12 * N + (size_t)3 * C * N + (size_t)2 * C * N + (size_t)K * N + (size_t)4 * C * K + 2 * 1024;
+}
+
+}  // namespace
+
+int filter_num_params(const lmpcr_filter_cfg* cfg) {
+  const int half = (cfg->net_depth / (cfg->iter_num + 1)) / 2;
+  return block_num_params(half) * (cfg->iter_num + 1);
+}
+
+static int validate_cfg(const lmpcr_filter_cfg* cfg) {
+  LMPCR_REQUIRE(cfg, LMPCR_ERR_ARG, "lmpcr_filter: null cfg");
+  LMPCR_REQUIRE(cfg->iter_num >= 0 && cfg->iter_num <= 7, LMPCR_ERR_ARG, "lmpcr_filter: iter_num=%d", cfg->iter_num);
+  const int depth = cfg->net_depth / (cfg->iter_num + 1);
+  LMPCR_REQUIRE(depth >= 2 && depth / 2 <= MAX_HALF, LMPCR_ERR_ARG, "lmpcr_filter: net_depth=%d unsupported", cfg->net_depth);
+  LMPCR_REQUIRE(cfg->net_channel >= 4 && cfg->net_channel % 4 == 0 && cfg->net_channel <= 512, LMPCR_ERR_ARG, "lmpcr_filter: net_channel=%d (multiple of 4, <= 512)", cfg->net_channel);
+  LMPCR_REQUIRE(cfg->clusters >= 4 && cfg->clusters % 4 == 0 && cfg->clusters <= 1024, LMPCR_ERR_ARG, "lmpcr_filter: clusters=%d (multiple of 4, <= 1024)", cfg->clusters);
+  LMPCR_REQUIRE(cfg->side_channel == 0 || cfg->side_channel == 1, LMPCR_ERR_ARG, "lmpcr_filter: side_channel");
+  LMPCR_REQUIRE(cfg->guard_mode == LMPCR_GUARD_BATCH || cfg->guard_mode == LMPCR_GUARD_PAIR, LMPCR_ERR_ARG, "lmpcr_filter: guard_mode");
+  return LMPCR_OK;
+}
+
+// fixed part: residuals [P,N] (when the caller passes none) + anypos [P] + flag
+static size_t fixed_bytes(int P, int N) { return align_up((size_t)P * N * 4, 256) + align_up((size_t)P * 4, 256) + 256; }
+
+size_t filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int P, int N) {
+  if (validate_cfg(cfg) != LMPCR_OK || P <= 0 || N <= 0) return 0;
+  const size_t pp = per_pair_floats(cfg->net_channel, cfg->clusters, N) * 4;
+  size_t G = (size_t(1) << 30) / pp;   // ~1 GiB of activations per group of pairs
+  if (G < 1) G = 1;
+  if (G > (size_t)P) G = P;
+  return fixed_bytes(P, N) + align_up(G * pp, 256) + 4096;
+}
+
+int launch_filter_forward(const float* xs, int P, int N, const float* const* params, int n_params,
+                          const lmpcr_filter_cfg* cfg, float* logits, float* scores, float* Rout, float* tout,
+                          float* residuals, float* latent, float* conf, uint32_t* status, void* ws, size_t ws_bytes,
+                          cudaStream_t st) {
+  LMPCR_TRY(validate_cfg(cfg));
+  LMPCR_REQUIRE(xs && params && logits && scores && Rout && tout, LMPCR_ERR_ARG, "lmpcr_filter_forward: null pointer");
+  LMPCR_REQUIRE(P >= 0 && N >= 1, LMPCR_ERR_ARG, "lmpcr_filter_forward: bad sizes");
+  LMPCR_REQUIRE(cfg->gemm_algo == 0, LMPCR_ERR_UNSUPPORTED, "lmpcr_filter_forward: gemm_algo=%d not built", cfg->gemm_algo);
+  LMPCR_REQUIRE(n_params == filter_num_params(cfg), LMPCR_ERR_ARG, "lmpcr_filter_forward: expected %d parameter tensors, got %d", filter_num_params(cfg), n_params);
+  for (int i = 0; i < n_params; ++i) LMPCR_REQUIRE(params[i], LMPCR_ERR_ARG, "lmpcr_filter_forward: params[%d] is null", i);
+  if (P == 0) return LMPCR_OK;
+  const int C = cfg->net_channel, K = cfg->clusters, iters = cfg->iter_num + 1;
+  const int half = (cfg->net_depth / iters) / 2;
+  const int Cx = 6 + cfg->side_channel;
+  const size_t pp = per_pair_floats(C, K, N) * 4;
+  const size_t fixed = fixed_bytes(P, N);
+  LMPCR_REQUIRE(ws && ws_bytes >= fixed + pp + 4096, LMPCR_ERR_WORKSPACE, "lmpcr_filter_forward: workspace %zu < %zu bytes", ws_bytes, fixed + pp + 4096);
+  LMPCR_REQUIRE(((uintptr_t)ws & 255) == 0, LMPCR_ERR_ARG, "lmpcr_filter_forward: workspace must be 256-byte aligned");
+  int G = (int)((ws_bytes - fixed - 4096) / pp);
+  if (G > P) G = P;
+
+  char* base = reinterpret_cast<char*>(ws);
+  float* res_buf = residuals ? residuals : reinterpret_cast<float*>(base);
+  int32_t* anypos = reinterpret_cast<int32_t*>(base + align_up((size_t)P * N * 4, 256));
+  int32_t* gflag = reinterpret_cast<int32_t*>(base + align_up((size_t)P * N * 4, 256) + align_up((size_t)P * 4, 256));
+  float* f = reinterpret_cast<float*>(base + fixed);
+  Work W;
+  W.in0 = f; f += (size_t)G * 12 * N;
+  W.T0 = f; f += (size_t)G * C * N;
+  W.T1 = f; f += (size_t)G * C * N;
+  W.T2 = f; f += (size_t)G * C * N;
+  W.CAT = f; f += (size_t)G * 2 * C * N;
+  W.E = f; f += (size_t)G * K * N;
+  W.XD0 = f; f += (size_t)G * C * K;
+  W.XD1 = f; f += (size_t)G * C * K;
+  W.Y = f; f += (size_t)G * C * K;
+  W.Z = f; f += (size_t)G * C * K;
+  W.scale = f; f += (size_t)G * 1024;
+  W.shift = f; f += (size_t)G * 1024;
+
+  if (status) cudaMemsetAsync(status, 0, (size_t)P * 4, st);
+
+  Cursor cur{params, 0, n_params};
+  const long long CN = (long long)C * N, CK = (long long)C * K;
+
+  auto affine = [&](const float* x, long long xb, int ch, int L, int g, bool use_in, float eps, const BNP& bn) -> int {
+    const int rows = use_in ? g * ch : ch;
+    in_affine_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, xb, ch, L, use_in ? 1 : 0, eps, bn.g, bn.b, bn.rm, bn.rv, W.scale, W.shift, rows);
+    return check_launch("in_affine_kernel");
+  };
+  // out[p, :, :] = conv(relu(bn(in(x))))  (+ residual), x [g, cin, L] with batch stride xb
+  auto conv_norm = [&](const float* x, long long xb, int cin, int L, int g, float eps, const BNP& bn, const ConvP& cv, int cout,
+                       float* out, long long ob, const float* res, long long rb) -> int {
+    LMPCR_TRY(affine(x, xb, cin, L, g, true, eps, bn));
+    GemmArgs a{};
+    a.A = cv.w; a.a_batch = 0; a.a_i = cin;
+    a.B = x; a.b_batch = xb; a.b_k = L; a.b_j = 1;
+    a.C = out; a.c_batch = ob; a.c_i = L; a.c_j = 1;
+    a.Res = res; a.r_batch = rb; a.bias = cv.b;
+    a.scale = W.scale; a.shift = W.shift; a.aff_batch = cin;
+    a.M = cout; a.N = L; a.K = cin;
+    return gemm(a, g, st);
+  };
+  auto conv_plain = [&](const float* x, long long xb, int cin, int L, int g, const ConvP& cv, int cout, float* out, long long ob) -> int {
+    GemmArgs a{};
+    a.A = cv.w; a.a_batch = 0; a.a_i = cin;
+    a.B = x; a.b_batch = xb; a.b_k = L; a.b_j = 1;
+    a.C = out; a.c_batch = ob; a.c_i = L; a.c_j = 1;
+    a.bias = cv.b; a.M = cout; a.N = L; a.K = cin;
+    return gemm(a, g, st);
+  };
+  // PointCN (oanet.py:18-43): out = conv2(f(conv1(f(x)))) + (shot_cut(x) | x)
+  auto pointcn = [&](const PointCNP& q, const float* x, long long xb, int cin, int g, float* tmp, float* sc_buf, float* out, long long ob) -> int {
+    const float* res = x; long long rb = xb;
+    if (q.has_sc) {
+      LMPCR_TRY(conv_plain(x, xb, cin, N, g, q.sc, C, sc_buf, CN));
+      res = sc_buf; rb = CN;
+    }
+    LMPCR_TRY(conv_norm(x, xb, cin, N, g, 1e-5f, q.bn1, q.c1, C, tmp, CN, nullptr, 0));
+    return conv_norm(tmp, CN, C, N, g, 1e-5f, q.bn2, q.c2, C, out, ob, res, rb);
+  };
+
+  for (int it = 0; it < iters; ++it) {
+    BlockP blk;
+    parse_block(cur, half, blk);
+    const int Cin = (it == 0 ? 6 : 8) + cfg->side_channel;
+    float* logits_it = logits + (size_t)it * P * N;
+    float* scores_it = scores + (size_t)it * P * N;
+    const float* scores_prev = it ? scores + (size_t)(it - 1) * P * N : nullptr;
+    cudaMemsetAsync(anypos, 0, (size_t)P * 4, st);
+    const bool last = (it == iters - 1);
+
+    for (int p0 = 0; p0 < P; p0 += G) {
+      const int g = min(G, P - p0);
+      const size_t tot = (size_t)g * N;
+      pack_input_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(xs + (size_t)p0 * N * Cx, Cx, it ? res_buf + (size_t)p0 * N : nullptr,
+                                                                      it ? scores_prev + (size_t)p0 * N : nullptr, g, N, W.in0, Cin);
+      LMPCR_TRY(check_launch("pack_input_kernel"));
+      // conv1 (oanet.py:167)
+      LMPCR_TRY(conv_plain(W.in0, (long long)Cin * N, Cin, N, g, blk.conv1, C, W.T0, CN));
+      // l1_1 (oanet.py:168): last PointCN writes x1_1 straight into the lower half of the concat buffer
+      float* cur_in = W.T0; float* cur_out = W.T1;
+      for (int i = 0; i < half; ++i) {
+        const bool fin = (i == half - 1);
+        float* o = fin ? W.CAT : cur_out;
+        LMPCR_TRY(pointcn(blk.l1_1[i], cur_in, CN, C, g, W.T2, nullptr, o, fin ? 2 * CN : CN));
+        if (!fin) { float* t = cur_in; cur_in = cur_out; cur_out = t; }
+      }
+      const float* x11 = W.CAT; const long long x11b = 2 * CN;
+      // diff_pool (oanet.py:106-110)
+      LMPCR_TRY(conv_norm(x11, x11b, C, N, g, 1e-3f, blk.down_bn, blk.down_conv, K, W.E, (long long)K * N, nullptr, 0));
+      softmax_rows_kernel<<<g * K, 256, 0, st>>>(W.E, N, g * K);
+      LMPCR_TRY(check_launch("softmax_rows_kernel"));
+      {
+        GemmArgs a{};   // x_down[c,k] = sum_n x11[c,n] * S[k,n]
+        a.A = x11; a.a_batch = x11b; a.a_i = N;
+        a.B = W.E; a.b_batch = (long long)K * N; a.b_k = 1; a.b_j = N;
+        a.C = W.XD0; a.c_batch = CK; a.c_i = K; a.c_j = 1;
+        a.M = C; a.N = K; a.K = N;
+        LMPCR_TRY(gemm(a, g, st));
+      }
+      // l2: OAFilter x half (oanet.py:85-93)
+      float* xd_in = W.XD0; float* xd_out = W.XD1;
+      for (int i = 0; i < half; ++i) {
+        const OAFilterP& q = blk.l2[i];
+        LMPCR_TRY(conv_norm(xd_in, CK, C, K, g, 1e-3f, q.bn1, q.c1, C, W.Y, CK, nullptr, 0));     // conv1 -> Y [g,C,K]
+        LMPCR_TRY(affine(nullptr, 0, K, 0, g, false, 0.f, q.bn2));                                 // BN over the cluster axis
+        {
+          GemmArgs a{};   // Z[c,k'] = Y[c,k'] + b2[k'] + sum_k W2[k',k] relu(bn_k(Y[c,k]))   (trans(1,2) via strides)
+          a.A = q.c2.w; a.a_batch = 0; a.a_i = K;
+          a.B = W.Y; a.b_batch = CK; a.b_k = 1; a.b_j = K;
+          a.C = W.Z; a.c_batch = CK; a.c_i = 1; a.c_j = K;
+          a.Res = W.Y; a.r_batch = CK; a.bias = q.c2.b;
+          a.scale = W.scale; a.shift = W.shift; a.aff_batch = 0;
+          a.M = K; a.N = C; a.K = K;
+          LMPCR_TRY(gemm(a, g, st));
+        }
+        LMPCR_TRY(conv_norm(W.Z, CK, C, K, g, 1e-3f, q.bn3, q.c3, C, xd_out, CK, xd_in, CK));      // conv3 + x
+        float* t = xd_in; xd_in = xd_out; xd_out = t;
+      }
+      // diff_unpool (oanet.py:122-129): x_up -> upper half of the concat buffer
+      LMPCR_TRY(conv_norm(x11, x11b, C, N, g, 1e-3f, blk.up_bn, blk.up_conv, K, W.E, (long long)K * N, nullptr, 0));
+      softmax_cols_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g);
+      LMPCR_TRY(check_launch("softmax_cols_kernel"));
+      {
+        GemmArgs a{};   // x_up[c,n] = sum_k x2[c,k] * S[k,n]
+        a.A = xd_in; a.a_batch = CK; a.a_i = K;
+        a.B = W.E; a.b_batch = (long long)K * N; a.b_k = N; a.b_j = 1;
+        a.C = W.CAT + CN; a.c_batch = 2 * CN; a.c_i = N; a.c_j = 1;
+        a.M = C; a.N = N; a.K = K;
+        LMPCR_TRY(gemm(a, g, st));
+      }
+      // l1_2 (oanet.py:171): PointCN(2C -> C) with shot_cut, then half-1 PointCN(C); T1/T0 ping-pong, T2 = temp
+      float* lat_dst = (last && latent) ? latent + (size_t)p0 * CN : nullptr;
+      {
+        float* o = (half == 1 && lat_dst) ? lat_dst : W.T1;
+        LMPCR_TRY(pointcn(blk.l1_2[0], W.CAT, 2 * CN, 2 * C, g, W.T2, W.T0, o, CN));
+        cur_in = o; cur_out = W.T0;
+      }
+      for (int i = 1; i < half; ++i) {
+        float* o = (i == half - 1 && lat_dst) ? lat_dst : cur_out;
+        LMPCR_TRY(pointcn(blk.l1_2[i], cur_in, CN, C, g, W.T2, nullptr, o, CN));
+        cur_out = cur_in;   // the buffer just consumed becomes the next destination
+        cur_in = o;
+      }
+      // output conv + weights (oanet.py:173-175)
+      logits_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cur_in, CN, C, N, g, blk.output.w, blk.output.b, logits_it + (size_t)p0 * N,
+                                                                  scores_it + (size_t)p0 * N, anypos + p0);
+      LMPCR_TRY(check_launch("logits_kernel"));
+    }
+    // zero-weight guard (oanet.py:177-178) + weighted Kabsch (oanet.py:182-183) for all pairs of the call
+    if (cfg->guard_mode == LMPCR_GUARD_BATCH) {
+      guard_flag_kernel<<<1, 256, 0, st>>>(anypos, P, gflag);
+      LMPCR_TRY(check_launch("guard_flag_kernel"));
+    }
+    LMPCR_TRY(launch_kabsch(xs, xs + 3, Cx, scores_it, P, N, cfg->guard_mode, cfg->guard_mode == LMPCR_GUARD_BATCH ? gflag : nullptr,
+                            scores_it, Rout + (size_t)it * P * 9, tout + (size_t)it * P * 3, res_buf, last ? conf : nullptr, status, st));
+  }
+  return LMPCR_OK;
+}
+
+}  // namespace lmpcr

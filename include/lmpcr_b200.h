@@ -1,0 +1,167 @@
+/* lmpcr_b200.h -- C ABI of the B200-native pairwise-registration hot path (liblmpcr_b200.so).
+ *
+ * The reference (zgojcic/3D_multiview_reg) is pure Python/PyTorch and has no FFI layer of its own; the
+ * boundary a maintainer binds is the Python module surface lib.pairwise / lib.filtering / lib.layers /
+ * lib.utils.  Every entry point below names the reference function (file:line, relative to the reference
+ * root) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stubs a maintainer adds on the
+ * reference side.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers (cudaMalloc / torch allocations) unless a parameter says "host".
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are asynchronous
+ *     with respect to the host; nothing synchronises.
+ *   - Every call returns 0 on success, <0 on an argument / launch error; lmpcr_last_error() then returns a
+ *     thread-local description.  Numerical degeneracy is NOT an error: it sets bits in the per-pair
+ *     `status` word (LMPCR_STATUS_*), mirroring the reference's `gradient_flag` (lib/utils.py:214-223).
+ *   - Scratch memory comes from the caller (`workspace`, size from the matching *_workspace_bytes call)
+ *     so that the caller's allocator (torch's caching allocator) stays in charge.  No call allocates.
+ *   - No CPU fallback exists: on a machine without an sm_100 device every compute call fails with
+ *     LMPCR_ERR_DEVICE.
+ */
+#ifndef LMPCR_B200_H_
+#define LMPCR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMPCR_ABI_VERSION 1
+
+#define LMPCR_OK 0
+#define LMPCR_ERR_ARG (-1)
+#define LMPCR_ERR_WORKSPACE (-2)
+#define LMPCR_ERR_LAUNCH (-3)
+#define LMPCR_ERR_DEVICE (-4)
+#define LMPCR_ERR_UNSUPPORTED (-5)
+
+/* per-pair status bits */
+#define LMPCR_STATUS_ZERO_WEIGHT 1u   /* sum(w) == 0: the +1/N guard fired (oanet.py:177-178)              */
+#define LMPCR_STATUS_DEGENERATE 2u    /* covariance rank < 2: rotation is not determined (identity returned, *
+                                       * the analogue of the reference's SVD-failure path lib/utils.py:216)  */
+
+/* NN algorithms */
+#define LMPCR_NN_EXACT_SIMT 0 /* fp32 CUDA-core evaluation of the reference formula (bit-exact)            */
+#define LMPCR_NN_TENSOR 1     /* tcgen05 BF16 screening + fp32 rescoring of near-tie candidates (bit-exact) */
+
+/* mutual-NN definitions */
+#define LMPCR_MUTUAL_INDEX 0     /* scripts/extract_data.py:186   idx_ts[idx_st[i]] == i                    */
+#define LMPCR_MUTUAL_GEOMETRIC 1 /* lib/utils.py:822-848 on hard matches: |x_s[i]-x_s[idx_ts[idx_st[i]]]|^2 < thr^2 */
+
+/* zero-weight guard coupling */
+#define LMPCR_GUARD_BATCH 0 /* reference: any pair with sum(w)==0 adds 1/N to EVERY pair of the call       */
+#define LMPCR_GUARD_PAIR 1  /* per pair (partition-invariant; used by the multi-GPU scene path)            */
+
+int lmpcr_abi_version(void);
+const char* lmpcr_last_error(void);
+/* Fills sm_count / l2_bytes / cc_major / cc_minor of the current device (host ints, any may be NULL). */
+int lmpcr_device_info(int* sm_count, int* l2_bytes, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Stage 1 -- feature-space nearest neighbours.
+ * Replaces lib/utils.py:968-992 `pairwise_distance` + lib/layers.py:81-86 (`dist.min` / one-hot / matmul
+ * gather), invoked twice per pair from lib/pairwise/__init__.py:110-111.
+ *
+ * q_feat [n_q_sets, n_q, dim], b_feat [n_b_sets, n_b, dim] fp32 row-major.  For every job j=(qs,bs) in
+ * `jobs` [n_jobs,2] (int32) and every row i of query set qs:
+ *   idx_out[j, i]  = argmin_k dist(q_feat[qs,i], b_feat[bs,k])  (first minimum; int32)
+ *   dist_out[j, i] = that fp32 distance (optional, may be NULL)
+ * with dist evaluated exactly as the reference does in fp32 (sequential FMA dot, then 2*(-c) + |q|^2 + |b|^2).
+ * The N x M distance matrix is never materialised.  A scene passes its scans once as both q_feat and b_feat
+ * and two jobs (i,j),(j,i) per scan pair -- features are never copied per pair (cf. lib/utils.py:879-883).
+ * dim must be a multiple of 8 and <= 64 (LMPCR_NN_TENSOR: dim == 32).
+ * ---------------------------------------------------------------------------------------------------- */
+size_t lmpcr_nn_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, int dim, int n_jobs, int algo);
+int lmpcr_nn_argmin(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
+                    const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, int algo, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* lib/utils.py:968-992 `pairwise_distance` itself, materialised: src [B,n,dim], dst [B,m,dim] -> out [B,n,m] fp32,
+ * bit-identical to the reference's CPU evaluation.  Not on the hot path (which never stores the matrix); kept so
+ * that `lib.utils.pairwise_distance` stays importable.  workspace >= 256-aligned (B*n + B*m) floats. */
+int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, int dim, int batch, float* out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* Correspondence coordinates of hard matches: out[j,i,:] = b_xyz[jobs[j].bs, idx[j,i], :]
+ * (lib/layers.py:86 `torch.matmul(one_hot, y_c)`).  b_xyz [n_b_sets, n_b, 3]. */
+int lmpcr_gather_xyz(const float* b_xyz, int n_b, const int32_t* jobs, int n_jobs, const int32_t* idx, int n_q,
+                     float* out, void* stream);
+
+/* Mutual flags + filtering-network input for scan pairs (lib/utils.py:822-848 / scripts/extract_data.py:186,
+ * lib/utils.py:915-926).  idx_st [n_pairs, n_s] = NN of source points in the target, idx_ts [n_pairs, n_t].
+ * xyz [n_sets, n_pts, 3]; pairs [n_pairs,2] = (source set, target set).
+ *   mutual[p,i] (uint8, optional)   per `mutual_mode`
+ *   xs[p,0,i,:] (fp32, [n_pairs,1,n_pts,xs_channels]) = (xyz_s[i], xyz_t[idx_st[i]] [, mutual]) ; xs_channels 6|7 */
+int lmpcr_mutual_xs(const float* xyz, int n_pts, const int32_t* pairs, int n_pairs, const int32_t* idx_st,
+                    const int32_t* idx_ts, int mutual_mode, float mutual_thresh, uint8_t* mutual, float* xs,
+                    int xs_channels, void* stream);
+
+/* Brute-force 3-D 1-NN, lib/utils.py:274-299 `knn_point(k=1, pos1, pos2)`: for each row of pos2 [B,M,3] the
+ * index (int32) of the closest row of pos1 [B,N,3] under sum((p1-p2)^2) in fp32 (first best wins). */
+int lmpcr_knn3d_1(const float* pos1, int n, const float* pos2, int m, int batch, int32_t* idx_out, float* sqdist_out,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Stage 3 -- weighted Kabsch + residuals + confidence.
+ * Replaces lib/utils.py:164-237 `kabsch_transformation_estimation` (normalize_w=True, best_k=0,
+ * w_threshold=0) and lib/utils.py:240-256 `transformation_residuals`.
+ *
+ * x1, x2: first element of the source / corresponding-target coordinates of pair 0; point i of pair p is at
+ * x[(p*n_pts + i)*ld .. +2] (fp32).  For the filtering-network layout xs [P,1,N,C]: x1 = xs, x2 = xs+3, ld = C;
+ * for separate [P,N,3] tensors ld = 3.  w [P,N].  One warp per pair.
+ *   R [P,3,3], t [P,3,1], res [P,N] (optional)
+ *   conf [P,4] = (#(w>0.5), sum w, sqrt(sum w_norm res^2), #(res<0.05))   optional
+ *   status [P] uint32 bits OR-ed in (must be initialised by the caller)     optional
+ * guard: if guard_flag (device int32, optional) is non-zero [LMPCR_GUARD_BATCH] or the pair's own sum(w)==0
+ * [LMPCR_GUARD_PAIR], w+1/N is used and written to `w_out` (optional, may alias w).
+ * ---------------------------------------------------------------------------------------------------- */
+int lmpcr_kabsch(const float* x1, const float* x2, int ld, const float* w, int n_pairs, int n_pts, int guard_mode,
+                 const int32_t* guard_flag, float* w_out, float* R, float* t, float* res, float* conf,
+                 uint32_t* status, void* stream);
+
+/* lib/utils.py:240-256 alone: x1,x2 [P,N,3] (row stride `ld` floats), R [P,3,3], t [P,3,1] -> res [P,N]. */
+int lmpcr_residuals(const float* x1, const float* x2, int ld, const float* R, const float* t, int n_pairs, int n_pts,
+                    float* res, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Stage 2(+3) -- correspondence-weighting network, eval mode.
+ * Replaces lib/filtering/oanet.py:218-265 `OANet.forward` (OANBlock :165-185, PointCN :18-43, OAFilter
+ * :56-93, diff_pool :96-110, diff_unpool :113-129) including the Kabsch call of every block.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct lmpcr_filter_cfg {
+  int32_t net_channel;  /* cfg['misc']['net_channel']  (128)                                   */
+  int32_t clusters;     /* cfg['misc']['clusters']     (500)                                   */
+  int32_t net_depth;    /* cfg['misc']['net_depth']    (12)  -> depth per block = net_depth/(iter_num+1) */
+  int32_t iter_num;     /* cfg['misc']['iter_num']     (1)                                     */
+  int32_t side_channel; /* cfg['data']['use_mutuals'] == 2 -> 1 (xs has 7 channels)            */
+  int32_t guard_mode;   /* LMPCR_GUARD_BATCH | LMPCR_GUARD_PAIR                                */
+  int32_t gemm_algo;    /* 0 = fp32 CUDA-core GEMMs, 1 = tcgen05 split-BF16 tensor-core GEMMs  */
+  int32_t reserved;
+} lmpcr_filter_cfg;
+
+/* Number of tensors of OANet(cfg).state_dict() excluding `num_batches_tracked` entries; `params` below is
+ * a HOST array of that many DEVICE pointers (fp32, contiguous), in state_dict order. */
+int lmpcr_filter_num_params(const lmpcr_filter_cfg* cfg);
+size_t lmpcr_filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int n_pairs, int n_pts);
+/* xs [P,1,N,6+side] fp32.  Outputs, for it in [0, iter_num]:
+ *   logits [iter_num+1, P, N], scores [iter_num+1, P, N], R [iter_num+1, P, 3, 3], t [iter_num+1, P, 3, 1]
+ *   residuals [P,N] of the last block (optional), latent [P, C, N] of the last block (optional),
+ *   conf [P,4] of the last block (optional), status [P] uint32 (optional; zeroed by the call).        */
+int lmpcr_filter_forward(const float* xs, int n_pairs, int n_pts, const float* const* params, int n_params,
+                         const lmpcr_filter_cfg* cfg, float* logits, float* scores, float* R, float* t,
+                         float* residuals, float* latent, float* conf, uint32_t* status, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Pose record packing for the multi-GPU all-gather:
+ * rec [P,16] = (R row-major (9), t (3), #(w>0.5), sum w, rms residual, status as float).
+ * ---------------------------------------------------------------------------------------------------- */
+int lmpcr_pack_pose_records(const float* R, const float* t, const float* conf, const uint32_t* status, int n_pairs,
+                            float* rec, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMPCR_B200_H_ */

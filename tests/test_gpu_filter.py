@@ -1,0 +1,108 @@
+"""GPU parity, stage 2(+3): the filtering network through lmpcr_filter_forward vs the fp64 oracle and the reference
+goldens.  Gates (DESIGN.md "tolerances"): logits/scores 5e-4, rotation 5e-4 rad (chordal), translation 1e-3 m --
+5x the reference's own fp32-vs-fp64 spread on these inputs; the Kabsch stage alone is gated at 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lmpcr_oracle as O
+from util import cabi, cu, load_oanet
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL, ROT_TOL, TRANS_TOL = 5e-4, 5e-4, 1e-3
+
+
+def _run(net, xs):
+    with torch.no_grad():
+        return net({"xs": torch.from_numpy(xs)})          # CPU input, moved inside like oanet.py:234
+
+
+@pytest.mark.parametrize("name", ["full_p2_n2000", "full_p1_n5000", "small_p3_n64", "guard_p2_n500"])
+def test_oanet_vs_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "oanet_golden.npz"))
+    P, N, seed, small, guard = [int(v) for v in g[name + "_cfg"]]
+    kw = dict(net_channel=32, clusters=16) if small else {}
+    sd = O.synth_state_dict(seed, **kw)
+    if guard:
+        sd["reg_init.output.bias"] = np.full((1,), -50.0, np.float32)
+    xs, _, _ = O.synth_xs(P, N, seed=seed)
+    out = _run(load_oanet(sd, **kw), xs)
+    assert set(["logits", "scores", "rot_est", "trans_est", "latent features", "gradient_flag"]) <= set(out.keys())
+    assert len(out["logits"]) == 2 and tuple(out["rot_est"][-1].shape) == (P, 3, 3) and tuple(out["trans_est"][-1].shape) == (P, 3, 1)
+    assert tuple(out["latent features"].shape) == (P, kw.get("net_channel", 128), N, 1)
+    for it in range(2):
+        assert np.abs(out["logits"][it].cpu().numpy() - g["%s_logits%d" % (name, it)]).max() < LOGIT_TOL
+        assert np.abs(out["scores"][it].cpu().numpy() - g["%s_scores%d" % (name, it)]).max() < LOGIT_TOL
+        assert O.chordal_angle(out["rot_est"][it].cpu().numpy(), g["%s_R%d" % (name, it)]).max() < ROT_TOL
+        assert np.abs(out["trans_est"][it].cpu().numpy() - g["%s_t%d" % (name, it)]).max() < TRANS_TOL
+    assert out["gradient_flag"] == bool(g[name + "_flag"])
+    assert abs(float(out["latent features"].abs().mean()) - float(g[name + "_latent_absmean"])) < 1e-3
+    if guard:
+        assert np.allclose(out["scores"][0].cpu().numpy(), 1.0 / N)
+
+
+@pytest.mark.parametrize("P,N,seed", [(3, 777, 31), (2, 1001, 32), (1, 130, 33)])
+def test_oanet_vs_fp64_oracle_ragged_sizes(P, N, seed):
+    """Point counts that are not multiples of 4 / of the tile sizes (mutual-filtered inputs have arbitrary N)."""
+    sd = O.synth_state_dict(seed)
+    xs, _, _ = O.synth_xs(P, N, seed=seed)
+    out = _run(load_oanet(sd), xs)
+    o64 = O.oanet_forward(xs, sd, dtype=np.float64)
+    for it in range(2):
+        assert np.abs(out["logits"][it].cpu().numpy() - o64["logits"][it]).max() < LOGIT_TOL
+        assert O.chordal_angle(out["rot_est"][it].cpu().numpy(), o64["rot_est"][it]).max() < ROT_TOL
+        assert np.abs(out["trans_est"][it].cpu().numpy() - o64["trans_est"][it]).max() < TRANS_TOL
+    # stage 3 on the net's own weights: 1e-5 gate
+    w = out["scores"][-1].cpu().numpy()
+    Ro, to, reso, _ = O.kabsch(xs[:, 0, :, :3], xs[:, 0, :, 3:], w, dtype=np.float64)
+    assert O.chordal_angle(out["rot_est"][-1].cpu().numpy(), Ro).max() < 1e-5
+    assert np.abs(out["trans_est"][-1].cpu().numpy() - to).max() < 1e-5
+    assert np.abs(out["residuals"].cpu().numpy() - reso).max() < 1e-5
+
+
+def test_group_size_does_not_change_results():
+    """Pairs are processed in workspace-sized groups; per-pair arithmetic must not depend on the grouping."""
+    sd = O.synth_state_dict(5)
+    xs, _, _ = O.synth_xs(5, 512, seed=5)
+    net = load_oanet(sd)
+    cfg = net.cabi_cfg()
+    x = cu(xs)
+    full = cabi.filter_forward(x, net.param_table(), cfg)
+    one_pair = cabi.filter_workspace_bytes(cfg, 1, 512)
+    small = cabi.filter_forward(x, net.param_table(), cfg,
+                                workspace=torch.empty(one_pair + 5 * 512 * 4 + 4096, dtype=torch.uint8, device="cuda"))
+    for k in ("logits", "scores", "R", "t", "residuals", "latent", "conf"):
+        assert torch.equal(full[k], small[k]), k
+
+
+def test_side_channel_and_iter0():
+    """use_mutuals == 2 (7-channel xs) and iter_num = 0 (single block of depth 12)."""
+    sd = O.synth_state_dict(9, side_channel=1)
+    xs, _, _ = O.synth_xs(2, 300, seed=9)
+    xs7 = np.concatenate([xs, (np.random.default_rng(1).uniform(size=(2, 1, 300, 1)) > 0.5).astype(np.float32)], axis=3)
+    import importlib
+    oanet = importlib.import_module("3d_multiview_reg_b200.lib.filtering.oanet")
+    net = oanet.OANet({"misc": dict(iter_num=1, net_depth=12, net_channel=128, clusters=500, normalize_weights=True, use_gpu=True),
+                       "data": {"use_mutuals": 2}}).eval()
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    out = _run(net.cuda(), xs7)
+    o64 = O.oanet_forward(xs7, sd, dtype=np.float64)
+    assert np.abs(out["logits"][-1].cpu().numpy() - o64["logits"][-1]).max() < LOGIT_TOL
+    sd0 = O.synth_state_dict(10, iter_num=0)
+    out0 = _run(load_oanet(sd0, iter_num=0), xs)
+    o0 = O.oanet_forward(xs, sd0, iter_num=0, dtype=np.float64)
+    assert len(out0["logits"]) == 1
+    assert np.abs(out0["logits"][0].cpu().numpy() - o0["logits"][0]).max() < LOGIT_TOL
+
+
+def test_empty_batch_and_bad_args():
+    sd = O.synth_state_dict(1)
+    net = load_oanet(sd)
+    out = cabi.filter_forward(torch.zeros((0, 1, 100, 6), device="cuda"), net.param_table(), net.cabi_cfg())
+    assert out["logits"].shape == (2, 0, 100)
+    with pytest.raises(AssertionError):
+        net({"xs": torch.zeros(2, 100, 6)})
+    with pytest.raises(cabi.LmpcrError):
+        cabi.filter_forward(torch.zeros((1, 1, 100, 6), device="cuda"), net.param_table()[:-1], net.cabi_cfg())

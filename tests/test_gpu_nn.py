@@ -1,0 +1,123 @@
+"""GPU parity, stage 1: CUDA nearest-neighbour path (through the C ABI) vs the CPU oracle and vs the golden
+vectors produced by the unmodified reference.  Gate: BIT-EXACT indices (and distances)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lmpcr_oracle as O
+from oracle import nn_c
+from util import cabi, cu
+
+pytestmark = pytest.mark.gpu
+ALGOS = [cabi.NN_EXACT_SIMT]
+
+
+def _jobs(pairs):
+    return torch.tensor(pairs, dtype=torch.int32, device="cuda")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("name", ["s300x700", "s1000", "s5000", "s2049x777"])
+def test_nn_vs_reference_golden(golden_dir, name, algo):
+    g = np.load(os.path.join(golden_dir, "nn_golden.npz"))
+    n, m, seed = [int(v) for v in g[name + "_shape"]]
+    feats, xyz, _ = O.synth_scene(2, max(n, m), seed=seed)
+    fs, ft = cu(feats[0:1, :n]), cu(feats[1:2, :m])
+    idx_st, d_st = cabi.nn_argmin(fs, ft, _jobs([[0, 0]]), algo=algo, return_dist=True)
+    idx_ts = cabi.nn_argmin(ft, fs, _jobs([[0, 0]]), algo=algo)
+    assert np.array_equal(idx_st[0].cpu().numpy(), g[name + "_idx_st"])
+    assert np.array_equal(idx_ts[0].cpu().numpy(), g[name + "_idx_ts"])
+    assert np.array_equal(d_st[0].cpu().numpy(), g[name + "_min_st"])
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_nn_scene_jobs_vs_oracle(algo):
+    """4 scans -> 6 pairs x 2 directions in ONE call, features never copied per pair."""
+    feats, xyz, _ = O.synth_scene(4, 1500, seed=3)
+    pairs = O.enumerate_pairs(4)
+    f = cu(feats)
+    jobs = np.concatenate([pairs, pairs[:, ::-1]], 0)
+    idx, dist = cabi.nn_argmin(f, f, _jobs(jobs.tolist()), algo=algo, return_dist=True)
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    for j, (a, b) in enumerate(jobs):
+        ref_i, ref_d = nn_c.nn_argmin(feats[a], feats[b])
+        assert np.array_equal(idx[j], ref_i) and np.array_equal(dist[j], ref_d)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_nn_ties_and_unnormalised(golden_dir, algo):
+    g = np.load(os.path.join(golden_dir, "nn_golden.npz"))
+    feats, _, _ = O.synth_scene(2, 256, seed=5)
+    ft = np.concatenate([feats[1][:128], feats[1][:128]], axis=0)
+    idx = cabi.nn_argmin(cu(feats[0:1]), cu(ft[None]), _jobs([[0, 0]]), algo=algo)
+    assert np.array_equal(idx[0].cpu().numpy(), g["ties_idx"])          # first minimum wins
+    if algo == cabi.NN_EXACT_SIMT:                                       # tensor path assumes |f| <= ~1 (FCGF)
+        rng = np.random.default_rng(99)
+        fa = (rng.standard_normal((400, 32)) * 2).astype(np.float32)
+        fb = (rng.standard_normal((600, 32)) * 0.5 + 0.3).astype(np.float32)
+        idx = cabi.nn_argmin(cu(fa[None]), cu(fb[None]), _jobs([[0, 0]]), algo=algo)
+        assert np.array_equal(idx[0].cpu().numpy(), g["unnorm_idx"])
+
+
+@pytest.mark.parametrize("dim", [8, 16, 64])
+def test_nn_other_dims(dim):
+    rng = np.random.default_rng(dim)
+    a = rng.standard_normal((333, dim)).astype(np.float32)
+    b = rng.standard_normal((500, dim)).astype(np.float32)
+    idx, d = cabi.nn_argmin(cu(a[None]), cu(b[None]), _jobs([[0, 0]]), return_dist=True)
+    ri, rd = nn_c.nn_argmin(a, b)
+    assert np.array_equal(idx[0].cpu().numpy(), ri) and np.array_equal(d[0].cpu().numpy(), rd)
+
+
+def test_edge_sizes():
+    rng = np.random.default_rng(0)
+    for n, m in [(1, 1), (1, 129), (127, 1), (129, 3)]:
+        a = rng.standard_normal((n, 32)).astype(np.float32)
+        b = rng.standard_normal((m, 32)).astype(np.float32)
+        idx = cabi.nn_argmin(cu(a[None]), cu(b[None]), _jobs([[0, 0]]))
+        assert np.array_equal(idx[0].cpu().numpy(), nn_c.nn_argmin(a, b)[0])
+    # empty job list
+    out = cabi.nn_argmin(cu(a[None]), cu(b[None]), torch.zeros((0, 2), dtype=torch.int32, device="cuda"))
+    assert out.shape == (0, a.shape[0])
+
+
+def test_pairwise_distance_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "nn_golden.npz"))
+    rng = np.random.default_rng(99)
+    fa = (rng.standard_normal((400, 32)) * 2).astype(np.float32)
+    fb = (rng.standard_normal((600, 32)) * 0.5 + 0.3).astype(np.float32)
+    d = cabi.pairwise_distance(cu(fa[None]), cu(fb[None]))[0].cpu().numpy()
+    assert np.array_equal(d[:64, :64], g["unnorm_dist"])
+    assert np.array_equal(d, nn_c.pairwise_distance(fa, fb))
+
+
+def test_mutual_xs_gather_knn(golden_dir):
+    g = np.load(os.path.join(golden_dir, "nn_golden.npz"))
+    feats, xyz, _ = O.synth_scene(2, 1000, seed=12)
+    f, x = cu(feats), cu(xyz)
+    pairs = _jobs([[0, 1]])
+    idx_st = cabi.nn_argmin(f, f, pairs)
+    idx_ts = cabi.nn_argmin(f, f, pairs.flip(1).contiguous())
+    o_st, o_ts, o_mut, o_xs = O.register_pair_stage1(feats[0], feats[1], xyz[0], xyz[1], mutual_mode="geometric")
+    m_geo, xs = cabi.mutual_xs(x, pairs, idx_st, idx_ts, cabi.MUTUAL_GEOMETRIC, 0.05)
+    assert np.array_equal(m_geo[0].cpu().numpy(), g["s1000_mutual_geo"])      # reference's extract_mutuals
+    assert np.array_equal(xs[0].cpu().numpy(), o_xs)
+    m_idx, xs7 = cabi.mutual_xs(x, pairs, idx_st, idx_ts, cabi.MUTUAL_INDEX, 0.05, xs_channels=7)
+    assert np.array_equal(m_idx[0].cpu().numpy(), O.mutual_index(o_st, o_ts))
+    assert np.array_equal(xs7[0, 0, :, 6].cpu().numpy(), O.mutual_index(o_st, o_ts).astype(np.float32))
+    # Soft_NN('hard') output == gathered target coordinates (lib/layers.py:86)
+    corr = cabi.gather_xyz(x, pairs, idx_st)
+    assert np.array_equal(corr[0].cpu().numpy(), xyz[1][o_st])
+    # knn_point(k=1) (lib/utils.py:274) and the module-level mirror of extract_mutuals
+    sq, idx = cabi.knn3d_1(x[1:2], corr)
+    assert np.array_equal(idx[0].cpu().numpy().astype(np.int64), O.knn_point_1(xyz[1], xyz[1][o_st]))
+    import importlib
+    U = importlib.import_module("3d_multiview_reg_b200.lib.utils")
+    L = importlib.import_module("3d_multiview_reg_b200.lib.layers")
+    back = cabi.gather_xyz(x, pairs.flip(1).contiguous(), idx_ts)
+    mut = U.extract_mutuals(x[0:1], x[1:2], corr, back)
+    assert np.array_equal(mut[0].cpu().numpy().astype(np.uint8), g["s1000_mutual_geo"])
+    hard = L.Soft_NN(corr_type="hard", device="cuda")
+    assert np.array_equal(hard(f[0:1], f[1:2], x[1:2])[0].cpu().numpy(), xyz[1][o_st])

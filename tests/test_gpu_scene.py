@@ -1,0 +1,70 @@
+"""GPU: scene-level path (stage 1 -> 2 -> 3 over all pairs) vs the oracle, and partition invariance."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lmpcr_oracle as O
+from oracle import nn_c
+from util import cabi, cu, load_oanet
+
+pytestmark = pytest.mark.gpu
+scene = importlib.import_module("3d_multiview_reg_b200.scene")
+
+
+def test_scene_vs_oracle_and_partition_invariance():
+    S, n = 5, 768
+    feats, xyz, _ = O.synth_scene(S, n, seed=77)
+    sd = O.synth_state_dict(77)
+    net = load_oanet(sd)
+    f, x = cu(feats), cu(xyz)
+    reg = scene.SceneRegistrar(net, pair_chunk=4)
+    rec = reg.register_scene(f, x)
+    pairs = O.enumerate_pairs(S)
+    assert rec.shape == (len(pairs), 16)
+    r = rec.cpu().numpy()
+    for p in (0, 4, 9):
+        a, b = pairs[p]
+        i_st, _ = nn_c.nn_argmin(feats[a], feats[b])
+        xs = O.construct_xs(xyz[a], xyz[b][i_st])[None]
+        o = O.oanet_forward(xs, sd, dtype=np.float64, guard="pair")
+        assert O.chordal_angle(r[p, :9].reshape(3, 3), o["rot_est"][-1][0]) < 5e-4
+        assert np.abs(r[p, 9:12] - o["trans_est"][-1][0, :, 0]).max() < 1e-3
+        conf = O.pair_confidence(o["scores"][-1], o["residuals"][-1])
+        assert abs(r[p, 12] - conf[0, 0]) <= 2 and abs(r[p, 13] - conf[0, 1]) < 1e-2 * max(1.0, conf[0, 1])
+    # the same pairs computed as 1, 2, 3 "ranks" (contiguous shards) are bit-identical
+    for W in (2, 3):
+        shard, ranges = scene.partition_pairs(len(pairs), W)
+        parts = [scene.SceneRegistrar(net, pair_chunk=3).register_scene(f, x, rank=k, world_size=W, gather=False)[0] for k in range(W)]
+        assert torch.equal(torch.cat(parts, 0), rec)
+    u = scene.unpack_records(rec)
+    assert u["R"].shape == (10, 3, 3) and u["t"].shape == (10, 3, 1)
+
+
+def test_pairwise_reg_module_surface():
+    """lib.pairwise.PairwiseReg drop-in: compute_descriptors on precomputed features + filter_correspondences."""
+    pw = importlib.import_module("3d_multiview_reg_b200.lib.pairwise")
+    S, n = 3, 600
+    feats, xyz, _ = O.synth_scene(S, n, seed=5)
+    sd = O.synth_state_dict(5)
+    net = load_oanet(sd)
+    model = pw.PairwiseReg(descriptor_module=lambda d: d["feat_in"], filtering_module=net, device=torch.device("cuda"),
+                           samp_type="rand", corr_type="hard", tgt_num_points=n).eval()
+    np.random.seed(41)
+    data = {"pcd0": torch.from_numpy(xyz.reshape(-1, 3)), "feat_in": torch.from_numpy(feats.reshape(-1, 32)),
+            "pts_list": torch.tensor([n] * S)}
+    filt_in, F0, F1, out = model(data)
+    assert tuple(filt_in["xs"].shape) == (3, 1, n, 6) and tuple(filt_in["Rs"].shape) == (3, 3, 3)
+    assert tuple(out["rot_est"][-1].shape) == (3, 3, 3) and len(out["scores"]) == 2
+    # correspondences equal the oracle's for the sampled points
+    np.random.seed(41)
+    xs = filt_in["xs"].cpu().numpy()
+    sel = [np.random.choice(np.arange(i * n, (i + 1) * n), n, replace=False) - i * n for i in range(S)]
+    fa, fb = feats[0][sel[0]], feats[1][sel[1]]
+    i_st, _ = nn_c.nn_argmin(fa, fb)
+    assert np.array_equal(xs[0, 0, :, :3], xyz[0][sel[0]]) and np.array_equal(xs[0, 0, :, 3:], xyz[1][sel[1]][i_st])
+    # precomputed mode passes the dict straight through (lib/pairwise/__init__.py:122-125)
+    m2 = pw.PairwiseReg(None, net, torch.device("cuda"))
+    d, a, b = m2.compute_descriptors({"xs": filt_in["xs"]})
+    assert a is None and b is None and d["xs"] is filt_in["xs"]
