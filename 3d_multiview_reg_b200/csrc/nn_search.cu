@@ -233,6 +233,8 @@ size_t nn_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, int dim,
 int launch_nn_argmin(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
                      const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, int algo, void* ws,
                      size_t ws_bytes, cudaStream_t st) {
+  LMPCR_REQUIRE(n_jobs >= 0, LMPCR_ERR_ARG, "lmpcr_nn_argmin: n_jobs < 0");
+  if (n_jobs == 0) return LMPCR_OK;
   LMPCR_REQUIRE(q_feat && b_feat && jobs && idx_out, LMPCR_ERR_ARG, "lmpcr_nn_argmin: null pointer");
   LMPCR_REQUIRE(n_q_sets > 0 && n_b_sets > 0 && n_q > 0 && n_b > 0 && n_jobs >= 0, LMPCR_ERR_ARG, "lmpcr_nn_argmin: bad sizes");
   LMPCR_REQUIRE(dim % 8 == 0 && dim >= 8 && dim <= 64, LMPCR_ERR_UNSUPPORTED, "lmpcr_nn_argmin: dim=%d (multiple of 8, <= 64)", dim);
