@@ -19,7 +19,7 @@ GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
 EXPORTS = [
-    "lmpcr_abi_version", "lmpcr_last_error", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
     "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
     "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
 ]
@@ -53,6 +53,8 @@ def load():
     lib.lmpcr_nn_workspace_bytes.restype = _sz
     lib.lmpcr_nn_workspace_bytes.argtypes = [_i] * 7
     lib.lmpcr_nn_argmin.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]
+    lib.lmpcr_launch_count.restype = ctypes.c_longlong
+    lib.lmpcr_nn_tensor_debug.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
     lib.lmpcr_pairwise_distance.argtypes = [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]
     lib.lmpcr_gather_xyz.argtypes = [_vp, _i, _vp, _i, _vp, _i, _vp, _vp]
     lib.lmpcr_mutual_xs.argtypes = [_vp, _i, _vp, _i, _vp, _vp, _i, _f, _vp, _vp, _i, _vp]
@@ -119,6 +121,29 @@ def nn_argmin(q_feat, b_feat, jobs, algo=NN_EXACT_SIMT, return_dist=False):
         _check(lib.lmpcr_nn_argmin(_p(q), q.shape[0], n, _p(b), b.shape[0], b.shape[1], q.shape[2], _p(jobs), J, _p(idx), _p(dist),
                                    algo, _p(ws), ws.numel(), _stream(q)))
     return (idx, dist) if return_dist else idx
+
+
+def launch_count():
+    return int(load().lmpcr_launch_count())
+
+
+def nn_tensor_debug(q_feat, b_feat, jobs):
+    """Tensor-path NN with the raw screening scores: returns (idx [J,n], dist [J,n], scores [J,n,m_pad], approx_min [J,n])."""
+    lib = load()
+    q = _dev(q_feat, name="q_feat")
+    b = q if b_feat is q_feat else _dev(b_feat, name="b_feat")
+    jobs = _dev(jobs, torch.int32, "jobs")
+    J, n, m = jobs.shape[0], q.shape[1], b.shape[1]
+    m_pad = (m + 255) // 256 * 256
+    with torch.cuda.device(q.device):
+        idx = torch.empty((J, n), dtype=torch.int32, device=q.device)
+        dist = torch.empty((J, n), dtype=torch.float32, device=q.device)
+        scores = torch.zeros((J, n, m_pad), dtype=torch.float32, device=q.device)
+        amin = torch.empty((J, n), dtype=torch.float32, device=q.device)
+        ws = _ws(lib.lmpcr_nn_workspace_bytes(q.shape[0], n, b.shape[0], m, q.shape[2], J, NN_TENSOR), q.device)
+        _check(lib.lmpcr_nn_tensor_debug(_p(q), q.shape[0], n, _p(b), b.shape[0], m, q.shape[2], _p(jobs), J, _p(idx), _p(dist),
+                                         _p(scores), _p(amin), _p(ws), ws.numel(), _stream(q)))
+    return idx, dist, scores, amin
 
 
 def pairwise_distance(src, dst):

@@ -15,7 +15,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launches = 0;
+void count_launches(int n) { __atomic_add_fetch(&g_launches, (long long)n, __ATOMIC_RELAXED); }
+
 int check_launch(const char* what) {
+  count_launches(1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -63,6 +67,7 @@ using namespace lmpcr;
 extern "C" {
 
 int lmpcr_abi_version(void) { return LMPCR_ABI_VERSION; }
+long long lmpcr_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 const char* lmpcr_last_error(void) { return g_err; }
 
 int lmpcr_device_info(int* sms, int* l2_bytes, int* cc_major, int* cc_minor) {
@@ -90,6 +95,15 @@ int lmpcr_nn_argmin(const float* q_feat, int n_q_sets, int n_q, const float* b_f
   LMPCR_TRY(check_device());
   return launch_nn_argmin(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, dim, jobs, n_jobs, idx_out, dist_out, algo, workspace,
                           workspace_bytes, (cudaStream_t)stream);
+}
+
+int lmpcr_nn_tensor_debug(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
+                          const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, float* scores, float* approx_min,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  LMPCR_REQUIRE(q_feat && b_feat && jobs && idx_out && n_jobs > 0, LMPCR_ERR_ARG, "lmpcr_nn_tensor_debug: bad arguments");
+  return launch_nn_tensor_ex(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, dim, jobs, n_jobs, idx_out, dist_out, scores, approx_min,
+                             workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, int dim, int batch, float* out, void* workspace,

@@ -13,6 +13,7 @@ void set_error(const char* fmt, ...);
 int check_device();          // LMPCR_OK iff the current device is sm_100 (B200)
 int check_launch(const char* what);
 int sm_count();
+void count_launches(int n);   // bookkeeping behind lmpcr_launch_count()
 
 #define LMPCR_REQUIRE(cond, code, ...)   \
   do {                                   \
@@ -71,6 +72,9 @@ int launch_mutual_xs(const float* xyz, int n_pts, const int32_t* pairs, int n_pa
 int launch_knn3d(const float* pos1, int n, const float* pos2, int m, int batch, int32_t* idx, float* sq, cudaStream_t st);
 // nn_tensor.cu (tcgen05 path)
 size_t nn_tensor_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, int dim, int n_jobs);
+int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
+                        const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, float* dbg_scores, float* approx_min,
+                        void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_nn_tensor(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
                      const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, void* ws, size_t ws_bytes,
                      cudaStream_t st);

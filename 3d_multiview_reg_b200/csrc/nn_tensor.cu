@@ -1,10 +1,530 @@
-// Stage 1 (tensor-core path) -- placeholder translation unit until the tcgen05 kernel lands.
+// Stage 1 (tensor-core path): feature-space hard nearest neighbour on tcgen05, bit-exact against the reference.
+//
+// Replaces lib/utils.py:968-992 + lib/layers.py:81 for D = 32 (FCGF).  Three kernels:
+//
+//  (1) nn_prep_kernel     once per scan: fp32 features -> fp16 MMA operands in the UMMA canonical K-major layout
+//                         (so that a tile is ONE contiguous TMA bulk copy), the fp32 squared norms in the reference's
+//                         summation order, a chunk-transposed fp32 copy for coalesced rescoring, and the rounding-error
+//                         norms that make the screening margin rigorous.
+//  (2) nn_sweep_kernel    persistent, warp-specialised: TMA producer warp -> tcgen05.mma (M128 x N256 x K48, fp16 in,
+//                         fp32 accumulate in TMEM, double-buffered accumulators) -> 8 epilogue warps that read the
+//                         accumulators with tcgen05.ld and keep, per query row, the running minimum of the SCREENING
+//                         score  s_ij = |b_j|^2 - 2 a_i.b_j  (the norm term rides in 3 extra K columns, so the
+//                         accumulator is the score itself and the epilogue is min-only: 16 FMNMX3 per 32 columns).
+//                         Every 32-column chunk whose minimum is within `margin_i` of the row minimum is recorded.
+//  (3) nn_rescore_kernel  one warp per query row: evaluates the reference's exact fp32 formula (sequential FMA chain,
+//                         then 2*(-c) + |a|^2 + |b|^2) for the recorded chunks only (about one chunk per row) and takes
+//                         the first minimum.  Because margin_i bounds twice the worst-case screening error, the
+//                         reference's argmin is always inside a recorded chunk => indices are bit-exact.
+//
+// The N x M matrix never exists in memory; HBM traffic per pair is the operands (2 x 0.5 MB, L2-resident per scene).
+#include <cuda_fp16.h>
+#include <math.h>
+
 #include "common.cuh"
+
 namespace lmpcr {
-size_t nn_tensor_workspace_bytes(int, int, int, int, int, int) { return 0; }
-int launch_nn_tensor(const float*, int, int, const float*, int, int, int, const int32_t*, int, int32_t*, float*, void*, size_t,
-                     cudaStream_t) {
-  set_error("lmpcr_nn_argmin: LMPCR_NN_TENSOR is not built yet");
-  return LMPCR_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int D = 32;                  // feature dimension of this path
+constexpr int KP = 48;                 // padded K of the fp16 operands: 32 features + 16 (norm terms / ones / zeros)
+constexpr int RG_BYTES = 8 * KP * 2;   // 768: one 8-row group = KP/8 core matrices of 128 B, adjacent along K
+constexpr int TM = 128;                // query rows per stripe (UMMA M)
+constexpr int TN = 256;                // target rows per tile   (UMMA N)
+constexpr int STAGES = 4;              // TMA ring depth for target tiles
+constexpr int CHUNK = 32;              // columns per bookkeeping chunk (= one tcgen05.ld.32x32b.x32)
+constexpr int CAP = 16;                // ring of candidate chunks per (row, column half)
+constexpr int EPI_THREADS = 256;
+constexpr int NTHREADS = 128 + EPI_THREADS;
+constexpr int A_BYTES = TM * KP * 2;   // 12288
+constexpr int B_BYTES = TN * KP * 2;   // 24576
+constexpr uint32_t OVERFLOW = 0xFFFFu;
+constexpr float PAD_NORM = 60000.0f;   // |b|^2 stand-in of padding rows: never a minimum
+
+struct RowStat { float u, v, na; };    // u = 2|da|, v = 2|a_hat|, na = |a|  (all rounded up)
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1u << 26)) __trap();   // a lost arrival becomes an error instead of a hung GPU
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t of the warp = TMEM lane base+t)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 B stored as 128 contiguous bytes;
+// LBO = byte distance between core matrices adjacent along K (128), SBO = between 8-row groups along M/N (768).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = 256
+constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+// ---------------------------------------------------------------- (1) operand preparation
+// One thread per (padded) row.  form_q: [-2*a_hat (32) | 1 1 1 | 0..]   form_b: [b_hat (32) | dn_hi dn_mid dn_lo | 0..]
+__global__ void nn_prep_kernel(const float* __restrict__ feat, int n_sets, int n, int rows_pad, uint8_t* __restrict__ form_q,
+                               uint8_t* __restrict__ form_b, float4* __restrict__ feat_t, float* __restrict__ sqn,
+                               RowStat* __restrict__ rstat, int* __restrict__ set_bmax, int* __restrict__ set_dbmax,
+                               int* __restrict__ unsupported) {
+  const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (size_t)n_sets * rows_pad) return;
+  const int s = (int)(r / rows_pad), i = (int)(r - (size_t)s * rows_pad);
+  const bool valid = i < n;
+  float f[D];
+  if (valid) {
+    const float4* src = reinterpret_cast<const float4*>(feat + ((size_t)s * n + i) * D);
+#pragma unroll
+    for (int k = 0; k < D / 4; ++k) {
+      const float4 v = __ldg(src + k);
+      f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < D; ++k) f[k] = 0.f;
+  }
+  // exact squared norm in torch's evaluation order (see nn_search.cu::sqnorm_kernel)
+  float t[8];
+#pragma unroll
+  for (int c = 0; c < D / 8; ++c)
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const float sq = __fmul_rn(f[8 * c + l], f[8 * c + l]);
+      t[l] = (c == 0) ? sq : __fadd_rn(t[l], sq);
+    }
+  float sn = t[0];
+#pragma unroll
+  for (int l = 1; l < 8; ++l) sn = __fadd_rn(sn, t[l]);
+
+  __align__(16) __half hq[KP];
+  __align__(16) __half hb[KP];
+  float nda2 = 0.f, nah2 = 0.f, na2 = 0.f, amax = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const __half h = __float2half_rn(f[k]);
+    const float fh = __half2float(h);
+    const float dl = f[k] - fh;
+    nda2 = fmaf(dl, dl, nda2);
+    nah2 = fmaf(fh, fh, nah2);
+    na2 = fmaf(f[k], f[k], na2);
+    amax = fmaxf(amax, fabsf(f[k]));
+    hb[k] = h;
+    hq[k] = __float2half_rn(-2.0f * fh);   // exact (power-of-two scaling) unless it overflows -> `unsupported`
+  }
+#pragma unroll
+  for (int k = D; k < KP; ++k) { hq[k] = __float2half_rn(0.f); hb[k] = __float2half_rn(0.f); }
+  if (valid) {
+    hq[D] = hq[D + 1] = hq[D + 2] = __float2half_rn(1.0f);
+    const __half h1 = __float2half_rn(sn);
+    const float r1 = sn - __half2float(h1);
+    const __half h2 = __float2half_rn(r1);
+    const float r2 = r1 - __half2float(h2);
+    hb[D] = h1; hb[D + 1] = h2; hb[D + 2] = __float2half_rn(r2);
+    if (!(amax < 16000.f) || !(sn < 30000.f)) *unsupported = 1;   // outside the fp16 operand range: rescoring scans every chunk
+  } else {
+    hb[D] = __float2half_rn(PAD_NORM);
+  }
+  // UMMA canonical K-major layout: 8-row group rg -> RG_BYTES; inside: core matrix kc at kc*128, row (i%8) at *16
+  const size_t base = (r >> 3) * RG_BYTES + (size_t)(i & 7) * 16;
+#pragma unroll
+  for (int kc = 0; kc < KP / 8; ++kc) {
+    *reinterpret_cast<uint4*>(form_q + base + kc * 128) = *reinterpret_cast<const uint4*>(&hq[kc * 8]);
+    *reinterpret_cast<uint4*>(form_b + base + kc * 128) = *reinterpret_cast<const uint4*>(&hb[kc * 8]);
+  }
+  // chunk-transposed fp32 copy: [chunk of 32 rows][k/4][row in chunk] float4
+  float4* ft = feat_t + (r >> 5) * 256 + (r & 31);
+#pragma unroll
+  for (int kq = 0; kq < 8; ++kq) ft[kq * 32] = make_float4(f[4 * kq], f[4 * kq + 1], f[4 * kq + 2], f[4 * kq + 3]);
+  sqn[r] = valid ? sn : PAD_NORM;
+  const float up = 1.0f + 1e-4f;
+  const float na = sqrtf(na2) * up, nda = sqrtf(nda2) * up, nah = sqrtf(nah2) * up;
+  rstat[r] = RowStat{2.0f * nda, 2.0f * nah, na};
+  if (valid) {
+    atomicMax(set_bmax + s, __float_as_int(na));
+    atomicMax(set_dbmax + s, __float_as_int(nda));
+  }
+}
+
+// ---------------------------------------------------------------- (2) tcgen05 sweep
+struct SweepArgs {
+  const uint8_t* form_q; const uint8_t* form_b;
+  const RowStat* rstat_q; const int* set_bmax; const int* set_dbmax;
+  const int32_t* jobs; int n_jobs; int n_q, rows_pad_q, n_b, rows_pad_b;
+  uint2* cand;             // [n_jobs, n_q, 2]  packed candidate chunks per (row, column half)
+  float* dbg_scores;       // optional [n_jobs, n_q, rows_pad_b] raw screening scores (tests)
+  float* approx_min;       // optional [n_jobs, n_q]
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + A_BYTES;
+  uint2* ring = reinterpret_cast<uint2*>(sB + STAGES * B_BYTES);            // [CAP][EPI_THREADS]
+  float* rowmin = reinterpret_cast<float*>(ring + CAP * EPI_THREADS);       // [2][TM]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowmin + 2 * TM);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t A_FULL = bar0 + 8u * (2 * STAGES), A_EMPTY = bar0 + 8u * (2 * STAGES + 1);
+  auto T_FULL = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  auto T_EMPTY = [&](int a) { return bar0 + 8u * (2 * STAGES + 4 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_stripes = (g.n_q + TM - 1) / TM;
+  const int n_tiles = g.rows_pad_b / TN;
+  const long long n_items = (long long)g.n_jobs * n_stripes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    mbar_init(A_FULL, 1); mbar_init(A_EMPTY, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(T_FULL(a), 1); mbar_init(T_EMPTY(a), EPI_THREADS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: all 512 columns = two 256-column accumulator stages
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
+      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int job = (int)(item / n_stripes), stripe = (int)(item - (long long)job * n_stripes);
+        const int qs = __ldg(g.jobs + 2 * job), bs = __ldg(g.jobs + 2 * job + 1);
+        mbar_wait(A_EMPTY, a_phase ^ 1);
+        mbar_expect_tx(A_FULL, A_BYTES);
+        bulk_g2s(smem_u32(sA), g.form_q + ((size_t)qs * g.rows_pad_q + (size_t)stripe * TM) / 8 * RG_BYTES, A_BYTES, A_FULL);
+        const uint8_t* bsrc = g.form_b + (size_t)bs * g.rows_pad_b / 8 * RG_BYTES;
+        for (int t = 0; t < n_tiles; ++t) {
+          mbar_wait(EMPTY(stage), phase ^ 1);
+          mbar_expect_tx(FULL(stage), B_BYTES);
+          bulk_g2s(smem_u32(sB + stage * B_BYTES), bsrc + (size_t)t * B_BYTES, B_BYTES, FULL(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        a_phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0, acc = 0; uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+      const uint32_t sA_u = smem_u32(sA);
+      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait(A_FULL, a_phase);
+        for (int t = 0; t < n_tiles; ++t) {
+          mbar_wait(T_EMPTY(acc), acc_phase ^ 1);
+          mbar_wait(FULL(stage), phase);
+          tc_fence_after();
+          const uint32_t sB_u = smem_u32(sB + stage * B_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < KP / 16; ++kk)   // one K=16 step = two core matrices = 256 B further along K
+            tc_mma_f16(tmem_base + acc * TN, make_desc(sA_u + kk * 256, 128, RG_BYTES), make_desc(sB_u + kk * 256, 128, RG_BYTES),
+                       IDESC, kk > 0 ? 1u : 0u);
+          tc_commit(EMPTY(stage));     // smem slot reusable once these MMAs have read it
+          tc_commit(T_FULL(acc));      // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        }
+        tc_commit(A_EMPTY);
+        a_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: 8 warps, thread = (row, column half) =====================
+    const int te = threadIdx.x - 128;
+    const int half = te >> 7;                 // 0: columns 0..127 of a tile, 1: columns 128..255
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int job = (int)(item / n_stripes), stripe = (int)(item - (long long)job * n_stripes);
+      const int qs = __ldg(g.jobs + 2 * job), bs = __ldg(g.jobs + 2 * job + 1);
+      const int grow = stripe * TM + row;
+      float margin = 0.f;
+      if (grow < g.n_q) {
+        const RowStat rs = g.rstat_q[(size_t)qs * g.rows_pad_q + grow];
+        const float bmax = __int_as_float(__ldg(g.set_bmax + bs)), dbmax = __int_as_float(__ldg(g.set_dbmax + bs));
+        const float E = rs.u * bmax + rs.v * dbmax + 2e-5f * (rs.na * rs.na + rs.na * bmax + bmax * bmax) + 1e-30f;
+        margin = 2.02f * E;
+      }
+      float run = INFINITY;
+      uint32_t cnt = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(T_FULL(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN + half * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tc_ld32(taddr + c * CHUNK, v);
+          if (g.dbg_scores && grow < g.n_q) {
+            float* o = g.dbg_scores + ((size_t)job * g.n_q + grow) * g.rows_pad_b + (size_t)t * TN + half * 128 + c * CHUNK;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = v[i];
+          }
+          float m = min3(v[0], v[1], v[2]);
+#pragma unroll
+          for (int i = 3; i < 31; i += 2) m = min3(m, v[i], v[i + 1]);
+          m = fminf(m, v[31]);
+          run = fminf(run, m);
+          if (m <= run + margin) {
+            ring[(cnt & (CAP - 1)) * EPI_THREADS + te] = make_uint2(__float_as_uint(m), (uint32_t)(t * 8 + half * 4 + c));
+            ++cnt;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(T_EMPTY(acc));
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+      // combine the two column halves of every row, then keep the chunks within `margin` of the row minimum
+      rowmin[half * TM + row] = run;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float fin = fminf(rowmin[row], rowmin[TM + row]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (grow < g.n_q) {
+        const float thr = fin + margin;
+        uint32_t ids[3] = {0, 0, 0}, k = 0;
+        bool over = cnt > CAP;
+        if (!over) {
+          for (uint32_t e = 0; e < cnt; ++e) {
+            const uint2 en = ring[e * EPI_THREADS + te];
+            if (__uint_as_float(en.x) <= thr) {
+              if (k < 3) ids[k] = en.y;
+              ++k;
+            }
+          }
+          over = k > 3;
+        }
+        const uint32_t c16 = over ? OVERFLOW : k;
+        g.cand[((size_t)job * g.n_q + grow) * 2 + half] = make_uint2(c16 | (ids[0] << 16), ids[1] | (ids[2] << 16));
+        if (g.approx_min && half == 0) g.approx_min[(size_t)job * g.n_q + grow] = fin;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- (3) exact fp32 rescoring, one warp per query row
+__global__ void __launch_bounds__(256)
+nn_rescore_kernel(const float* __restrict__ q_feat, const float* __restrict__ sqn_q, int n_q, int rows_pad_q,
+                  const float4* __restrict__ featT_b, const float* __restrict__ sqn_b, int n_b, int rows_pad_b,
+                  const int32_t* __restrict__ jobs, int n_jobs, const uint2* __restrict__ cand, const int* __restrict__ unsupported,
+                  int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= (long long)n_jobs * n_q) return;
+  const int lane = threadIdx.x & 31;
+  const int job = (int)(w / n_q), row = (int)(w - (long long)job * n_q);
+  const int qs = __ldg(jobs + 2 * job), bs = __ldg(jobs + 2 * job + 1);
+  float a[D];
+  {
+    const float4* src = reinterpret_cast<const float4*>(q_feat + ((size_t)qs * n_q + row) * D);
+#pragma unroll
+    for (int k = 0; k < D / 4; ++k) {
+      const float4 v = __ldg(src + k);
+      a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+    }
+  }
+  const float an = __ldg(sqn_q + (size_t)qs * rows_pad_q + row);
+  const float4* tb = featT_b + (size_t)bs * rows_pad_b * 8;    // rows_pad_b/32 chunks * 256 float4
+  const float* nb = sqn_b + (size_t)bs * rows_pad_b;
+  float best = INFINITY;
+  int bj = 0x7fffffff;
+  auto score_chunk = [&](int ch) {
+    const int j = ch * CHUNK + lane;
+    const float4* src = tb + (size_t)ch * 256 + lane;
+    float c = 0.f;
+#pragma unroll
+    for (int kq = 0; kq < 8; ++kq) {
+      const float4 v = __ldg(src + kq * 32);
+      c = fmaf(a[4 * kq], v.x, c); c = fmaf(a[4 * kq + 1], v.y, c); c = fmaf(a[4 * kq + 2], v.z, c); c = fmaf(a[4 * kq + 3], v.w, c);
+    }
+    const float d = __fadd_rn(__fadd_rn(__fmul_rn(2.0f, -c), an), __ldg(nb + j));
+    if (j < n_b && (d < best || (d == best && j < bj))) { best = d; bj = j; }
+  };
+  const bool scan_all = (*unsupported != 0);
+  const int n_chunks = (n_b + CHUNK - 1) / CHUNK;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const uint2 e = __ldg(cand + ((size_t)job * n_q + row) * 2 + half);
+    const uint32_t c16 = e.x & 0xFFFFu;
+    if (scan_all || c16 == OVERFLOW) {
+      for (int ch = 0; ch < n_chunks; ++ch)
+        if (((ch >> 2) & 1) == half) score_chunk(ch);
+    } else {
+      if (c16 > 0) score_chunk((int)(e.x >> 16));
+      if (c16 > 1) score_chunk((int)(e.y & 0xFFFFu));
+      if (c16 > 2) score_chunk((int)(e.y >> 16));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (od < best || (od == best && oj < bj)) { best = od; bj = oj; }
+  }
+  if (lane == 0) {
+    idx_out[(size_t)job * n_q + row] = bj;
+    if (dist_out) dist_out[(size_t)job * n_q + row] = best;
+  }
+}
+
+// ---------------------------------------------------------------- host side
+struct Prep {
+  uint8_t *form_q, *form_b; float4* feat_t; float* sqn; RowStat* rstat; int *bmax, *dbmax;
+  int rows_pad;
+};
+
+size_t prep_bytes(int n_sets, int n) {
+  const size_t rows = (size_t)n_sets * align_up((size_t)n, TN);
+  return align_up(rows * KP * 2, 256) * 2 + align_up(rows * D * 4, 256) + align_up(rows * 4, 256) + align_up(rows * sizeof(RowStat), 256) +
+         2 * align_up((size_t)n_sets * 4, 256);
+}
+
+Prep carve_prep(char*& p, int n_sets, int n) {
+  Prep P;
+  P.rows_pad = (int)align_up((size_t)n, TN);
+  const size_t rows = (size_t)n_sets * P.rows_pad;
+  P.form_q = reinterpret_cast<uint8_t*>(p); p += align_up(rows * KP * 2, 256);
+  P.form_b = reinterpret_cast<uint8_t*>(p); p += align_up(rows * KP * 2, 256);
+  P.feat_t = reinterpret_cast<float4*>(p); p += align_up(rows * D * 4, 256);
+  P.sqn = reinterpret_cast<float*>(p); p += align_up(rows * 4, 256);
+  P.rstat = reinterpret_cast<RowStat*>(p); p += align_up(rows * sizeof(RowStat), 256);
+  P.bmax = reinterpret_cast<int*>(p); p += align_up((size_t)n_sets * 4, 256);
+  P.dbmax = reinterpret_cast<int*>(p); p += align_up((size_t)n_sets * 4, 256);
+  return P;
+}
+
+int run_prep(const float* feat, int n_sets, int n, const Prep& P, int* unsupported, cudaStream_t st) {
+  cudaMemsetAsync(P.bmax, 0, (size_t)n_sets * 4, st);
+  cudaMemsetAsync(P.dbmax, 0, (size_t)n_sets * 4, st);
+  const size_t rows = (size_t)n_sets * P.rows_pad;
+  nn_prep_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(feat, n_sets, n, P.rows_pad, P.form_q, P.form_b, P.feat_t, P.sqn, P.rstat,
+                                                                P.bmax, P.dbmax, unsupported);
+  return check_launch("nn_prep_kernel");
+}
+
+constexpr size_t SWEEP_SMEM = A_BYTES + (size_t)STAGES * B_BYTES + (size_t)CAP * EPI_THREADS * 8 + 2 * TM * 4 + 16 * 8 + 16;
+
+}  // namespace
+
+size_t nn_tensor_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, int dim, int n_jobs) {
+  (void)dim;
+  return prep_bytes(n_q_sets, n_q) + prep_bytes(n_b_sets, n_b) + align_up((size_t)n_jobs * n_q * 16, 256) + 256;
+}
+
+int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
+                        const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, float* dbg_scores, float* approx_min,
+                        void* ws, size_t ws_bytes, cudaStream_t st) {
+  LMPCR_REQUIRE(dim == D, LMPCR_ERR_UNSUPPORTED, "lmpcr_nn_argmin: LMPCR_NN_TENSOR needs dim == 32 (got %d)", dim);
+  LMPCR_REQUIRE(n_b <= 65535 * CHUNK, LMPCR_ERR_UNSUPPORTED, "lmpcr_nn_argmin: too many target rows for the tensor path");
+  LMPCR_REQUIRE(ws_bytes >= nn_tensor_workspace_bytes(n_q_sets, n_q, n_b_sets, n_b, dim, n_jobs), LMPCR_ERR_WORKSPACE, "lmpcr_nn_argmin: workspace too small");
+  LMPCR_REQUIRE(((uintptr_t)ws & 255) == 0, LMPCR_ERR_ARG, "lmpcr_nn_argmin: workspace must be 256-byte aligned");
+  char* p = reinterpret_cast<char*>(ws);
+  int* unsupported = reinterpret_cast<int*>(p); p += 256;
+  cudaMemsetAsync(unsupported, 0, 4, st);
+  const bool same = (q_feat == b_feat) && n_q_sets == n_b_sets && n_q == n_b;
+  Prep PQ = carve_prep(p, n_q_sets, n_q);
+  LMPCR_TRY(run_prep(q_feat, n_q_sets, n_q, PQ, unsupported, st));
+  Prep PB = PQ;
+  if (!same) {
+    PB = carve_prep(p, n_b_sets, n_b);
+    LMPCR_TRY(run_prep(b_feat, n_b_sets, n_b, PB, unsupported, st));
+  } else {
+    char* skip = p; (void)carve_prep(skip, n_b_sets, n_b); p = skip;
+  }
+  uint2* cand = reinterpret_cast<uint2*>(p);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(nn_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
+    LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "nn_sweep_kernel: cannot reserve %zu bytes of shared memory: %s", SWEEP_SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  SweepArgs a;
+  a.form_q = PQ.form_q; a.form_b = PB.form_b; a.rstat_q = PQ.rstat; a.set_bmax = PB.bmax; a.set_dbmax = PB.dbmax;
+  a.jobs = jobs; a.n_jobs = n_jobs; a.n_q = n_q; a.rows_pad_q = PQ.rows_pad; a.n_b = n_b; a.rows_pad_b = PB.rows_pad;
+  a.cand = cand; a.dbg_scores = dbg_scores; a.approx_min = approx_min;
+  const long long items = (long long)n_jobs * ((n_q + TM - 1) / TM);
+  const int grid = (int)(items < sm_count() ? items : sm_count());
+  nn_sweep_kernel<<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
+  LMPCR_TRY(check_launch("nn_sweep_kernel"));
+  const long long warps = (long long)n_jobs * n_q;
+  nn_rescore_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(q_feat, PQ.sqn, n_q, PQ.rows_pad, PB.feat_t, PB.sqn, n_b, PB.rows_pad, jobs,
+                                                                         n_jobs, cand, unsupported, idx_out, dist_out);
+  return check_launch("nn_rescore_kernel");
+}
+
+int launch_nn_tensor(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
+                     const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  return launch_nn_tensor_ex(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, dim, jobs, n_jobs, idx_out, dist_out, nullptr, nullptr, ws,
+                             ws_bytes, st);
+}
+
 }  // namespace lmpcr

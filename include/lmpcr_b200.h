@@ -55,6 +55,8 @@ extern "C" {
 #define LMPCR_GUARD_PAIR 1  /* per pair (partition-invariant; used by the multi-GPU scene path)            */
 
 int lmpcr_abi_version(void);
+/* Number of kernels this library has launched in this process so far (bench.py's `gpu_launches`). */
+long long lmpcr_launch_count(void);
 const char* lmpcr_last_error(void);
 /* Fills sm_count / l2_bytes / cc_major / cc_minor of the current device (host ints, any may be NULL). */
 int lmpcr_device_info(int* sm_count, int* l2_bytes, int* cc_major, int* cc_minor);
@@ -77,6 +79,14 @@ size_t lmpcr_nn_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, in
 int lmpcr_nn_argmin(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
                     const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, int algo, void* workspace,
                     size_t workspace_bytes, void* stream);
+
+/* Diagnostic twin of lmpcr_nn_argmin(LMPCR_NN_TENSOR): additionally stores the raw tcgen05 screening scores
+ * s_ij = |b_j|^2 - 2 a_i.b_j (fp16 operands, fp32 accumulate) into scores [n_jobs, n_q, ceil(n_b/256)*256] and the
+ * screened row minimum into approx_min [n_jobs, n_q] (either may be NULL).  Used by the tests to localise
+ * descriptor / layout errors; not on the hot path. */
+int lmpcr_nn_tensor_debug(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
+                          const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, float* scores, float* approx_min,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* lib/utils.py:968-992 `pairwise_distance` itself, materialised: src [B,n,dim], dst [B,m,dim] -> out [B,n,m] fp32,
  * bit-identical to the reference's CPU evaluation.  Not on the hot path (which never stores the matrix); kept so

@@ -11,7 +11,7 @@ from oracle import nn_c
 from util import cabi, cu
 
 pytestmark = pytest.mark.gpu
-ALGOS = [cabi.NN_EXACT_SIMT]
+ALGOS = [cabi.NN_EXACT_SIMT, cabi.NN_TENSOR]
 
 
 def _jobs(pairs):
@@ -53,7 +53,7 @@ def test_nn_ties_and_unnormalised(golden_dir, algo):
     ft = np.concatenate([feats[1][:128], feats[1][:128]], axis=0)
     idx = cabi.nn_argmin(cu(feats[0:1]), cu(ft[None]), _jobs([[0, 0]]), algo=algo)
     assert np.array_equal(idx[0].cpu().numpy(), g["ties_idx"])          # first minimum wins
-    if algo == cabi.NN_EXACT_SIMT:                                       # tensor path assumes |f| <= ~1 (FCGF)
+    if True:   # un-normalised features: the screening margin adapts to the actual norms / rounding errors
         rng = np.random.default_rng(99)
         fa = (rng.standard_normal((400, 32)) * 2).astype(np.float32)
         fb = (rng.standard_normal((600, 32)) * 0.5 + 0.3).astype(np.float32)
@@ -121,3 +121,34 @@ def test_mutual_xs_gather_knn(golden_dir):
     assert np.array_equal(mut[0].cpu().numpy().astype(np.uint8), g["s1000_mutual_geo"])
     hard = L.Soft_NN(corr_type="hard", device="cuda")
     assert np.array_equal(hard(f[0:1], f[1:2], x[1:2])[0].cpu().numpy(), xyz[1][o_st])
+
+
+def test_tensor_path_screening_scores_and_margin():
+    """The raw tcgen05 scores equal |b|^2 - 2 a_hat.b_hat (fp16-rounded operands) to fp32 accumulation accuracy, and
+    the fp16 range guard (features outside the operand range) still yields exact indices via full rescoring."""
+    feats, _, _ = O.synth_scene(2, 700, seed=11)
+    fs, ft = feats[0, :300], feats[1, :700]
+    idx, dist, sc, amin = cabi.nn_tensor_debug(cu(fs[None]), cu(ft[None]), _jobs([[0, 0]]))
+    sc = sc[0].cpu().numpy()[:, :700]
+    ah, bh = fs.astype(np.float16).astype(np.float64), ft.astype(np.float16).astype(np.float64)
+    exp = nn_c.sqnorm(ft).astype(np.float64)[None, :] - 2 * ah @ bh.T
+    assert np.abs(sc - exp).max() < 5e-6
+    ri, rd = nn_c.nn_argmin(fs, ft)
+    assert np.array_equal(idx[0].cpu().numpy(), ri) and np.array_equal(dist[0].cpu().numpy(), rd)
+    big = (np.random.default_rng(3).standard_normal((200, 32)) * 3e4).astype(np.float32)     # overflows fp16 operands
+    idx = cabi.nn_argmin(cu(big[None]), cu(big[None, ::-1].copy()), _jobs([[0, 0]]), algo=cabi.NN_TENSOR)
+    assert np.array_equal(idx[0].cpu().numpy(), nn_c.nn_argmin(big, big[::-1].copy())[0])
+
+
+def test_tensor_path_many_jobs_persistent_grid():
+    """More work items than SMs (persistent CTAs loop; barrier phases carry across items) and n not a tile multiple."""
+    feats, _, _ = O.synth_scene(6, 1100, seed=8)
+    pairs = O.enumerate_pairs(6)
+    jobs = np.concatenate([pairs, pairs[:, ::-1]], 0)
+    f = cu(feats)
+    idx, dist = cabi.nn_argmin(f, f, _jobs(jobs.tolist()), algo=cabi.NN_TENSOR, return_dist=True)
+    ref = cabi.nn_argmin(f, f, _jobs(jobs.tolist()), algo=cabi.NN_EXACT_SIMT)
+    assert torch.equal(idx, ref)
+    for j in (0, 7, 29):
+        ri, rd = nn_c.nn_argmin(feats[jobs[j][0]], feats[jobs[j][1]])
+        assert np.array_equal(idx[j].cpu().numpy(), ri) and np.array_equal(dist[j].cpu().numpy(), rd)

@@ -1,0 +1,25 @@
+"""NN stage only: 60 scans x 5000 pts, one chunk of pairs, both directions (used under ncu for per-kernel times)."""
+import sys, os, argparse
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+from oracle import lmpcr_oracle as O
+from util import cabi
+ap = argparse.ArgumentParser()
+ap.add_argument("--scans", type=int, default=60); ap.add_argument("--points", type=int, default=5000)
+ap.add_argument("--pairs", type=int, default=256); ap.add_argument("--algo", type=int, default=1); ap.add_argument("--iters", type=int, default=5)
+a = ap.parse_args()
+feats, xyz, _ = O.synth_scene(a.scans, a.points, seed=41)
+f = torch.from_numpy(feats).cuda()
+pairs = torch.from_numpy(O.enumerate_pairs(a.scans)[: a.pairs]).cuda()
+jobs = torch.cat([pairs, pairs.flip(1)], 0).contiguous()
+for _ in range(2):
+    cabi.nn_argmin(f, f, jobs, algo=a.algo)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.iters):
+    idx = cabi.nn_argmin(f, f, jobs, algo=a.algo)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.iters
+print("algo %d: %.3f ms per call, %.2f us/pair, %.1f TFLOP/s algorithmic" % (a.algo, ms, 1e3 * ms / a.pairs, a.pairs * 2.0 * a.points ** 2 * 32 / ms / 1e9))
