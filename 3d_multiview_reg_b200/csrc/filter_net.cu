@@ -12,6 +12,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tcgemm.cuh"
 
 namespace lmpcr {
 namespace {
@@ -272,6 +273,48 @@ __global__ void softmax_cols_kernel(float* __restrict__ e, int K, int N, int P) 
   for (int k = 0; k < K; ++k) col[(size_t)k * N] *= inv;
 }
 
+// Softmax statistics only (tensor-core path): the normalisation exp(x - max) / sum is applied by the consuming GEMM's
+// operand prologue, so the [P,K,N] embedding is written once and never rewritten.
+__global__ void softmax_rowstats_kernel(const float* __restrict__ e, int L, int n_rows, float* __restrict__ smax, float* __restrict__ sinv) {
+  const int row = blockIdx.x;
+  if (row >= n_rows) return;
+  const float* r = e + (size_t)row * L;
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, __ldg(r + i));
+  m = warp_max(m);
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < nw; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) s += __expf(__ldg(r + i) - m);
+  s = warp_sum(s);
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = 0.f;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    smax[row] = m;
+    sinv[row] = 1.0f / s;
+  }
+}
+
+__global__ void softmax_colstats_kernel(const float* __restrict__ e, int K, int N, int P, float* __restrict__ cmax, float* __restrict__ cinv) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)P * N) return;
+  const int p = (int)(gid / N), n = (int)(gid - (size_t)p * N);
+  const float* col = e + (size_t)p * K * N + n;
+  float m = -INFINITY;
+  for (int k = 0; k < K; ++k) m = fmaxf(m, __ldg(col + (size_t)k * N));
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s += __expf(__ldg(col + (size_t)k * N) - m);
+  cmax[gid] = m;
+  cinv[gid] = 1.0f / s;
+}
+
 // output conv (C -> 1) + tanh/relu weights (oanet.py:174-175) + "any positive weight" flag per pair
 __global__ void logits_kernel(const float* __restrict__ x, long long x_batch, int C, int N, int P,
                               const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ logits,
@@ -300,7 +343,7 @@ __global__ void guard_flag_kernel(const int32_t* __restrict__ anypos, int P, int
 // ------------------------------------------------------------------------------------------------
 // parameter table (state_dict order)
 // ------------------------------------------------------------------------------------------------
-struct ConvP { const float* w; const float* b; };
+struct ConvP { const float* w; const float* b; const uint8_t* blob; };
 struct BNP { const float* g; const float* b; const float* rm; const float* rv; };
 struct PointCNP { bool has_sc; ConvP sc; BNP bn1; ConvP c1; BNP bn2; ConvP c2; };
 struct OAFilterP { BNP bn1; ConvP c1; BNP bn2; ConvP c2; BNP bn3; ConvP c3; };
@@ -313,9 +356,9 @@ struct BlockP {
 struct Cursor {
   const float* const* p; int i, n;
   const float* next() { return (i < n) ? p[i++] : (i++, nullptr); }
-  ConvP conv() { ConvP c; c.w = next(); c.b = next(); return c; }
+  ConvP conv() { ConvP c; c.w = next(); c.b = next(); c.blob = nullptr; return c; }
   BNP bn() { BNP b; b.g = next(); b.b = next(); b.rm = next(); b.rv = next(); return b; }
-  PointCNP pointcn(bool sc) { PointCNP q; q.has_sc = sc; if (sc) q.sc = conv(); else q.sc = ConvP{nullptr, nullptr}; q.bn1 = bn(); q.c1 = conv(); q.bn2 = bn(); q.c2 = conv(); return q; }
+  PointCNP pointcn(bool sc) { PointCNP q; q.has_sc = sc; if (sc) q.sc = conv(); else q.sc = ConvP{nullptr, nullptr, nullptr}; q.bn1 = bn(); q.c1 = conv(); q.bn2 = bn(); q.c2 = conv(); return q; }
 };
 
 void parse_block(Cursor& cur, int half, BlockP& b) {
@@ -342,7 +385,17 @@ struct Work {   // per-group scratch, all fp32
 };
 
 size_t per_pair_floats(int C, int K, int N) {
-  return (size_t)12 * N + (size_t)3 * C * N + (size_t)2 * C * N + (size_t)K * N + (size_t)4 * C * K + 2 * 1024;
+  return (size_t)12 * N + (size_t)3 * C * N + (size_t)2 * C * N + (size_t)K * N + (size_t)4 * C * K + 2 * 1024 + 2 * (size_t)(N > K ? N : K);
+}
+
+// bytes of pre-split weight blobs of one OANBlock (tensor-core path)
+size_t block_blob_bytes(int C, int K, int half) {
+  size_t b = 2 * tc_weight_blob_bytes(K, C);                                      // down / up embedding convs
+  b += (size_t)half * 2 * tc_weight_blob_bytes(C, C);                             // l1_1
+  b += 2 * tc_weight_blob_bytes(C, 2 * C) + tc_weight_blob_bytes(C, C);          // l1_2.0 (shot_cut, conv.3, conv.7)
+  b += (size_t)(half - 1) * 2 * tc_weight_blob_bytes(C, C);                       // l1_2.1..
+  b += (size_t)half * (2 * tc_weight_blob_bytes(C, C) + tc_weight_blob_bytes(K, K));   // l2
+  return align_up(b, 256);
 }
 
 }  // namespace
@@ -365,7 +418,11 @@ static int validate_cfg(const lmpcr_filter_cfg* cfg) {
 }
 
 // fixed part: residuals [P,N] (when the caller passes none) + anypos [P] + flag
-static size_t fixed_bytes(int P, int N) { return align_up((size_t)P * N * 4, 256) + align_up((size_t)P * 4, 256) + 256; }
+static size_t fixed_bytes(const lmpcr_filter_cfg* cfg, int P, int N) {
+  const int half = (cfg->net_depth / (cfg->iter_num + 1)) / 2;
+  return align_up((size_t)P * N * 4, 256) + align_up((size_t)P * 4, 256) + 256 +
+         (cfg->gemm_algo == 1 ? block_blob_bytes(cfg->net_channel, cfg->clusters, half) : 0);
+}
 
 size_t filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int P, int N) {
   if (validate_cfg(cfg) != LMPCR_OK || P <= 0 || N <= 0) return 0;
@@ -373,7 +430,7 @@ size_t filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int P, int N) {
   size_t G = (size_t(1) << 30) / pp;   // ~1 GiB of activations per group of pairs
   if (G < 1) G = 1;
   if (G > (size_t)P) G = P;
-  return fixed_bytes(P, N) + align_up(G * pp, 256) + 4096;
+  return fixed_bytes(cfg, P, N) + align_up(G * pp, 256) + 4096;
 }
 
 int launch_filter_forward(const float* xs, int P, int N, const float* const* params, int n_params,
@@ -383,7 +440,8 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   LMPCR_TRY(validate_cfg(cfg));
   LMPCR_REQUIRE(xs && params && logits && scores && Rout && tout, LMPCR_ERR_ARG, "lmpcr_filter_forward: null pointer");
   LMPCR_REQUIRE(P >= 0 && N >= 1, LMPCR_ERR_ARG, "lmpcr_filter_forward: bad sizes");
-  LMPCR_REQUIRE(cfg->gemm_algo == 0, LMPCR_ERR_UNSUPPORTED, "lmpcr_filter_forward: gemm_algo=%d not built", cfg->gemm_algo);
+  LMPCR_REQUIRE(cfg->gemm_algo == 0 || cfg->gemm_algo == 1, LMPCR_ERR_UNSUPPORTED, "lmpcr_filter_forward: gemm_algo=%d unknown", cfg->gemm_algo);
+  const bool tc = cfg->gemm_algo == 1;
   LMPCR_REQUIRE(n_params == filter_num_params(cfg), LMPCR_ERR_ARG, "lmpcr_filter_forward: expected %d parameter tensors, got %d", filter_num_params(cfg), n_params);
   for (int i = 0; i < n_params; ++i) LMPCR_REQUIRE(params[i], LMPCR_ERR_ARG, "lmpcr_filter_forward: params[%d] is null", i);
   if (P == 0) return LMPCR_OK;
@@ -391,7 +449,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   const int half = (cfg->net_depth / iters) / 2;
   const int Cx = 6 + cfg->side_channel;
   const size_t pp = per_pair_floats(C, K, N) * 4;
-  const size_t fixed = fixed_bytes(P, N);
+  const size_t fixed = fixed_bytes(cfg, P, N);
   LMPCR_REQUIRE(ws && ws_bytes >= fixed + pp + 4096, LMPCR_ERR_WORKSPACE, "lmpcr_filter_forward: workspace %zu < %zu bytes", ws_bytes, fixed + pp + 4096);
   LMPCR_REQUIRE(((uintptr_t)ws & 255) == 0, LMPCR_ERR_ARG, "lmpcr_filter_forward: workspace must be 256-byte aligned");
   int G = (int)((ws_bytes - fixed - 4096) / pp);
@@ -401,6 +459,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   float* res_buf = residuals ? residuals : reinterpret_cast<float*>(base);
   int32_t* anypos = reinterpret_cast<int32_t*>(base + align_up((size_t)P * N * 4, 256));
   int32_t* gflag = reinterpret_cast<int32_t*>(base + align_up((size_t)P * N * 4, 256) + align_up((size_t)P * 4, 256));
+  uint8_t* blob_base = reinterpret_cast<uint8_t*>(base + align_up((size_t)P * N * 4, 256) + align_up((size_t)P * 4, 256) + 256);
   float* f = reinterpret_cast<float*>(base + fixed);
   Work W;
   W.in0 = f; f += (size_t)G * 12 * N;
@@ -415,6 +474,8 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   W.Z = f; f += (size_t)G * C * K;
   W.scale = f; f += (size_t)G * 1024;
   W.shift = f; f += (size_t)G * 1024;
+  float* sm_max = f; f += (size_t)G * (N > K ? N : K);
+  float* sm_inv = f; f += (size_t)G * (N > K ? N : K);
 
   if (status) cudaMemsetAsync(status, 0, (size_t)P * 4, st);
 
@@ -430,6 +491,16 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   auto conv_norm = [&](const float* x, long long xb, int cin, int L, int g, float eps, const BNP& bn, const ConvP& cv, int cout,
                        float* out, long long ob, const float* res, long long rb) -> int {
     LMPCR_TRY(affine(x, xb, cin, L, g, true, eps, bn));
+    if (tc) {
+      TcGemmArgs a{};
+      a.a_blob = cv.blob;
+      a.B = x; a.b_batch = xb; a.b_ld = L; a.b_kmajor = 0;
+      a.C = out; a.c_batch = ob; a.c_i = L; a.c_j = 1;
+      a.Res = res; a.r_batch = rb; a.bias = cv.b;
+      a.prologue = TC_PRO_AFFINE_RELU; a.p0 = W.scale; a.p1 = W.shift; a.p_batch = cin;
+      a.M = cout; a.N = L; a.K = cin;
+      return launch_tcgemm(a, g, st);
+    }
     GemmArgs a{};
     a.A = cv.w; a.a_batch = 0; a.a_i = cin;
     a.B = x; a.b_batch = xb; a.b_k = L; a.b_j = 1;
@@ -440,6 +511,15 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     return gemm(a, g, st);
   };
   auto conv_plain = [&](const float* x, long long xb, int cin, int L, int g, const ConvP& cv, int cout, float* out, long long ob) -> int {
+    if (tc && cv.blob) {
+      TcGemmArgs a{};
+      a.a_blob = cv.blob;
+      a.B = x; a.b_batch = xb; a.b_ld = L; a.b_kmajor = 0;
+      a.C = out; a.c_batch = ob; a.c_i = L; a.c_j = 1;
+      a.bias = cv.b; a.prologue = TC_PRO_NONE;
+      a.M = cout; a.N = L; a.K = cin;
+      return launch_tcgemm(a, g, st);
+    }
     GemmArgs a{};
     a.A = cv.w; a.a_batch = 0; a.a_i = cin;
     a.B = x; a.b_batch = xb; a.b_k = L; a.b_j = 1;
@@ -461,6 +541,21 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   for (int it = 0; it < iters; ++it) {
     BlockP blk;
     parse_block(cur, half, blk);
+    if (tc) {   // split every GEMM weight of this block into bf16 hi/lo tiles in the UMMA layout (conv1 / output stay fp32 SIMT)
+      uint8_t* bp = blob_base;
+      auto prep = [&](ConvP& cv, int M_, int K_) -> int {
+        cv.blob = bp;
+        const int rc = launch_split_weights(cv.w, M_, K_, bp, st);
+        bp += tc_weight_blob_bytes(M_, K_);
+        return rc;
+      };
+      LMPCR_TRY(prep(blk.down_conv, K, C));
+      LMPCR_TRY(prep(blk.up_conv, K, C));
+      for (int i = 0; i < half; ++i) { LMPCR_TRY(prep(blk.l1_1[i].c1, C, C)); LMPCR_TRY(prep(blk.l1_1[i].c2, C, C)); }
+      LMPCR_TRY(prep(blk.l1_2[0].sc, C, 2 * C)); LMPCR_TRY(prep(blk.l1_2[0].c1, C, 2 * C)); LMPCR_TRY(prep(blk.l1_2[0].c2, C, C));
+      for (int i = 1; i < half; ++i) { LMPCR_TRY(prep(blk.l1_2[i].c1, C, C)); LMPCR_TRY(prep(blk.l1_2[i].c2, C, C)); }
+      for (int i = 0; i < half; ++i) { LMPCR_TRY(prep(blk.l2[i].c1, C, C)); LMPCR_TRY(prep(blk.l2[i].c2, K, K)); LMPCR_TRY(prep(blk.l2[i].c3, C, C)); }
+    }
     const int Cin = (it == 0 ? 6 : 8) + cfg->side_channel;
     float* logits_it = logits + (size_t)it * P * N;
     float* scores_it = scores + (size_t)it * P * N;
@@ -487,9 +582,19 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       const float* x11 = W.CAT; const long long x11b = 2 * CN;
       // diff_pool (oanet.py:106-110)
       LMPCR_TRY(conv_norm(x11, x11b, C, N, g, 1e-3f, blk.down_bn, blk.down_conv, K, W.E, (long long)K * N, nullptr, 0));
-      softmax_rows_kernel<<<g * K, 256, 0, st>>>(W.E, N, g * K);
-      LMPCR_TRY(check_launch("softmax_rows_kernel"));
-      {
+      if (tc) {
+        softmax_rowstats_kernel<<<g * K, 256, 0, st>>>(W.E, N, g * K, sm_max, sm_inv);
+        LMPCR_TRY(check_launch("softmax_rowstats_kernel"));
+        TcGemmArgs a{};   // x_down[c,k] = sum_n x11[c,n] * softmax_n(E[k,:])[n]
+        a.A = x11; a.a_batch = x11b; a.a_i = N;
+        a.B = W.E; a.b_batch = (long long)K * N; a.b_ld = N; a.b_kmajor = 1;
+        a.C = W.XD0; a.c_batch = CK; a.c_i = K; a.c_j = 1;
+        a.prologue = TC_PRO_SOFTMAX; a.p0 = sm_max; a.p1 = sm_inv; a.p_batch = K;
+        a.M = C; a.N = K; a.K = N;
+        LMPCR_TRY(launch_tcgemm(a, g, st));
+      } else {
+        softmax_rows_kernel<<<g * K, 256, 0, st>>>(W.E, N, g * K);
+        LMPCR_TRY(check_launch("softmax_rows_kernel"));
         GemmArgs a{};   // x_down[c,k] = sum_n x11[c,n] * S[k,n]
         a.A = x11; a.a_batch = x11b; a.a_i = N;
         a.B = W.E; a.b_batch = (long long)K * N; a.b_k = 1; a.b_j = N;
@@ -503,7 +608,16 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         const OAFilterP& q = blk.l2[i];
         LMPCR_TRY(conv_norm(xd_in, CK, C, K, g, 1e-3f, q.bn1, q.c1, C, W.Y, CK, nullptr, 0));     // conv1 -> Y [g,C,K]
         LMPCR_TRY(affine(nullptr, 0, K, 0, g, false, 0.f, q.bn2));                                 // BN over the cluster axis
-        {
+        if (tc) {
+          TcGemmArgs a{};   // Z[c,k'] = Y[c,k'] + b2[k'] + sum_k W2[k',k] relu(bn_k(Y[c,k]))   (trans(1,2) via strides)
+          a.a_blob = q.c2.blob;
+          a.B = W.Y; a.b_batch = CK; a.b_ld = K; a.b_kmajor = 1;
+          a.C = W.Z; a.c_batch = CK; a.c_i = 1; a.c_j = K;
+          a.Res = W.Y; a.r_batch = CK; a.bias = q.c2.b;
+          a.prologue = TC_PRO_AFFINE_RELU; a.p0 = W.scale; a.p1 = W.shift; a.p_batch = 0;
+          a.M = K; a.N = C; a.K = K;
+          LMPCR_TRY(launch_tcgemm(a, g, st));
+        } else {
           GemmArgs a{};   // Z[c,k'] = Y[c,k'] + b2[k'] + sum_k W2[k',k] relu(bn_k(Y[c,k]))   (trans(1,2) via strides)
           a.A = q.c2.w; a.a_batch = 0; a.a_i = K;
           a.B = W.Y; a.b_batch = CK; a.b_k = 1; a.b_j = K;
@@ -518,9 +632,19 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       }
       // diff_unpool (oanet.py:122-129): x_up -> upper half of the concat buffer
       LMPCR_TRY(conv_norm(x11, x11b, C, N, g, 1e-3f, blk.up_bn, blk.up_conv, K, W.E, (long long)K * N, nullptr, 0));
-      softmax_cols_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g);
-      LMPCR_TRY(check_launch("softmax_cols_kernel"));
-      {
+      if (tc) {
+        softmax_colstats_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g, sm_max, sm_inv);
+        LMPCR_TRY(check_launch("softmax_colstats_kernel"));
+        TcGemmArgs a{};   // x_up[c,n] = sum_k x2[c,k] * softmax_k(E[:,n])[k]
+        a.A = xd_in; a.a_batch = CK; a.a_i = K;
+        a.B = W.E; a.b_batch = (long long)K * N; a.b_ld = N; a.b_kmajor = 0;
+        a.C = W.CAT + CN; a.c_batch = 2 * CN; a.c_i = N; a.c_j = 1;
+        a.prologue = TC_PRO_SOFTMAX; a.p0 = sm_max; a.p1 = sm_inv; a.p_batch = N;
+        a.M = C; a.N = N; a.K = K;
+        LMPCR_TRY(launch_tcgemm(a, g, st));
+      } else {
+        softmax_cols_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g);
+        LMPCR_TRY(check_launch("softmax_cols_kernel"));
         GemmArgs a{};   // x_up[c,n] = sum_k x2[c,k] * S[k,n]
         a.A = xd_in; a.a_batch = CK; a.a_i = K;
         a.B = W.E; a.b_batch = (long long)K * N; a.b_k = N; a.b_j = 1;

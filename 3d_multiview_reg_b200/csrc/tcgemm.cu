@@ -1,0 +1,327 @@
+// Split-BF16 tensor-core GEMM for the filtering network (tcgen05 / TMEM / TMA bulk copies), sm_100a.
+//
+//   C[p,i,j] = sum_k A[p,i,k] * f(B[p,k,j]) + bias[i] + Res[p,i,j]
+//
+// Every fp32 operand value x is split as x = hi + lo (two bf16 numbers, 16 significant bits) and the product is
+// evaluated as A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with fp32 accumulation in TMEM -- the 1x1 convolutions of
+// lib/filtering/oanet.py need fp32-faithful products (TF32 moves the estimated pose by 4e-3 rad).
+//
+// Persistent, warp-specialised CTA (512 threads), one 128x128 output tile at a time, K in chunks of 64:
+//   warp 0      TMA bulk copies of the pre-split weight tile (A) into the stage          (only when A is a weight blob)
+//   warp 1      tcgen05.mma issue: per 64-chunk 4 K-steps x 3 products, M128 x N128 x K16, accumulators in TMEM
+//   warps 4-7   epilogue: tcgen05.ld -> +bias +residual -> shared-memory transpose -> coalesced stores
+//   warps 8-15  operand producers: load fp32 activations, apply the fused prologue (InstanceNorm+BatchNorm affine and
+//               ReLU, or the softmax normalisation exp(x-max)/sum), split into hi/lo bf16 and store them straight
+//               in the UMMA canonical (no-swizzle) layout -- normalised activations never touch HBM.
+// Pipelines: 3-stage shared-memory ring (full/empty mbarriers), double-buffered TMEM accumulator (128 columns each).
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "tc_ptx.cuh"
+#include "tcgemm.cuh"
+
+namespace lmpcr {
+namespace {
+
+constexpr int TM = 128, TN = 128, KC = 64;
+constexpr int STAGES = 3;
+constexpr int OP_BYTES = 128 * KC * 2;       // one bf16 operand tile (hi or lo): 16 KB
+constexpr int STAGE_BYTES = 4 * OP_BYTES;    // [A_hi][A_lo][B_hi][B_lo]
+constexpr int N_PROD_WARPS = 8;
+constexpr int FIRST_EPI_WARP = 4, FIRST_PROD_WARP = 8;
+constexpr int NTHREADS = 32 * (FIRST_PROD_WARP + N_PROD_WARPS);   // 512
+constexpr uint32_t K_LBO = 128, K_SBO = (KC / 8) * 128;           // K-major operand: k-groups adjacent, 8-row groups 1 KB apart
+constexpr uint32_t MN_SBO = 128, MN_LBO = (TN / 8) * 128;         // MN-major operand: j-groups adjacent, k-groups 2 KB apart
+constexpr int TR_LD = 33;                                         // padded row of the epilogue transpose buffer
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 4 * 32 * TR_LD * 4 + 16 * 8 + 16;
+
+__device__ __forceinline__ void split8_store(const float (&x)[8], uint8_t* hi_dst, uint8_t* lo_dst) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __nv_bfloat162 hv = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
+    const float2 hf = __bfloat1622float2(hv);
+    const __nv_bfloat162 lv = __floats2bfloat162_rn(x[2 * q] - hf.x, x[2 * q + 1] - hf.y);
+    h[q] = *reinterpret_cast<const uint32_t*>(&hv);
+    l[q] = *reinterpret_cast<const uint32_t*>(&lv);
+  }
+  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// 8 consecutive floats starting at src; the first `nvalid` (0..8) are in range, the rest read as 0
+__device__ __forceinline__ void load8(const float* src, int nvalid, float (&x)[8]) {
+  if (nvalid >= 8 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = (e < nvalid) ? __ldg(src + e) : 0.f;
+  }
+}
+
+// fp32 weights [M,K] (k contiguous) -> per (m-tile, k-chunk) blob [hi 16 KB | lo 16 KB], K-major canonical layout
+__global__ void split_weights_kernel(const float* __restrict__ W, int M, int K, uint8_t* __restrict__ blob) {
+  const int n_kc = (K + KC - 1) / KC, n_mt = (M + TM - 1) / TM;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, k-group of 8)
+  const long long total = (long long)n_mt * TM * n_kc * (KC / 8);
+  if (gid >= total) return;
+  const int kg_all = (int)(gid % (n_kc * (KC / 8)));
+  const int row = (int)(gid / (n_kc * (KC / 8)));
+  const int mt = row / TM, r = row % TM, kc = kg_all / (KC / 8), kg = kg_all % (KC / 8);
+  const int k0 = kc * KC + kg * 8;
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] = (row < M && k0 + e < K) ? __ldg(W + (size_t)row * K + k0 + e) : 0.f;
+  uint8_t* base = blob + ((size_t)mt * n_kc + kc) * 2 * OP_BYTES + (r >> 3) * K_SBO + kg * K_LBO + (r & 7) * 16;
+  split8_store(x, base, base + OP_BYTES);
+}
+
+template <bool B_KMAJOR>
+__global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int batch) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* trbuf = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);     // [4 warps][32][TR_LD]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(trbuf + 4 * 32 * TR_LD);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto T_FULL = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto T_EMPTY = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool a_blob = g.a_blob != nullptr;
+  const int tiles_m = (g.M + TM - 1) / TM, tiles_n = (g.N + TN - 1) / TN, n_kc = (g.K + KC - 1) / KC;
+  const long long n_tiles = (long long)batch * tiles_m * tiles_n;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), N_PROD_WARPS + (a_blob ? 1 : 0)); mbar_init(EMPTY(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(T_FULL(a), 1); mbar_init(T_EMPTY(a), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256u);   // two 128-column fp32 accumulators
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](long long tile, int& p, int& mt, int& nt) {
+    const int per = tiles_m * tiles_n;
+    p = (int)(tile / per);
+    const int r = (int)(tile - (long long)p * per);
+    mt = r % tiles_m;            // m fastest: CTAs that share a B tile run next to each other (L2 reuse)
+    nt = r / tiles_m;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer for the weight blob =====================
+    if (a_blob && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int p, mt, nt; decode(tile, p, mt, nt);
+        for (int kc = 0; kc < n_kc; ++kc) {
+          mbar_wait(EMPTY(stage), phase ^ 1);
+          mbar_expect_tx(FULL(stage), 2 * OP_BYTES);
+          bulk_g2s(smem_u32(smem + (size_t)stage * STAGE_BYTES), g.a_blob + ((size_t)mt * n_kc + kc) * 2 * OP_BYTES, 2 * OP_BYTES, FULL(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t IDESC = make_idesc(1, 0, B_KMAJOR ? 0 : 1, TM, TN);
+      constexpr uint32_t B_LBO = B_KMAJOR ? K_LBO : MN_LBO, B_SBO = B_KMAJOR ? K_SBO : MN_SBO;
+      int stage = 0, acc = 0; uint32_t phase = 0, acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(T_EMPTY(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TN;
+        for (int kc = 0; kc < n_kc; ++kc) {
+          mbar_wait(FULL(stage), phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + (size_t)stage * STAGE_BYTES), sB = sA + 2 * OP_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint64_t a_hi = make_desc(sA + ks * 2 * K_LBO, K_LBO, K_SBO);
+            const uint64_t a_lo = make_desc(sA + OP_BYTES + ks * 2 * K_LBO, K_LBO, K_SBO);
+            const uint64_t b_hi = make_desc(sB + ks * 2 * B_LBO, B_LBO, B_SBO);
+            const uint64_t b_lo = make_desc(sB + OP_BYTES + ks * 2 * B_LBO, B_LBO, B_SBO);
+            tc_mma_f16(d_tmem, a_lo, b_hi, IDESC, (kc | ks) ? 1u : 0u);   // small terms first
+            tc_mma_f16(d_tmem, a_hi, b_lo, IDESC, 1u);
+            tc_mma_f16(d_tmem, a_hi, b_hi, IDESC, 1u);
+          }
+          tc_commit(EMPTY(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(T_FULL(acc));
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= FIRST_PROD_WARP) {
+    // ===================== operand producers =====================
+    const int pw = warp - FIRST_PROD_WARP;
+    const int l8 = lane & 7, g4 = lane >> 3;
+    int stage = 0; uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int p, mt, nt; decode(tile, p, mt, nt);
+      const float* Bp = g.B + (long long)p * g.b_batch;
+      const float* Ap = a_blob ? nullptr : g.A + (long long)p * g.a_batch;
+      const float* q0 = g.p0 ? g.p0 + (long long)p * g.p_batch : nullptr;
+      const float* q1 = g.p1 ? g.p1 + (long long)p * g.p_batch : nullptr;
+      for (int kc = 0; kc < n_kc; ++kc) {
+        mbar_wait(EMPTY(stage), phase ^ 1);
+        uint8_t* st_base = smem + (size_t)stage * STAGE_BYTES;
+        // ---- B operand ----
+#pragma unroll 1
+        for (int it = pw; it < 32; it += N_PROD_WARPS) {
+          float x[8];
+          uint32_t off;
+          if (B_KMAJOR) {                      // rows j (128) x k (64); lane: row = l8, k-group = g4
+            const int rg = it >> 1, kb = it & 1;
+            const int j = nt * TN + rg * 8 + l8, k0 = kc * KC + kb * 32 + g4 * 8;
+            const int nv = (j < g.N) ? min(8, max(0, g.K - k0)) : 0;
+            load8(Bp + (long long)j * g.b_ld + k0, nv, x);
+            if (g.prologue == TC_PRO_AFFINE_RELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) if (e < nv) x[e] = fmaxf(fmaf(x[e], __ldg(q0 + k0 + e), __ldg(q1 + k0 + e)), 0.f);
+            } else if (g.prologue == TC_PRO_SOFTMAX) {
+              if (nv > 0) {
+                const float m = __ldg(q0 + j), inv = __ldg(q1 + j);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (e < nv) x[e] = __expf(x[e] - m) * inv;
+              }
+            }
+            off = rg * K_SBO + (kb * 4 + g4) * K_LBO + l8 * 16;
+          } else {                             // k (64) x columns j (128); lane: k = l8, j-group = g4
+            const int kg = it >> 2, nb = it & 3;
+            const int k = kc * KC + kg * 8 + l8, j0 = nt * TN + nb * 32 + g4 * 8;
+            const int nv = (k < g.K) ? min(8, max(0, g.N - j0)) : 0;
+            load8(Bp + (long long)k * g.b_ld + j0, nv, x);
+            if (g.prologue == TC_PRO_AFFINE_RELU) {
+              if (nv > 0) {
+                const float s = __ldg(q0 + k), t = __ldg(q1 + k);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (e < nv) x[e] = fmaxf(fmaf(x[e], s, t), 0.f);
+              }
+            } else if (g.prologue == TC_PRO_SOFTMAX) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) if (e < nv) x[e] = __expf(x[e] - __ldg(q0 + j0 + e)) * __ldg(q1 + j0 + e);
+            }
+            off = (nb * 4 + g4) * MN_SBO + kg * MN_LBO + l8 * 16;
+          }
+          split8_store(x, st_base + 2 * OP_BYTES + off, st_base + 3 * OP_BYTES + off);
+        }
+        // ---- A operand from fp32 activations (k contiguous) ----
+        if (!a_blob) {
+#pragma unroll 1
+          for (int it = pw; it < 32; it += N_PROD_WARPS) {
+            const int rg = it >> 1, kb = it & 1;
+            const int i = mt * TM + rg * 8 + l8, k0 = kc * KC + kb * 32 + g4 * 8;
+            const int nv = (i < g.M) ? min(8, max(0, g.K - k0)) : 0;
+            float x[8];
+            load8(Ap + (long long)i * g.a_i + k0, nv, x);
+            const uint32_t off = rg * K_SBO + (kb * 4 + g4) * K_LBO + l8 * 16;
+            split8_store(x, st_base + off, st_base + OP_BYTES + off);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(FULL(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= FIRST_EPI_WARP) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;
+    float* tr = trbuf + quarter * 32 * TR_LD;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int p, mt, nt; decode(tile, p, mt, nt);
+      float* Cp = g.C + (long long)p * g.c_batch;
+      const float* Rp = g.Res ? g.Res + (long long)p * g.r_batch : nullptr;
+      const int i_own = mt * TM + quarter * 32 + lane;                 // the row this thread owns in TMEM
+      const float bias_own = (g.bias && i_own < g.M) ? __ldg(g.bias + i_own) : 0.f;
+      mbar_wait(T_FULL(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN;
+#pragma unroll 1
+      for (int c = 0; c < TN / 32; ++c) {
+        float v[32];
+        tc_ld32(taddr + c * 32, v);
+        const int jb = nt * TN + c * 32;
+        if (g.c_j == 1) {
+          // rows are contiguous along j: transpose through shared memory so that a warp stores 128 contiguous bytes
+#pragma unroll
+          for (int e = 0; e < 32; ++e) tr[lane * TR_LD + e] = v[e] + bias_own;
+          __syncwarp();
+          const int j = jb + lane;
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const int i = mt * TM + quarter * 32 + r;
+            if (i < g.M && j < g.N) {
+              const long long o = (long long)i * g.c_i + j;
+              float val = tr[r * TR_LD + lane];
+              if (Rp) val += __ldg(Rp + o);
+              Cp[o] = val;
+            }
+          }
+          __syncwarp();
+        } else {
+          // rows are contiguous along i (transposed output, OAFilter's cluster mixing): lanes already coalesce
+          if (i_own < g.M) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int j = jb + e;
+              if (j < g.N) {
+                const long long o = (long long)i_own * g.c_i + (long long)j * g.c_j;
+                float val = v[e] + bias_own;
+                if (Rp) val += __ldg(Rp + o);
+                Cp[o] = val;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(T_EMPTY(acc));
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256u);
+  }
+}
+
+}  // namespace
+
+size_t tc_weight_blob_bytes(int M, int K) {
+  return (size_t)((M + TM - 1) / TM) * ((K + KC - 1) / KC) * 2 * OP_BYTES;
+}
+
+int launch_split_weights(const float* W, int M, int K, uint8_t* blob, cudaStream_t st) {
+  const long long total = (long long)((M + TM - 1) / TM) * TM * ((K + KC - 1) / KC) * (KC / 8);
+  split_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, M, K, blob);
+  return check_launch("split_weights_kernel");
+}
+
+int launch_tcgemm(const TcGemmArgs& a, int batch, cudaStream_t st) {
+  LMPCR_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && batch > 0, LMPCR_ERR_ARG, "tcgemm: bad sizes");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(tcgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(tcgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    LMPCR_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, LMPCR_ERR_LAUNCH, "tcgemm: cannot reserve %zu bytes of shared memory", SMEM_BYTES);
+    attr_set = true;
+  }
+  const long long tiles = (long long)batch * ((a.M + TM - 1) / TM) * ((a.N + TN - 1) / TN);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  if (a.b_kmajor) tcgemm_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, batch);
+  else tcgemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, batch);
+  return check_launch("tcgemm_kernel");
+}
+
+}  // namespace lmpcr

@@ -19,8 +19,12 @@ def _run(net, xs):
         return net({"xs": torch.from_numpy(xs)})          # CPU input, moved inside like oanet.py:234
 
 
+GEMM_ALGOS = [0, 1]      # 0: fp32 CUDA cores, 1: tcgen05 split-bf16 tensor cores
+
+
+@pytest.mark.parametrize("algo", GEMM_ALGOS)
 @pytest.mark.parametrize("name", ["full_p2_n2000", "full_p1_n5000", "small_p3_n64", "guard_p2_n500"])
-def test_oanet_vs_reference_golden(golden_dir, name):
+def test_oanet_vs_reference_golden(golden_dir, name, algo):
     g = np.load(os.path.join(golden_dir, "oanet_golden.npz"))
     P, N, seed, small, guard = [int(v) for v in g[name + "_cfg"]]
     kw = dict(net_channel=32, clusters=16) if small else {}
@@ -28,7 +32,7 @@ def test_oanet_vs_reference_golden(golden_dir, name):
     if guard:
         sd["reg_init.output.bias"] = np.full((1,), -50.0, np.float32)
     xs, _, _ = O.synth_xs(P, N, seed=seed)
-    out = _run(load_oanet(sd, **kw), xs)
+    out = _run(load_oanet(sd, gemm_algo=algo, **kw), xs)
     assert set(["logits", "scores", "rot_est", "trans_est", "latent features", "gradient_flag"]) <= set(out.keys())
     assert len(out["logits"]) == 2 and tuple(out["rot_est"][-1].shape) == (P, 3, 3) and tuple(out["trans_est"][-1].shape) == (P, 3, 1)
     assert tuple(out["latent features"].shape) == (P, kw.get("net_channel", 128), N, 1)
@@ -43,12 +47,13 @@ def test_oanet_vs_reference_golden(golden_dir, name):
         assert np.allclose(out["scores"][0].cpu().numpy(), 1.0 / N)
 
 
+@pytest.mark.parametrize("algo", GEMM_ALGOS)
 @pytest.mark.parametrize("P,N,seed", [(3, 777, 31), (2, 1001, 32), (1, 130, 33)])
-def test_oanet_vs_fp64_oracle_ragged_sizes(P, N, seed):
+def test_oanet_vs_fp64_oracle_ragged_sizes(P, N, seed, algo):
     """Point counts that are not multiples of 4 / of the tile sizes (mutual-filtered inputs have arbitrary N)."""
     sd = O.synth_state_dict(seed)
     xs, _, _ = O.synth_xs(P, N, seed=seed)
-    out = _run(load_oanet(sd), xs)
+    out = _run(load_oanet(sd, gemm_algo=algo), xs)
     o64 = O.oanet_forward(xs, sd, dtype=np.float64)
     for it in range(2):
         assert np.abs(out["logits"][it].cpu().numpy() - o64["logits"][it]).max() < LOGIT_TOL
@@ -62,17 +67,18 @@ def test_oanet_vs_fp64_oracle_ragged_sizes(P, N, seed):
     assert np.abs(out["residuals"].cpu().numpy() - reso).max() < 1e-5
 
 
-def test_group_size_does_not_change_results():
+@pytest.mark.parametrize("algo", GEMM_ALGOS)
+def test_group_size_does_not_change_results(algo):
     """Pairs are processed in workspace-sized groups; per-pair arithmetic must not depend on the grouping."""
     sd = O.synth_state_dict(5)
     xs, _, _ = O.synth_xs(5, 512, seed=5)
-    net = load_oanet(sd)
+    net = load_oanet(sd, gemm_algo=algo)
     cfg = net.cabi_cfg()
     x = cu(xs)
     full = cabi.filter_forward(x, net.param_table(), cfg)
     one_pair = cabi.filter_workspace_bytes(cfg, 1, 512)
     small = cabi.filter_forward(x, net.param_table(), cfg,
-                                workspace=torch.empty(one_pair + 5 * 512 * 4 + 4096, dtype=torch.uint8, device="cuda"))
+                                workspace=torch.empty(one_pair + 5 * 512 * 4 + 8192, dtype=torch.uint8, device="cuda"))
     for k in ("logits", "scores", "R", "t", "residuals", "latent", "conf"):
         assert torch.equal(full[k], small[k]), k
 
