@@ -454,6 +454,10 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   LMPCR_REQUIRE(((uintptr_t)ws & 255) == 0, LMPCR_ERR_ARG, "lmpcr_filter_forward: workspace must be 256-byte aligned");
   int G = (int)((ws_bytes - fixed - 4096) / pp);
   if (G > P) G = P;
+  {  // groups whose tile counts are whole waves: the pooling GEMM has 4 tiles per pair, so G % (SMs/4) == 0
+    const int q = sm_count() / 4;
+    if (q > 0 && G > q) G = G / q * q;
+  }
 
   char* base = reinterpret_cast<char*>(ws);
   float* res_buf = residuals ? residuals : reinterpret_cast<float*>(base);

@@ -24,7 +24,7 @@ namespace lmpcr {
 namespace {
 
 constexpr int TM = 128, TN = 128, KC = 64;
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;
 constexpr int OP_BYTES = 128 * KC * 2;       // one bf16 operand tile (hi or lo): 16 KB
 constexpr int STAGE_BYTES = 4 * OP_BYTES;    // [A_hi][A_lo][B_hi][B_lo]
 constexpr int N_PROD_WARPS = 8;
@@ -32,8 +32,18 @@ constexpr int FIRST_EPI_WARP = 4, FIRST_PROD_WARP = 8;
 constexpr int NTHREADS = 32 * (FIRST_PROD_WARP + N_PROD_WARPS);   // 512
 constexpr uint32_t K_LBO = 128, K_SBO = (KC / 8) * 128;           // K-major operand: k-groups adjacent, 8-row groups 1 KB apart
 constexpr uint32_t MN_SBO = 128, MN_LBO = (TN / 8) * 128;         // MN-major operand: j-groups adjacent, k-groups 2 KB apart
-constexpr int TR_LD = 33;                                         // padded row of the epilogue transpose buffer
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 4 * 32 * TR_LD * 4 + 16 * 8 + 16;
+constexpr int TR_LD = 33;                                         // padded row of the (generic) epilogue transpose buffer
+constexpr int HALF_COLS = 64;                                     // the TMA epilogue works on half tiles (128 rows x 64 columns)
+constexpr int STG_ROW = HALF_COLS * 4 + 16;                       // 272 B: 16-byte aligned, conflict-free for float4 at one row per lane
+constexpr int STG_BYTES = TM * STG_ROW;                           // 34816
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 2 * STG_BYTES + 4 * 32 * TR_LD * 4 + 2 * 128 * 8 + 16 * 8 + 16;
+
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void split8_store(const float (&x)[8], uint8_t* hi_dst, uint8_t* lo_dst) {
   uint32_t h[4], l[4];
@@ -80,8 +90,10 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int M, int K, 
 template <bool B_KMAJOR>
 __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int batch) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  float* trbuf = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);     // [4 warps][32][TR_LD]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(trbuf + 4 * 32 * TR_LD);
+  uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;                                  // [2 halves][128 rows][STG_ROW]
+  float* trbuf = reinterpret_cast<float*>(stg + 2 * STG_BYTES);                        // [4 warps][32][TR_LD]
+  uint64_t* rowbars = reinterpret_cast<uint64_t*>(trbuf + 4 * 32 * TR_LD);             // [2 halves][128 rows]
+  uint64_t* bars = rowbars + 2 * 128;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const uint32_t bar0 = smem_u32(bars);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -97,8 +109,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), N_PROD_WARPS + (a_blob ? 1 : 0)); mbar_init(EMPTY(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(T_FULL(a), 1); mbar_init(T_EMPTY(a), 128); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x < 256) mbar_init(smem_u32(rowbars + threadIdx.x), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256u);   // two 128-column fp32 accumulators
   tc_fence_before();
   __syncthreads();
@@ -160,132 +173,245 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
     }
   } else if (warp >= FIRST_PROD_WARP) {
     // ===================== operand producers =====================
+    // Software-pipelined: the fp32 values of the NEXT 64-chunk are fetched into registers right after the current
+    // chunk has been converted, so the global-memory round trip overlaps the wait for a free stage.
     const int pw = warp - FIRST_PROD_WARP;
     const int l8 = lane & 7, g4 = lane >> 3;
-    int stage = 0; uint32_t phase = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    constexpr int NIT = 32 / N_PROD_WARPS;     // warp-iterations per operand chunk
+    float xb[NIT][8];
+    int nvb[NIT];
+    auto fetch_b = [&](long long tile, int kc) {
       int p, mt, nt; decode(tile, p, mt, nt);
       const float* Bp = g.B + (long long)p * g.b_batch;
+#pragma unroll
+      for (int u = 0; u < NIT; ++u) {
+        const int it = pw + u * N_PROD_WARPS;
+        if (B_KMAJOR) {                      // rows j (128) x k (64); lane: row = l8, k-group = g4
+          const int rg = it >> 1, kb = it & 1;
+          const int j = nt * TN + rg * 8 + l8, k0 = kc * KC + kb * 32 + g4 * 8;
+          nvb[u] = (j < g.N) ? min(8, max(0, g.K - k0)) : 0;
+          load8(Bp + (long long)j * g.b_ld + k0, nvb[u], xb[u]);
+        } else {                             // k (64) x columns j (128); lane: k = l8, j-group = g4
+          const int kg = it >> 2, nb = it & 3;
+          const int k = kc * KC + kg * 8 + l8, j0 = nt * TN + nb * 32 + g4 * 8;
+          nvb[u] = (k < g.K) ? min(8, max(0, g.N - j0)) : 0;
+          load8(Bp + (long long)k * g.b_ld + j0, nvb[u], xb[u]);
+        }
+      }
+    };
+    int stage = 0; uint32_t phase = 0;
+    if ((long long)blockIdx.x < n_tiles) fetch_b(blockIdx.x, 0);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int p, mt, nt; decode(tile, p, mt, nt);
       const float* Ap = a_blob ? nullptr : g.A + (long long)p * g.a_batch;
       const float* q0 = g.p0 ? g.p0 + (long long)p * g.p_batch : nullptr;
       const float* q1 = g.p1 ? g.p1 + (long long)p * g.p_batch : nullptr;
       for (int kc = 0; kc < n_kc; ++kc) {
+        // prologue parameters of this chunk (L1/L2 hits; fetched before the wait)
+        float ps[NIT][8], pt[NIT][8];
+#pragma unroll
+        for (int u = 0; u < NIT; ++u) {
+          const int it = pw + u * N_PROD_WARPS;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { ps[u][e] = 0.f; pt[u][e] = 0.f; }
+          if (g.prologue != TC_PRO_NONE && nvb[u] > 0) {
+            if (B_KMAJOR) {
+              const int rg = it >> 1, kb = it & 1;
+              const int j = nt * TN + rg * 8 + l8, k0 = kc * KC + kb * 32 + g4 * 8;
+              if (g.prologue == TC_PRO_AFFINE_RELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (e < nvb[u]) { ps[u][e] = __ldg(q0 + k0 + e); pt[u][e] = __ldg(q1 + k0 + e); }
+              } else {
+                ps[u][0] = __ldg(q0 + j); pt[u][0] = __ldg(q1 + j);
+              }
+            } else {
+              const int kg = it >> 2, nb = it & 3;
+              const int k = kc * KC + kg * 8 + l8, j0 = nt * TN + nb * 32 + g4 * 8;
+              if (g.prologue == TC_PRO_AFFINE_RELU) {
+                ps[u][0] = __ldg(q0 + k); pt[u][0] = __ldg(q1 + k);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (e < nvb[u]) { ps[u][e] = __ldg(q0 + j0 + e); pt[u][e] = __ldg(q1 + j0 + e); }
+              }
+            }
+          }
+        }
         mbar_wait(EMPTY(stage), phase ^ 1);
         uint8_t* st_base = smem + (size_t)stage * STAGE_BYTES;
-        // ---- B operand ----
-#pragma unroll 1
-        for (int it = pw; it < 32; it += N_PROD_WARPS) {
-          float x[8];
-          uint32_t off;
-          if (B_KMAJOR) {                      // rows j (128) x k (64); lane: row = l8, k-group = g4
-            const int rg = it >> 1, kb = it & 1;
-            const int j = nt * TN + rg * 8 + l8, k0 = kc * KC + kb * 32 + g4 * 8;
-            const int nv = (j < g.N) ? min(8, max(0, g.K - k0)) : 0;
-            load8(Bp + (long long)j * g.b_ld + k0, nv, x);
-            if (g.prologue == TC_PRO_AFFINE_RELU) {
+        // ---- B operand: prologue, hi/lo split, store in the UMMA canonical layout ----
 #pragma unroll
-              for (int e = 0; e < 8; ++e) if (e < nv) x[e] = fmaxf(fmaf(x[e], __ldg(q0 + k0 + e), __ldg(q1 + k0 + e)), 0.f);
-            } else if (g.prologue == TC_PRO_SOFTMAX) {
-              if (nv > 0) {
-                const float m = __ldg(q0 + j), inv = __ldg(q1 + j);
+        for (int u = 0; u < NIT; ++u) {
+          const int it = pw + u * N_PROD_WARPS;
+          const bool per_elem = B_KMAJOR ? (g.prologue == TC_PRO_AFFINE_RELU) : (g.prologue == TC_PRO_SOFTMAX);
+          if (g.prologue == TC_PRO_AFFINE_RELU) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) if (e < nv) x[e] = __expf(x[e] - m) * inv;
-              }
-            }
-            off = rg * K_SBO + (kb * 4 + g4) * K_LBO + l8 * 16;
-          } else {                             // k (64) x columns j (128); lane: k = l8, j-group = g4
-            const int kg = it >> 2, nb = it & 3;
-            const int k = kc * KC + kg * 8 + l8, j0 = nt * TN + nb * 32 + g4 * 8;
-            const int nv = (k < g.K) ? min(8, max(0, g.N - j0)) : 0;
-            load8(Bp + (long long)k * g.b_ld + j0, nv, x);
-            if (g.prologue == TC_PRO_AFFINE_RELU) {
-              if (nv > 0) {
-                const float s = __ldg(q0 + k), t = __ldg(q1 + k);
+            for (int e = 0; e < 8; ++e)
+              if (e < nvb[u]) xb[u][e] = fmaxf(fmaf(xb[u][e], per_elem ? ps[u][e] : ps[u][0], per_elem ? pt[u][e] : pt[u][0]), 0.f);
+          } else if (g.prologue == TC_PRO_SOFTMAX) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) if (e < nv) x[e] = fmaxf(fmaf(x[e], s, t), 0.f);
-              }
-            } else if (g.prologue == TC_PRO_SOFTMAX) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) if (e < nv) x[e] = __expf(x[e] - __ldg(q0 + j0 + e)) * __ldg(q1 + j0 + e);
-            }
-            off = (nb * 4 + g4) * MN_SBO + kg * MN_LBO + l8 * 16;
+            for (int e = 0; e < 8; ++e)
+              if (e < nvb[u]) xb[u][e] = __expf(xb[u][e] - (per_elem ? ps[u][e] : ps[u][0])) * (per_elem ? pt[u][e] : pt[u][0]);
           }
-          split8_store(x, st_base + 2 * OP_BYTES + off, st_base + 3 * OP_BYTES + off);
+          uint32_t off;
+          if (B_KMAJOR) off = (it >> 1) * K_SBO + ((it & 1) * 4 + g4) * K_LBO + l8 * 16;
+          else off = ((it & 3) * 4 + g4) * MN_SBO + (it >> 2) * MN_LBO + l8 * 16;
+          split8_store(xb[u], st_base + 2 * OP_BYTES + off, st_base + 3 * OP_BYTES + off);
         }
-        // ---- A operand from fp32 activations (k contiguous) ----
+        // ---- A operand from fp32 activations (k contiguous): all loads of the chunk in flight together ----
         if (!a_blob) {
-#pragma unroll 1
-          for (int it = pw; it < 32; it += N_PROD_WARPS) {
+#pragma unroll
+          for (int u = 0; u < NIT; ++u) {
+            const int it = pw + u * N_PROD_WARPS;
             const int rg = it >> 1, kb = it & 1;
             const int i = mt * TM + rg * 8 + l8, k0 = kc * KC + kb * 32 + g4 * 8;
-            const int nv = (i < g.M) ? min(8, max(0, g.K - k0)) : 0;
-            float x[8];
-            load8(Ap + (long long)i * g.a_i + k0, nv, x);
-            const uint32_t off = rg * K_SBO + (kb * 4 + g4) * K_LBO + l8 * 16;
-            split8_store(x, st_base + off, st_base + OP_BYTES + off);
+            nvb[u] = (i < g.M) ? min(8, max(0, g.K - k0)) : 0;
+            load8(Ap + (long long)i * g.a_i + k0, nvb[u], xb[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < NIT; ++u) {
+            const int it = pw + u * N_PROD_WARPS;
+            const uint32_t off = (it >> 1) * K_SBO + ((it & 1) * 4 + g4) * K_LBO + l8 * 16;
+            split8_store(xb[u], st_base + off, st_base + OP_BYTES + off);
           }
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(FULL(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        // ---- prefetch the next chunk's B values ----
+        if (kc + 1 < n_kc) fetch_b(tile, kc + 1);
+        else if (tile + gridDim.x < n_tiles) fetch_b(tile + gridDim.x, 0);
       }
     }
   } else if (warp >= FIRST_EPI_WARP) {
     // ===================== epilogue =====================
     const int quarter = warp & 3;
-    float* tr = trbuf + quarter * 32 * TR_LD;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      int p, mt, nt; decode(tile, p, mt, nt);
-      float* Cp = g.C + (long long)p * g.c_batch;
-      const float* Rp = g.Res ? g.Res + (long long)p * g.r_batch : nullptr;
-      const int i_own = mt * TM + quarter * 32 + lane;                 // the row this thread owns in TMEM
-      const float bias_own = (g.bias && i_own < g.M) ? __ldg(g.bias + i_own) : 0.f;
-      mbar_wait(T_FULL(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN;
-#pragma unroll 1
-      for (int c = 0; c < TN / 32; ++c) {
-        float v[32];
-        tc_ld32(taddr + c * 32, v);
-        const int jb = nt * TN + c * 32;
-        if (g.c_j == 1) {
-          // rows are contiguous along j: transpose through shared memory so that a warp stores 128 contiguous bytes
+    const int r_own = quarter * 32 + lane;                             // the accumulator row (TMEM lane) this thread owns
+    // Fast path (outputs contiguous along j, 16-byte friendly): every thread moves ITS OWN row with TMA bulk copies --
+    // residual row -> shared memory (prefetched a tile ahead, completion on a per-thread mbarrier), accumulator + bias +
+    // residual combined in place, then one bulk store of the finished row.  No LSU traffic to global memory at all.
+    const bool fast = (g.c_j == 1) && ((g.c_i & 3) == 0) && ((g.N & 3) == 0) && ((g.c_batch & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                      (!g.Res || (((g.r_batch & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Res) & 15) == 0)));
+    if (fast) {
+      uint8_t* my_row[2] = {stg + (size_t)r_own * STG_ROW, stg + STG_BYTES + (size_t)r_own * STG_ROW};
+      const uint32_t my_bar[2] = {smem_u32(rowbars + r_own), smem_u32(rowbars + 128 + r_own)};
+      uint32_t par[2] = {0, 0};
+      bool pending[2] = {false, false};
+      auto prefetch = [&](long long tile) {
+        if (!g.Res || tile >= n_tiles) { pending[0] = pending[1] = false; return; }
+        int p, mt, nt; decode(tile, p, mt, nt);
+        const int i = mt * TM + r_own;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) tr[lane * TR_LD + e] = v[e] + bias_own;
-          __syncwarp();
-          const int j = jb + lane;
-#pragma unroll 4
-          for (int r = 0; r < 32; ++r) {
-            const int i = mt * TM + quarter * 32 + r;
-            if (i < g.M && j < g.N) {
-              const long long o = (long long)i * g.c_i + j;
-              float val = tr[r * TR_LD + lane];
-              if (Rp) val += __ldg(Rp + o);
-              Cp[o] = val;
+        for (int h = 0; h < 2; ++h) {
+          const int j0 = nt * TN + h * HALF_COLS;
+          const int nc = (i < g.M) ? min(HALF_COLS, max(0, g.N - j0)) : 0;
+          pending[h] = nc > 0;
+          if (nc > 0) {
+            mbar_expect_tx(my_bar[h], nc * 4);
+            bulk_g2s(smem_u32(my_row[h]), g.Res + (long long)p * g.r_batch + (long long)i * g.c_i + j0, nc * 4, my_bar[h]);
+          }
+        }
+      };
+      int acc = 0; uint32_t acc_phase = 0;
+      prefetch(blockIdx.x);
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int p, mt, nt; decode(tile, p, mt, nt);
+        const int i = mt * TM + r_own;
+        const float bias_own = (g.bias && i < g.M) ? __ldg(g.bias + i) : 0.f;
+        mbar_wait(T_FULL(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const bool has_res = pending[h];
+          if (has_res) { mbar_wait(my_bar[h], par[h]); par[h] ^= 1; }
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            float v[32];
+            tc_ld32(taddr + h * HALF_COLS + cc * 32, v);
+            float4* dst = reinterpret_cast<float4*>(my_row[h] + cc * 128);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o = make_float4(v[4 * q] + bias_own, v[4 * q + 1] + bias_own, v[4 * q + 2] + bias_own, v[4 * q + 3] + bias_own);
+              if (has_res) { const float4 r4 = dst[q]; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+              dst[q] = o;
             }
           }
-          __syncwarp();
-        } else {
-          // rows are contiguous along i (transposed output, OAFilter's cluster mixing): lanes already coalesce
-          if (i_own < g.M) {
+          const int j0 = nt * TN + h * HALF_COLS;
+          const int nc = (i < g.M) ? min(HALF_COLS, max(0, g.N - j0)) : 0;
+          fence_proxy_async();
+          if (nc > 0) {
+            bulk_s2g(g.C + (long long)p * g.c_batch + (long long)i * g.c_i + j0, smem_u32(my_row[h]), nc * 4);
+            bulk_commit();
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(T_EMPTY(acc));
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        bulk_wait_read0();                   // the row buffers may be overwritten once the stores have read them
+        prefetch(tile + gridDim.x);
+      }
+      bulk_wait0();
+    } else {
+      float* tr = trbuf + quarter * 32 * TR_LD;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int p, mt, nt; decode(tile, p, mt, nt);
+        float* Cp = g.C + (long long)p * g.c_batch;
+        const float* Rp = g.Res ? g.Res + (long long)p * g.r_batch : nullptr;
+        const int i_own = mt * TM + quarter * 32 + lane;                 // the row this thread owns in TMEM
+        const float bias_own = (g.bias && i_own < g.M) ? __ldg(g.bias + i_own) : 0.f;
+        mbar_wait(T_FULL(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN;
+#pragma unroll 1
+        for (int c = 0; c < TN / 32; ++c) {
+          float v[32];
+          tc_ld32(taddr + c * 32, v);
+          const int jb = nt * TN + c * 32;
+          if (g.c_j == 1) {
+            // rows are contiguous along j: transpose through shared memory so that a warp stores 128 contiguous bytes
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int j = jb + e;
-              if (j < g.N) {
-                const long long o = (long long)i_own * g.c_i + (long long)j * g.c_j;
-                float val = v[e] + bias_own;
-                if (Rp) val += __ldg(Rp + o);
-                Cp[o] = val;
+            for (int e = 0; e < 32; ++e) tr[lane * TR_LD + e] = v[e] + bias_own;
+            __syncwarp();
+            const int j = jb + lane;
+            const int ibase = mt * TM + quarter * 32;
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              float rv[8];
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                const int i = ibase + r0 + r;
+                rv[r] = (Rp && i < g.M && j < g.N) ? __ldg(Rp + (long long)i * g.c_i + j) : 0.f;
+              }
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                const int i = ibase + r0 + r;
+                if (i < g.M && j < g.N) Cp[(long long)i * g.c_i + j] = tr[(r0 + r) * TR_LD + lane] + rv[r];
+              }
+            }
+            __syncwarp();
+          } else {
+            // rows are contiguous along i (transposed output, OAFilter's cluster mixing): lanes already coalesce
+            if (i_own < g.M) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const int j = jb + e;
+                if (j < g.N) {
+                  const long long o = (long long)i_own * g.c_i + (long long)j * g.c_j;
+                  float val = v[e] + bias_own;
+                  if (Rp) val += __ldg(Rp + o);
+                  Cp[o] = val;
+                }
               }
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(T_EMPTY(acc));
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
-      tc_fence_before();
-      mbar_arrive(T_EMPTY(acc));
-      acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
   }
   tc_fence_before();
