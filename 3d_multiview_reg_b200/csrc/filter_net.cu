@@ -315,6 +315,46 @@ __global__ void softmax_colstats_kernel(const float* __restrict__ e, int K, int 
   cinv[gid] = 1.0f / s;
 }
 
+// InstanceNorm statistics from the per-tile (mean, M2) partials written by the tensor-core GEMM epilogue (Chan's
+// parallel merge, fixed tile order => deterministic), folded with eval BatchNorm exactly like in_affine_kernel.
+// part [g, ch, tiles, 2]; one thread per (pair, channel).  out index = p*out_stride + out_off + c.
+__global__ void affine_from_partials_kernel(const float* __restrict__ part, int ch, int tiles, int L, int n_rows, float eps_in,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                            float* __restrict__ scale, float* __restrict__ shift, int out_stride, int out_off) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const int p = row / ch, c = row - p * ch;
+  const float* q = part + (size_t)row * tiles * 2;
+  float n = 0.f, mean = 0.f, M2 = 0.f;
+  for (int t = 0; t < tiles; ++t) {
+    const float nb = (float)min(128, L - t * 128);
+    const float mb = __ldg(q + 2 * t), Mb = __ldg(q + 2 * t + 1);
+    const float delta = mb - mean, nn = n + nb;
+    mean += delta * (nb / nn);
+    M2 += Mb + delta * delta * (n * nb / nn);
+    n = nn;
+  }
+  const float rstd = 1.0f / sqrtf(M2 / (float)L + eps_in);
+  const float gsc = __ldg(gamma + c) / sqrtf(__ldg(rvar + c) + 1e-5f);
+  scale[(size_t)p * out_stride + out_off + c] = rstd * gsc;
+  shift[(size_t)p * out_stride + out_off + c] = (-mean * rstd - __ldg(rmean + c)) * gsc + __ldg(beta + c);
+}
+
+// softmax-over-points statistics (diff_pool) from the per-tile (max, sum exp) partials of the embedding conv
+__global__ void softmax_from_partials_kernel(const float* __restrict__ part, int tiles, int n_rows, float* __restrict__ smax,
+                                             float* __restrict__ sinv) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const float* q = part + (size_t)row * tiles * 2;
+  float m = -INFINITY;
+  for (int t = 0; t < tiles; ++t) m = fmaxf(m, __ldg(q + 2 * t));
+  float s = 0.f;
+  for (int t = 0; t < tiles; ++t) s += __ldg(q + 2 * t + 1) * __expf(__ldg(q + 2 * t) - m);
+  smax[row] = m;
+  sinv[row] = 1.0f / s;
+}
+
 // output conv (C -> 1) + tanh/relu weights (oanet.py:174-175) + "any positive weight" flag per pair
 __global__ void logits_kernel(const float* __restrict__ x, long long x_batch, int C, int N, int P,
                               const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ logits,
@@ -384,8 +424,17 @@ struct Work {   // per-group scratch, all fp32
   float *in0, *T0, *T1, *T2, *CAT, *E, *XD0, *XD1, *Y, *Z, *scale, *shift;
 };
 
+constexpr int N_PART = 7;   // activation buffers whose producer can emit InstanceNorm partials (T0,T1,T2,CAT.lo,CAT.hi,XD0,XD1)
+
+inline size_t r64(size_t n) { return (n + 63) / 64 * 64; }   // every per-pair buffer is a multiple of 256 bytes (TMA alignment)
+
+// per-pair workspace, in floats: the carve in launch_filter_forward takes the same terms in the same order
 size_t per_pair_floats(int C, int K, int N) {
-  return (size_t)12 * N + (size_t)3 * C * N + (size_t)2 * C * N + (size_t)K * N + (size_t)4 * C * K + 2 * 1024 + 2 * (size_t)(N > K ? N : K);
+  const size_t L = (size_t)(N > K ? N : K), tmax = (L + 127) / 128;
+  size_t f = r64((size_t)12 * N) + 3 * r64((size_t)C * N) + r64((size_t)2 * C * N) + r64((size_t)K * N) + 4 * r64((size_t)C * K) + 2 * r64(1024) + 2 * r64(L);
+  f += (size_t)N_PART * r64((size_t)C * tmax * 2) + r64((size_t)K * tmax * 2);            // norm / softmax partials
+  f += r64(tc_weight_blob_bytes(C, K) / 4) + r64(tc_weight_blob_bytes(C, N) / 4);        // pre-split x2 / x1_1 (pool, unpool A operands)
+  return f;
 }
 
 // bytes of pre-split weight blobs of one OANBlock (tensor-core path)
@@ -466,20 +515,28 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   uint8_t* blob_base = reinterpret_cast<uint8_t*>(base + align_up((size_t)P * N * 4, 256) + align_up((size_t)P * 4, 256) + 256);
   float* f = reinterpret_cast<float*>(base + fixed);
   Work W;
-  W.in0 = f; f += (size_t)G * 12 * N;
-  W.T0 = f; f += (size_t)G * C * N;
-  W.T1 = f; f += (size_t)G * C * N;
-  W.T2 = f; f += (size_t)G * C * N;
-  W.CAT = f; f += (size_t)G * 2 * C * N;
-  W.E = f; f += (size_t)G * K * N;
-  W.XD0 = f; f += (size_t)G * C * K;
-  W.XD1 = f; f += (size_t)G * C * K;
-  W.Y = f; f += (size_t)G * C * K;
-  W.Z = f; f += (size_t)G * C * K;
-  W.scale = f; f += (size_t)G * 1024;
-  W.shift = f; f += (size_t)G * 1024;
-  float* sm_max = f; f += (size_t)G * (N > K ? N : K);
-  float* sm_inv = f; f += (size_t)G * (N > K ? N : K);
+  auto take = [&](size_t per_pair) { float* r = f; f += (size_t)G * r64(per_pair); return r; };
+  W.in0 = take((size_t)12 * N);
+  W.T0 = take((size_t)C * N); W.T1 = take((size_t)C * N); W.T2 = take((size_t)C * N);
+  W.CAT = take((size_t)2 * C * N);
+  W.E = take((size_t)K * N);
+  W.XD0 = take((size_t)C * K); W.XD1 = take((size_t)C * K); W.Y = take((size_t)C * K); W.Z = take((size_t)C * K);
+  W.scale = take(1024); W.shift = take(1024);
+  float* sm_max = take((size_t)(N > K ? N : K));
+  float* sm_inv = take((size_t)(N > K ? N : K));
+  const int tmax = ((N > K ? N : K) + 127) / 128, tilesN = (N + 127) / 128;
+  bool want_sm = false;   // set around the diff_pool embedding conv: its epilogue also emits softmax-over-points partials
+  float* part_buf[N_PART];
+  const float* part_key[N_PART] = {W.T0, W.T1, W.T2, W.CAT, W.CAT + (size_t)C * N, W.XD0, W.XD1};
+  bool part_valid[N_PART];
+  for (int i = 0; i < N_PART; ++i) { part_buf[i] = take((size_t)C * tmax * 2); part_valid[i] = false; }
+  float* sm_part = take((size_t)K * tmax * 2);
+  uint8_t* blob_x2 = reinterpret_cast<uint8_t*>(take(tc_weight_blob_bytes(C, K) / 4));
+  uint8_t* blob_x11 = reinterpret_cast<uint8_t*>(take(tc_weight_blob_bytes(C, N) / 4));
+  auto part_index = [&](const float* x) -> int {
+    for (int i = 0; i < N_PART; ++i) if (part_key[i] == x) return i;
+    return -1;
+  };
 
   if (status) cudaMemsetAsync(status, 0, (size_t)P * 4, st);
 
@@ -491,10 +548,27 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     in_affine_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, xb, ch, L, use_in ? 1 : 0, eps, bn.g, bn.b, bn.rm, bn.rv, W.scale, W.shift, rows);
     return check_launch("in_affine_kernel");
   };
+  auto aff_part = [&](const float* part, int ch, int L, int g, float eps, const BNP& bn, int bn_off, int out_stride, int out_off) -> int {
+    const int rows = g * ch, tiles = (L + 127) / 128;
+    affine_from_partials_kernel<<<(rows + 127) / 128, 128, 0, st>>>(part, ch, tiles, L, rows, eps, bn.g + bn_off, bn.b + bn_off, bn.rm + bn_off,
+                                                                    bn.rv + bn_off, W.scale, W.shift, out_stride, out_off);
+    return check_launch("affine_from_partials_kernel");
+  };
   // out[p, :, :] = conv(relu(bn(in(x))))  (+ residual), x [g, cin, L] with batch stride xb
   auto conv_norm = [&](const float* x, long long xb, int cin, int L, int g, float eps, const BNP& bn, const ConvP& cv, int cout,
                        float* out, long long ob, const float* res, long long rb) -> int {
-    LMPCR_TRY(affine(x, xb, cin, L, g, true, eps, bn));
+    // InstanceNorm statistics of the input: from the producer's fused partials when available, else a pass over x
+    const int xi = part_index(x);
+    const int xi_hi = (cin == 2 * C) ? part_index(x + (size_t)C * L) : -1;
+    if (tc && cin == C && xi >= 0 && part_valid[xi]) {
+      LMPCR_TRY(aff_part(part_buf[xi], C, L, g, eps, bn, 0, C, 0));
+    } else if (tc && cin == 2 * C && xi >= 0 && xi_hi >= 0 && part_valid[xi] && part_valid[xi_hi]) {
+      LMPCR_TRY(aff_part(part_buf[xi], C, L, g, eps, bn, 0, 2 * C, 0));
+      LMPCR_TRY(aff_part(part_buf[xi_hi], C, L, g, eps, bn, C, 2 * C, C));
+    } else {
+      LMPCR_TRY(affine(x, xb, cin, L, g, true, eps, bn));
+    }
+    const int oi = part_index(out);
     if (tc) {
       TcGemmArgs a{};
       a.a_blob = cv.blob;
@@ -503,8 +577,14 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       a.Res = res; a.r_batch = rb; a.bias = cv.b;
       a.prologue = TC_PRO_AFFINE_RELU; a.p0 = W.scale; a.p1 = W.shift; a.p_batch = cin;
       a.M = cout; a.N = L; a.K = cin;
+      if (oi >= 0 && cout == C) {
+        part_valid[oi] = tc_fast_epilogue(a);
+        a.stats_out = part_valid[oi] ? part_buf[oi] : nullptr;
+      }
+      if (want_sm && out == W.E && tc_fast_epilogue(a)) a.smstats_out = sm_part;   // softmax over points (diff_pool)
       return launch_tcgemm(a, g, st);
     }
+    if (oi >= 0) part_valid[oi] = false;
     GemmArgs a{};
     a.A = cv.w; a.a_batch = 0; a.a_i = cin;
     a.B = x; a.b_batch = xb; a.b_k = L; a.b_j = 1;
@@ -515,6 +595,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     return gemm(a, g, st);
   };
   auto conv_plain = [&](const float* x, long long xb, int cin, int L, int g, const ConvP& cv, int cout, float* out, long long ob) -> int {
+    { const int oi = part_index(out); if (oi >= 0) part_valid[oi] = false; }
     if (tc && cv.blob) {
       TcGemmArgs a{};
       a.a_blob = cv.blob;
@@ -585,16 +666,27 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       }
       const float* x11 = W.CAT; const long long x11b = 2 * CN;
       // diff_pool (oanet.py:106-110)
+      want_sm = true;
       LMPCR_TRY(conv_norm(x11, x11b, C, N, g, 1e-3f, blk.down_bn, blk.down_conv, K, W.E, (long long)K * N, nullptr, 0));
+      want_sm = false;
       if (tc) {
-        softmax_rowstats_kernel<<<g * K, 256, 0, st>>>(W.E, N, g * K, sm_max, sm_inv);
-        LMPCR_TRY(check_launch("softmax_rowstats_kernel"));
         TcGemmArgs a{};   // x_down[c,k] = sum_n x11[c,n] * softmax_n(E[k,:])[n]
-        a.A = x11; a.a_batch = x11b; a.a_i = N;
         a.B = W.E; a.b_batch = (long long)K * N; a.b_ld = N; a.b_kmajor = 1;
         a.C = W.XD0; a.c_batch = CK; a.c_i = K; a.c_j = 1;
         a.prologue = TC_PRO_SOFTMAX; a.p0 = sm_max; a.p1 = sm_inv; a.p_batch = K;
         a.M = C; a.N = K; a.K = N;
+        if ((N & 3) == 0) {   // softmax statistics came fused out of the embedding conv's epilogue
+          softmax_from_partials_kernel<<<(g * K + 127) / 128, 128, 0, st>>>(sm_part, tilesN, g * K, sm_max, sm_inv);
+          LMPCR_TRY(check_launch("softmax_from_partials_kernel"));
+        } else {
+          softmax_rowstats_kernel<<<g * K, 256, 0, st>>>(W.E, N, g * K, sm_max, sm_inv);
+          LMPCR_TRY(check_launch("softmax_rowstats_kernel"));
+        }
+        // A operand (x1_1) is shared by the 4 cluster tiles of a pair: split it once into bf16 hi/lo tiles
+        LMPCR_TRY(launch_split_weights(x11, C, N, blob_x11, st, g, x11b, N));
+        a.a_blob = blob_x11; a.a_blob_batch = (long long)tc_weight_blob_bytes(C, N);
+        part_valid[part_index(W.XD0)] = tc_fast_epilogue(a);
+        a.stats_out = part_valid[part_index(W.XD0)] ? part_buf[part_index(W.XD0)] : nullptr;
         LMPCR_TRY(launch_tcgemm(a, g, st));
       } else {
         softmax_rows_kernel<<<g * K, 256, 0, st>>>(W.E, N, g * K);
@@ -605,6 +697,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         a.C = W.XD0; a.c_batch = CK; a.c_i = K; a.c_j = 1;
         a.M = C; a.N = K; a.K = N;
         LMPCR_TRY(gemm(a, g, st));
+        part_valid[part_index(W.XD0)] = false;
       }
       // l2: OAFilter x half (oanet.py:85-93)
       float* xd_in = W.XD0; float* xd_out = W.XD1;
@@ -640,11 +733,13 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         softmax_colstats_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g, sm_max, sm_inv);
         LMPCR_TRY(check_launch("softmax_colstats_kernel"));
         TcGemmArgs a{};   // x_up[c,n] = sum_k x2[c,k] * softmax_k(E[:,n])[k]
-        a.A = xd_in; a.a_batch = CK; a.a_i = K;
+        LMPCR_TRY(launch_split_weights(xd_in, C, K, blob_x2, st, g, CK, K));   // A operand (x2) shared by all point tiles of a pair
+        a.a_blob = blob_x2; a.a_blob_batch = (long long)tc_weight_blob_bytes(C, K);
         a.B = W.E; a.b_batch = (long long)K * N; a.b_ld = N; a.b_kmajor = 0;
         a.C = W.CAT + CN; a.c_batch = 2 * CN; a.c_i = N; a.c_j = 1;
         a.prologue = TC_PRO_SOFTMAX; a.p0 = sm_max; a.p1 = sm_inv; a.p_batch = N;
         a.M = C; a.N = N; a.K = K;
+        { const int oi = part_index(W.CAT + CN); part_valid[oi] = tc_fast_epilogue(a); a.stats_out = part_valid[oi] ? part_buf[oi] : nullptr; }
         LMPCR_TRY(launch_tcgemm(a, g, st));
       } else {
         softmax_cols_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g);
@@ -655,6 +750,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         a.C = W.CAT + CN; a.c_batch = 2 * CN; a.c_i = N; a.c_j = 1;
         a.M = C; a.N = N; a.K = K;
         LMPCR_TRY(gemm(a, g, st));
+        part_valid[part_index(W.CAT + CN)] = false;
       }
       // l1_2 (oanet.py:171): PointCN(2C -> C) with shot_cut, then half-1 PointCN(C); T1/T0 ping-pong, T2 = temp
       float* lat_dst = (last && latent) ? latent + (size_t)p0 * CN : nullptr;

@@ -16,6 +16,7 @@
 // Pipelines: 3-stage shared-memory ring (full/empty mbarriers), double-buffered TMEM accumulator (128 columns each).
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "tc_ptx.cuh"
 #include "tcgemm.cuh"
@@ -33,13 +34,15 @@ constexpr int NTHREADS = 32 * (FIRST_PROD_WARP + N_PROD_WARPS);   // 512
 constexpr uint32_t K_LBO = 128, K_SBO = (KC / 8) * 128;           // K-major operand: k-groups adjacent, 8-row groups 1 KB apart
 constexpr uint32_t MN_SBO = 128, MN_LBO = (TN / 8) * 128;         // MN-major operand: j-groups adjacent, k-groups 2 KB apart
 constexpr int TR_LD = 33;                                         // padded row of the (generic) epilogue transpose buffer
-constexpr int HALF_COLS = 64;                                     // the TMA epilogue works on half tiles (128 rows x 64 columns)
-constexpr int STG_ROW = HALF_COLS * 4 + 16;                       // 272 B: 16-byte aligned, conflict-free for float4 at one row per lane
-constexpr int STG_BYTES = TM * STG_ROW;                           // 34816
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 2 * STG_BYTES + 4 * 32 * TR_LD * 4 + 2 * 128 * 8 + 16 * 8 + 16;
+constexpr int STG_ROW = TN * 4 + 16;                              // 528 B: 16-byte aligned, conflict-free for float4 at one row per lane
+constexpr int STG_BYTES = TM * STG_ROW;                           // 67584: one staged output tile
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 4 * 32 * TR_LD * 4 + 2 * 128 * 8 + 16 * 8 + 16;
 
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {   // 16-byte aligned, multiple of 16
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -71,7 +74,10 @@ __device__ __forceinline__ void load8(const float* src, int nvalid, float (&x)[8
 }
 
 // fp32 weights [M,K] (k contiguous) -> per (m-tile, k-chunk) blob [hi 16 KB | lo 16 KB], K-major canonical layout
-__global__ void split_weights_kernel(const float* __restrict__ W, int M, int K, uint8_t* __restrict__ blob) {
+__global__ void split_weights_kernel(const float* __restrict__ Wb, int M, int K, uint8_t* __restrict__ blobb, long long w_batch, int ld,
+                                     long long blob_batch) {
+  const float* W = Wb + (long long)blockIdx.y * w_batch;
+  uint8_t* blob = blobb + (long long)blockIdx.y * blob_batch;
   const int n_kc = (K + KC - 1) / KC, n_mt = (M + TM - 1) / TM;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, k-group of 8)
   const long long total = (long long)n_mt * TM * n_kc * (KC / 8);
@@ -82,7 +88,7 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int M, int K, 
   const int k0 = kc * KC + kg * 8;
   float x[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) x[e] = (row < M && k0 + e < K) ? __ldg(W + (size_t)row * K + k0 + e) : 0.f;
+  for (int e = 0; e < 8; ++e) x[e] = (row < M && k0 + e < K) ? __ldg(W + (size_t)row * ld + k0 + e) : 0.f;
   uint8_t* base = blob + ((size_t)mt * n_kc + kc) * 2 * OP_BYTES + (r >> 3) * K_SBO + kg * K_LBO + (r & 7) * 16;
   split8_store(x, base, base + OP_BYTES);
 }
@@ -90,8 +96,8 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int M, int K, 
 template <bool B_KMAJOR>
 __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int batch) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;                                  // [2 halves][128 rows][STG_ROW]
-  float* trbuf = reinterpret_cast<float*>(stg + 2 * STG_BYTES);                        // [4 warps][32][TR_LD]
+  uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;                                  // [128 rows][STG_ROW]
+  float* trbuf = reinterpret_cast<float*>(stg + STG_BYTES);                            // [4 warps][32][TR_LD]
   uint64_t* rowbars = reinterpret_cast<uint64_t*>(trbuf + 4 * 32 * TR_LD);             // [2 halves][128 rows]
   uint64_t* bars = rowbars + 2 * 128;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
@@ -127,17 +133,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
   };
 
   if (warp == 0) {
-    // ===================== TMA producer for the weight blob =====================
-    if (a_blob && lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int p, mt, nt; decode(tile, p, mt, nt);
-        for (int kc = 0; kc < n_kc; ++kc) {
-          mbar_wait(EMPTY(stage), phase ^ 1);
-          mbar_expect_tx(FULL(stage), 2 * OP_BYTES);
-          bulk_g2s(smem_u32(smem + (size_t)stage * STAGE_BYTES), g.a_blob + ((size_t)mt * n_kc + kc) * 2 * OP_BYTES, 2 * OP_BYTES, FULL(stage));
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    // ===================== TMA producer for the weight blob + L2 prefetcher =====================
+    // The activations of a group of pairs do not fit L2, so a producer warp would see the full HBM latency once per
+    // 64-chunk.  This warp runs PF_CHUNKS chunks ahead of the pipeline and pulls the B rows (and the residual rows of the
+    // tile) into L2 with cp.async.bulk.prefetch.L2 -- no registers, no shared memory.
+    constexpr int PF_CHUNKS = 6;
+    const bool pf_ok = ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && ((g.b_ld & 3) == 0) && ((g.b_batch & 3) == 0);
+    const bool pf_res = g.Res && tc_fast_epilogue(g);
+    auto prefetch_chunk = [&](long long tile, int kc) {
+      int p, mt, nt; decode(tile, p, mt, nt);
+      const float* Bp = g.B + (long long)p * g.b_batch;
+      if (pf_ok) {
+        if (B_KMAJOR) {
+          const int nb = min(KC, g.K - kc * KC) * 4;
+          if (nb > 0 && (nb & 15) == 0)
+            for (int r = lane; r < TN; r += 32) {
+              const int j = nt * TN + r;
+              if (j < g.N) l2_prefetch(Bp + (long long)j * g.b_ld + kc * KC, nb);
+            }
+        } else {
+          const int nb = min(TN, g.N - nt * TN) * 4;
+          if (nb > 0 && (nb & 15) == 0)
+            for (int r = lane; r < KC; r += 32) {
+              const int k = kc * KC + r;
+              if (k < g.K) l2_prefetch(Bp + (long long)k * g.b_ld + nt * TN, nb);
+            }
         }
+      }
+      if (pf_res && kc == 0) {
+        const int nb = min(TN, g.N - nt * TN) * 4;
+        for (int r = lane; r < TM; r += 32) {
+          const int i = mt * TM + r;
+          if (i < g.M) l2_prefetch(g.Res + (long long)p * g.r_batch + (long long)i * g.c_i + nt * TN, nb);
+        }
+      }
+    };
+    long long pf_tile = blockIdx.x; int pf_kc = 0;
+    auto pf_advance = [&]() {
+      if (pf_tile >= n_tiles) return;
+      if (!(g.debug & 128)) prefetch_chunk(pf_tile, pf_kc);
+      if (++pf_kc == n_kc) { pf_kc = 0; pf_tile += gridDim.x; }
+    };
+    for (int i = 0; i < PF_CHUNKS; ++i) pf_advance();
+    int stage = 0; uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int p, mt, nt; decode(tile, p, mt, nt);
+      for (int kc = 0; kc < n_kc; ++kc) {
+        pf_advance();
+        mbar_wait(EMPTY(stage), phase ^ 1);      // paces the prefetcher with the pipeline
+        if (a_blob && lane == 0) {
+          mbar_expect_tx(FULL(stage), 2 * OP_BYTES);
+          bulk_g2s(smem_u32(smem + (size_t)stage * STAGE_BYTES), g.a_blob + (long long)p * g.a_blob_batch + ((size_t)mt * n_kc + kc) * 2 * OP_BYTES,
+                   2 * OP_BYTES, FULL(stage));
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -155,7 +205,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + (size_t)stage * STAGE_BYTES), sB = sA + 2 * OP_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks) {
+          for (int ks = 0; ks < ((g.debug & 16) ? 0 : KC / 16); ++ks) {
             const uint64_t a_hi = make_desc(sA + ks * 2 * K_LBO, K_LBO, K_SBO);
             const uint64_t a_lo = make_desc(sA + OP_BYTES + ks * 2 * K_LBO, K_LBO, K_SBO);
             const uint64_t b_hi = make_desc(sB + ks * 2 * B_LBO, B_LBO, B_SBO);
@@ -182,6 +232,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
     int nvb[NIT];
     auto fetch_b = [&](long long tile, int kc) {
       int p, mt, nt; decode(tile, p, mt, nt);
+      if (g.debug & 1) {
+#pragma unroll
+        for (int u = 0; u < NIT; ++u) { nvb[u] = 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xb[u][e] = 1.0f; }
+        return;
+      }
       const float* Bp = g.B + (long long)p * g.b_batch;
 #pragma unroll
       for (int u = 0; u < NIT; ++u) {
@@ -214,7 +271,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
           const int it = pw + u * N_PROD_WARPS;
 #pragma unroll
           for (int e = 0; e < 8; ++e) { ps[u][e] = 0.f; pt[u][e] = 0.f; }
-          if (g.prologue != TC_PRO_NONE && nvb[u] > 0) {
+          if (g.prologue != TC_PRO_NONE && nvb[u] > 0 && !(g.debug & 64)) {
             if (B_KMAJOR) {
               const int rg = it >> 1, kb = it & 1;
               const int j = nt * TN + rg * 8 + l8, k0 = kc * KC + kb * 32 + g4 * 8;
@@ -239,6 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
         mbar_wait(EMPTY(stage), phase ^ 1);
         uint8_t* st_base = smem + (size_t)stage * STAGE_BYTES;
         // ---- B operand: prologue, hi/lo split, store in the UMMA canonical layout ----
+        if (!(g.debug & 2))
 #pragma unroll
         for (int u = 0; u < NIT; ++u) {
           const int it = pw + u * N_PROD_WARPS;
@@ -290,27 +348,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
     // Fast path (outputs contiguous along j, 16-byte friendly): every thread moves ITS OWN row with TMA bulk copies --
     // residual row -> shared memory (prefetched a tile ahead, completion on a per-thread mbarrier), accumulator + bias +
     // residual combined in place, then one bulk store of the finished row.  No LSU traffic to global memory at all.
-    const bool fast = (g.c_j == 1) && ((g.c_i & 3) == 0) && ((g.N & 3) == 0) && ((g.c_batch & 3) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
-                      (!g.Res || (((g.r_batch & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Res) & 15) == 0)));
+    const bool fast = tc_fast_epilogue(g);
     if (fast) {
-      uint8_t* my_row[2] = {stg + (size_t)r_own * STG_ROW, stg + STG_BYTES + (size_t)r_own * STG_ROW};
-      const uint32_t my_bar[2] = {smem_u32(rowbars + r_own), smem_u32(rowbars + 128 + r_own)};
-      uint32_t par[2] = {0, 0};
-      bool pending[2] = {false, false};
+      uint8_t* my_row = stg + (size_t)r_own * STG_ROW;
+      const uint8_t* warp_rows = stg + (size_t)(quarter * 32) * STG_ROW;
+      const uint32_t my_bar = smem_u32(rowbars + r_own);
+      uint32_t par = 0;
+      bool pending = false;
       auto prefetch = [&](long long tile) {
-        if (!g.Res || tile >= n_tiles) { pending[0] = pending[1] = false; return; }
+        pending = false;
+        if (!g.Res || tile >= n_tiles || (g.debug & 8)) return;
         int p, mt, nt; decode(tile, p, mt, nt);
         const int i = mt * TM + r_own;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int j0 = nt * TN + h * HALF_COLS;
-          const int nc = (i < g.M) ? min(HALF_COLS, max(0, g.N - j0)) : 0;
-          pending[h] = nc > 0;
-          if (nc > 0) {
-            mbar_expect_tx(my_bar[h], nc * 4);
-            bulk_g2s(smem_u32(my_row[h]), g.Res + (long long)p * g.r_batch + (long long)i * g.c_i + j0, nc * 4, my_bar[h]);
-          }
+        const int nc = (i < g.M) ? min(TN, g.N - nt * TN) : 0;
+        if (nc > 0) {
+          pending = true;
+          mbar_expect_tx(my_bar, nc * 4);
+          bulk_g2s(smem_u32(my_row), g.Res + (long long)p * g.r_batch + (long long)i * g.c_i + nt * TN, nc * 4, my_bar);
         }
       };
       int acc = 0; uint32_t acc_phase = 0;
@@ -322,37 +376,73 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
         mbar_wait(T_FULL(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN;
+        const int ncv = min(TN, g.N - nt * TN);      // valid columns of this tile (multiple of 4 on this path)
+        float c0 = 0.f, s1 = 0.f, s2 = 0.f, vmax = -INFINITY;
+        const bool has_res = pending;
+        if (has_res) { mbar_wait(my_bar, par); par ^= 1; }
+        // ---- phase 1: thread = row.  accumulator + bias + residual, in place in this thread's staged row ----
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const bool has_res = pending[h];
-          if (has_res) { mbar_wait(my_bar[h], par[h]); par[h] ^= 1; }
+        for (int cc = 0; cc < ((g.debug & 32) ? 0 : TN / 32); ++cc) {
+          float v[32];
+          tc_ld32(taddr + cc * 32, v);
+          float4* dst = reinterpret_cast<float4*>(my_row + cc * 128);
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            float v[32];
-            tc_ld32(taddr + h * HALF_COLS + cc * 32, v);
-            float4* dst = reinterpret_cast<float4*>(my_row[h] + cc * 128);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 o = make_float4(v[4 * q] + bias_own, v[4 * q + 1] + bias_own, v[4 * q + 2] + bias_own, v[4 * q + 3] + bias_own);
-              if (has_res) { const float4 r4 = dst[q]; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
-              dst[q] = o;
+          for (int q = 0; q < 8; ++q) {
+            float4 o = make_float4(v[4 * q] + bias_own, v[4 * q + 1] + bias_own, v[4 * q + 2] + bias_own, v[4 * q + 3] + bias_own);
+            if (has_res) { const float4 r4 = dst[q]; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+            dst[q] = o;
+            if (cc * 32 + q * 4 < ncv) {
+              if (g.stats_out) {            // shifted sums: robust against |mean| >> std
+                if (cc == 0 && q == 0) c0 = o.x;
+                const float d0 = o.x - c0, d1 = o.y - c0, d2 = o.z - c0, d3 = o.w - c0;
+                s1 += (d0 + d1) + (d2 + d3);
+                s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+              }
+              if (g.smstats_out) vmax = fmaxf(fmaxf(vmax, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
             }
-          }
-          const int j0 = nt * TN + h * HALF_COLS;
-          const int nc = (i < g.M) ? min(HALF_COLS, max(0, g.N - j0)) : 0;
-          fence_proxy_async();
-          if (nc > 0) {
-            bulk_s2g(g.C + (long long)p * g.c_batch + (long long)i * g.c_i + j0, smem_u32(my_row[h]), nc * 4);
-            bulk_commit();
           }
         }
         tc_fence_before();
         mbar_arrive(T_EMPTY(acc));
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
-        bulk_wait_read0();                   // the row buffers may be overwritten once the stores have read them
+        if (i < g.M) {
+          const long long so = (((long long)p * g.M + i) * tiles_n + nt) * 2;
+          if (g.stats_out) {
+            const float inv = 1.0f / (float)ncv;
+            g.stats_out[so] = c0 + s1 * inv;
+            g.stats_out[so + 1] = fmaxf(s2 - s1 * s1 * inv, 0.f);
+          }
+          if (g.smstats_out) {             // second pass over the finished row (still in shared memory)
+            float se = 0.f;
+#pragma unroll 4
+            for (int q = 0; q < TN / 4; ++q)
+              if (q * 4 < ncv) {
+                const float4 o = reinterpret_cast<const float4*>(my_row)[q];
+                se += (__expf(o.x - vmax) + __expf(o.y - vmax)) + (__expf(o.z - vmax) + __expf(o.w - vmax));
+              }
+            g.smstats_out[so] = vmax;
+            g.smstats_out[so + 1] = se;
+          }
+        }
+        // ---- phase 2: warp = 32 rows.  Each row leaves as one coalesced 512-byte store (lane = 4 columns) ----
+        __syncwarp();
+        {
+          float* Cp = g.C + (long long)p * g.c_batch + nt * TN + 4 * lane;
+          const int ibase = mt * TM + quarter * 32;
+          if (4 * lane < ncv && !(g.debug & 4)) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              if (ibase + r < g.M) {
+                const float4 o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 16 * lane);
+                *reinterpret_cast<float4*>(Cp + (long long)(ibase + r) * g.c_i) = o;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        fence_proxy_async();                 // generic reads of the staged rows are ordered before the next TMA write
         prefetch(tile + gridDim.x);
       }
-      bulk_wait0();
     } else {
       float* tr = trbuf + quarter * 32 * TR_LD;
       int acc = 0; uint32_t acc_phase = 0;
@@ -428,13 +518,18 @@ size_t tc_weight_blob_bytes(int M, int K) {
   return (size_t)((M + TM - 1) / TM) * ((K + KC - 1) / KC) * 2 * OP_BYTES;
 }
 
-int launch_split_weights(const float* W, int M, int K, uint8_t* blob, cudaStream_t st) {
+int launch_split_weights(const float* W, int M, int K, uint8_t* blob, cudaStream_t st, int batch, long long w_batch, int ld) {
   const long long total = (long long)((M + TM - 1) / TM) * TM * ((K + KC - 1) / KC) * (KC / 8);
-  split_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, M, K, blob);
+  dim3 grid((unsigned)((total + 255) / 256), batch);
+  split_weights_kernel<<<grid, 256, 0, st>>>(W, M, K, blob, w_batch, ld < 0 ? K : ld, (long long)tc_weight_blob_bytes(M, K));
   return check_launch("split_weights_kernel");
 }
 
-int launch_tcgemm(const TcGemmArgs& a, int batch, cudaStream_t st) {
+int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
+  TcGemmArgs a = a_in;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("LMPCR_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+  a.debug = dbg;
   LMPCR_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && batch > 0, LMPCR_ERR_ARG, "tcgemm: bad sizes");
   static bool attr_set = false;
   if (!attr_set) {

@@ -11,7 +11,7 @@ enum TcPrologue { TC_PRO_NONE = 0, TC_PRO_AFFINE_RELU = 1, TC_PRO_SOFTMAX = 2 };
 // accumulation on tcgen05: products carry ~2^-16 relative error, ~30x tighter than TF32.
 struct TcGemmArgs {
   // A: either a pre-split weight blob (a_blob != nullptr; made by launch_split_weights) or fp32 rows with k contiguous
-  const uint8_t* a_blob;
+  const uint8_t* a_blob; long long a_blob_batch;     // bytes between the blobs of consecutive batch elements (0: shared weights)
   const float* A; long long a_batch; int a_i;       // A[p,i,k] at A + p*a_batch + i*a_i + k
   // B: fp32; b_kmajor = 0: B[p,k,j] at B + p*b_batch + k*b_ld + j (j contiguous)
   //          b_kmajor = 1: B[p,k,j] at B + p*b_batch + j*b_ld + k (k contiguous)
@@ -22,11 +22,24 @@ struct TcGemmArgs {
   int prologue;                                     // TcPrologue
   const float* p0; const float* p1; int p_batch;    // AFFINE_RELU: scale/shift indexed [p*p_batch + k];
                                                     // SOFTMAX: max / 1/sum indexed [p*p_batch + j]: f(x) = exp(x - p0[j]) * p1[j]
+  // Optional fused statistics of the OUTPUT, written by the TMA epilogue (only when tc_fast_epilogue(args) holds):
+  //   stats_out   [batch, M, ceil(N/128), 2] = (mean, M2) of every row over the tile's valid columns  (InstanceNorm of the consumer)
+  //   smstats_out [batch, M, ceil(N/128), 2] = (max, sum exp(x - max)) of every row over the tile       (softmax over the j axis)
+  float* stats_out; float* smstats_out;
   int M, N, K;
+  int debug;   // timing experiments only (LMPCR_TC_DEBUG bit mask, see tcgemm.cu); 0 in production
 };
 
+// the epilogue moves whole rows with TMA bulk copies when rows are contiguous along j and 16-byte friendly
+__host__ __device__ inline bool tc_fast_epilogue(const TcGemmArgs& g) {
+  return (g.c_j == 1) && ((g.c_i & 3) == 0) && ((g.N & 3) == 0) && ((g.c_batch & 3) == 0) &&
+         ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+         (!g.Res || (((g.r_batch & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Res) & 15) == 0)));
+}
+
 size_t tc_weight_blob_bytes(int M, int K);
-int launch_split_weights(const float* W, int M, int K, uint8_t* blob, cudaStream_t st);
+// W[b] = W + b*w_batch, rows `ld` floats apart (k contiguous); blob[b] = blob + b*tc_weight_blob_bytes(M,K)
+int launch_split_weights(const float* W, int M, int K, uint8_t* blob, cudaStream_t st, int batch = 1, long long w_batch = 0, int ld = -1);
 int launch_tcgemm(const TcGemmArgs& a, int batch, cudaStream_t st);
 
 }  // namespace lmpcr

@@ -211,6 +211,10 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    torch.cuda.synchronize()
+    l0 = cabi.launch_count()
+    step_resident()
+    launches_per_step = cabi.launch_count() - l0          # kernels of liblmpcr_b200 launched by one step (library counter)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -230,10 +234,10 @@ def run_ours(args):
         filt_tf = per_rank * FILTER_FLOP_PER_PAIR(n) / (filt_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (NN screen fp16->f32, GEMMs bf16x3->f32 on tensor cores)", "data": "synthetic",
             "config": {"workload": "configs[1]: %d scans -> %d pairs x %d keypoints x 32-d per GPU (rank-0 scene of %d scans, %d pairs total)"
                                    % (S, per_rank, n, S_glob, pairs_total),
-                       "nn_algo": "tcgen05+rescore" if args.nn_algo == 1 else "exact_simt", "gemm_algo": args.gemm_algo,
+                       "nn_algo": "tcgen05+rescore" if args.nn_algo == 1 else "exact_simt", "gemm_algo": "tcgen05 split-bf16" if args.gemm_algo == 1 else "fp32 simt",
                        "pair_chunk": args.pair_chunk, "l2": "256 MiB flush buffer written between timed iterations",
                        "parallelism": "pairs x%d" % world},
             # dominant stage = filtering network (GEMM kernels); stage time brackets every kernel of the stage, so the
@@ -252,7 +256,7 @@ def run_ours(args):
             "clocks": clocks,
         }
         # launches of OUR kernels per step (counted from the call structure: see DESIGN.md "launch count")
-        line["gpu_launches"] = int(n_chunks * launches_per_chunk(args, per_rank))
+        line["gpu_launches"] = int(launches_per_step * args.steps)
         if world == 1 and not args.no_cpu_baseline:
             cf, cx, csd = feats[:8], xyz[:8], sd
             cp = O.enumerate_pairs(8)[: args.cpu_pairs]
@@ -285,8 +289,8 @@ def main():
     ap.add_argument("--scans", type=int, default=60)
     ap.add_argument("--points", type=int, default=5000)
     ap.add_argument("--pair-chunk", type=int, default=256)
-    ap.add_argument("--nn-algo", type=int, default=int(os.environ.get("LMPCR_NN_ALGO", "0")))
-    ap.add_argument("--gemm-algo", type=int, default=int(os.environ.get("LMPCR_GEMM_ALGO", "0")))
+    ap.add_argument("--nn-algo", type=int, default=int(os.environ.get("LMPCR_NN_ALGO", "1")))
+    ap.add_argument("--gemm-algo", type=int, default=int(os.environ.get("LMPCR_GEMM_ALGO", "1")))
     ap.add_argument("--ref-pairs", type=int, default=12)
     ap.add_argument("--cpu-pairs", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
