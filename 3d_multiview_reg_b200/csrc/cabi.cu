@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "tcgemm.cuh"
 
 namespace lmpcr {
 
@@ -105,6 +106,8 @@ int lmpcr_nn_tensor_debug(const float* q_feat, int n_q_sets, int n_q, const floa
   return launch_nn_tensor_ex(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, dim, jobs, n_jobs, idx_out, dist_out, scores, approx_min,
                              workspace, workspace_bytes, (cudaStream_t)stream);
 }
+
+int lmpcr_debug_tc_profile(unsigned long long* out16, int reset) { return tc_profile_read(out16, reset); }
 
 int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, int dim, int batch, float* out, void* workspace,
                             size_t workspace_bytes, void* stream) {

@@ -322,23 +322,39 @@ __global__ void affine_from_partials_kernel(const float* __restrict__ part, int 
                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                             const float* __restrict__ rmean, const float* __restrict__ rvar,
                                             float* __restrict__ scale, float* __restrict__ shift, int out_stride, int out_off) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per (pair, channel): lanes take tiles lane, lane+32, ... in order, then a fixed shuffle tree merges them
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
   const int p = row / ch, c = row - p * ch;
   const float* q = part + (size_t)row * tiles * 2;
   float n = 0.f, mean = 0.f, M2 = 0.f;
-  for (int t = 0; t < tiles; ++t) {
+  for (int t = lane; t < tiles; t += 32) {
     const float nb = (float)min(128, L - t * 128);
-    const float mb = __ldg(q + 2 * t), Mb = __ldg(q + 2 * t + 1);
-    const float delta = mb - mean, nn = n + nb;
+    const float2 v = __ldg(reinterpret_cast<const float2*>(q) + t);
+    const float delta = v.x - mean, nn = n + nb;
     mean += delta * (nb / nn);
-    M2 += Mb + delta * delta * (n * nb / nn);
+    M2 += v.y + delta * delta * (n * nb / nn);
     n = nn;
   }
-  const float rstd = 1.0f / sqrtf(M2 / (float)L + eps_in);
-  const float gsc = __ldg(gamma + c) / sqrtf(__ldg(rvar + c) + 1e-5f);
-  scale[(size_t)p * out_stride + out_off + c] = rstd * gsc;
-  shift[(size_t)p * out_stride + out_off + c] = (-mean * rstd - __ldg(rmean + c)) * gsc + __ldg(beta + c);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o), Mb = __shfl_xor_sync(0xffffffffu, M2, o);
+    const float nn = n + nb;
+    if (nn > 0.f) {
+      const float delta = mb - mean;
+      // symmetric form: both partners of the butterfly compute the same merged value
+      mean = (n * mean + nb * mb) / nn;
+      M2 = M2 + Mb + delta * delta * (n * nb / nn);
+      n = nn;
+    }
+  }
+  if (lane == 0) {
+    const float rstd = 1.0f / sqrtf(M2 / (float)L + eps_in);
+    const float gsc = __ldg(gamma + c) / sqrtf(__ldg(rvar + c) + 1e-5f);
+    scale[(size_t)p * out_stride + out_off + c] = rstd * gsc;
+    shift[(size_t)p * out_stride + out_off + c] = (-mean * rstd - __ldg(rmean + c)) * gsc + __ldg(beta + c);
+  }
 }
 
 // softmax-over-points statistics (diff_pool) from the per-tile (max, sum exp) partials of the embedding conv
@@ -476,7 +492,7 @@ static size_t fixed_bytes(const lmpcr_filter_cfg* cfg, int P, int N) {
 size_t filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int P, int N) {
   if (validate_cfg(cfg) != LMPCR_OK || P <= 0 || N <= 0) return 0;
   const size_t pp = per_pair_floats(cfg->net_channel, cfg->clusters, N) * 4;
-  size_t G = (size_t(1) << 30) / pp;   // ~1 GiB of activations per group of pairs
+  size_t G = (size_t(8) << 30) / pp;   // up to ~8 GiB of activations per group of pairs (fewer, larger launches)
   if (G < 1) G = 1;
   if (G > (size_t)P) G = P;
   return fixed_bytes(cfg, P, N) + align_up(G * pp, 256) + 4096;
@@ -550,7 +566,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   };
   auto aff_part = [&](const float* part, int ch, int L, int g, float eps, const BNP& bn, int bn_off, int out_stride, int out_off) -> int {
     const int rows = g * ch, tiles = (L + 127) / 128;
-    affine_from_partials_kernel<<<(rows + 127) / 128, 128, 0, st>>>(part, ch, tiles, L, rows, eps, bn.g + bn_off, bn.b + bn_off, bn.rm + bn_off,
+    affine_from_partials_kernel<<<(rows + 7) / 8, 256, 0, st>>>(part, ch, tiles, L, rows, eps, bn.g + bn_off, bn.b + bn_off, bn.rm + bn_off,
                                                                     bn.rv + bn_off, W.scale, W.shift, out_stride, out_off);
     return check_launch("affine_from_partials_kernel");
   };

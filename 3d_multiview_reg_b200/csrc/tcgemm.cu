@@ -41,8 +41,8 @@ constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 4 * 32 
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {   // 16-byte aligned, multiple of 16
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+__device__ __forceinline__ void l2_prefetch_line(const void* src) {   // one 128-byte line into L2 (LSU path, not the TMA unit)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -93,6 +93,17 @@ __global__ void split_weights_kernel(const float* __restrict__ Wb, int M, int K,
   split8_store(x, base, base + OP_BYTES);
 }
 
+// cycle counters for timing experiments (LMPCR_TC_DEBUG bit 8): one representative thread per role accumulates here
+__device__ unsigned long long g_tc_prof[16];
+#define TC_PROF(slot, t0)                                                                  \
+  do {                                                                                     \
+    if (g.debug & 256) {                                                                   \
+      const long long _t = clock64();                                                      \
+      if (prof_me) atomicAdd(&g_tc_prof[slot], (unsigned long long)(_t - (t0)));           \
+      (t0) = clock64();                                                                    \
+    }                                                                                      \
+  } while (0)
+
 template <bool B_KMAJOR>
 __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int batch) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -108,6 +119,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
   auto T_EMPTY = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool prof_me = (blockIdx.x == 0) && (threadIdx.x == 32 || threadIdx.x == 32 * FIRST_EPI_WARP || threadIdx.x == 32 * FIRST_PROD_WARP);
+  long long tp = clock64();
   const bool a_blob = g.a_blob != nullptr;
   const int tiles_m = (g.M + TM - 1) / TM, tiles_n = (g.N + TN - 1) / TN, n_kc = (g.K + KC - 1) / KC;
   const long long n_tiles = (long long)batch * tiles_m * tiles_n;
@@ -124,12 +137,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto decode = [&](long long tile, int& p, int& mt, int& nt) {
-    const int per = tiles_m * tiles_n;
-    p = (int)(tile / per);
-    const int r = (int)(tile - (long long)p * per);
-    mt = r % tiles_m;            // m fastest: CTAs that share a B tile run next to each other (L2 reuse)
-    nt = r / tiles_m;
+  const unsigned per_batch = (unsigned)(tiles_m * tiles_n);
+  auto decode = [&](long long tile, int& p, int& mt, int& nt) {   // n_tiles < 2^31 (checked on the host): 32-bit divides
+    const unsigned t = (unsigned)tile;
+    const unsigned pp = t / per_batch, r = t - pp * per_batch;
+    const unsigned q = r / (unsigned)tiles_m;
+    p = (int)pp;
+    mt = (int)(r - q * (unsigned)tiles_m);   // m fastest: CTAs that share a B tile run next to each other (L2 reuse)
+    nt = (int)q;
   };
 
   if (warp == 0) {
@@ -142,29 +157,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
     const bool pf_res = g.Res && tc_fast_epilogue(g);
     auto prefetch_chunk = [&](long long tile, int kc) {
       int p, mt, nt; decode(tile, p, mt, nt);
-      const float* Bp = g.B + (long long)p * g.b_batch;
+      const char* Bp = reinterpret_cast<const char*>(g.B + (long long)p * g.b_batch);
       if (pf_ok) {
-        if (B_KMAJOR) {
+        if (B_KMAJOR) {          // 128 rows (j) x 256 bytes: 2 lines per row
           const int nb = min(KC, g.K - kc * KC) * 4;
-          if (nb > 0 && (nb & 15) == 0)
-            for (int r = lane; r < TN; r += 32) {
-              const int j = nt * TN + r;
-              if (j < g.N) l2_prefetch(Bp + (long long)j * g.b_ld + kc * KC, nb);
-            }
-        } else {
+          for (int q = lane; q < TN * 2; q += 32) {
+            const int j = nt * TN + (q >> 1), off = (q & 1) * 128;
+            if (j < g.N && off < nb) l2_prefetch_line(Bp + ((long long)j * g.b_ld + kc * KC) * 4 + off);
+          }
+        } else {                 // 64 rows (k) x 512 bytes: 4 lines per row
           const int nb = min(TN, g.N - nt * TN) * 4;
-          if (nb > 0 && (nb & 15) == 0)
-            for (int r = lane; r < KC; r += 32) {
-              const int k = kc * KC + r;
-              if (k < g.K) l2_prefetch(Bp + (long long)k * g.b_ld + nt * TN, nb);
-            }
+          for (int q = lane; q < KC * 4; q += 32) {
+            const int k = kc * KC + (q >> 2), off = (q & 3) * 128;
+            if (k < g.K && off < nb) l2_prefetch_line(Bp + ((long long)k * g.b_ld + nt * TN) * 4 + off);
+          }
         }
       }
-      if (pf_res && kc == 0) {
+      if (pf_res && kc == 0) {   // residual rows of the tile: 128 rows x 512 bytes
         const int nb = min(TN, g.N - nt * TN) * 4;
-        for (int r = lane; r < TM; r += 32) {
-          const int i = mt * TM + r;
-          if (i < g.M) l2_prefetch(g.Res + (long long)p * g.r_batch + (long long)i * g.c_i + nt * TN, nb);
+        const char* Rp = reinterpret_cast<const char*>(g.Res + (long long)p * g.r_batch);
+        for (int q = lane; q < TM * 4; q += 32) {
+          const int i = mt * TM + (q >> 2), off = (q & 3) * 128;
+          if (i < g.M && off < nb) l2_prefetch_line(Rp + ((long long)i * g.c_i + nt * TN) * 4 + off);
         }
       }
     };
@@ -197,12 +211,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
       constexpr uint32_t B_LBO = B_KMAJOR ? K_LBO : MN_LBO, B_SBO = B_KMAJOR ? K_SBO : MN_SBO;
       int stage = 0, acc = 0; uint32_t phase = 0, acc_phase = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        TC_PROF(2, tp);
         mbar_wait(T_EMPTY(acc), acc_phase ^ 1);
         tc_fence_after();
+        TC_PROF(0, tp);
         const uint32_t d_tmem = tmem_base + acc * TN;
         for (int kc = 0; kc < n_kc; ++kc) {
           mbar_wait(FULL(stage), phase);
           tc_fence_after();
+          TC_PROF(1, tp);
           const uint32_t sA = smem_u32(smem + (size_t)stage * STAGE_BYTES), sB = sA + 2 * OP_BYTES;
 #pragma unroll
           for (int ks = 0; ks < ((g.debug & 16) ? 0 : KC / 16); ++ks) {
@@ -216,6 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
           }
           tc_commit(EMPTY(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          TC_PROF(2, tp);
         }
         tc_commit(T_FULL(acc));
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -225,13 +243,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
     // ===================== operand producers =====================
     // Software-pipelined: the fp32 values of the NEXT 64-chunk are fetched into registers right after the current
     // chunk has been converted, so the global-memory round trip overlaps the wait for a free stage.
+    // Interior chunks (fully inside the matrix, 16-byte aligned rows) take a branch-free path; edge chunks a guarded one.
     const int pw = warp - FIRST_PROD_WARP;
     const int l8 = lane & 7, g4 = lane >> 3;
     constexpr int NIT = 32 / N_PROD_WARPS;     // warp-iterations per operand chunk
+    const bool b_aligned = ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && ((g.b_ld & 3) == 0) && ((g.b_batch & 3) == 0);
+    const bool p_aligned = !g.p0 || (((reinterpret_cast<uintptr_t>(g.p0) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.p1) & 15) == 0) && ((g.p_batch & 3) == 0));
     float xb[NIT][8];
     int nvb[NIT];
+    bool interior = false;                     // state of the chunk currently held in xb (warp-uniform)
     auto fetch_b = [&](long long tile, int kc) {
       int p, mt, nt; decode(tile, p, mt, nt);
+      const float* Bp = g.B + (long long)p * g.b_batch;
+      interior = b_aligned && p_aligned && ((kc + 1) * KC <= g.K) && ((nt + 1) * TN <= g.N) && !(g.debug & 1);
       if (g.debug & 1) {
 #pragma unroll
         for (int u = 0; u < NIT; ++u) { nvb[u] = 8;
@@ -239,7 +263,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
           for (int e = 0; e < 8; ++e) xb[u][e] = 1.0f; }
         return;
       }
-      const float* Bp = g.B + (long long)p * g.b_batch;
+      if (interior) {
+#pragma unroll
+        for (int u = 0; u < NIT; ++u) {
+          const int it = pw + u * N_PROD_WARPS;
+          const float* src = B_KMAJOR ? Bp + (long long)(nt * TN + (it >> 1) * 8 + l8) * g.b_ld + kc * KC + (it & 1) * 32 + g4 * 8
+                                      : Bp + (long long)(kc * KC + (it >> 2) * 8 + l8) * g.b_ld + nt * TN + (it & 3) * 32 + g4 * 8;
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          xb[u][0] = a.x; xb[u][1] = a.y; xb[u][2] = a.z; xb[u][3] = a.w; xb[u][4] = b.x; xb[u][5] = b.y; xb[u][6] = b.z; xb[u][7] = b.w;
+          nvb[u] = 8;
+        }
+        return;
+      }
 #pragma unroll
       for (int u = 0; u < NIT; ++u) {
         const int it = pw + u * N_PROD_WARPS;
@@ -264,56 +299,80 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
       const float* q0 = g.p0 ? g.p0 + (long long)p * g.p_batch : nullptr;
       const float* q1 = g.p1 ? g.p1 + (long long)p * g.p_batch : nullptr;
       for (int kc = 0; kc < n_kc; ++kc) {
-        // prologue parameters of this chunk (L1/L2 hits; fetched before the wait)
-        float ps[NIT][8], pt[NIT][8];
+        // per-k affine of the j-major layout: two scalars per warp-iteration, fetched before the wait
+        float sc_u[NIT], sh_u[NIT];
 #pragma unroll
         for (int u = 0; u < NIT; ++u) {
-          const int it = pw + u * N_PROD_WARPS;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { ps[u][e] = 0.f; pt[u][e] = 0.f; }
-          if (g.prologue != TC_PRO_NONE && nvb[u] > 0 && !(g.debug & 64)) {
-            if (B_KMAJOR) {
-              const int rg = it >> 1, kb = it & 1;
-              const int j = nt * TN + rg * 8 + l8, k0 = kc * KC + kb * 32 + g4 * 8;
-              if (g.prologue == TC_PRO_AFFINE_RELU) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) if (e < nvb[u]) { ps[u][e] = __ldg(q0 + k0 + e); pt[u][e] = __ldg(q1 + k0 + e); }
-              } else {
-                ps[u][0] = __ldg(q0 + j); pt[u][0] = __ldg(q1 + j);
-              }
-            } else {
-              const int kg = it >> 2, nb = it & 3;
-              const int k = kc * KC + kg * 8 + l8, j0 = nt * TN + nb * 32 + g4 * 8;
-              if (g.prologue == TC_PRO_AFFINE_RELU) {
-                ps[u][0] = __ldg(q0 + k); pt[u][0] = __ldg(q1 + k);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) if (e < nvb[u]) { ps[u][e] = __ldg(q0 + j0 + e); pt[u][e] = __ldg(q1 + j0 + e); }
-              }
-            }
+          sc_u[u] = 1.f; sh_u[u] = 0.f;
+          if (!B_KMAJOR && g.prologue == TC_PRO_AFFINE_RELU && !(g.debug & 64)) {
+            const int k = kc * KC + ((pw + u * N_PROD_WARPS) >> 2) * 8 + l8;
+            if (k < g.K) { sc_u[u] = __ldg(q0 + k); sh_u[u] = __ldg(q1 + k); }
           }
         }
+        TC_PROF(6, tp);
         mbar_wait(EMPTY(stage), phase ^ 1);
+        TC_PROF(3, tp);
         uint8_t* st_base = smem + (size_t)stage * STAGE_BYTES;
         // ---- B operand: prologue, hi/lo split, store in the UMMA canonical layout ----
-        if (!(g.debug & 2))
+        if (!(g.debug & 2)) {
 #pragma unroll
-        for (int u = 0; u < NIT; ++u) {
-          const int it = pw + u * N_PROD_WARPS;
-          const bool per_elem = B_KMAJOR ? (g.prologue == TC_PRO_AFFINE_RELU) : (g.prologue == TC_PRO_SOFTMAX);
-          if (g.prologue == TC_PRO_AFFINE_RELU) {
+          for (int u = 0; u < NIT; ++u) {
+            const int it = pw + u * N_PROD_WARPS;
+            if (interior) {
+              if (g.prologue == TC_PRO_AFFINE_RELU) {
+                if (B_KMAJOR) {                 // per-k parameters, 8 consecutive k per lane
+                  const int k0 = kc * KC + (it & 1) * 32 + g4 * 8;
+                  const float4 s0 = __ldg(reinterpret_cast<const float4*>(q0 + k0)), s1 = __ldg(reinterpret_cast<const float4*>(q0 + k0) + 1);
+                  const float4 t0 = __ldg(reinterpret_cast<const float4*>(q1 + k0)), t1 = __ldg(reinterpret_cast<const float4*>(q1 + k0) + 1);
+                  const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (e < nvb[u]) xb[u][e] = fmaxf(fmaf(xb[u][e], per_elem ? ps[u][e] : ps[u][0], per_elem ? pt[u][e] : pt[u][0]), 0.f);
-          } else if (g.prologue == TC_PRO_SOFTMAX) {
+                  for (int e = 0; e < 8; ++e) xb[u][e] = fmaxf(fmaf(xb[u][e], ss[e], tt[e]), 0.f);
+                } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (e < nvb[u]) xb[u][e] = __expf(xb[u][e] - (per_elem ? ps[u][e] : ps[u][0])) * (per_elem ? pt[u][e] : pt[u][0]);
+                  for (int e = 0; e < 8; ++e) xb[u][e] = fmaxf(fmaf(xb[u][e], sc_u[u], sh_u[u]), 0.f);
+                }
+              } else if (g.prologue == TC_PRO_SOFTMAX) {
+                if (B_KMAJOR) {                 // per-row (j) parameters
+                  const int j = nt * TN + (it >> 1) * 8 + l8;
+                  const float m = __ldg(q0 + j), inv = __ldg(q1 + j);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) xb[u][e] = __expf(xb[u][e] - m) * inv;
+                } else {                        // per-column (j) parameters, 8 consecutive j per lane
+                  const int j0 = nt * TN + (it & 3) * 32 + g4 * 8;
+                  const float4 m0 = __ldg(reinterpret_cast<const float4*>(q0 + j0)), m1 = __ldg(reinterpret_cast<const float4*>(q0 + j0) + 1);
+                  const float4 i0 = __ldg(reinterpret_cast<const float4*>(q1 + j0)), i1 = __ldg(reinterpret_cast<const float4*>(q1 + j0) + 1);
+                  const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w}, ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) xb[u][e] = __expf(xb[u][e] - mm[e]) * ii[e];
+                }
+              }
+            } else if (g.prologue != TC_PRO_NONE && nvb[u] > 0) {      // guarded edge path (same arithmetic)
+              if (B_KMAJOR) {
+                const int j = nt * TN + (it >> 1) * 8 + l8, k0 = kc * KC + (it & 1) * 32 + g4 * 8;
+                if (g.prologue == TC_PRO_AFFINE_RELU) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = fmaxf(fmaf(xb[u][e], __ldg(q0 + k0 + e), __ldg(q1 + k0 + e)), 0.f);
+                } else {
+                  const float m = __ldg(q0 + j), inv = __ldg(q1 + j);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = __expf(xb[u][e] - m) * inv;
+                }
+              } else {
+                const int j0 = nt * TN + (it & 3) * 32 + g4 * 8;
+                if (g.prologue == TC_PRO_AFFINE_RELU) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = fmaxf(fmaf(xb[u][e], sc_u[u], sh_u[u]), 0.f);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = __expf(xb[u][e] - __ldg(q0 + j0 + e)) * __ldg(q1 + j0 + e);
+                }
+              }
+            }
+            uint32_t off;
+            if (B_KMAJOR) off = (it >> 1) * K_SBO + ((it & 1) * 4 + g4) * K_LBO + l8 * 16;
+            else off = ((it & 3) * 4 + g4) * MN_SBO + (it >> 2) * MN_LBO + l8 * 16;
+            split8_store(xb[u], st_base + 2 * OP_BYTES + off, st_base + 3 * OP_BYTES + off);
           }
-          uint32_t off;
-          if (B_KMAJOR) off = (it >> 1) * K_SBO + ((it & 1) * 4 + g4) * K_LBO + l8 * 16;
-          else off = ((it & 3) * 4 + g4) * MN_SBO + (it >> 2) * MN_LBO + l8 * 16;
-          split8_store(xb[u], st_base + 2 * OP_BYTES + off, st_base + 3 * OP_BYTES + off);
         }
         // ---- A operand from fp32 activations (k contiguous): all loads of the chunk in flight together ----
         if (!a_blob) {
@@ -332,10 +391,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
             split8_store(xb[u], st_base + off, st_base + OP_BYTES + off);
           }
         }
+        TC_PROF(4, tp);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(FULL(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        TC_PROF(5, tp);
         // ---- prefetch the next chunk's B values ----
         if (kc + 1 < n_kc) fetch_b(tile, kc + 1);
         else if (tile + gridDim.x < n_tiles) fetch_b(tile + gridDim.x, 0);
@@ -373,13 +434,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
         int p, mt, nt; decode(tile, p, mt, nt);
         const int i = mt * TM + r_own;
         const float bias_own = (g.bias && i < g.M) ? __ldg(g.bias + i) : 0.f;
+        TC_PROF(11, tp);
         mbar_wait(T_FULL(acc), acc_phase);
         tc_fence_after();
+        TC_PROF(7, tp);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN;
         const int ncv = min(TN, g.N - nt * TN);      // valid columns of this tile (multiple of 4 on this path)
         float c0 = 0.f, s1 = 0.f, s2 = 0.f, vmax = -INFINITY;
         const bool has_res = pending;
         if (has_res) { mbar_wait(my_bar, par); par ^= 1; }
+        TC_PROF(8, tp);
         // ---- phase 1: thread = row.  accumulator + bias + residual, in place in this thread's staged row ----
 #pragma unroll
         for (int cc = 0; cc < ((g.debug & 32) ? 0 : TN / 32); ++cc) {
@@ -405,6 +469,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
         tc_fence_before();
         mbar_arrive(T_EMPTY(acc));
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        TC_PROF(9, tp);
         if (i < g.M) {
           const long long so = (((long long)p * g.M + i) * tiles_n + nt) * 2;
           if (g.stats_out) {
@@ -425,6 +490,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
           }
         }
         // ---- phase 2: warp = 32 rows.  Each row leaves as one coalesced 512-byte store (lane = 4 columns) ----
+        TC_PROF(10, tp);
         __syncwarp();
         {
           float* Cp = g.C + (long long)p * g.c_batch + nt * TN + 4 * lane;
@@ -525,6 +591,13 @@ int launch_split_weights(const float* W, int M, int K, uint8_t* blob, cudaStream
   return check_launch("split_weights_kernel");
 }
 
+int tc_profile_read(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z)); }
+  return e == cudaSuccess ? 0 : -1;
+}
+
 int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
   TcGemmArgs a = a_in;
   static int dbg = -1;
@@ -539,6 +612,7 @@ int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
     attr_set = true;
   }
   const long long tiles = (long long)batch * ((a.M + TM - 1) / TM) * ((a.N + TN - 1) / TN);
+  LMPCR_REQUIRE(tiles < (1ll << 31), LMPCR_ERR_ARG, "tcgemm: too many tiles");
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (a.b_kmajor) tcgemm_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, batch);
   else tcgemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, batch);

@@ -41,5 +41,6 @@ size_t tc_weight_blob_bytes(int M, int K);
 // W[b] = W + b*w_batch, rows `ld` floats apart (k contiguous); blob[b] = blob + b*tc_weight_blob_bytes(M,K)
 int launch_split_weights(const float* W, int M, int K, uint8_t* blob, cudaStream_t st, int batch = 1, long long w_batch = 0, int ld = -1);
 int launch_tcgemm(const TcGemmArgs& a, int batch, cudaStream_t st);
+int tc_profile_read(unsigned long long* out16, int reset);   // timing experiments (LMPCR_TC_DEBUG bit 8)
 
 }  // namespace lmpcr

@@ -288,7 +288,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scans", type=int, default=60)
     ap.add_argument("--points", type=int, default=5000)
-    ap.add_argument("--pair-chunk", type=int, default=256)
+    ap.add_argument("--pair-chunk", type=int, default=296)
     ap.add_argument("--nn-algo", type=int, default=int(os.environ.get("LMPCR_NN_ALGO", "1")))
     ap.add_argument("--gemm-algo", type=int, default=int(os.environ.get("LMPCR_GEMM_ALGO", "1")))
     ap.add_argument("--ref-pairs", type=int, default=12)

@@ -88,6 +88,9 @@ int lmpcr_nn_tensor_debug(const float* q_feat, int n_q_sets, int n_q, const floa
                           const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, float* scores, float* approx_min,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Diagnostic: per-role cycle counters of the tensor-core GEMM (filled only when LMPCR_TC_DEBUG has bit 8 set). */
+int lmpcr_debug_tc_profile(unsigned long long* out16, int reset);
+
 /* lib/utils.py:968-992 `pairwise_distance` itself, materialised: src [B,n,dim], dst [B,m,dim] -> out [B,n,m] fp32,
  * bit-identical to the reference's CPU evaluation.  Not on the hot path (which never stores the matrix); kept so
  * that `lib.utils.pairwise_distance` stays importable.  workspace >= 256-aligned (B*n + B*m) floats. */

@@ -25,3 +25,15 @@ for _ in range(a.iters):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
 print("gemm_algo %d: %.2f ms per call, %.1f us/pair, %.1f TFLOP/s algorithmic" % (a.algo, ms, 1e3 * ms / a.pairs, a.pairs * 10.636e9 / ms / 1e9))
+
+import ctypes
+if int(os.environ.get("LMPCR_TC_DEBUG", "0")) & 256:
+    buf = (ctypes.c_ulonglong * 16)()
+    cabi.load().lmpcr_debug_tc_profile(buf, 1)
+    cabi.filter_forward(xs, params, cfg, want_latent=False)
+    cabi.load().lmpcr_debug_tc_profile(buf, 1)
+    names = ["mma wait T_EMPTY", "mma wait FULL", "mma issue", "prod wait EMPTY", "prod convert", "prod fence+arrive", "prod fetch/params",
+             "epi wait T_FULL", "epi wait residual", "epi phase1", "epi stats", "epi phase2 stores"]
+    tot = 1.0
+    for i, n in enumerate(names):
+        print("%-20s %10.3f Mcycles" % (n, buf[i] / 1e6))
