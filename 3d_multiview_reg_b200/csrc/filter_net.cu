@@ -330,7 +330,7 @@ __global__ void affine_from_partials_kernel(const float* __restrict__ part, int 
   const float* q = part + (size_t)row * tiles * 2;
   float n = 0.f, mean = 0.f, M2 = 0.f;
   for (int t = lane; t < tiles; t += 32) {
-    const float nb = (float)min(128, L - t * 128);
+    const float nb = (float)min(TC_TILE_N, L - t * TC_TILE_N);
     const float2 v = __ldg(reinterpret_cast<const float2*>(q) + t);
     const float delta = v.x - mean, nn = n + nb;
     mean += delta * (nb / nn);
@@ -446,7 +446,7 @@ inline size_t r64(size_t n) { return (n + 63) / 64 * 64; }   // every per-pair b
 
 // per-pair workspace, in floats: the carve in launch_filter_forward takes the same terms in the same order
 size_t per_pair_floats(int C, int K, int N) {
-  const size_t L = (size_t)(N > K ? N : K), tmax = (L + 127) / 128;
+  const size_t L = (size_t)(N > K ? N : K), tmax = (L + TC_TILE_N - 1) / TC_TILE_N;
   size_t f = r64((size_t)12 * N) + 3 * r64((size_t)C * N) + r64((size_t)2 * C * N) + r64((size_t)K * N) + 4 * r64((size_t)C * K) + 2 * r64(1024) + 2 * r64(L);
   f += (size_t)N_PART * r64((size_t)C * tmax * 2) + r64((size_t)K * tmax * 2);            // norm / softmax partials
   f += r64(tc_weight_blob_bytes(C, K) / 4) + r64(tc_weight_blob_bytes(C, N) / 4);        // pre-split x2 / x1_1 (pool, unpool A operands)
@@ -540,7 +540,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   W.scale = take(1024); W.shift = take(1024);
   float* sm_max = take((size_t)(N > K ? N : K));
   float* sm_inv = take((size_t)(N > K ? N : K));
-  const int tmax = ((N > K ? N : K) + 127) / 128, tilesN = (N + 127) / 128;
+  const int tmax = ((N > K ? N : K) + TC_TILE_N - 1) / TC_TILE_N, tilesN = (N + TC_TILE_N - 1) / TC_TILE_N;
   bool want_sm = false;   // set around the diff_pool embedding conv: its epilogue also emits softmax-over-points partials
   float* part_buf[N_PART];
   const float* part_key[N_PART] = {W.T0, W.T1, W.T2, W.CAT, W.CAT + (size_t)C * N, W.XD0, W.XD1};
@@ -565,7 +565,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     return check_launch("in_affine_kernel");
   };
   auto aff_part = [&](const float* part, int ch, int L, int g, float eps, const BNP& bn, int bn_off, int out_stride, int out_off) -> int {
-    const int rows = g * ch, tiles = (L + 127) / 128;
+    const int rows = g * ch, tiles = (L + TC_TILE_N - 1) / TC_TILE_N;
     affine_from_partials_kernel<<<(rows + 7) / 8, 256, 0, st>>>(part, ch, tiles, L, rows, eps, bn.g + bn_off, bn.b + bn_off, bn.rm + bn_off,
                                                                     bn.rv + bn_off, W.scale, W.shift, out_stride, out_off);
     return check_launch("affine_from_partials_kernel");

@@ -6,14 +6,17 @@
 // evaluated as A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with fp32 accumulation in TMEM -- the 1x1 convolutions of
 // lib/filtering/oanet.py need fp32-faithful products (TF32 moves the estimated pose by 4e-3 rad).
 //
-// Persistent, warp-specialised CTA (512 threads), one 128x128 output tile at a time, K in chunks of 64:
-//   warp 0      TMA bulk copies of the pre-split weight tile (A) into the stage          (only when A is a weight blob)
-//   warp 1      tcgen05.mma issue: per 64-chunk 4 K-steps x 3 products, M128 x N128 x K16, accumulators in TMEM
-//   warps 4-7   epilogue: tcgen05.ld -> +bias +residual -> shared-memory transpose -> coalesced stores
-//   warps 8-15  operand producers: load fp32 activations, apply the fused prologue (InstanceNorm+BatchNorm affine and
+// Persistent, warp-specialised CTAs of 320 threads, TWO per SM (108 KB of shared memory, 128 TMEM columns, <=102
+// registers each) so that one CTA's epilogue overlaps the other's operand production.  One 128 x 64 output tile at a
+// time, K in chunks of 32:
+//   warp 0      TMA bulk copies of the pre-split weight tile (A) into the stage + L2 prefetch of the B / residual rows
+//   warp 1      tcgen05.mma issue: per chunk 2 K-steps x 3 products, M128 x N64 x K16, accumulators in TMEM
+//   warps 2-5   epilogue: tcgen05.ld -> +bias +residual (row prefetched by TMA) -> per-row statistics -> staged tile ->
+//               coalesced 256-byte row stores
+//   warps 6-9   operand producers: load fp32 activations, apply the fused prologue (InstanceNorm+BatchNorm affine and
 //               ReLU, or the softmax normalisation exp(x-max)/sum), split into hi/lo bf16 and store them straight
 //               in the UMMA canonical (no-swizzle) layout -- normalised activations never touch HBM.
-// Pipelines: 3-stage shared-memory ring (full/empty mbarriers), double-buffered TMEM accumulator (128 columns each).
+// Pipelines: 3-stage shared-memory ring (full/empty mbarriers), double-buffered TMEM accumulator (64 columns each).
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
@@ -24,29 +27,27 @@
 namespace lmpcr {
 namespace {
 
-constexpr int TM = 128, TN = 128, KC = 64;
-constexpr int STAGES = 2;
-constexpr int OP_BYTES = 128 * KC * 2;       // one bf16 operand tile (hi or lo): 16 KB
-constexpr int STAGE_BYTES = 4 * OP_BYTES;    // [A_hi][A_lo][B_hi][B_lo]
-constexpr int N_PROD_WARPS = 8;
-constexpr int FIRST_EPI_WARP = 4, FIRST_PROD_WARP = 8;
-constexpr int NTHREADS = 32 * (FIRST_PROD_WARP + N_PROD_WARPS);   // 512
-constexpr uint32_t K_LBO = 128, K_SBO = (KC / 8) * 128;           // K-major operand: k-groups adjacent, 8-row groups 1 KB apart
-constexpr uint32_t MN_SBO = 128, MN_LBO = (TN / 8) * 128;         // MN-major operand: j-groups adjacent, k-groups 2 KB apart
-constexpr int TR_LD = 33;                                         // padded row of the (generic) epilogue transpose buffer
-constexpr int STG_ROW = TN * 4 + 16;                              // 528 B: 16-byte aligned, conflict-free for float4 at one row per lane
-constexpr int STG_BYTES = TM * STG_ROW;                           // 67584: one staged output tile
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 4 * 32 * TR_LD * 4 + 2 * 128 * 8 + 16 * 8 + 16;
+constexpr int TM = 128, TN = TC_TILE_N, KC = 32;
+constexpr int STAGES = 3;
+constexpr int A_OP_BYTES = TM * KC * 2;      // one bf16 A tile (hi or lo): 8 KB
+constexpr int B_OP_BYTES = TN * KC * 2;      // one bf16 B tile (hi or lo): 4 KB
+constexpr int STAGE_BYTES = 2 * A_OP_BYTES + 2 * B_OP_BYTES;   // [A_hi][A_lo][B_hi][B_lo] = 24 KB
+constexpr int N_PROD_WARPS = 4;
+constexpr int FIRST_EPI_WARP = 2, FIRST_PROD_WARP = 6;
+constexpr int NTHREADS = 32 * (FIRST_PROD_WARP + N_PROD_WARPS);   // 320
+constexpr int TMEM_COLS = 2 * TN;                                  // two accumulators (power of two >= 32)
+constexpr uint32_t K_LBO = 128, K_SBO = (KC / 8) * 128;           // K-major operand: k-groups adjacent, 8-row groups 512 B apart
+constexpr uint32_t MN_SBO = 128, MN_LBO = (TN / 8) * 128;         // MN-major operand: j-groups adjacent, k-groups 1 KB apart
+constexpr int TR_LD = 33;                                         // padded row of the generic epilogue's transpose buffer
+constexpr int STG_ROW = TN * 4 + 16;                              // 272 B: 16-byte aligned, conflict-free for float4 at one row per lane
+constexpr int STG_BYTES = TM * STG_ROW;                           // 34816: one staged output tile (also hosts the transpose buffers)
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 128 * 8 + 16 * 8 + 16;
+static_assert(4 * 32 * TR_LD * 4 <= STG_BYTES, "transpose buffers must fit the staging area");
+static_assert(TN % 32 == 0 && TN <= 128, "tile width");
 
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void l2_prefetch_line(const void* src) {   // one 128-byte line into L2 (LSU path, not the TMA unit)
   asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void split8_store(const float (&x)[8], uint8_t* hi_dst, uint8_t* lo_dst) {
   uint32_t h[4], l[4];
@@ -73,7 +74,7 @@ __device__ __forceinline__ void load8(const float* src, int nvalid, float (&x)[8
   }
 }
 
-// fp32 weights [M,K] (k contiguous) -> per (m-tile, k-chunk) blob [hi 16 KB | lo 16 KB], K-major canonical layout
+// fp32 rows [M,K] (k contiguous, `ld` floats apart) -> per (m-tile, k-chunk) blob [hi 8 KB | lo 8 KB], K-major canonical
 __global__ void split_weights_kernel(const float* __restrict__ Wb, int M, int K, uint8_t* __restrict__ blobb, long long w_batch, int ld,
                                      long long blob_batch) {
   const float* W = Wb + (long long)blockIdx.y * w_batch;
@@ -89,8 +90,8 @@ __global__ void split_weights_kernel(const float* __restrict__ Wb, int M, int K,
   float x[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) x[e] = (row < M && k0 + e < K) ? __ldg(W + (size_t)row * ld + k0 + e) : 0.f;
-  uint8_t* base = blob + ((size_t)mt * n_kc + kc) * 2 * OP_BYTES + (r >> 3) * K_SBO + kg * K_LBO + (r & 7) * 16;
-  split8_store(x, base, base + OP_BYTES);
+  uint8_t* base = blob + ((size_t)mt * n_kc + kc) * 2 * A_OP_BYTES + (r >> 3) * K_SBO + kg * K_LBO + (r & 7) * 16;
+  split8_store(x, base, base + A_OP_BYTES);
 }
 
 // cycle counters for timing experiments (LMPCR_TC_DEBUG bit 8): one representative thread per role accumulates here
@@ -105,12 +106,12 @@ __device__ unsigned long long g_tc_prof[16];
   } while (0)
 
 template <bool B_KMAJOR>
-__global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int batch) {
+__global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int batch) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;                                  // [128 rows][STG_ROW]
-  float* trbuf = reinterpret_cast<float*>(stg + STG_BYTES);                            // [4 warps][32][TR_LD]
-  uint64_t* rowbars = reinterpret_cast<uint64_t*>(trbuf + 4 * 32 * TR_LD);             // [2 halves][128 rows]
-  uint64_t* bars = rowbars + 2 * 128;
+  uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;                  // [128 rows][STG_ROW]
+  float* trbuf = reinterpret_cast<float*>(stg);                        // generic epilogue: [4 warps][32][TR_LD] (aliases stg)
+  uint64_t* rowbars = reinterpret_cast<uint64_t*>(stg + STG_BYTES);    // [128 rows]
+  uint64_t* bars = rowbars + 128;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const uint32_t bar0 = smem_u32(bars);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -129,9 +130,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
     for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), N_PROD_WARPS + (a_blob ? 1 : 0)); mbar_init(EMPTY(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(T_FULL(a), 1); mbar_init(T_EMPTY(a), 128); }
   }
-  if (threadIdx.x < 256) mbar_init(smem_u32(rowbars + threadIdx.x), 1);
+  if (threadIdx.x < 128) mbar_init(smem_u32(rowbars + threadIdx.x), 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256u);   // two 128-column fp32 accumulators
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -149,35 +150,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
 
   if (warp == 0) {
     // ===================== TMA producer for the weight blob + L2 prefetcher =====================
-    // The activations of a group of pairs do not fit L2, so a producer warp would see the full HBM latency once per
-    // 64-chunk.  This warp runs PF_CHUNKS chunks ahead of the pipeline and pulls the B rows (and the residual rows of the
-    // tile) into L2 with cp.async.bulk.prefetch.L2 -- no registers, no shared memory.
-    constexpr int PF_CHUNKS = 6;
+    // The activations of a group of pairs do not fit L2; this warp runs PF_CHUNKS chunks ahead of the pipeline and pulls
+    // the B rows (and the residual rows of the tile) into L2 with prefetch.global.L2.
+    constexpr int PF_CHUNKS = 8;
     const bool pf_ok = ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && ((g.b_ld & 3) == 0) && ((g.b_batch & 3) == 0);
     const bool pf_res = g.Res && tc_fast_epilogue(g);
     auto prefetch_chunk = [&](long long tile, int kc) {
       int p, mt, nt; decode(tile, p, mt, nt);
       const char* Bp = reinterpret_cast<const char*>(g.B + (long long)p * g.b_batch);
       if (pf_ok) {
-        if (B_KMAJOR) {          // 128 rows (j) x 256 bytes: 2 lines per row
+        if (B_KMAJOR) {          // TN rows (j) x 128 bytes
           const int nb = min(KC, g.K - kc * KC) * 4;
-          for (int q = lane; q < TN * 2; q += 32) {
-            const int j = nt * TN + (q >> 1), off = (q & 1) * 128;
-            if (j < g.N && off < nb) l2_prefetch_line(Bp + ((long long)j * g.b_ld + kc * KC) * 4 + off);
+          for (int q = lane; q < TN; q += 32) {
+            const int j = nt * TN + q;
+            if (j < g.N && nb > 0) l2_prefetch_line(Bp + ((long long)j * g.b_ld + kc * KC) * 4);
           }
-        } else {                 // 64 rows (k) x 512 bytes: 4 lines per row
+        } else {                 // KC rows (k) x TN*4 bytes
           const int nb = min(TN, g.N - nt * TN) * 4;
-          for (int q = lane; q < KC * 4; q += 32) {
-            const int k = kc * KC + (q >> 2), off = (q & 3) * 128;
+          for (int q = lane; q < KC * (TN / 32); q += 32) {
+            const int k = kc * KC + q / (TN / 32), off = (q % (TN / 32)) * 128;
             if (k < g.K && off < nb) l2_prefetch_line(Bp + ((long long)k * g.b_ld + nt * TN) * 4 + off);
           }
         }
       }
-      if (pf_res && kc == 0) {   // residual rows of the tile: 128 rows x 512 bytes
+      if (pf_res && kc == 0) {   // residual rows of the tile
         const int nb = min(TN, g.N - nt * TN) * 4;
         const char* Rp = reinterpret_cast<const char*>(g.Res + (long long)p * g.r_batch);
-        for (int q = lane; q < TM * 4; q += 32) {
-          const int i = mt * TM + (q >> 2), off = (q & 3) * 128;
+        for (int q = lane; q < TM * (TN / 32); q += 32) {
+          const int i = mt * TM + q / (TN / 32), off = (q % (TN / 32)) * 128;
           if (i < g.M && off < nb) l2_prefetch_line(Rp + ((long long)i * g.c_i + nt * TN) * 4 + off);
         }
       }
@@ -196,9 +196,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
         pf_advance();
         mbar_wait(EMPTY(stage), phase ^ 1);      // paces the prefetcher with the pipeline
         if (a_blob && lane == 0) {
-          mbar_expect_tx(FULL(stage), 2 * OP_BYTES);
-          bulk_g2s(smem_u32(smem + (size_t)stage * STAGE_BYTES), g.a_blob + (long long)p * g.a_blob_batch + ((size_t)mt * n_kc + kc) * 2 * OP_BYTES,
-                   2 * OP_BYTES, FULL(stage));
+          mbar_expect_tx(FULL(stage), 2 * A_OP_BYTES);
+          bulk_g2s(smem_u32(smem + (size_t)stage * STAGE_BYTES), g.a_blob + (long long)p * g.a_blob_batch + ((size_t)mt * n_kc + kc) * 2 * A_OP_BYTES,
+                   2 * A_OP_BYTES, FULL(stage));
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -220,13 +220,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
           mbar_wait(FULL(stage), phase);
           tc_fence_after();
           TC_PROF(1, tp);
-          const uint32_t sA = smem_u32(smem + (size_t)stage * STAGE_BYTES), sB = sA + 2 * OP_BYTES;
+          const uint32_t sA = smem_u32(smem + (size_t)stage * STAGE_BYTES), sB = sA + 2 * A_OP_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < ((g.debug & 16) ? 0 : KC / 16); ++ks) {
+          for (int ks = 0; ks < KC / 16; ++ks) {
             const uint64_t a_hi = make_desc(sA + ks * 2 * K_LBO, K_LBO, K_SBO);
-            const uint64_t a_lo = make_desc(sA + OP_BYTES + ks * 2 * K_LBO, K_LBO, K_SBO);
+            const uint64_t a_lo = make_desc(sA + A_OP_BYTES + ks * 2 * K_LBO, K_LBO, K_SBO);
             const uint64_t b_hi = make_desc(sB + ks * 2 * B_LBO, B_LBO, B_SBO);
-            const uint64_t b_lo = make_desc(sB + OP_BYTES + ks * 2 * B_LBO, B_LBO, B_SBO);
+            const uint64_t b_lo = make_desc(sB + B_OP_BYTES + ks * 2 * B_LBO, B_LBO, B_SBO);
             tc_mma_f16(d_tmem, a_lo, b_hi, IDESC, (kc | ks) ? 1u : 0u);   // small terms first
             tc_mma_f16(d_tmem, a_hi, b_lo, IDESC, 1u);
             tc_mma_f16(d_tmem, a_hi, b_hi, IDESC, 1u);
@@ -241,53 +241,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
     }
   } else if (warp >= FIRST_PROD_WARP) {
     // ===================== operand producers =====================
-    // Software-pipelined: the fp32 values of the NEXT 64-chunk are fetched into registers right after the current
-    // chunk has been converted, so the global-memory round trip overlaps the wait for a free stage.
+    // Software-pipelined: the fp32 values of the NEXT chunk are fetched into registers right after the current chunk
+    // has been converted, so the global-memory round trip overlaps the wait for a free stage.
     // Interior chunks (fully inside the matrix, 16-byte aligned rows) take a branch-free path; edge chunks a guarded one.
+    // Warp-iteration = 8 x 32 elements: lane = (l8 = position inside the 8-row core matrix, g4 = group of 8 contiguous elements).
     const int pw = warp - FIRST_PROD_WARP;
     const int l8 = lane & 7, g4 = lane >> 3;
-    constexpr int NIT = 32 / N_PROD_WARPS;     // warp-iterations per operand chunk
+    constexpr int B_ITERS = (KC / 8) * (TN / 32);      // 8 for a 32 x 64 chunk, either layout
+    constexpr int NIT = B_ITERS / N_PROD_WARPS;        // 2
+    constexpr int A_ITERS = (TM / 8) * (KC / 32), NIT_A = A_ITERS / N_PROD_WARPS;
     const bool b_aligned = ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && ((g.b_ld & 3) == 0) && ((g.b_batch & 3) == 0);
     const bool p_aligned = !g.p0 || (((reinterpret_cast<uintptr_t>(g.p0) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.p1) & 15) == 0) && ((g.p_batch & 3) == 0));
+    // element coordinates of warp-iteration `it`
+    //   j-major B (k rows, j contiguous): k = kc*KC + (it / (TN/32))*8 + l8,  j0 = nt*TN + (it % (TN/32))*32 + g4*8
+    //   k-major B (j rows, k contiguous): j = nt*TN + it*8 + l8,              k0 = kc*KC + g4*8
     float xb[NIT][8];
     int nvb[NIT];
     bool interior = false;                     // state of the chunk currently held in xb (warp-uniform)
     auto fetch_b = [&](long long tile, int kc) {
       int p, mt, nt; decode(tile, p, mt, nt);
       const float* Bp = g.B + (long long)p * g.b_batch;
-      interior = b_aligned && p_aligned && ((kc + 1) * KC <= g.K) && ((nt + 1) * TN <= g.N) && !(g.debug & 1);
-      if (g.debug & 1) {
-#pragma unroll
-        for (int u = 0; u < NIT; ++u) { nvb[u] = 8;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) xb[u][e] = 1.0f; }
-        return;
-      }
-      if (interior) {
-#pragma unroll
-        for (int u = 0; u < NIT; ++u) {
-          const int it = pw + u * N_PROD_WARPS;
-          const float* src = B_KMAJOR ? Bp + (long long)(nt * TN + (it >> 1) * 8 + l8) * g.b_ld + kc * KC + (it & 1) * 32 + g4 * 8
-                                      : Bp + (long long)(kc * KC + (it >> 2) * 8 + l8) * g.b_ld + nt * TN + (it & 3) * 32 + g4 * 8;
-          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-          xb[u][0] = a.x; xb[u][1] = a.y; xb[u][2] = a.z; xb[u][3] = a.w; xb[u][4] = b.x; xb[u][5] = b.y; xb[u][6] = b.z; xb[u][7] = b.w;
-          nvb[u] = 8;
-        }
-        return;
-      }
+      interior = b_aligned && p_aligned && ((kc + 1) * KC <= g.K) && ((nt + 1) * TN <= g.N);
 #pragma unroll
       for (int u = 0; u < NIT; ++u) {
         const int it = pw + u * N_PROD_WARPS;
-        if (B_KMAJOR) {                      // rows j (128) x k (64); lane: row = l8, k-group = g4
-          const int rg = it >> 1, kb = it & 1;
-          const int j = nt * TN + rg * 8 + l8, k0 = kc * KC + kb * 32 + g4 * 8;
+        const float* src;
+        if (B_KMAJOR) {
+          const int j = nt * TN + it * 8 + l8, k0 = kc * KC + g4 * 8;
           nvb[u] = (j < g.N) ? min(8, max(0, g.K - k0)) : 0;
-          load8(Bp + (long long)j * g.b_ld + k0, nvb[u], xb[u]);
-        } else {                             // k (64) x columns j (128); lane: k = l8, j-group = g4
-          const int kg = it >> 2, nb = it & 3;
-          const int k = kc * KC + kg * 8 + l8, j0 = nt * TN + nb * 32 + g4 * 8;
+          src = Bp + (long long)j * g.b_ld + k0;
+        } else {
+          const int k = kc * KC + (it / (TN / 32)) * 8 + l8, j0 = nt * TN + (it % (TN / 32)) * 32 + g4 * 8;
           nvb[u] = (k < g.K) ? min(8, max(0, g.N - j0)) : 0;
-          load8(Bp + (long long)k * g.b_ld + j0, nvb[u], xb[u]);
+          src = Bp + (long long)k * g.b_ld + j0;
+        }
+        if (interior) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          xb[u][0] = a.x; xb[u][1] = a.y; xb[u][2] = a.z; xb[u][3] = a.w; xb[u][4] = b.x; xb[u][5] = b.y; xb[u][6] = b.z; xb[u][7] = b.w;
+        } else {
+          load8(src, nvb[u], xb[u]);
         }
       }
     };
@@ -304,8 +296,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
 #pragma unroll
         for (int u = 0; u < NIT; ++u) {
           sc_u[u] = 1.f; sh_u[u] = 0.f;
-          if (!B_KMAJOR && g.prologue == TC_PRO_AFFINE_RELU && !(g.debug & 64)) {
-            const int k = kc * KC + ((pw + u * N_PROD_WARPS) >> 2) * 8 + l8;
+          if (!B_KMAJOR && g.prologue == TC_PRO_AFFINE_RELU) {
+            const int k = kc * KC + ((pw + u * N_PROD_WARPS) / (TN / 32)) * 8 + l8;
             if (k < g.K) { sc_u[u] = __ldg(q0 + k); sh_u[u] = __ldg(q1 + k); }
           }
         }
@@ -314,81 +306,72 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
         TC_PROF(3, tp);
         uint8_t* st_base = smem + (size_t)stage * STAGE_BYTES;
         // ---- B operand: prologue, hi/lo split, store in the UMMA canonical layout ----
-        if (!(g.debug & 2)) {
 #pragma unroll
-          for (int u = 0; u < NIT; ++u) {
-            const int it = pw + u * N_PROD_WARPS;
-            if (interior) {
-              if (g.prologue == TC_PRO_AFFINE_RELU) {
-                if (B_KMAJOR) {                 // per-k parameters, 8 consecutive k per lane
-                  const int k0 = kc * KC + (it & 1) * 32 + g4 * 8;
-                  const float4 s0 = __ldg(reinterpret_cast<const float4*>(q0 + k0)), s1 = __ldg(reinterpret_cast<const float4*>(q0 + k0) + 1);
-                  const float4 t0 = __ldg(reinterpret_cast<const float4*>(q1 + k0)), t1 = __ldg(reinterpret_cast<const float4*>(q1 + k0) + 1);
-                  const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        for (int u = 0; u < NIT; ++u) {
+          const int it = pw + u * N_PROD_WARPS;
+          const int jrow = nt * TN + it * 8 + l8, k0 = kc * KC + g4 * 8;                  // k-major coordinates
+          const int j0 = nt * TN + (it % (TN / 32)) * 32 + g4 * 8;                        // j-major coordinate
+          if (interior) {
+            if (g.prologue == TC_PRO_AFFINE_RELU) {
+              if (B_KMAJOR) {                 // per-k parameters, 8 consecutive k per lane
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(q0 + k0)), s1 = __ldg(reinterpret_cast<const float4*>(q0 + k0) + 1);
+                const float4 t0 = __ldg(reinterpret_cast<const float4*>(q1 + k0)), t1 = __ldg(reinterpret_cast<const float4*>(q1 + k0) + 1);
+                const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) xb[u][e] = fmaxf(fmaf(xb[u][e], ss[e], tt[e]), 0.f);
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) xb[u][e] = fmaxf(fmaf(xb[u][e], sc_u[u], sh_u[u]), 0.f);
-                }
-              } else if (g.prologue == TC_PRO_SOFTMAX) {
-                if (B_KMAJOR) {                 // per-row (j) parameters
-                  const int j = nt * TN + (it >> 1) * 8 + l8;
-                  const float m = __ldg(q0 + j), inv = __ldg(q1 + j);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) xb[u][e] = __expf(xb[u][e] - m) * inv;
-                } else {                        // per-column (j) parameters, 8 consecutive j per lane
-                  const int j0 = nt * TN + (it & 3) * 32 + g4 * 8;
-                  const float4 m0 = __ldg(reinterpret_cast<const float4*>(q0 + j0)), m1 = __ldg(reinterpret_cast<const float4*>(q0 + j0) + 1);
-                  const float4 i0 = __ldg(reinterpret_cast<const float4*>(q1 + j0)), i1 = __ldg(reinterpret_cast<const float4*>(q1 + j0) + 1);
-                  const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w}, ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) xb[u][e] = __expf(xb[u][e] - mm[e]) * ii[e];
-                }
-              }
-            } else if (g.prologue != TC_PRO_NONE && nvb[u] > 0) {      // guarded edge path (same arithmetic)
-              if (B_KMAJOR) {
-                const int j = nt * TN + (it >> 1) * 8 + l8, k0 = kc * KC + (it & 1) * 32 + g4 * 8;
-                if (g.prologue == TC_PRO_AFFINE_RELU) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = fmaxf(fmaf(xb[u][e], __ldg(q0 + k0 + e), __ldg(q1 + k0 + e)), 0.f);
-                } else {
-                  const float m = __ldg(q0 + j), inv = __ldg(q1 + j);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = __expf(xb[u][e] - m) * inv;
-                }
+                for (int e = 0; e < 8; ++e) xb[u][e] = fmaxf(fmaf(xb[u][e], ss[e], tt[e]), 0.f);
               } else {
-                const int j0 = nt * TN + (it & 3) * 32 + g4 * 8;
-                if (g.prologue == TC_PRO_AFFINE_RELU) {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = fmaxf(fmaf(xb[u][e], sc_u[u], sh_u[u]), 0.f);
-                } else {
+                for (int e = 0; e < 8; ++e) xb[u][e] = fmaxf(fmaf(xb[u][e], sc_u[u], sh_u[u]), 0.f);
+              }
+            } else if (g.prologue == TC_PRO_SOFTMAX) {
+              if (B_KMAJOR) {                 // per-row (j) parameters
+                const float m = __ldg(q0 + jrow), inv = __ldg(q1 + jrow);
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = __expf(xb[u][e] - __ldg(q0 + j0 + e)) * __ldg(q1 + j0 + e);
-                }
+                for (int e = 0; e < 8; ++e) xb[u][e] = __expf(xb[u][e] - m) * inv;
+              } else {                        // per-column (j) parameters, 8 consecutive j per lane
+                const float4 m0 = __ldg(reinterpret_cast<const float4*>(q0 + j0)), m1 = __ldg(reinterpret_cast<const float4*>(q0 + j0) + 1);
+                const float4 i0 = __ldg(reinterpret_cast<const float4*>(q1 + j0)), i1 = __ldg(reinterpret_cast<const float4*>(q1 + j0) + 1);
+                const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w}, ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) xb[u][e] = __expf(xb[u][e] - mm[e]) * ii[e];
               }
             }
-            uint32_t off;
-            if (B_KMAJOR) off = (it >> 1) * K_SBO + ((it & 1) * 4 + g4) * K_LBO + l8 * 16;
-            else off = ((it & 3) * 4 + g4) * MN_SBO + (it >> 2) * MN_LBO + l8 * 16;
-            split8_store(xb[u], st_base + 2 * OP_BYTES + off, st_base + 3 * OP_BYTES + off);
+          } else if (g.prologue != TC_PRO_NONE && nvb[u] > 0) {      // guarded edge path (same arithmetic)
+            if (B_KMAJOR) {
+              if (g.prologue == TC_PRO_AFFINE_RELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = fmaxf(fmaf(xb[u][e], __ldg(q0 + k0 + e), __ldg(q1 + k0 + e)), 0.f);
+              } else {
+                const float m = __ldg(q0 + jrow), inv = __ldg(q1 + jrow);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = __expf(xb[u][e] - m) * inv;
+              }
+            } else {
+              if (g.prologue == TC_PRO_AFFINE_RELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = fmaxf(fmaf(xb[u][e], sc_u[u], sh_u[u]), 0.f);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = __expf(xb[u][e] - __ldg(q0 + j0 + e)) * __ldg(q1 + j0 + e);
+              }
+            }
           }
+          uint32_t off;
+          if (B_KMAJOR) off = it * K_SBO + g4 * K_LBO + l8 * 16;
+          else off = ((it % (TN / 32)) * 4 + g4) * MN_SBO + (it / (TN / 32)) * MN_LBO + l8 * 16;
+          split8_store(xb[u], st_base + 2 * A_OP_BYTES + off, st_base + 2 * A_OP_BYTES + B_OP_BYTES + off);
         }
-        // ---- A operand from fp32 activations (k contiguous): all loads of the chunk in flight together ----
+        // ---- A operand from fp32 activations (k contiguous): not used by the network (A is always pre-split) ----
         if (!a_blob) {
-#pragma unroll
-          for (int u = 0; u < NIT; ++u) {
+#pragma unroll 1
+          for (int u = 0; u < NIT_A; ++u) {
             const int it = pw + u * N_PROD_WARPS;
-            const int rg = it >> 1, kb = it & 1;
-            const int i = mt * TM + rg * 8 + l8, k0 = kc * KC + kb * 32 + g4 * 8;
-            nvb[u] = (i < g.M) ? min(8, max(0, g.K - k0)) : 0;
-            load8(Ap + (long long)i * g.a_i + k0, nvb[u], xb[u]);
-          }
-#pragma unroll
-          for (int u = 0; u < NIT; ++u) {
-            const int it = pw + u * N_PROD_WARPS;
-            const uint32_t off = (it >> 1) * K_SBO + ((it & 1) * 4 + g4) * K_LBO + l8 * 16;
-            split8_store(xb[u], st_base + off, st_base + OP_BYTES + off);
+            const int i = mt * TM + it * 8 + l8, k0 = kc * KC + g4 * 8;
+            const int nv = (i < g.M) ? min(8, max(0, g.K - k0)) : 0;
+            float xa[8];
+            load8(Ap + (long long)i * g.a_i + k0, nv, xa);
+            const uint32_t off = it * K_SBO + g4 * K_LBO + l8 * 16;
+            split8_store(xa, st_base + off, st_base + A_OP_BYTES + off);
           }
         }
         TC_PROF(4, tp);
@@ -402,15 +385,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
         else if (tile + gridDim.x < n_tiles) fetch_b(tile + gridDim.x, 0);
       }
     }
-  } else if (warp >= FIRST_EPI_WARP) {
-    // ===================== epilogue =====================
+  } else {
+    // ===================== epilogue (warps 2..5; TMEM lane quarter = warp & 3) =====================
     const int quarter = warp & 3;
     const int r_own = quarter * 32 + lane;                             // the accumulator row (TMEM lane) this thread owns
-    // Fast path (outputs contiguous along j, 16-byte friendly): every thread moves ITS OWN row with TMA bulk copies --
-    // residual row -> shared memory (prefetched a tile ahead, completion on a per-thread mbarrier), accumulator + bias +
-    // residual combined in place, then one bulk store of the finished row.  No LSU traffic to global memory at all.
     const bool fast = tc_fast_epilogue(g);
     if (fast) {
+      // Fast path (rows contiguous along j, 16-byte friendly).  Phase 1, thread = row: the residual row was prefetched by
+      // TMA into this thread's staged row (own mbarrier); accumulator + bias + residual are combined in place and the row
+      // statistics are taken.  Phase 2, warp = 32 rows: every row leaves as one coalesced TN*4-byte store.
       uint8_t* my_row = stg + (size_t)r_own * STG_ROW;
       const uint8_t* warp_rows = stg + (size_t)(quarter * 32) * STG_ROW;
       const uint32_t my_bar = smem_u32(rowbars + r_own);
@@ -418,7 +401,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
       bool pending = false;
       auto prefetch = [&](long long tile) {
         pending = false;
-        if (!g.Res || tile >= n_tiles || (g.debug & 8)) return;
+        if (!g.Res || tile >= n_tiles) return;
         int p, mt, nt; decode(tile, p, mt, nt);
         const int i = mt * TM + r_own;
         const int nc = (i < g.M) ? min(TN, g.N - nt * TN) : 0;
@@ -444,9 +427,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
         const bool has_res = pending;
         if (has_res) { mbar_wait(my_bar, par); par ^= 1; }
         TC_PROF(8, tp);
-        // ---- phase 1: thread = row.  accumulator + bias + residual, in place in this thread's staged row ----
 #pragma unroll
-        for (int cc = 0; cc < ((g.debug & 32) ? 0 : TN / 32); ++cc) {
+        for (int cc = 0; cc < TN / 32; ++cc) {
           float v[32];
           tc_ld32(taddr + cc * 32, v);
           float4* dst = reinterpret_cast<float4*>(my_row + cc * 128);
@@ -489,17 +471,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
             g.smstats_out[so + 1] = se;
           }
         }
-        // ---- phase 2: warp = 32 rows.  Each row leaves as one coalesced 512-byte store (lane = 4 columns) ----
         TC_PROF(10, tp);
         __syncwarp();
         {
-          float* Cp = g.C + (long long)p * g.c_batch + nt * TN + 4 * lane;
+          constexpr int LPR = TN / 4;                 // lanes per row (16): a warp instruction stores 32/LPR rows
+          const int sub = lane / LPR, col = 4 * (lane % LPR);
+          float* Cp = g.C + (long long)p * g.c_batch + nt * TN + col;
           const int ibase = mt * TM + quarter * 32;
-          if (4 * lane < ncv && !(g.debug & 4)) {
+          if (col < ncv) {
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
+            for (int r = sub; r < 32; r += 32 / LPR) {
               if (ibase + r < g.M) {
-                const float4 o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 16 * lane);
+                const float4 o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 4 * col);
                 *reinterpret_cast<float4*>(Cp + (long long)(ibase + r) * g.c_i) = o;
               }
             }
@@ -510,13 +493,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
         prefetch(tile + gridDim.x);
       }
     } else {
+      // Generic path: arbitrary output strides (transposed outputs of OAFilter's cluster mixing, ragged point counts).
       float* tr = trbuf + quarter * 32 * TR_LD;
       int acc = 0; uint32_t acc_phase = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int p, mt, nt; decode(tile, p, mt, nt);
         float* Cp = g.C + (long long)p * g.c_batch;
         const float* Rp = g.Res ? g.Res + (long long)p * g.r_batch : nullptr;
-        const int i_own = mt * TM + quarter * 32 + lane;                 // the row this thread owns in TMEM
+        const int i_own = mt * TM + r_own;
         const float bias_own = (g.bias && i_own < g.M) ? __ldg(g.bias + i_own) : 0.f;
         mbar_wait(T_FULL(acc), acc_phase);
         tc_fence_after();
@@ -549,9 +533,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
             }
             __syncwarp();
           } else {
-            // rows are contiguous along i (transposed output, OAFilter's cluster mixing): lanes already coalesce
+            // rows are contiguous along i (transposed output): lanes (consecutive i) already coalesce
             if (i_own < g.M) {
-#pragma unroll
+#pragma unroll 8
               for (int e = 0; e < 32; ++e) {
                 const int j = jb + e;
                 if (j < g.N) {
@@ -574,14 +558,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcgemm_kernel(TcGemmArgs g, int b
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256u);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 }  // namespace
 
 size_t tc_weight_blob_bytes(int M, int K) {
-  return (size_t)((M + TM - 1) / TM) * ((K + KC - 1) / KC) * 2 * OP_BYTES;
+  return (size_t)((M + TM - 1) / TM) * ((K + KC - 1) / KC) * 2 * A_OP_BYTES;
 }
 
 int launch_split_weights(const float* W, int M, int K, uint8_t* blob, cudaStream_t st, int batch, long long w_batch, int ld) {
@@ -613,7 +597,8 @@ int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
   }
   const long long tiles = (long long)batch * ((a.M + TM - 1) / TM) * ((a.N + TN - 1) / TN);
   LMPCR_REQUIRE(tiles < (1ll << 31), LMPCR_ERR_ARG, "tcgemm: too many tiles");
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  const long long slots = 2ll * sm_count();          // two resident CTAs per SM
+  const int grid = (int)(tiles < slots ? tiles : slots);
   if (a.b_kmajor) tcgemm_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, batch);
   else tcgemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, batch);
   return check_launch("tcgemm_kernel");

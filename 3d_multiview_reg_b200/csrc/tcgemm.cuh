@@ -4,6 +4,8 @@
 
 namespace lmpcr {
 
+constexpr int TC_TILE_N = 64;   // output-tile width along j; the fused row statistics are per tile of this width
+
 enum TcPrologue { TC_PRO_NONE = 0, TC_PRO_AFFINE_RELU = 1, TC_PRO_SOFTMAX = 2 };
 
 // C[p,i,j] = sum_k A[p,i,k] * f(B[p,k,j]) + bias[i] + Res[p,i,j]          (fp32 in / fp32 out)
@@ -23,8 +25,8 @@ struct TcGemmArgs {
   const float* p0; const float* p1; int p_batch;    // AFFINE_RELU: scale/shift indexed [p*p_batch + k];
                                                     // SOFTMAX: max / 1/sum indexed [p*p_batch + j]: f(x) = exp(x - p0[j]) * p1[j]
   // Optional fused statistics of the OUTPUT, written by the TMA epilogue (only when tc_fast_epilogue(args) holds):
-  //   stats_out   [batch, M, ceil(N/128), 2] = (mean, M2) of every row over the tile's valid columns  (InstanceNorm of the consumer)
-  //   smstats_out [batch, M, ceil(N/128), 2] = (max, sum exp(x - max)) of every row over the tile       (softmax over the j axis)
+  //   stats_out   [batch, M, ceil(N/TC_TILE_N), 2] = (mean, M2) of every row over the tile's valid columns  (InstanceNorm of the consumer)
+  //   smstats_out [batch, M, ceil(N/TC_TILE_N), 2] = (max, sum exp(x - max)) of every row over the tile       (softmax over the j axis)
   float* stats_out; float* smstats_out;
   int M, N, K;
   int debug;   // timing experiments only (LMPCR_TC_DEBUG bit mask, see tcgemm.cu); 0 in production
