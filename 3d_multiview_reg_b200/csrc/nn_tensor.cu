@@ -244,25 +244,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
         mbar_wait(T_FULL(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN + half * 128;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          float v[32];
-          tc_ld32(taddr + c * CHUNK, v);
+        // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is reduced
+        uint32_t va[32], vb[32];
+        auto reduce_chunk = [&](const uint32_t (&cur)[32], int c) {
           if (g.dbg_scores && grow < g.n_q) {
             float* o = g.dbg_scores + ((size_t)job * g.n_q + grow) * g.rows_pad_b + (size_t)t * TN + half * 128 + c * CHUNK;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = v[i];
+            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(cur[i]);
           }
-          float m = min3(v[0], v[1], v[2]);
+          float m = min3(__uint_as_float(cur[0]), __uint_as_float(cur[1]), __uint_as_float(cur[2]));
 #pragma unroll
-          for (int i = 3; i < 31; i += 2) m = min3(m, v[i], v[i + 1]);
-          m = fminf(m, v[31]);
+          for (int i = 3; i < 31; i += 2) m = min3(m, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+          m = fminf(m, __uint_as_float(cur[31]));
           run = fminf(run, m);
           if (m <= run + margin) {
             ring[(cnt & (CAP - 1)) * EPI_THREADS + te] = make_uint2(__float_as_uint(m), (uint32_t)(t * 8 + half * 4 + c));
             ++cnt;
           }
-        }
+        };
+        tc_ld32_issue(taddr, va);
+        tc_ld_wait();
+        tc_ld32_issue(taddr + CHUNK, vb);
+        reduce_chunk(va, 0);
+        tc_ld_wait();
+        tc_ld32_issue(taddr + 2 * CHUNK, va);
+        reduce_chunk(vb, 1);
+        tc_ld_wait();
+        tc_ld32_issue(taddr + 3 * CHUNK, vb);
+        reduce_chunk(va, 2);
+        tc_ld_wait();
+        reduce_chunk(vb, 3);
         tc_fence_before();
         mbar_arrive(T_EMPTY(acc));
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -301,7 +312,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
 }
 
 // ---------------------------------------------------------------- (3) exact fp32 rescoring, one warp per query row
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 nn_rescore_kernel(const float* __restrict__ q_feat, const float* __restrict__ sqn_q, int n_q, int rows_pad_q,
                   const float4* __restrict__ featT_b, const float* __restrict__ sqn_b, int n_b, int rows_pad_b,
                   const int32_t* __restrict__ jobs, int n_jobs, const uint2* __restrict__ cand, const int* __restrict__ unsupported,
@@ -311,15 +322,9 @@ nn_rescore_kernel(const float* __restrict__ q_feat, const float* __restrict__ sq
   const int lane = threadIdx.x & 31;
   const int job = (int)(w / n_q), row = (int)(w - (long long)job * n_q);
   const int qs = __ldg(jobs + 2 * job), bs = __ldg(jobs + 2 * job + 1);
-  float a[D];
-  {
-    const float4* src = reinterpret_cast<const float4*>(q_feat + ((size_t)qs * n_q + row) * D);
-#pragma unroll
-    for (int k = 0; k < D / 4; ++k) {
-      const float4 v = __ldg(src + k);
-      a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
-    }
-  }
+  // lane k keeps feature k of the query row (one coalesced 128-byte load); the FMA chain broadcasts it with shuffles,
+  // which keeps the kernel at ~48 registers (40 resident warps per SM: the kernel is latency-bound on L2 hits).
+  const float a_l = __ldg(q_feat + ((size_t)qs * n_q + row) * D + lane);
   const float an = __ldg(sqn_q + (size_t)qs * rows_pad_q + row);
   const float4* tb = featT_b + (size_t)bs * rows_pad_b * 8;    // rows_pad_b/32 chunks * 256 float4
   const float* nb = sqn_b + (size_t)bs * rows_pad_b;
@@ -328,13 +333,19 @@ nn_rescore_kernel(const float* __restrict__ q_feat, const float* __restrict__ sq
   auto score_chunk = [&](int ch) {
     const int j = ch * CHUNK + lane;
     const float4* src = tb + (size_t)ch * 256 + lane;
+    float4 v[8];
+#pragma unroll
+    for (int kq = 0; kq < 8; ++kq) v[kq] = __ldg(src + kq * 32);
+    const float bnj = __ldg(nb + j);
     float c = 0.f;
 #pragma unroll
     for (int kq = 0; kq < 8; ++kq) {
-      const float4 v = __ldg(src + kq * 32);
-      c = fmaf(a[4 * kq], v.x, c); c = fmaf(a[4 * kq + 1], v.y, c); c = fmaf(a[4 * kq + 2], v.z, c); c = fmaf(a[4 * kq + 3], v.w, c);
+      c = fmaf(__shfl_sync(0xffffffffu, a_l, 4 * kq), v[kq].x, c);
+      c = fmaf(__shfl_sync(0xffffffffu, a_l, 4 * kq + 1), v[kq].y, c);
+      c = fmaf(__shfl_sync(0xffffffffu, a_l, 4 * kq + 2), v[kq].z, c);
+      c = fmaf(__shfl_sync(0xffffffffu, a_l, 4 * kq + 3), v[kq].w, c);
     }
-    const float d = __fadd_rn(__fadd_rn(__fmul_rn(2.0f, -c), an), __ldg(nb + j));
+    const float d = __fadd_rn(__fadd_rn(__fmul_rn(2.0f, -c), an), bnj);
     if (j < n_b && (d < best || (d == best && j < bj))) { best = d; bj = j; }
   };
   const bool scan_all = (*unsupported != 0);

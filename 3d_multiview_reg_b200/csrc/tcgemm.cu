@@ -32,7 +32,7 @@ constexpr int STAGES = 3;
 constexpr int A_OP_BYTES = TM * KC * 2;      // one bf16 A tile (hi or lo): 8 KB
 constexpr int B_OP_BYTES = TN * KC * 2;      // one bf16 B tile (hi or lo): 4 KB
 constexpr int STAGE_BYTES = 2 * A_OP_BYTES + 2 * B_OP_BYTES;   // [A_hi][A_lo][B_hi][B_lo] = 24 KB
-constexpr int N_PROD_WARPS = 4;
+constexpr int N_PROD_WARPS = 8;
 constexpr int FIRST_EPI_WARP = 2, FIRST_PROD_WARP = 6;
 constexpr int NTHREADS = 32 * (FIRST_PROD_WARP + N_PROD_WARPS);   // 320
 constexpr int TMEM_COLS = 2 * TN;                                  // two accumulators (power of two >= 32)
@@ -139,12 +139,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
   const uint32_t tmem_base = *tmem_slot;
 
   const unsigned per_batch = (unsigned)(tiles_m * tiles_n);
-  auto decode = [&](long long tile, int& p, int& mt, int& nt) {   // n_tiles < 2^31 (checked on the host): 32-bit divides
+  // tile -> (batch element, m-tile, n-tile); m fastest so that CTAs sharing a B tile run next to each other (L2 reuse).
+  // n_tiles < 2^31 (checked on the host).  Divisions by the loop-invariant divisors go through float reciprocals
+  // (exact for these magnitudes after the +-1 correction), which is ~4x cheaper than the integer division sequence.
+  const float inv_per = 1.0f / (float)per_batch, inv_tm = 1.0f / (float)tiles_m;
+  auto decode = [&](long long tile, int& p, int& mt, int& nt) {
     const unsigned t = (unsigned)tile;
-    const unsigned pp = t / per_batch, r = t - pp * per_batch;
-    const unsigned q = r / (unsigned)tiles_m;
+    unsigned pp = (unsigned)((float)t * inv_per);
+    if (pp * per_batch > t) --pp;
+    if ((pp + 1) * per_batch <= t) ++pp;
+    const unsigned r = t - pp * per_batch;
+    unsigned q = (tiles_m == 1) ? r : (unsigned)((float)r * inv_tm);
+    if (tiles_m != 1) {
+      if (q * (unsigned)tiles_m > r) --q;
+      if ((q + 1) * (unsigned)tiles_m <= r) ++q;
+    }
     p = (int)pp;
-    mt = (int)(r - q * (unsigned)tiles_m);   // m fastest: CTAs that share a B tile run next to each other (L2 reuse)
+    mt = (int)(r - q * (unsigned)tiles_m);
     nt = (int)q;
   };
 
@@ -483,7 +494,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
             for (int r = sub; r < 32; r += 32 / LPR) {
               if (ibase + r < g.M) {
                 const float4 o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 4 * col);
-                *reinterpret_cast<float4*>(Cp + (long long)(ibase + r) * g.c_i) = o;
+                __stcs(reinterpret_cast<float4*>(Cp + (long long)(ibase + r) * g.c_i), o);
               }
             }
           }
@@ -596,7 +607,7 @@ int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
     attr_set = true;
   }
   const long long tiles = (long long)batch * ((a.M + TM - 1) / TM) * ((a.N + TN - 1) / TN);
-  LMPCR_REQUIRE(tiles < (1ll << 31), LMPCR_ERR_ARG, "tcgemm: too many tiles");
+  LMPCR_REQUIRE(tiles < (1ll << 24), LMPCR_ERR_ARG, "tcgemm: too many tiles in one launch");
   const long long slots = 2ll * sm_count();          // two resident CTAs per SM
   const int grid = (int)(tiles < slots ? tiles : slots);
   if (a.b_kmajor) tcgemm_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, batch);
