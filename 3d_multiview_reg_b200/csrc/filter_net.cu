@@ -371,6 +371,23 @@ __global__ void softmax_from_partials_kernel(const float* __restrict__ part, int
   sinv[row] = 1.0f / s;
 }
 
+// softmax-over-clusters statistics (diff_unpool) from the per-slab column partials of the embedding conv's epilogue
+__global__ void softmax_cols_from_partials_kernel(const float* __restrict__ part, int np, size_t n_cols, float* __restrict__ cmax,
+                                                  float* __restrict__ cinv) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_cols) return;
+  const float2* q = reinterpret_cast<const float2*>(part) + gid * np;
+  float m = -INFINITY;
+  for (int t = 0; t < np; ++t) m = fmaxf(m, __ldg(q + t).x);
+  float s = 0.f;
+  for (int t = 0; t < np; ++t) {
+    const float2 v = __ldg(q + t);
+    if (v.x != -INFINITY) s += v.y * __expf(v.x - m);
+  }
+  cmax[gid] = m;
+  cinv[gid] = 1.0f / s;
+}
+
 // output conv (C -> 1) + tanh/relu weights (oanet.py:174-175) + "any positive weight" flag per pair
 __global__ void logits_kernel(const float* __restrict__ x, long long x_batch, int C, int N, int P,
                               const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ logits,
@@ -449,6 +466,7 @@ size_t per_pair_floats(int C, int K, int N) {
   const size_t L = (size_t)(N > K ? N : K), tmax = (L + TC_TILE_N - 1) / TC_TILE_N;
   size_t f = r64((size_t)12 * N) + 3 * r64((size_t)C * N) + r64((size_t)2 * C * N) + r64((size_t)K * N) + 4 * r64((size_t)C * K) + 2 * r64(1024) + 2 * r64(L);
   f += (size_t)N_PART * r64((size_t)C * tmax * 2) + r64((size_t)K * tmax * 2);            // norm / softmax partials
+  f += r64((size_t)N * 4 * ((K + 127) / 128) * 2);                                        // column-softmax partials (diff_unpool)
   f += r64(tc_weight_blob_bytes(C, K) / 4) + r64(tc_weight_blob_bytes(C, N) / 4);        // pre-split x2 / x1_1 (pool, unpool A operands)
   return f;
 }
@@ -547,6 +565,8 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   bool part_valid[N_PART];
   for (int i = 0; i < N_PART; ++i) { part_buf[i] = take((size_t)C * tmax * 2); part_valid[i] = false; }
   float* sm_part = take((size_t)K * tmax * 2);
+  float* col_part = take((size_t)N * 4 * ((K + 127) / 128) * 2);
+  bool want_col = false;   // set around the diff_unpool embedding conv: its epilogue emits softmax-over-clusters partials
   uint8_t* blob_x2 = reinterpret_cast<uint8_t*>(take(tc_weight_blob_bytes(C, K) / 4));
   uint8_t* blob_x11 = reinterpret_cast<uint8_t*>(take(tc_weight_blob_bytes(C, N) / 4));
   auto part_index = [&](const float* x) -> int {
@@ -597,7 +617,8 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         part_valid[oi] = tc_fast_epilogue(a);
         a.stats_out = part_valid[oi] ? part_buf[oi] : nullptr;
       }
-      if (want_sm && out == W.E && tc_fast_epilogue(a)) a.smstats_out = sm_part;   // softmax over points (diff_pool)
+      if (want_sm && out == W.E && tc_fast_epilogue(a)) a.smstats_out = sm_part;
+      if (want_col && out == W.E && tc_fast_epilogue(a)) a.colstats_out = col_part;   // softmax over points (diff_pool)
       return launch_tcgemm(a, g, st);
     }
     if (oi >= 0) part_valid[oi] = false;
@@ -744,10 +765,17 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         float* t = xd_in; xd_in = xd_out; xd_out = t;
       }
       // diff_unpool (oanet.py:122-129): x_up -> upper half of the concat buffer
+      want_col = true;
       LMPCR_TRY(conv_norm(x11, x11b, C, N, g, 1e-3f, blk.up_bn, blk.up_conv, K, W.E, (long long)K * N, nullptr, 0));
+      want_col = false;
       if (tc) {
-        softmax_colstats_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g, sm_max, sm_inv);
-        LMPCR_TRY(check_launch("softmax_colstats_kernel"));
+        if ((N & 3) == 0) {   // statistics came fused out of the embedding conv's epilogue
+          softmax_cols_from_partials_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(col_part, 4 * ((K + 127) / 128), tot, sm_max, sm_inv);
+          LMPCR_TRY(check_launch("softmax_cols_from_partials_kernel"));
+        } else {
+          softmax_colstats_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g, sm_max, sm_inv);
+          LMPCR_TRY(check_launch("softmax_colstats_kernel"));
+        }
         TcGemmArgs a{};   // x_up[c,n] = sum_k x2[c,k] * softmax_k(E[:,n])[k]
         LMPCR_TRY(launch_split_weights(xd_in, C, K, blob_x2, st, g, CK, K));   // A operand (x2) shared by all point tiles of a pair
         a.a_blob = blob_x2; a.a_blob_batch = (long long)tc_weight_blob_bytes(C, K);

@@ -489,12 +489,44 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
           const int sub = lane / LPR, col = 4 * (lane % LPR);
           float* Cp = g.C + (long long)p * g.c_batch + nt * TN + col;
           const int ibase = mt * TM + quarter * 32;
+          float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
           if (col < ncv) {
 #pragma unroll 8
             for (int r = sub; r < 32; r += 32 / LPR) {
               if (ibase + r < g.M) {
                 const float4 o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 4 * col);
                 __stcs(reinterpret_cast<float4*>(Cp + (long long)(ibase + r) * g.c_i), o);
+                if (g.colstats_out) { cm[0] = fmaxf(cm[0], o.x); cm[1] = fmaxf(cm[1], o.y); cm[2] = fmaxf(cm[2], o.z); cm[3] = fmaxf(cm[3], o.w); }
+              }
+            }
+          }
+          if (g.colstats_out) {
+            // softmax over the row (cluster) axis: per-column (max, sum exp) of this warp's 32-row slab; the two 16-lane
+            // halves hold alternate rows of the same 4 columns and are merged with one shuffle
+            float cs[4] = {0.f, 0.f, 0.f, 0.f};
+            if (col < ncv) {
+#pragma unroll 4
+              for (int r = sub; r < 32; r += 32 / LPR) {
+                if (ibase + r < g.M) {
+                  const float4 o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 4 * col);
+                  cs[0] += __expf(o.x - cm[0]); cs[1] += __expf(o.y - cm[1]); cs[2] += __expf(o.z - cm[2]); cs[3] += __expf(o.w - cm[3]);
+                }
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float om = __shfl_xor_sync(0xffffffffu, cm[e], LPR), os = __shfl_xor_sync(0xffffffffu, cs[e], LPR);
+              const float m = fmaxf(cm[e], om);
+              const float sa = (cm[e] == -INFINITY) ? 0.f : cs[e] * __expf(cm[e] - m);
+              const float sb = (om == -INFINITY) ? 0.f : os * __expf(om - m);
+              cm[e] = m; cs[e] = sa + sb;
+            }
+            if (sub == 0 && col < ncv) {
+              const int np = tiles_m * 4, slab = mt * 4 + quarter;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float* o = g.colstats_out + ((((long long)p * g.N + nt * TN + col + e) * np) + slab) * 2;
+                o[0] = cm[e]; o[1] = cs[e];
               }
             }
           }

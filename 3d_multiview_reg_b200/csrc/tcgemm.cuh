@@ -27,7 +27,8 @@ struct TcGemmArgs {
   // Optional fused statistics of the OUTPUT, written by the TMA epilogue (only when tc_fast_epilogue(args) holds):
   //   stats_out   [batch, M, ceil(N/TC_TILE_N), 2] = (mean, M2) of every row over the tile's valid columns  (InstanceNorm of the consumer)
   //   smstats_out [batch, M, ceil(N/TC_TILE_N), 2] = (max, sum exp(x - max)) of every row over the tile       (softmax over the j axis)
-  float* stats_out; float* smstats_out;
+  //   colstats_out [batch, N, 4*ceil(M/128), 2] = (max, sum exp(x - max)) of every COLUMN over each 32-row slab        (softmax over the i axis)
+  float* stats_out; float* smstats_out; float* colstats_out;
   int M, N, K;
   int debug;   // timing experiments only (LMPCR_TC_DEBUG bit mask, see tcgemm.cu); 0 in production
 };
