@@ -19,7 +19,7 @@ GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
 EXPORTS = [
-    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
     "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
     "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
 ]
@@ -61,6 +61,9 @@ def load():
     lib.lmpcr_knn3d_1.argtypes = [_vp, _i, _vp, _i, _i, _vp, _vp, _vp]
     lib.lmpcr_kabsch.argtypes = [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.lmpcr_residuals.argtypes = [_vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]
+    lib.lmpcr_conv1x1_workspace_bytes.restype = _sz
+    lib.lmpcr_conv1x1_workspace_bytes.argtypes = [_i, _i]
+    lib.lmpcr_conv1x1.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _sz, _vp]
     lib.lmpcr_filter_num_params.argtypes = [ctypes.POINTER(FilterCfg)]
     lib.lmpcr_filter_workspace_bytes.restype = _sz
     lib.lmpcr_filter_workspace_bytes.argtypes = [ctypes.POINTER(FilterCfg), _i, _i]
@@ -278,6 +281,25 @@ def filter_forward(xs, params, cfg, want_latent=True, want_conf=True, workspace=
         _check(lib.lmpcr_filter_forward(_p(x), P, N, table, n_par, ctypes.byref(cfg), _p(out["logits"]), _p(out["scores"]), _p(out["R"]),
                                         _p(out["t"]), _p(out["residuals"]), _p(out["latent"]), _p(out["conf"]), _p(out["status"]),
                                         _p(workspace), workspace.numel(), _stream(x)))
+    return out
+
+
+def conv1x1(x, weight, bias=None, scale=None, shift=None, residual=None, gemm_algo=1, out=None, workspace=None):
+    """Fused (scale/shift + ReLU) -> 1x1 conv -> +bias (+residual).  x [P,cin,N], weight [cout,cin] -> out [P,cout,N]."""
+    lib = load()
+    x = _dev(x, name="x")
+    w = _dev(weight, name="weight").reshape(weight.shape[0], -1)
+    P, cin, N = x.shape
+    cout = w.shape[0]
+    opt = lambda t, n: _dev(t, name=n) if t is not None else None
+    bias, scale, shift, residual = opt(bias, "bias"), opt(scale, "scale"), opt(shift, "shift"), opt(residual, "residual")
+    with torch.cuda.device(x.device):
+        if out is None:
+            out = torch.empty((P, cout, N), dtype=torch.float32, device=x.device)
+        if workspace is None:
+            workspace = _ws(lib.lmpcr_conv1x1_workspace_bytes(cout, cin), x.device)
+        _check(lib.lmpcr_conv1x1(_p(x), P, cin, N, _p(w), _p(bias), _p(scale), _p(shift), _p(residual), cout, _p(out), gemm_algo,
+                                 _p(workspace), workspace.numel(), _stream(x)))
     return out
 
 

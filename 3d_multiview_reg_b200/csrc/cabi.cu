@@ -148,6 +148,16 @@ int lmpcr_residuals(const float* x1, const float* x2, int ld, const float* R, co
   return launch_residuals(x1, x2, ld, R, t, n_pairs, n_pts, res, (cudaStream_t)stream);
 }
 
+size_t lmpcr_conv1x1_workspace_bytes(int cout, int cin) { return conv1x1_workspace_bytes(cout, cin); }
+
+int lmpcr_conv1x1(const float* x, int n_pairs, int cin, int n_pts, const float* weight, const float* bias, const float* scale,
+                  const float* shift, const float* residual, int cout, float* out, int gemm_algo, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_conv1x1(x, n_pairs, cin, n_pts, weight, bias, scale, shift, residual, cout, out, gemm_algo, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
+}
+
 int lmpcr_filter_num_params(const lmpcr_filter_cfg* cfg) {
   if (!cfg) return LMPCR_ERR_ARG;
   return filter_num_params(cfg);

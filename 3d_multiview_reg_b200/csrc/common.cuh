@@ -80,6 +80,9 @@ int launch_nn_tensor(const float* q_feat, int n_q_sets, int n_q, const float* b_
                      cudaStream_t st);
 
 // filter_net.cu
+size_t conv1x1_workspace_bytes(int cout, int cin);
+int launch_conv1x1(const float* x, int P, int cin, int N, const float* weight, const float* bias, const float* scale, const float* shift,
+                   const float* residual, int cout, float* out, int algo, void* ws, size_t ws_bytes, cudaStream_t st);
 int filter_num_params(const lmpcr_filter_cfg* cfg);
 size_t filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int P, int N);
 int launch_filter_forward(const float* xs, int P, int N, const float* const* params, int n_params,

@@ -483,6 +483,46 @@ size_t block_blob_bytes(int C, int K, int half) {
 
 }  // namespace
 
+size_t conv1x1_workspace_bytes(int cout, int cin) { return align_up(tc_weight_blob_bytes(cout, cin), 256) + 256; }
+
+// One fused layer: out = conv1x1(relu(x*scale + shift)) + bias (+ residual)   (lib/filtering/oanet.py:27-34 after folding IN+BN)
+int launch_conv1x1(const float* x, int P, int cin, int N, const float* weight, const float* bias, const float* scale, const float* shift,
+                   const float* residual, int cout, float* out, int algo, void* ws, size_t ws_bytes, cudaStream_t st) {
+  LMPCR_REQUIRE(x && weight && out, LMPCR_ERR_ARG, "lmpcr_conv1x1: null pointer");
+  LMPCR_REQUIRE(P >= 0 && cin > 0 && cout > 0 && N > 0, LMPCR_ERR_ARG, "lmpcr_conv1x1: bad sizes");
+  LMPCR_REQUIRE((scale == nullptr) == (shift == nullptr), LMPCR_ERR_ARG, "lmpcr_conv1x1: scale and shift go together");
+  if (P == 0) return LMPCR_OK;
+  if (algo == 1) {
+    LMPCR_REQUIRE(ws && ws_bytes >= conv1x1_workspace_bytes(cout, cin) && ((uintptr_t)ws & 255) == 0, LMPCR_ERR_WORKSPACE, "lmpcr_conv1x1: workspace");
+    uint8_t* blob = reinterpret_cast<uint8_t*>(ws);
+    LMPCR_TRY(launch_split_weights(weight, cout, cin, blob, st));
+    TcGemmArgs a{};
+    a.a_blob = blob;
+    a.B = x; a.b_batch = (long long)cin * N; a.b_ld = N; a.b_kmajor = 0;
+    a.C = out; a.c_batch = (long long)cout * N; a.c_i = N; a.c_j = 1;
+    a.Res = residual; a.r_batch = (long long)cout * N; a.bias = bias;
+    a.prologue = scale ? TC_PRO_AFFINE_RELU : TC_PRO_NONE; a.p0 = scale; a.p1 = shift; a.p_batch = cin;
+    a.M = cout; a.N = N; a.K = cin;
+    return launch_tcgemm(a, P, st);
+  }
+  LMPCR_REQUIRE(algo == 0, LMPCR_ERR_ARG, "lmpcr_conv1x1: unknown gemm_algo %d", algo);
+  GemmArgs a{};
+  a.A = weight; a.a_batch = 0; a.a_i = cin;
+  a.B = x; a.b_batch = (long long)cin * N; a.b_k = N; a.b_j = 1;
+  a.C = out; a.c_batch = (long long)cout * N; a.c_i = N; a.c_j = 1;
+  a.Res = residual; a.r_batch = (long long)cout * N; a.bias = bias;
+  a.scale = scale; a.shift = shift; a.aff_batch = cin;
+  a.M = cout; a.N = N; a.K = cin;
+  for (int p0 = 0; p0 < P; p0 += 65535) {
+    GemmArgs b = a;
+    b.B = a.B + (long long)p0 * a.b_batch; b.C = a.C + (long long)p0 * a.c_batch;
+    if (a.Res) b.Res = a.Res + (long long)p0 * a.r_batch;
+    if (a.scale) { b.scale = a.scale + (long long)p0 * cin; b.shift = a.shift + (long long)p0 * cin; }
+    LMPCR_TRY(gemm(b, min(65535, P - p0), st));
+  }
+  return LMPCR_OK;
+}
+
 int filter_num_params(const lmpcr_filter_cfg* cfg) {
   const int half = (cfg->net_depth / (cfg->iter_num + 1)) / 2;
   return block_num_params(half) * (cfg->iter_num + 1);

@@ -252,10 +252,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(cur[i]);
           }
-          float m = min3(__uint_as_float(cur[0]), __uint_as_float(cur[1]), __uint_as_float(cur[2]));
+          // four independent 3-input-min chains over 8 columns each (depth 6 instead of 16), then a 2-op merge
+          float mq[4];
 #pragma unroll
-          for (int i = 3; i < 31; i += 2) m = min3(m, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
-          m = fminf(m, __uint_as_float(cur[31]));
+          for (int q = 0; q < 4; ++q) {
+            const int b = 8 * q;
+            float t = min3(__uint_as_float(cur[b]), __uint_as_float(cur[b + 1]), __uint_as_float(cur[b + 2]));
+            t = min3(t, __uint_as_float(cur[b + 3]), __uint_as_float(cur[b + 4]));
+            t = min3(t, __uint_as_float(cur[b + 5]), __uint_as_float(cur[b + 6]));
+            mq[q] = fminf(t, __uint_as_float(cur[b + 7]));
+          }
+          const float m = fminf(min3(mq[0], mq[1], mq[2]), mq[3]);
           run = fminf(run, m);
           if (m <= run + margin) {
             ring[(cnt & (CAP - 1)) * EPI_THREADS + te] = make_uint2(__float_as_uint(m), (uint32_t)(t * 8 + half * 4 + c));

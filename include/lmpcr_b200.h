@@ -154,6 +154,17 @@ typedef struct lmpcr_filter_cfg {
   int32_t reserved;
 } lmpcr_filter_cfg;
 
+/* One fused layer of the network (the building block lmpcr_filter_forward is made of; exported so that it can be timed
+ * and tested alone):  out[p,co,n] = sum_ci W[co,ci] * relu(x[p,ci,n]*scale[p,ci] + shift[p,ci]) + bias[co] (+ residual[p,co,n])
+ * i.e. nn.Conv2d(kernel_size=1) preceded by InstanceNorm + eval BatchNorm + ReLU folded into scale/shift
+ * (lib/filtering/oanet.py:27-34, 63-68, 101-104).  x [P,cin,N], out/residual [P,cout,N], weight [cout,cin] fp32;
+ * scale/shift [P,cin] or both NULL (plain convolution); bias / residual optional.
+ * gemm_algo 0 = fp32 CUDA cores, 1 = tcgen05 split-bf16 (needs workspace >= lmpcr_conv1x1_workspace_bytes). */
+size_t lmpcr_conv1x1_workspace_bytes(int cout, int cin);
+int lmpcr_conv1x1(const float* x, int n_pairs, int cin, int n_pts, const float* weight, const float* bias, const float* scale,
+                  const float* shift, const float* residual, int cout, float* out, int gemm_algo, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
 /* Number of tensors of OANet(cfg).state_dict() excluding `num_batches_tracked` entries; `params` below is
  * a HOST array of that many DEVICE pointers (fp32, contiguous), in state_dict order. */
 int lmpcr_filter_num_params(const lmpcr_filter_cfg* cfg);

@@ -112,3 +112,22 @@ def test_empty_batch_and_bad_args():
         net({"xs": torch.zeros(2, 100, 6)})
     with pytest.raises(cabi.LmpcrError):
         cabi.filter_forward(torch.zeros((1, 1, 100, 6), device="cuda"), net.param_table()[:-1], net.cabi_cfg())
+
+
+@pytest.mark.parametrize("algo", GEMM_ALGOS)
+@pytest.mark.parametrize("P,cin,cout,N,res", [(3, 128, 128, 1000, True), (2, 256, 128, 777, False), (2, 128, 500, 640, False), (1, 8, 128, 130, False)])
+def test_conv1x1_layer(P, cin, cout, N, res, algo):
+    """The fused layer alone (lmpcr_conv1x1) against fp64 numpy: relative error of a split-bf16 product is ~2^-16."""
+    rng = np.random.default_rng(cin + N)
+    x = rng.standard_normal((P, cin, N)).astype(np.float32)
+    w = (rng.standard_normal((cout, cin)) / np.sqrt(cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, (P, cin)).astype(np.float32)
+    sh = (0.3 * rng.standard_normal((P, cin))).astype(np.float32)
+    r = rng.standard_normal((P, cout, N)).astype(np.float32) if res else None
+    out = cabi.conv1x1(cu(x), cu(w), cu(b), cu(sc), cu(sh), cu(r) if res else None, gemm_algo=algo).cpu().numpy()
+    h = np.maximum(x.astype(np.float64) * sc[:, :, None] + sh[:, :, None], 0)
+    ref = np.einsum("oc,pcn->pon", w.astype(np.float64), h) + b[None, :, None] + (r if res else 0)
+    assert np.abs(out - ref).max() < (2e-5 if algo == 0 else 1e-4) * max(1.0, np.abs(ref).max())
+    plain = cabi.conv1x1(cu(x), cu(w), gemm_algo=algo).cpu().numpy()
+    assert np.abs(plain - np.einsum("oc,pcn->pon", w.astype(np.float64), x.astype(np.float64))).max() < 1e-4 * max(1.0, np.abs(ref).max())
