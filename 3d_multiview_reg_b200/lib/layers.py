@@ -7,8 +7,9 @@ from .. import _cabi
 
 class Soft_NN(torch.nn.Module):
     """lib/layers.py:10-88.  corr_type 'hard', and 'soft' with st=True (whose forward value is the hard match:
-    y_hard - y_soft.detach() + y_soft, lib/layers.py:63-67), run on the sm_100a NN kernel.  The stochastic /
-    blended modes ('soft' with st=False, 'soft_gumbel') are not built yet and raise.
+    y_hard - y_soft.detach() + y_soft, lib/layers.py:63-67), run on the sm_100a NN kernels; 'soft' with st=False (the demo
+    configuration: softmax-blended target coordinates) runs the online-softmax kernel lmpcr_nn_soft.  The stochastic
+    'soft_gumbel' mode is not built and raises.
     `_temperature` is kept so that checkpoints load (state_dict key feature_matching._temperature)."""
 
     def __init__(self, corr_type="soft", st=True, temp=0.3, min_temp=1e-4, device="cuda", algo=None):
@@ -33,13 +34,17 @@ class Soft_NN(torch.nn.Module):
         return _cabi.nn_argmin(x_f, y_f, jobs, algo=algo), jobs
 
     def forward(self, x_f, y_f, y_c):
-        if self.corr_type == "soft_gumbel" or (self.corr_type == "soft" and not self.st):
-            raise NotImplementedError("corr_type=%r with st=%r is not built on the B200 path yet" % (self.corr_type, self.st))
+        if self.corr_type == "soft_gumbel":
+            raise NotImplementedError("corr_type='soft_gumbel' (stochastic) is not built on the B200 path")
+        if self.corr_type == "soft" and not self.st:
+            b = x_f.shape[0]
+            jobs = torch.arange(b, dtype=torch.int32, device=x_f.device).unsqueeze(1).repeat(1, 2)
+            return _cabi.nn_soft(x_f, y_f, y_c, jobs, float(self.get_temp().item()))
         idx, jobs = self.nn_indices(x_f, y_f)
         return _cabi.gather_xyz(y_c, jobs, idx)
 
 
-_NN_ALGO = {"value": None}
+_NN_ALGO = {"value": _cabi.NN_TENSOR}     # tcgen05 screening + exact rescoring for 32-d features; exact SIMT otherwise
 
 
 def default_nn_algo(dim):

@@ -61,21 +61,35 @@ class PairwiseReg(nn.Module):
         pairs = torch.as_tensor(pairs, dtype=torch.int32, device=xyz_batch.device).reshape(-1, 2)
         xyz_batch = xyz_batch.float().contiguous()
         f_batch = f_batch.float().contiguous()
-        if self.feature_matching.corr_type == "soft_gumbel" or (self.feature_matching.corr_type == "soft" and not self.feature_matching.st):
-            raise NotImplementedError("soft (non straight-through) correspondences are not built on the B200 path yet")
-        from ..layers import default_nn_algo
-        algo = default_nn_algo(f_batch.shape[2])
-        idx_st = _cabi.nn_argmin(f_batch, f_batch, pairs, algo=algo)                     # :110
-        idx_ts = _cabi.nn_argmin(f_batch, f_batch, pairs.flip(1).contiguous(), algo=algo)  # :111
-        if self.mutuals:
-            # computed like the reference (:114-115) -- and, like there, not forwarded to the filter
-            nn_C_s_t = _cabi.gather_xyz(xyz_batch, pairs, idx_st)
-            nn_C_t_s = _cabi.gather_xyz(xyz_batch, pairs.flip(1).contiguous(), idx_ts)
+        fm = self.feature_matching
+        if fm.corr_type == "soft_gumbel":
+            raise NotImplementedError("corr_type='soft_gumbel' (stochastic) is not built on the B200 path")
+        pairs_r = pairs.flip(1).contiguous()
+        if fm.corr_type == "soft" and not fm.st:
+            # demo configuration: softmax-blended target coordinates (lib/layers.py:59-70,86)
+            T = float(fm.get_temp().item())
+            nn_C_s_t = _cabi.nn_soft(f_batch, f_batch, xyz_batch, pairs, T)                      # :110
             xyz_s = torch.index_select(xyz_batch, 0, pairs[:, 0].long())
-            xyz_t = torch.index_select(xyz_batch, 0, pairs[:, 1].long())
-            self.last_mutuals = extract_mutuals(xyz_s, xyz_t, nn_C_s_t, nn_C_t_s)
-        _, xs = _cabi.mutual_xs(xyz_batch, pairs, idx_st, idx_ts, want_mutual=False)
-        n_pairs, n = idx_st.shape
+            if self.mutuals:
+                nn_C_t_s = _cabi.nn_soft(f_batch, f_batch, xyz_batch, pairs_r, T)                # :111
+                xyz_t = torch.index_select(xyz_batch, 0, pairs[:, 1].long())
+                self.last_mutuals = extract_mutuals(xyz_s, xyz_t, nn_C_s_t, nn_C_t_s)            # computed, not forwarded (Q2)
+            xs = torch.cat((xyz_s, nn_C_s_t), dim=-1).unsqueeze(1)                               # lib/utils.py:915-926
+            n_pairs, n = xs.shape[0], xs.shape[2]
+        else:
+            from ..layers import default_nn_algo
+            algo = default_nn_algo(f_batch.shape[2])
+            idx_st = _cabi.nn_argmin(f_batch, f_batch, pairs, algo=algo)                         # :110
+            idx_ts = _cabi.nn_argmin(f_batch, f_batch, pairs_r, algo=algo)                       # :111
+            if self.mutuals:
+                # computed like the reference (:114-115) -- and, like there, not forwarded to the filter
+                nn_C_s_t = _cabi.gather_xyz(xyz_batch, pairs, idx_st)
+                nn_C_t_s = _cabi.gather_xyz(xyz_batch, pairs_r, idx_ts)
+                xyz_s = torch.index_select(xyz_batch, 0, pairs[:, 0].long())
+                xyz_t = torch.index_select(xyz_batch, 0, pairs[:, 1].long())
+                self.last_mutuals = extract_mutuals(xyz_s, xyz_t, nn_C_s_t, nn_C_t_s)
+            _, xs = _cabi.mutual_xs(xyz_batch, pairs, idx_st, idx_ts, want_mutual=False)
+            n_pairs, n = idx_st.shape
         filtering_input = {"xs": xs, "ys": torch.zeros(n_pairs, n, 1), "ts": torch.zeros(n_pairs, 3, 1),
                            "Rs": torch.eye(3).unsqueeze(0).repeat(n_pairs, 1, 1)}               # lib/utils.py:911-913
         return filtering_input, F0, F1

@@ -97,6 +97,15 @@ int lmpcr_debug_tc_profile(unsigned long long* out16, int reset);
 int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, int dim, int batch, float* out, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* Soft (non straight-through) correspondences, lib/layers.py:59-70,86 `Soft_NN(corr_type='soft', st=False)` -- the demo
+ * configuration (configs/pairwise_registration/demo/config.yaml):
+ *   out[j,i,:] = sum_k softmax_k(-dist(q_i, b_k) / temperature) * b_xyz[bs,k,:]        out [n_jobs, n_q, 3]
+ * temperature = max(_temperature^2, min_temp) (lib/layers.py:41-42), passed by the caller.  Online softmax over streamed
+ * target tiles: the N x M matrix is never stored.  fp32 CUDA cores; dist is the reference's exact fp32 value, the softmax
+ * agrees with torch to ~1e-6 relative.  workspace as lmpcr_nn_workspace_bytes(..., LMPCR_NN_EXACT_SIMT).  dim == 32. */
+int lmpcr_nn_soft(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, const float* b_xyz, int n_b_sets, int n_b, int dim,
+                  const int32_t* jobs, int n_jobs, float temperature, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Correspondence coordinates of hard matches: out[j,i,:] = b_xyz[jobs[j].bs, idx[j,i], :]
  * (lib/layers.py:86 `torch.matmul(one_hot, y_c)`).  b_xyz [n_b_sets, n_b, 3]. */
 int lmpcr_gather_xyz(const float* b_xyz, int n_b, const int32_t* jobs, int n_jobs, const int32_t* idx, int n_q,

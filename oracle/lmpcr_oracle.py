@@ -81,6 +81,17 @@ def hard_correspondences(x_f, y_f, y_c):
     return np.asarray(y_c, dtype=np.float32)[idx], idx
 
 
+def soft_correspondences(x_f, y_f, y_c, temperature):
+    """Soft_NN(corr_type='soft', st=False).forward (lib/layers.py:59-70,86): softmax(-dist/T, dim=2) @ y_c, with dist the
+    reference's fp32 distance; the softmax and the blend are carried in fp64 here (truth witness)."""
+    dist = pairwise_distance_f32(x_f, y_f).astype(np.float64)
+    l = -dist / float(temperature)
+    l -= l.max(axis=1, keepdims=True)
+    w = np.exp(l)
+    w /= w.sum(axis=1, keepdims=True)
+    return w @ np.asarray(y_c, np.float64)
+
+
 def mutual_index(idx_st, idx_ts):
     """Index definition of a mutual nearest neighbour, scripts/extract_data.py:186-190, expressed for
     source points:  i is mutual iff idx_ts[idx_st[i]] == i."""

@@ -34,6 +34,7 @@ def main():
     nn = {}
     cases = [("s300x700", 300, 700, 11), ("s1000", 1000, 1000, 12), ("s5000", 5000, 5000, 41), ("s2049x777", 2049, 777, 13)]
     hard = lib.layers.Soft_NN(corr_type="hard", device="cpu")
+    soft = lib.layers.Soft_NN(corr_type="soft", st=False, device="cpu")     # demo config: temp 0.3 -> T = 0.09
     for name, n, m, seed in cases:
         big = max(n, m)
         feats, xyz, _ = O.synth_scene(2, big, seed=seed)
@@ -47,6 +48,9 @@ def main():
             c_st = hard(t(fs)[None], t(ft)[None], t(xt)[None])            # lib/layers.py:44
             c_ts = hard(t(ft)[None], t(fs)[None], t(xs_)[None])
             assert np.array_equal(c_st[0].numpy(), xt[nn[name + "_idx_st"]])
+            if n <= 1000:
+                nn[name + "_soft_st"] = soft(t(fs)[None], t(ft)[None], t(xt)[None])[0].numpy()
+                nn[name + "_soft_T"] = np.array(float(soft.get_temp().item()))
             if n == m and n <= 1000:
                 mut = lib.utils.extract_mutuals(t(xs_)[None], t(xt)[None], c_st, c_ts)   # lib/utils.py:822
                 nn[name + "_mutual_geo"] = mut[0].numpy().astype(np.uint8)

@@ -152,3 +152,24 @@ def test_tensor_path_many_jobs_persistent_grid():
     for j in (0, 7, 29):
         ri, rd = nn_c.nn_argmin(feats[jobs[j][0]], feats[jobs[j][1]])
         assert np.array_equal(idx[j].cpu().numpy(), ri) and np.array_equal(dist[j].cpu().numpy(), rd)
+
+
+@pytest.mark.parametrize("name", ["s300x700", "s1000"])
+def test_soft_correspondences_vs_reference(golden_dir, name):
+    """corr_type='soft', st=False (demo config): online-softmax kernel vs the reference's output and the fp64 oracle."""
+    import importlib
+    g = np.load(os.path.join(golden_dir, "nn_golden.npz"))
+    n, m, seed = [int(v) for v in g[name + "_shape"]]
+    feats, xyz, _ = O.synth_scene(2, max(n, m), seed=seed)
+    fs, ft, xt = feats[0:1, :n], feats[1:2, :m], xyz[1:2, :m]
+    T = float(g[name + "_soft_T"])
+    out = cabi.nn_soft(cu(fs), cu(ft), cu(xt), _jobs([[0, 0]]), T)[0].cpu().numpy()
+    assert np.abs(out - g[name + "_soft_st"]).max() < 2e-5
+    assert np.abs(out - O.soft_correspondences(fs[0], ft[0], xt[0], T)).max() < 2e-5
+    L = importlib.import_module("3d_multiview_reg_b200.lib.layers")
+    soft = L.Soft_NN(corr_type="soft", st=False, device="cuda").cuda()
+    assert np.abs(soft(cu(fs), cu(ft), cu(xt))[0].cpu().numpy() - g[name + "_soft_st"]).max() < 2e-5
+    # sharp temperature -> converges to the hard match
+    hard = cabi.gather_xyz(cu(xt), _jobs([[0, 0]]), cabi.nn_argmin(cu(fs), cu(ft), _jobs([[0, 0]])))[0].cpu().numpy()
+    sharp = cabi.nn_soft(cu(fs), cu(ft), cu(xt), _jobs([[0, 0]]), 1e-4)[0].cpu().numpy()
+    assert np.median(np.abs(sharp - hard).max(axis=1)) < 1e-6

@@ -68,3 +68,28 @@ def test_pairwise_reg_module_surface():
     m2 = pw.PairwiseReg(None, net, torch.device("cuda"))
     d, a, b = m2.compute_descriptors({"xs": filt_in["xs"]})
     assert a is None and b is None and d["xs"] is filt_in["xs"]
+
+
+def test_pairwise_reg_demo_config_soft_correspondences():
+    """configs/pairwise_registration/demo/config.yaml: corr_type soft, st_grad_flag False, use_mutuals True."""
+    pw = importlib.import_module("3d_multiview_reg_b200.lib.pairwise")
+    S, n = 2, 500
+    feats, xyz, _ = O.synth_scene(S, n, seed=15)
+    sd = O.synth_state_dict(15)
+    net = load_oanet(sd)
+    model = pw.PairwiseReg(descriptor_module=lambda d: d["feat_in"], filtering_module=net, device=torch.device("cuda"),
+                           samp_type="rand", corr_type="soft", mutuals_flag=True, tgt_num_points=n,
+                           straight_through_gradient=False).eval().cuda()
+    np.random.seed(41)
+    data = {"pcd0": torch.from_numpy(xyz.reshape(-1, 3)), "feat_in": torch.from_numpy(feats.reshape(-1, 32)), "pts_list": torch.tensor([n] * S)}
+    filt_in, F0, F1, out = model(data)
+    np.random.seed(41)
+    sel = [np.random.choice(np.arange(i * n, (i + 1) * n), n, replace=False) - i * n for i in range(S)]
+    fa, fb, xa, xb = feats[0][sel[0]], feats[1][sel[1]], xyz[0][sel[0]], xyz[1][sel[1]]
+    ref = O.soft_correspondences(fa, fb, xb, 0.09)
+    xs = filt_in["xs"].cpu().numpy()
+    assert np.array_equal(xs[0, 0, :, :3], xa) and np.abs(xs[0, 0, :, 3:] - ref).max() < 2e-5
+    ref_back = O.soft_correspondences(fb, fa, xa, 0.09)
+    mut = O.extract_mutuals(xa, xb, ref.astype(np.float32), ref_back.astype(np.float32))
+    assert (model.last_mutuals[0].cpu().numpy() != mut).mean() < 0.01          # blended coordinates: a few borderline flips allowed
+    assert tuple(out["rot_est"][-1].shape) == (1, 3, 3)

@@ -72,6 +72,16 @@ def test_mutuals_and_xs(nn_g):
     assert mi.sum() > 0 and np.all(mutual_geo >= mi)     # index-mutual implies geometric-mutual (Q3)
 
 
+@pytest.mark.parametrize("name", ["s300x700", "s1000"])
+def test_soft_correspondences(nn_g, name):
+    """Soft (non-ST) correspondences vs the reference's Soft_NN('soft', st=False): 2e-5 m (fp32 softmax over 700-1000 terms)."""
+    fs, ft, _, xt = _nn_inputs(nn_g, name)
+    T = float(nn_g[name + "_soft_T"])
+    assert abs(T - 0.09) < 1e-6
+    out = O.soft_correspondences(fs, ft, xt, T)
+    assert np.abs(out - nn_g[name + "_soft_st"]).max() < 2e-5
+
+
 def test_pair_enumeration():
     p = O.enumerate_pairs(5)
     assert p.shape == (10, 2) and p[0].tolist() == [0, 1] and p[-1].tolist() == [3, 4] and np.all(p[:, 0] < p[:, 1])
