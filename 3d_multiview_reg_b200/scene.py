@@ -38,14 +38,15 @@ class SceneRegistrar:
     """Registers scan pairs of one scene with the sm_100a kernels.
 
     filtering_module: a `lib.filtering.oanet.OANet` (this package's mirror) already on the GPU.
-    nn_algo: _cabi.NN_EXACT_SIMT | _cabi.NN_TENSOR.   pair_chunk: pairs per stage-1/2/3 launch group.
+    nn_algo: _cabi.NN_EXACT_SIMT | _cabi.NN_TENSOR.   nn_chunk: pairs per stage-1 call; pair_chunk: pairs per stage-2/3 call.
     """
 
-    def __init__(self, filtering_module, nn_algo=_cabi.NN_EXACT_SIMT, pair_chunk=512, mutual_mode=_cabi.MUTUAL_INDEX,
-                 mutual_thresh=0.05):
+    def __init__(self, filtering_module, nn_algo=_cabi.NN_EXACT_SIMT, pair_chunk=296, mutual_mode=_cabi.MUTUAL_INDEX,
+                 mutual_thresh=0.05, nn_chunk=2048):
         self.net = filtering_module
         self.nn_algo = nn_algo
         self.pair_chunk = int(pair_chunk)
+        self.nn_chunk = max(int(nn_chunk), self.pair_chunk)
         self.mutual_mode = mutual_mode
         self.mutual_thresh = mutual_thresh
         self._params = None
@@ -79,27 +80,34 @@ class SceneRegistrar:
         cfg = self.net.cabi_cfg()
         cfg.guard_mode = _cabi.GUARD_PAIR
         params = self._param_table()
-        for p0 in range(0, P, self.pair_chunk):
-            pc = pairs[p0:p0 + self.pair_chunk].contiguous()
+        # stage 1 for large slabs of pairs, both directions in ONE call: the per-scan operand preparation of the tensor
+        # path is then paid once per slab instead of twice per filter chunk
+        for s0 in range(0, P, self.nn_chunk):
+            ps = pairs[s0:s0 + self.nn_chunk].contiguous()
+            ns = ps.shape[0]
             t = self._tic("nn")
-            idx_st = _cabi.nn_argmin(feats, feats, pc, algo=self.nn_algo)
-            idx_ts = _cabi.nn_argmin(feats, feats, pc.flip(1).contiguous(), algo=self.nn_algo)
+            idx_both = _cabi.nn_argmin(feats, feats, torch.cat([ps, ps.flip(1)], 0).contiguous(), algo=self.nn_algo)
             self._toc(t)
-            t = self._tic("mutual_xs")
-            mutual, xs = _cabi.mutual_xs(xyz, pc, idx_st, idx_ts, self.mutual_mode, self.mutual_thresh,
-                                         xs_channels=6 + cfg.side_channel, want_mutual=keep_correspondences or cfg.side_channel == 1)
-            self._toc(t)
-            t = self._tic("filter")
-            out = _cabi.filter_forward(xs, params, cfg, want_latent=False, want_conf=True)
-            self._toc(t)
-            t = self._tic("records")
-            rec[p0:p0 + pc.shape[0]] = _cabi.pack_pose_records(out["R"][-1], out["t"][-1], out["conf"], out["status"])
-            self._toc(t)
-            if extras is not None:
-                extras["idx_st"].append(idx_st)
-                extras["idx_ts"].append(idx_ts)
-                extras["mutual"].append(mutual)
-                extras["scores"].append(out["scores"][-1])
+            for q0 in range(0, ns, self.pair_chunk):
+                pc = ps[q0:q0 + self.pair_chunk].contiguous()
+                nc = pc.shape[0]
+                idx_st, idx_ts = idx_both[q0:q0 + nc], idx_both[ns + q0:ns + q0 + nc]
+                t = self._tic("mutual_xs")
+                mutual, xs = _cabi.mutual_xs(xyz, pc, idx_st, idx_ts, self.mutual_mode, self.mutual_thresh,
+                                             xs_channels=6 + cfg.side_channel, want_mutual=keep_correspondences or cfg.side_channel == 1)
+                self._toc(t)
+                t = self._tic("filter")
+                out = _cabi.filter_forward(xs, params, cfg, want_latent=False, want_conf=True)
+                self._toc(t)
+                t = self._tic("records")
+                p0 = s0 + q0
+                rec[p0:p0 + nc] = _cabi.pack_pose_records(out["R"][-1], out["t"][-1], out["conf"], out["status"])
+                self._toc(t)
+                if extras is not None:
+                    extras["idx_st"].append(idx_st)
+                    extras["idx_ts"].append(idx_ts)
+                    extras["mutual"].append(mutual)
+                    extras["scores"].append(out["scores"][-1])
         if extras is not None:
             extras = {k: torch.cat(v, 0) for k, v in extras.items()}
         return rec, extras
