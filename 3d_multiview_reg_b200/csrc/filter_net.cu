@@ -468,6 +468,7 @@ size_t per_pair_floats(int C, int K, int N) {
   f += (size_t)N_PART * r64((size_t)C * tmax * 2) + r64((size_t)K * tmax * 2);            // norm / softmax partials
   f += r64((size_t)N * 4 * ((K + 127) / 128) * 2);                                        // column-softmax partials (diff_unpool)
   f += r64(tc_weight_blob_bytes(C, K) / 4) + r64(tc_weight_blob_bytes(C, N) / 4);        // pre-split x2 / x1_1 (pool, unpool A operands)
+  f += r64(tc_b_blob_bytes(C, N) / 4);                                                    // converted B of the embedding convs
   return f;
 }
 
@@ -609,6 +610,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   bool want_col = false;   // set around the diff_unpool embedding conv: its epilogue emits softmax-over-clusters partials
   uint8_t* blob_x2 = reinterpret_cast<uint8_t*>(take(tc_weight_blob_bytes(C, K) / 4));
   uint8_t* blob_x11 = reinterpret_cast<uint8_t*>(take(tc_weight_blob_bytes(C, N) / 4));
+  uint8_t* blob_bconv = reinterpret_cast<uint8_t*>(take(tc_b_blob_bytes(C, N) / 4));
   auto part_index = [&](const float* x) -> int {
     for (int i = 0; i < N_PART; ++i) if (part_key[i] == x) return i;
     return -1;
@@ -653,6 +655,13 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       a.Res = res; a.r_batch = rb; a.bias = cv.b;
       a.prologue = TC_PRO_AFFINE_RELU; a.p0 = W.scale; a.p1 = W.shift; a.p_batch = cin;
       a.M = cout; a.N = L; a.K = cin;
+      if (cout > 128 && cin == C && L == N && g <= 65535) {
+        // several m-tiles share every B tile (500-cluster embedding convs): normalise + split the activations ONCE into a
+        // bf16 hi/lo blob, then both operands stream in by TMA and no conversion is repeated per m-tile
+        LMPCR_TRY(launch_convert_b(x, xb, L, cin, L, W.scale, W.shift, cin, blob_bconv, g, st));
+        a.b_blob = blob_bconv; a.b_blob_batch = (long long)tc_b_blob_bytes(cin, L);
+        a.prologue = TC_PRO_NONE;
+      }
       if (oi >= 0 && cout == C) {
         part_valid[oi] = tc_fast_epilogue(a);
         a.stats_out = part_valid[oi] ? part_buf[oi] : nullptr;

@@ -94,6 +94,32 @@ __global__ void split_weights_kernel(const float* __restrict__ Wb, int M, int K,
   split8_store(x, base, base + A_OP_BYTES);
 }
 
+// fp32 activations [K rows, N columns] (+ fused affine/ReLU) -> per (n-tile, k-chunk) [hi 4 KB | lo 4 KB] in the j-major UMMA
+// layout, i.e. exactly the shared-memory image the producer warps would have written.  One warp per 8 x 32 block.
+__global__ void convert_b_kernel(const float* __restrict__ Bb, long long b_batch, int b_ld, int K, int N, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, int p_batch, uint8_t* __restrict__ blobb, long long blob_batch) {
+  const int p = blockIdx.z;
+  const int n_kc = (K + KC - 1) / KC, tiles_n = (N + TN - 1) / TN;
+  const int lane = threadIdx.x & 31, l8 = lane & 7, g4 = lane >> 3;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (nt, kc, it)
+  constexpr int ITS = (KC / 8) * (TN / 32);
+  if (wid >= (long long)tiles_n * n_kc * ITS) return;
+  const int it = (int)(wid % ITS);
+  const int kc = (int)((wid / ITS) % n_kc), nt = (int)(wid / ((long long)ITS * n_kc));
+  const int k = kc * KC + (it / (TN / 32)) * 8 + l8, j0 = nt * TN + (it % (TN / 32)) * 32 + g4 * 8;
+  const int nv = (k < K) ? min(8, max(0, N - j0)) : 0;
+  float x[8];
+  load8(Bb + (long long)p * b_batch + (long long)k * b_ld + j0, nv, x);
+  if (scale && nv > 0) {
+    const float sc = __ldg(scale + (long long)p * p_batch + k), sh = __ldg(shift + (long long)p * p_batch + k);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) if (e < nv) x[e] = fmaxf(fmaf(x[e], sc, sh), 0.f);
+  }
+  uint8_t* base = blobb + (long long)p * blob_batch + ((size_t)nt * n_kc + kc) * 2 * B_OP_BYTES +
+                  ((it % (TN / 32)) * 4 + g4) * MN_SBO + (it / (TN / 32)) * MN_LBO + l8 * 16;
+  split8_store(x, base, base + B_OP_BYTES);
+}
+
 // cycle counters for timing experiments (LMPCR_TC_DEBUG bit 8): one representative thread per role accumulates here
 __device__ unsigned long long g_tc_prof[16];
 #define TC_PROF(slot, t0)                                                                  \
@@ -123,11 +149,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
   const bool prof_me = (blockIdx.x == 0) && (threadIdx.x == 32 || threadIdx.x == 32 * FIRST_EPI_WARP || threadIdx.x == 32 * FIRST_PROD_WARP);
   long long tp = clock64();
   const bool a_blob = g.a_blob != nullptr;
+  const bool b_blob = g.b_blob != nullptr;        // both operands by TMA: the producer warps have nothing to do
   const int tiles_m = (g.M + TM - 1) / TM, tiles_n = (g.N + TN - 1) / TN, n_kc = (g.K + KC - 1) / KC;
   const long long n_tiles = (long long)batch * tiles_m * tiles_n;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), N_PROD_WARPS + (a_blob ? 1 : 0)); mbar_init(EMPTY(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), b_blob ? 1 : N_PROD_WARPS + (a_blob ? 1 : 0)); mbar_init(EMPTY(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(T_FULL(a), 1); mbar_init(T_EMPTY(a), 128); }
   }
   if (threadIdx.x < 128) mbar_init(smem_u32(rowbars + threadIdx.x), 1);
@@ -164,7 +191,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
     // The activations of a group of pairs do not fit L2; this warp runs PF_CHUNKS chunks ahead of the pipeline and pulls
     // the B rows (and the residual rows of the tile) into L2 with prefetch.global.L2.
     constexpr int PF_CHUNKS = 8;
-    const bool pf_ok = ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && ((g.b_ld & 3) == 0) && ((g.b_batch & 3) == 0);
+    const bool pf_ok = !b_blob && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && ((g.b_ld & 3) == 0) && ((g.b_batch & 3) == 0);
     const bool pf_res = g.Res && tc_fast_epilogue(g);
     auto prefetch_chunk = [&](long long tile, int kc) {
       int p, mt, nt; decode(tile, p, mt, nt);
@@ -207,9 +234,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
         pf_advance();
         mbar_wait(EMPTY(stage), phase ^ 1);      // paces the prefetcher with the pipeline
         if (a_blob && lane == 0) {
-          mbar_expect_tx(FULL(stage), 2 * A_OP_BYTES);
+          mbar_expect_tx(FULL(stage), 2 * A_OP_BYTES + (b_blob ? 2 * B_OP_BYTES : 0));
           bulk_g2s(smem_u32(smem + (size_t)stage * STAGE_BYTES), g.a_blob + (long long)p * g.a_blob_batch + ((size_t)mt * n_kc + kc) * 2 * A_OP_BYTES,
                    2 * A_OP_BYTES, FULL(stage));
+          if (b_blob)
+            bulk_g2s(smem_u32(smem + (size_t)stage * STAGE_BYTES + 2 * A_OP_BYTES),
+                     g.b_blob + (long long)p * g.b_blob_batch + ((size_t)nt * n_kc + kc) * 2 * B_OP_BYTES, 2 * B_OP_BYTES, FULL(stage));
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -251,6 +281,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
       }
     }
   } else if (warp >= FIRST_PROD_WARP) {
+    if (!b_blob) {
     // ===================== operand producers =====================
     // Software-pipelined: the fp32 values of the NEXT chunk are fetched into registers right after the current chunk
     // has been converted, so the global-memory round trip overlaps the wait for a free stage.
@@ -395,6 +426,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
         if (kc + 1 < n_kc) fetch_b(tile, kc + 1);
         else if (tile + gridDim.x < n_tiles) fetch_b(tile + gridDim.x, 0);
       }
+    }
     }
   } else {
     // ===================== epilogue (warps 2..5; TMEM lane quarter = warp & 3) =====================
@@ -607,6 +639,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
 
 }  // namespace
 
+size_t tc_b_blob_bytes(int K, int N) { return (size_t)((N + TN - 1) / TN) * ((K + KC - 1) / KC) * 2 * B_OP_BYTES; }
+
+int launch_convert_b(const float* B, long long b_batch, int b_ld, int K, int N, const float* scale, const float* shift, int p_batch,
+                     uint8_t* blob, int batch, cudaStream_t st) {
+  LMPCR_REQUIRE(batch > 0 && batch <= 65535, LMPCR_ERR_ARG, "convert_b: batch");
+  const long long warps = (long long)((N + TN - 1) / TN) * ((K + KC - 1) / KC) * (KC / 8) * (TN / 32);
+  dim3 grid((unsigned)((warps + 7) / 8), 1, batch);
+  convert_b_kernel<<<grid, 256, 0, st>>>(B, b_batch, b_ld, K, N, scale, shift, p_batch, blob, (long long)tc_b_blob_bytes(K, N));
+  return check_launch("convert_b_kernel");
+}
+
 size_t tc_weight_blob_bytes(int M, int K) {
   return (size_t)((M + TM - 1) / TM) * ((K + KC - 1) / KC) * 2 * A_OP_BYTES;
 }
@@ -631,6 +674,7 @@ int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
   if (dbg < 0) { const char* e = getenv("LMPCR_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
   a.debug = dbg;
   LMPCR_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && batch > 0, LMPCR_ERR_ARG, "tcgemm: bad sizes");
+  LMPCR_REQUIRE(!a.b_blob || (a.a_blob && !a.b_kmajor), LMPCR_ERR_ARG, "tcgemm: b_blob needs a_blob and the j-major layout");
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(tcgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);

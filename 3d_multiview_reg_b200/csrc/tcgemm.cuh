@@ -18,6 +18,10 @@ struct TcGemmArgs {
   // B: fp32; b_kmajor = 0: B[p,k,j] at B + p*b_batch + k*b_ld + j (j contiguous)
   //          b_kmajor = 1: B[p,k,j] at B + p*b_batch + j*b_ld + k (k contiguous)
   const float* B; long long b_batch; int b_ld; int b_kmajor;
+  // ... or an already converted B (launch_convert_b): per (batch, n-tile, k-chunk) [hi 4 KB | lo 4 KB] in the UMMA j-major layout,
+  // prologue already applied.  Both operands then arrive by TMA and the producer warps stay idle (used when M spans several
+  // m-tiles, e.g. the 500-cluster embedding convs, so that the conversion is not repeated per m-tile).
+  const uint8_t* b_blob; long long b_blob_batch;
   float* C; long long c_batch; int c_i, c_j;        // C[p,i,j] at C + p*c_batch + i*c_i + j*c_j
   const float* Res; long long r_batch;              // same i/j strides as C (optional)
   const float* bias;                                // [M] (optional)
@@ -44,6 +48,10 @@ size_t tc_weight_blob_bytes(int M, int K);
 // W[b] = W + b*w_batch, rows `ld` floats apart (k contiguous); blob[b] = blob + b*tc_weight_blob_bytes(M,K)
 int launch_split_weights(const float* W, int M, int K, uint8_t* blob, cudaStream_t st, int batch = 1, long long w_batch = 0, int ld = -1);
 int launch_tcgemm(const TcGemmArgs& a, int batch, cudaStream_t st);
+// B[p,k,j] (j contiguous, rows b_ld apart) -> relu(x*scale[p,k]+shift[p,k]) (scale may be NULL) -> bf16 hi/lo tiles for b_blob
+size_t tc_b_blob_bytes(int K, int N);
+int launch_convert_b(const float* B, long long b_batch, int b_ld, int K, int N, const float* scale, const float* shift, int p_batch,
+                     uint8_t* blob, int batch, cudaStream_t st);
 int tc_profile_read(unsigned long long* out16, int reset);   // timing experiments (LMPCR_TC_DEBUG bit 8)
 
 }  // namespace lmpcr
