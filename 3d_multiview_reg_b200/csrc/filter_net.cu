@@ -551,7 +551,7 @@ static size_t fixed_bytes(const lmpcr_filter_cfg* cfg, int P, int N) {
 size_t filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int P, int N) {
   if (validate_cfg(cfg) != LMPCR_OK || P <= 0 || N <= 0) return 0;
   const size_t pp = per_pair_floats(cfg->net_channel, cfg->clusters, N) * 4;
-  size_t G = (size_t(8) << 30) / pp;   // up to ~8 GiB of activations per group of pairs (fewer, larger launches)
+  size_t G = (size_t(12) << 30) / pp;  // up to ~12 GiB of activations per group of pairs (fewer, larger launches)
   if (G < 1) G = 1;
   if (G > (size_t)P) G = P;
   return fixed_bytes(cfg, P, N) + align_up(G * pp, 256) + 4096;

@@ -324,61 +324,75 @@ nn_rescore_kernel(const float* __restrict__ q_feat, const float* __restrict__ sq
                   const float4* __restrict__ featT_b, const float* __restrict__ sqn_b, int n_b, int rows_pad_b,
                   const int32_t* __restrict__ jobs, int n_jobs, const uint2* __restrict__ cand, const int* __restrict__ unsupported,
                   int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= (long long)n_jobs * n_q) return;
+  // Persistent warps: each warp walks rows w, w + W, ... and fetches the NEXT row's candidate record, query feature and
+  // norms while it scores the current one, so only the candidate chunk itself (an L2 hit) is on the critical path.
+  const long long total = (long long)n_jobs * n_q;
+  const long long W = ((long long)gridDim.x * blockDim.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int job = (int)(w / n_q), row = (int)(w - (long long)job * n_q);
-  const int qs = __ldg(jobs + 2 * job), bs = __ldg(jobs + 2 * job + 1);
-  // lane k keeps feature k of the query row (one coalesced 128-byte load); the FMA chain broadcasts it with shuffles,
-  // which keeps the kernel at ~48 registers (40 resident warps per SM: the kernel is latency-bound on L2 hits).
-  const float a_l = __ldg(q_feat + ((size_t)qs * n_q + row) * D + lane);
-  const float an = __ldg(sqn_q + (size_t)qs * rows_pad_q + row);
-  const float4* tb = featT_b + (size_t)bs * rows_pad_b * 8;    // rows_pad_b/32 chunks * 256 float4
-  const float* nb = sqn_b + (size_t)bs * rows_pad_b;
-  float best = INFINITY;
-  int bj = 0x7fffffff;
-  auto score_chunk = [&](int ch) {
-    const int j = ch * CHUNK + lane;
-    const float4* src = tb + (size_t)ch * 256 + lane;
-    float4 v[8];
-#pragma unroll
-    for (int kq = 0; kq < 8; ++kq) v[kq] = __ldg(src + kq * 32);
-    const float bnj = __ldg(nb + j);
-    float c = 0.f;
-#pragma unroll
-    for (int kq = 0; kq < 8; ++kq) {
-      c = fmaf(__shfl_sync(0xffffffffu, a_l, 4 * kq), v[kq].x, c);
-      c = fmaf(__shfl_sync(0xffffffffu, a_l, 4 * kq + 1), v[kq].y, c);
-      c = fmaf(__shfl_sync(0xffffffffu, a_l, 4 * kq + 2), v[kq].z, c);
-      c = fmaf(__shfl_sync(0xffffffffu, a_l, 4 * kq + 3), v[kq].w, c);
-    }
-    const float d = __fadd_rn(__fadd_rn(__fmul_rn(2.0f, -c), an), bnj);
-    if (j < n_b && (d < best || (d == best && j < bj))) { best = d; bj = j; }
-  };
   const bool scan_all = (*unsupported != 0);
   const int n_chunks = (n_b + CHUNK - 1) / CHUNK;
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    const uint2 e = __ldg(cand + ((size_t)job * n_q + row) * 2 + half);
-    const uint32_t c16 = e.x & 0xFFFFu;
-    if (scan_all || c16 == OVERFLOW) {
-      for (int ch = 0; ch < n_chunks; ++ch)
-        if (((ch >> 2) & 1) == half) score_chunk(ch);
-    } else {
-      if (c16 > 0) score_chunk((int)(e.x >> 16));
-      if (c16 > 1) score_chunk((int)(e.y & 0xFFFFu));
-      if (c16 > 2) score_chunk((int)(e.y >> 16));
-    }
-  }
+  struct Row { uint4 cd; float a_l, an; int bs; };
+  auto fetch = [&](long long w) {
+    Row r;
+    const int job = (int)(w / n_q), row = (int)(w - (long long)job * n_q);
+    const int qs = __ldg(jobs + 2 * job);
+    r.bs = __ldg(jobs + 2 * job + 1);
+    r.cd = __ldg(reinterpret_cast<const uint4*>(cand) + w);                 // both column halves: 16 bytes
+    r.a_l = __ldg(q_feat + ((size_t)qs * n_q + row) * D + lane);             // lane k keeps feature k (coalesced 128 B)
+    r.an = __ldg(sqn_q + (size_t)qs * rows_pad_q + row);
+    return r;
+  };
+  long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= total) return;
+  Row nxt = fetch(w);
+  for (; w < total; w += W) {
+    const Row cur = nxt;
+    if (w + W < total) nxt = fetch(w + W);
+    const float4* tb = featT_b + (size_t)cur.bs * rows_pad_b * 8;    // rows_pad_b/32 chunks * 256 float4
+    const float* nb = sqn_b + (size_t)cur.bs * rows_pad_b;
+    float best = INFINITY;
+    int bj = 0x7fffffff;
+    auto score_chunk = [&](int ch) {
+      const int j = ch * CHUNK + lane;
+      const float4* src = tb + (size_t)ch * 256 + lane;
+      float4 v[8];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float od = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-    if (od < best || (od == best && oj < bj)) { best = od; bj = oj; }
-  }
-  if (lane == 0) {
-    idx_out[(size_t)job * n_q + row] = bj;
-    if (dist_out) dist_out[(size_t)job * n_q + row] = best;
+      for (int kq = 0; kq < 8; ++kq) v[kq] = __ldg(src + kq * 32);
+      const float bnj = __ldg(nb + j);
+      float c = 0.f;
+#pragma unroll
+      for (int kq = 0; kq < 8; ++kq) {
+        c = fmaf(__shfl_sync(0xffffffffu, cur.a_l, 4 * kq), v[kq].x, c);
+        c = fmaf(__shfl_sync(0xffffffffu, cur.a_l, 4 * kq + 1), v[kq].y, c);
+        c = fmaf(__shfl_sync(0xffffffffu, cur.a_l, 4 * kq + 2), v[kq].z, c);
+        c = fmaf(__shfl_sync(0xffffffffu, cur.a_l, 4 * kq + 3), v[kq].w, c);
+      }
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(2.0f, -c), cur.an), bnj);
+      if (j < n_b && (d < best || (d == best && j < bj))) { best = d; bj = j; }
+    };
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const uint32_t ex = half ? cur.cd.z : cur.cd.x, ey = half ? cur.cd.w : cur.cd.y;
+      const uint32_t c16 = ex & 0xFFFFu;
+      if (scan_all || c16 == OVERFLOW) {
+        for (int ch = 0; ch < n_chunks; ++ch)
+          if (((ch >> 2) & 1) == half) score_chunk(ch);
+      } else {
+        if (c16 > 0) score_chunk((int)(ex >> 16));
+        if (c16 > 1) score_chunk((int)(ey & 0xFFFFu));
+        if (c16 > 2) score_chunk((int)(ey >> 16));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (od < best || (od == best && oj < bj)) { best = od; bj = oj; }
+    }
+    if (lane == 0) {
+      idx_out[w] = bj;
+      if (dist_out) dist_out[w] = best;
+    }
   }
 }
 
@@ -463,7 +477,9 @@ int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float*
   nn_sweep_kernel<<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
   LMPCR_TRY(check_launch("nn_sweep_kernel"));
   const long long warps = (long long)n_jobs * n_q;
-  nn_rescore_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(q_feat, PQ.sqn, n_q, PQ.rows_pad, PB.feat_t, PB.sqn, n_b, PB.rows_pad, jobs,
+  const long long max_blocks = 4ll * sm_count();            // 4 resident blocks of 8 persistent warps per SM
+  const long long want_blocks = (warps + 7) / 8;
+  nn_rescore_kernel<<<(unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks), 256, 0, st>>>(q_feat, PQ.sqn, n_q, PQ.rows_pad, PB.feat_t, PB.sqn, n_b, PB.rows_pad, jobs,
                                                                          n_jobs, cand, unsupported, idx_out, dist_out);
   return check_launch("nn_rescore_kernel");
 }

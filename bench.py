@@ -235,11 +235,11 @@ def run_ours(args):
         dom = dominant_kernel_roofline(cabi, dev, n, pk)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (NN screen fp16->f32, GEMMs bf16x3->f32 on tensor cores)", "data": "synthetic",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: %d scans -> %d pairs x %d keypoints x 32-d per GPU (rank-0 scene of %d scans, %d pairs total)"
                                    % (S, per_rank, n, S_glob, pairs_total),
                        "nn_algo": "tcgen05+rescore" if args.nn_algo == 1 else "exact_simt", "gemm_algo": "tcgen05 split-bf16" if args.gemm_algo == 1 else "fp32 simt",
-                       "pair_chunk": args.pair_chunk, "l2": "256 MiB flush buffer written between timed iterations",
+                       "pair_chunk": args.pair_chunk, "arithmetic": "results in f32; NN screening fp16 operands -> f32 TMEM accumulators + exact f32 rescoring; GEMMs split-bf16 (hi+lo) -> f32", "l2": "256 MiB flush buffer written between timed iterations",
                        "parallelism": "pairs x%d" % world},
             # dominant kernel = tcgemm_kernel (the fused 1x1-conv layer; ~77 % of the step in the ncu launch list under
             # profiles/): timed alone, live, with CUDA events on a 128->128-channel layer with residual over 148 pairs.
