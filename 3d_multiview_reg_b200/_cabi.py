@@ -19,7 +19,7 @@ GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
 EXPORTS = [
-    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
     "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
     "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
 ]
@@ -53,6 +53,7 @@ def load():
     lib.lmpcr_nn_workspace_bytes.restype = _sz
     lib.lmpcr_nn_workspace_bytes.argtypes = [_i] * 7
     lib.lmpcr_nn_argmin.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]
+    lib.lmpcr_nn_top2.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]
     lib.lmpcr_nn_soft.argtypes = [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _sz, _vp]
     lib.lmpcr_launch_count.restype = ctypes.c_longlong
     lib.lmpcr_nn_tensor_debug.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
@@ -125,6 +126,22 @@ def nn_argmin(q_feat, b_feat, jobs, algo=NN_EXACT_SIMT, return_dist=False):
         _check(lib.lmpcr_nn_argmin(_p(q), q.shape[0], n, _p(b), b.shape[0], b.shape[1], q.shape[2], _p(jobs), J, _p(idx), _p(dist),
                                    algo, _p(ws), ws.numel(), _stream(q)))
     return (idx, dist) if return_dist else idx
+
+
+def nn_top2(q_feat, b_feat, jobs):
+    """Two nearest neighbours: (idx [J,n,2] int32, squared fp32 distances [J,n,2])  (scripts/extract_data.py:178-184)."""
+    lib = load()
+    q = _dev(q_feat, name="q_feat")
+    b = q if b_feat is q_feat else _dev(b_feat, name="b_feat")
+    jobs = _dev(jobs, torch.int32, "jobs")
+    J, n = jobs.shape[0], q.shape[1]
+    with torch.cuda.device(q.device):
+        idx = torch.empty((J, n, 2), dtype=torch.int32, device=q.device)
+        dist = torch.empty((J, n, 2), dtype=torch.float32, device=q.device)
+        ws = _ws(lib.lmpcr_nn_workspace_bytes(q.shape[0], n, b.shape[0], b.shape[1], q.shape[2], J, NN_EXACT_SIMT), q.device)
+        _check(lib.lmpcr_nn_top2(_p(q), q.shape[0], n, _p(b), b.shape[0], b.shape[1], q.shape[2], _p(jobs), J, _p(idx), _p(dist), _p(ws),
+                                 ws.numel(), _stream(q)))
+    return idx, dist
 
 
 def nn_soft(q_feat, b_feat, b_xyz, jobs, temperature):

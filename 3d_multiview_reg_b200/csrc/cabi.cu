@@ -115,6 +115,13 @@ int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, in
   return launch_pairwise_distance(src, n, dst, m, dim, batch, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int lmpcr_nn_top2(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim, const int32_t* jobs,
+                  int n_jobs, int32_t* idx_out, float* dist_out, void* workspace, size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_nn_top2(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, dim, jobs, n_jobs, idx_out, dist_out, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
+}
+
 int lmpcr_nn_soft(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, const float* b_xyz, int n_b_sets, int n_b, int dim,
                   const int32_t* jobs, int n_jobs, float temperature, float* out, void* workspace, size_t workspace_bytes, void* stream) {
   LMPCR_TRY(check_device());

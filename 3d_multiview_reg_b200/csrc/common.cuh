@@ -62,6 +62,8 @@ size_t nn_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, int dim,
 int launch_nn_argmin(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
                      const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, int algo, void* ws,
                      size_t ws_bytes, cudaStream_t st);
+int launch_nn_top2(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim, const int32_t* jobs,
+                   int n_jobs, int32_t* idx_out, float* dist_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_nn_soft(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, const float* b_xyz, int n_b_sets, int n_b, int dim,
                    const int32_t* jobs, int n_jobs, float temperature, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_pairwise_distance(const float* src, int n, const float* dst, int m, int dim, int batch, float* out, void* ws,

@@ -113,6 +113,69 @@ nn_exact_kernel(const float* __restrict__ q_feat, const float* __restrict__ q_no
   }
 }
 
+// Two nearest neighbours per query row (scripts/extract_data.py:178-184 asks sklearn for n_neighbors=2 to form the Lowe ratio
+// d1/d2, :191).  Same exact fp32 distance as nn_exact_kernel; first minimum wins, the runner-up is the smallest remaining.
+template <int DIM>
+__global__ void __launch_bounds__(NN_ROWS)
+nn_top2_kernel(const float* __restrict__ q_feat, const float* __restrict__ q_norm, int n_q, const float* __restrict__ b_feat,
+               const float* __restrict__ b_norm, int n_b, const int32_t* __restrict__ jobs, int32_t* __restrict__ idx_out,
+               float* __restrict__ dist_out) {
+  __shared__ __align__(16) float sb[NN_TILE * DIM];
+  __shared__ float sbn[NN_TILE];
+  const int job = blockIdx.y;
+  const int qs = __ldg(jobs + 2 * job), bs = __ldg(jobs + 2 * job + 1);
+  const int row = blockIdx.x * NN_ROWS + threadIdx.x;
+  const bool valid = row < n_q;
+  float a[DIM];
+  float an = 0.f;
+  if (valid) {
+    const float4* src = reinterpret_cast<const float4*>(q_feat + ((size_t)qs * n_q + row) * DIM);
+#pragma unroll
+    for (int k = 0; k < DIM / 4; ++k) {
+      const float4 v = __ldg(src + k);
+      a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+    }
+    an = __ldg(q_norm + (size_t)qs * n_q + row);
+  } else {
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) a[k] = 0.f;
+  }
+  float d1 = INFINITY, d2 = INFINITY;
+  int j1 = 0, j2 = 0;
+  const float* bbase = b_feat + (size_t)bs * n_b * DIM;
+  const float* bnbase = b_norm + (size_t)bs * n_b;
+  for (int j0 = 0; j0 < n_b; j0 += NN_TILE) {
+    const int rows = min(NN_TILE, n_b - j0);
+    __syncthreads();
+    {
+      const float4* g = reinterpret_cast<const float4*>(bbase + (size_t)j0 * DIM);
+      float4* s4 = reinterpret_cast<float4*>(sb);
+      const int n4 = rows * DIM / 4;
+      for (int e = threadIdx.x; e < NN_TILE * DIM / 4; e += NN_ROWS) s4[e] = (e < n4) ? __ldg(g + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e = threadIdx.x; e < NN_TILE; e += NN_ROWS) sbn[e] = (e < rows) ? __ldg(bnbase + j0 + e) : INFINITY;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int jj = 0; jj < rows; ++jj) {
+      float c = 0.f;
+      const float4* r0 = reinterpret_cast<const float4*>(sb + jj * DIM);
+#pragma unroll
+      for (int k = 0; k < DIM / 4; ++k) {
+        const float4 v = r0[k];
+        c = fmaf(a[4 * k], v.x, c); c = fmaf(a[4 * k + 1], v.y, c); c = fmaf(a[4 * k + 2], v.z, c); c = fmaf(a[4 * k + 3], v.w, c);
+      }
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(2.0f, -c), an), sbn[jj]);
+      if (d < d1) { d2 = d1; j2 = j1; d1 = d; j1 = j0 + jj; }
+      else if (d < d2) { d2 = d; j2 = j0 + jj; }
+    }
+  }
+  if (valid) {
+    const size_t o = ((size_t)job * n_q + row) * 2;
+    idx_out[o] = j1; idx_out[o + 1] = j2;
+    dist_out[o] = d1; dist_out[o + 1] = d2;
+  }
+}
+
 // Soft (non straight-through) correspondences, lib/layers.py:59-70,86 with st=False:
 //   x_corr[i] = sum_j softmax_j(-dist_ij / T) * y_c[j]
 // One thread per query row, online softmax over the streamed target tiles (running max, rescaled sum and 3 weighted
@@ -333,6 +396,32 @@ int launch_nn_argmin(const float* q_feat, int n_q_sets, int n_q, const float* b_
     case 56: return run_exact<56>(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, jobs, n_jobs, idx_out, dist_out, qn, bn, st);
     default: return run_exact<64>(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, jobs, n_jobs, idx_out, dist_out, qn, bn, st);
   }
+}
+
+int launch_nn_top2(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim, const int32_t* jobs,
+                   int n_jobs, int32_t* idx_out, float* dist_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  LMPCR_REQUIRE(n_jobs >= 0, LMPCR_ERR_ARG, "lmpcr_nn_top2: n_jobs < 0");
+  if (n_jobs == 0) return LMPCR_OK;
+  LMPCR_REQUIRE(q_feat && b_feat && jobs && idx_out && dist_out, LMPCR_ERR_ARG, "lmpcr_nn_top2: null pointer");
+  LMPCR_REQUIRE(dim == 32, LMPCR_ERR_UNSUPPORTED, "lmpcr_nn_top2: dim=%d (only 32 is built)", dim);
+  LMPCR_REQUIRE(n_b >= 2, LMPCR_ERR_ARG, "lmpcr_nn_top2: needs at least two target rows");
+  LMPCR_REQUIRE(((uintptr_t)q_feat % 16 == 0) && ((uintptr_t)b_feat % 16 == 0), LMPCR_ERR_ARG, "lmpcr_nn_top2: features must be 16-byte aligned");
+  const size_t need = nn_workspace_bytes(n_q_sets, n_q, n_b_sets, n_b, dim, n_jobs, LMPCR_NN_EXACT_SIMT);
+  LMPCR_REQUIRE(ws && ws_bytes >= need, LMPCR_ERR_WORKSPACE, "lmpcr_nn_top2: workspace %zu < %zu bytes", ws_bytes, need);
+  float* qn = reinterpret_cast<float*>(ws);
+  const bool same = (q_feat == b_feat) && (n_q_sets == n_b_sets) && (n_q == n_b);
+  float* bn = same ? qn : reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up((size_t)n_q_sets * n_q * 4, 256));
+  const size_t qr = (size_t)n_q_sets * n_q, br = (size_t)n_b_sets * n_b;
+  sqnorm_kernel<32><<<(unsigned)((qr + 127) / 128), 128, 0, st>>>(q_feat, qr, qn);
+  if (bn != qn) sqnorm_kernel<32><<<(unsigned)((br + 127) / 128), 128, 0, st>>>(b_feat, br, bn);
+  LMPCR_TRY(check_launch("sqnorm_kernel"));
+  for (int j0 = 0; j0 < n_jobs; j0 += 65535) {
+    const int nj = min(65535, n_jobs - j0);
+    dim3 grid((n_q + NN_ROWS - 1) / NN_ROWS, nj);
+    nn_top2_kernel<32><<<grid, NN_ROWS, 0, st>>>(q_feat, qn, n_q, b_feat, bn, n_b, jobs + 2 * (size_t)j0, idx_out + (size_t)j0 * n_q * 2,
+                                                 dist_out + (size_t)j0 * n_q * 2);
+  }
+  return check_launch("nn_top2_kernel");
 }
 
 int launch_nn_soft(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, const float* b_xyz, int n_b_sets, int n_b, int dim,

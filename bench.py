@@ -8,7 +8,7 @@ a 3DMatch-style scene of 60 fragments -> 1770 pairs at 5000 keypoints, 32-d feat
 One "step" = one pass of the whole path over the rank's pairs.  N>1: launched by torchrun, one rank per GPU; every
 rank holds the scene, registers its contiguous slice of the lexicographic pair list (1770 pairs per rank: weak
 scaling) and the step ends with the NCCL all-gather of the 16-float pose records.  Synthetic data
-(oracle.lmpcr_oracle.synth_scene, seed 41) and seeded random weights -- there is no network for datasets.
+(synthdata.synth_scene, seed 41) and seeded random weights -- there is no network for datasets.
 
 --impl reference: the reference's CPU implementation of the same path.  The reference is pure Python/torch and
 cannot travel to the GPU box, so the arm runs the oracle port (oracle/: C for the NN arithmetic, numpy for the
@@ -81,10 +81,15 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def lex_pairs(S):
+    """All scan pairs i < j in lexicographic order (lib/utils.py:873 itertools.combinations)."""
+    return np.array([(i, j) for i in range(S) for j in range(i + 1, S)], dtype=np.int32).reshape(-1, 2)
+
+
 def make_workload(S, n, seed=41):
-    from oracle import lmpcr_oracle as O
-    feats, xyz, _ = O.synth_scene(S, n, seed=seed)
-    sd = O.synth_state_dict(seed)
+    import synthdata                                     # neutral numpy generator (no oracle, no CUDA)
+    feats, xyz, _ = synthdata.synth_scene(S, n, seed=seed)
+    sd = synthdata.synth_state_dict(seed)
     return feats, xyz, sd
 
 
@@ -110,7 +115,7 @@ def run_reference(args):
     from oracle import nn_c
     S, n = args.scans, args.points
     feats, xyz, sd = make_workload(min(S, 8), n)         # a bounded sample only touches the first scans
-    pairs = O.enumerate_pairs(min(S, 8))[: args.ref_pairs]
+    pairs = lex_pairs(min(S, 8))[: args.ref_pairs]
     for _ in range(args.warmup):
         cpu_port_pairs(feats, xyz, sd, pairs[:1])
     t = [cpu_port_pairs(feats, xyz, sd, pairs) for _ in range(args.steps)]
@@ -141,7 +146,6 @@ def run_ours(args):
     cabi = pkg._cabi
     scene = importlib.import_module("3d_multiview_reg_b200.scene")
     oanet = importlib.import_module("3d_multiview_reg_b200.lib.filtering.oanet")
-    from oracle import lmpcr_oracle as O
 
     S, n = args.scans, args.points
     per_rank = S * (S - 1) // 2                          # weak scaling: every rank registers this many pairs
@@ -150,7 +154,7 @@ def run_ours(args):
     while S_glob * (S_glob - 1) // 2 < world * per_rank:
         S_glob += 1
     feats, xyz, sd = make_workload(S_glob, n)
-    all_pairs = O.enumerate_pairs(S_glob)[: world * per_rank]
+    all_pairs = lex_pairs(S_glob)[: world * per_rank]
     my_pairs = all_pairs[rank * per_rank:(rank + 1) * per_rank]
 
     net = oanet.OANet({"misc": dict(iter_num=1, net_depth=12, net_channel=128, clusters=500, normalize_weights=True, use_gpu=True,
@@ -260,7 +264,7 @@ def run_ours(args):
         line["gpu_launches"] = int(launches_per_step * args.steps)
         if world == 1 and not args.no_cpu_baseline:
             cf, cx, csd = feats[:8], xyz[:8], sd
-            cp = O.enumerate_pairs(8)[: args.cpu_pairs]
+            cp = lex_pairs(8)[: args.cpu_pairs]
             cpu_port_pairs(cf, cx, csd, cp[:1])
             sec = cpu_port_pairs(cf, cx, csd, cp)
             from oracle import nn_c

@@ -97,6 +97,12 @@ int lmpcr_debug_tc_profile(unsigned long long* out16, int reset);
 int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, int dim, int batch, float* out, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* Two nearest neighbours per query row, scripts/extract_data.py:178-184 (`kneighbors(n_neighbors=2)`), for the Lowe ratio
+ * d1/d2 (:191):  idx_out [n_jobs, n_q, 2] (int32), dist_out [n_jobs, n_q, 2] = SQUARED fp32 distances evaluated with the
+ * reference's torch formula (the ratio of Euclidean distances is sqrt(d1/d2)).  fp32 CUDA cores, dim == 32. */
+int lmpcr_nn_top2(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim, const int32_t* jobs,
+                  int n_jobs, int32_t* idx_out, float* dist_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Soft (non straight-through) correspondences, lib/layers.py:59-70,86 `Soft_NN(corr_type='soft', st=False)` -- the demo
  * configuration (configs/pairwise_registration/demo/config.yaml):
  *   out[j,i,:] = sum_k softmax_k(-dist(q_i, b_k) / temperature) * b_xyz[bs,k,:]        out [n_jobs, n_q, 3]

@@ -4,13 +4,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from oracle import lmpcr_oracle as O
+import synthdata
 from util import cabi, load_oanet
 ap = argparse.ArgumentParser()
 ap.add_argument("--pairs", type=int, default=64); ap.add_argument("--points", type=int, default=5000)
 ap.add_argument("--algo", type=int, default=1); ap.add_argument("--iters", type=int, default=3)
 a = ap.parse_args()
-sd = O.synth_state_dict(41)
-xs, _, _ = O.synth_xs(8, a.points, seed=41)
+sd = synthdata.synth_state_dict(41)
+xs, _, _ = synthdata.synth_xs(8, a.points, seed=41)
 xs = torch.from_numpy(np.tile(xs, (a.pairs // 8, 1, 1, 1))).cuda()
 net = load_oanet(sd, gemm_algo=a.algo)
 cfg, params = net.cabi_cfg(), net.param_table()

@@ -4,10 +4,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from oracle import lmpcr_oracle as O
+import synthdata
 from util import cabi, cu, load_oanet
 for (P, N, kw, seed) in [(3, 64, dict(net_channel=32, clusters=16), 9), (2, 2000, {}, 7)]:
-    sd = O.synth_state_dict(seed, **kw)
-    xs, _, _ = O.synth_xs(P, N, seed=seed)
+    sd = synthdata.synth_state_dict(seed, **kw)
+    xs, _, _ = synthdata.synth_xs(P, N, seed=seed)
     o64 = O.oanet_forward(xs, sd, dtype=np.float64)
     for algo in (0, 1):
         net = load_oanet(sd, gemm_algo=algo, **kw)

@@ -3,10 +3,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from oracle import lmpcr_oracle as O
+import synthdata
 from util import cabi, cu, load_oanet
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
-sd = O.synth_state_dict(50)
-xs, _, _ = O.synth_xs(1, N, seed=50)
+sd = synthdata.synth_state_dict(50)
+xs, _, _ = synthdata.synth_xs(1, N, seed=50)
 o64 = O.oanet_forward(xs, sd, dtype=np.float64)
 o32 = O.oanet_forward(xs, sd, dtype=np.float32)
 print("numpy fp32 vs fp64: logits %.2e" % np.abs(o32["logits"][-1] - o64["logits"][-1]).max())

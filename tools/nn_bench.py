@@ -4,12 +4,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from oracle import lmpcr_oracle as O
+import synthdata
 from util import cabi
 ap = argparse.ArgumentParser()
 ap.add_argument("--scans", type=int, default=60); ap.add_argument("--points", type=int, default=5000)
 ap.add_argument("--pairs", type=int, default=256); ap.add_argument("--algo", type=int, default=1); ap.add_argument("--iters", type=int, default=5)
 a = ap.parse_args()
-feats, xyz, _ = O.synth_scene(a.scans, a.points, seed=41)
+feats, xyz, _ = synthdata.synth_scene(a.scans, a.points, seed=41)
 f = torch.from_numpy(feats).cuda()
 pairs = torch.from_numpy(O.enumerate_pairs(a.scans)[: a.pairs]).cuda()
 jobs = torch.cat([pairs, pairs.flip(1)], 0).contiguous()

@@ -1,9 +1,10 @@
 import sys; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import numpy as np, torch
 from oracle import lmpcr_oracle as O, nn_c
+import synthdata
 from util import cabi, cu
 for (n,m,seed) in [(128,256,1),(300,700,11),(1000,1000,12)]:
-    feats,_,_=O.synth_scene(2,max(n,m),seed=seed)
+    feats,_,_=synthdata.synth_scene(2,max(n,m),seed=seed)
     fs,ft=feats[0,:n],feats[1,:m]
     jobs=torch.zeros((1,2),dtype=torch.int32,device='cuda')
     idx,dist,sc,amin=cabi.nn_tensor_debug(cu(fs[None]),cu(ft[None]),jobs)

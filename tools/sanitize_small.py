@@ -4,10 +4,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from oracle import lmpcr_oracle as O
+import synthdata
 from util import cabi, cu, load_oanet
 scene = importlib.import_module("3d_multiview_reg_b200.scene")
-feats, xyz, _ = O.synth_scene(3, 516, seed=1)
-sd = O.synth_state_dict(1)
+feats, xyz, _ = synthdata.synth_scene(3, 516, seed=1)
+sd = synthdata.synth_state_dict(1)
 f, x = cu(feats), cu(xyz)
 for g in (0, 1):
     net = load_oanet(sd, gemm_algo=g)
@@ -17,7 +18,7 @@ for g in (0, 1):
         print("gemm", g, "nn", a, float(rec.abs().sum()))
 jobs = torch.tensor([[0, 1]], dtype=torch.int32, device="cuda")
 print("soft", float(cabi.nn_soft(f, f, x, jobs, 0.09).sum()))
-xs, _, _ = O.synth_xs(2, 301, seed=3)     # ragged N: generic epilogue paths
+xs, _, _ = synthdata.synth_xs(2, 301, seed=3)     # ragged N: generic epilogue paths
 out = load_oanet(sd, gemm_algo=1)({"xs": torch.from_numpy(xs)})
 torch.cuda.synchronize()
 print("ragged ok", float(out["logits"][-1].sum()))
