@@ -21,6 +21,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_ptx.cuh"
 #include "tcgemm.cuh"
 
@@ -47,6 +49,12 @@ static_assert(TN % 32 == 0 && TN <= 128, "tile width");
 
 __device__ __forceinline__ void l2_prefetch_line(const void* src) {   // one 128-byte line into L2 (LSU path, not the TMA unit)
   asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+}
+
+__device__ __forceinline__ float exp2f_fast(float x) {   // MUFU.EX2
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ void split8_store(const float (&x)[8], uint8_t* hi_dst, uint8_t* lo_dst) {
@@ -131,7 +139,7 @@ __device__ unsigned long long g_tc_prof[16];
     }                                                                                      \
   } while (0)
 
-template <bool B_KMAJOR>
+template <bool B_KMAJOR, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int batch) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;                  // [128 rows][STG_ROW]
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
       int p, mt, nt; decode(tile, p, mt, nt);
       for (int kc = 0; kc < n_kc; ++kc) {
         pf_advance();
-        mbar_wait(EMPTY(stage), phase ^ 1);      // paces the prefetcher with the pipeline
+        mbar_wait_relaxed(EMPTY(stage), phase ^ 1);      // paces the prefetcher with the pipeline
         if (a_blob && lane == 0) {
           mbar_expect_tx(FULL(stage), 2 * A_OP_BYTES + (b_blob ? 2 * B_OP_BYTES : 0));
           bulk_g2s(smem_u32(smem + (size_t)stage * STAGE_BYTES), g.a_blob + (long long)p * g.a_blob_batch + ((size_t)mt * n_kc + kc) * 2 * A_OP_BYTES,
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
           }
         }
         TC_PROF(6, tp);
-        mbar_wait(EMPTY(stage), phase ^ 1);
+        mbar_wait_relaxed(EMPTY(stage), phase ^ 1);
         TC_PROF(3, tp);
         uint8_t* st_base = smem + (size_t)stage * STAGE_BYTES;
         // ---- B operand: prologue, hi/lo split, store in the UMMA canonical layout ----
@@ -433,6 +441,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
     const int quarter = warp & 3;
     const int r_own = quarter * 32 + lane;                             // the accumulator row (TMEM lane) this thread owns
     const bool fast = tc_fast_epilogue(g);
+    // EPI >= 0: the set of fused epilogue features is a compile-time constant (bit 0 row mean/M2, bit 1 row max/sum-exp, bit 2 column
+    // max/sum-exp, bit 3 residual) so that unused features cost no instructions; EPI < 0: decided at run time from the arguments.
+    constexpr bool RT = (EPI < 0);
+    const bool f_stats = RT ? (g.stats_out != nullptr) : ((EPI & 1) != 0);
+    const bool f_sm = RT ? (g.smstats_out != nullptr) : ((EPI & 2) != 0);
+    const bool f_col = RT ? (g.colstats_out != nullptr) : ((EPI & 4) != 0);
+    const bool f_res = RT ? (g.Res != nullptr) : ((EPI & 8) != 0);
     if (fast) {
       // Fast path (rows contiguous along j, 16-byte friendly).  Phase 1, thread = row: the residual row was prefetched by
       // TMA into this thread's staged row (own mbarrier); accumulator + bias + residual are combined in place and the row
@@ -444,7 +459,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
       bool pending = false;
       auto prefetch = [&](long long tile) {
         pending = false;
-        if (!g.Res || tile >= n_tiles) return;
+        if (!f_res || tile >= n_tiles) return;
         int p, mt, nt; decode(tile, p, mt, nt);
         const int i = mt * TM + r_own;
         const int nc = (i < g.M) ? min(TN, g.N - nt * TN) : 0;
@@ -466,103 +481,110 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
         TC_PROF(7, tp);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN;
         const int ncv = min(TN, g.N - nt * TN);      // valid columns of this tile (multiple of 4 on this path)
-        float c0 = 0.f, s1 = 0.f, s2 = 0.f, vmax = -INFINITY;
-        const bool has_res = pending;
+        const bool has_res = f_res && pending;
         if (has_res) { mbar_wait(my_bar, par); par ^= 1; }
         TC_PROF(8, tp);
+        // The body is instantiated twice: FULL tiles (all TM rows and TN columns valid: no guards in the inner loops) and edge tiles.
+        auto tile_body = [&](auto full_c) {
+          constexpr bool FULL = decltype(full_c)::value;
+          float c0 = 0.f, s1 = 0.f, s2 = 0.f, vmax = -INFINITY;
 #pragma unroll
-        for (int cc = 0; cc < TN / 32; ++cc) {
-          float v[32];
-          tc_ld32(taddr + cc * 32, v);
-          float4* dst = reinterpret_cast<float4*>(my_row + cc * 128);
+          for (int cc = 0; cc < TN / 32; ++cc) {
+            float v[32];
+            tc_ld32(taddr + cc * 32, v);
+            float4* dst = reinterpret_cast<float4*>(my_row + cc * 128);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 o = make_float4(v[4 * q] + bias_own, v[4 * q + 1] + bias_own, v[4 * q + 2] + bias_own, v[4 * q + 3] + bias_own);
-            if (has_res) { const float4 r4 = dst[q]; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
-            dst[q] = o;
-            if (cc * 32 + q * 4 < ncv) {
-              if (g.stats_out) {            // shifted sums: robust against |mean| >> std
-                if (cc == 0 && q == 0) c0 = o.x;
-                const float d0 = o.x - c0, d1 = o.y - c0, d2 = o.z - c0, d3 = o.w - c0;
-                s1 += (d0 + d1) + (d2 + d3);
-                s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+            for (int q = 0; q < 8; ++q) {
+              float4 o = make_float4(v[4 * q] + bias_own, v[4 * q + 1] + bias_own, v[4 * q + 2] + bias_own, v[4 * q + 3] + bias_own);
+              if (has_res) { const float4 r4 = dst[q]; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+              dst[q] = o;
+              if (FULL || cc * 32 + q * 4 < ncv) {
+                if (f_stats) {            // shifted sums: robust against |mean| >> std
+                  if (cc == 0 && q == 0) c0 = o.x;
+                  const float d0 = o.x - c0, d1 = o.y - c0, d2 = o.z - c0, d3 = o.w - c0;
+                  s1 += (d0 + d1) + (d2 + d3);
+                  s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+                }
+                if (f_sm) vmax = fmaxf(fmaxf(vmax, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
               }
-              if (g.smstats_out) vmax = fmaxf(fmaxf(vmax, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
             }
           }
-        }
-        tc_fence_before();
-        mbar_arrive(T_EMPTY(acc));
-        acc ^= 1; if (acc == 0) acc_phase ^= 1;
-        TC_PROF(9, tp);
-        if (i < g.M) {
-          const long long so = (((long long)p * g.M + i) * tiles_n + nt) * 2;
-          if (g.stats_out) {
-            const float inv = 1.0f / (float)ncv;
-            g.stats_out[so] = c0 + s1 * inv;
-            g.stats_out[so + 1] = fmaxf(s2 - s1 * s1 * inv, 0.f);
-          }
-          if (g.smstats_out) {             // second pass over the finished row (still in shared memory)
-            float se = 0.f;
+          tc_fence_before();
+          mbar_arrive(T_EMPTY(acc));
+          TC_PROF(9, tp);
+          if (FULL || i < g.M) {
+            const long long so = (((long long)p * g.M + i) * tiles_n + nt) * 2;
+            if (f_stats) {
+              const float inv = 1.0f / (float)ncv;
+              *reinterpret_cast<float2*>(g.stats_out + so) = make_float2(c0 + s1 * inv, fmaxf(s2 - s1 * s1 * inv, 0.f));
+            }
+            if (f_sm) {             // second pass over the finished row (still in shared memory); exp(x - max) = 2^(x*log2e - max*log2e)
+              const float mb = vmax * 1.4426950408889634f;
+              float se0 = 0.f, se1 = 0.f;
 #pragma unroll 4
-            for (int q = 0; q < TN / 4; ++q)
-              if (q * 4 < ncv) {
-                const float4 o = reinterpret_cast<const float4*>(my_row)[q];
-                se += (__expf(o.x - vmax) + __expf(o.y - vmax)) + (__expf(o.z - vmax) + __expf(o.w - vmax));
-              }
-            g.smstats_out[so] = vmax;
-            g.smstats_out[so + 1] = se;
+              for (int q = 0; q < TN / 4; ++q)
+                if (FULL || q * 4 < ncv) {
+                  const float4 o = reinterpret_cast<const float4*>(my_row)[q];
+                  se0 += exp2f_fast(fmaf(o.x, 1.4426950408889634f, -mb)) + exp2f_fast(fmaf(o.y, 1.4426950408889634f, -mb));
+                  se1 += exp2f_fast(fmaf(o.z, 1.4426950408889634f, -mb)) + exp2f_fast(fmaf(o.w, 1.4426950408889634f, -mb));
+                }
+              *reinterpret_cast<float2*>(g.smstats_out + so) = make_float2(vmax, se0 + se1);
+            }
           }
-        }
-        TC_PROF(10, tp);
-        __syncwarp();
-        {
-          constexpr int LPR = TN / 4;                 // lanes per row (16): a warp instruction stores 32/LPR rows
-          const int sub = lane / LPR, col = 4 * (lane % LPR);
-          float* Cp = g.C + (long long)p * g.c_batch + nt * TN + col;
-          const int ibase = mt * TM + quarter * 32;
-          float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          if (col < ncv) {
+          TC_PROF(10, tp);
+          __syncwarp();
+          {
+            constexpr int LPR = TN / 4;                 // lanes per row (16): a warp instruction stores 32/LPR rows
+            const int sub = lane / LPR, col = 4 * (lane % LPR);
+            float* Cp = g.C + (long long)p * g.c_batch + nt * TN + col;
+            const int ibase = mt * TM + quarter * 32;
+            float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (FULL || col < ncv) {
 #pragma unroll 8
-            for (int r = sub; r < 32; r += 32 / LPR) {
-              if (ibase + r < g.M) {
-                const float4 o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 4 * col);
-                __stcs(reinterpret_cast<float4*>(Cp + (long long)(ibase + r) * g.c_i), o);
-                if (g.colstats_out) { cm[0] = fmaxf(cm[0], o.x); cm[1] = fmaxf(cm[1], o.y); cm[2] = fmaxf(cm[2], o.z); cm[3] = fmaxf(cm[3], o.w); }
-              }
-            }
-          }
-          if (g.colstats_out) {
-            // softmax over the row (cluster) axis: per-column (max, sum exp) of this warp's 32-row slab; the two 16-lane
-            // halves hold alternate rows of the same 4 columns and are merged with one shuffle
-            float cs[4] = {0.f, 0.f, 0.f, 0.f};
-            if (col < ncv) {
-#pragma unroll 4
               for (int r = sub; r < 32; r += 32 / LPR) {
-                if (ibase + r < g.M) {
+                if (FULL || ibase + r < g.M) {
                   const float4 o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 4 * col);
-                  cs[0] += __expf(o.x - cm[0]); cs[1] += __expf(o.y - cm[1]); cs[2] += __expf(o.z - cm[2]); cs[3] += __expf(o.w - cm[3]);
+                  __stcs(reinterpret_cast<float4*>(Cp + (long long)(ibase + r) * g.c_i), o);
+                  if (f_col) { cm[0] = fmaxf(cm[0], o.x); cm[1] = fmaxf(cm[1], o.y); cm[2] = fmaxf(cm[2], o.z); cm[3] = fmaxf(cm[3], o.w); }
                 }
               }
             }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float om = __shfl_xor_sync(0xffffffffu, cm[e], LPR), os = __shfl_xor_sync(0xffffffffu, cs[e], LPR);
-              const float m = fmaxf(cm[e], om);
-              const float sa = (cm[e] == -INFINITY) ? 0.f : cs[e] * __expf(cm[e] - m);
-              const float sb = (om == -INFINITY) ? 0.f : os * __expf(om - m);
-              cm[e] = m; cs[e] = sa + sb;
-            }
-            if (sub == 0 && col < ncv) {
-              const int np = tiles_m * 4, slab = mt * 4 + quarter;
+            if (f_col) {
+              // softmax over the row (cluster) axis: per-column (max, sum exp) of this warp's 32-row slab; the two 16-lane
+              // halves hold alternate rows of the same 4 columns and are merged with one shuffle
+              float cs[4] = {0.f, 0.f, 0.f, 0.f};
+              if (FULL || col < ncv) {
+                const float mb0 = cm[0] * 1.4426950408889634f, mb1 = cm[1] * 1.4426950408889634f, mb2 = cm[2] * 1.4426950408889634f,
+                            mb3 = cm[3] * 1.4426950408889634f;
+#pragma unroll 4
+                for (int r = sub; r < 32; r += 32 / LPR) {
+                  if (FULL || ibase + r < g.M) {
+                    const float4 o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 4 * col);
+                    cs[0] += exp2f_fast(fmaf(o.x, 1.4426950408889634f, -mb0)); cs[1] += exp2f_fast(fmaf(o.y, 1.4426950408889634f, -mb1));
+                    cs[2] += exp2f_fast(fmaf(o.z, 1.4426950408889634f, -mb2)); cs[3] += exp2f_fast(fmaf(o.w, 1.4426950408889634f, -mb3));
+                  }
+                }
+              }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float* o = g.colstats_out + ((((long long)p * g.N + nt * TN + col + e) * np) + slab) * 2;
-                o[0] = cm[e]; o[1] = cs[e];
+                const float om = __shfl_xor_sync(0xffffffffu, cm[e], LPR), os = __shfl_xor_sync(0xffffffffu, cs[e], LPR);
+                const float m = fmaxf(cm[e], om);
+                const float sa = (cm[e] == -INFINITY) ? 0.f : cs[e] * __expf(cm[e] - m);
+                const float sb = (om == -INFINITY) ? 0.f : os * __expf(om - m);
+                cm[e] = m; cs[e] = sa + sb;
+              }
+              if (sub == 0 && (FULL || col < ncv)) {
+                const int np = tiles_m * 4, slab = mt * 4 + quarter;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  *reinterpret_cast<float2*>(g.colstats_out + ((((long long)p * g.N + nt * TN + col + e) * np) + slab) * 2) = make_float2(cm[e], cs[e]);
               }
             }
           }
-        }
+        };
+        if (ncv == TN && (mt + 1) * TM <= g.M) tile_body(std::true_type{});
+        else tile_body(std::false_type{});
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
         __syncwarp();
         fence_proxy_async();                 // generic reads of the staged rows are ordered before the next TMA write
         prefetch(tile + gridDim.x);
@@ -675,19 +697,38 @@ int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
   a.debug = dbg;
   LMPCR_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && batch > 0, LMPCR_ERR_ARG, "tcgemm: bad sizes");
   LMPCR_REQUIRE(!a.b_blob || (a.a_blob && !a.b_kmajor), LMPCR_ERR_ARG, "tcgemm: b_blob needs a_blob and the j-major layout");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(tcgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    cudaError_t e2 = cudaFuncSetAttribute(tcgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    LMPCR_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, LMPCR_ERR_LAUNCH, "tcgemm: cannot reserve %zu bytes of shared memory", SMEM_BYTES);
-    attr_set = true;
-  }
   const long long tiles = (long long)batch * ((a.M + TM - 1) / TM) * ((a.N + TN - 1) / TN);
   LMPCR_REQUIRE(tiles < (1ll << 24), LMPCR_ERR_ARG, "tcgemm: too many tiles in one launch");
   const long long slots = 2ll * sm_count();          // two resident CTAs per SM
   const int grid = (int)(tiles < slots ? tiles : slots);
-  if (a.b_kmajor) tcgemm_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, batch);
-  else tcgemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(a, batch);
+  // epilogue specialisations built for the feature sets the network uses; anything else takes the run-time-flag instance
+  const int epi = (a.stats_out ? 1 : 0) | (a.smstats_out ? 2 : 0) | (a.colstats_out ? 4 : 0) | (a.Res ? 8 : 0);
+  typedef void (*kern_t)(TcGemmArgs, int);
+  kern_t k = nullptr;
+  if (a.b_kmajor) {
+    k = (epi == 1) ? tcgemm_kernel<true, 1> : tcgemm_kernel<true, -1>;
+  } else {
+    switch (tc_fast_epilogue(a) ? epi : -1) {
+      case 0: k = tcgemm_kernel<false, 0>; break;
+      case 1: k = tcgemm_kernel<false, 1>; break;
+      case 2: k = tcgemm_kernel<false, 2>; break;
+      case 4: k = tcgemm_kernel<false, 4>; break;
+      case 8: k = tcgemm_kernel<false, 8>; break;
+      case 9: k = tcgemm_kernel<false, 9>; break;
+      default: k = tcgemm_kernel<false, -1>; break;
+    }
+  }
+  {
+    static kern_t done[16]; static int n_done = 0;       // opt in to the large dynamic shared memory once per instance
+    bool seen = false;
+    for (int i = 0; i < n_done; ++i) seen = seen || (done[i] == k);
+    if (!seen) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "tcgemm: cannot reserve %zu bytes of shared memory", SMEM_BYTES);
+      if (n_done < 16) done[n_done++] = k;
+    }
+  }
+  k<<<grid, NTHREADS, SMEM_BYTES, st>>>(a, batch);
   return check_launch("tcgemm_kernel");
 }
 
