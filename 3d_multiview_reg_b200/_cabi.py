@@ -43,10 +43,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("LMPCR_B200_LIB", LIB_PATH)      # override: an experimental build of the same ABI
+    if not os.path.exists(path):
         raise LmpcrError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                         "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+                         "(there is no CPU / PyTorch fallback for this path)" % path)
+    lib = ctypes.CDLL(path)
     lib.lmpcr_abi_version.restype = _i
     lib.lmpcr_last_error.restype = ctypes.c_char_p
     lib.lmpcr_device_info.argtypes = [ctypes.POINTER(_i)] * 4
