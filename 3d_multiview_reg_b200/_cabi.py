@@ -19,7 +19,7 @@ GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
 EXPORTS = [
-    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
     "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
     "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
 ]
@@ -55,6 +55,10 @@ def load():
     lib.lmpcr_nn_workspace_bytes.argtypes = [_i] * 7
     lib.lmpcr_nn_argmin.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]
     lib.lmpcr_nn_top2.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]
+    lib.lmpcr_overlap_workspace_bytes.restype = _sz
+    lib.lmpcr_overlap_workspace_bytes.argtypes = [_i]
+    lib.lmpcr_overlap_count.argtypes = [_vp, _i, _vp, _i, _vp, ctypes.c_double, _vp, _vp, _vp, _sz, _vp]
+    lib.lmpcr_voxel_downsample.argtypes = [_vp, _i, ctypes.c_double, _vp, _vp, _vp, _vp, _sz, _vp]
     lib.lmpcr_nn_soft.argtypes = [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _sz, _vp]
     lib.lmpcr_launch_count.restype = ctypes.c_longlong
     lib.lmpcr_nn_tensor_debug.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
@@ -143,6 +147,39 @@ def nn_top2(q_feat, b_feat, jobs):
         _check(lib.lmpcr_nn_top2(_p(q), q.shape[0], n, _p(b), b.shape[0], b.shape[1], q.shape[2], _p(jobs), J, _p(idx), _p(dist), _p(ws),
                                  ws.numel(), _stream(q)))
     return idx, dist
+
+
+def overlap_count(query, target, T, radius):
+    """Number of `query` points [n,3] (fp64, CUDA) with a point of `target` [m,3], moved by the 4x4 pose T (or None), closer than
+    `radius` (lib/utils.py:743-751).  Returns a python int (one device->host read)."""
+    lib = load()
+    q = _dev(query, torch.float64, "query")
+    b = _dev(target, torch.float64, "target")
+    Tm = _dev(T, torch.float64, "T") if T is not None else None
+    with torch.cuda.device(q.device):
+        out = torch.zeros(2, dtype=torch.int32, device=q.device)
+        ws = _ws(lib.lmpcr_overlap_workspace_bytes(b.shape[0]), q.device)
+        _check(lib.lmpcr_overlap_count(_p(q), q.shape[0], _p(b), b.shape[0], _p(Tm), float(radius), _p(out), _p(out[1:]), _p(ws), ws.numel(),
+                                       _stream(q)))
+        cnt, flag = out.tolist()
+    if flag:
+        raise LmpcrError("lmpcr_overlap_count: coordinates outside the hash grid (|x| >= 2^20 * radius)")
+    return cnt
+
+
+def voxel_downsample(points, voxel_size):
+    """Open3D-style voxel_down_sample of fp64 points [n,3] (CUDA) -> [n_voxels,3] (lib/utils.py:754-762)."""
+    lib = load()
+    x = _dev(points, torch.float64, "points")
+    with torch.cuda.device(x.device):
+        out = torch.empty((max(x.shape[0], 1), 3), dtype=torch.float64, device=x.device)
+        cnt = torch.zeros(2, dtype=torch.int32, device=x.device)
+        ws = _ws(lib.lmpcr_overlap_workspace_bytes(x.shape[0]), x.device)
+        _check(lib.lmpcr_voxel_downsample(_p(x), x.shape[0], float(voxel_size), _p(out), _p(cnt), _p(cnt[1:]), _p(ws), ws.numel(), _stream(x)))
+        n, flag = cnt.tolist()
+    if flag:
+        raise LmpcrError("lmpcr_voxel_downsample: extent exceeds 2^20 voxels per axis")
+    return out[:n]
 
 
 def nn_soft(q_feat, b_feat, b_xyz, jobs, temperature):

@@ -115,6 +115,20 @@ int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, in
   return launch_pairwise_distance(src, n, dst, m, dim, batch, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t lmpcr_overlap_workspace_bytes(int n_points) { return overlap_workspace_bytes(n_points); }
+
+int lmpcr_overlap_count(const double* query, int n_query, const double* target, int n_target, const double* T, double radius, int32_t* count_out,
+                        int32_t* range_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_overlap_count(query, n_query, target, n_target, T, radius, count_out, range_flag, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int lmpcr_voxel_downsample(const double* points, int n_points, double voxel_size, double* out, int32_t* n_out, int32_t* range_flag,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_voxel_downsample(points, n_points, voxel_size, out, n_out, range_flag, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int lmpcr_nn_top2(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim, const int32_t* jobs,
                   int n_jobs, int32_t* idx_out, float* dist_out, void* workspace, size_t workspace_bytes, void* stream) {
   LMPCR_TRY(check_device());

@@ -74,6 +74,12 @@ int launch_mutual_xs(const float* xyz, int n_pts, const int32_t* pairs, int n_pa
                      const int32_t* idx_ts, int mode, float thresh, uint8_t* mutual, float* xs, int xs_channels,
                      cudaStream_t st);
 int launch_knn3d(const float* pos1, int n, const float* pos2, int m, int batch, int32_t* idx, float* sq, cudaStream_t st);
+// overlap.cu
+size_t overlap_workspace_bytes(int n);
+int launch_overlap_count(const double* q, int n_q, const double* b, int n_b, const double* T, double radius, int32_t* count_out, int32_t* flag_out,
+                         void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_voxel_downsample(const double* pts, int n, double voxel, double* out, int32_t* n_out, int32_t* flag_out, void* ws, size_t ws_bytes,
+                            cudaStream_t st);
 // nn_tensor.cu (tcgen05 path)
 size_t nn_tensor_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, int dim, int n_jobs);
 int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,

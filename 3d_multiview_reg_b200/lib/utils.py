@@ -83,3 +83,26 @@ def kabsch_transformation_estimation(x1, x2, weights=None, normalize_w=True, eps
 def transformation_residuals(x1, x2, R, t):
     """lib/utils.py:240-256."""
     return _cabi.residuals(x1, x2, R, t)
+
+
+def compute_overlap_ratio(pc_i, pc_j, trans, method="3DMatch", voxel_size=0.025):
+    """lib/utils.py:713-786: max over both directions of the fraction of points that have a point of the other cloud,
+    moved by the estimated pose, within 5 cm ('3DMatch') or within 3 voxels after voxel down-sampling ('FCGF').
+    pc_i, pc_j: [N,3] / [M,3] numpy arrays or tensors (any device; computed on the GPU in fp64 like the reference's numpy
+    arrays), trans: [4,4].  The reference's KD-tree queries become a hash-grid kernel (lmpcr_overlap_count); the Open3D
+    voxel_down_sample of the 'FCGF' method becomes lmpcr_voxel_downsample."""
+    import numpy as np
+    dev = torch.device("cuda", torch.cuda.current_device())
+    as_dev = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(device=dev, dtype=torch.float64)
+    pi, pj, T = as_dev(pc_i).reshape(-1, 3), as_dev(pc_j).reshape(-1, 3), as_dev(trans).reshape(4, 4)
+    T_inv = torch.linalg.inv(T)                      # 4x4 on the device: plumbing, like np.linalg.inv in the reference (:740)
+    if method == "3DMatch":
+        radius = 0.05
+    elif method == "FCGF":
+        pi, pj = _cabi.voxel_downsample(pi, voxel_size), _cabi.voxel_downsample(pj, voxel_size)
+        radius = 3 * voxel_size
+    else:
+        raise ValueError("Wrong overlap computation method was selected.")     # the reference logs an error and then fails (:781)
+    matching01 = _cabi.overlap_count(pi, pj, T, radius)          # pc_i against trans * pc_j          (:746-748)
+    matching10 = _cabi.overlap_count(pj, pi, T_inv, radius)      # pc_j against trans^-1 * pc_i       (:750-752)
+    return max(matching01 / pi.shape[0], matching10 / pj.shape[0])

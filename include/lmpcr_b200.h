@@ -132,6 +132,27 @@ int lmpcr_knn3d_1(const float* pos1, int n, const float* pos2, int m, int batch,
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Overlap ratio under an estimated pose (the check after stage 3 in scripts/benchmark_pairwise_registration.py:219).
+ * Replaces the sklearn KD-tree queries of lib/utils.py:713-786 `compute_overlap_ratio`.
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* Bytes of workspace for lmpcr_overlap_count (n = n_target) / lmpcr_voxel_downsample (n = n_points). */
+size_t lmpcr_overlap_workspace_bytes(int n_points);
+
+/* count_out[0] = number of query points (fp64 [n_query,3]) that have a target point (fp64 [n_target,3], moved by the 4x4
+ * row-major pose T, NULL = identity) closer than `radius`:  lib/utils.py:743-751 (`neigh.fit(pc_j_t)`,
+ * `kneighbors(pc_i)`, `dist < 0.05`).  Uniform hash grid with cell size = radius, fp64 throughout like the reference's numpy
+ * arrays.  range_flag[0] (optional) is set when a coordinate leaves the grid's +-2^20 cells; the count is then invalid. */
+int lmpcr_overlap_count(const double* query, int n_query, const double* target, int n_target, const double* T, double radius, int32_t* count_out,
+                        int32_t* range_flag, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Voxel down-sampling as used by the 'FCGF' overlap method (lib/utils.py:754-762 -> Open3D `voxel_down_sample`): grid anchored
+ * at min_bound - voxel/2, one output point per occupied voxel = mean of its points.  out has room for n_points rows (fp64),
+ * n_out[0] receives the number of voxels; rows are ordered by voxel key (Open3D's order is unspecified). */
+int lmpcr_voxel_downsample(const double* points, int n_points, double voxel_size, double* out, int32_t* n_out, int32_t* range_flag,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * Stage 3 -- weighted Kabsch + residuals + confidence.
  * Replaces lib/utils.py:164-237 `kabsch_transformation_estimation` (normalize_w=True, best_k=0,
  * w_threshold=0) and lib/utils.py:240-256 `transformation_residuals`.

@@ -393,10 +393,57 @@ def oanet_forward(xs, state_dict, net_depth=12, iter_num=1, prefix="", dtype=np.
 
 
 # --------------------------------------------------------------------------------------------------
+# Overlap ratio under an estimated pose  (lib/utils.py:713-786)
+# --------------------------------------------------------------------------------------------------
+
+
+def voxel_down_sample(pts, voxel):
+    """Restates Open3D 0.9 `PointCloud::VoxelDownSample` (called at lib/utils.py:760-761; Open3D itself is absent here, so
+    this part is UNPINNED): voxel index = floor((p - (min_bound - voxel/2)) / voxel), output = mean of the points of each
+    occupied voxel.  Rows are returned sorted by (ix, iy, iz); Open3D's order is an unordered_map's."""
+    pts = np.asarray(pts, np.float64)
+    origin = pts.min(axis=0) - 0.5 * voxel
+    ijk = np.floor((pts - origin) / voxel).astype(np.int64)
+    order = np.lexsort((ijk[:, 2], ijk[:, 1], ijk[:, 0]))
+    ijk, p = ijk[order], pts[order]
+    head = np.ones(len(p), bool)
+    head[1:] = np.any(ijk[1:] != ijk[:-1], axis=1)
+    starts = np.flatnonzero(head)
+    sums = np.add.reduceat(p, starts, axis=0)
+    counts = np.diff(np.append(starts, len(p)))[:, None]
+    return sums / counts
+
+
+def _count_within(query, target, radius):
+    """Number of query points whose nearest target point is closer than radius (brute force in fp64, blocked)."""
+    n = 0
+    for s in range(0, len(query), 2048):
+        d2 = ((query[s:s + 2048, None, :] - target[None, :, :]) ** 2).sum(-1)
+        n += int((np.sqrt(d2.min(axis=1)) < radius).sum())
+    return n
+
+
+def compute_overlap_ratio(pc_i, pc_j, trans, method="3DMatch", voxel_size=0.025):
+    """lib/utils.py:713-786 with the KD-tree replaced by brute force (same Euclidean metric, same strict `<`)."""
+    pc_i, pc_j, trans = np.asarray(pc_i, np.float64), np.asarray(pc_j, np.float64), np.asarray(trans, np.float64)
+    trans_inv = np.linalg.inv(trans)
+    if method == "FCGF":
+        pc_i, pc_j = voxel_down_sample(pc_i, voxel_size), voxel_down_sample(pc_j, voxel_size)
+        radius = 3 * voxel_size
+    else:
+        radius = 0.05
+    pc_i_t = (trans_inv[0:3, 0:3] @ pc_i.T + trans_inv[0:3, 3].reshape(-1, 1)).T
+    pc_j_t = (trans[0:3, 0:3] @ pc_j.T + trans[0:3, 3].reshape(-1, 1)).T
+    m01 = _count_within(pc_i, pc_j_t, radius)
+    m10 = _count_within(pc_j, pc_i_t, radius)
+    return max(m01 / pc_i.shape[0], m10 / pc_j.shape[0]), m01, m10
+
+
+# --------------------------------------------------------------------------------------------------
 # Synthetic inputs: shared, neutral generators (synthdata.py at the repo root) re-exported for the tests
 # --------------------------------------------------------------------------------------------------
 import os as _os
 import sys as _sys
 
 _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
-from synthdata import oanet_param_schema, random_rotation, synth_scene, synth_state_dict, synth_xs  # noqa: E402,F401
+from synthdata import oanet_param_schema, random_rotation, synth_cloud_pair, synth_scene, synth_state_dict, synth_xs  # noqa: E402,F401

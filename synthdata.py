@@ -64,6 +64,24 @@ def synth_xs(n_pairs, n_pts, inlier_frac=0.3, seed=41, noise=0.01):
     return xs, Rs, ts
 
 
+def synth_cloud_pair(seed, n_i, n_j, overlap):
+    """Two partially overlapping clouds in their own frames + a slightly wrong 4x4 estimate of the pose that maps cloud j
+    into the frame of cloud i (inputs of the overlap-ratio check, lib/utils.py:713).  fp64."""
+    rng = np.random.default_rng(seed)
+    n_ov = int(overlap * min(n_i, n_j))
+    shared = rng.uniform(0, 2, (n_ov, 3))
+    wi = np.concatenate([shared + 0.004 * rng.standard_normal((n_ov, 3)), rng.uniform(0, 2, (n_i - n_ov, 3)) + [2.2, 0, 0]])
+    wj = np.concatenate([shared + 0.004 * rng.standard_normal((n_ov, 3)), rng.uniform(0, 2, (n_j - n_ov, 3)) - [2.2, 0, 0]])
+    R, t = random_rotation(rng), rng.standard_normal(3)
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = t                                                     # x_i = R x_j + t
+    pj = (wj - t) @ R                                                # j's own frame
+    Tn = T.copy()
+    Tn[:3, 3] += 0.01 * rng.standard_normal(3)
+    return wi[rng.permutation(n_i)], pj[rng.permutation(n_j)], Tn
+
+
 # --------------------------------------------------------------------------------------------------
 # Parameter schema of the filtering network (SURVEY.md Appendix A) + seeded synthetic weights
 # --------------------------------------------------------------------------------------------------
