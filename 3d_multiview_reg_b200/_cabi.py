@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "liblmpcr_b200.so")
 
 NN_EXACT_SIMT, NN_TENSOR = 0, 1
 MUTUAL_INDEX, MUTUAL_GEOMETRIC = 0, 1
+BN_EVAL, BN_BATCH = 0, 1
 GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
@@ -31,7 +32,7 @@ class LmpcrError(RuntimeError):
 
 class FilterCfg(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
-                ("net_channel", "clusters", "net_depth", "iter_num", "side_channel", "guard_mode", "gemm_algo", "reserved")]
+                ("net_channel", "clusters", "net_depth", "iter_num", "side_channel", "guard_mode", "gemm_algo", "bn_mode")]
 
 
 _lib = None

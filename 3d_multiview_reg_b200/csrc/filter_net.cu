@@ -185,12 +185,13 @@ int gemm(const GemmArgs& g, int batch, cudaStream_t st) {
 __global__ void in_affine_kernel(const float* __restrict__ x, long long x_batch, int C, int L, int use_in, float eps_in,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ rmean, const float* __restrict__ rvar,
-                                 float* __restrict__ scale, float* __restrict__ shift, int n_rows) {
+                                 float* __restrict__ scale, float* __restrict__ shift, int n_rows, int bn_train) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
   const int p = row / C, c = row - p * C;
-  const float gsc = __ldg(gamma + c) / sqrtf(__ldg(rvar + c) + 1e-5f);
+  // bn_train: emit the InstanceNorm-only affine (scale = rstd, shift = -mean*rstd); bn_train_finalize_kernel folds the batch statistics in
+  const float gsc = bn_train ? 1.f : __ldg(gamma + c) / sqrtf(__ldg(rvar + c) + 1e-5f);
   float mean = 0.f, rstd = 1.f;
   if (use_in) {
     const float* r = x + (long long)p * x_batch + (long long)c * L;
@@ -206,8 +207,59 @@ __global__ void in_affine_kernel(const float* __restrict__ x, long long x_batch,
   }
   if (lane == 0) {
     scale[row] = rstd * gsc;
-    shift[row] = (-mean * rstd - __ldg(rmean + c)) * gsc + __ldg(beta + c);
+    shift[row] = bn_train ? -mean * rstd : (-mean * rstd - __ldg(rmean + c)) * gsc + __ldg(beta + c);
   }
+}
+
+// Training-mode BatchNorm behind an InstanceNorm (oanet.py:27-28 etc. with self.training).  The InstanceNorm output
+// of (pair p, channel c) has mean 0 and biased variance var/(var+eps) = 1 - eps*rstd^2, so the batch statistics over (pairs,
+// points) are mu_B = 0 and sigma2_B = mean_p(1 - eps*rstd_pc^2): no pass over the activations is needed.  One warp per channel:
+// folds gamma/sqrt(sigma2_B+1e-5), beta into the per-pair InstanceNorm affine and updates the running statistics in place
+// (momentum 0.1, unbiased variance; F.batch_norm semantics).
+__global__ void bn_train_finalize_kernel(float* __restrict__ scale, float* __restrict__ shift, int stride, int off, int ch, int g, float eps_in,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ rmean,
+                                         float* __restrict__ rvar, int L, float momentum) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= ch) return;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int p = lane; p < g; p += 32) {
+    const float r = scale[(size_t)p * stride + off + c];
+    acc += 1.f - eps_in * r * r;
+  }
+  const float var_b = warp_sum(acc) / (float)g;
+  const float inv = __ldg(gamma + c) / sqrtf(var_b + 1e-5f), b = __ldg(beta + c);
+  for (int p = lane; p < g; p += 32) {
+    const size_t o = (size_t)p * stride + off + c;
+    scale[o] = scale[o] * inv;
+    shift[o] = shift[o] * inv + b;
+  }
+  if (lane == 0) {
+    const float n = (float)g * (float)L;
+    rmean[c] = (1.f - momentum) * rmean[c];                                  // + momentum * mu_B, mu_B = 0
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * var_b * (n / fmaxf(n - 1.f, 1.f));
+  }
+}
+
+// Training-mode BatchNorm over the cluster axis of Y [g, C, K] (OAFilter.conv2, oanet.py:73, after trans(1,2)): channel = k, batch
+// statistics over (pairs, C).  One thread per k (coalesced along k), fp64 accumulators; per-channel scale/shift (p_batch = 0).
+__global__ void bn_train_cols_kernel(const float* __restrict__ y, long long y_batch, int C, int K, int g, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                                     float* __restrict__ scale, float* __restrict__ shift, float momentum) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double s = 0.0, s2 = 0.0;
+  for (int p = 0; p < g; ++p)
+    for (int c = 0; c < C; ++c) {
+      const double v = (double)__ldg(y + (long long)p * y_batch + (long long)c * K + k);
+      s += v; s2 += v * v;
+    }
+  const double n = (double)g * (double)C, mean = s / n, var = fmax(s2 / n - mean * mean, 0.0);
+  const float sc = __ldg(gamma + k) / sqrtf((float)var + 1e-5f);
+  scale[k] = sc;
+  shift[k] = __ldg(beta + k) - (float)mean * sc;
+  rmean[k] = (1.f - momentum) * rmean[k] + momentum * (float)mean;
+  rvar[k] = (1.f - momentum) * rvar[k] + momentum * (float)(var * (n / fmax(n - 1.0, 1.0)));
 }
 
 // xs [P,1,N,Cx] (+ residuals, scores of the previous block) -> in0 [P, Cin, N]   (oanet.py:233, 245-248)
@@ -321,7 +373,7 @@ __global__ void softmax_colstats_kernel(const float* __restrict__ e, int K, int 
 __global__ void affine_from_partials_kernel(const float* __restrict__ part, int ch, int tiles, int L, int n_rows, float eps_in,
                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                             const float* __restrict__ rmean, const float* __restrict__ rvar,
-                                            float* __restrict__ scale, float* __restrict__ shift, int out_stride, int out_off) {
+                                            float* __restrict__ scale, float* __restrict__ shift, int out_stride, int out_off, int bn_train) {
   // one warp per (pair, channel): lanes take tiles lane, lane+32, ... in order, then a fixed shuffle tree merges them
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -351,9 +403,9 @@ __global__ void affine_from_partials_kernel(const float* __restrict__ part, int 
   }
   if (lane == 0) {
     const float rstd = 1.0f / sqrtf(M2 / (float)L + eps_in);
-    const float gsc = __ldg(gamma + c) / sqrtf(__ldg(rvar + c) + 1e-5f);
+    const float gsc = bn_train ? 1.f : __ldg(gamma + c) / sqrtf(__ldg(rvar + c) + 1e-5f);
     scale[(size_t)p * out_stride + out_off + c] = rstd * gsc;
-    shift[(size_t)p * out_stride + out_off + c] = (-mean * rstd - __ldg(rmean + c)) * gsc + __ldg(beta + c);
+    shift[(size_t)p * out_stride + out_off + c] = bn_train ? -mean * rstd : (-mean * rstd - __ldg(rmean + c)) * gsc + __ldg(beta + c);
   }
 }
 
@@ -538,6 +590,7 @@ static int validate_cfg(const lmpcr_filter_cfg* cfg) {
   LMPCR_REQUIRE(cfg->clusters >= 4 && cfg->clusters % 4 == 0 && cfg->clusters <= 1024, LMPCR_ERR_ARG, "lmpcr_filter: clusters=%d (multiple of 4, <= 1024)", cfg->clusters);
   LMPCR_REQUIRE(cfg->side_channel == 0 || cfg->side_channel == 1, LMPCR_ERR_ARG, "lmpcr_filter: side_channel");
   LMPCR_REQUIRE(cfg->guard_mode == LMPCR_GUARD_BATCH || cfg->guard_mode == LMPCR_GUARD_PAIR, LMPCR_ERR_ARG, "lmpcr_filter: guard_mode");
+  LMPCR_REQUIRE(cfg->bn_mode == LMPCR_BN_EVAL || cfg->bn_mode == LMPCR_BN_BATCH, LMPCR_ERR_ARG, "lmpcr_filter: bn_mode");
   return LMPCR_OK;
 }
 
@@ -553,7 +606,7 @@ size_t filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int P, int N) {
   const size_t pp = per_pair_floats(cfg->net_channel, cfg->clusters, N) * 4;
   size_t G = (size_t(12) << 30) / pp;  // up to ~12 GiB of activations per group of pairs (fewer, larger launches)
   if (G < 1) G = 1;
-  if (G > (size_t)P) G = P;
+  if (G > (size_t)P || cfg->bn_mode == LMPCR_BN_BATCH) G = P;      // batch-statistics BatchNorm: every pair of the call in one group
   return fixed_bytes(cfg, P, N) + align_up(G * pp, 256) + 4096;
 }
 
@@ -566,6 +619,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   LMPCR_REQUIRE(P >= 0 && N >= 1, LMPCR_ERR_ARG, "lmpcr_filter_forward: bad sizes");
   LMPCR_REQUIRE(cfg->gemm_algo == 0 || cfg->gemm_algo == 1, LMPCR_ERR_UNSUPPORTED, "lmpcr_filter_forward: gemm_algo=%d unknown", cfg->gemm_algo);
   const bool tc = cfg->gemm_algo == 1;
+  const bool bn_train = cfg->bn_mode == LMPCR_BN_BATCH;
   LMPCR_REQUIRE(n_params == filter_num_params(cfg), LMPCR_ERR_ARG, "lmpcr_filter_forward: expected %d parameter tensors, got %d", filter_num_params(cfg), n_params);
   for (int i = 0; i < n_params; ++i) LMPCR_REQUIRE(params[i], LMPCR_ERR_ARG, "lmpcr_filter_forward: params[%d] is null", i);
   if (P == 0) return LMPCR_OK;
@@ -578,7 +632,10 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   LMPCR_REQUIRE(((uintptr_t)ws & 255) == 0, LMPCR_ERR_ARG, "lmpcr_filter_forward: workspace must be 256-byte aligned");
   int G = (int)((ws_bytes - fixed - 4096) / pp);
   if (G > P) G = P;
-  {  // groups whose tile counts are whole waves: the pooling GEMM has 4 tiles per pair, so G % (SMs/4) == 0
+  // training-mode BatchNorm couples all pairs of the call: they must form ONE group
+  LMPCR_REQUIRE(!bn_train || G >= P, LMPCR_ERR_WORKSPACE,
+                "lmpcr_filter_forward: batch-statistics BatchNorm needs all %d pairs in one group, the workspace holds %d", P, G);
+  if (!bn_train) {  // groups whose tile counts are whole waves: the pooling GEMM has 4 tiles per pair, so G % (SMs/4) == 0
     const int q = sm_count() / 4;
     if (q > 0 && G > q) G = G / q * q;
   }
@@ -621,16 +678,32 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   Cursor cur{params, 0, n_params};
   const long long CN = (long long)C * N, CK = (long long)C * K;
 
+  // Training-mode BatchNorm (cfg->bn_mode == LMPCR_BN_BATCH): the kernels above emit the InstanceNorm-only affine and
+  // bn_train_finalize_kernel folds in the statistics of the batch (= all pairs of the call) and updates the running buffers.
+  auto bn_finalize = [&](int ch, int L, int g, float eps, const BNP& bn, int bn_off, int out_stride, int out_off) -> int {
+    if (!bn_train) return LMPCR_OK;
+    bn_train_finalize_kernel<<<(ch + 7) / 8, 256, 0, st>>>(W.scale, W.shift, out_stride, out_off, ch, g, eps, bn.g + bn_off, bn.b + bn_off,
+                                                          const_cast<float*>(bn.rm) + bn_off, const_cast<float*>(bn.rv) + bn_off, L, 0.1f);
+    return check_launch("bn_train_finalize_kernel");
+  };
   auto affine = [&](const float* x, long long xb, int ch, int L, int g, bool use_in, float eps, const BNP& bn) -> int {
+    if (!use_in && bn_train) {        // BatchNorm over the cluster axis of x [g, C, ch]: batch statistics over (pairs, C)
+      bn_train_cols_kernel<<<(ch + 127) / 128, 128, 0, st>>>(x, xb, C, ch, g, bn.g, bn.b, const_cast<float*>(bn.rm), const_cast<float*>(bn.rv),
+                                                            W.scale, W.shift, 0.1f);
+      return check_launch("bn_train_cols_kernel");
+    }
     const int rows = use_in ? g * ch : ch;
-    in_affine_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, xb, ch, L, use_in ? 1 : 0, eps, bn.g, bn.b, bn.rm, bn.rv, W.scale, W.shift, rows);
-    return check_launch("in_affine_kernel");
+    in_affine_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, xb, ch, L, use_in ? 1 : 0, eps, bn.g, bn.b, bn.rm, bn.rv, W.scale, W.shift, rows,
+                                                    bn_train ? 1 : 0);
+    LMPCR_TRY(check_launch("in_affine_kernel"));
+    return use_in ? bn_finalize(ch, L, g, eps, bn, 0, ch, 0) : LMPCR_OK;
   };
   auto aff_part = [&](const float* part, int ch, int L, int g, float eps, const BNP& bn, int bn_off, int out_stride, int out_off) -> int {
     const int rows = g * ch, tiles = (L + TC_TILE_N - 1) / TC_TILE_N;
     affine_from_partials_kernel<<<(rows + 7) / 8, 256, 0, st>>>(part, ch, tiles, L, rows, eps, bn.g + bn_off, bn.b + bn_off, bn.rm + bn_off,
-                                                                    bn.rv + bn_off, W.scale, W.shift, out_stride, out_off);
-    return check_launch("affine_from_partials_kernel");
+                                                                    bn.rv + bn_off, W.scale, W.shift, out_stride, out_off, bn_train ? 1 : 0);
+    LMPCR_TRY(check_launch("affine_from_partials_kernel"));
+    return bn_finalize(ch, L, g, eps, bn, bn_off, out_stride, out_off);
   };
   // out[p, :, :] = conv(relu(bn(in(x))))  (+ residual), x [g, cin, L] with batch stride xb
   auto conv_norm = [&](const float* x, long long xb, int cin, int L, int g, float eps, const BNP& bn, const ConvP& cv, int cout,
@@ -790,7 +863,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       for (int i = 0; i < half; ++i) {
         const OAFilterP& q = blk.l2[i];
         LMPCR_TRY(conv_norm(xd_in, CK, C, K, g, 1e-3f, q.bn1, q.c1, C, W.Y, CK, nullptr, 0));     // conv1 -> Y [g,C,K]
-        LMPCR_TRY(affine(nullptr, 0, K, 0, g, false, 0.f, q.bn2));                                 // BN over the cluster axis
+        LMPCR_TRY(affine(W.Y, CK, K, 0, g, false, 0.f, q.bn2));                                    // BN over the cluster axis
         if (tc) {
           TcGemmArgs a{};   // Z[c,k'] = Y[c,k'] + b2[k'] + sum_k W2[k',k] relu(bn_k(Y[c,k]))   (trans(1,2) via strides)
           a.a_blob = q.c2.blob;

@@ -115,7 +115,7 @@ class OANet(nn.Module):
 
     def cabi_cfg(self):
         return _cabi.FilterCfg(self.net_channel, self.clusters, self.net_depth, self.iter_num, int(self.side_channel),
-                               self.guard_mode, self.gemm_algo, 0)
+                               self.guard_mode, self.gemm_algo, _cabi.BN_BATCH if self.training else _cabi.BN_EVAL)
 
     def param_table(self):
         sd = dict(self.named_parameters())
@@ -124,16 +124,17 @@ class OANet(nn.Module):
 
     def forward(self, data):
         assert data["xs"].dim() == 4 and data["xs"].shape[1] == 1
-        if self.training and not self._warned_train:
-            warnings.warn("OANet(B200) implements eval-mode BatchNorm (running statistics) only; the module is in "
-                          "train mode (scripts/benchmark_pairwise_registration.py never calls .eval()) -- running "
-                          "statistics are used and NOT updated.")
-            self._warned_train = True
+        # self.training (scripts/benchmark_pairwise_registration.py never calls .eval()): BatchNorm uses the statistics of this
+        # batch and the kernels update running_mean / running_var in place, like nn.BatchNorm2d; forward only -- no autograd graph
         if self.device.type != "cuda":
             raise _cabi.LmpcrError("OANet(B200) needs a CUDA device (cfg['misc']['use_gpu'] and an sm_100 GPU); no CPU fallback")
         xs = data["xs"].to(self.device, dtype=torch.float32)
         with torch.no_grad():
             out = _cabi.filter_forward(xs, self.param_table(), self.cabi_cfg())
+            if self.training:
+                for name, buf in self.named_buffers():
+                    if name.endswith("num_batches_tracked"):
+                        buf += 1
         n_it = self.iter_num + 1
         flag = bool((out["status"] & _cabi.STATUS_DEGENERATE).any().item())
         return {

@@ -175,7 +175,7 @@ int lmpcr_residuals(const float* x1, const float* x2, int ld, const float* R, co
                     float* res, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
- * Stage 2(+3) -- correspondence-weighting network, eval mode.
+ * Stage 2(+3) -- correspondence-weighting network (forward pass; eval- or training-mode BatchNorm).
  * Replaces lib/filtering/oanet.py:218-265 `OANet.forward` (OANBlock :165-185, PointCN :18-43, OAFilter
  * :56-93, diff_pool :96-110, diff_unpool :113-129) including the Kabsch call of every block.
  * ---------------------------------------------------------------------------------------------------- */
@@ -187,8 +187,13 @@ typedef struct lmpcr_filter_cfg {
   int32_t side_channel; /* cfg['data']['use_mutuals'] == 2 -> 1 (xs has 7 channels)            */
   int32_t guard_mode;   /* LMPCR_GUARD_BATCH | LMPCR_GUARD_PAIR                                */
   int32_t gemm_algo;    /* 0 = fp32 CUDA-core GEMMs, 1 = tcgen05 split-BF16 tensor-core GEMMs  */
-  int32_t reserved;
+  int32_t bn_mode;      /* LMPCR_BN_EVAL: running statistics (module.eval());  LMPCR_BN_BATCH: nn.BatchNorm2d in training mode --
+                           statistics of the batch (all pairs of the call, which must fit one workspace group) and in-place update
+                           of running_mean / running_var (momentum 0.1, unbiased variance) through the parameter pointers; the
+                           state scripts/benchmark_pairwise_registration.py runs the model in (it never calls .eval())      */
 } lmpcr_filter_cfg;
+#define LMPCR_BN_EVAL 0
+#define LMPCR_BN_BATCH 1
 
 /* One fused layer of the network (the building block lmpcr_filter_forward is made of; exported so that it can be timed
  * and tested alone):  out[p,co,n] = sum_ci W[co,ci] * relu(x[p,ci,n]*scale[p,ci] + shift[p,ci]) + bias[co] (+ residual[p,co,n])

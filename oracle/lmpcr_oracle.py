@@ -260,11 +260,12 @@ def chordal_angle(Ra, Rb):
 class _SD:
     """state_dict view with a key prefix; values as numpy arrays of the working dtype."""
 
-    def __init__(self, sd, prefix, dtype):
+    def __init__(self, sd, prefix, dtype, train=False, updates=None):
         self.sd, self.prefix, self.dtype = sd, prefix, dtype
+        self.train, self.updates = train, updates          # train: BatchNorm uses batch statistics and records its buffer updates
 
     def sub(self, name):
-        return _SD(self.sd, self.prefix + name + ".", self.dtype)
+        return _SD(self.sd, self.prefix + name + ".", self.dtype, self.train, self.updates)
 
     def __getitem__(self, name):
         v = self.sd[self.prefix + name]
@@ -284,8 +285,21 @@ def _inorm(x, eps):
     return (x - mean) / np.sqrt(var + x.dtype.type(eps))
 
 
-def _bn_eval(x, sd, eps=1e-5):
-    """nn.BatchNorm2d in eval mode (running statistics), channel axis = 1 (oanet.py:28,32,66,73,80,102,119)."""
+def _bn_eval(x, sd, eps=1e-5, momentum=0.1):
+    """nn.BatchNorm2d, channel axis = 1 (oanet.py:28,32,66,73,80,102,119).  Eval mode: running statistics.  Train mode
+    (sd.train; the state scripts/benchmark_pairwise_registration.py leaves the model in): statistics of the
+    batch -- biased variance over (pairs, points) for the normalisation, unbiased for the running_var update, momentum 0.1
+    (oanet.py:15), num_batches_tracked + 1; the updated buffers are recorded in sd.updates."""
+    if sd.train:
+        mean = x.mean(axis=(0, 2))
+        var = ((x - mean[None, :, None]) ** 2).mean(axis=(0, 2))
+        n = x.shape[0] * x.shape[2]
+        m = x.dtype.type(momentum)
+        sd.updates[sd.prefix + "running_mean"] = (1 - m) * sd["running_mean"] + m * mean
+        sd.updates[sd.prefix + "running_var"] = (1 - m) * sd["running_var"] + m * var * x.dtype.type(n / max(n - 1, 1))
+        sd.updates[sd.prefix + "num_batches_tracked"] = np.asarray(sd.sd[sd.prefix + "num_batches_tracked"]).astype(np.int64) + 1
+        s = sd["weight"] / np.sqrt(var + x.dtype.type(eps))
+        return (x - mean[None, :, None]) * s[None, :, None] + sd["bias"][None, :, None]
     s = sd["weight"] / np.sqrt(sd["running_var"] + x.dtype.type(eps))
     return (x - sd["running_mean"][None, :, None]) * s[None, :, None] + sd["bias"][None, :, None]
 
@@ -369,13 +383,15 @@ def oan_block(data, xs, sd, depth, dtype, guard="batch"):
     return logits, weights, R, t, res, out, flag
 
 
-def oanet_forward(xs, state_dict, net_depth=12, iter_num=1, prefix="", dtype=np.float32, guard="batch"):
-    """OANet.forward, oanet.py:218-265, eval mode.  xs [P,1,N,6(+1)].  state_dict: reference key names
-    (optionally with `prefix`, e.g. 'filtering_module.')."""
+def oanet_forward(xs, state_dict, net_depth=12, iter_num=1, prefix="", dtype=np.float32, guard="batch", train=False):
+    """OANet.forward, oanet.py:218-265.  xs [P,1,N,6(+1)].  state_dict: reference key names (optionally with `prefix`, e.g.
+    'filtering_module.').  train=True: BatchNorm in training mode (batch statistics); out["bn_updates"] then maps every
+    BatchNorm buffer name to its value after the forward pass (the input state_dict is not modified)."""
     xs = np.asarray(xs, dtype)
     assert xs.ndim == 4 and xs.shape[1] == 1
     depth = net_depth // (iter_num + 1)
-    sd = _SD(state_dict, prefix, dtype)
+    updates = {}
+    sd = _SD(state_dict, prefix, dtype, train, updates)
     inp = xs.transpose(0, 3, 2, 1)[:, :, :, 0]                       # [P,Cx,N]
     out = {"logits": [], "scores": [], "rot_est": [], "trans_est": [], "residuals": []}
     logits, w, R, t, res, lat, flag = oan_block(inp, xs, sd.sub("reg_init"), depth, dtype, guard)
@@ -389,6 +405,8 @@ def oanet_forward(xs, state_dict, net_depth=12, iter_num=1, prefix="", dtype=np.
             out[k].append(v)
     out["latent features"] = lat[:, :, :, None]
     out["gradient_flag"] = flag
+    if train:
+        out["bn_updates"] = updates
     return out
 
 
