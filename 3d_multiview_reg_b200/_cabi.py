@@ -20,7 +20,7 @@ GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
 EXPORTS = [
-    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
     "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
     "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
 ]
@@ -60,6 +60,9 @@ def load():
     lib.lmpcr_overlap_workspace_bytes.argtypes = [_i]
     lib.lmpcr_overlap_count.argtypes = [_vp, _i, _vp, _i, _vp, ctypes.c_double, _vp, _vp, _vp, _sz, _vp]
     lib.lmpcr_voxel_downsample.argtypes = [_vp, _i, ctypes.c_double, _vp, _vp, _vp, _vp, _sz, _vp]
+    lib.lmpcr_softmax_pool_workspace_bytes.restype = _sz
+    lib.lmpcr_softmax_pool_workspace_bytes.argtypes = [_i, _i, _i, _i]
+    lib.lmpcr_softmax_pool.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]
     lib.lmpcr_nn_soft.argtypes = [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _sz, _vp]
     lib.lmpcr_launch_count.restype = ctypes.c_longlong
     lib.lmpcr_nn_tensor_debug.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
@@ -373,6 +376,19 @@ def conv1x1(x, weight, bias=None, scale=None, shift=None, residual=None, gemm_al
             workspace = _ws(lib.lmpcr_conv1x1_workspace_bytes(cout, cin), x.device)
         _check(lib.lmpcr_conv1x1(_p(x), P, cin, N, _p(w), _p(bias), _p(scale), _p(shift), _p(residual), cout, _p(out), gemm_algo,
                                  _p(workspace), workspace.numel(), _stream(x)))
+    return out
+
+
+def softmax_pool(x, embed, mode=1):
+    """diff_pool's weighted sum (oanet.py:107-109): x [P,C,N], embed [P,K,N] -> [P,C,K]; mode 0 separate statistics, 1 deferred."""
+    lib = load()
+    x, e = _dev(x, name="x"), _dev(embed, name="embed")
+    P, C, N = x.shape
+    K = e.shape[1]
+    with torch.cuda.device(x.device):
+        out = torch.empty((P, C, K), dtype=torch.float32, device=x.device)
+        ws = _ws(lib.lmpcr_softmax_pool_workspace_bytes(P, C, K, N), x.device)
+        _check(lib.lmpcr_softmax_pool(_p(x), _p(e), P, C, K, N, int(mode), _p(out), _p(ws), ws.numel(), _stream(x)))
     return out
 
 

@@ -12,6 +12,8 @@
 #include <math.h>
 
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "tcgemm.cuh"
 
 namespace lmpcr {
@@ -409,35 +411,26 @@ __global__ void affine_from_partials_kernel(const float* __restrict__ part, int 
   }
 }
 
-// softmax-over-points statistics (diff_pool) from the per-tile (max, sum exp) partials of the embedding conv
-__global__ void softmax_from_partials_kernel(const float* __restrict__ part, int tiles, int n_rows, float* __restrict__ smax,
-                                             float* __restrict__ sinv) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+// softmax-over-points maximum (diff_pool) from the per-tile row maxima written by the embedding conv's epilogue; the sums are
+// accumulated by the pooling GEMM itself (TC_PRO_SOFTMAX_DEFER).  One warp per (pair, cluster) row, part [n_rows, tiles].
+__global__ void rowmax_from_partials_kernel(const float* __restrict__ part, int tiles, int n_rows, float* __restrict__ smax) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
-  const float* q = part + (size_t)row * tiles * 2;
+  const int lane = threadIdx.x & 31;
   float m = -INFINITY;
-  for (int t = 0; t < tiles; ++t) m = fmaxf(m, __ldg(q + 2 * t));
-  float s = 0.f;
-  for (int t = 0; t < tiles; ++t) s += __ldg(q + 2 * t + 1) * __expf(__ldg(q + 2 * t) - m);
-  smax[row] = m;
-  sinv[row] = 1.0f / s;
+  for (int t = lane; t < tiles; t += 32) m = fmaxf(m, __ldg(part + (size_t)row * tiles + t));
+  m = warp_max(m);
+  if (lane == 0) smax[row] = m * 1.4426950408889634f;      // pre-scaled by log2(e) for the GEMM's 2^x prologue
 }
 
-// softmax-over-clusters statistics (diff_unpool) from the per-slab column partials of the embedding conv's epilogue
-__global__ void softmax_cols_from_partials_kernel(const float* __restrict__ part, int np, size_t n_cols, float* __restrict__ cmax,
-                                                  float* __restrict__ cinv) {
+// softmax-over-clusters maximum (diff_unpool) from the per-slab column maxima; part [n_cols, np], one thread per (pair, point)
+__global__ void colmax_from_partials_kernel(const float* __restrict__ part, int np, size_t n_cols, float* __restrict__ cmax) {
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n_cols) return;
-  const float2* q = reinterpret_cast<const float2*>(part) + gid * np;
+  const float* q = part + gid * np;
   float m = -INFINITY;
-  for (int t = 0; t < np; ++t) m = fmaxf(m, __ldg(q + t).x);
-  float s = 0.f;
-  for (int t = 0; t < np; ++t) {
-    const float2 v = __ldg(q + t);
-    if (v.x != -INFINITY) s += v.y * __expf(v.x - m);
-  }
-  cmax[gid] = m;
-  cinv[gid] = 1.0f / s;
+  for (int t = 0; t < np; ++t) m = fmaxf(m, __ldg(q + t));
+  cmax[gid] = m * 1.4426950408889634f;
 }
 
 // output conv (C -> 1) + tanh/relu weights (oanet.py:174-175) + "any positive weight" flag per pair
@@ -576,6 +569,46 @@ int launch_conv1x1(const float* x, int P, int cin, int N, const float* weight, c
   return LMPCR_OK;
 }
 
+__global__ void scale_inplace_kernel(float* __restrict__ v, size_t n, float f) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] *= f;
+}
+
+// diff_pool's weighted sum alone (oanet.py:107-109): out[p,c,k] = sum_n x[p,c,n] * softmax_n(E[p,k,:])[n]; tensor-core path only.
+// mode 0: softmax statistics by a separate pass, normalised weights as the B operand; mode 1: deferred normalisation (the producers
+// accumulate the sums, the epilogue divides) -- the two ways lmpcr_filter_forward can run this step.
+size_t softmax_pool_workspace_bytes(int P, int C, int K, int N) {
+  return align_up((size_t)P * tc_weight_blob_bytes(C, N), 256) + 2 * align_up((size_t)P * K * 4, 256) +
+         align_up((size_t)P * C * ((K + TC_TILE_N - 1) / TC_TILE_N) * 8, 256) + 256;
+}
+
+int launch_softmax_pool(const float* x, const float* E, int P, int C, int K, int N, int mode, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  LMPCR_REQUIRE(x && E && out && P >= 0 && C > 0 && K > 0 && N > 0, LMPCR_ERR_ARG, "lmpcr_softmax_pool: bad arguments");
+  LMPCR_REQUIRE(mode == 0 || (mode == 1 && N >= TC_DEFER_MIN_K), LMPCR_ERR_ARG, "lmpcr_softmax_pool: mode");
+  LMPCR_REQUIRE(ws && ws_bytes >= softmax_pool_workspace_bytes(P, C, K, N) && ((uintptr_t)ws & 255) == 0, LMPCR_ERR_WORKSPACE, "lmpcr_softmax_pool: workspace");
+  if (P == 0) return LMPCR_OK;
+  char* w = reinterpret_cast<char*>(ws);
+  uint8_t* blob = reinterpret_cast<uint8_t*>(w); w += align_up((size_t)P * tc_weight_blob_bytes(C, N), 256);
+  float* smax = reinterpret_cast<float*>(w); w += align_up((size_t)P * K * 4, 256);
+  float* sinv = reinterpret_cast<float*>(w); w += align_up((size_t)P * K * 4, 256);
+  float* stats = reinterpret_cast<float*>(w);          // per-tile (mean, M2) of the output rows, as the network's consumer wants them
+  softmax_rowstats_kernel<<<P * K, 256, 0, st>>>(E, N, P * K, smax, sinv);
+  LMPCR_TRY(check_launch("softmax_rowstats_kernel"));
+  if (mode == 1) {
+    scale_inplace_kernel<<<(unsigned)(((size_t)P * K + 255) / 256), 256, 0, st>>>(smax, (size_t)P * K, 1.4426950408889634f);
+    LMPCR_TRY(check_launch("scale_inplace_kernel"));
+  }
+  LMPCR_TRY(launch_split_weights(x, C, N, blob, st, P, (long long)C * N, N));
+  TcGemmArgs a{};
+  a.a_blob = blob; a.a_blob_batch = (long long)tc_weight_blob_bytes(C, N);
+  a.B = E; a.b_batch = (long long)K * N; a.b_ld = N; a.b_kmajor = 1;
+  a.C = out; a.c_batch = (long long)C * K; a.c_i = K; a.c_j = 1;
+  a.prologue = mode ? TC_PRO_SOFTMAX_DEFER : TC_PRO_SOFTMAX; a.p0 = smax; a.p1 = mode ? nullptr : sinv; a.p_batch = K;
+  a.M = C; a.N = K; a.K = N;
+  a.stats_out = tc_fast_epilogue(a) ? stats : nullptr;
+  return launch_tcgemm(a, P, st);
+}
+
 int filter_num_params(const lmpcr_filter_cfg* cfg) {
   const int half = (cfg->net_depth / (cfg->iter_num + 1)) / 2;
   return block_num_params(half) * (cfg->iter_num + 1);
@@ -620,6 +653,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   LMPCR_REQUIRE(cfg->gemm_algo == 0 || cfg->gemm_algo == 1, LMPCR_ERR_UNSUPPORTED, "lmpcr_filter_forward: gemm_algo=%d unknown", cfg->gemm_algo);
   const bool tc = cfg->gemm_algo == 1;
   const bool bn_train = cfg->bn_mode == LMPCR_BN_BATCH;
+  static const int no_defer = getenv("LMPCR_NO_DEFER") ? atoi(getenv("LMPCR_NO_DEFER")) : 0;   // debug aid: softmax statistics by separate passes
   LMPCR_REQUIRE(n_params == filter_num_params(cfg), LMPCR_ERR_ARG, "lmpcr_filter_forward: expected %d parameter tensors, got %d", filter_num_params(cfg), n_params);
   for (int i = 0; i < n_params; ++i) LMPCR_REQUIRE(params[i], LMPCR_ERR_ARG, "lmpcr_filter_forward: params[%d] is null", i);
   if (P == 0) return LMPCR_OK;
@@ -834,9 +868,10 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         a.C = W.XD0; a.c_batch = CK; a.c_i = K; a.c_j = 1;
         a.prologue = TC_PRO_SOFTMAX; a.p0 = sm_max; a.p1 = sm_inv; a.p_batch = K;
         a.M = C; a.N = K; a.K = N;
-        if ((N & 3) == 0) {   // softmax statistics came fused out of the embedding conv's epilogue
-          softmax_from_partials_kernel<<<(g * K + 127) / 128, 128, 0, st>>>(sm_part, tilesN, g * K, sm_max, sm_inv);
-          LMPCR_TRY(check_launch("softmax_from_partials_kernel"));
+        if ((N & 3) == 0 && N >= TC_DEFER_MIN_K && !(no_defer & 1)) {   // row maxima came fused out of the embedding conv's epilogue; the GEMM accumulates the sums itself
+          rowmax_from_partials_kernel<<<(g * K + 7) / 8, 256, 0, st>>>(sm_part, tilesN, g * K, sm_max);
+          LMPCR_TRY(check_launch("rowmax_from_partials_kernel"));
+          a.prologue = TC_PRO_SOFTMAX_DEFER; a.p1 = nullptr;
         } else {
           softmax_rowstats_kernel<<<g * K, 256, 0, st>>>(W.E, N, g * K, sm_max, sm_inv);
           LMPCR_TRY(check_launch("softmax_rowstats_kernel"));
@@ -891,9 +926,10 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       LMPCR_TRY(conv_norm(x11, x11b, C, N, g, 1e-3f, blk.up_bn, blk.up_conv, K, W.E, (long long)K * N, nullptr, 0));
       want_col = false;
       if (tc) {
-        if ((N & 3) == 0) {   // statistics came fused out of the embedding conv's epilogue
-          softmax_cols_from_partials_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(col_part, 4 * ((K + 127) / 128), tot, sm_max, sm_inv);
-          LMPCR_TRY(check_launch("softmax_cols_from_partials_kernel"));
+        const bool defer_up = (N & 3) == 0 && K >= TC_DEFER_MIN_K && !(no_defer & 2);
+        if (defer_up) {   // column maxima came fused out of the embedding conv's epilogue; the GEMM accumulates the sums itself
+          colmax_from_partials_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(col_part, 4 * ((K + 127) / 128), tot, sm_max);
+          LMPCR_TRY(check_launch("colmax_from_partials_kernel"));
         } else {
           softmax_colstats_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g, sm_max, sm_inv);
           LMPCR_TRY(check_launch("softmax_colstats_kernel"));
@@ -903,7 +939,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         a.a_blob = blob_x2; a.a_blob_batch = (long long)tc_weight_blob_bytes(C, K);
         a.B = W.E; a.b_batch = (long long)K * N; a.b_ld = N; a.b_kmajor = 0;
         a.C = W.CAT + CN; a.c_batch = 2 * CN; a.c_i = N; a.c_j = 1;
-        a.prologue = TC_PRO_SOFTMAX; a.p0 = sm_max; a.p1 = sm_inv; a.p_batch = N;
+        a.prologue = defer_up ? TC_PRO_SOFTMAX_DEFER : TC_PRO_SOFTMAX; a.p0 = sm_max; a.p1 = defer_up ? nullptr : sm_inv; a.p_batch = N;
         a.M = C; a.N = N; a.K = K;
         { const int oi = part_index(W.CAT + CN); part_valid[oi] = tc_fast_epilogue(a); a.stats_out = part_valid[oi] ? part_buf[oi] : nullptr; }
         LMPCR_TRY(launch_tcgemm(a, g, st));

@@ -43,7 +43,8 @@ constexpr uint32_t MN_SBO = 128, MN_LBO = (TN / 8) * 128;         // MN-major op
 constexpr int TR_LD = 33;                                         // padded row of the generic epilogue's transpose buffer
 constexpr int STG_ROW = TN * 4 + 16;                              // 272 B: 16-byte aligned, conflict-free for float4 at one row per lane
 constexpr int STG_BYTES = TM * STG_ROW;                           // 34816: one staged output tile (also hosts the transpose buffers)
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 128 * 8 + 16 * 8 + 16;
+constexpr int ZPART_FLOATS = 2 * 4 * TN, INVZ_FLOATS = 4 * TN;    // deferred softmax: [tile parity][4 partial sums][column], [epilogue warp][column]
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 128 * 8 + 16 * 8 + 16 + (ZPART_FLOATS + INVZ_FLOATS) * 4;
 static_assert(4 * 32 * TR_LD * 4 <= STG_BYTES, "transpose buffers must fit the staging area");
 static_assert(TN % 32 == 0 && TN <= 128, "tile width");
 
@@ -51,6 +52,7 @@ __device__ __forceinline__ void l2_prefetch_line(const void* src) {   // one 128
   asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
 }
 
+constexpr float LOG2E = 1.4426950408889634f;
 __device__ __forceinline__ float exp2f_fast(float x) {   // MUFU.EX2
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -69,6 +71,13 @@ __device__ __forceinline__ void split8_store(const float (&x)[8], uint8_t* hi_ds
   }
   *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// 8 consecutive floats with ONE 256-bit load (SASS LDG.256; src 32-byte aligned): a warp then requests whole 128-byte lines
+// instead of two interleaved halves, i.e. half as many L1 requests in flight per byte
+__device__ __forceinline__ void ldg256(const float* src, float (&x)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]), "=f"(x[4]), "=f"(x[5]), "=f"(x[6]), "=f"(x[7]) : "l"(src));
 }
 
 // 8 consecutive floats starting at src; the first `nvalid` (0..8) are in range, the rest read as 0
@@ -147,6 +156,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
   uint64_t* rowbars = reinterpret_cast<uint64_t*>(stg + STG_BYTES);    // [128 rows]
   uint64_t* bars = rowbars + 128;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* zpart = reinterpret_cast<float*>(tmem_slot + 4);               // [2][4][TN]
+  float* invz = zpart + ZPART_FLOATS;                                   // [4 epilogue warps][TN]
+  const bool defer = g.prologue == TC_PRO_SOFTMAX_DEFER;
   const uint32_t bar0 = smem_u32(bars);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
   auto EMPTY = [&](int s) { return bar0 + 8u * (STAGES + s); };
@@ -160,6 +172,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
   const bool b_blob = g.b_blob != nullptr;        // both operands by TMA: the producer warps have nothing to do
   const int tiles_m = (g.M + TM - 1) / TM, tiles_n = (g.N + TN - 1) / TN, n_kc = (g.K + KC - 1) / KC;
   const long long n_tiles = (long long)batch * tiles_m * tiles_n;
+  // tcgen05 accumulates in fp32 with round-toward-zero: over thousands of K steps (diff_pool: K = number of points) that is a
+  // systematic bias (measured -1e-4 relative at K = 50,000).  Long reductions are therefore cut into segments of FL chunks: each
+  // segment is accumulated in TMEM, then added (round-to-nearest, CUDA cores) into the staged output tile by the epilogue warps.
+  // Only beyond 8192 K elements: below that the bias is < 2e-5 relative and the hand-offs cost 2.5 % of the network's time.
+  const int FL = (n_kc > 256 && !g.Res && tc_fast_epilogue(g)) ? 32 : n_kc;
+  const int n_seg = (n_kc + FL - 1) / FL;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), b_blob ? 1 : N_PROD_WARPS + (a_blob ? 1 : 0)); mbar_init(EMPTY(s), 1); }
@@ -260,12 +278,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
       constexpr uint32_t B_LBO = B_KMAJOR ? K_LBO : MN_LBO, B_SBO = B_KMAJOR ? K_SBO : MN_SBO;
       int stage = 0, acc = 0; uint32_t phase = 0, acc_phase = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        TC_PROF(2, tp);
-        mbar_wait(T_EMPTY(acc), acc_phase ^ 1);
-        tc_fence_after();
-        TC_PROF(0, tp);
-        const uint32_t d_tmem = tmem_base + acc * TN;
-        for (int kc = 0; kc < n_kc; ++kc) {
+        uint32_t d_tmem = 0;
+        for (int kc = 0, kf = 0; kc < n_kc; ++kc) {
+          if (kf == 0) {                         // first chunk of a segment: claim an accumulator
+            TC_PROF(2, tp);
+            mbar_wait(T_EMPTY(acc), acc_phase ^ 1);
+            tc_fence_after();
+            TC_PROF(0, tp);
+            d_tmem = tmem_base + acc * TN;
+          }
           mbar_wait(FULL(stage), phase);
           tc_fence_after();
           TC_PROF(1, tp);
@@ -276,16 +297,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
             const uint64_t a_lo = make_desc(sA + A_OP_BYTES + ks * 2 * K_LBO, K_LBO, K_SBO);
             const uint64_t b_hi = make_desc(sB + ks * 2 * B_LBO, B_LBO, B_SBO);
             const uint64_t b_lo = make_desc(sB + B_OP_BYTES + ks * 2 * B_LBO, B_LBO, B_SBO);
-            tc_mma_f16(d_tmem, a_lo, b_hi, IDESC, (kc | ks) ? 1u : 0u);   // small terms first
+            tc_mma_f16(d_tmem, a_lo, b_hi, IDESC, (kf | ks) ? 1u : 0u);   // small terms first
             tc_mma_f16(d_tmem, a_hi, b_lo, IDESC, 1u);
             tc_mma_f16(d_tmem, a_hi, b_hi, IDESC, 1u);
           }
           tc_commit(EMPTY(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           TC_PROF(2, tp);
+          if (++kf == FL || kc == n_kc - 1) {    // segment complete: hand the accumulator to the epilogue warps
+            tc_commit(T_FULL(acc));
+            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            kf = 0;
+          }
         }
-        tc_commit(T_FULL(acc));
-        acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
     }
   } else if (warp >= FIRST_PROD_WARP) {
@@ -301,46 +325,68 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
     constexpr int NIT = B_ITERS / N_PROD_WARPS;        // 2
     constexpr int A_ITERS = (TM / 8) * (KC / 32), NIT_A = A_ITERS / N_PROD_WARPS;
     const bool b_aligned = ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && ((g.b_ld & 3) == 0) && ((g.b_batch & 3) == 0);
+    const bool b_al32 = ((reinterpret_cast<uintptr_t>(g.B) & 31) == 0) && ((g.b_ld & 7) == 0) && ((g.b_batch & 7) == 0);
     const bool p_aligned = !g.p0 || (((reinterpret_cast<uintptr_t>(g.p0) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.p1) & 15) == 0) && ((g.p_batch & 3) == 0));
     // element coordinates of warp-iteration `it`
     //   j-major B (k rows, j contiguous): k = kc*KC + (it / (TN/32))*8 + l8,  j0 = nt*TN + (it % (TN/32))*32 + g4*8
     //   k-major B (j rows, k contiguous): j = nt*TN + it*8 + l8,              k0 = kc*KC + g4*8
-    float xb[NIT][8];
-    int nvb[NIT];
-    bool interior = false;                     // state of the chunk currently held in xb (warp-uniform)
-    auto fetch_b = [&](long long tile, int kc) {
-      int p, mt, nt; decode(tile, p, mt, nt);
-      const float* Bp = g.B + (long long)p * g.b_batch;
-      interior = b_aligned && p_aligned && ((kc + 1) * KC <= g.K) && ((nt + 1) * TN <= g.N);
+    // Register prefetch ring, PF chunks deep (statically indexed: the chunk loop dispatches on the slot).  Measured on B200:
+    // PF = 1 is fastest everywhere -- class-A layers 436 / 423 / 515 us per launch at PF = 1 / 2 / 3, and the whole network
+    // 108.1 vs 110.5 us per pair with PF = 3 on the k-major GEMMs only: the SM runs out of L1 miss-tracking entries before it
+    // runs out of latency to hide, which is also why the 256-bit loads below (half as many requests per byte) do help.
+    constexpr int PF = 1;
+    float xr[PF][NIT][8];
+    int nvr[PF][NIT];
+    bool inr[PF];                              // the chunk held in slot s is an interior chunk (warp-uniform)
+    long long f_tile = blockIdx.x; int f_kc = 0, f_p = 0, f_mt = 0, f_nt = 0;     // fetch cursor (PF chunks ahead of the consume cursor)
+    if (f_tile < n_tiles) decode(f_tile, f_p, f_mt, f_nt);
+    // deferred softmax normalisation: running sum of f(B[k,j]) over this thread's share of the tile's k range
+    //   k-major: one row j per thread (zacc[0]);  j-major: 8 consecutive columns per thread (zacc[e])
+    static_assert(NIT == 1, "the column sums below assume one warp-iteration per chunk");
+    float zacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int tpar = 0;                              // tile parity = the accumulator / zpart buffer the epilogue will use
+    auto fetch_b = [&](auto slot_c) {
+      constexpr int S = decltype(slot_c)::value;
+      if (f_tile >= n_tiles) return;           // nothing left: the slot is never consumed
+      const int kc = f_kc, nt = f_nt;
+      const float* Bp = g.B + (long long)f_p * g.b_batch;
+      inr[S] = b_aligned && p_aligned && ((kc + 1) * KC <= g.K) && ((nt + 1) * TN <= g.N);
 #pragma unroll
       for (int u = 0; u < NIT; ++u) {
         const int it = pw + u * N_PROD_WARPS;
         const float* src;
         if (B_KMAJOR) {
           const int j = nt * TN + it * 8 + l8, k0 = kc * KC + g4 * 8;
-          nvb[u] = (j < g.N) ? min(8, max(0, g.K - k0)) : 0;
+          nvr[S][u] = (j < g.N) ? min(8, max(0, g.K - k0)) : 0;
           src = Bp + (long long)j * g.b_ld + k0;
         } else {
           const int k = kc * KC + (it / (TN / 32)) * 8 + l8, j0 = nt * TN + (it % (TN / 32)) * 32 + g4 * 8;
-          nvb[u] = (k < g.K) ? min(8, max(0, g.N - j0)) : 0;
+          nvr[S][u] = (k < g.K) ? min(8, max(0, g.N - j0)) : 0;
           src = Bp + (long long)k * g.b_ld + j0;
         }
-        if (interior) {
+        if (inr[S] && b_al32) {
+          ldg256(src, xr[S][u]);
+        } else if (inr[S]) {
           const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-          xb[u][0] = a.x; xb[u][1] = a.y; xb[u][2] = a.z; xb[u][3] = a.w; xb[u][4] = b.x; xb[u][5] = b.y; xb[u][6] = b.z; xb[u][7] = b.w;
+          xr[S][u][0] = a.x; xr[S][u][1] = a.y; xr[S][u][2] = a.z; xr[S][u][3] = a.w; xr[S][u][4] = b.x; xr[S][u][5] = b.y; xr[S][u][6] = b.z; xr[S][u][7] = b.w;
         } else {
-          load8(src, nvb[u], xb[u]);
+          load8(src, nvr[S][u], xr[S][u]);
         }
+      }
+      if (++f_kc == n_kc) {
+        f_kc = 0; f_tile += gridDim.x;
+        if (f_tile < n_tiles) decode(f_tile, f_p, f_mt, f_nt);
       }
     };
     int stage = 0; uint32_t phase = 0;
-    if ((long long)blockIdx.x < n_tiles) fetch_b(blockIdx.x, 0);
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      int p, mt, nt; decode(tile, p, mt, nt);
-      const float* Ap = a_blob ? nullptr : g.A + (long long)p * g.a_batch;
-      const float* q0 = g.p0 ? g.p0 + (long long)p * g.p_batch : nullptr;
-      const float* q1 = g.p1 ? g.p1 + (long long)p * g.p_batch : nullptr;
-      for (int kc = 0; kc < n_kc; ++kc) {
+    fetch_b(std::integral_constant<int, 0>{});
+    if (PF > 1) fetch_b(std::integral_constant<int, (PF > 1 ? 1 : 0)>{});
+    if (PF > 2) fetch_b(std::integral_constant<int, (PF > 2 ? 2 : 0)>{});
+    int p = 0, mt = 0, nt = 0;
+    const float* Ap = nullptr; const float* q0 = nullptr; const float* q1 = nullptr;
+    auto chunk = [&](auto slot_c, int kc) {
+      constexpr int S = decltype(slot_c)::value;
+      {
         // per-k affine of the j-major layout: two scalars per warp-iteration, fetched before the wait
         float sc_u[NIT], sh_u[NIT];
 #pragma unroll
@@ -361,55 +407,74 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
           const int it = pw + u * N_PROD_WARPS;
           const int jrow = nt * TN + it * 8 + l8, k0 = kc * KC + g4 * 8;                  // k-major coordinates
           const int j0 = nt * TN + (it % (TN / 32)) * 32 + g4 * 8;                        // j-major coordinate
-          if (interior) {
+          if (inr[S]) {
             if (g.prologue == TC_PRO_AFFINE_RELU) {
               if (B_KMAJOR) {                 // per-k parameters, 8 consecutive k per lane
                 const float4 s0 = __ldg(reinterpret_cast<const float4*>(q0 + k0)), s1 = __ldg(reinterpret_cast<const float4*>(q0 + k0) + 1);
                 const float4 t0 = __ldg(reinterpret_cast<const float4*>(q1 + k0)), t1 = __ldg(reinterpret_cast<const float4*>(q1 + k0) + 1);
                 const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) xb[u][e] = fmaxf(fmaf(xb[u][e], ss[e], tt[e]), 0.f);
+                for (int e = 0; e < 8; ++e) xr[S][u][e] = fmaxf(fmaf(xr[S][u][e], ss[e], tt[e]), 0.f);
               } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) xb[u][e] = fmaxf(fmaf(xb[u][e], sc_u[u], sh_u[u]), 0.f);
+                for (int e = 0; e < 8; ++e) xr[S][u][e] = fmaxf(fmaf(xr[S][u][e], sc_u[u], sh_u[u]), 0.f);
               }
             } else if (g.prologue == TC_PRO_SOFTMAX) {
               if (B_KMAJOR) {                 // per-row (j) parameters
                 const float m = __ldg(q0 + jrow), inv = __ldg(q1 + jrow);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) xb[u][e] = __expf(xb[u][e] - m) * inv;
+                for (int e = 0; e < 8; ++e) xr[S][u][e] = __expf(xr[S][u][e] - m) * inv;
               } else {                        // per-column (j) parameters, 8 consecutive j per lane
                 const float4 m0 = __ldg(reinterpret_cast<const float4*>(q0 + j0)), m1 = __ldg(reinterpret_cast<const float4*>(q0 + j0) + 1);
                 const float4 i0 = __ldg(reinterpret_cast<const float4*>(q1 + j0)), i1 = __ldg(reinterpret_cast<const float4*>(q1 + j0) + 1);
                 const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w}, ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) xb[u][e] = __expf(xb[u][e] - mm[e]) * ii[e];
+                for (int e = 0; e < 8; ++e) xr[S][u][e] = __expf(xr[S][u][e] - mm[e]) * ii[e];
+              }
+            } else if (g.prologue == TC_PRO_SOFTMAX_DEFER) {
+              if (B_KMAJOR) {
+                const float mb = __ldg(q0 + jrow);          // max * log2(e): exp(x - max) = 2^(x*log2e - mb), one FFMA + one MUFU.EX2
+#pragma unroll
+                for (int e = 0; e < 8; ++e) xr[S][u][e] = exp2f_fast(fmaf(xr[S][u][e], LOG2E, -mb));
+                zacc[0] += ((xr[S][u][0] + xr[S][u][1]) + (xr[S][u][2] + xr[S][u][3])) + ((xr[S][u][4] + xr[S][u][5]) + (xr[S][u][6] + xr[S][u][7]));
+              } else {
+                const float4 m0 = __ldg(reinterpret_cast<const float4*>(q0 + j0)), m1 = __ldg(reinterpret_cast<const float4*>(q0 + j0) + 1);
+                const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { xr[S][u][e] = exp2f_fast(fmaf(xr[S][u][e], LOG2E, -mm[e])); zacc[e] += xr[S][u][e]; }
               }
             }
-          } else if (g.prologue != TC_PRO_NONE && nvb[u] > 0) {      // guarded edge path (same arithmetic)
+          } else if (g.prologue != TC_PRO_NONE && nvr[S][u] > 0) {      // guarded edge path (same arithmetic)
             if (B_KMAJOR) {
               if (g.prologue == TC_PRO_AFFINE_RELU) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = fmaxf(fmaf(xb[u][e], __ldg(q0 + k0 + e), __ldg(q1 + k0 + e)), 0.f);
-              } else {
+                for (int e = 0; e < 8; ++e) if (e < nvr[S][u]) xr[S][u][e] = fmaxf(fmaf(xr[S][u][e], __ldg(q0 + k0 + e), __ldg(q1 + k0 + e)), 0.f);
+              } else if (g.prologue == TC_PRO_SOFTMAX) {
                 const float m = __ldg(q0 + jrow), inv = __ldg(q1 + jrow);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = __expf(xb[u][e] - m) * inv;
+                for (int e = 0; e < 8; ++e) if (e < nvr[S][u]) xr[S][u][e] = __expf(xr[S][u][e] - m) * inv;
+              } else {
+                const float mb = __ldg(q0 + jrow);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (e < nvr[S][u]) { xr[S][u][e] = exp2f_fast(fmaf(xr[S][u][e], LOG2E, -mb)); zacc[0] += xr[S][u][e]; }
               }
             } else {
               if (g.prologue == TC_PRO_AFFINE_RELU) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = fmaxf(fmaf(xb[u][e], sc_u[u], sh_u[u]), 0.f);
+                for (int e = 0; e < 8; ++e) if (e < nvr[S][u]) xr[S][u][e] = fmaxf(fmaf(xr[S][u][e], sc_u[u], sh_u[u]), 0.f);
+              } else if (g.prologue == TC_PRO_SOFTMAX) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (e < nvr[S][u]) xr[S][u][e] = __expf(xr[S][u][e] - __ldg(q0 + j0 + e)) * __ldg(q1 + j0 + e);
               } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) if (e < nvb[u]) xb[u][e] = __expf(xb[u][e] - __ldg(q0 + j0 + e)) * __ldg(q1 + j0 + e);
+                for (int e = 0; e < 8; ++e) if (e < nvr[S][u]) { xr[S][u][e] = exp2f_fast(fmaf(xr[S][u][e], LOG2E, -__ldg(q0 + j0 + e))); zacc[e] += xr[S][u][e]; }
               }
             }
           }
           uint32_t off;
           if (B_KMAJOR) off = it * K_SBO + g4 * K_LBO + l8 * 16;
           else off = ((it % (TN / 32)) * 4 + g4) * MN_SBO + (it / (TN / 32)) * MN_LBO + l8 * 16;
-          split8_store(xb[u], st_base + 2 * A_OP_BYTES + off, st_base + 2 * A_OP_BYTES + B_OP_BYTES + off);
+          split8_store(xr[S][u], st_base + 2 * A_OP_BYTES + off, st_base + 2 * A_OP_BYTES + B_OP_BYTES + off);
         }
         // ---- A operand from fp32 activations (k contiguous): not used by the network (A is always pre-split) ----
         if (!a_blob) {
@@ -424,15 +489,44 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
             split8_store(xa, st_base + off, st_base + A_OP_BYTES + off);
           }
         }
+        if (defer && kc == n_kc - 1) {
+          // publish this thread's share of the column sums (fixed slots, fixed order => deterministic); the epilogue reads them after
+          // T_FULL, which the MMA warp commits only after it has seen this warp's arrive below
+          float* zp = zpart + tpar * 4 * TN;
+          if (B_KMAJOR) {
+            zp[g4 * TN + pw * 8 + l8] = zacc[0];
+            zacc[0] = 0.f;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float v = zacc[e];
+              v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+              if (l8 == 0) zp[(pw / (TN / 32)) * TN + (pw % (TN / 32)) * 32 + g4 * 8 + e] = v;
+              zacc[e] = 0.f;
+            }
+          }
+          tpar ^= 1;
+        }
         TC_PROF(4, tp);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(FULL(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
         TC_PROF(5, tp);
-        // ---- prefetch the next chunk's B values ----
-        if (kc + 1 < n_kc) fetch_b(tile, kc + 1);
-        else if (tile + gridDim.x < n_tiles) fetch_b(tile + gridDim.x, 0);
+      }
+      fetch_b(slot_c);                         // refill this slot with the chunk PF steps ahead
+    };
+    int slot = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      decode(tile, p, mt, nt);
+      Ap = a_blob ? nullptr : g.A + (long long)p * g.a_batch;
+      q0 = g.p0 ? g.p0 + (long long)p * g.p_batch : nullptr;
+      q1 = g.p1 ? g.p1 + (long long)p * g.p_batch : nullptr;
+      for (int kc = 0; kc < n_kc; ++kc) {
+        if (PF == 1 || slot == 0) chunk(std::integral_constant<int, 0>{}, kc);
+        else if (PF == 2 || slot == 1) chunk(std::integral_constant<int, (PF > 1 ? 1 : 0)>{}, kc);
+        else chunk(std::integral_constant<int, (PF > 2 ? 2 : 0)>{}, kc);
+        if (++slot == PF) slot = 0;
       }
     }
     }
@@ -448,6 +542,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
     const bool f_sm = RT ? (g.smstats_out != nullptr) : ((EPI & 2) != 0);
     const bool f_col = RT ? (g.colstats_out != nullptr) : ((EPI & 4) != 0);
     const bool f_res = RT ? (g.Res != nullptr) : ((EPI & 8) != 0);
+    const bool f_cs = RT ? defer : ((EPI & 16) != 0);                  // divide column j by the producers' sum (deferred softmax)
     if (fast) {
       // Fast path (rows contiguous along j, 16-byte friendly).  Phase 1, thread = row: the residual row was prefetched by
       // TMA into this thread's staged row (own mbarrier); accumulator + bias + residual are combined in place and the row
@@ -469,12 +564,34 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
           bulk_g2s(smem_u32(my_row), g.Res + (long long)p * g.r_batch + (long long)i * g.c_i + nt * TN, nc * 4, my_bar);
         }
       };
-      int acc = 0; uint32_t acc_phase = 0;
+      int acc = 0, tpar_e = 0; uint32_t acc_phase = 0;
+      const bool has_part = n_seg > 1;
       prefetch(blockIdx.x);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int p, mt, nt; decode(tile, p, mt, nt);
         const int i = mt * TM + r_own;
         const float bias_own = (g.bias && i < g.M) ? __ldg(g.bias + i) : 0.f;
+        // all but the last segment of a long reduction: add the TMEM partial into this thread's staged row (round-to-nearest)
+        for (int seg = 0; seg + 1 < n_seg; ++seg) {
+          mbar_wait(T_FULL(acc), acc_phase);
+          tc_fence_after();
+          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN;
+#pragma unroll
+          for (int cc = 0; cc < TN / 32; ++cc) {
+            float v[32];
+            tc_ld32(ta + cc * 32, v);
+            float4* dst = reinterpret_cast<float4*>(my_row + cc * 128);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              if (seg) { const float4 r4 = dst[q]; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+              dst[q] = o;
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(T_EMPTY(acc));
+          acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        }
         TC_PROF(11, tp);
         mbar_wait(T_FULL(acc), acc_phase);
         tc_fence_after();
@@ -484,6 +601,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
         const bool has_res = f_res && pending;
         if (has_res) { mbar_wait(my_bar, par); par ^= 1; }
         TC_PROF(8, tp);
+        const float* iz = invz + quarter * TN;
+        if (f_cs) {   // 1 / (sum of the four partial column sums), per warp copy so that only a __syncwarp is needed
+          const float* zp = zpart + tpar_e * 4 * TN;
+#pragma unroll
+          for (int c = lane; c < TN; c += 32) invz[quarter * TN + c] = 1.0f / ((zp[c] + zp[TN + c]) + (zp[2 * TN + c] + zp[3 * TN + c]));
+          __syncwarp();
+        }
         // The body is instantiated twice: FULL tiles (all TM rows and TN columns valid: no guards in the inner loops) and edge tiles.
         auto tile_body = [&](auto full_c) {
           constexpr bool FULL = decltype(full_c)::value;
@@ -495,7 +619,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
             float4* dst = reinterpret_cast<float4*>(my_row + cc * 128);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              float4 o = make_float4(v[4 * q] + bias_own, v[4 * q + 1] + bias_own, v[4 * q + 2] + bias_own, v[4 * q + 3] + bias_own);
+              if (has_part) {           // earlier segments of this tile
+                const float4 r4 = dst[q];
+                v[4 * q] += r4.x; v[4 * q + 1] += r4.y; v[4 * q + 2] += r4.z; v[4 * q + 3] += r4.w;
+              }
+              float4 o;
+              if (f_cs) {
+                const float4 z4 = reinterpret_cast<const float4*>(iz)[cc * 8 + q];
+                o = make_float4(fmaf(v[4 * q], z4.x, bias_own), fmaf(v[4 * q + 1], z4.y, bias_own), fmaf(v[4 * q + 2], z4.z, bias_own),
+                                fmaf(v[4 * q + 3], z4.w, bias_own));
+              } else {
+                o = make_float4(v[4 * q] + bias_own, v[4 * q + 1] + bias_own, v[4 * q + 2] + bias_own, v[4 * q + 3] + bias_own);
+              }
               if (has_res) { const float4 r4 = dst[q]; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
               dst[q] = o;
               if (FULL || cc * 32 + q * 4 < ncv) {
@@ -518,18 +653,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
               const float inv = 1.0f / (float)ncv;
               *reinterpret_cast<float2*>(g.stats_out + so) = make_float2(c0 + s1 * inv, fmaxf(s2 - s1 * s1 * inv, 0.f));
             }
-            if (f_sm) {             // second pass over the finished row (still in shared memory); exp(x - max) = 2^(x*log2e - max*log2e)
-              const float mb = vmax * 1.4426950408889634f;
-              float se0 = 0.f, se1 = 0.f;
-#pragma unroll 4
-              for (int q = 0; q < TN / 4; ++q)
-                if (FULL || q * 4 < ncv) {
-                  const float4 o = reinterpret_cast<const float4*>(my_row)[q];
-                  se0 += exp2f_fast(fmaf(o.x, 1.4426950408889634f, -mb)) + exp2f_fast(fmaf(o.y, 1.4426950408889634f, -mb));
-                  se1 += exp2f_fast(fmaf(o.z, 1.4426950408889634f, -mb)) + exp2f_fast(fmaf(o.w, 1.4426950408889634f, -mb));
-                }
-              *reinterpret_cast<float2*>(g.smstats_out + so) = make_float2(vmax, se0 + se1);
-            }
+            if (f_sm) g.smstats_out[((long long)p * g.M + i) * tiles_n + nt] = vmax;     // the sum comes from the consumer (TC_PRO_SOFTMAX_DEFER)
           }
           TC_PROF(10, tp);
           __syncwarp();
@@ -550,34 +674,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
               }
             }
             if (f_col) {
-              // softmax over the row (cluster) axis: per-column (max, sum exp) of this warp's 32-row slab; the two 16-lane
-              // halves hold alternate rows of the same 4 columns and are merged with one shuffle
-              float cs[4] = {0.f, 0.f, 0.f, 0.f};
-              if (FULL || col < ncv) {
-                const float mb0 = cm[0] * 1.4426950408889634f, mb1 = cm[1] * 1.4426950408889634f, mb2 = cm[2] * 1.4426950408889634f,
-                            mb3 = cm[3] * 1.4426950408889634f;
-#pragma unroll 4
-                for (int r = sub; r < 32; r += 32 / LPR) {
-                  if (FULL || ibase + r < g.M) {
-                    const float4 o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 4 * col);
-                    cs[0] += exp2f_fast(fmaf(o.x, 1.4426950408889634f, -mb0)); cs[1] += exp2f_fast(fmaf(o.y, 1.4426950408889634f, -mb1));
-                    cs[2] += exp2f_fast(fmaf(o.z, 1.4426950408889634f, -mb2)); cs[3] += exp2f_fast(fmaf(o.w, 1.4426950408889634f, -mb3));
-                  }
-                }
-              }
+              // softmax over the row (cluster) axis: per-column max of this warp's 32-row slab; the two 16-lane halves hold
+              // alternate rows of the same 4 columns and are merged with one shuffle (the sums come from the consumer)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float om = __shfl_xor_sync(0xffffffffu, cm[e], LPR), os = __shfl_xor_sync(0xffffffffu, cs[e], LPR);
-                const float m = fmaxf(cm[e], om);
-                const float sa = (cm[e] == -INFINITY) ? 0.f : cs[e] * __expf(cm[e] - m);
-                const float sb = (om == -INFINITY) ? 0.f : os * __expf(om - m);
-                cm[e] = m; cs[e] = sa + sb;
-              }
+              for (int e = 0; e < 4; ++e) cm[e] = fmaxf(cm[e], __shfl_xor_sync(0xffffffffu, cm[e], LPR));
               if (sub == 0 && (FULL || col < ncv)) {
                 const int np = tiles_m * 4, slab = mt * 4 + quarter;
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  *reinterpret_cast<float2*>(g.colstats_out + ((((long long)p * g.N + nt * TN + col + e) * np) + slab) * 2) = make_float2(cm[e], cs[e]);
+                for (int e = 0; e < 4; ++e) g.colstats_out[((long long)p * g.N + nt * TN + col + e) * np + slab] = cm[e];
               }
             }
           }
@@ -585,6 +689,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
         if (ncv == TN && (mt + 1) * TM <= g.M) tile_body(std::true_type{});
         else tile_body(std::false_type{});
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        tpar_e ^= 1;
         __syncwarp();
         fence_proxy_async();                 // generic reads of the staged rows are ordered before the next TMA write
         prefetch(tile + gridDim.x);
@@ -693,8 +798,13 @@ int tc_profile_read(unsigned long long* out16, int reset) {
 int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
   TcGemmArgs a = a_in;
   static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("LMPCR_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-  a.debug = dbg;
+  static int dbg_sel = 0;   // LMPCR_TC_PROF_SEL: restrict the debug mask to one kind of launch (1 pool, 2 unpool, 3 / 4 embedding convs, 5 class A)
+  if (dbg < 0) { const char* e = getenv("LMPCR_TC_DEBUG"); dbg = e ? atoi(e) : 0; const char* s2 = getenv("LMPCR_TC_PROF_SEL"); dbg_sel = s2 ? atoi(s2) : 0; }
+  {
+    const bool dfr = a.prologue == TC_PRO_SOFTMAX_DEFER;
+    const int kind = (dfr && a.b_kmajor) ? 1 : dfr ? 2 : a.smstats_out ? 3 : a.colstats_out ? 4 : (a.M == 128 && a.K == 128 && !a.b_kmajor && a.N > 1000) ? 5 : 6;
+    a.debug = (dbg_sel == 0 || dbg_sel == kind) ? dbg : 0;
+  }
   LMPCR_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && batch > 0, LMPCR_ERR_ARG, "tcgemm: bad sizes");
   LMPCR_REQUIRE(!a.b_blob || (a.a_blob && !a.b_kmajor), LMPCR_ERR_ARG, "tcgemm: b_blob needs a_blob and the j-major layout");
   const long long tiles = (long long)batch * ((a.M + TM - 1) / TM) * ((a.N + TN - 1) / TN);
@@ -702,11 +812,14 @@ int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
   const long long slots = 2ll * sm_count();          // two resident CTAs per SM
   const int grid = (int)(tiles < slots ? tiles : slots);
   // epilogue specialisations built for the feature sets the network uses; anything else takes the run-time-flag instance
-  const int epi = (a.stats_out ? 1 : 0) | (a.smstats_out ? 2 : 0) | (a.colstats_out ? 4 : 0) | (a.Res ? 8 : 0);
+  const bool defer = a.prologue == TC_PRO_SOFTMAX_DEFER;
+  LMPCR_REQUIRE(!defer || (a.a_blob && !a.b_blob && tc_fast_epilogue(a) && (a.K + KC - 1) / KC > STAGES && a.p0), LMPCR_ERR_ARG,
+                "tcgemm: deferred softmax needs a pre-split A, fp32 B, the row-store epilogue and more than %d K chunks", STAGES);
+  const int epi = (a.stats_out ? 1 : 0) | (a.smstats_out ? 2 : 0) | (a.colstats_out ? 4 : 0) | (a.Res ? 8 : 0) | (defer ? 16 : 0);
   typedef void (*kern_t)(TcGemmArgs, int);
   kern_t k = nullptr;
   if (a.b_kmajor) {
-    k = (epi == 1) ? tcgemm_kernel<true, 1> : tcgemm_kernel<true, -1>;
+    k = (epi == 1) ? tcgemm_kernel<true, 1> : (epi == 17) ? tcgemm_kernel<true, 17> : tcgemm_kernel<true, -1>;
   } else {
     switch (tc_fast_epilogue(a) ? epi : -1) {
       case 0: k = tcgemm_kernel<false, 0>; break;
@@ -715,6 +828,7 @@ int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
       case 4: k = tcgemm_kernel<false, 4>; break;
       case 8: k = tcgemm_kernel<false, 8>; break;
       case 9: k = tcgemm_kernel<false, 9>; break;
+      case 17: k = tcgemm_kernel<false, 17>; break;
       default: k = tcgemm_kernel<false, -1>; break;
     }
   }

@@ -6,7 +6,13 @@ namespace lmpcr {
 
 constexpr int TC_TILE_N = 64;   // output-tile width along j; the fused row statistics are per tile of this width
 
-enum TcPrologue { TC_PRO_NONE = 0, TC_PRO_AFFINE_RELU = 1, TC_PRO_SOFTMAX = 2 };
+// TC_PRO_SOFTMAX:       f(x) = exp(x - p0[j]) * p1[j]                       (max and 1/sum known before the launch)
+// TC_PRO_SOFTMAX_DEFER: f(x) = 2^(x*log2(e) - p0[j]), p0[j] = max_j * log2(e)  (= exp(x - max_j)); the producer warps accumulate sum_k f(B[k,j]) for the tile's columns while they
+//                       convert, and the epilogue divides column j by that sum: only the max has to be known up front
+// TC_PRO_SOFTMAX_DEFER needs more K chunks (of 32) than pipeline stages (3): the column sums of a tile are published while the
+// epilogue of the tile before the previous one is guaranteed to have finished
+constexpr int TC_DEFER_MIN_K = 3 * 32 + 1;
+enum TcPrologue { TC_PRO_NONE = 0, TC_PRO_AFFINE_RELU = 1, TC_PRO_SOFTMAX = 2, TC_PRO_SOFTMAX_DEFER = 3 };
 
 // C[p,i,j] = sum_k A[p,i,k] * f(B[p,k,j]) + bias[i] + Res[p,i,j]          (fp32 in / fp32 out)
 // evaluated as A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with bf16 operands (x = hi + lo, 16 significant bits) and fp32
@@ -30,8 +36,8 @@ struct TcGemmArgs {
                                                     // SOFTMAX: max / 1/sum indexed [p*p_batch + j]: f(x) = exp(x - p0[j]) * p1[j]
   // Optional fused statistics of the OUTPUT, written by the TMA epilogue (only when tc_fast_epilogue(args) holds):
   //   stats_out   [batch, M, ceil(N/TC_TILE_N), 2] = (mean, M2) of every row over the tile's valid columns  (InstanceNorm of the consumer)
-  //   smstats_out [batch, M, ceil(N/TC_TILE_N), 2] = (max, sum exp(x - max)) of every row over the tile       (softmax over the j axis)
-  //   colstats_out [batch, N, 4*ceil(M/128), 2] = (max, sum exp(x - max)) of every COLUMN over each 32-row slab        (softmax over the i axis)
+  //   smstats_out [batch, M, ceil(N/TC_TILE_N)] = max of every row over the tile                  (softmax over the j axis; the
+  //   colstats_out [batch, N, 4*ceil(M/128)]    = max of every COLUMN over each 32-row slab        sums come from TC_PRO_SOFTMAX_DEFER)
   float* stats_out; float* smstats_out; float* colstats_out;
   int M, N, K;
   int debug;   // timing experiments only (LMPCR_TC_DEBUG bit mask, see tcgemm.cu); 0 in production

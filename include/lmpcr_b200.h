@@ -131,6 +131,14 @@ int lmpcr_mutual_xs(const float* xyz, int n_pts, const int32_t* pairs, int n_pai
 int lmpcr_knn3d_1(const float* pos1, int n, const float* pos2, int m, int batch, int32_t* idx_out, float* sqdist_out,
                   void* stream);
 
+/* The pooling step of diff_pool alone (lib/filtering/oanet.py:107-109), exported like lmpcr_conv1x1 so that it can be timed and
+ * tested by itself:  out[p,c,k] = sum_n x[p,c,n] * softmax_n(embed[p,k,:])[n].   x [P,C,N], embed [P,K,N], out [P,C,K] fp32.
+ * tcgen05 split-bf16 GEMM with K = N points.  mode 0: softmax max / sum by a separate pass, normalised weights as operand;
+ * mode 1: deferred normalisation (sums accumulated by the operand producers, division in the epilogue; needs N >= 97). */
+size_t lmpcr_softmax_pool_workspace_bytes(int n_pairs, int channels, int clusters, int n_pts);
+int lmpcr_softmax_pool(const float* x, const float* embed, int n_pairs, int channels, int clusters, int n_pts, int mode, float* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Overlap ratio under an estimated pose (the check after stage 3 in scripts/benchmark_pairwise_registration.py:219).
  * Replaces the sklearn KD-tree queries of lib/utils.py:713-786 `compute_overlap_ratio`.

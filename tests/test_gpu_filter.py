@@ -131,3 +131,21 @@ def test_conv1x1_layer(P, cin, cout, N, res, algo):
     assert np.abs(out - ref).max() < (2e-5 if algo == 0 else 1e-4) * max(1.0, np.abs(ref).max())
     plain = cabi.conv1x1(cu(x), cu(w), gemm_algo=algo).cpu().numpy()
     assert np.abs(plain - np.einsum("oc,pcn->pon", w.astype(np.float64), x.astype(np.float64))).max() < 1e-4 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [200, 2000, 20000])
+def test_softmax_pool_modes_against_fp64(N):
+    """diff_pool's weighted sum alone (oanet.py:107-109) through lmpcr_softmax_pool: normalised operand vs deferred normalisation.
+    Gate 5e-5 relative to the largest output: split-bf16 products carry 2^-17 per operand, and reductions longer than 8192 points
+    are re-summed in round-to-nearest segments (tcgen05 accumulates with round-toward-zero)."""
+    rng = np.random.default_rng(N)
+    x = (rng.standard_normal((2, 128, N)) * 2 + 0.5).astype(np.float32)
+    E = (rng.standard_normal((2, 500, N)) * 3).astype(np.float32)
+    e64 = E.astype(np.float64)
+    S = np.exp(e64 - e64.max(2, keepdims=True))
+    S /= S.sum(2, keepdims=True)
+    ref = np.matmul(x.astype(np.float64), S.transpose(0, 2, 1))
+    for mode in (0, 1):
+        got = cabi.softmax_pool(cu(x), cu(E), mode).cpu().numpy()
+        assert np.abs(got - ref).max() < 5e-5 * np.abs(ref).max(), (N, mode)

@@ -48,13 +48,15 @@ def test_dense_50k_pair():
     o64 = O.oanet_forward(xs.cpu().numpy(), sd, dtype=np.float64)
     o32 = O.oanet_forward(xs.cpu().numpy(), sd, dtype=np.float32)
     # At N = 50,000 the fp32 evaluation itself (numpy restatement of the reference) is 3e-4 away from fp64 in the logits, 3x
-    # more than at N = 2000; the gate is 4x the fp32 restatement's own distance to fp64 (measured on B200: 2.5x / 3.7x / 2.3x).
+    # more than at N = 2000.  The tensor path cuts the 50,000-term pooling reduction into segments that are summed with
+    # round-to-nearest (tcgen05 accumulates with round-toward-zero: -1e-4 relative bias otherwise) and lands at 1.3e-4
+    # (measured on B200), i.e. closer to fp64 than the fp32 restatement; the gate is 2x the restatement's own distance.
     e_l = np.abs(o32["logits"][-1] - o64["logits"][-1]).max()
     e_r = O.chordal_angle(o32["rot_est"][-1], o64["rot_est"][-1]).max()
     e_t = np.abs(o32["trans_est"][-1] - o64["trans_est"][-1]).max()
-    assert np.abs(out["logits"][-1].cpu().numpy() - o64["logits"][-1]).max() < 4 * e_l + 1e-4
-    assert O.chordal_angle(out["rot_est"][-1].cpu().numpy(), o64["rot_est"][-1]).max() < 4 * e_r + 2e-4
-    assert np.abs(out["trans_est"][-1].cpu().numpy() - o64["trans_est"][-1]).max() < 4 * e_t + 5e-4
+    assert np.abs(out["logits"][-1].cpu().numpy() - o64["logits"][-1]).max() < 2 * e_l + 1e-4
+    assert O.chordal_angle(out["rot_est"][-1].cpu().numpy(), o64["rot_est"][-1]).max() < 2 * e_r + 2e-4
+    assert np.abs(out["trans_est"][-1].cpu().numpy() - o64["trans_est"][-1]).max() < 2 * e_t + 5e-4
     w = out["scores"][-1].cpu().numpy()
     Ro, to, reso, _ = O.kabsch(xs[:, 0, :, :3].cpu().numpy(), xs[:, 0, :, 3:].cpu().numpy(), w, dtype=np.float64)
     assert O.chordal_angle(out["rot_est"][-1].cpu().numpy(), Ro).max() < 1e-5

@@ -6,8 +6,9 @@ from oracle import lmpcr_oracle as O
 import synthdata
 from util import cabi, cu, load_oanet
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
-sd = synthdata.synth_state_dict(50)
-xs, _, _ = synthdata.synth_xs(1, N, seed=50)
+SEED = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+sd = synthdata.synth_state_dict(SEED)
+xs, _, _ = synthdata.synth_xs(1, N, seed=SEED)
 o64 = O.oanet_forward(xs, sd, dtype=np.float64)
 o32 = O.oanet_forward(xs, sd, dtype=np.float32)
 print("numpy fp32 vs fp64: logits %.2e" % np.abs(o32["logits"][-1] - o64["logits"][-1]).max())
