@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
     // the B rows (and the residual rows of the tile) into L2 with prefetch.global.L2.
     constexpr int PF_CHUNKS = 8;
     const bool pf_ok = !b_blob && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && ((g.b_ld & 3) == 0) && ((g.b_batch & 3) == 0);
-    const bool pf_res = g.Res && tc_fast_epilogue(g);
+    // The residual rows are NOT prefetched here: the epilogue's own TMA row copies run a whole tile ahead, and an L2 prefetch on
+    // top of them made DRAM fetch the residual tensor twice (ncu: 1.23 GB read instead of the algorithmic 0.76 GB per launch).
+    const bool pf_res = false;
     auto prefetch_chunk = [&](long long tile, int kc) {
       int p, mt, nt; decode(tile, p, mt, nt);
       const char* Bp = reinterpret_cast<const char*>(g.B + (long long)p * g.b_batch);
