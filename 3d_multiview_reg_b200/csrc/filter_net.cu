@@ -698,6 +698,8 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   for (int i = 0; i < N_PART; ++i) { part_buf[i] = take((size_t)C * tmax * 2); part_valid[i] = false; }
   float* sm_part = take((size_t)K * tmax * 2);
   float* col_part = take((size_t)N * 4 * ((K + 127) / 128) * 2);
+  const float* blob_out_for = nullptr;   // set around the conv that produces x1_1: its epilogue also writes the pool GEMM's A-operand blob
+  bool x11_blob_ready = false;
   bool want_col = false;   // set around the diff_unpool embedding conv: its epilogue emits softmax-over-clusters partials
   uint8_t* blob_x2 = reinterpret_cast<uint8_t*>(take(tc_weight_blob_bytes(C, K) / 4));
   uint8_t* blob_x11 = reinterpret_cast<uint8_t*>(take(tc_weight_blob_bytes(C, N) / 4));
@@ -772,6 +774,10 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       if (oi >= 0 && cout == C) {
         part_valid[oi] = tc_fast_epilogue(a);
         a.stats_out = part_valid[oi] ? part_buf[oi] : nullptr;
+      }
+      if (blob_out_for == out && cout == C && tc_fast_epilogue(a)) {
+        a.a_blob_out = blob_x11; a.a_blob_out_batch = (long long)tc_weight_blob_bytes(C, L);
+        x11_blob_ready = true;
       }
       if (want_sm && out == W.E && tc_fast_epilogue(a)) a.smstats_out = sm_part;
       if (want_col && out == W.E && tc_fast_epilogue(a)) a.colstats_out = col_part;   // softmax over points (diff_pool)
@@ -854,7 +860,9 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       for (int i = 0; i < half; ++i) {
         const bool fin = (i == half - 1);
         float* o = fin ? W.CAT : cur_out;
+        if (fin) { blob_out_for = W.CAT; x11_blob_ready = false; }
         LMPCR_TRY(pointcn(blk.l1_1[i], cur_in, CN, C, g, W.T2, nullptr, o, fin ? 2 * CN : CN));
+        blob_out_for = nullptr;
         if (!fin) { float* t = cur_in; cur_in = cur_out; cur_out = t; }
       }
       const float* x11 = W.CAT; const long long x11b = 2 * CN;
@@ -877,7 +885,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
           LMPCR_TRY(check_launch("softmax_rowstats_kernel"));
         }
         // A operand (x1_1) is shared by the 4 cluster tiles of a pair: split it once into bf16 hi/lo tiles
-        LMPCR_TRY(launch_split_weights(x11, C, N, blob_x11, st, g, x11b, N));
+        if (!x11_blob_ready) LMPCR_TRY(launch_split_weights(x11, C, N, blob_x11, st, g, x11b, N));   // else written by the producing conv's epilogue
         a.a_blob = blob_x11; a.a_blob_batch = (long long)tc_weight_blob_bytes(C, N);
         part_valid[part_index(W.XD0)] = tc_fast_epilogue(a);
         a.stats_out = part_valid[part_index(W.XD0)] ? part_buf[part_index(W.XD0)] : nullptr;

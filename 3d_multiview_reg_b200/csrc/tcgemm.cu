@@ -665,6 +665,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
             float* Cp = g.C + (long long)p * g.c_batch + nt * TN + col;
             const int ibase = mt * TM + quarter * 32;
             float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (g.a_blob_out) {
+              // the tile as hi/lo bf16 in the K-major A-operand layout of a GEMM with K = this GEMM's j axis: chunk = 32 columns,
+              // 8-row groups 512 B apart, 8-column groups 128 B apart, 16 B per row inside; columns past N (up to the end of the last
+              // chunk) are written as zeros so that the consumer's K padding multiplies finite values
+              const int jg = nt * TN + col, n_kc_out = (g.N + KC - 1) / KC;
+              if (jg < n_kc_out * KC) {
+                uint8_t* bb = g.a_blob_out + (long long)p * g.a_blob_out_batch + ((size_t)mt * n_kc_out + jg / KC) * 2 * A_OP_BYTES +
+                              ((jg % KC) >> 3) * K_LBO + (jg & 7) * 2;
+                const bool live = FULL || col < ncv;
+#pragma unroll 8
+                for (int r = sub; r < 32; r += 32 / LPR) {
+                  const int rt = quarter * 32 + r;                       // row inside the m-tile (rows past M are written as zeros too)
+                  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (live && (FULL || ibase + r < g.M)) o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 4 * col);
+                  const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+                  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                  const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+                  uint8_t* dsth = bb + (rt >> 3) * K_SBO + (rt & 7) * 16;
+                  *reinterpret_cast<uint2*>(dsth) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                  *reinterpret_cast<uint2*>(dsth + A_OP_BYTES) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+                }
+              }
+            }
             if (FULL || col < ncv) {
 #pragma unroll 8
               for (int r = sub; r < 32; r += 32 / LPR) {
@@ -809,6 +832,7 @@ int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
   }
   LMPCR_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && batch > 0, LMPCR_ERR_ARG, "tcgemm: bad sizes");
   LMPCR_REQUIRE(!a.b_blob || (a.a_blob && !a.b_kmajor), LMPCR_ERR_ARG, "tcgemm: b_blob needs a_blob and the j-major layout");
+  LMPCR_REQUIRE(!a.a_blob_out || tc_fast_epilogue(a), LMPCR_ERR_ARG, "tcgemm: a_blob_out needs the row-store epilogue");
   const long long tiles = (long long)batch * ((a.M + TM - 1) / TM) * ((a.N + TN - 1) / TN);
   LMPCR_REQUIRE(tiles < (1ll << 24), LMPCR_ERR_ARG, "tcgemm: too many tiles in one launch");
   const long long slots = 2ll * sm_count();          // two resident CTAs per SM

@@ -39,6 +39,9 @@ struct TcGemmArgs {
   //   smstats_out [batch, M, ceil(N/TC_TILE_N)] = max of every row over the tile                  (softmax over the j axis; the
   //   colstats_out [batch, N, 4*ceil(M/128)]    = max of every COLUMN over each 32-row slab        sums come from TC_PRO_SOFTMAX_DEFER)
   float* stats_out; float* smstats_out; float* colstats_out;
+  // Optional second copy of the OUTPUT as a pre-split A-operand blob (same format as launch_split_weights: the output matrix read as
+  // A[i, k = j]), so that a following GEMM that uses it as its A operand needs no separate split pass.  Row-store epilogue only.
+  uint8_t* a_blob_out; long long a_blob_out_batch;
   int M, N, K;
   int debug;   // timing experiments only (LMPCR_TC_DEBUG bit mask, see tcgemm.cu); 0 in production
 };
