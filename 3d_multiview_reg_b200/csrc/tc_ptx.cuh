@@ -18,31 +18,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Waits use try_wait WITH a suspend-time hint: ptxas turns it into TRYWAIT + NANOSLEEP.SYNCS, i.e. the warp sleeps in hardware
+// until the barrier's phase flips (or the hint expires) instead of spinning through issue slots that the working warps need.
+#ifndef LMPCR_MBAR_HINT_NS
+#define LMPCR_MBAR_HINT_NS 20000
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spin > (1u << 26)) __trap();   // a lost arrival becomes an error instead of a hung GPU
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(LMPCR_MBAR_HINT_NS) : "memory");
+    if (spin > (1u << 20)) __trap();   // a lost arrival becomes an error instead of a hung GPU (2^20 x 20 us = 21 s)
   }
 }
-// For waits that are off the critical path (a full ring): back off between polls so that the spinning warp does not take
-// issue slots from the warps doing the work.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done) __nanosleep(64);
-    if (spin > (1u << 24)) __trap();
-  }
-}
+// kept as a separate name for the waits that are off the critical path
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
