@@ -31,6 +31,7 @@ struct GemmArgs {
   const float* Res; long long r_batch;                 // same i/j strides as C (optional)
   const float* bias;                                   // [M] (optional)
   const float* scale; const float* shift; int aff_batch;  // prologue affine, index p*aff_batch + k (optional)
+  float* stats_out;                                    // optional [batch, M, ceil(N/64), 2] = (mean, M2) of every output row per 64-column tile
   int M, N, K;
 };
 
@@ -157,6 +158,7 @@ gemm_fused_kernel(GemmArgs g) {
           v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
         }
         *reinterpret_cast<float4*>(C + off) = v;
+        if (g.stats_out) { acc[r][4 * h] = v.x; acc[r][4 * h + 1] = v.y; acc[r][4 * h + 2] = v.z; acc[r][4 * h + 3] = v.w; }
       } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -165,6 +167,30 @@ gemm_fused_kernel(GemmArgs g) {
             float v = acc[r][4 * h + c] + bi;
             if (R) v += __ldg(R + off);
             C[off] = v;
+            acc[r][4 * h + c] = v;
+          }
+        }
+      }
+      if (g.stats_out) {
+        // InstanceNorm partials of the finished values for the consuming layer (same layout as the tensor-core GEMM's epilogue):
+        // the 64 columns of (row, half) live in the 16 lanes that share ty; two-pass mean / M2 over the valid columns
+        const int ncv = min(64, g.N - (j0 + h * 64));
+        if (ncv > 0) {
+          const unsigned hm = (tid & 16) ? 0xffff0000u : 0x0000ffffu;
+          float s1 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (tx * 4 + c < ncv) s1 += acc[r][4 * h + c];
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) s1 += __shfl_xor_sync(hm, s1, o);
+          const float mean = s1 / (float)ncv;
+          float m2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (tx * 4 + c < ncv) { const float d = acc[r][4 * h + c] - mean; m2 = fmaf(d, d, m2); }
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) m2 += __shfl_xor_sync(hm, m2, o);
+          if (tx == 0) {
+            const int tiles = (g.N + 63) / 64;
+            *reinterpret_cast<float2*>(g.stats_out + (((long long)p * g.M + gi) * tiles + (j0 + h * 64) / 64) * 2) = make_float2(mean, m2);
           }
         }
       }
@@ -809,6 +835,10 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     a.B = x; a.b_batch = xb; a.b_k = L; a.b_j = 1;
     a.C = out; a.c_batch = ob; a.c_i = L; a.c_j = 1;
     a.bias = cv.b; a.M = cout; a.N = L; a.K = cin;
+    {   // conv1 runs here in fp32 also on the tensor path: let it emit the InstanceNorm partials its consumer wants
+      const int oi = part_index(out);
+      if (tc && oi >= 0 && cout == C) { a.stats_out = part_buf[oi]; part_valid[oi] = true; }
+    }
     return gemm(a, g, st);
   };
   // PointCN (oanet.py:18-43): out = conv2(f(conv1(f(x)))) + (shot_cut(x) | x)
