@@ -724,6 +724,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   for (int i = 0; i < N_PART; ++i) { part_buf[i] = take((size_t)C * tmax * 2); part_valid[i] = false; }
   float* sm_part = take((size_t)K * tmax * 2);
   float* col_part = take((size_t)N * 4 * ((K + 127) / 128) * 2);
+  struct { const float* out; const float* w; const float* b; float* logits; float* scores; int32_t* anypos; bool store; bool done; } head = {};
   const float* blob_out_for = nullptr;   // set around the conv that produces x1_1: its epilogue also writes the pool GEMM's A-operand blob
   bool x11_blob_ready = false;
   bool want_col = false;   // set around the diff_unpool embedding conv: its epilogue emits softmax-over-clusters partials
@@ -800,6 +801,15 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       if (oi >= 0 && cout == C) {
         part_valid[oi] = tc_fast_epilogue(a);
         a.stats_out = part_valid[oi] ? part_buf[oi] : nullptr;
+      }
+      if (head.out == out && cout == C && C <= 128 && tc_fast_epilogue(a)) {
+        // last layer of the block: the 128 -> 1 output conv, tanh / relu and the any-positive flag ride on its epilogue (oanet.py:173-175);
+        // nobody normalises this output, and unless the caller wants the latent features it is not even stored
+        a.lg_w = head.w; a.lg_b = head.b; a.lg_logits = head.logits; a.lg_scores = head.scores; a.lg_anypos = head.anypos;
+        a.stats_out = nullptr;
+        if (oi >= 0) part_valid[oi] = false;
+        if (!head.store) a.C = nullptr;
+        head.done = true;
       }
       if (blob_out_for == out && cout == C && tc_fast_epilogue(a)) {
         a.a_blob_out = blob_x11; a.a_blob_out_batch = (long long)tc_weight_blob_bytes(C, L);
@@ -994,21 +1004,30 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       }
       // l1_2 (oanet.py:171): PointCN(2C -> C) with shot_cut, then half-1 PointCN(C); T1/T0 ping-pong, T2 = temp
       float* lat_dst = (last && latent) ? latent + (size_t)p0 * CN : nullptr;
+      auto arm_head = [&](const float* o) {
+        head.out = o; head.w = blk.output.w; head.b = blk.output.b; head.logits = logits_it + (size_t)p0 * N;
+        head.scores = scores_it + (size_t)p0 * N; head.anypos = anypos + p0; head.store = lat_dst != nullptr; head.done = false;
+      };
       {
         float* o = (half == 1 && lat_dst) ? lat_dst : W.T1;
+        if (half == 1) arm_head(o);
         LMPCR_TRY(pointcn(blk.l1_2[0], W.CAT, 2 * CN, 2 * C, g, W.T2, W.T0, o, CN));
         cur_in = o; cur_out = W.T0;
       }
       for (int i = 1; i < half; ++i) {
         float* o = (i == half - 1 && lat_dst) ? lat_dst : cur_out;
+        if (i == half - 1) arm_head(o);
         LMPCR_TRY(pointcn(blk.l1_2[i], cur_in, CN, C, g, W.T2, nullptr, o, CN));
         cur_out = cur_in;   // the buffer just consumed becomes the next destination
         cur_in = o;
       }
-      // output conv + weights (oanet.py:173-175)
-      logits_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cur_in, CN, C, N, g, blk.output.w, blk.output.b, logits_it + (size_t)p0 * N,
-                                                                  scores_it + (size_t)p0 * N, anypos + p0);
-      LMPCR_TRY(check_launch("logits_kernel"));
+      head.out = nullptr;
+      // output conv + weights (oanet.py:173-175): fused into the last layer's epilogue on the tensor path, else a kernel of its own
+      if (!head.done) {
+        logits_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cur_in, CN, C, N, g, blk.output.w, blk.output.b, logits_it + (size_t)p0 * N,
+                                                                    scores_it + (size_t)p0 * N, anypos + p0);
+        LMPCR_TRY(check_launch("logits_kernel"));
+      }
     }
     // zero-weight guard (oanet.py:177-178) + weighted Kabsch (oanet.py:182-183) for all pairs of the call
     if (cfg->guard_mode == LMPCR_GUARD_BATCH) {

@@ -544,7 +544,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
     const bool f_sm = RT ? (g.smstats_out != nullptr) : ((EPI & 2) != 0);
     const bool f_col = RT ? (g.colstats_out != nullptr) : ((EPI & 4) != 0);
     const bool f_res = RT ? (g.Res != nullptr) : ((EPI & 8) != 0);
-    const bool f_cs = RT ? defer : ((EPI & 16) != 0);                  // divide column j by the producers' sum (deferred softmax)
+    const bool f_cs = RT ? defer : ((EPI & 16) != 0);
+    const bool f_lg = RT ? (g.lg_w != nullptr) : ((EPI & 32) != 0);       // fused 1-channel head (logits / scores)                  // divide column j by the producers' sum (deferred softmax)
     if (fast) {
       // Fast path (rows contiguous along j, 16-byte friendly).  Phase 1, thread = row: the residual row was prefetched by
       // TMA into this thread's staged row (own mbarrier); accumulator + bias + residual are combined in place and the row
@@ -662,7 +663,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
           {
             constexpr int LPR = TN / 4;                 // lanes per row (16): a warp instruction stores 32/LPR rows
             const int sub = lane / LPR, col = 4 * (lane % LPR);
-            float* Cp = g.C + (long long)p * g.c_batch + nt * TN + col;
+            float* Cp = g.C ? g.C + (long long)p * g.c_batch + nt * TN + col : nullptr;
             const int ibase = mt * TM + quarter * 32;
             float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             if (g.a_blob_out) {
@@ -688,14 +689,39 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
                 }
               }
             }
+            float la[4] = {0.f, 0.f, 0.f, 0.f};          // fused head: this lane's share of sum_i w[i] * C[i, col..col+3]
             if (FULL || col < ncv) {
 #pragma unroll 8
               for (int r = sub; r < 32; r += 32 / LPR) {
                 if (FULL || ibase + r < g.M) {
                   const float4 o = *reinterpret_cast<const float4*>(warp_rows + (size_t)r * STG_ROW + 4 * col);
-                  __stcs(reinterpret_cast<float4*>(Cp + (long long)(ibase + r) * g.c_i), o);
+                  if (!f_lg || g.C) __stcs(reinterpret_cast<float4*>(Cp + (long long)(ibase + r) * g.c_i), o);
                   if (f_col) { cm[0] = fmaxf(cm[0], o.x); cm[1] = fmaxf(cm[1], o.y); cm[2] = fmaxf(cm[2], o.z); cm[3] = fmaxf(cm[3], o.w); }
+                  if (f_lg) {
+                    const float wv = __ldg(g.lg_w + ibase + r);
+                    la[0] = fmaf(wv, o.x, la[0]); la[1] = fmaf(wv, o.y, la[1]); la[2] = fmaf(wv, o.z, la[2]); la[3] = fmaf(wv, o.w, la[3]);
+                  }
                 }
+              }
+            }
+            if (f_lg) {
+              // even / odd rows of the warp -> the four warps of the tile -> logit, score (fixed order: deterministic)
+              float* lp = zpart + tpar_e * 4 * TN;        // [4 warps][TN] partial sums; the deferred-softmax slots are free here
+#pragma unroll
+              for (int e = 0; e < 4; ++e) la[e] += __shfl_xor_sync(0xffffffffu, la[e], LPR);
+              if (sub == 0) *reinterpret_cast<float4*>(lp + quarter * TN + col) = make_float4(la[0], la[1], la[2], la[3]);
+              asm volatile("bar.sync 2, 128;" ::: "memory");      // the four epilogue warps
+              if (quarter == 0 && sub == 0 && (FULL || col < ncv)) {
+                const float4 p0 = *reinterpret_cast<const float4*>(lp + col), p1 = *reinterpret_cast<const float4*>(lp + TN + col);
+                const float4 p2 = *reinterpret_cast<const float4*>(lp + 2 * TN + col), p3 = *reinterpret_cast<const float4*>(lp + 3 * TN + col);
+                const float b = __ldg(g.lg_b);
+                const float4 lg = make_float4(((p0.x + p1.x) + (p2.x + p3.x)) + b, ((p0.y + p1.y) + (p2.y + p3.y)) + b,
+                                              ((p0.z + p1.z) + (p2.z + p3.z)) + b, ((p0.w + p1.w) + (p2.w + p3.w)) + b);
+                const float4 sc = make_float4(fmaxf(tanhf(lg.x), 0.f), fmaxf(tanhf(lg.y), 0.f), fmaxf(tanhf(lg.z), 0.f), fmaxf(tanhf(lg.w), 0.f));
+                const long long o = (long long)p * g.N + nt * TN + col;
+                *reinterpret_cast<float4*>(g.lg_logits + o) = lg;
+                *reinterpret_cast<float4*>(g.lg_scores + o) = sc;
+                if (sc.x > 0.f || sc.y > 0.f || sc.z > 0.f || sc.w > 0.f) g.lg_anypos[p] = 1;
               }
             }
             if (f_col) {
@@ -841,7 +867,10 @@ int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
   const bool defer = a.prologue == TC_PRO_SOFTMAX_DEFER;
   LMPCR_REQUIRE(!defer || (a.a_blob && !a.b_blob && tc_fast_epilogue(a) && (a.K + KC - 1) / KC > STAGES && a.p0), LMPCR_ERR_ARG,
                 "tcgemm: deferred softmax needs a pre-split A, fp32 B, the row-store epilogue and more than %d K chunks", STAGES);
-  const int epi = (a.stats_out ? 1 : 0) | (a.smstats_out ? 2 : 0) | (a.colstats_out ? 4 : 0) | (a.Res ? 8 : 0) | (defer ? 16 : 0);
+  LMPCR_REQUIRE(!a.lg_w || (a.M <= TM && !defer && a.lg_b && a.lg_logits && a.lg_scores && a.lg_anypos && (a.c_i & 3) == 0 && (a.N & 3) == 0 &&
+                            (!a.Res || tc_fast_epilogue(a))), LMPCR_ERR_ARG, "tcgemm: the fused head needs M <= 128 and the row-store epilogue");
+  LMPCR_REQUIRE(a.C || a.lg_w, LMPCR_ERR_ARG, "tcgemm: no output");
+  const int epi = (a.stats_out ? 1 : 0) | (a.smstats_out ? 2 : 0) | (a.colstats_out ? 4 : 0) | (a.Res ? 8 : 0) | (defer ? 16 : 0) | (a.lg_w ? 32 : 0);
   typedef void (*kern_t)(TcGemmArgs, int);
   kern_t k = nullptr;
   if (a.b_kmajor) {
@@ -855,6 +884,7 @@ int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
       case 8: k = tcgemm_kernel<false, 8>; break;
       case 9: k = tcgemm_kernel<false, 9>; break;
       case 17: k = tcgemm_kernel<false, 17>; break;
+      case 40: k = tcgemm_kernel<false, 40>; break;
       default: k = tcgemm_kernel<false, -1>; break;
     }
   }

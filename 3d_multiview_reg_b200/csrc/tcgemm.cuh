@@ -42,6 +42,10 @@ struct TcGemmArgs {
   // Optional second copy of the OUTPUT as a pre-split A-operand blob (same format as launch_split_weights: the output matrix read as
   // A[i, k = j]), so that a following GEMM that uses it as its A operand needs no separate split pass.  Row-store epilogue only.
   uint8_t* a_blob_out; long long a_blob_out_batch;
+  // Optional fused 1-channel head on the OUTPUT (the network's `output` conv + weights, oanet.py:173-175), M <= 128 only:
+  //   logit[p,j] = sum_i lg_w[i] * C[p,i,j] + lg_b[0];  lg_logits / lg_scores [batch, N] (score = relu(tanh(logit)));  lg_anypos[p] is
+  //   set to 1 when any score of pair p is positive.  With the head present C may be NULL: the tile itself is then not stored.
+  const float* lg_w; const float* lg_b; float* lg_logits; float* lg_scores; int32_t* lg_anypos;
   int M, N, K;
   int debug;   // timing experiments only (LMPCR_TC_DEBUG bit mask, see tcgemm.cu); 0 in production
 };
