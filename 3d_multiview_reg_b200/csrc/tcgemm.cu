@@ -179,8 +179,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
   const int FL = (n_kc > 256 && !g.Res && tc_fast_epilogue(g)) ? 32 : n_kc;
   const int n_seg = (n_kc + FL - 1) / FL;
 
+  // the lean producer loop (see the producer warps below) hands a stage over with four warp arrivals instead of eight
+  const bool lean_shape = a_blob && !b_blob && !(g.debug & 512) && ((reinterpret_cast<uintptr_t>(g.B) & 31) == 0) && ((g.b_ld & 7) == 0) &&
+                          ((g.b_batch & 7) == 0);
+  const bool lean = lean_shape && (B_KMAJOR ? (g.prologue == TC_PRO_SOFTMAX_DEFER && (g.K & 7) == 0)
+                                            : ((g.prologue == TC_PRO_NONE || g.prologue == TC_PRO_AFFINE_RELU || g.prologue == TC_PRO_SOFTMAX_DEFER) &&
+                                               (g.N & 7) == 0 && (g.prologue != TC_PRO_SOFTMAX_DEFER || ((reinterpret_cast<uintptr_t>(g.p0) & 31) == 0 && (g.p_batch & 7) == 0))));
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), b_blob ? 1 : N_PROD_WARPS + (a_blob ? 1 : 0)); mbar_init(EMPTY(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), b_blob ? 1 : (lean ? N_PROD_WARPS / 2 : N_PROD_WARPS) + (a_blob ? 1 : 0)); mbar_init(EMPTY(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(T_FULL(a), 1); mbar_init(T_EMPTY(a), 128); }
   }
   if (threadIdx.x < 128) mbar_init(smem_u32(rowbars + threadIdx.x), 1);
@@ -315,75 +321,91 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
       }
     }
   } else if (warp >= FIRST_PROD_WARP) {
-    // Lean producer loop for the shapes the network runs at scale (pre-split A, 32-byte aligned B rows, whole 8-element groups):
-    // everything that is invariant per thread (shared-memory offset, element coordinates) or per tile (row pointer, softmax maxima) is
-    // hoisted, the fetch cursor advances by pointer increments, and validity is one predicate per thread -- ~75 instructions per chunk
-    // and warp instead of ~220 in the general loop below (the class-A layers are issue-bound in the producers).
-    // Same arithmetic and the same shared-memory image as the general loop.
-    const bool lean_shape = a_blob && !b_blob && !(g.debug & (256 | 512)) && ((reinterpret_cast<uintptr_t>(g.B) & 31) == 0) && ((g.b_ld & 7) == 0) &&
-                            ((g.b_batch & 7) == 0);
-    const bool lean = lean_shape && (B_KMAJOR ? (g.prologue == TC_PRO_SOFTMAX_DEFER && (g.K & 7) == 0)
-                                              : ((g.prologue == TC_PRO_NONE || g.prologue == TC_PRO_AFFINE_RELU || g.prologue == TC_PRO_SOFTMAX_DEFER) &&
-                                                 (g.N & 7) == 0 && (g.prologue != TC_PRO_SOFTMAX_DEFER || ((reinterpret_cast<uintptr_t>(g.p0) & 31) == 0 && (g.p_batch & 7) == 0))));
+    // Lean producer loop for the shapes the network runs at scale (pre-split A, 32-byte aligned B rows, whole 8-element groups).
+    // Everything that is invariant per thread (shared-memory offset, element coordinates) or per tile (row pointer, softmax maxima) is
+    // hoisted and the fetch cursor advances by pointer increments.  The eight producer warps form TWO GROUPS of four that take
+    // alternate chunks (group g: chunks g, g+2, ... of the CTA's chunk sequence): a thread converts two 8-element blocks per chunk and
+    // keeps two 256-bit loads in flight, and both groups have loads in flight at the same time.  fence.proxy.async is a
+    // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: it waits for the thread's outstanding loads, so a thread cannot prefetch across its own
+    // fence -- alternating groups double the bytes in flight per SM without that and halve the fences per element.
+    // Same arithmetic and the same shared-memory image as the general loop below.
     if (lean) {
-      static_assert(TN == 64 && KC == 32 && N_PROD_WARPS == 8, "lean producer: one 8 x 32 block per warp and chunk");
+      static_assert(TN == 64 && KC == 32 && N_PROD_WARPS == 8 && STAGES == 3, "lean producer: two groups of four warps, 8 x 32 blocks");
       const int pw = warp - FIRST_PROD_WARP;
+      const int grp = pw >> 2, pwg = pw & 3;
       const int l8 = lane & 7, g4 = lane >> 3;
       const bool affine = g.prologue == TC_PRO_AFFINE_RELU;
-      // thread coordinates inside a chunk: (row, first of 8 contiguous elements) and the matching offset in the UMMA image
-      const int row_l = B_KMAJOR ? pw * 8 + l8 : (pw >> 1) * 8 + l8;              // k-major: j inside the tile;  j-major: k inside the chunk
-      const int col_l = B_KMAJOR ? g4 * 8 : (pw & 1) * 32 + g4 * 8;               // k-major: k inside the chunk; j-major: j inside the tile
-      uint32_t sm_off = 2 * A_OP_BYTES + (B_KMAJOR ? pw * K_SBO + g4 * K_LBO + l8 * 16
-                                                   : ((pw & 1) * 4 + g4) * MN_SBO + (pw >> 1) * MN_LBO + l8 * 16);
+      // block u (0, 1) of this thread inside a chunk = warp-iteration it = pwg + 4u of the general loop:
+      //   j-major: k = (pwg>>1)*8 + 16u + l8, j = (pwg&1)*32 + g4*8 ..+8      k-major: j = pwg*8 + 32u + l8, k = g4*8 ..+8
+      const int row_l = B_KMAJOR ? pwg * 8 + l8 : (pwg >> 1) * 8 + l8;
+      const int col_l = B_KMAJOR ? g4 * 8 : (pwg & 1) * 32 + g4 * 8;
+      constexpr int ROW_U = B_KMAJOR ? 32 : 16;                                    // rows between the two blocks
+      constexpr uint32_t SM_U = B_KMAJOR ? 4 * K_SBO : 2 * MN_LBO;                 // bytes between the two blocks in the UMMA image
+      uint32_t sm_off = 2 * A_OP_BYTES + (B_KMAJOR ? pwg * K_SBO + g4 * K_LBO + l8 * 16
+                                                   : ((pwg & 1) * 4 + g4) * MN_SBO + (pwg >> 1) * MN_LBO + l8 * 16);
       unsigned nt32 = (unsigned)n_tiles;                      // < 2^24 (checked on the host)
-      asm volatile("" : "+r"(sm_off), "+r"(nt32));            // opaque: kept in registers instead of being re-derived from %tid / the arguments per chunk
-      const long long cstride = B_KMAJOR ? (long long)KC : (long long)KC * g.b_ld;   // floats between consecutive chunks of a tile
-      // ---- fetch cursor: one chunk ahead of the consume loop ----
-      unsigned f_tile = blockIdx.x; int f_kc = 0;
-      const float* f_src = nullptr; const float* f_q = nullptr; bool f_tile_ok = false;
-      auto f_setup = [&]() {
+      asm volatile("" : "+r"(sm_off), "+r"(nt32));            // opaque: kept in registers instead of being re-derived per chunk
+      const long long cstride2 = 2 * (B_KMAJOR ? (long long)KC : (long long)KC * g.b_ld);   // floats between this group's consecutive chunks
+      const long long ustride = (long long)ROW_U * g.b_ld;                                    // floats between the two blocks
+      // position p = (tile, kc) -> position two chunks later in the CTA's chunk sequence
+      auto advance = [&](unsigned& t, int& k) {
+        k += 2;
+        while (k >= n_kc && t < nt32) { k -= n_kc; t += gridDim.x; }
+      };
+      // ---- fetch cursor: one step (= two chunks) ahead of the consume loop ----
+      unsigned f_tile = blockIdx.x; int f_kc = grp - 2;
+      advance(f_tile, f_kc);
+      const float* f_src = nullptr; const float* f_q = nullptr; bool f_ok0 = false, f_ok1 = false;
+      auto f_setup = [&]() {                                  // pointers of chunk f_kc of tile f_tile
         int fp, fmt, fnt; decode(f_tile, fp, fmt, fnt);
         if (B_KMAJOR) {
           const int j = fnt * TN + row_l;
-          f_tile_ok = j < g.N;
-          f_src = g.B + (long long)fp * g.b_batch + (long long)j * g.b_ld + col_l;
+          f_ok0 = j < g.N; f_ok1 = j + ROW_U < g.N;
+          f_src = g.B + (long long)fp * g.b_batch + (long long)j * g.b_ld + col_l + (long long)f_kc * KC;
         } else {
           const int j0 = fnt * TN + col_l;
-          f_tile_ok = j0 < g.N;
-          f_src = g.B + (long long)fp * g.b_batch + (long long)row_l * g.b_ld + j0;
-          if (affine) f_q = g.p0 + (long long)fp * g.p_batch + row_l;
+          f_ok0 = f_ok1 = j0 < g.N;
+          f_src = g.B + (long long)fp * g.b_batch + ((long long)f_kc * KC + row_l) * g.b_ld + j0;
+          if (affine) f_q = g.p0 + (long long)fp * g.p_batch + f_kc * KC + row_l;
         }
       };
-      float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      float sc = 1.f, sh = 0.f;
-      bool valid = false;
+      float x0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, x1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float sc0 = 1.f, sh0 = 0.f, sc1 = 1.f, sh1 = 0.f;
+      bool valid0 = false, valid1 = false;
       auto fetch = [&]() {
         if (f_tile >= nt32) return;
-        valid = f_tile_ok && (f_kc * KC + (B_KMAJOR ? col_l : row_l) < g.K);
-        if (valid) {
-          ldg256(f_src, x);
-          if (affine) { sc = __ldg(f_q); sh = __ldg(f_q + (g.p1 - g.p0)); }
+        const int kb = f_kc * KC;
+        valid0 = f_ok0 && (kb + (B_KMAJOR ? col_l : row_l) < g.K);
+        valid1 = f_ok1 && (kb + (B_KMAJOR ? col_l : row_l + ROW_U) < g.K);
+        if (valid0) ldg256(f_src, x0);
+        if (valid1) ldg256(f_src + ustride, x1);
+        if (affine) {
+          const long long dq = g.p1 - g.p0;
+          if (valid0) { sc0 = __ldg(f_q); sh0 = __ldg(f_q + dq); }
+          if (valid1) { sc1 = __ldg(f_q + ROW_U); sh1 = __ldg(f_q + ROW_U + dq); }
         }
-        if (++f_kc == n_kc) {
-          f_kc = 0; f_tile += gridDim.x;
-          if (f_tile < nt32) f_setup();
-        } else {
-          f_src += cstride;
-          if (affine) f_q += KC;
-        }
+        const unsigned t_old = f_tile;
+        advance(f_tile, f_kc);
+        if (f_tile != t_old) { if (f_tile < nt32) f_setup(); }
+        else { f_src += cstride2; if (affine) f_q += 2 * KC; }
       };
       if (f_tile < nt32) f_setup();
       fetch();
-      float zacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float zacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // k-major uses [0] (block 0's row) and [1] (block 1's row)
       float mm[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      int tpar = 0, stage = 0; uint32_t phase = 0;
-      for (unsigned tile = blockIdx.x; tile < nt32; tile += gridDim.x) {
-        if (defer) {             // maxima (pre-scaled by log2 e) of this thread's row / 8 columns: constant over the tile's chunks
+      int tpar = 0, stage = grp; uint32_t phase = 0;
+      unsigned tile = blockIdx.x; int kc = grp - 2;
+      advance(tile, kc);
+      unsigned mm_tile = 0xffffffffu;
+      while (tile < nt32) {
+        if (defer && tile != mm_tile) {   // maxima (pre-scaled by log2 e) of this thread's rows / 8 columns: constant over the tile's chunks
+          mm_tile = tile;
           int p, mt, nt; decode(tile, p, mt, nt);
           const float* q0 = g.p0 + (long long)p * g.p_batch;
           if (B_KMAJOR) {
             const int j = nt * TN + row_l;
             mm[0] = (j < g.N) ? __ldg(q0 + j) : 0.f;
+            mm[1] = (j + ROW_U < g.N) ? __ldg(q0 + j + ROW_U) : 0.f;
           } else {
             const int j0 = nt * TN + col_l;
             if (j0 < g.N) {
@@ -392,50 +414,87 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
             }
           }
         }
-        for (int kc = 0; kc < n_kc; ++kc) {
-          mbar_wait_relaxed(EMPTY(stage), phase ^ 1);
-          if (valid) {
-            if (defer) {
-              if (B_KMAJOR) {
+        TC_PROF(6, tp);
+        mbar_wait_relaxed(EMPTY(stage), phase ^ 1);
+        TC_PROF(3, tp);
+        if (defer) {
+          if (B_KMAJOR) {
+            if (valid0) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = exp2f_fast(fmaf(x[e], LOG2E, -mm[0]));
-                zacc[0] += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
-              } else {
+              for (int e = 0; e < 8; ++e) x0[e] = exp2f_fast(fmaf(x0[e], LOG2E, -mm[0]));
+              zacc[0] += ((x0[0] + x0[1]) + (x0[2] + x0[3])) + ((x0[4] + x0[5]) + (x0[6] + x0[7]));
+            }
+            if (valid1) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { x[e] = exp2f_fast(fmaf(x[e], LOG2E, -mm[e])); zacc[e] += x[e]; }
-              }
-            } else if (affine) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], sc, sh), 0.f);
+              for (int e = 0; e < 8; ++e) x1[e] = exp2f_fast(fmaf(x1[e], LOG2E, -mm[1]));
+              zacc[1] += ((x1[0] + x1[1]) + (x1[2] + x1[3])) + ((x1[4] + x1[5]) + (x1[6] + x1[7]));
             }
           } else {
+            if (valid0) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = 0.f;
-          }
-          uint8_t* dst = smem + (size_t)stage * STAGE_BYTES + sm_off;
-          split8_store(x, dst, dst + B_OP_BYTES);
-          if (defer && kc == n_kc - 1) {        // publish the column sums of the tile (same slots and order as the general loop)
-            float* zp = zpart + tpar * 4 * TN;
-            if (B_KMAJOR) {
-              zp[g4 * TN + pw * 8 + l8] = zacc[0];
-              zacc[0] = 0.f;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float v = zacc[e];
-                v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
-                if (l8 == 0) zp[(pw >> 1) * TN + (pw & 1) * 32 + g4 * 8 + e] = v;
-                zacc[e] = 0.f;
-              }
+              for (int e = 0; e < 8; ++e) { x0[e] = exp2f_fast(fmaf(x0[e], LOG2E, -mm[e])); zacc[e] += x0[e]; }
             }
-            tpar ^= 1;
+            if (valid1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { x1[e] = exp2f_fast(fmaf(x1[e], LOG2E, -mm[e])); zacc[e] += x1[e]; }
+            }
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(FULL(stage));
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          fetch();
+        } else if (affine) {
+          if (valid0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x0[e] = fmaxf(fmaf(x0[e], sc0, sh0), 0.f);
+          }
+          if (valid1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x1[e] = fmaxf(fmaf(x1[e], sc1, sh1), 0.f);
+          }
         }
+        if (!valid0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x0[e] = 0.f;
+        }
+        if (!valid1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x1[e] = 0.f;
+        }
+        uint8_t* dst = smem + (size_t)stage * STAGE_BYTES + sm_off;
+        split8_store(x0, dst, dst + B_OP_BYTES);
+        split8_store(x1, dst + SM_U, dst + SM_U + B_OP_BYTES);
+        unsigned n_tile = tile; int n_kc2 = kc;
+        advance(n_tile, n_kc2);
+        if (defer && n_tile != tile) {
+          // this group's last chunk of the tile: publish its share of the column sums.  Four slots per column, fixed owners and a fixed
+          // summation order in the epilogue => deterministic.  The epilogue reads them after T_FULL, which the MMA warp commits only
+          // after it has seen the arrive below of both groups.
+          float* zp = zpart + tpar * 4 * TN;
+          if (B_KMAJOR) {          // rows pwg*8+l8 (+32); the four k-octets (g4) fold pairwise, slot = group*2 + (g4>>1)
+            float v0 = zacc[0], v1 = zacc[1];
+            v0 += __shfl_xor_sync(0xffffffffu, v0, 8); v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
+            if ((g4 & 1) == 0) {
+              zp[(grp * 2 + (g4 >> 1)) * TN + row_l] = v0;
+              zp[(grp * 2 + (g4 >> 1)) * TN + row_l + ROW_U] = v1;
+            }
+            zacc[0] = 0.f; zacc[1] = 0.f;
+          } else {                 // columns col_l+e; both blocks and the eight rows (l8) fold, slot = group*2 + (pwg>>1)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float v = zacc[e];
+              v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+              if (l8 == 0) zp[(grp * 2 + (pwg >> 1)) * TN + col_l + e] = v;
+              zacc[e] = 0.f;
+            }
+          }
+          tpar ^= 1;
+        }
+        TC_PROF(4, tp);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(FULL(stage));
+        stage += 2;
+        if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
+        TC_PROF(5, tp);
+        fetch();
+        tile = n_tile; kc = n_kc2;
       }
     } else if (!b_blob) {
     // ===================== operand producers (general loop) =====================
