@@ -222,11 +222,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
     // ===================== TMA producer for the weight blob + L2 prefetcher =====================
     // The activations of a group of pairs do not fit L2; this warp runs PF_CHUNKS chunks ahead of the pipeline and pulls
     // the B rows (and the residual rows of the tile) into L2 with prefetch.global.L2.
-    constexpr int PF_CHUNKS = 8;
+    constexpr int PF_CHUNKS = 4;     // measured on B200: 4 beats 8 (class-A layer with residual 448 -> 413 us), 16 and 24 thrash L2 (555 us)
     const bool pf_ok = !b_blob && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && ((g.b_ld & 3) == 0) && ((g.b_batch & 3) == 0);
     // The residual rows are NOT prefetched here: the epilogue's own TMA row copies run a whole tile ahead, and an L2 prefetch on
     // top of them made DRAM fetch the residual tensor twice (ncu: 1.23 GB read instead of the algorithmic 0.76 GB per launch).
-    const bool pf_res = false;
+    // The residual rows are NOT prefetched by default (LMPCR_TC_DEBUG bit 13 turns it on): measured twice, with the TMA row copies
+    // (DRAM fetched the residual twice: 1.23 GB instead of 0.76 GB read per launch) and with the cp.async copies (430 -> 455 us).
+    const bool pf_res = g.Res != nullptr && (g.debug & 8192) && !(g.debug & 4096) && tc_fast_epilogue(g);
     auto prefetch_chunk = [&](long long tile, int kc) {
       int p, mt, nt; decode(tile, p, mt, nt);
       const char* Bp = reinterpret_cast<const char*>(g.B + (long long)p * g.b_batch);
@@ -260,7 +262,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
       if (!(g.debug & 128)) prefetch_chunk(pf_tile, pf_kc);
       if (++pf_kc == n_kc) { pf_kc = 0; pf_tile += gridDim.x; }
     };
-    for (int i = 0; i < PF_CHUNKS; ++i) pf_advance();
+    const int pf_sel = (g.debug >> 10) & 3;                 // timing experiments: prefetch distance 4 (default) / 8 / 2 / 6 chunks
+    const int pf_chunks = pf_sel == 0 ? PF_CHUNKS : pf_sel == 1 ? 8 : pf_sel == 2 ? 2 : 6;
+    for (int i = 0; i < pf_chunks; ++i) pf_advance();
     int stage = 0; uint32_t phase = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       int p, mt, nt; decode(tile, p, mt, nt);
@@ -736,16 +740,36 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
       const uint32_t my_bar = smem_u32(rowbars + r_own);
       uint32_t par = 0;
       bool pending = false;
+      // Residual tile -> staged rows.  Default: Ampere-style cp.async (LDGSTS, generic proxy) in the coalesced phase-2 mapping -- 16
+      // copies of 16 bytes per lane, no mbarrier, no proxy fence; the warp's own wait_group + __syncwarp publishes them to the row
+      // owners.  LMPCR_TC_DEBUG bit 12 selects the earlier scheme, one TMA bulk copy per thread and row: ptxas serialises a warp's 32
+      // bulk copies (uniform operands; ~480 instructions per warp and tile) and the proxy fence in front of them is a MEMBAR.ALL.CTA
+      // that waits for the tile's global stores -- both sat on the epilogue's critical path (45 % of its time on residual layers).
+      const bool res_tma = (g.debug & 4096) != 0;
       auto prefetch = [&](long long tile) {
         pending = false;
         if (!f_res || tile >= n_tiles) return;
         int p, mt, nt; decode(tile, p, mt, nt);
-        const int i = mt * TM + r_own;
-        const int nc = (i < g.M) ? min(TN, g.N - nt * TN) : 0;
-        if (nc > 0) {
-          pending = true;
-          mbar_expect_tx(my_bar, nc * 4);
-          bulk_g2s(smem_u32(my_row), g.Res + (long long)p * g.r_batch + (long long)i * g.c_i + nt * TN, nc * 4, my_bar);
+        if (res_tma) {
+          const int i = mt * TM + r_own;
+          const int nc = (i < g.M) ? min(TN, g.N - nt * TN) : 0;
+          if (nc > 0) {
+            pending = true;
+            mbar_expect_tx(my_bar, nc * 4);
+            bulk_g2s(smem_u32(my_row), g.Res + (long long)p * g.r_batch + (long long)i * g.c_i + nt * TN, nc * 4, my_bar);
+          }
+        } else {
+          pending = (mt * TM + r_own) < g.M;
+          const int sub = lane >> 4, col = 4 * (lane & 15);
+          const int ib = mt * TM + quarter * 32;
+          if (col < g.N - nt * TN) {
+            const float* Rp = g.Res + (long long)p * g.r_batch + nt * TN + col;
+            const uint32_t dst0 = smem_u32(warp_rows) + 4 * col;
+#pragma unroll 8
+            for (int r = sub; r < 32; r += 2)
+              if (ib + r < g.M) cp_async16(dst0 + r * STG_ROW, Rp + (long long)(ib + r) * g.c_i);
+          }
+          cp_async_commit();
         }
       };
       int acc = 0, tpar_e = 0; uint32_t acc_phase = 0;
@@ -783,7 +807,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN;
         const int ncv = min(TN, g.N - nt * TN);      // valid columns of this tile (multiple of 4 on this path)
         const bool has_res = f_res && pending;
-        if (has_res) { mbar_wait(my_bar, par); par ^= 1; }
+        if (f_res) {
+          if (res_tma) { if (has_res) { mbar_wait(my_bar, par); par ^= 1; } }
+          else { cp_async_wait_all(); __syncwarp(); }
+        }
         TC_PROF(8, tp);
         const float* iz = invz + quarter * TN;
         if (f_cs) {   // 1 / (sum of the four partial column sums), per warp copy so that only a __syncwarp is needed
@@ -923,7 +950,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
         tpar_e ^= 1;
         __syncwarp();
-        fence_proxy_async();                 // generic reads of the staged rows are ordered before the next TMA write
+        if ((f_res && res_tma) || (g.debug & 16384)) fence_proxy_async();   // generic reads of the staged rows are ordered before the next TMA write
         prefetch(tile + gridDim.x);
       }
     } else {
