@@ -408,27 +408,35 @@ __global__ void affine_from_partials_kernel(const float* __restrict__ part, int 
   const int lane = threadIdx.x & 31;
   const int p = row / ch, c = row - p * ch;
   const float* q = part + (size_t)row * tiles * 2;
-  float n = 0.f, mean = 0.f, M2 = 0.f;
-  for (int t = lane; t < tiles; t += 32) {
-    const float nb = (float)min(TC_TILE_N, L - t * TC_TILE_N);
-    const float2 v = __ldg(reinterpret_cast<const float2*>(q) + t);
-    const float delta = v.x - mean, nn = n + nb;
-    mean += delta * (nb / nn);
-    M2 += v.y + delta * delta * (n * nb / nn);
-    n = nn;
+  // Two passes over the (register-resident) partials instead of a chain of pairwise Chan merges with their divisions:
+  //   mean = sum_t n_t * mean_t / L;   M2 = sum_t [M2_t + n_t * (mean_t - mean)^2]      (exact identity, fixed order => deterministic)
+  constexpr int MAXT = 4;                        // tiles per lane kept in registers (L <= 8192 points); longer rows re-read the partials
+  float2 v[MAXT];
+  float s1 = 0.f;
+#pragma unroll
+  for (int u = 0; u < MAXT; ++u) {
+    const int t = lane + 32 * u;
+    v[u] = (t < tiles) ? __ldg(reinterpret_cast<const float2*>(q) + t) : make_float2(0.f, 0.f);
+    if (t < tiles) s1 = fmaf((float)min(TC_TILE_N, L - t * TC_TILE_N), v[u].x, s1);
+  }
+  for (int t = lane + 32 * MAXT; t < tiles; t += 32) s1 = fmaf((float)min(TC_TILE_N, L - t * TC_TILE_N), __ldg(q + 2 * t), s1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  const float mean = s1 / (float)L;
+  float M2 = 0.f;
+#pragma unroll
+  for (int u = 0; u < MAXT; ++u) {
+    const int t = lane + 32 * u;
+    const float d = v[u].x - mean;
+    if (t < tiles) M2 += fmaf((float)min(TC_TILE_N, L - t * TC_TILE_N) * d, d, v[u].y);
+  }
+  for (int t = lane + 32 * MAXT; t < tiles; t += 32) {
+    const float2 w = __ldg(reinterpret_cast<const float2*>(q) + t);
+    const float d = w.x - mean;
+    M2 += fmaf((float)min(TC_TILE_N, L - t * TC_TILE_N) * d, d, w.y);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o), Mb = __shfl_xor_sync(0xffffffffu, M2, o);
-    const float nn = n + nb;
-    if (nn > 0.f) {
-      const float delta = mb - mean;
-      // symmetric form: both partners of the butterfly compute the same merged value
-      mean = (n * mean + nb * mb) / nn;
-      M2 = M2 + Mb + delta * delta * (n * nb / nn);
-      n = nn;
-    }
-  }
+  for (int o = 16; o > 0; o >>= 1) M2 += __shfl_xor_sync(0xffffffffu, M2, o);
   if (lane == 0) {
     const float rstd = 1.0f / sqrtf(M2 / (float)L + eps_in);
     const float gsc = bn_train ? 1.f : __ldg(gamma + c) / sqrtf(__ldg(rvar + c) + 1e-5f);

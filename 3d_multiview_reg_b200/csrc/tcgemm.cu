@@ -775,10 +775,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
       int acc = 0, tpar_e = 0; uint32_t acc_phase = 0;
       const bool has_part = n_seg > 1;
       prefetch(blockIdx.x);
+      // one m-tile (every 128-channel layer): the thread's bias never changes -- keep it out of the per-tile critical path (its load
+      // was 5 % of the epilogue warps' stall samples)
+      const bool bias_const = tiles_m == 1;
+      const float bias_c = (bias_const && g.bias && r_own < g.M) ? __ldg(g.bias + r_own) : 0.f;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int p, mt, nt; decode(tile, p, mt, nt);
         const int i = mt * TM + r_own;
-        const float bias_own = (g.bias && i < g.M) ? __ldg(g.bias + i) : 0.f;
+        const float bias_own = bias_const ? bias_c : ((g.bias && i < g.M) ? __ldg(g.bias + i) : 0.f);
         // all but the last segment of a long reduction: add the TMEM partial into this thread's staged row (round-to-nearest)
         for (int seg = 0; seg + 1 < n_seg; ++seg) {
           mbar_wait(T_FULL(acc), acc_phase);
