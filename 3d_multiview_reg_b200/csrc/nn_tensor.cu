@@ -319,7 +319,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
 }
 
 // ---------------------------------------------------------------- (3) exact fp32 rescoring, one warp per query row
-__global__ void __launch_bounds__(256, 4)
+#ifndef LMPCR_RESCORE_BLOCKS
+#define LMPCR_RESCORE_BLOCKS 3          // resident CTAs per SM: 80 registers, no spills (at 4 the 64-register budget spills in the row loop: 11.5 vs 6.7 ms)
+#endif
+__global__ void __launch_bounds__(256, LMPCR_RESCORE_BLOCKS)
 nn_rescore_kernel(const float* __restrict__ q_feat, const float* __restrict__ sqn_q, int n_q, int rows_pad_q,
                   const float4* __restrict__ featT_b, const float* __restrict__ sqn_b, int n_b, int rows_pad_b,
                   const int32_t* __restrict__ jobs, int n_jobs, const uint2* __restrict__ cand, const int* __restrict__ unsupported,
@@ -332,9 +335,15 @@ nn_rescore_kernel(const float* __restrict__ q_feat, const float* __restrict__ sq
   const bool scan_all = (*unsupported != 0);
   const int n_chunks = (n_b + CHUNK - 1) / CHUNK;
   struct Row { uint4 cd; float a_l, an; int bs; };
-  auto fetch = [&](long long w) {
+  __shared__ __align__(16) float q_sm[8][D];                        // one staged query row per warp of the CTA
+  static_assert(D == 32, "one feature per lane");
+  float* qrow = q_sm[threadIdx.x >> 5];
+  const float4* qa = reinterpret_cast<const float4*>(qrow);
+  // (job, row) of the row being fetched advance incrementally: the 64-bit division w / n_q per row cost more instructions than the
+  // scoring of a candidate chunk (the kernel is issue-bound: ~2.6 IPC)
+  const int step_job = (int)(W / n_q), step_row = (int)(W - (long long)step_job * n_q);
+  auto fetch = [&](long long w, int job, int row) {
     Row r;
-    const int job = (int)(w / n_q), row = (int)(w - (long long)job * n_q);
     const int qs = __ldg(jobs + 2 * job);
     r.bs = __ldg(jobs + 2 * job + 1);
     r.cd = __ldg(reinterpret_cast<const uint4*>(cand) + w);                 // both column halves: 16 bytes
@@ -344,10 +353,16 @@ nn_rescore_kernel(const float* __restrict__ q_feat, const float* __restrict__ sq
   };
   long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= total) return;
-  Row nxt = fetch(w);
+  int f_job = (int)(w / n_q), f_row = (int)(w - (long long)f_job * n_q);      // once per warp
+  Row nxt = fetch(w, f_job, f_row);
   for (; w < total; w += W) {
     const Row cur = nxt;
-    if (w + W < total) nxt = fetch(w + W);
+    __syncwarp();                                   // the previous row's reads of the staged query are complete
+    qrow[lane] = cur.a_l;
+    __syncwarp();
+    f_job += step_job; f_row += step_row;
+    if (f_row >= n_q) { f_row -= n_q; ++f_job; }
+    if (w + W < total) nxt = fetch(w + W, f_job, f_row);
     const float4* tb = featT_b + (size_t)cur.bs * rows_pad_b * 8;    // rows_pad_b/32 chunks * 256 float4
     const float* nb = sqn_b + (size_t)cur.bs * rows_pad_b;
     float best = INFINITY;
@@ -361,11 +376,12 @@ nn_rescore_kernel(const float* __restrict__ q_feat, const float* __restrict__ sq
       const float bnj = __ldg(nb + j);
       float c = 0.f;
 #pragma unroll
-      for (int kq = 0; kq < 8; ++kq) {
-        c = fmaf(__shfl_sync(0xffffffffu, cur.a_l, 4 * kq), v[kq].x, c);
-        c = fmaf(__shfl_sync(0xffffffffu, cur.a_l, 4 * kq + 1), v[kq].y, c);
-        c = fmaf(__shfl_sync(0xffffffffu, cur.a_l, 4 * kq + 2), v[kq].z, c);
-        c = fmaf(__shfl_sync(0xffffffffu, cur.a_l, 4 * kq + 3), v[kq].w, c);
+      for (int kq = 0; kq < 8; ++kq) {         // the query row is broadcast from shared memory: 8 LDS.128 instead of 32 shuffles per chunk
+        const float4 a4 = qa[kq];
+        c = fmaf(a4.x, v[kq].x, c);
+        c = fmaf(a4.y, v[kq].y, c);
+        c = fmaf(a4.z, v[kq].z, c);
+        c = fmaf(a4.w, v[kq].w, c);
       }
       const float d = __fadd_rn(__fadd_rn(__fmul_rn(2.0f, -c), cur.an), bnj);
       if (j < n_b && (d < best || (d == best && j < bj))) { best = d; bj = j; }
@@ -477,7 +493,7 @@ int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float*
   nn_sweep_kernel<<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
   LMPCR_TRY(check_launch("nn_sweep_kernel"));
   const long long warps = (long long)n_jobs * n_q;
-  const long long max_blocks = 4ll * sm_count();            // 4 resident blocks of 8 persistent warps per SM
+  const long long max_blocks = (long long)LMPCR_RESCORE_BLOCKS * sm_count();            // resident blocks of 8 persistent warps per SM
   const long long want_blocks = (warps + 7) / 8;
   nn_rescore_kernel<<<(unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks), 256, 0, st>>>(q_feat, PQ.sqn, n_q, PQ.rows_pad, PB.feat_t, PB.sqn, n_b, PB.rows_pad, jobs,
                                                                          n_jobs, cand, unsupported, idx_out, dist_out);
