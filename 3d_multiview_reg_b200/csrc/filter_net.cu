@@ -198,6 +198,79 @@ gemm_fused_kernel(GemmArgs g) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 1x1 conv with a handful of input channels (the network's conv1: 6..9 coordinate / side channels -> 128, oanet.py:167), fp32.
+// The generic 128x128-tile SGEMM above spends its time on tile set-up for a K of 8; this one streams: a CTA takes one
+// (pair, 64-column tile), a warp 4 output channels x 64 columns per pass (lane = channel r, 2 x 4 columns), so that every store
+// instruction writes whole 128-byte row segments and the per-tile InstanceNorm partials (same layout and two-pass form as the GEMM
+// epilogues) reduce over 8 lanes.  Same arithmetic as the SGEMM: one FMA chain over k starting from 0, then + bias.
+// ------------------------------------------------------------------------------------------------
+constexpr int SK_MAX = 16;
+__global__ void __launch_bounds__(256)
+conv_smallk_kernel(const float* __restrict__ x, long long xb, int K, int L, const float* __restrict__ W, const float* __restrict__ bias, int M,
+                   float* __restrict__ out, long long ob, float* __restrict__ stats_out, int vec_ok) {
+  __shared__ __align__(16) float xs[SK_MAX][64];
+  const int p = blockIdx.y, tile = blockIdx.x, j0 = tile * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 3, cg = lane & 7;
+  const int ncv = min(64, L - j0);
+  const float* xp = x + (long long)p * xb + j0;
+  for (int e = tid; e < K * 64; e += 256) {
+    const int k = e >> 6, j = e & 63;
+    xs[k][j] = (j < ncv) ? __ldg(xp + (long long)k * L + j) : 0.f;
+  }
+  __syncthreads();
+  const int tiles = (L + 63) / 64;
+  float* op = out + (long long)p * ob + j0;
+  const int ca = 4 * cg, cb = 32 + 4 * cg;             // this lane's two groups of four columns
+  for (int c0 = 0; c0 < M; c0 += 32) {                 // uniform trip count: every lane takes part in the shuffles
+    const int c = c0 + warp * 4 + r;
+    const bool c_ok = c < M;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* wr = W + (long long)(c_ok ? c : 0) * K;
+    for (int k = 0; k < K; ++k) {
+      const float w = __ldg(wr + k);
+      const float4 a = *reinterpret_cast<const float4*>(&xs[k][ca]), b = *reinterpret_cast<const float4*>(&xs[k][cb]);
+      acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+      acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+    }
+    const float bi = (bias && c_ok) ? __ldg(bias + c) : 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += bi;
+    if (c_ok) {
+      float* orow = op + (long long)c * L;
+      if (vec_ok && ca + 3 < ncv) *reinterpret_cast<float4*>(orow + ca) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (ca + e < ncv) orow[ca + e] = acc[e];
+      }
+      if (vec_ok && cb + 3 < ncv) *reinterpret_cast<float4*>(orow + cb) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (cb + e < ncv) orow[cb + e] = acc[4 + e];
+      }
+    }
+    if (stats_out) {
+      // two-pass (mean, M2) over the tile's valid columns.  Summation order = the SGEMM epilogue's (16 lanes x 4 columns, butterfly
+      // 8-4-2-1): this lane's two column groups are that butterfly's first partners, so the partials are bit-identical to it
+      float s1a = 0.f, s1b = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { if (ca + e < ncv) s1a += acc[e]; if (cb + e < ncv) s1b += acc[4 + e]; }
+      float s1 = s1a + s1b;
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 4); s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      const float mean = s1 / (float)ncv;
+      float m2a = 0.f, m2b = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (ca + e < ncv) { const float d = acc[e] - mean; m2a = fmaf(d, d, m2a); }
+        if (cb + e < ncv) { const float d = acc[4 + e] - mean; m2b = fmaf(d, d, m2b); }
+      }
+      float m2 = m2a + m2b;
+      m2 += __shfl_xor_sync(0xffffffffu, m2, 4); m2 += __shfl_xor_sync(0xffffffffu, m2, 2); m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+      if (cg == 0 && c_ok) *reinterpret_cast<float2*>(stats_out + (((long long)p * M + c) * tiles + tile) * 2) = make_float2(mean, m2);
+    }
+  }
+}
+
 int gemm(const GemmArgs& g, int batch, cudaStream_t st) {
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, batch);
   gemm_fused_kernel<<<grid, GT, 0, st>>>(g);
@@ -856,6 +929,12 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     {   // conv1 runs here in fp32 also on the tensor path: let it emit the InstanceNorm partials its consumer wants
       const int oi = part_index(out);
       if (tc && oi >= 0 && cout == C) { a.stats_out = part_buf[oi]; part_valid[oi] = true; }
+    }
+    if (tc && cin <= SK_MAX && g <= 65535) {     // conv1: the streaming small-K kernel (same arithmetic, same partials layout)
+      const int vec_ok = ((L & 3) == 0) && ((ob & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+      dim3 grid((unsigned)((L + 63) / 64), (unsigned)g);
+      conv_smallk_kernel<<<grid, 256, 0, st>>>(x, xb, cin, L, cv.w, cv.b, cout, out, ob, a.stats_out, vec_ok);
+      return check_launch("conv_smallk_kernel");
     }
     return gemm(a, g, st);
   };

@@ -6,16 +6,17 @@
 // evaluated as A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with fp32 accumulation in TMEM -- the 1x1 convolutions of
 // lib/filtering/oanet.py need fp32-faithful products (TF32 moves the estimated pose by 4e-3 rad).
 //
-// Persistent, warp-specialised CTAs of 320 threads, TWO per SM (108 KB of shared memory, 128 TMEM columns, <=102
-// registers each) so that one CTA's epilogue overlaps the other's operand production.  One 128 x 64 output tile at a
-// time, K in chunks of 32:
-//   warp 0      TMA bulk copies of the pre-split weight tile (A) into the stage + L2 prefetch of the B / residual rows
+// Persistent, warp-specialised CTAs of 448 threads, TWO per SM (108 KB of shared memory, 128 TMEM columns, 72 registers each) so
+// that one CTA's epilogue overlaps the other's operand production.  One 128 x 64 output tile at a time, K in chunks of 32:
+//   warp 0      TMA bulk copies of the pre-split weight tile (A) into the stage + L2 prefetch of the B rows 4 chunks ahead
 //   warp 1      tcgen05.mma issue: per chunk 2 K-steps x 3 products, M128 x N64 x K16, accumulators in TMEM
-//   warps 2-5   epilogue: tcgen05.ld -> +bias +residual (row prefetched by TMA) -> per-row statistics -> staged tile ->
+//   warps 2-5   epilogue: tcgen05.ld -> +bias +residual (tile staged by per-lane cp.async) -> per-row statistics -> staged tile ->
 //               coalesced 256-byte row stores
-//   warps 6-9   operand producers: load fp32 activations, apply the fused prologue (InstanceNorm+BatchNorm affine and
-//               ReLU, or the softmax normalisation exp(x-max)/sum), split into hi/lo bf16 and store them straight
-//               in the UMMA canonical (no-swizzle) layout -- normalised activations never touch HBM.
+//   warps 6-13  operand producers: load fp32 activations, apply the fused prologue (InstanceNorm+BatchNorm affine and
+//               ReLU, or the softmax numerator 2^(x*log2e - max)), split into hi/lo bf16 and store them straight
+//               in the UMMA canonical (no-swizzle) layout -- normalised activations never touch HBM.  Two loops: the lean one
+//               (two groups of four warps on alternate chunks; every GEMM of the network at its shipped sizes) and the general one
+//               (ragged sizes, unaligned rows, fp32 A operands).
 // Pipelines: 3-stage shared-memory ring (full/empty mbarriers), double-buffered TMEM accumulator (64 columns each).
 #include <cuda_bf16.h>
 #include <math.h>
@@ -36,7 +37,7 @@ constexpr int B_OP_BYTES = TN * KC * 2;      // one bf16 B tile (hi or lo): 4 KB
 constexpr int STAGE_BYTES = 2 * A_OP_BYTES + 2 * B_OP_BYTES;   // [A_hi][A_lo][B_hi][B_lo] = 24 KB
 constexpr int N_PROD_WARPS = 8;
 constexpr int FIRST_EPI_WARP = 2, FIRST_PROD_WARP = 6;
-constexpr int NTHREADS = 32 * (FIRST_PROD_WARP + N_PROD_WARPS);   // 320
+constexpr int NTHREADS = 32 * (FIRST_PROD_WARP + N_PROD_WARPS);   // 448
 constexpr int TMEM_COLS = 2 * TN;                                  // two accumulators (power of two >= 32)
 constexpr uint32_t K_LBO = 128, K_SBO = (KC / 8) * 128;           // K-major operand: k-groups adjacent, 8-row groups 512 B apart
 constexpr uint32_t MN_SBO = 128, MN_LBO = (TN / 8) * 128;         // MN-major operand: j-groups adjacent, k-groups 1 KB apart
