@@ -18,7 +18,7 @@ sets = 3
 bufs = [(torch.randn(P, Ci, n, device=dev), torch.randn(P, Co, n, device=dev), torch.empty(P, Co, n, device=dev)) for _ in range(sets)]
 ws = torch.empty(1 << 22, dtype=torch.uint8, device=dev)
 names = ["mma wait T_EMPTY", "mma wait FULL", "mma issue", "prod wait EMPTY", "prod convert", "prod fence+arrive", "prod fetch/params",
-         "epi wait T_FULL", "epi wait residual", "epi phase1", "epi stats", "epi phase2 stores", "prod wait loaded x"]
+         "epi wait T_FULL", "epi wait residual", "epi phase1", "epi stats", "epi phase2 stores"]
 for use_res in (False, True):
     for x, r, o in bufs:
         cabi.conv1x1(x, w, b, sc, sh, r if use_res else None, gemm_algo=1, out=o, workspace=ws)
