@@ -20,9 +20,11 @@ GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
 EXPORTS = [
-    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_launch_count_named", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
     "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
     "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
+    "lmpcr_filter_pack_bytes", "lmpcr_filter_pack_weights", "lmpcr_filter_forward_packed",
+    "lmpcr_pointcn_stack", "lmpcr_pointcn_stack_workspace_bytes",
 ]
 
 
@@ -65,6 +67,8 @@ def load():
     lib.lmpcr_softmax_pool.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]
     lib.lmpcr_nn_soft.argtypes = [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _sz, _vp]
     lib.lmpcr_launch_count.restype = ctypes.c_longlong
+    lib.lmpcr_launch_count_named.restype = ctypes.c_longlong
+    lib.lmpcr_launch_count_named.argtypes = [ctypes.c_char_p]
     lib.lmpcr_nn_tensor_debug.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
     lib.lmpcr_pairwise_distance.argtypes = [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]
     lib.lmpcr_gather_xyz.argtypes = [_vp, _i, _vp, _i, _vp, _i, _vp, _vp]
@@ -81,6 +85,14 @@ def load():
     lib.lmpcr_filter_forward.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), _i, ctypes.POINTER(FilterCfg),
                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
     lib.lmpcr_pack_pose_records.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _vp]
+    lib.lmpcr_pointcn_stack_workspace_bytes.restype = _sz
+    lib.lmpcr_pointcn_stack_workspace_bytes.argtypes = [_i, _i]
+    lib.lmpcr_pointcn_stack.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _sz, _vp]
+    lib.lmpcr_filter_pack_bytes.restype = _sz
+    lib.lmpcr_filter_pack_bytes.argtypes = [ctypes.POINTER(FilterCfg)]
+    lib.lmpcr_filter_pack_weights.argtypes = [ctypes.POINTER(_vp), _i, ctypes.POINTER(FilterCfg), _vp, _sz, _vp]
+    lib.lmpcr_filter_forward_packed.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), _i, ctypes.POINTER(FilterCfg), _vp, _sz,
+                                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
     if lib.lmpcr_abi_version() != 1:
         raise LmpcrError("liblmpcr_b200.so ABI version mismatch")
     _lib = lib
@@ -206,6 +218,10 @@ def launch_count():
     return int(load().lmpcr_launch_count())
 
 
+def launch_count_named(kernel_name):
+    return int(load().lmpcr_launch_count_named(kernel_name.encode()))
+
+
 def nn_tensor_debug(q_feat, b_feat, jobs):
     """Tensor-path NN with the raw screening scores: returns (idx [J,n], dist [J,n], scores [J,n,m_pad], approx_min [J,n])."""
     lib = load()
@@ -324,19 +340,45 @@ def residuals(x1, x2, R, t):
 
 
 # ---------------------------------------------------------------------------------------------- stage 2
-def filter_forward(xs, params, cfg, want_latent=True, want_conf=True, workspace=None):
+def _param_ptrs(params, cfg, strict=False):
+    """Device-pointer table of the state_dict tensors.  strict (training-mode BatchNorm: the kernels update running_mean /
+    running_var in place through these pointers): every tensor must already be contiguous fp32 CUDA -- a silent copy would
+    lose the update."""
+    lib = load()
+    n_par = lib.lmpcr_filter_num_params(ctypes.byref(cfg))
+    if len(params) != n_par:
+        raise LmpcrError("expected %d parameter tensors, got %d" % (n_par, len(params)))
+    if strict:
+        for p in params:
+            if not (isinstance(p, torch.Tensor) and p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise LmpcrError("training-mode BatchNorm updates the running statistics in place: parameters and buffers must be "
+                                 "contiguous float32 CUDA tensors (got %s %s)" % (getattr(p, "dtype", type(p)), getattr(p, "device", "")))
+    keep = [_dev(p, name="parameter") for p in params]
+    return keep, (ctypes.c_void_p * n_par)(*[p.data_ptr() for p in keep]), n_par
+
+
+def filter_pack_weights(params, cfg):
+    """The load_state_dict-time step: all GEMM weights -> bf16 hi/lo operand tiles, once (lmpcr_filter_pack_weights).
+    Returns an opaque uint8 CUDA tensor for filter_forward(packed=...)."""
+    lib = load()
+    keep, table, n_par = _param_ptrs(params, cfg)
+    dev = keep[0].device
+    with torch.cuda.device(dev):
+        packed = _ws(lib.lmpcr_filter_pack_bytes(ctypes.byref(cfg)), dev)
+        _check(lib.lmpcr_filter_pack_weights(table, n_par, ctypes.byref(cfg), _p(packed), packed.numel(), _stream(packed)))
+    return packed
+
+
+def filter_forward(xs, params, cfg, want_latent=True, want_conf=True, workspace=None, packed=None):
     """xs [P,1,N,6+side] CUDA fp32; params: list of CUDA fp32 tensors in state_dict order (no num_batches_tracked);
-    cfg: FilterCfg.  Returns dict(logits [I,P,N], scores [I,P,N], R [I,P,3,3], t [I,P,3,1], residuals [P,N],
+    cfg: FilterCfg; packed: filter_pack_weights(params, cfg) or None (weights are then split inside the call).
+    Returns dict(logits [I,P,N], scores [I,P,N], R [I,P,3,3], t [I,P,3,1], residuals [P,N],
     latent [P,C,N] | None, conf [P,4] | None, status [P])."""
     lib = load()
     x = _dev(xs, name="xs")
     assert x.dim() == 4 and x.shape[1] == 1 and x.shape[3] == 6 + cfg.side_channel
     P, N = x.shape[0], x.shape[2]
-    n_par = lib.lmpcr_filter_num_params(ctypes.byref(cfg))
-    if len(params) != n_par:
-        raise LmpcrError("expected %d parameter tensors, got %d" % (n_par, len(params)))
-    keep = [_dev(p, name="parameter") for p in params]
-    table = (ctypes.c_void_p * n_par)(*[p.data_ptr() for p in keep])
+    keep, table, n_par = _param_ptrs(params, cfg, strict=(cfg.bn_mode == BN_BATCH))
     I = cfg.iter_num + 1
     dev = x.device
     with torch.cuda.device(dev):
@@ -354,9 +396,16 @@ def filter_forward(xs, params, cfg, want_latent=True, want_conf=True, workspace=
             return out
         if workspace is None:
             workspace = _ws(lib.lmpcr_filter_workspace_bytes(ctypes.byref(cfg), P, N), dev)
-        _check(lib.lmpcr_filter_forward(_p(x), P, N, table, n_par, ctypes.byref(cfg), _p(out["logits"]), _p(out["scores"]), _p(out["R"]),
-                                        _p(out["t"]), _p(out["residuals"]), _p(out["latent"]), _p(out["conf"]), _p(out["status"]),
-                                        _p(workspace), workspace.numel(), _stream(x)))
+        if packed is not None:
+            _check(lib.lmpcr_filter_forward_packed(_p(x), P, N, table, n_par, ctypes.byref(cfg), _p(packed), packed.numel(),
+                                                   _p(out["logits"]), _p(out["scores"]), _p(out["R"]), _p(out["t"]), _p(out["residuals"]),
+                                                   _p(out["latent"]), _p(out["conf"]), _p(out["status"]), _p(workspace), workspace.numel(),
+                                                   _stream(x)))
+        else:
+            _check(lib.lmpcr_filter_forward(_p(x), P, N, table, n_par, ctypes.byref(cfg), _p(out["logits"]), _p(out["scores"]), _p(out["R"]),
+                                            _p(out["t"]), _p(out["residuals"]), _p(out["latent"]), _p(out["conf"]), _p(out["status"]),
+                                            _p(workspace), workspace.numel(), _stream(x)))
+    out["_workspace"] = workspace      # handed back so that callers can keep it for the next call
     return out
 
 
@@ -379,6 +428,23 @@ def conv1x1(x, weight, bias=None, scale=None, shift=None, residual=None, gemm_al
     return out
 
 
+def pointcn_stack(x, layer_params, out=None, want_stats=False):
+    """A stack of plain PointCN layers in one pair-resident launch (lmpcr_pointcn_stack).  x [P,128,N]; layer_params: list (one entry
+    per layer) of 12 tensors in state_dict order: BN conv.1 (w, b, rm, rv), conv.3 (w, b), BN conv.5 (x4), conv.7 (w, b)."""
+    lib = load()
+    x = _dev(x, name="x")
+    P, C, N = x.shape
+    flat = [_dev(t, name="parameter").reshape(-1) if t.dim() != 4 else _dev(t, name="parameter") for lp in layer_params for t in lp]
+    table = (ctypes.c_void_p * len(flat))(*[t.data_ptr() for t in flat])
+    with torch.cuda.device(x.device):
+        if out is None:
+            out = torch.empty_like(x)
+        stats = torch.empty((P, C, 2), dtype=torch.float32, device=x.device) if want_stats else None
+        ws = _ws(lib.lmpcr_pointcn_stack_workspace_bytes(P, len(layer_params)), x.device)
+        _check(lib.lmpcr_pointcn_stack(_p(x), P, N, table, len(layer_params), _p(out), _p(stats), _p(ws), ws.numel(), _stream(x)))
+    return (out, stats) if want_stats else out
+
+
 def softmax_pool(x, embed, mode=1):
     """diff_pool's weighted sum (oanet.py:107-109): x [P,C,N], embed [P,K,N] -> [P,C,K]; mode 0 separate statistics, 1 deferred."""
     lib = load()
@@ -394,6 +460,13 @@ def softmax_pool(x, embed, mode=1):
 
 def filter_workspace_bytes(cfg, P, N):
     return int(load().lmpcr_filter_workspace_bytes(ctypes.byref(cfg), P, N))
+
+
+def reusable_workspace(cached, cfg, P, N, device):
+    """`cached` if it is a scratch tensor on `device` large enough for (cfg, P, N), else None (filter_forward then allocates)."""
+    if cached is None or cached.device != device or P <= 0:
+        return None
+    return cached if cached.numel() >= filter_workspace_bytes(cfg, P, N) else None
 
 
 def pack_pose_records(R, t, conf, status):

@@ -19,8 +19,23 @@ void set_error(const char* fmt, ...) {
 static long long g_launches = 0;
 void count_launches(int n) { __atomic_add_fetch(&g_launches, (long long)n, __ATOMIC_RELAXED); }
 
+// per-kernel launch counters (lmpcr_launch_count_named): `what` is a string literal, so the pointer identifies the kernel
+static const char* g_names[128];
+static long long g_named[128];
+static int g_n_names = 0;
+
 int check_launch(const char* what) {
   count_launches(1);
+  {
+    int i = 0;
+    const int n = __atomic_load_n(&g_n_names, __ATOMIC_ACQUIRE);
+    for (; i < n; ++i) if (g_names[i] == what) break;
+    if (i == n && n < 128) {          // first launch of this kernel (racing first launches may register a name twice: the reader sums)
+      g_names[n] = what;
+      __atomic_store_n(&g_n_names, n + 1, __ATOMIC_RELEASE);
+    }
+    if (i < 128) __atomic_add_fetch(&g_named[i], 1, __ATOMIC_RELAXED);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -55,6 +70,12 @@ int check_device() {
   return LMPCR_OK;
 }
 
+int device_ordinal() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+}
+
 int sm_count() {
   int dev = 0;
   cudaGetDevice(&dev);
@@ -70,6 +91,13 @@ extern "C" {
 int lmpcr_abi_version(void) { return LMPCR_ABI_VERSION; }
 long long lmpcr_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 const char* lmpcr_last_error(void) { return g_err; }
+long long lmpcr_launch_count_named(const char* kernel_name) {
+  long long c = 0;
+  const int n = __atomic_load_n(&g_n_names, __ATOMIC_ACQUIRE);
+  for (int i = 0; i < n; ++i)
+    if (kernel_name && g_names[i] && strcmp(g_names[i], kernel_name) == 0) c += __atomic_load_n(&g_named[i], __ATOMIC_RELAXED);
+  return c;
+}
 
 int lmpcr_device_info(int* sms, int* l2_bytes, int* cc_major, int* cc_minor) {
   int dev = -1;
@@ -195,6 +223,14 @@ int lmpcr_conv1x1(const float* x, int n_pairs, int cin, int n_pts, const float* 
                         (cudaStream_t)stream);
 }
 
+size_t lmpcr_pointcn_stack_workspace_bytes(int n_pairs, int n_layers) { return pointcn_stack_workspace_bytes(n_pairs, n_layers); }
+
+int lmpcr_pointcn_stack(const float* x, int n_pairs, int n_pts, const float* const* params, int n_layers, float* out, float* stats_out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_pointcn_stack(x, n_pairs, n_pts, params, n_layers, out, stats_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int lmpcr_filter_num_params(const lmpcr_filter_cfg* cfg) {
   if (!cfg) return LMPCR_ERR_ARG;
   return filter_num_params(cfg);
@@ -211,6 +247,24 @@ int lmpcr_filter_forward(const float* xs, int n_pairs, int n_pts, const float* c
   LMPCR_TRY(check_device());
   return launch_filter_forward(xs, n_pairs, n_pts, params, n_params, cfg, logits, scores, R, t, residuals, latent, conf, status,
                                workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t lmpcr_filter_pack_bytes(const lmpcr_filter_cfg* cfg) { return filter_pack_bytes(cfg); }
+
+int lmpcr_filter_pack_weights(const float* const* params, int n_params, const lmpcr_filter_cfg* cfg, void* packed, size_t packed_bytes,
+                              void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_filter_pack_weights(params, n_params, cfg, packed, packed_bytes, (cudaStream_t)stream);
+}
+
+int lmpcr_filter_forward_packed(const float* xs, int n_pairs, int n_pts, const float* const* params, int n_params,
+                                const lmpcr_filter_cfg* cfg, const void* packed, size_t packed_bytes, float* logits, float* scores, float* R,
+                                float* t, float* residuals, float* latent, float* conf, uint32_t* status, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  LMPCR_REQUIRE(packed, LMPCR_ERR_ARG, "lmpcr_filter_forward_packed: packed weights are null (lmpcr_filter_pack_weights)");
+  return launch_filter_forward(xs, n_pairs, n_pts, params, n_params, cfg, logits, scores, R, t, residuals, latent, conf, status,
+                               workspace, workspace_bytes, (cudaStream_t)stream, reinterpret_cast<const uint8_t*>(packed), packed_bytes);
 }
 
 int lmpcr_pack_pose_records(const float* R, const float* t, const float* conf, const uint32_t* status, int n_pairs, float* rec,

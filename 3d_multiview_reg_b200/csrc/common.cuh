@@ -13,6 +13,7 @@ void set_error(const char* fmt, ...);
 int check_device();          // LMPCR_OK iff the current device is sm_100 (B200)
 int check_launch(const char* what);
 int sm_count();
+int device_ordinal();    // current device clamped to [0, 63] (index of the per-device caches)
 void count_launches(int n);   // bookkeeping behind lmpcr_launch_count()
 
 #define LMPCR_REQUIRE(cond, code, ...)   \
@@ -95,10 +96,17 @@ int launch_nn_tensor(const float* q_feat, int n_q_sets, int n_q, const float* b_
 size_t conv1x1_workspace_bytes(int cout, int cin);
 int launch_conv1x1(const float* x, int P, int cin, int N, const float* weight, const float* bias, const float* scale, const float* shift,
                    const float* residual, int cout, float* out, int algo, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t pointcn_stack_workspace_bytes(int P, int n_layers);
+int launch_pointcn_stack(const float* x, int P, int N, const float* const* params, int n_layers, float* out, float* stats_out, void* ws,
+                         size_t ws_bytes, cudaStream_t st);
 int filter_num_params(const lmpcr_filter_cfg* cfg);
 size_t filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int P, int N);
 int launch_filter_forward(const float* xs, int P, int N, const float* const* params, int n_params,
                           const lmpcr_filter_cfg* cfg, float* logits, float* scores, float* R, float* t, float* residuals,
-                          float* latent, float* conf, uint32_t* status, void* ws, size_t ws_bytes, cudaStream_t st);
+                          float* latent, float* conf, uint32_t* status, void* ws, size_t ws_bytes, cudaStream_t st,
+                          const uint8_t* packed = nullptr, size_t packed_bytes = 0);
+size_t filter_pack_bytes(const lmpcr_filter_cfg* cfg);
+int launch_filter_pack_weights(const float* const* params, int n_params, const lmpcr_filter_cfg* cfg, void* packed, size_t packed_bytes,
+                               cudaStream_t st);
 
 }  // namespace lmpcr

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "tcgemm.cuh"
+#include "pcn.cuh"
 
 namespace lmpcr {
 namespace {
@@ -474,7 +475,9 @@ __global__ void softmax_colstats_kernel(const float* __restrict__ e, int K, int 
 __global__ void affine_from_partials_kernel(const float* __restrict__ part, int ch, int tiles, int L, int n_rows, float eps_in,
                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                             const float* __restrict__ rmean, const float* __restrict__ rvar,
-                                            float* __restrict__ scale, float* __restrict__ shift, int out_stride, int out_off, int bn_train) {
+                                            float* __restrict__ scale, float* __restrict__ shift, int out_stride, int out_off, int bn_train,
+                                            int tile_n) {
+  // tile_n: columns per partial (TC_TILE_N for the GEMM epilogues; L when the producer emitted ONE whole-row (mean, M2), pcn.cu)
   // one warp per (pair, channel): lanes take tiles lane, lane+32, ... in order, then a fixed shuffle tree merges them
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -490,9 +493,9 @@ __global__ void affine_from_partials_kernel(const float* __restrict__ part, int 
   for (int u = 0; u < MAXT; ++u) {
     const int t = lane + 32 * u;
     v[u] = (t < tiles) ? __ldg(reinterpret_cast<const float2*>(q) + t) : make_float2(0.f, 0.f);
-    if (t < tiles) s1 = fmaf((float)min(TC_TILE_N, L - t * TC_TILE_N), v[u].x, s1);
+    if (t < tiles) s1 = fmaf((float)min(tile_n, L - t * tile_n), v[u].x, s1);
   }
-  for (int t = lane + 32 * MAXT; t < tiles; t += 32) s1 = fmaf((float)min(TC_TILE_N, L - t * TC_TILE_N), __ldg(q + 2 * t), s1);
+  for (int t = lane + 32 * MAXT; t < tiles; t += 32) s1 = fmaf((float)min(tile_n, L - t * tile_n), __ldg(q + 2 * t), s1);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
   const float mean = s1 / (float)L;
@@ -501,12 +504,12 @@ __global__ void affine_from_partials_kernel(const float* __restrict__ part, int 
   for (int u = 0; u < MAXT; ++u) {
     const int t = lane + 32 * u;
     const float d = v[u].x - mean;
-    if (t < tiles) M2 += fmaf((float)min(TC_TILE_N, L - t * TC_TILE_N) * d, d, v[u].y);
+    if (t < tiles) M2 += fmaf((float)min(tile_n, L - t * tile_n) * d, d, v[u].y);
   }
   for (int t = lane + 32 * MAXT; t < tiles; t += 32) {
     const float2 w = __ldg(reinterpret_cast<const float2*>(q) + t);
     const float d = w.x - mean;
-    M2 += fmaf((float)min(TC_TILE_N, L - t * TC_TILE_N) * d, d, w.y);
+    M2 += fmaf((float)min(tile_n, L - t * tile_n) * d, d, w.y);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) M2 += __shfl_xor_sync(0xffffffffu, M2, o);
@@ -634,6 +637,24 @@ size_t block_blob_bytes(int C, int K, int half) {
   return align_up(b, 256);
 }
 
+// Assigns (and, with do_split, fills) the pre-split weight blobs of one OANBlock, in a fixed order: the packed-weights layout of
+// lmpcr_filter_pack_weights is this order, block after block (conv1 / output stay fp32 SIMT and are not packed).
+int block_blobs(BlockP& blk, int C, int K, int half, uint8_t* bp, bool do_split, cudaStream_t st) {
+  auto prep = [&](ConvP& cv, int M_, int K_) -> int {
+    cv.blob = bp;
+    const int rc = do_split ? launch_split_weights(cv.w, M_, K_, bp, st) : LMPCR_OK;
+    bp += tc_weight_blob_bytes(M_, K_);
+    return rc;
+  };
+  LMPCR_TRY(prep(blk.down_conv, K, C));
+  LMPCR_TRY(prep(blk.up_conv, K, C));
+  for (int i = 0; i < half; ++i) { LMPCR_TRY(prep(blk.l1_1[i].c1, C, C)); LMPCR_TRY(prep(blk.l1_1[i].c2, C, C)); }
+  LMPCR_TRY(prep(blk.l1_2[0].sc, C, 2 * C)); LMPCR_TRY(prep(blk.l1_2[0].c1, C, 2 * C)); LMPCR_TRY(prep(blk.l1_2[0].c2, C, C));
+  for (int i = 1; i < half; ++i) { LMPCR_TRY(prep(blk.l1_2[i].c1, C, C)); LMPCR_TRY(prep(blk.l1_2[i].c2, C, C)); }
+  for (int i = 0; i < half; ++i) { LMPCR_TRY(prep(blk.l2[i].c1, C, C)); LMPCR_TRY(prep(blk.l2[i].c2, K, K)); LMPCR_TRY(prep(blk.l2[i].c3, C, C)); }
+  return LMPCR_OK;
+}
+
 }  // namespace
 
 size_t conv1x1_workspace_bytes(int cout, int cin) { return align_up(tc_weight_blob_bytes(cout, cin), 256) + 256; }
@@ -716,9 +737,72 @@ int launch_softmax_pool(const float* x, const float* E, int P, int C, int K, int
   return launch_tcgemm(a, P, st);
 }
 
+// A stack of plain PointCN layers alone (lib/filtering/oanet.py:18-43, 128 channels, eval BatchNorm) through the pair-resident
+// kernel of pcn.cu; exported like lmpcr_conv1x1 so that it can be tested and timed by itself.
+// params: 12 tensors per layer in state_dict order: conv.1 (BN weight, bias, running_mean, running_var), conv.3 (weight, bias),
+// conv.5 (BN x 4), conv.7 (weight, bias).
+size_t pointcn_stack_workspace_bytes(int P, int n_layers) {
+  return (size_t)n_layers * 2 * tc_weight_blob_bytes(PCN_C, PCN_C) + 2 * align_up((size_t)(P > 0 ? P : 1) * PCN_C * 4, 256) + 256;
+}
+
+int launch_pointcn_stack(const float* x, int P, int N, const float* const* params, int n_layers, float* out, float* stats_out, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+  LMPCR_REQUIRE(x && out && params && P >= 0 && N > 0 && n_layers >= 1 && n_layers <= PCN_MAX_LAYERS, LMPCR_ERR_ARG, "lmpcr_pointcn_stack: bad arguments");
+  LMPCR_REQUIRE(ws && ws_bytes >= pointcn_stack_workspace_bytes(P, n_layers) && ((uintptr_t)ws & 255) == 0, LMPCR_ERR_WORKSPACE, "lmpcr_pointcn_stack: workspace");
+  if (P == 0) return LMPCR_OK;
+  const long long CN = (long long)PCN_C * N;
+  LMPCR_REQUIRE(pcn_supported(PCN_C, N, x, CN, out, CN), LMPCR_ERR_UNSUPPORTED, "lmpcr_pointcn_stack: needs n_pts %% 4 == 0 and 16-byte aligned tensors");
+  uint8_t* bp = reinterpret_cast<uint8_t*>(ws);
+  PcnArgs pa{};
+  for (int l = 0; l < n_layers; ++l) {
+    const float* const* q = params + 12 * l;
+    for (int i = 0; i < 12; ++i) LMPCR_REQUIRE(q[i], LMPCR_ERR_ARG, "lmpcr_pointcn_stack: params[%d] is null", 12 * l + i);
+    PcnLayer& L = pa.layer[l];
+    L.bn1 = PcnBN{q[0], q[1], q[2], q[3]};
+    L.b1 = q[5];
+    L.bn2 = PcnBN{q[6], q[7], q[8], q[9]};
+    L.b2 = q[11];
+    L.w1 = bp; LMPCR_TRY(launch_split_weights(q[4], PCN_C, PCN_C, bp, st)); bp += tc_weight_blob_bytes(PCN_C, PCN_C);
+    L.w2 = bp; LMPCR_TRY(launch_split_weights(q[10], PCN_C, PCN_C, bp, st)); bp += tc_weight_blob_bytes(PCN_C, PCN_C);
+  }
+  float* scale = reinterpret_cast<float*>(bp);
+  float* shift = reinterpret_cast<float*>(bp + align_up((size_t)P * PCN_C * 4, 256));
+  const int rows = P * PCN_C;
+  in_affine_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, CN, PCN_C, N, 1, 1e-5f, params[0], params[1], params[2], params[3], scale, shift, rows, 0);
+  LMPCR_TRY(check_launch("in_affine_kernel"));
+  pa.n_layers = n_layers; pa.scale0 = scale; pa.shift0 = shift; pa.stats_out = stats_out; pa.P = P; pa.N = N; pa.store_out = 1;
+  return launch_pcn_stack(x, CN, out, CN, pa, st);
+}
+
 int filter_num_params(const lmpcr_filter_cfg* cfg) {
   const int half = (cfg->net_depth / (cfg->iter_num + 1)) / 2;
   return block_num_params(half) * (cfg->iter_num + 1);
+}
+
+static int validate_cfg(const lmpcr_filter_cfg* cfg);
+
+size_t filter_pack_bytes(const lmpcr_filter_cfg* cfg) {
+  if (validate_cfg(cfg) != LMPCR_OK || cfg->gemm_algo != 1) return 0;
+  const int iters = cfg->iter_num + 1, half = (cfg->net_depth / iters) / 2;
+  return (size_t)iters * block_blob_bytes(cfg->net_channel, cfg->clusters, half);
+}
+
+// The load_state_dict-time step of SURVEY.md 8b: every GEMM weight of the network -> bf16 hi/lo tiles in the UMMA layout, once.
+int launch_filter_pack_weights(const float* const* params, int n_params, const lmpcr_filter_cfg* cfg, void* packed, size_t packed_bytes,
+                               cudaStream_t st) {
+  LMPCR_TRY(validate_cfg(cfg));
+  LMPCR_REQUIRE(cfg->gemm_algo == 1, LMPCR_ERR_ARG, "lmpcr_filter_pack_weights: only the tensor-core path (gemm_algo=1) uses packed weights");
+  LMPCR_REQUIRE(params && n_params == filter_num_params(cfg), LMPCR_ERR_ARG, "lmpcr_filter_pack_weights: expected %d parameter tensors, got %d", filter_num_params(cfg), n_params);
+  LMPCR_REQUIRE(packed && packed_bytes >= filter_pack_bytes(cfg) && ((uintptr_t)packed & 255) == 0, LMPCR_ERR_WORKSPACE, "lmpcr_filter_pack_weights: buffer (%zu bytes, 256-byte aligned)", filter_pack_bytes(cfg));
+  for (int i = 0; i < n_params; ++i) LMPCR_REQUIRE(params[i], LMPCR_ERR_ARG, "lmpcr_filter_pack_weights: params[%d] is null", i);
+  const int C = cfg->net_channel, K = cfg->clusters, iters = cfg->iter_num + 1, half = (cfg->net_depth / iters) / 2;
+  Cursor cur{params, 0, n_params};
+  for (int it = 0; it < iters; ++it) {
+    BlockP blk;
+    parse_block(cur, half, blk);
+    LMPCR_TRY(block_blobs(blk, C, K, half, reinterpret_cast<uint8_t*>(packed) + (size_t)it * block_blob_bytes(C, K, half), true, st));
+  }
+  return LMPCR_OK;
 }
 
 static int validate_cfg(const lmpcr_filter_cfg* cfg) {
@@ -753,7 +837,7 @@ size_t filter_workspace_bytes(const lmpcr_filter_cfg* cfg, int P, int N) {
 int launch_filter_forward(const float* xs, int P, int N, const float* const* params, int n_params,
                           const lmpcr_filter_cfg* cfg, float* logits, float* scores, float* Rout, float* tout,
                           float* residuals, float* latent, float* conf, uint32_t* status, void* ws, size_t ws_bytes,
-                          cudaStream_t st) {
+                          cudaStream_t st, const uint8_t* packed, size_t packed_bytes) {
   LMPCR_TRY(validate_cfg(cfg));
   LMPCR_REQUIRE(xs && params && logits && scores && Rout && tout, LMPCR_ERR_ARG, "lmpcr_filter_forward: null pointer");
   LMPCR_REQUIRE(P >= 0 && N >= 1, LMPCR_ERR_ARG, "lmpcr_filter_forward: bad sizes");
@@ -761,12 +845,16 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   const bool tc = cfg->gemm_algo == 1;
   const bool bn_train = cfg->bn_mode == LMPCR_BN_BATCH;
   static const int no_defer = getenv("LMPCR_NO_DEFER") ? atoi(getenv("LMPCR_NO_DEFER")) : 0;   // debug aid: softmax statistics by separate passes
+  static const int pcn_on = getenv("LMPCR_PCN") ? atoi(getenv("LMPCR_PCN")) : 1;                // 0: PointCN layers on the per-layer GEMM path (A/B runs)
+  static const int pcn_min_pairs = getenv("LMPCR_PCN_MIN_PAIRS") ? atoi(getenv("LMPCR_PCN_MIN_PAIRS")) : 64;
   LMPCR_REQUIRE(n_params == filter_num_params(cfg), LMPCR_ERR_ARG, "lmpcr_filter_forward: expected %d parameter tensors, got %d", filter_num_params(cfg), n_params);
   for (int i = 0; i < n_params; ++i) LMPCR_REQUIRE(params[i], LMPCR_ERR_ARG, "lmpcr_filter_forward: params[%d] is null", i);
   if (P == 0) return LMPCR_OK;
   const int C = cfg->net_channel, K = cfg->clusters, iters = cfg->iter_num + 1;
   const int half = (cfg->net_depth / iters) / 2;
   const int Cx = 6 + cfg->side_channel;
+  LMPCR_REQUIRE(!packed || (tc && packed_bytes >= filter_pack_bytes(cfg) && ((uintptr_t)packed & 255) == 0), LMPCR_ERR_ARG,
+                "lmpcr_filter_forward_packed: packed weights need gemm_algo=1, %zu bytes and 256-byte alignment", filter_pack_bytes(cfg));
   const size_t pp = per_pair_floats(C, K, N) * 4;
   const size_t fixed = fixed_bytes(cfg, P, N);
   LMPCR_REQUIRE(ws && ws_bytes >= fixed + pp + 4096, LMPCR_ERR_WORKSPACE, "lmpcr_filter_forward: workspace %zu < %zu bytes", ws_bytes, fixed + pp + 4096);
@@ -802,7 +890,8 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   float* part_buf[N_PART];
   const float* part_key[N_PART] = {W.T0, W.T1, W.T2, W.CAT, W.CAT + (size_t)C * N, W.XD0, W.XD1};
   bool part_valid[N_PART];
-  for (int i = 0; i < N_PART; ++i) { part_buf[i] = take((size_t)C * tmax * 2); part_valid[i] = false; }
+  bool part_whole[N_PART];   // the partials are ONE whole-row (mean, M2) per (pair, channel) (written by the pcn stack) instead of one per 64-column tile
+  for (int i = 0; i < N_PART; ++i) { part_buf[i] = take((size_t)C * tmax * 2); part_valid[i] = false; part_whole[i] = false; }
   float* sm_part = take((size_t)K * tmax * 2);
   float* col_part = take((size_t)N * 4 * ((K + 127) / 128) * 2);
   struct { const float* out; const float* w; const float* b; float* logits; float* scores; int32_t* anypos; bool store; bool done; } head = {};
@@ -842,27 +931,29 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     LMPCR_TRY(check_launch("in_affine_kernel"));
     return use_in ? bn_finalize(ch, L, g, eps, bn, 0, ch, 0) : LMPCR_OK;
   };
-  auto aff_part = [&](const float* part, int ch, int L, int g, float eps, const BNP& bn, int bn_off, int out_stride, int out_off) -> int {
-    const int rows = g * ch, tiles = (L + TC_TILE_N - 1) / TC_TILE_N;
+  auto aff_part = [&](const float* part, bool whole, int ch, int L, int g, float eps, const BNP& bn, int bn_off, int out_stride, int out_off) -> int {
+    const int rows = g * ch, tiles = whole ? 1 : (L + TC_TILE_N - 1) / TC_TILE_N;
     affine_from_partials_kernel<<<(rows + 7) / 8, 256, 0, st>>>(part, ch, tiles, L, rows, eps, bn.g + bn_off, bn.b + bn_off, bn.rm + bn_off,
-                                                                    bn.rv + bn_off, W.scale, W.shift, out_stride, out_off, bn_train ? 1 : 0);
+                                                                    bn.rv + bn_off, W.scale, W.shift, out_stride, out_off, bn_train ? 1 : 0,
+                                                                    whole ? L : TC_TILE_N);
     LMPCR_TRY(check_launch("affine_from_partials_kernel"));
     return bn_finalize(ch, L, g, eps, bn, bn_off, out_stride, out_off);
+  };
+  // W.scale / W.shift [g, cin] <- InstanceNorm (+ BatchNorm) of x: from the producer's fused partials when available, else a pass over x
+  auto norm_affine = [&](const float* x, long long xb, int cin, int L, int g, float eps, const BNP& bn) -> int {
+    const int xi = part_index(x);
+    const int xi_hi = (cin == 2 * C) ? part_index(x + (size_t)C * L) : -1;
+    if (tc && cin == C && xi >= 0 && part_valid[xi]) return aff_part(part_buf[xi], part_whole[xi], C, L, g, eps, bn, 0, C, 0);
+    if (tc && cin == 2 * C && xi >= 0 && xi_hi >= 0 && part_valid[xi] && part_valid[xi_hi]) {
+      LMPCR_TRY(aff_part(part_buf[xi], part_whole[xi], C, L, g, eps, bn, 0, 2 * C, 0));
+      return aff_part(part_buf[xi_hi], part_whole[xi_hi], C, L, g, eps, bn, C, 2 * C, C);
+    }
+    return affine(x, xb, cin, L, g, true, eps, bn);
   };
   // out[p, :, :] = conv(relu(bn(in(x))))  (+ residual), x [g, cin, L] with batch stride xb
   auto conv_norm = [&](const float* x, long long xb, int cin, int L, int g, float eps, const BNP& bn, const ConvP& cv, int cout,
                        float* out, long long ob, const float* res, long long rb) -> int {
-    // InstanceNorm statistics of the input: from the producer's fused partials when available, else a pass over x
-    const int xi = part_index(x);
-    const int xi_hi = (cin == 2 * C) ? part_index(x + (size_t)C * L) : -1;
-    if (tc && cin == C && xi >= 0 && part_valid[xi]) {
-      LMPCR_TRY(aff_part(part_buf[xi], C, L, g, eps, bn, 0, C, 0));
-    } else if (tc && cin == 2 * C && xi >= 0 && xi_hi >= 0 && part_valid[xi] && part_valid[xi_hi]) {
-      LMPCR_TRY(aff_part(part_buf[xi], C, L, g, eps, bn, 0, 2 * C, 0));
-      LMPCR_TRY(aff_part(part_buf[xi_hi], C, L, g, eps, bn, C, 2 * C, C));
-    } else {
-      LMPCR_TRY(affine(x, xb, cin, L, g, true, eps, bn));
-    }
+    LMPCR_TRY(norm_affine(x, xb, cin, L, g, eps, bn));
     const int oi = part_index(out);
     if (tc) {
       TcGemmArgs a{};
@@ -880,7 +971,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         a.prologue = TC_PRO_NONE;
       }
       if (oi >= 0 && cout == C) {
-        part_valid[oi] = tc_fast_epilogue(a);
+        part_valid[oi] = tc_fast_epilogue(a); part_whole[oi] = false;
         a.stats_out = part_valid[oi] ? part_buf[oi] : nullptr;
       }
       if (head.out == out && cout == C && C <= 128 && tc_fast_epilogue(a)) {
@@ -888,7 +979,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         // nobody normalises this output, and unless the caller wants the latent features it is not even stored
         a.lg_w = head.w; a.lg_b = head.b; a.lg_logits = head.logits; a.lg_scores = head.scores; a.lg_anypos = head.anypos;
         a.stats_out = nullptr;
-        if (oi >= 0) part_valid[oi] = false;
+        if (oi >= 0) { part_valid[oi] = false; part_whole[oi] = false; }
         if (!head.store) a.C = nullptr;
         head.done = true;
       }
@@ -900,7 +991,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       if (want_col && out == W.E && tc_fast_epilogue(a)) a.colstats_out = col_part;   // softmax over points (diff_pool)
       return launch_tcgemm(a, g, st);
     }
-    if (oi >= 0) part_valid[oi] = false;
+    if (oi >= 0) { part_valid[oi] = false; part_whole[oi] = false; }
     GemmArgs a{};
     a.A = cv.w; a.a_batch = 0; a.a_i = cin;
     a.B = x; a.b_batch = xb; a.b_k = L; a.b_j = 1;
@@ -911,7 +1002,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     return gemm(a, g, st);
   };
   auto conv_plain = [&](const float* x, long long xb, int cin, int L, int g, const ConvP& cv, int cout, float* out, long long ob) -> int {
-    { const int oi = part_index(out); if (oi >= 0) part_valid[oi] = false; }
+    { const int oi = part_index(out); if (oi >= 0) { part_valid[oi] = false; part_whole[oi] = false; } }
     if (tc && cv.blob) {
       TcGemmArgs a{};
       a.a_blob = cv.blob;
@@ -928,7 +1019,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     a.bias = cv.b; a.M = cout; a.N = L; a.K = cin;
     {   // conv1 runs here in fp32 also on the tensor path: let it emit the InstanceNorm partials its consumer wants
       const int oi = part_index(out);
-      if (tc && oi >= 0 && cout == C) { a.stats_out = part_buf[oi]; part_valid[oi] = true; }
+      if (tc && oi >= 0 && cout == C) { a.stats_out = part_buf[oi]; part_valid[oi] = true; part_whole[oi] = false; }
     }
     if (tc && cin <= SK_MAX && g <= 65535) {     // conv1: the streaming small-K kernel (same arithmetic, same partials layout)
       const int vec_ok = ((L & 3) == 0) && ((ob & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
@@ -952,20 +1043,10 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   for (int it = 0; it < iters; ++it) {
     BlockP blk;
     parse_block(cur, half, blk);
-    if (tc) {   // split every GEMM weight of this block into bf16 hi/lo tiles in the UMMA layout (conv1 / output stay fp32 SIMT)
-      uint8_t* bp = blob_base;
-      auto prep = [&](ConvP& cv, int M_, int K_) -> int {
-        cv.blob = bp;
-        const int rc = launch_split_weights(cv.w, M_, K_, bp, st);
-        bp += tc_weight_blob_bytes(M_, K_);
-        return rc;
-      };
-      LMPCR_TRY(prep(blk.down_conv, K, C));
-      LMPCR_TRY(prep(blk.up_conv, K, C));
-      for (int i = 0; i < half; ++i) { LMPCR_TRY(prep(blk.l1_1[i].c1, C, C)); LMPCR_TRY(prep(blk.l1_1[i].c2, C, C)); }
-      LMPCR_TRY(prep(blk.l1_2[0].sc, C, 2 * C)); LMPCR_TRY(prep(blk.l1_2[0].c1, C, 2 * C)); LMPCR_TRY(prep(blk.l1_2[0].c2, C, C));
-      for (int i = 1; i < half; ++i) { LMPCR_TRY(prep(blk.l1_2[i].c1, C, C)); LMPCR_TRY(prep(blk.l1_2[i].c2, C, C)); }
-      for (int i = 0; i < half; ++i) { LMPCR_TRY(prep(blk.l2[i].c1, C, C)); LMPCR_TRY(prep(blk.l2[i].c2, K, K)); LMPCR_TRY(prep(blk.l2[i].c3, C, C)); }
+    if (tc) {   // bf16 hi/lo weight tiles in the UMMA layout: packed once by the caller (lmpcr_filter_pack_weights), else split here per call
+      const size_t bb = block_blob_bytes(C, K, half);
+      if (packed) LMPCR_TRY(block_blobs(blk, C, K, half, const_cast<uint8_t*>(packed) + (size_t)it * bb, false, st));
+      else LMPCR_TRY(block_blobs(blk, C, K, half, blob_base, true, st));
     }
     const int Cin = (it == 0 ? 6 : 8) + cfg->side_channel;
     float* logits_it = logits + (size_t)it * P * N;
@@ -984,13 +1065,35 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       LMPCR_TRY(conv_plain(W.in0, (long long)Cin * N, Cin, N, g, blk.conv1, C, W.T0, CN));
       // l1_1 (oanet.py:168): last PointCN writes x1_1 straight into the lower half of the concat buffer
       float* cur_in = W.T0; float* cur_out = W.T1;
-      for (int i = 0; i < half; ++i) {
-        const bool fin = (i == half - 1);
-        float* o = fin ? W.CAT : cur_out;
-        if (fin) { blob_out_for = W.CAT; x11_blob_ready = false; }
-        LMPCR_TRY(pointcn(blk.l1_1[i], cur_in, CN, C, g, W.T2, nullptr, o, fin ? 2 * CN : CN));
-        blob_out_for = nullptr;
-        if (!fin) { float* t = cur_in; cur_in = cur_out; cur_out = t; }
+      // PointCN layers of plain shape (128 -> 128, no shot_cut) run as ONE pair-resident launch when the group is large enough to
+      // give every SM a pair (pcn.cu): 3 HBM passes per layer instead of 5, the intermediate W1 f1(x) never leaves the SM
+      const bool use_pcn = pcn_on && tc && !bn_train && g >= pcn_min_pairs && half <= PCN_MAX_LAYERS && pcn_supported(C, N, W.T0, CN, W.CAT, 2 * CN);
+      auto pcn_layer = [&](const PointCNP& q) {
+        PcnLayer L{};
+        L.w1 = q.c1.blob; L.w2 = q.c2.blob; L.b1 = q.c1.b; L.b2 = q.c2.b;
+        L.bn1 = PcnBN{q.bn1.g, q.bn1.b, q.bn1.rm, q.bn1.rv};
+        L.bn2 = PcnBN{q.bn2.g, q.bn2.b, q.bn2.rm, q.bn2.rv};
+        return L;
+      };
+      if (use_pcn) {
+        LMPCR_TRY(norm_affine(W.T0, CN, C, N, g, 1e-5f, blk.l1_1[0].bn1));
+        PcnArgs pa{};
+        for (int i = 0; i < half; ++i) pa.layer[i] = pcn_layer(blk.l1_1[i]);
+        pa.n_layers = half; pa.scale0 = W.scale; pa.shift0 = W.shift; pa.P = g; pa.N = N; pa.store_out = 1;
+        const int oi = part_index(W.CAT);
+        pa.stats_out = part_buf[oi];
+        LMPCR_TRY(launch_pcn_stack(W.T0, CN, W.CAT, 2 * CN, pa, st));
+        part_valid[oi] = true; part_whole[oi] = true;
+        x11_blob_ready = false;
+      } else {
+        for (int i = 0; i < half; ++i) {
+          const bool fin = (i == half - 1);
+          float* o = fin ? W.CAT : cur_out;
+          if (fin) { blob_out_for = W.CAT; x11_blob_ready = false; }
+          LMPCR_TRY(pointcn(blk.l1_1[i], cur_in, CN, C, g, W.T2, nullptr, o, fin ? 2 * CN : CN));
+          blob_out_for = nullptr;
+          if (!fin) { float* t = cur_in; cur_in = cur_out; cur_out = t; }
+        }
       }
       const float* x11 = W.CAT; const long long x11b = 2 * CN;
       // diff_pool (oanet.py:106-110)
@@ -1014,7 +1117,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         // A operand (x1_1) is shared by the 4 cluster tiles of a pair: split it once into bf16 hi/lo tiles
         if (!x11_blob_ready) LMPCR_TRY(launch_split_weights(x11, C, N, blob_x11, st, g, x11b, N));   // else written by the producing conv's epilogue
         a.a_blob = blob_x11; a.a_blob_batch = (long long)tc_weight_blob_bytes(C, N);
-        part_valid[part_index(W.XD0)] = tc_fast_epilogue(a);
+        part_valid[part_index(W.XD0)] = tc_fast_epilogue(a); part_whole[part_index(W.XD0)] = false;
         a.stats_out = part_valid[part_index(W.XD0)] ? part_buf[part_index(W.XD0)] : nullptr;
         LMPCR_TRY(launch_tcgemm(a, g, st));
       } else {
@@ -1026,7 +1129,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         a.C = W.XD0; a.c_batch = CK; a.c_i = K; a.c_j = 1;
         a.M = C; a.N = K; a.K = N;
         LMPCR_TRY(gemm(a, g, st));
-        part_valid[part_index(W.XD0)] = false;
+        part_valid[part_index(W.XD0)] = false; part_whole[part_index(W.XD0)] = false;
       }
       // l2: OAFilter x half (oanet.py:85-93)
       float* xd_in = W.XD0; float* xd_out = W.XD1;
@@ -1076,7 +1179,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         a.C = W.CAT + CN; a.c_batch = 2 * CN; a.c_i = N; a.c_j = 1;
         a.prologue = defer_up ? TC_PRO_SOFTMAX_DEFER : TC_PRO_SOFTMAX; a.p0 = sm_max; a.p1 = defer_up ? nullptr : sm_inv; a.p_batch = N;
         a.M = C; a.N = N; a.K = K;
-        { const int oi = part_index(W.CAT + CN); part_valid[oi] = tc_fast_epilogue(a); a.stats_out = part_valid[oi] ? part_buf[oi] : nullptr; }
+        { const int oi = part_index(W.CAT + CN); part_valid[oi] = tc_fast_epilogue(a); part_whole[oi] = false; a.stats_out = part_valid[oi] ? part_buf[oi] : nullptr; }
         LMPCR_TRY(launch_tcgemm(a, g, st));
       } else {
         softmax_cols_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g);
@@ -1087,7 +1190,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         a.C = W.CAT + CN; a.c_batch = 2 * CN; a.c_i = N; a.c_j = 1;
         a.M = C; a.N = N; a.K = K;
         LMPCR_TRY(gemm(a, g, st));
-        part_valid[part_index(W.CAT + CN)] = false;
+        part_valid[part_index(W.CAT + CN)] = false; part_whole[part_index(W.CAT + CN)] = false;
       }
       // l1_2 (oanet.py:171): PointCN(2C -> C) with shot_cut, then half-1 PointCN(C); T1/T0 ping-pong, T2 = temp
       float* lat_dst = (last && latent) ? latent + (size_t)p0 * CN : nullptr;
@@ -1101,7 +1204,20 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         LMPCR_TRY(pointcn(blk.l1_2[0], W.CAT, 2 * CN, 2 * C, g, W.T2, W.T0, o, CN));
         cur_in = o; cur_out = W.T0;
       }
-      for (int i = 1; i < half; ++i) {
+      int i_first = 1;
+      if (use_pcn && half >= 3) {
+        // the middle layers (all but the last, which carries the fused output head) in place on the buffer l1_2.0 has just written
+        LMPCR_TRY(norm_affine(cur_in, CN, C, N, g, 1e-5f, blk.l1_2[1].bn1));
+        PcnArgs pa{};
+        for (int i = 1; i < half - 1; ++i) pa.layer[i - 1] = pcn_layer(blk.l1_2[i]);
+        pa.n_layers = half - 2; pa.scale0 = W.scale; pa.shift0 = W.shift; pa.P = g; pa.N = N; pa.store_out = 1;
+        const int oi = part_index(cur_in);
+        pa.stats_out = oi >= 0 ? part_buf[oi] : nullptr;
+        LMPCR_TRY(launch_pcn_stack(cur_in, CN, cur_in, CN, pa, st));
+        if (oi >= 0) { part_valid[oi] = true; part_whole[oi] = true; }
+        i_first = half - 1;
+      }
+      for (int i = i_first; i < half; ++i) {
         float* o = (i == half - 1 && lat_dst) ? lat_dst : cur_out;
         if (i == half - 1) arm_head(o);
         LMPCR_TRY(pointcn(blk.l1_2[i], cur_in, CN, C, g, W.T2, nullptr, o, CN));

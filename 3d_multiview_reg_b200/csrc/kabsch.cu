@@ -107,7 +107,7 @@ __device__ bool rotation_from_cov(const float H[9], float Rout[9]) {
 }
 
 __global__ void __launch_bounds__(KB_WARPS * 32)
-kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int ld, const float* __restrict__ wg, int P,
+kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int ld, const float* wg, int P,
               int N, int guard_mode, const int32_t* __restrict__ guard_flag, float* w_out, float* __restrict__ Rg,
               float* __restrict__ tg, float* __restrict__ resg, float* __restrict__ confg, uint32_t* statusg) {
   const int lane = threadIdx.x & 31;
@@ -115,7 +115,7 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
   if (p >= P) return;
   const float* x1 = x1g + (size_t)p * N * ld;
   const float* x2 = x2g + (size_t)p * N * ld;
-  const float* w = wg + (size_t)p * N;
+  const float* w = wg + (size_t)p * N;     // may alias w_out (guarded weights written in sweep 3): plain loads, no __restrict__ / __ldg
   const float eps = 1e-7f;
   const float invN = 1.0f / (float)N;
   bool guard = (guard_mode == LMPCR_GUARD_BATCH) && guard_flag != nullptr && (*guard_flag != 0);
@@ -128,7 +128,7 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
     float s0 = 0.f, sraw = 0.f, b1[3] = {0.f, 0.f, 0.f}, b2[3] = {0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int i = lane; i < N; i += 32) {
-      const float wraw = __ldg(w + i);
+      const float wraw = w[i];
       const float wi = wraw + add;
       const float* r1 = x1 + (size_t)i * ld;
       const float* r2 = x2 + (size_t)i * ld;
@@ -172,7 +172,7 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
   for (int k = 0; k < 9; ++k) h[k] = 0.f;
 #pragma unroll 2
   for (int i = lane; i < N; i += 32) {
-    const float wi = (__ldg(w + i) + add) / denom;
+    const float wi = (w[i] + add) / denom;
     const float* r1 = x1 + (size_t)i * ld;
     const float* r2 = x2 + (size_t)i * ld;
     float c1[3], c2[3];
@@ -197,7 +197,10 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
     if (!ok) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.f : 0.f;
-      T[0] = T[1] = T[2] = 0.f;   // reference failure path: r = I, t = 0  (:217-219)
+      // rotation undetermined (rank < 2).  The reference reaches r = I, t = 0 only when the SVD throws (:217-219); otherwise it always
+      // forms t = mean2 - R mean1 (:232) -- with R = I that is the centroid offset, which is what we return (status bit DEGENERATE)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) T[a] = m2[a] - m1[a];
     } else {
 #pragma unroll
       for (int a = 0; a < 3; ++a) T[a] = m2[a] - (R[3 * a] * m1[0] + R[3 * a + 1] * m1[1] + R[3 * a + 2] * m1[2]);  // :232
@@ -217,7 +220,7 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
   float wr2 = 0.f;
 #pragma unroll 2
   for (int i = lane; i < N; i += 32) {
-    const float wi = __ldg(w + i) + add;
+    const float wi = w[i] + add;
     const float* r1 = x1 + (size_t)i * ld;
     const float* r2 = x2 + (size_t)i * ld;
     const float px = __ldg(r1), py = __ldg(r1 + 1), pz = __ldg(r1 + 2);

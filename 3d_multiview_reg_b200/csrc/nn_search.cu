@@ -257,7 +257,8 @@ __global__ void gather_xyz_kernel(const float* __restrict__ b_xyz, int n_b, cons
   if (gid >= (size_t)n_jobs * n_q) return;
   const int job = (int)(gid / n_q);
   const int bs = __ldg(jobs + 2 * job + 1);
-  const float* src = b_xyz + ((size_t)bs * n_b + __ldg(idx + gid)) * 3;
+  const int j = min(max(__ldg(idx + gid), 0), n_b - 1);      // an index outside the set (corrupt input) must not become a wild read
+  const float* src = b_xyz + ((size_t)bs * n_b + j) * 3;
   out[gid * 3 + 0] = __ldg(src);
   out[gid * 3 + 1] = __ldg(src + 1);
   out[gid * 3 + 2] = __ldg(src + 2);
@@ -271,15 +272,16 @@ __global__ void mutual_xs_kernel(const float* __restrict__ xyz, int n_pts, const
   const int p = (int)(gid / n_pts);
   const int i = (int)(gid - (size_t)p * n_pts);
   const int s = __ldg(pairs + 2 * p), t = __ldg(pairs + 2 * p + 1);
-  const int j = __ldg(idx_st + gid);
+  const int j = min(max(__ldg(idx_st + gid), 0), n_pts - 1);  // indices are clamped: a corrupt index must not become a wild read
   const float* ps = xyz + ((size_t)s * n_pts + i) * 3;
   const float* pt = xyz + ((size_t)t * n_pts + j) * 3;
   const float sx = __ldg(ps), sy = __ldg(ps + 1), sz = __ldg(ps + 2);
   uint8_t m = 0;
   if (mutual != nullptr || C == 7) {
-    const int back = __ldg(idx_ts + (size_t)p * n_pts + j);
+    const int back_raw = __ldg(idx_ts + (size_t)p * n_pts + j);
+    const int back = min(max(back_raw, 0), n_pts - 1);
     if (mode == LMPCR_MUTUAL_INDEX) {
-      m = (back == i);
+      m = (back_raw == i);
     } else {
       const float* pb = xyz + ((size_t)s * n_pts + back) * 3;
       const float dx = sx - __ldg(pb), dy = sy - __ldg(pb + 1), dz = sz - __ldg(pb + 2);

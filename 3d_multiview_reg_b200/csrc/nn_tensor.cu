@@ -406,7 +406,9 @@ nn_rescore_kernel(const float* __restrict__ q_feat, const float* __restrict__ sq
       if (od < best || (od == best && oj < bj)) { best = od; bj = oj; }
     }
     if (lane == 0) {
-      idx_out[w] = bj;
+      // a row of NaN / Inf features compares false everywhere: return index 0 like the exact SIMT kernel (the reference's
+      // argmin of an all-NaN row is a valid index too), never the 0x7fffffff sentinel
+      idx_out[w] = (bj < n_b) ? bj : 0;
       if (dist_out) dist_out[w] = best;
     }
   }
@@ -478,11 +480,15 @@ int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float*
   }
   uint2* cand = reinterpret_cast<uint2*>(p);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(nn_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
-    LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "nn_sweep_kernel: cannot reserve %zu bytes of shared memory: %s", SWEEP_SMEM, cudaGetErrorString(e));
-    attr_set = true;
+  {
+    // the opt-in to large dynamic shared memory is per device: remembered per device ordinal (benign race: setting it twice is harmless)
+    static unsigned char attr_set[64];
+    const int dev = device_ordinal();
+    if (!attr_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(nn_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
+      LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "nn_sweep_kernel: cannot reserve %zu bytes of shared memory: %s", SWEEP_SMEM, cudaGetErrorString(e));
+      attr_set[dev] = 1;
+    }
   }
   SweepArgs a;
   a.form_q = PQ.form_q; a.form_b = PB.form_b; a.rstat_q = PQ.rstat; a.set_bmax = PB.bmax; a.set_dbmax = PB.dbmax;

@@ -1,0 +1,477 @@
+// Pair-resident fused PointCN stack for the filtering network (tcgen05 / TMEM / TMA tensor maps), sm_100a.
+//
+// A PointCN layer (lib/filtering/oanet.py:18-43) is   z = x + W2 f2(W1 f1(x) + b1) + b2   with f = ReLU o BatchNorm(eval) o
+// InstanceNorm: every f needs the mean / variance of its input over ALL points of the pair, which is why the per-layer GEMM
+// path (tcgemm.cu) runs one launch per convolution and streams x, W1 f1(x), and z through HBM five times per layer.
+//
+// Here ONE CTA OWNS A PAIR: all per-pair reductions are CTA-local, so a whole stack of PointCN layers runs in one launch
+// without grid-wide synchronisation, and W1 f1(x) never leaves the SM.  Per layer the CTA streams its pair twice:
+//   pass A  x tile -> f1 -> h1 (bf16 hi/lo, smem) -> tcgen05 W1.h1 -> TMEM -> per-channel mean / variance of y = W1 h1 + b1
+//   pass B  x tile -> f1 -> h1 -> W1.h1 -> TMEM -> f2 (statistics of pass A) -> h2 (smem) -> tcgen05 W2.h2 -> TMEM -> + b2 + x
+//           -> statistics of z (f1 of the next layer) -> tile stored in place of the x tile
+// 3 HBM passes per layer instead of 5, both weight matrices resident in shared memory (128 KB as bf16 hi/lo), the residual
+// is the x tile that is in shared memory anyway, and tiles move by TMA (tensor maps, SWIZZLE_128B: thread = channel row reads
+// and writes its 128-byte row conflict-free) -- no per-element address arithmetic, no register-staged global loads.
+// Products are split-bf16 (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, fp32 accumulation in TMEM) exactly as in tcgemm.cu.
+//
+// Warp roles (448 threads, one CTA per SM):
+//   warp 0       TMA: x tile loads (+ L2 prefetch a few tiles ahead), weight loads, output tile stores
+//   warp 1       tcgen05.mma issue (M128 x N32 x K16, 24 per GEMM tile)
+//   warps 2-5    TMEM readers A: pass A statistics of y; pass B f2 + hi/lo split -> h2
+//   warps 6-9    TMEM readers B: pass B epilogue (z + b2 + x, statistics, tile written back over the x tile)
+//   warps 10-13  producers: x tile (smem, fp32) -> f1 -> hi/lo split -> h1
+// Thread t of every 4-warp role owns channel ((warp & 3) << 5) | lane = the TMEM lane its warp may read.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "pcn.cuh"
+#include "tc_ptx.cuh"
+
+namespace lmpcr {
+namespace {
+
+constexpr int C = PCN_C;                     // channels = M = K of both GEMMs
+constexpr int TP = 32;                       // points per tile (= 128 bytes per channel row: one SWIZZLE_128B span)
+constexpr int NX = 4;                        // x-tile ring
+constexpr int PF_DIST = 8;                   // L2 prefetch distance in tiles
+constexpr int W_BYTES = 4 * 2 * 128 * 32 * 2;   // one convolution: 4 k-chunks x [hi 8 KB | lo 8 KB] = 64 KB
+constexpr int X_BYTES = C * TP * 4;          // 16 KB
+constexpr int HP_BYTES = C * TP * 2;         // one bf16 part of an h tile: 8 KB
+constexpr int H_BYTES = 2 * HP_BYTES;        // hi | lo
+constexpr int OFF_W1 = 0, OFF_W2 = W_BYTES, OFF_X = 2 * W_BYTES, OFF_H1 = OFF_X + NX * X_BYTES, OFF_H2 = OFF_H1 + H_BYTES;
+constexpr int OFF_SC = OFF_H2 + H_BYTES;     // sc1[128], sh1[128]: f1 of the next layer, written by the epilogue threads
+constexpr int OFF_BAR = OFF_SC + 2 * C * 4;
+constexpr int N_BARS = 3 * NX + 13;
+constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
+constexpr size_t SMEM_BYTES = OFF_TMEM + 16;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
+constexpr int NTHREADS = 14 * 32;
+constexpr int TMEM_COLS = 128;               // y[2] | z[2], 32 columns each
+constexpr uint32_t K_LBO = 128, K_SBO = 512;             // weight chunk (K-major, 32 k): k-groups adjacent, 8-row groups 512 B apart
+constexpr uint32_t MN_SBO = 128, MN_LBO = (TP / 8) * 128;   // h tile (MN-major): point-groups adjacent, channel-groups 512 B apart
+constexpr uint32_t IDESC = make_idesc(1, 0, 1, 128, TP);
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 32 fp32 values of one channel row -> bf16 hi/lo in the MN-major operand image: channel-group (k>>3) at 512 B, point-group g at
+// 128 B, row (k&7) at 16 B; the lo part HP_BYTES further
+__device__ __forceinline__ void store_h_row(uint8_t* hbase, int k, const float (&v)[TP]) {
+  uint8_t* row = hbase + (k >> 3) * MN_LBO + (k & 7) * 16;
+#pragma unroll
+  for (int gq = 0; gq < TP / 8; ++gq) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float a = v[8 * gq + 2 * q], b = v[8 * gq + 2 * q + 1];
+      const __nv_bfloat162 hv = __floats2bfloat162_rn(a, b);
+      const float2 hf = __bfloat1622float2(hv);
+      const __nv_bfloat162 lv = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+      h[q] = *reinterpret_cast<const uint32_t*>(&hv);
+      l[q] = *reinterpret_cast<const uint32_t*>(&lv);
+    }
+    *reinterpret_cast<uint4*>(row + gq * MN_SBO) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(row + gq * MN_SBO + HP_BYTES) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// one channel row (32 floats = 8 chunks of 16 bytes) of a SWIZZLE_128B tile: chunk c of row r sits at chunk position c ^ (r & 7)
+__device__ __forceinline__ void load_x_row(const uint8_t* xt, int r, float (&v)[TP]) {
+  const uint8_t* row = xt + r * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 q = *reinterpret_cast<const float4*>(row + ((c ^ (r & 7)) << 4));
+    v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+  }
+}
+__device__ __forceinline__ void store_x_row(uint8_t* xt, int r, const float (&v)[TP]) {
+  uint8_t* row = xt + r * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(row + ((c ^ (r & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+
+// shifted running sums of one channel: pivot c0 = the first value seen, then per-tile partial sums folded into the totals
+struct RunStat {
+  float c0, s1, s2; bool have;
+  __device__ __forceinline__ void reset() { c0 = 0.f; s1 = 0.f; s2 = 0.f; have = false; }
+  __device__ __forceinline__ void add_tile(const float (&v)[TP], int ncv) {
+    if (!have) { c0 = v[0]; have = true; }
+    float a = 0.f, b = 0.f;
+    if (ncv >= TP) {
+#pragma unroll
+      for (int i = 0; i < TP; ++i) { const float d = v[i] - c0; a += d; b = fmaf(d, d, b); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < TP; ++i) if (i < ncv) { const float d = v[i] - c0; a += d; b = fmaf(d, d, b); }
+    }
+    s1 += a; s2 += b;
+  }
+  __device__ __forceinline__ void finish(int n, float& mean, float& var) const {
+    const float inv = 1.0f / (float)n, m = s1 * inv;
+    mean = c0 + m;
+    var = fmaxf(s2 * inv - m * m, 0.f);
+  }
+};
+
+// InstanceNorm (biased variance, eps) + eval BatchNorm -> relu(x * sc + sh)       (oanet.py:27-28,31-32)
+__device__ __forceinline__ void fold_affine(float mean, float var, float eps_in, const PcnBN& bn, int c, float& sc, float& sh) {
+  const float rstd = 1.0f / sqrtf(var + eps_in);
+  const float gsc = __ldg(bn.g + c) / sqrtf(__ldg(bn.rv + c) + 1e-5f);
+  sc = rstd * gsc;
+  sh = (-mean * rstd - __ldg(bn.rm + c)) * gsc + __ldg(bn.b + c);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const PcnArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* sc1_s = reinterpret_cast<float*>(smem + OFF_SC);
+  float* sh1_s = sc1_s + C;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  const uint32_t bar0 = smem_u32(smem + OFF_BAR);
+  auto XFULL = [&](int s) { return bar0 + 8u * s; };
+  auto XREAD = [&](int s) { return bar0 + 8u * (NX + s); };
+  auto OUTRDY = [&](int s) { return bar0 + 8u * (2 * NX + s); };
+  const uint32_t H1FULL = bar0 + 8u * (3 * NX), H1EMPTY = H1FULL + 8, H2FULL = H1FULL + 16, H2EMPTY = H1FULL + 24, WFULL = H1FULL + 32;
+  auto YFULL = [&](int a) { return H1FULL + 40 + 8u * a; };
+  auto YEMPTY = [&](int a) { return H1FULL + 56 + 8u * a; };
+  auto ZFULL = [&](int a) { return H1FULL + 72 + 8u * a; };
+  auto ZEMPTY = [&](int a) { return H1FULL + 88 + 8u * a; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch = ((warp & 3) << 5) | lane;                 // channel row / TMEM lane owned by this thread in the 4-warp roles
+  const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+  const int n_tiles = (g.N + TP - 1) / TP;
+  const uint32_t sX = smem_u32(smem + OFF_X), sH1 = smem_u32(smem + OFF_H1), sH2 = smem_u32(smem + OFF_H2);
+  const uint32_t sW1 = smem_u32(smem + OFF_W1), sW2 = smem_u32(smem + OFF_W2);
+
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmY = tmem_base, tmZ = tmem_base + 2 * TP;
+
+  // all barriers are re-initialised at the start of every pass (the pipeline is fully drained at a pass boundary), so the phase
+  // arithmetic of every role is local to a pass: use k of a ring slot / of a single barrier completes phase k
+  auto pass_begin = [&]() {
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < NX; ++s) { mbar_init(XFULL(s), 1); mbar_init(XREAD(s), 4); mbar_init(OUTRDY(s), 4); }
+      mbar_init(H1FULL, 4); mbar_init(H1EMPTY, 1); mbar_init(H2FULL, 4); mbar_init(H2EMPTY, 1); mbar_init(WFULL, 1);
+      for (int a = 0; a < 2; ++a) { mbar_init(YFULL(a), 1); mbar_init(YEMPTY(a), 128); mbar_init(ZFULL(a), 1); mbar_init(ZEMPTY(a), 128); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  };
+  auto pass_end = [&]() {
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  };
+
+  // one GEMM tile: D[128 x 32] = W (resident blob at sW) . h (operand image at sH), three bf16 products per K step
+  auto issue_gemm = [&](uint32_t sW, uint32_t sH, uint32_t d_tmem) {
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t a0 = sW + kc * (2 * 8192) + ks * 2 * K_LBO;
+        const uint32_t b0 = sH + (kc * 4 + ks * 2) * MN_LBO;
+        const uint64_t a_hi = make_desc(a0, K_LBO, K_SBO), a_lo = make_desc(a0 + 8192, K_LBO, K_SBO);
+        const uint64_t b_hi = make_desc(b0, MN_LBO, MN_SBO), b_lo = make_desc(b0 + HP_BYTES, MN_LBO, MN_SBO);
+        tc_mma_f16(d_tmem, a_lo, b_hi, IDESC, (kc | ks) ? 1u : 0u);     // small terms first
+        tc_mma_f16(d_tmem, a_hi, b_lo, IDESC, 1u);
+        tc_mma_f16(d_tmem, a_hi, b_hi, IDESC, 1u);
+      }
+    }
+  };
+
+  float sc1 = 1.f, sh1 = 0.f;      // producers: f1 of the current layer for channel `ch`
+  float sc2 = 1.f, sh2 = 0.f;      // TMEM readers A: f2 (with conv1's bias folded into the shift)
+  RunStat rs;                      // TMEM readers A (pass A: y) / B (pass B: z)
+
+  for (int p = blockIdx.x; p < g.P; p += gridDim.x) {
+    for (int l = 0; l < g.n_layers; ++l) {
+      const PcnLayer& L = g.layer[l];
+      const CUtensorMap* tm_src = (l == 0) ? &tm_in : &tm_out;
+      if (warp >= 10) {
+        if (l == 0) { sc1 = __ldg(g.scale0 + (size_t)p * C + ch); sh1 = __ldg(g.shift0 + (size_t)p * C + ch); }
+        else { sc1 = sc1_s[ch]; sh1 = sh1_s[ch]; }
+      }
+      // ======================================================== pass A: statistics of y = W1 f1(x) + b1
+      pass_begin();
+      if (warp == 0) {
+        if (lane == 0) {
+          mbar_expect_tx(WFULL, 2 * W_BYTES);
+#pragma unroll 1
+          for (int i = 0; i < 4; ++i) {
+            bulk_g2s(sW1 + i * 16384, L.w1 + i * 16384, 16384, WFULL);
+            bulk_g2s(sW2 + i * 16384, L.w2 + i * 16384, 16384, WFULL);
+          }
+          for (int t = 0; t < PF_DIST && t < n_tiles; ++t) tma_prefetch_3d(tm_src, t * TP, 0, p);
+          for (int t = 0; t < n_tiles; ++t) {
+            const int s = t % NX;
+            if (t >= NX) mbar_wait(XREAD(s), ((t / NX) - 1) & 1);
+            mbar_expect_tx(XFULL(s), X_BYTES);
+            tma_load_3d(sX + s * X_BYTES, tm_src, t * TP, 0, p, XFULL(s));
+            if (t + PF_DIST < n_tiles) tma_prefetch_3d(tm_src, (t + PF_DIST) * TP, 0, p);
+          }
+        }
+      } else if (warp == 1) {
+        if (lane == 0) {
+          mbar_wait(WFULL, 0);
+          for (int t = 0; t < n_tiles; ++t) {
+            const int a = t & 1;
+            mbar_wait(H1FULL, t & 1);
+            mbar_wait(YEMPTY(a), ((t >> 1) & 1) ^ 1);
+            tc_fence_after();
+            issue_gemm(sW1, sH1, tmY + a * TP);
+            tc_commit(H1EMPTY);
+            tc_commit(YFULL(a));
+          }
+          mbar_wait(H1EMPTY, (n_tiles - 1) & 1);
+        }
+      } else if (warp < 6) {
+        rs.reset();
+        const float b1 = __ldg(L.b1 + ch);
+        for (int t = 0; t < n_tiles; ++t) {
+          const int a = t & 1;
+          mbar_wait(YFULL(a), (t >> 1) & 1);
+          tc_fence_after();
+          float v[TP];
+          tc_ld32(tmY + lane_sel + a * TP, v);
+          tc_fence_before();
+          mbar_arrive(YEMPTY(a));
+#pragma unroll
+          for (int i = 0; i < TP; ++i) v[i] += b1;
+          rs.add_tile(v, g.N - t * TP);
+        }
+        float mean, var;
+        rs.finish(g.N, mean, var);
+        fold_affine(mean, var, 1e-5f, L.bn2, ch, sc2, sh2);
+        sh2 = fmaf(b1, sc2, sh2);            // f2(acc + b1) = relu(acc * sc2 + (b1 * sc2 + sh2))
+      } else if (warp >= 10) {
+        for (int t = 0; t < n_tiles; ++t) {
+          const int s = t % NX;
+          mbar_wait(XFULL(s), (t / NX) & 1);
+          float v[TP];
+          load_x_row(smem + OFF_X + s * X_BYTES, ch, v);
+#pragma unroll
+          for (int i = 0; i < TP; ++i) v[i] = fmaxf(fmaf(v[i], sc1, sh1), 0.f);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(XREAD(s));        // the tile is in registers: the slot may be refilled
+          mbar_wait(H1EMPTY, (t & 1) ^ 1);
+          store_h_row(smem + OFF_H1, ch, v);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(H1FULL);
+        }
+      }
+      pass_end();
+      // ======================================================== pass B: z = x + W2 f2(W1 f1(x) + b1) + b2
+      const CUtensorMap* tm_dst = &tm_out;
+      pass_begin();
+      if (warp == 0) {
+        if (lane == 0) {
+          for (int t = 0; t < PF_DIST && t < n_tiles; ++t) tma_prefetch_3d(tm_src, t * TP, 0, p);
+          for (int t = 0; t < n_tiles; ++t) {
+            const int s = t % NX;
+            if (t >= NX) {
+              const int u = t - NX;
+              mbar_wait(OUTRDY(s), (u / NX) & 1);
+              tma_store_3d(tm_dst, sX + s * X_BYTES, u * TP, 0, p);
+              bulk_commit();
+              bulk_wait_read0();
+            }
+            mbar_expect_tx(XFULL(s), X_BYTES);
+            tma_load_3d(sX + s * X_BYTES, tm_src, t * TP, 0, p, XFULL(s));
+            if (t + PF_DIST < n_tiles) tma_prefetch_3d(tm_src, (t + PF_DIST) * TP, 0, p);
+          }
+          for (int u = (n_tiles > NX ? n_tiles - NX : 0); u < n_tiles; ++u) {
+            const int s = u % NX;
+            mbar_wait(OUTRDY(s), (u / NX) & 1);
+            tma_store_3d(tm_dst, sX + s * X_BYTES, u * TP, 0, p);
+            bulk_commit();
+          }
+          bulk_wait0();                                   // the pair's new activations are in global memory before the next pass reads them
+        }
+      } else if (warp == 1) {
+        if (lane == 0) {
+          for (int t = 0; t <= n_tiles; ++t) {
+            if (t < n_tiles) {
+              const int a = t & 1;
+              mbar_wait(H1FULL, t & 1);
+              mbar_wait(YEMPTY(a), ((t >> 1) & 1) ^ 1);
+              tc_fence_after();
+              issue_gemm(sW1, sH1, tmY + a * TP);
+              tc_commit(H1EMPTY);
+              tc_commit(YFULL(a));
+            }
+            if (t >= 1) {
+              const int u = t - 1, a = u & 1;
+              mbar_wait(H2FULL, u & 1);
+              mbar_wait(ZEMPTY(a), ((u >> 1) & 1) ^ 1);
+              tc_fence_after();
+              issue_gemm(sW2, sH2, tmZ + a * TP);
+              tc_commit(H2EMPTY);
+              tc_commit(ZFULL(a));
+            }
+          }
+          mbar_wait(H1EMPTY, (n_tiles - 1) & 1);
+          mbar_wait(H2EMPTY, (n_tiles - 1) & 1);
+        }
+      } else if (warp < 6) {
+        for (int t = 0; t < n_tiles; ++t) {
+          const int a = t & 1;
+          mbar_wait(YFULL(a), (t >> 1) & 1);
+          tc_fence_after();
+          float v[TP];
+          tc_ld32(tmY + lane_sel + a * TP, v);
+          tc_fence_before();
+          mbar_arrive(YEMPTY(a));
+#pragma unroll
+          for (int i = 0; i < TP; ++i) v[i] = fmaxf(fmaf(v[i], sc2, sh2), 0.f);
+          mbar_wait(H2EMPTY, (t & 1) ^ 1);
+          store_h_row(smem + OFF_H2, ch, v);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(H2FULL);
+        }
+      } else if (warp < 10) {
+        rs.reset();
+        const float b2 = __ldg(L.b2 + ch);
+        for (int t = 0; t < n_tiles; ++t) {
+          const int a = t & 1, s = t % NX;
+          mbar_wait(ZFULL(a), (t >> 1) & 1);
+          tc_fence_after();
+          float v[TP];
+          tc_ld32(tmZ + lane_sel + a * TP, v);
+          tc_fence_before();
+          mbar_arrive(ZEMPTY(a));
+          mbar_wait(XFULL(s), (t / NX) & 1);              // completed long ago (the producers consumed the tile): orders our reads after the TMA write
+          uint8_t* xt = smem + OFF_X + s * X_BYTES;
+          float x[TP];
+          load_x_row(xt, ch, x);
+#pragma unroll
+          for (int i = 0; i < TP; ++i) v[i] = (v[i] + b2) + x[i];
+          rs.add_tile(v, g.N - t * TP);
+          store_x_row(xt, ch, v);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(OUTRDY(s));
+        }
+        float mean, var;
+        rs.finish(g.N, mean, var);
+        if (l + 1 < g.n_layers) {
+          float sc, sh;
+          fold_affine(mean, var, 1e-5f, g.layer[l + 1].bn1, ch, sc, sh);
+          sc1_s[ch] = sc; sh1_s[ch] = sh;
+        } else if (g.stats_out) {
+          *reinterpret_cast<float2*>(g.stats_out + ((size_t)p * C + ch) * 2) = make_float2(mean, var * (float)g.N);
+        }
+      } else {
+        for (int t = 0; t < n_tiles; ++t) {
+          const int s = t % NX;
+          mbar_wait(XFULL(s), (t / NX) & 1);
+          float v[TP];
+          load_x_row(smem + OFF_X + s * X_BYTES, ch, v);
+#pragma unroll
+          for (int i = 0; i < TP; ++i) v[i] = fmaxf(fmaf(v[i], sc1, sh1), 0.f);
+          mbar_wait(H1EMPTY, (t & 1) ^ 1);
+          store_h_row(smem + OFF_H1, ch, v);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(H1FULL);
+        }
+      }
+      pass_end();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    else
+      cudaGetLastError();
+    tried = true;
+  }
+  return fn;
+}
+
+// activations [P, C, N] fp32 with batch stride `batch` floats -> 3-D tensor map (N, C, P), box 32 points x 128 channels, SWIZZLE_128B
+int make_act_map(CUtensorMap* tm, const float* base, int N, long long batch, int P) {
+  PFN_cuTensorMapEncodeTiled_v12000 fn = encode_fn();
+  LMPCR_REQUIRE(fn, LMPCR_ERR_UNSUPPORTED, "pcn: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)C, (cuuint64_t)P};
+  const cuuint64_t strides[2] = {(cuuint64_t)N * 4, (cuuint64_t)batch * 4};
+  const cuuint32_t box[3] = {TP, C, 1}, estr[3] = {1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LMPCR_REQUIRE(r == CUDA_SUCCESS, LMPCR_ERR_LAUNCH, "pcn: cuTensorMapEncodeTiled failed (%d) for N=%d batch=%lld P=%d", (int)r, N, batch, P);
+  return LMPCR_OK;
+}
+
+}  // namespace
+
+bool pcn_supported(int Cc, int N, const float* x_in, long long in_batch, const float* x_out, long long out_batch) {
+  return Cc == C && N >= 1 && (N & 3) == 0 && (in_batch & 3) == 0 && (out_batch & 3) == 0 && ((reinterpret_cast<uintptr_t>(x_in) & 15) == 0) &&
+         ((reinterpret_cast<uintptr_t>(x_out) & 15) == 0) && encode_fn() != nullptr;
+}
+
+int launch_pcn_stack(const float* x_in, long long in_batch, float* x_out, long long out_batch, const PcnArgs& a, cudaStream_t st) {
+  LMPCR_REQUIRE(x_in && x_out && a.P > 0 && a.N > 0 && a.n_layers >= 1 && a.n_layers <= PCN_MAX_LAYERS && a.scale0 && a.shift0, LMPCR_ERR_ARG,
+                "pcn_stack: bad arguments");
+  LMPCR_REQUIRE(pcn_supported(C, a.N, x_in, in_batch, x_out, out_batch), LMPCR_ERR_UNSUPPORTED,
+                "pcn_stack: needs 128 channels, N %% 4 == 0, 16-byte aligned activations and a driver with tensor maps");
+  LMPCR_REQUIRE(!a.lg_w, LMPCR_ERR_UNSUPPORTED, "pcn_stack: fused head not built");
+  for (int l = 0; l < a.n_layers; ++l) {
+    const PcnLayer& L = a.layer[l];
+    LMPCR_REQUIRE(L.w1 && L.w2 && L.b1 && L.b2 && L.bn2.g && L.bn2.b && L.bn2.rm && L.bn2.rv && (l == 0 || (L.bn1.g && L.bn1.b && L.bn1.rm && L.bn1.rv)) &&
+                  ((reinterpret_cast<uintptr_t>(L.w1) | reinterpret_cast<uintptr_t>(L.w2)) & 15) == 0, LMPCR_ERR_ARG, "pcn_stack: layer %d parameters", l);
+  }
+  CUtensorMap tm_in, tm_out;
+  LMPCR_TRY(make_act_map(&tm_in, x_in, a.N, in_batch, a.P));
+  LMPCR_TRY(make_act_map(&tm_out, x_out, a.N, out_batch, a.P));
+  {
+    static unsigned char attr_set[64];
+    const int dev = device_ordinal();
+    if (!attr_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(pcn_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "pcn_stack: cannot reserve %zu bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
+      attr_set[dev] = 1;
+    }
+  }
+  const int grid = a.P < sm_count() ? a.P : sm_count();
+  pcn_stack_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_out, a);
+  return check_launch("pcn_stack_kernel");
+}
+
+}  // namespace lmpcr

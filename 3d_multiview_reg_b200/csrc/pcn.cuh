@@ -1,0 +1,35 @@
+// Pair-resident fused PointCN stack (pcn.cu): see the header comment there.
+#pragma once
+#include "common.cuh"
+
+namespace lmpcr {
+
+constexpr int PCN_MAX_LAYERS = 4;
+constexpr int PCN_C = 128;          // channels of the layers this kernel handles (lib/filtering/oanet.py: net_channel = 128)
+
+struct PcnBN { const float* g; const float* b; const float* rm; const float* rv; };
+struct PcnLayer {
+  // pre-split weights of conv.3 / conv.7 (lib/filtering/oanet.py:30,34): launch_split_weights(W, 128, 128) = 4 k-chunks x [hi 8 KB | lo 8 KB]
+  const uint8_t* w1; const uint8_t* w2;
+  const float* b1; const float* b2;
+  PcnBN bn1, bn2;                   // conv.1 (in front of conv.3) and conv.5 (in front of conv.7); bn1 is unused for the first layer
+};
+
+struct PcnArgs {
+  PcnLayer layer[PCN_MAX_LAYERS];
+  int n_layers;
+  const float* scale0; const float* shift0;   // [P,128]: InstanceNorm + BatchNorm of the stack's input folded to relu(x*scale+shift)
+  float* stats_out;                           // optional [P,128,2] = (mean, M2 over the N points) of the stack's output
+  // optional fused 1-channel head on the stack's output (the network's `output` conv + weights, oanet.py:173-175)
+  const float* lg_w; const float* lg_b; float* lg_logits; float* lg_scores; int32_t* lg_anypos;
+  int store_out;                              // 0: with the head present the output tiles themselves are not stored
+  int P, N;
+};
+
+// x_in [P,128,N] (batch stride in_batch floats) -> x_out (batch stride out_batch; may be the same buffer: the stack then runs in place).
+// Needs N % 4 == 0 and 16-byte aligned bases (TMA tensor maps).  Returns LMPCR_ERR_UNSUPPORTED when the driver entry point for
+// tensor maps is not available.
+bool pcn_supported(int C, int N, const float* x_in, long long in_batch, const float* x_out, long long out_batch);
+int launch_pcn_stack(const float* x_in, long long in_batch, float* x_out, long long out_batch, const PcnArgs& args, cudaStream_t st);
+
+}  // namespace lmpcr

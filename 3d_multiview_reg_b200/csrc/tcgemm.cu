@@ -1102,13 +1102,17 @@ int launch_tcgemm(const TcGemmArgs& a_in, int batch, cudaStream_t st) {
     }
   }
   {
-    static kern_t done[16]; static int n_done = 0;       // opt in to the large dynamic shared memory once per instance
+    // opt in to the large dynamic shared memory once per (device, instance): the attribute is per device / context, so a process that
+    // drives several GPUs must set it on each (benign race between host threads: setting it twice is harmless)
+    static kern_t done[64][16]; static unsigned char n_done[64];
+    const int dev = device_ordinal();
     bool seen = false;
-    for (int i = 0; i < n_done; ++i) seen = seen || (done[i] == k);
+    const int nd = n_done[dev] < 16 ? n_done[dev] : 16;
+    for (int i = 0; i < nd; ++i) seen = seen || (done[dev][i] == k);
     if (!seen) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
       LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "tcgemm: cannot reserve %zu bytes of shared memory", SMEM_BYTES);
-      if (n_done < 16) done[n_done++] = k;
+      if (nd < 16) { done[dev][nd] = k; n_done[dev] = (unsigned char)(nd + 1); }
     }
   }
   k<<<grid, NTHREADS, SMEM_BYTES, st>>>(a, batch);

@@ -82,7 +82,10 @@ class OANet(nn.Module):
         self.clusters = m["clusters"]
         self.side_channel = (cfg["data"]["use_mutuals"] == 2)
         self.guard_mode = _cabi.GUARD_BATCH        # reference semantics (oanet.py:177-178); scene.py uses GUARD_PAIR
-        self.gemm_algo = int(m.get("gemm_algo", 0))
+        # 1 = tcgen05 split-bf16 GEMMs (the measured path; the reference's YAMLs carry no such key, so they get it); 0 = fp32 CUDA cores
+        self.gemm_algo = int(m.get("gemm_algo", 1))
+        self._packed = None           # (key, packed weight blobs): rebuilt when a conv weight changes (load_state_dict, .to(), optimiser step)
+        self._workspace = None        # scratch of the last forward, reused while it is large enough
         self.device = torch.device("cuda" if (torch.cuda.is_available() and m["use_gpu"]) else "cpu")
         self._schema = param_schema(self.net_channel, self.clusters, self.net_depth, self.iter_num, int(self.side_channel))
         for name, shape, kind in self._schema:
@@ -122,6 +125,18 @@ class OANet(nn.Module):
         sd.update(dict(self.named_buffers()))
         return [sd[n].detach() for n, _, kind in self._schema if kind != "bn_nbt"]
 
+    def packed_weights(self, params=None):
+        """bf16 hi/lo operand tiles of every GEMM weight (SURVEY.md 8b "packed once at load_state_dict"): cached per
+        (data_ptr, _version) of the conv weights, so a load_state_dict / .to() / in-place update repacks and nothing else does."""
+        if self.gemm_algo != 1:
+            return None
+        params = self.param_table() if params is None else params
+        key = tuple((p.data_ptr(), p._version, str(p.device), p.dtype) for p, (_, _, kind) in
+                    zip(params, [e for e in self._schema if e[2] != "bn_nbt"]) if kind == "conv_w")
+        if self._packed is None or self._packed[0] != key:
+            self._packed = (key, _cabi.filter_pack_weights(params, self.cabi_cfg()))
+        return self._packed[1]
+
     def forward(self, data):
         assert data["xs"].dim() == 4 and data["xs"].shape[1] == 1
         # self.training (scripts/benchmark_pairwise_registration.py never calls .eval()): BatchNorm uses the statistics of this
@@ -130,7 +145,11 @@ class OANet(nn.Module):
             raise _cabi.LmpcrError("OANet(B200) needs a CUDA device (cfg['misc']['use_gpu'] and an sm_100 GPU); no CPU fallback")
         xs = data["xs"].to(self.device, dtype=torch.float32)
         with torch.no_grad():
-            out = _cabi.filter_forward(xs, self.param_table(), self.cabi_cfg())
+            params = self.param_table()
+            cfg = self.cabi_cfg()
+            ws = _cabi.reusable_workspace(self._workspace, cfg, xs.shape[0], xs.shape[2], xs.device)
+            out = _cabi.filter_forward(xs, params, cfg, workspace=ws, packed=self.packed_weights(params))
+            self._workspace = out.pop("_workspace", None)
             if self.training:
                 for name, buf in self.named_buffers():
                     if name.endswith("num_batches_tracked"):

@@ -49,13 +49,12 @@ class SceneRegistrar:
         self.nn_chunk = max(int(nn_chunk), self.pair_chunk)
         self.mutual_mode = mutual_mode
         self.mutual_thresh = mutual_thresh
-        self._params = None
+        self._workspace = None      # filter scratch, kept across chunks and calls (sized by the largest chunk seen)
         self.timers = None          # optional dict of stage -> list[(start_event, stop_event)]
 
     def _param_table(self):
-        if self._params is None:
-            self._params = self.net.param_table()
-        return self._params
+        # rebuilt per call (334 attribute look-ups): a cached table would go stale after net.to() / .half() / load_state_dict
+        return self.net.param_table()
 
     def _tic(self, name):
         if self.timers is None:
@@ -79,7 +78,12 @@ class SceneRegistrar:
         extras = {"idx_st": [], "idx_ts": [], "mutual": [], "scores": []} if keep_correspondences else None
         cfg = self.net.cabi_cfg()
         cfg.guard_mode = _cabi.GUARD_PAIR
+        # eval-mode BatchNorm always: batch statistics would couple the pairs of a chunk (results would depend on pair_chunk, the
+        # rank partition and the call order) and the kernels would overwrite running_mean / running_var -- a forgotten .eval()
+        # must not do that to a scene
+        cfg.bn_mode = _cabi.BN_EVAL
         params = self._param_table()
+        packed = self.net.packed_weights(params)
         # stage 1 for large slabs of pairs, both directions in ONE call: the per-scan operand preparation of the tensor
         # path is then paid once per slab instead of twice per filter chunk
         for s0 in range(0, P, self.nn_chunk):
@@ -97,7 +101,9 @@ class SceneRegistrar:
                                              xs_channels=6 + cfg.side_channel, want_mutual=keep_correspondences or cfg.side_channel == 1)
                 self._toc(t)
                 t = self._tic("filter")
-                out = _cabi.filter_forward(xs, params, cfg, want_latent=False, want_conf=True)
+                ws = _cabi.reusable_workspace(self._workspace, cfg, nc, xs.shape[2], dev)
+                out = _cabi.filter_forward(xs, params, cfg, want_latent=False, want_conf=True, workspace=ws, packed=packed)
+                self._workspace = out.pop("_workspace", None)
                 self._toc(t)
                 t = self._tic("records")
                 p0 = s0 + q0

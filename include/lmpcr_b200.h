@@ -57,6 +57,9 @@ extern "C" {
 int lmpcr_abi_version(void);
 /* Number of kernels this library has launched in this process so far (bench.py's `gpu_launches`). */
 long long lmpcr_launch_count(void);
+/* The same, for one kernel by name ("tcgemm_kernel", "split_weights_kernel", "pcn_stack_kernel", ...): lets a caller check which
+ * code path a call took (tests/test_gpu_boundary.py). */
+long long lmpcr_launch_count_named(const char* kernel_name);
 const char* lmpcr_last_error(void);
 /* Fills sm_count / l2_bytes / cc_major / cc_minor of the current device (host ints, any may be NULL). */
 int lmpcr_device_info(int* sm_count, int* l2_bytes, int* cc_major, int* cc_minor);
@@ -214,6 +217,17 @@ int lmpcr_conv1x1(const float* x, int n_pairs, int cin, int n_pts, const float* 
                   const float* shift, const float* residual, int cout, float* out, int gemm_algo, void* workspace, size_t workspace_bytes,
                   void* stream);
 
+/* A stack of 1..4 plain PointCN layers (lib/filtering/oanet.py:18-43: x + conv(relu(bn(in(conv(relu(bn(in(x)))))))), 128 channels,
+ * eval-mode BatchNorm, no shot_cut) in ONE launch: every CTA owns a pair, both weight matrices of a layer stay in shared memory and
+ * the inner activation never reaches HBM (csrc/pcn.cu).  The building block lmpcr_filter_forward uses for l1_1 / l1_2 when a call
+ * has at least 64 pairs; exported so that it can be tested and timed alone.
+ *   x, out [P,128,N] fp32 (out may alias x), n_pts % 4 == 0;  stats_out (optional) [P,128,2] = (mean, M2 over the points) of out.
+ *   params: HOST array of 12 * n_layers DEVICE pointers, per layer in state_dict order: conv.1 (weight, bias, running_mean,
+ *   running_var), conv.3 (weight [128,128], bias), conv.5 (x4), conv.7 (weight, bias). */
+size_t lmpcr_pointcn_stack_workspace_bytes(int n_pairs, int n_layers);
+int lmpcr_pointcn_stack(const float* x, int n_pairs, int n_pts, const float* const* params, int n_layers, float* out, float* stats_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of tensors of OANet(cfg).state_dict() excluding `num_batches_tracked` entries; `params` below is
  * a HOST array of that many DEVICE pointers (fp32, contiguous), in state_dict order. */
 int lmpcr_filter_num_params(const lmpcr_filter_cfg* cfg);
@@ -226,6 +240,20 @@ int lmpcr_filter_forward(const float* xs, int n_pairs, int n_pts, const float* c
                          const lmpcr_filter_cfg* cfg, float* logits, float* scores, float* R, float* t,
                          float* residuals, float* latent, float* conf, uint32_t* status, void* workspace,
                          size_t workspace_bytes, void* stream);
+
+/* Pack-once weights (the load_state_dict step of lib/checkpoints.py:92-105 on the reference side): every GEMM
+ * weight of the network split into bf16 hi/lo tiles in the tensor-core operand layout, block after block.  The caller keeps
+ * `packed` (lmpcr_filter_pack_bytes(cfg) bytes, 256-byte aligned, gemm_algo = 1 only) for as long as the parameters are
+ * unchanged and passes it to lmpcr_filter_forward_packed, which then launches no weight-split kernels.  `params` is still
+ * needed there for biases, BatchNorm tensors and the fp32 conv1 / output layers.  lmpcr_filter_forward == pack into the
+ * workspace + forward_packed. */
+size_t lmpcr_filter_pack_bytes(const lmpcr_filter_cfg* cfg);
+int lmpcr_filter_pack_weights(const float* const* params, int n_params, const lmpcr_filter_cfg* cfg, void* packed, size_t packed_bytes,
+                              void* stream);
+int lmpcr_filter_forward_packed(const float* xs, int n_pairs, int n_pts, const float* const* params, int n_params,
+                                const lmpcr_filter_cfg* cfg, const void* packed, size_t packed_bytes, float* logits, float* scores,
+                                float* R, float* t, float* residuals, float* latent, float* conf, uint32_t* status, void* workspace,
+                                size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Pose record packing for the multi-GPU all-gather:
