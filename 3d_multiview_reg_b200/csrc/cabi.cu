@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include "tcgemm.cuh"
+#include "pcn.cuh"
 
 namespace lmpcr {
 
@@ -136,6 +137,7 @@ int lmpcr_nn_tensor_debug(const float* q_feat, int n_q_sets, int n_q, const floa
 }
 
 int lmpcr_debug_tc_profile(unsigned long long* out16, int reset) { return tc_profile_read(out16, reset); }
+int lmpcr_debug_pcn_profile(unsigned long long* out40, int reset) { return pcn_profile_read(out40, reset); }
 
 int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, int dim, int batch, float* out, void* workspace,
                             size_t workspace_bytes, void* stream) {

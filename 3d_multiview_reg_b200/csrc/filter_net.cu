@@ -571,7 +571,7 @@ __global__ void guard_flag_kernel(const int32_t* __restrict__ anypos, int P, int
 // ------------------------------------------------------------------------------------------------
 // parameter table (state_dict order)
 // ------------------------------------------------------------------------------------------------
-struct ConvP { const float* w; const float* b; const uint8_t* blob; };
+struct ConvP { const float* w; const float* b; const uint8_t* blob; const uint8_t* blob_rm; };   // blob_rm: pcn.cu's tensor-memory image (plain 128 -> 128 layers)
 struct BNP { const float* g; const float* b; const float* rm; const float* rv; };
 struct PointCNP { bool has_sc; ConvP sc; BNP bn1; ConvP c1; BNP bn2; ConvP c2; };
 struct OAFilterP { BNP bn1; ConvP c1; BNP bn2; ConvP c2; BNP bn3; ConvP c3; };
@@ -584,9 +584,9 @@ struct BlockP {
 struct Cursor {
   const float* const* p; int i, n;
   const float* next() { return (i < n) ? p[i++] : (i++, nullptr); }
-  ConvP conv() { ConvP c; c.w = next(); c.b = next(); c.blob = nullptr; return c; }
+  ConvP conv() { ConvP c; c.w = next(); c.b = next(); c.blob = nullptr; c.blob_rm = nullptr; return c; }
   BNP bn() { BNP b; b.g = next(); b.b = next(); b.rm = next(); b.rv = next(); return b; }
-  PointCNP pointcn(bool sc) { PointCNP q; q.has_sc = sc; if (sc) q.sc = conv(); else q.sc = ConvP{nullptr, nullptr, nullptr}; q.bn1 = bn(); q.c1 = conv(); q.bn2 = bn(); q.c2 = conv(); return q; }
+  PointCNP pointcn(bool sc) { PointCNP q; q.has_sc = sc; if (sc) q.sc = conv(); else q.sc = ConvP{nullptr, nullptr, nullptr, nullptr}; q.bn1 = bn(); q.c1 = conv(); q.bn2 = bn(); q.c2 = conv(); return q; }
 };
 
 void parse_block(Cursor& cur, int half, BlockP& b) {
@@ -634,6 +634,7 @@ size_t block_blob_bytes(int C, int K, int half) {
   b += 2 * tc_weight_blob_bytes(C, 2 * C) + tc_weight_blob_bytes(C, C);          // l1_2.0 (shot_cut, conv.3, conv.7)
   b += (size_t)(half - 1) * 2 * tc_weight_blob_bytes(C, C);                       // l1_2.1..
   b += (size_t)half * (2 * tc_weight_blob_bytes(C, C) + tc_weight_blob_bytes(K, K));   // l2
+  if (C == PCN_C) b += (size_t)(2 * half + 2 * (half - 1)) * pcn_weight_bytes();       // second image of the plain PointCN weights (pcn.cu)
   return align_up(b, 256);
 }
 
@@ -652,6 +653,16 @@ int block_blobs(BlockP& blk, int C, int K, int half, uint8_t* bp, bool do_split,
   LMPCR_TRY(prep(blk.l1_2[0].sc, C, 2 * C)); LMPCR_TRY(prep(blk.l1_2[0].c1, C, 2 * C)); LMPCR_TRY(prep(blk.l1_2[0].c2, C, C));
   for (int i = 1; i < half; ++i) { LMPCR_TRY(prep(blk.l1_2[i].c1, C, C)); LMPCR_TRY(prep(blk.l1_2[i].c2, C, C)); }
   for (int i = 0; i < half; ++i) { LMPCR_TRY(prep(blk.l2[i].c1, C, C)); LMPCR_TRY(prep(blk.l2[i].c2, K, K)); LMPCR_TRY(prep(blk.l2[i].c3, C, C)); }
+  if (C == PCN_C) {
+    auto prep_rm = [&](ConvP& cv) -> int {
+      cv.blob_rm = bp;
+      const int rc = do_split ? launch_pcn_pack_weights(cv.w, bp, st) : LMPCR_OK;
+      bp += pcn_weight_bytes();
+      return rc;
+    };
+    for (int i = 0; i < half; ++i) { LMPCR_TRY(prep_rm(blk.l1_1[i].c1)); LMPCR_TRY(prep_rm(blk.l1_1[i].c2)); }
+    for (int i = 1; i < half; ++i) { LMPCR_TRY(prep_rm(blk.l1_2[i].c1)); LMPCR_TRY(prep_rm(blk.l1_2[i].c2)); }
+  }
   return LMPCR_OK;
 }
 
@@ -742,7 +753,7 @@ int launch_softmax_pool(const float* x, const float* E, int P, int C, int K, int
 // params: 12 tensors per layer in state_dict order: conv.1 (BN weight, bias, running_mean, running_var), conv.3 (weight, bias),
 // conv.5 (BN x 4), conv.7 (weight, bias).
 size_t pointcn_stack_workspace_bytes(int P, int n_layers) {
-  return (size_t)n_layers * 2 * tc_weight_blob_bytes(PCN_C, PCN_C) + 2 * align_up((size_t)(P > 0 ? P : 1) * PCN_C * 4, 256) + 256;
+  return (size_t)n_layers * 2 * pcn_weight_bytes() + 2 * align_up((size_t)(P > 0 ? P : 1) * PCN_C * 4, 256) + 256;
 }
 
 int launch_pointcn_stack(const float* x, int P, int N, const float* const* params, int n_layers, float* out, float* stats_out, void* ws,
@@ -762,8 +773,8 @@ int launch_pointcn_stack(const float* x, int P, int N, const float* const* param
     L.b1 = q[5];
     L.bn2 = PcnBN{q[6], q[7], q[8], q[9]};
     L.b2 = q[11];
-    L.w1 = bp; LMPCR_TRY(launch_split_weights(q[4], PCN_C, PCN_C, bp, st)); bp += tc_weight_blob_bytes(PCN_C, PCN_C);
-    L.w2 = bp; LMPCR_TRY(launch_split_weights(q[10], PCN_C, PCN_C, bp, st)); bp += tc_weight_blob_bytes(PCN_C, PCN_C);
+    L.w1 = bp; LMPCR_TRY(launch_pcn_pack_weights(q[4], bp, st)); bp += pcn_weight_bytes();
+    L.w2 = bp; LMPCR_TRY(launch_pcn_pack_weights(q[10], bp, st)); bp += pcn_weight_bytes();
   }
   float* scale = reinterpret_cast<float*>(bp);
   float* shift = reinterpret_cast<float*>(bp + align_up((size_t)P * PCN_C * 4, 256));
@@ -845,8 +856,9 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   const bool tc = cfg->gemm_algo == 1;
   const bool bn_train = cfg->bn_mode == LMPCR_BN_BATCH;
   static const int no_defer = getenv("LMPCR_NO_DEFER") ? atoi(getenv("LMPCR_NO_DEFER")) : 0;   // debug aid: softmax statistics by separate passes
-  static const int pcn_on = getenv("LMPCR_PCN") ? atoi(getenv("LMPCR_PCN")) : 1;                // 0: PointCN layers on the per-layer GEMM path (A/B runs)
-  static const int pcn_min_pairs = getenv("LMPCR_PCN_MIN_PAIRS") ? atoi(getenv("LMPCR_PCN_MIN_PAIRS")) : 64;
+  // read per call (two getenv look-ups) so that a test can switch paths inside one process
+  const int pcn_on = getenv("LMPCR_PCN") ? atoi(getenv("LMPCR_PCN")) : 1;                       // 0: PointCN layers on the per-layer GEMM path (A/B runs)
+  const int pcn_min_pairs = getenv("LMPCR_PCN_MIN_PAIRS") ? atoi(getenv("LMPCR_PCN_MIN_PAIRS")) : 64;
   LMPCR_REQUIRE(n_params == filter_num_params(cfg), LMPCR_ERR_ARG, "lmpcr_filter_forward: expected %d parameter tensors, got %d", filter_num_params(cfg), n_params);
   for (int i = 0; i < n_params; ++i) LMPCR_REQUIRE(params[i], LMPCR_ERR_ARG, "lmpcr_filter_forward: params[%d] is null", i);
   if (P == 0) return LMPCR_OK;
@@ -1070,7 +1082,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       const bool use_pcn = pcn_on && tc && !bn_train && g >= pcn_min_pairs && half <= PCN_MAX_LAYERS && pcn_supported(C, N, W.T0, CN, W.CAT, 2 * CN);
       auto pcn_layer = [&](const PointCNP& q) {
         PcnLayer L{};
-        L.w1 = q.c1.blob; L.w2 = q.c2.blob; L.b1 = q.c1.b; L.b2 = q.c2.b;
+        L.w1 = q.c1.blob_rm; L.w2 = q.c2.blob_rm; L.b1 = q.c1.b; L.b2 = q.c2.b;
         L.bn1 = PcnBN{q.bn1.g, q.bn1.b, q.bn1.rm, q.bn1.rv};
         L.bn2 = PcnBN{q.bn2.g, q.bn2.b, q.bn2.rm, q.bn2.rv};
         return L;

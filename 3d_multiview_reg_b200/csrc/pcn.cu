@@ -9,13 +9,13 @@
 //   pass A  x tile -> f1 -> h1 (bf16 hi/lo, smem) -> tcgen05 W1.h1 -> TMEM -> per-channel mean / variance of y = W1 h1 + b1
 //   pass B  x tile -> f1 -> h1 -> W1.h1 -> TMEM -> f2 (statistics of pass A) -> h2 (smem) -> tcgen05 W2.h2 -> TMEM -> + b2 + x
 //           -> statistics of z (f1 of the next layer) -> tile stored in place of the x tile
-// 3 HBM passes per layer instead of 5, both weight matrices resident in shared memory (128 KB as bf16 hi/lo), the residual
-// is the x tile that is in shared memory anyway, and tiles move by TMA (tensor maps, SWIZZLE_128B: thread = channel row reads
+// 3 HBM passes per layer instead of 5, both weight matrices resident in TENSOR MEMORY (bf16 hi/lo, the A operand of tcgen05.mma
+// read from TMEM), the residual is the x tile that is in shared memory anyway, and tiles move by TMA (tensor maps, SWIZZLE_128B: thread = channel row reads
 // and writes its 128-byte row conflict-free) -- no per-element address arithmetic, no register-staged global loads.
 // Products are split-bf16 (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, fp32 accumulation in TMEM) exactly as in tcgemm.cu.
 //
 // Warp roles (448 threads, one CTA per SM):
-//   warp 0       TMA: x tile loads (+ L2 prefetch a few tiles ahead), weight loads, output tile stores
+//   warp 0       TMA: x tile loads (+ L2 prefetch a few tiles ahead), output tile stores
 //   warp 1       tcgen05.mma issue (M128 x N32 x K16, 24 per GEMM tile)
 //   warps 2-5    TMEM readers A: pass A statistics of y; pass B f2 + hi/lo split -> h2
 //   warps 6-9    TMEM readers B: pass B epilogue (z + b2 + x, statistics, tile written back over the x tile)
@@ -35,24 +35,45 @@ namespace {
 
 constexpr int C = PCN_C;                     // channels = M = K of both GEMMs
 constexpr int TP = 32;                       // points per tile (= 128 bytes per channel row: one SWIZZLE_128B span)
-constexpr int NX = 4;                        // x-tile ring
+constexpr int NX = 6;                        // x-tile ring
 constexpr int PF_DIST = 8;                   // L2 prefetch distance in tiles
-constexpr int W_BYTES = 4 * 2 * 128 * 32 * 2;   // one convolution: 4 k-chunks x [hi 8 KB | lo 8 KB] = 64 KB
+constexpr int WP_BYTES = C * C * 2;          // one bf16 part (hi or lo) of a weight matrix, row-major [out][in]: 32 KB
 constexpr int X_BYTES = C * TP * 4;          // 16 KB
 constexpr int HP_BYTES = C * TP * 2;         // one bf16 part of an h tile: 8 KB
 constexpr int H_BYTES = 2 * HP_BYTES;        // hi | lo
-constexpr int OFF_W1 = 0, OFF_W2 = W_BYTES, OFF_X = 2 * W_BYTES, OFF_H1 = OFF_X + NX * X_BYTES, OFF_H2 = OFF_H1 + H_BYTES;
-constexpr int OFF_SC = OFF_H2 + H_BYTES;     // sc1[128], sh1[128]: f1 of the next layer, written by the epilogue threads
+constexpr int OFF_X = 0, OFF_H1 = OFF_X + NX * X_BYTES, OFF_H2 = OFF_H1 + 2 * H_BYTES;
+constexpr int OFF_SC = OFF_H2 + 2 * H_BYTES; // sc1[128], sh1[128]: f1 of the next layer, written by the epilogue threads
 constexpr int OFF_BAR = OFF_SC + 2 * C * 4;
-constexpr int N_BARS = 3 * NX + 13;
+constexpr int N_BARS = 3 * NX + 16;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr size_t SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
 constexpr int NTHREADS = 14 * 32;
-constexpr int TMEM_COLS = 128;               // y[2] | z[2], 32 columns each
-constexpr uint32_t K_LBO = 128, K_SBO = 512;             // weight chunk (K-major, 32 k): k-groups adjacent, 8-row groups 512 B apart
+// Tensor memory (512 columns): both weight matrices of the layer as bf16 hi | lo, row = TMEM lane, two elements per 32-bit column
+// (the A operand of tcgen05.mma read from TMEM: per MMA only the 1 KB activation operand crosses shared memory instead of 5 KB --
+// with the weights in shared memory the kernel was bound by the tensor core's operand reads, ncu: 52 % of the shared-memory
+// bandwidth, tensor pipe 21 %), then the accumulators y[2] | z[2] of 32 columns each
+constexpr int TMEM_COLS = 512;
+constexpr int TM_W1 = 0, TM_W2 = 128, TM_Y = 256, TM_Z = 256 + 2 * TP;       // W: [hi 64 columns | lo 64 columns]
 constexpr uint32_t MN_SBO = 128, MN_LBO = (TP / 8) * 128;   // h tile (MN-major): point-groups adjacent, channel-groups 512 B apart
 constexpr uint32_t IDESC = make_idesc(1, 0, 1, 128, TP);
+
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+        "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -138,6 +159,18 @@ __device__ __forceinline__ void fold_affine(float mean, float var, float eps_in,
   sh = (-mean * rstd - __ldg(bn.rm + c)) * gsc + __ldg(bn.b + c);
 }
 
+// cycle counters for timing experiments (LMPCR_PCN_DEBUG=1): lane 0 of the first warp of every role in CTA 0 accumulates the time
+// between consecutive PROF() marks into the slot named at the later mark (lmpcr_debug_pcn_profile reads them)
+__device__ unsigned long long g_pcn_prof[40];
+#define PROF(slot)                                                                      \
+  do {                                                                                  \
+    if (prof_me) {                                                                      \
+      const long long _t = clock64();                                                   \
+      atomicAdd(&g_pcn_prof[slot], (unsigned long long)(_t - tp));                      \
+      tp = _t;                                                                          \
+    }                                                                                   \
+  } while (0)
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const PcnArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -148,33 +181,40 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   auto XFULL = [&](int s) { return bar0 + 8u * s; };
   auto XREAD = [&](int s) { return bar0 + 8u * (NX + s); };
   auto OUTRDY = [&](int s) { return bar0 + 8u * (2 * NX + s); };
-  const uint32_t H1FULL = bar0 + 8u * (3 * NX), H1EMPTY = H1FULL + 8, H2FULL = H1FULL + 16, H2EMPTY = H1FULL + 24, WFULL = H1FULL + 32;
-  auto YFULL = [&](int a) { return H1FULL + 40 + 8u * a; };
-  auto YEMPTY = [&](int a) { return H1FULL + 56 + 8u * a; };
-  auto ZFULL = [&](int a) { return H1FULL + 72 + 8u * a; };
-  auto ZEMPTY = [&](int a) { return H1FULL + 88 + 8u * a; };
+  const uint32_t barB = bar0 + 8u * (3 * NX);
+  auto H1FULL = [&](int b) { return barB + 8u * b; };
+  auto H1EMPTY = [&](int b) { return barB + 16 + 8u * b; };
+  auto H2FULL = [&](int b) { return barB + 32 + 8u * b; };
+  auto H2EMPTY = [&](int b) { return barB + 48 + 8u * b; };
+  auto YFULL = [&](int a) { return barB + 64 + 8u * a; };
+  auto YEMPTY = [&](int a) { return barB + 80 + 8u * a; };
+  auto ZFULL = [&](int a) { return barB + 96 + 8u * a; };
+  auto ZEMPTY = [&](int a) { return barB + 112 + 8u * a; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = ((warp & 3) << 5) | lane;                 // channel row / TMEM lane owned by this thread in the 4-warp roles
   const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
   const int n_tiles = (g.N + TP - 1) / TP;
+  const bool prof_me = g.debug && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6 || warp == 10);
+  long long tp = clock64();
   const uint32_t sX = smem_u32(smem + OFF_X), sH1 = smem_u32(smem + OFF_H1), sH2 = smem_u32(smem + OFF_H2);
-  const uint32_t sW1 = smem_u32(smem + OFF_W1), sW2 = smem_u32(smem + OFF_W2);
 
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmY = tmem_base, tmZ = tmem_base + 2 * TP;
+  const uint32_t tmY = tmem_base + TM_Y, tmZ = tmem_base + TM_Z, tmW1 = tmem_base + TM_W1, tmW2 = tmem_base + TM_W2;
 
   // all barriers are re-initialised at the start of every pass (the pipeline is fully drained at a pass boundary), so the phase
   // arithmetic of every role is local to a pass: use k of a ring slot / of a single barrier completes phase k
   auto pass_begin = [&]() {
     if (threadIdx.x == 0) {
       for (int s = 0; s < NX; ++s) { mbar_init(XFULL(s), 1); mbar_init(XREAD(s), 4); mbar_init(OUTRDY(s), 4); }
-      mbar_init(H1FULL, 4); mbar_init(H1EMPTY, 1); mbar_init(H2FULL, 4); mbar_init(H2EMPTY, 1); mbar_init(WFULL, 1);
-      for (int a = 0; a < 2; ++a) { mbar_init(YFULL(a), 1); mbar_init(YEMPTY(a), 128); mbar_init(ZFULL(a), 1); mbar_init(ZEMPTY(a), 128); }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(H1FULL(a), 4); mbar_init(H1EMPTY(a), 1); mbar_init(H2FULL(a), 4); mbar_init(H2EMPTY(a), 1);
+        mbar_init(YFULL(a), 1); mbar_init(YEMPTY(a), 128); mbar_init(ZFULL(a), 1); mbar_init(ZEMPTY(a), 128);
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -185,19 +225,34 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     tc_fence_after();
   };
 
-  // one GEMM tile: D[128 x 32] = W (resident blob at sW) . h (operand image at sH), three bf16 products per K step
-  auto issue_gemm = [&](uint32_t sW, uint32_t sH, uint32_t d_tmem) {
+  // one GEMM tile: D[128 x 32] = W (bf16 hi | lo in tensor memory at tW) . h (operand image at sH), three bf16 products per K step.
+  // The shared-memory descriptors of the eight K steps differ only in the start-address field: one 32-bit add each.
+  constexpr uint32_t DESC_HI = (MN_SBO >> 4) | (1u << 14);                     // SBO, descriptor version
+  auto issue_gemm = [&](uint32_t tW, uint32_t sH, uint32_t d_tmem) {
+    const uint32_t lo0 = ((sH >> 4) & 0x3FFFu) | ((MN_LBO >> 4) << 16);
 #pragma unroll
-    for (int kc = 0; kc < 4; ++kc) {
+    for (int j = 0; j < C / 16; ++j) {
+      const uint32_t lo_hi = lo0 + j * ((2 * MN_LBO) >> 4), lo_lo = lo_hi + (HP_BYTES >> 4);
+      const uint64_t b_hi = ((uint64_t)DESC_HI << 32) | lo_hi, b_lo = ((uint64_t)DESC_HI << 32) | lo_lo;
+      tc_mma_ts(d_tmem, tW + 64 + j * 8, b_hi, IDESC, j ? 1u : 0u);            // W_lo . h_hi   (small terms first)
+      tc_mma_ts(d_tmem, tW + j * 8, b_lo, IDESC, 1u);                          // W_hi . h_lo
+      tc_mma_ts(d_tmem, tW + j * 8, b_hi, IDESC, 1u);                          // W_hi . h_hi
+    }
+  };
+  // this thread's row of a weight matrix (row-major bf16 [hi 32 KB | lo 32 KB] in global memory) -> tensor memory
+  auto load_w_row = [&](const uint8_t* wg, uint32_t tW) {
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint4* src = reinterpret_cast<const uint4*>(wg + (size_t)part * WP_BYTES + (size_t)ch * (C * 2) + hh * 128);
+        uint32_t r[32];
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const uint32_t a0 = sW + kc * (2 * 8192) + ks * 2 * K_LBO;
-        const uint32_t b0 = sH + (kc * 4 + ks * 2) * MN_LBO;
-        const uint64_t a_hi = make_desc(a0, K_LBO, K_SBO), a_lo = make_desc(a0 + 8192, K_LBO, K_SBO);
-        const uint64_t b_hi = make_desc(b0, MN_LBO, MN_SBO), b_lo = make_desc(b0 + HP_BYTES, MN_LBO, MN_SBO);
-        tc_mma_f16(d_tmem, a_lo, b_hi, IDESC, (kc | ks) ? 1u : 0u);     // small terms first
-        tc_mma_f16(d_tmem, a_hi, b_lo, IDESC, 1u);
-        tc_mma_f16(d_tmem, a_hi, b_hi, IDESC, 1u);
+        for (int q = 0; q < 8; ++q) {
+          const uint4 v = __ldg(src + q);
+          r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+        }
+        tc_st32(tW + lane_sel + part * 64 + hh * 32, r);
       }
     }
   };
@@ -214,20 +269,23 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         if (l == 0) { sc1 = __ldg(g.scale0 + (size_t)p * C + ch); sh1 = __ldg(g.shift0 + (size_t)p * C + ch); }
         else { sc1 = sc1_s[ch]; sh1 = sh1_s[ch]; }
       }
+      if (warp >= 2 && warp < 6) {          // the layer's weights -> tensor memory (every MMA of the previous layer has completed: pass_end)
+        load_w_row(L.w1, tmW1);
+        load_w_row(L.w2, tmW2);
+        tc_st_wait();
+        tc_fence_before();
+      }
       // ======================================================== pass A: statistics of y = W1 f1(x) + b1
       pass_begin();
+      tc_fence_after();
       if (warp == 0) {
         if (lane == 0) {
-          mbar_expect_tx(WFULL, 2 * W_BYTES);
-#pragma unroll 1
-          for (int i = 0; i < 4; ++i) {
-            bulk_g2s(sW1 + i * 16384, L.w1 + i * 16384, 16384, WFULL);
-            bulk_g2s(sW2 + i * 16384, L.w2 + i * 16384, 16384, WFULL);
-          }
           for (int t = 0; t < PF_DIST && t < n_tiles; ++t) tma_prefetch_3d(tm_src, t * TP, 0, p);
           for (int t = 0; t < n_tiles; ++t) {
             const int s = t % NX;
-            if (t >= NX) mbar_wait(XREAD(s), ((t / NX) - 1) & 1);
+            PROF(1);
+            if (t >= NX) mbar_wait_fast(XREAD(s), ((t / NX) - 1) & 1);
+            PROF(0);
             mbar_expect_tx(XFULL(s), X_BYTES);
             tma_load_3d(sX + s * X_BYTES, tm_src, t * TP, 0, p, XFULL(s));
             if (t + PF_DIST < n_tiles) tma_prefetch_3d(tm_src, (t + PF_DIST) * TP, 0, p);
@@ -235,24 +293,31 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         }
       } else if (warp == 1) {
         if (lane == 0) {
-          mbar_wait(WFULL, 0);
           for (int t = 0; t < n_tiles; ++t) {
-            const int a = t & 1;
-            mbar_wait(H1FULL, t & 1);
-            mbar_wait(YEMPTY(a), ((t >> 1) & 1) ^ 1);
+            const int a = t & 1, ph = (t >> 1) & 1;
+            PROF(7);
+            mbar_wait_fast(H1FULL(a), ph);
+            PROF(5);
+            mbar_wait_fast(YEMPTY(a), ph ^ 1);
+            PROF(6);
             tc_fence_after();
-            issue_gemm(sW1, sH1, tmY + a * TP);
-            tc_commit(H1EMPTY);
+            issue_gemm(tmW1, sH1 + a * H_BYTES, tmY + a * TP);
+            tc_commit(H1EMPTY(a));
             tc_commit(YFULL(a));
           }
-          mbar_wait(H1EMPTY, (n_tiles - 1) & 1);
+          for (int b = 0; b < 2; ++b) {                    // every commit of this pass has arrived before the barriers are re-initialised
+            const int uses = (n_tiles + 1 - b) >> 1;
+            if (uses > 0) mbar_wait_fast(H1EMPTY(b), (uses - 1) & 1);
+          }
         }
       } else if (warp < 6) {
         rs.reset();
         const float b1 = __ldg(L.b1 + ch);
         for (int t = 0; t < n_tiles; ++t) {
           const int a = t & 1;
-          mbar_wait(YFULL(a), (t >> 1) & 1);
+          PROF(12);
+          mbar_wait_fast(YFULL(a), (t >> 1) & 1);
+          PROF(11);
           tc_fence_after();
           float v[TP];
           tc_ld32(tmY + lane_sel + a * TP, v);
@@ -269,21 +334,26 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
       } else if (warp >= 10) {
         for (int t = 0; t < n_tiles; ++t) {
           const int s = t % NX;
-          mbar_wait(XFULL(s), (t / NX) & 1);
+          PROF(23);
+          mbar_wait_fast(XFULL(s), (t / NX) & 1);
+          PROF(20);
           float v[TP];
           load_x_row(smem + OFF_X + s * X_BYTES, ch, v);
 #pragma unroll
           for (int i = 0; i < TP; ++i) v[i] = fmaxf(fmaf(v[i], sc1, sh1), 0.f);
           __syncwarp();
           if (lane == 0) mbar_arrive(XREAD(s));        // the tile is in registers: the slot may be refilled
-          mbar_wait(H1EMPTY, (t & 1) ^ 1);
-          store_h_row(smem + OFF_H1, ch, v);
+          PROF(21);
+          mbar_wait_fast(H1EMPTY(t & 1), ((t >> 1) & 1) ^ 1);
+          PROF(22);
+          store_h_row(smem + OFF_H1 + (t & 1) * H_BYTES, ch, v);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(H1FULL);
+          if (lane == 0) mbar_arrive(H1FULL(t & 1));
         }
       }
       pass_end();
+      if (warp != 0) tp = clock64(); else PROF(28);     // 28: rest of pass A as seen by the loader thread (drain)
       // ======================================================== pass B: z = x + W2 f2(W1 f1(x) + b1) + b2
       const CUtensorMap* tm_dst = &tm_out;
       pass_begin();
@@ -292,12 +362,15 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           for (int t = 0; t < PF_DIST && t < n_tiles; ++t) tma_prefetch_3d(tm_src, t * TP, 0, p);
           for (int t = 0; t < n_tiles; ++t) {
             const int s = t % NX;
+            PROF(4);
             if (t >= NX) {
               const int u = t - NX;
-              mbar_wait(OUTRDY(s), (u / NX) & 1);
+              mbar_wait_fast(OUTRDY(s), (u / NX) & 1);
+              PROF(2);
               tma_store_3d(tm_dst, sX + s * X_BYTES, u * TP, 0, p);
               bulk_commit();
               bulk_wait_read0();
+              PROF(3);
             }
             mbar_expect_tx(XFULL(s), X_BYTES);
             tma_load_3d(sX + s * X_BYTES, tm_src, t * TP, 0, p, XFULL(s));
@@ -305,7 +378,7 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           }
           for (int u = (n_tiles > NX ? n_tiles - NX : 0); u < n_tiles; ++u) {
             const int s = u % NX;
-            mbar_wait(OUTRDY(s), (u / NX) & 1);
+            mbar_wait_fast(OUTRDY(s), (u / NX) & 1);
             tma_store_3d(tm_dst, sX + s * X_BYTES, u * TP, 0, p);
             bulk_commit();
           }
@@ -315,31 +388,41 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         if (lane == 0) {
           for (int t = 0; t <= n_tiles; ++t) {
             if (t < n_tiles) {
-              const int a = t & 1;
-              mbar_wait(H1FULL, t & 1);
-              mbar_wait(YEMPTY(a), ((t >> 1) & 1) ^ 1);
+              const int a = t & 1, ph = (t >> 1) & 1;
+              PROF(10);
+              mbar_wait_fast(H1FULL(a), ph);
+              PROF(5);
+              mbar_wait_fast(YEMPTY(a), ph ^ 1);
+              PROF(6);
               tc_fence_after();
-              issue_gemm(sW1, sH1, tmY + a * TP);
-              tc_commit(H1EMPTY);
+              issue_gemm(tmW1, sH1 + a * H_BYTES, tmY + a * TP);
+              tc_commit(H1EMPTY(a));
               tc_commit(YFULL(a));
             }
             if (t >= 1) {
-              const int u = t - 1, a = u & 1;
-              mbar_wait(H2FULL, u & 1);
-              mbar_wait(ZEMPTY(a), ((u >> 1) & 1) ^ 1);
+              const int u = t - 1, a = u & 1, ph = (u >> 1) & 1;
+              PROF(7);
+              mbar_wait_fast(H2FULL(a), ph);
+              PROF(8);
+              mbar_wait_fast(ZEMPTY(a), ph ^ 1);
+              PROF(9);
               tc_fence_after();
-              issue_gemm(sW2, sH2, tmZ + a * TP);
-              tc_commit(H2EMPTY);
+              issue_gemm(tmW2, sH2 + a * H_BYTES, tmZ + a * TP);
+              tc_commit(H2EMPTY(a));
               tc_commit(ZFULL(a));
             }
           }
-          mbar_wait(H1EMPTY, (n_tiles - 1) & 1);
-          mbar_wait(H2EMPTY, (n_tiles - 1) & 1);
+          for (int b = 0; b < 2; ++b) {
+            const int uses = (n_tiles + 1 - b) >> 1;
+            if (uses > 0) { mbar_wait_fast(H1EMPTY(b), (uses - 1) & 1); mbar_wait_fast(H2EMPTY(b), (uses - 1) & 1); }
+          }
         }
       } else if (warp < 6) {
         for (int t = 0; t < n_tiles; ++t) {
           const int a = t & 1;
-          mbar_wait(YFULL(a), (t >> 1) & 1);
+          PROF(16);
+          mbar_wait_fast(YFULL(a), (t >> 1) & 1);
+          PROF(13);
           tc_fence_after();
           float v[TP];
           tc_ld32(tmY + lane_sel + a * TP, v);
@@ -347,24 +430,28 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           mbar_arrive(YEMPTY(a));
 #pragma unroll
           for (int i = 0; i < TP; ++i) v[i] = fmaxf(fmaf(v[i], sc2, sh2), 0.f);
-          mbar_wait(H2EMPTY, (t & 1) ^ 1);
-          store_h_row(smem + OFF_H2, ch, v);
+          PROF(14);
+          mbar_wait_fast(H2EMPTY(a), ((t >> 1) & 1) ^ 1);
+          PROF(15);
+          store_h_row(smem + OFF_H2 + a * H_BYTES, ch, v);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(H2FULL);
+          if (lane == 0) mbar_arrive(H2FULL(a));
         }
       } else if (warp < 10) {
         rs.reset();
         const float b2 = __ldg(L.b2 + ch);
         for (int t = 0; t < n_tiles; ++t) {
           const int a = t & 1, s = t % NX;
-          mbar_wait(ZFULL(a), (t >> 1) & 1);
+          PROF(19);
+          mbar_wait_fast(ZFULL(a), (t >> 1) & 1);
+          PROF(17);
           tc_fence_after();
           float v[TP];
           tc_ld32(tmZ + lane_sel + a * TP, v);
           tc_fence_before();
           mbar_arrive(ZEMPTY(a));
-          mbar_wait(XFULL(s), (t / NX) & 1);              // completed long ago (the producers consumed the tile): orders our reads after the TMA write
+          mbar_wait_fast(XFULL(s), (t / NX) & 1);              // completed long ago (the producers consumed the tile): orders our reads after the TMA write
           uint8_t* xt = smem + OFF_X + s * X_BYTES;
           float x[TP];
           load_x_row(xt, ch, x);
@@ -388,19 +475,24 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
       } else {
         for (int t = 0; t < n_tiles; ++t) {
           const int s = t % NX;
-          mbar_wait(XFULL(s), (t / NX) & 1);
+          PROF(27);
+          mbar_wait_fast(XFULL(s), (t / NX) & 1);
+          PROF(24);
           float v[TP];
           load_x_row(smem + OFF_X + s * X_BYTES, ch, v);
 #pragma unroll
           for (int i = 0; i < TP; ++i) v[i] = fmaxf(fmaf(v[i], sc1, sh1), 0.f);
-          mbar_wait(H1EMPTY, (t & 1) ^ 1);
-          store_h_row(smem + OFF_H1, ch, v);
+          PROF(25);
+          mbar_wait_fast(H1EMPTY(t & 1), ((t >> 1) & 1) ^ 1);
+          PROF(26);
+          store_h_row(smem + OFF_H1 + (t & 1) * H_BYTES, ch, v);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(H1FULL);
+          if (lane == 0) mbar_arrive(H1FULL(t & 1));
         }
       }
       pass_end();
+      if (warp != 0) tp = clock64(); else PROF(29);
     }
   }
   tc_fence_before();
@@ -409,6 +501,25 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+// fp32 [128,128] (row = output channel) -> row-major bf16 [hi 32 KB | lo 32 KB]: the image load_w_row copies into tensor memory
+__global__ void pcn_pack_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ blob) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;            // one thread per (row, 8 consecutive k)
+  if (gid >= C * C / 8) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(W) + 2 * gid), b = __ldg(reinterpret_cast<const float4*>(W) + 2 * gid + 1);
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __nv_bfloat162 hv = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
+    const float2 hf = __bfloat1622float2(hv);
+    const __nv_bfloat162 lv = __floats2bfloat162_rn(x[2 * q] - hf.x, x[2 * q + 1] - hf.y);
+    h[q] = *reinterpret_cast<const uint32_t*>(&hv);
+    l[q] = *reinterpret_cast<const uint32_t*>(&lv);
+  }
+  *reinterpret_cast<uint4*>(blob + (size_t)gid * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(blob + WP_BYTES + (size_t)gid * 16) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
@@ -441,6 +552,21 @@ int make_act_map(CUtensorMap* tm, const float* base, int N, long long batch, int
 
 }  // namespace
 
+int pcn_profile_read(unsigned long long* out40, int reset) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out40, g_pcn_prof, sizeof(unsigned long long) * 40);
+  if (reset) { unsigned long long z[40] = {0}; cudaMemcpyToSymbol(g_pcn_prof, z, sizeof(z)); }
+  return e == cudaSuccess ? 0 : -1;
+}
+
+size_t pcn_weight_bytes() { return 2 * (size_t)WP_BYTES; }
+
+int launch_pcn_pack_weights(const float* W, uint8_t* blob, cudaStream_t st) {
+  LMPCR_REQUIRE(W && blob && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(blob)) & 15) == 0, LMPCR_ERR_ARG, "pcn_pack_weights: alignment");
+  pcn_pack_weights_kernel<<<(C * C / 8 + 255) / 256, 256, 0, st>>>(W, blob);
+  return check_launch("pcn_pack_weights_kernel");
+}
+
 bool pcn_supported(int Cc, int N, const float* x_in, long long in_batch, const float* x_out, long long out_batch) {
   return Cc == C && N >= 1 && (N & 3) == 0 && (in_batch & 3) == 0 && (out_batch & 3) == 0 && ((reinterpret_cast<uintptr_t>(x_in) & 15) == 0) &&
          ((reinterpret_cast<uintptr_t>(x_out) & 15) == 0) && encode_fn() != nullptr;
@@ -470,7 +596,9 @@ int launch_pcn_stack(const float* x_in, long long in_batch, float* x_out, long l
     }
   }
   const int grid = a.P < sm_count() ? a.P : sm_count();
-  pcn_stack_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_out, a);
+  PcnArgs b = a;
+  b.debug = getenv("LMPCR_PCN_DEBUG") ? atoi(getenv("LMPCR_PCN_DEBUG")) : 0;      // timing experiments only
+  pcn_stack_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_out, b);
   return check_launch("pcn_stack_kernel");
 }
 

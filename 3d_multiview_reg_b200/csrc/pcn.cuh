@@ -9,7 +9,7 @@ constexpr int PCN_C = 128;          // channels of the layers this kernel handle
 
 struct PcnBN { const float* g; const float* b; const float* rm; const float* rv; };
 struct PcnLayer {
-  // pre-split weights of conv.3 / conv.7 (lib/filtering/oanet.py:30,34): launch_split_weights(W, 128, 128) = 4 k-chunks x [hi 8 KB | lo 8 KB]
+  // weights of conv.3 / conv.7 (lib/filtering/oanet.py:30,34) as made by launch_pcn_pack_weights: row-major bf16 [hi 32 KB | lo 32 KB]
   const uint8_t* w1; const uint8_t* w2;
   const float* b1; const float* b2;
   PcnBN bn1, bn2;                   // conv.1 (in front of conv.3) and conv.5 (in front of conv.7); bn1 is unused for the first layer
@@ -24,11 +24,15 @@ struct PcnArgs {
   const float* lg_w; const float* lg_b; float* lg_logits; float* lg_scores; int32_t* lg_anypos;
   int store_out;                              // 0: with the head present the output tiles themselves are not stored
   int P, N;
+  int debug;                                  // timing experiments only (LMPCR_PCN_DEBUG); 0 in production
 };
 
 // x_in [P,128,N] (batch stride in_batch floats) -> x_out (batch stride out_batch; may be the same buffer: the stack then runs in place).
 // Needs N % 4 == 0 and 16-byte aligned bases (TMA tensor maps).  Returns LMPCR_ERR_UNSUPPORTED when the driver entry point for
 // tensor maps is not available.
+size_t pcn_weight_bytes();                                                       // bytes of one packed [128,128] weight matrix
+int launch_pcn_pack_weights(const float* W, uint8_t* blob, cudaStream_t st);    // W fp32 [128,128] contiguous, 16-byte aligned
+int pcn_profile_read(unsigned long long* out40, int reset);                     // timing experiments (LMPCR_PCN_DEBUG=1)
 bool pcn_supported(int C, int N, const float* x_in, long long in_batch, const float* x_out, long long out_batch);
 int launch_pcn_stack(const float* x_in, long long in_batch, float* x_out, long long out_batch, const PcnArgs& args, cudaStream_t st);
 

@@ -93,6 +93,8 @@ int lmpcr_nn_tensor_debug(const float* q_feat, int n_q_sets, int n_q, const floa
 
 /* Diagnostic: per-role cycle counters of the tensor-core GEMM (filled only when LMPCR_TC_DEBUG has bit 8 set). */
 int lmpcr_debug_tc_profile(unsigned long long* out16, int reset);
+/* The same for the pair-resident PointCN kernel (LMPCR_PCN_DEBUG=1): 40 counters, see csrc/pcn.cu. */
+int lmpcr_debug_pcn_profile(unsigned long long* out40, int reset);
 
 /* lib/utils.py:968-992 `pairwise_distance` itself, materialised: src [B,n,dim], dst [B,m,dim] -> out [B,n,m] fp32,
  * bit-identical to the reference's CPU evaluation.  Not on the hot path (which never stores the matrix); kept so
