@@ -14,12 +14,12 @@
 // and writes its 128-byte row conflict-free) -- no per-element address arithmetic, no register-staged global loads.
 // Products are split-bf16 (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, fp32 accumulation in TMEM) exactly as in tcgemm.cu.
 //
-// Warp roles (448 threads, one CTA per SM):
+// Warp roles (576 threads, one CTA per SM):
 //   warp 0       TMA: x tile loads (+ L2 prefetch a few tiles ahead), output tile stores
-//   warp 1       tcgen05.mma issue (M128 x N32 x K16, 24 per GEMM tile)
+//   warp 1       tcgen05.mma issue (M128 x N64 x K16, 24 per GEMM tile of 64 points)
 //   warps 2-5    TMEM readers A: pass A statistics of y; pass B f2 + hi/lo split -> h2
 //   warps 6-9    TMEM readers B: pass B epilogue (z + b2 + x, statistics, tile written back over the x tile)
-//   warps 10-13  producers: x tile (smem, fp32) -> f1 -> hi/lo split -> h1
+//   warps 10-17  producers: x tile (smem, fp32) -> f1 -> hi/lo split -> h1 (warps 10-13 the first box of a tile, 14-17 the second)
 // Thread t of every 4-warp role owns channel ((warp & 3) << 5) | lane = the TMEM lane its warp may read.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -34,28 +34,32 @@ namespace lmpcr {
 namespace {
 
 constexpr int C = PCN_C;                     // channels = M = K of both GEMMs
-constexpr int TP = 32;                       // points per tile (= 128 bytes per channel row: one SWIZZLE_128B span)
-constexpr int NX = 6;                        // x-tile ring
-constexpr int PF_DIST = 8;                   // L2 prefetch distance in tiles
+constexpr int TS = 32;                       // points per TMA box (= 128 bytes per channel row: one SWIZZLE_128B span)
+constexpr int NSUB = 2;                      // boxes per MMA tile
+constexpr int TP = TS * NSUB;                // points per MMA tile.  A tcgen05.mma M128 x N x K16 costs max(~50, N/2) clocks (measured,
+                                             // profiles/r2_mma_rate_microbench.txt): 24 of them per GEMM tile make 32-point tiles issue-bound
+constexpr int NX = 4;                        // x-tile ring (tiles of NSUB boxes)
+constexpr int PF_DIST = 3;                   // L2 prefetch distance in tiles (pass B only: its x slots are held until the tile is stored)
 constexpr int WP_BYTES = C * C * 2;          // one bf16 part (hi or lo) of a weight matrix, row-major [out][in]: 32 KB
-constexpr int X_BYTES = C * TP * 4;          // 16 KB
-constexpr int HP_BYTES = C * TP * 2;         // one bf16 part of an h tile: 8 KB
+constexpr int XS_BYTES = C * TS * 4;         // one box: 16 KB
+constexpr int X_BYTES = NSUB * XS_BYTES;     // 32 KB
+constexpr int HP_BYTES = C * TP * 2;         // one bf16 part of an h tile: 16 KB
 constexpr int H_BYTES = 2 * HP_BYTES;        // hi | lo
-constexpr int OFF_X = 0, OFF_H1 = OFF_X + NX * X_BYTES, OFF_H2 = OFF_H1 + 2 * H_BYTES;
-constexpr int OFF_SC = OFF_H2 + 2 * H_BYTES; // sc1[128], sh1[128]: f1 of the next layer, written by the epilogue threads
+constexpr int OFF_X = 0, OFF_H1 = OFF_X + NX * X_BYTES, OFF_H2 = OFF_H1 + 2 * H_BYTES;       // h1 double-buffered, h2 single
+constexpr int OFF_SC = OFF_H2 + H_BYTES; // sc1[128], sh1[128]: f1 of the next layer, written by the epilogue threads
 constexpr int OFF_BAR = OFF_SC + 2 * C * 4;
 constexpr int N_BARS = 3 * NX + 16;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr size_t SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
-constexpr int NTHREADS = 14 * 32;
+constexpr int NTHREADS = 18 * 32;
 // Tensor memory (512 columns): both weight matrices of the layer as bf16 hi | lo, row = TMEM lane, two elements per 32-bit column
-// (the A operand of tcgen05.mma read from TMEM: per MMA only the 1 KB activation operand crosses shared memory instead of 5 KB --
-// with the weights in shared memory the kernel was bound by the tensor core's operand reads, ncu: 52 % of the shared-memory
-// bandwidth, tensor pipe 21 %), then the accumulators y[2] | z[2] of 32 columns each
+// (the A operand of tcgen05.mma read from TMEM: per MMA only the activation operand crosses shared memory -- with the weights in
+// shared memory the tensor core's operand reads took 52 % of the shared-memory bandwidth), then the accumulators y[2] | z[2]
 constexpr int TMEM_COLS = 512;
 constexpr int TM_W1 = 0, TM_W2 = 128, TM_Y = 256, TM_Z = 256 + 2 * TP;       // W: [hi 64 columns | lo 64 columns]
-constexpr uint32_t MN_SBO = 128, MN_LBO = (TP / 8) * 128;   // h tile (MN-major): point-groups adjacent, channel-groups 512 B apart
+static_assert(TM_Z + 2 * TP <= TMEM_COLS, "tensor memory budget");
+constexpr uint32_t MN_SBO = 128, MN_LBO = (TP / 8) * 128;   // h tile (MN-major): point-groups adjacent, channel-groups 1 KB apart
 constexpr uint32_t IDESC = make_idesc(1, 0, 1, 128, TP);
 
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -91,12 +95,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// 32 fp32 values of one channel row -> bf16 hi/lo in the MN-major operand image: channel-group (k>>3) at 512 B, point-group g at
-// 128 B, row (k&7) at 16 B; the lo part HP_BYTES further
-__device__ __forceinline__ void store_h_row(uint8_t* hbase, int k, const float (&v)[TP]) {
-  uint8_t* row = hbase + (k >> 3) * MN_LBO + (k & 7) * 16;
+// 32 fp32 values of one channel row (box `sub` of the tile) -> bf16 hi/lo in the MN-major operand image: channel-group (k>>3) at
+// MN_LBO, point-group at 128 B, row (k&7) at 16 B; the lo part HP_BYTES further
+__device__ __forceinline__ void store_h_row(uint8_t* hbase, int k, int sub, const float (&v)[TS]) {
+  uint8_t* row = hbase + (k >> 3) * MN_LBO + (k & 7) * 16 + sub * (TS / 8) * MN_SBO;
 #pragma unroll
-  for (int gq = 0; gq < TP / 8; ++gq) {
+  for (int gq = 0; gq < TS / 8; ++gq) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -113,7 +117,7 @@ __device__ __forceinline__ void store_h_row(uint8_t* hbase, int k, const float (
 }
 
 // one channel row (32 floats = 8 chunks of 16 bytes) of a SWIZZLE_128B tile: chunk c of row r sits at chunk position c ^ (r & 7)
-__device__ __forceinline__ void load_x_row(const uint8_t* xt, int r, float (&v)[TP]) {
+__device__ __forceinline__ void load_x_row(const uint8_t* xt, int r, float (&v)[TS]) {
   const uint8_t* row = xt + r * 128;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -121,7 +125,7 @@ __device__ __forceinline__ void load_x_row(const uint8_t* xt, int r, float (&v)[
     v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
   }
 }
-__device__ __forceinline__ void store_x_row(uint8_t* xt, int r, const float (&v)[TP]) {
+__device__ __forceinline__ void store_x_row(uint8_t* xt, int r, const float (&v)[TS]) {
   uint8_t* row = xt + r * 128;
 #pragma unroll
   for (int c = 0; c < 8; ++c)
@@ -132,15 +136,16 @@ __device__ __forceinline__ void store_x_row(uint8_t* xt, int r, const float (&v)
 struct RunStat {
   float c0, s1, s2; bool have;
   __device__ __forceinline__ void reset() { c0 = 0.f; s1 = 0.f; s2 = 0.f; have = false; }
-  __device__ __forceinline__ void add_tile(const float (&v)[TP], int ncv) {
+  __device__ __forceinline__ void add_tile(const float (&v)[TS], int ncv) {      // ncv: valid columns of this box (may be <= 0)
+    if (ncv <= 0) return;
     if (!have) { c0 = v[0]; have = true; }
     float a = 0.f, b = 0.f;
-    if (ncv >= TP) {
+    if (ncv >= TS) {
 #pragma unroll
-      for (int i = 0; i < TP; ++i) { const float d = v[i] - c0; a += d; b = fmaf(d, d, b); }
+      for (int i = 0; i < TS; ++i) { const float d = v[i] - c0; a += d; b = fmaf(d, d, b); }
     } else {
 #pragma unroll
-      for (int i = 0; i < TP; ++i) if (i < ncv) { const float d = v[i] - c0; a += d; b = fmaf(d, d, b); }
+      for (int i = 0; i < TS; ++i) if (i < ncv) { const float d = v[i] - c0; a += d; b = fmaf(d, d, b); }
     }
     s1 += a; s2 += b;
   }
@@ -210,9 +215,9 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   // arithmetic of every role is local to a pass: use k of a ring slot / of a single barrier completes phase k
   auto pass_begin = [&]() {
     if (threadIdx.x == 0) {
-      for (int s = 0; s < NX; ++s) { mbar_init(XFULL(s), 1); mbar_init(XREAD(s), 4); mbar_init(OUTRDY(s), 4); }
+      for (int s = 0; s < NX; ++s) { mbar_init(XFULL(s), 1); mbar_init(XREAD(s), 8); mbar_init(OUTRDY(s), 4); }
       for (int a = 0; a < 2; ++a) {
-        mbar_init(H1FULL(a), 4); mbar_init(H1EMPTY(a), 1); mbar_init(H2FULL(a), 4); mbar_init(H2EMPTY(a), 1);
+        mbar_init(H1FULL(a), 8); mbar_init(H1EMPTY(a), 1); mbar_init(H2FULL(a), 4); mbar_init(H2EMPTY(a), 1);
         mbar_init(YFULL(a), 1); mbar_init(YEMPTY(a), 128); mbar_init(ZFULL(a), 1); mbar_init(ZEMPTY(a), 128);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -225,18 +230,18 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     tc_fence_after();
   };
 
-  // one GEMM tile: D[128 x 32] = W (bf16 hi | lo in tensor memory at tW) . h (operand image at sH), three bf16 products per K step.
+  // one GEMM tile: D[128 x TP] = W (bf16 hi | lo in tensor memory at tW) . h (operand image at sH), three bf16 products per K step.
   // The shared-memory descriptors of the eight K steps differ only in the start-address field: one 32-bit add each.
   constexpr uint32_t DESC_HI = (MN_SBO >> 4) | (1u << 14);                     // SBO, descriptor version
-  auto issue_gemm = [&](uint32_t tW, uint32_t sH, uint32_t d_tmem) {
+  auto issue_gemm = [&](uint32_t tW, uint32_t sH, uint32_t d_tmem, uint32_t leader) {
     const uint32_t lo0 = ((sH >> 4) & 0x3FFFu) | ((MN_LBO >> 4) << 16);
 #pragma unroll
     for (int j = 0; j < C / 16; ++j) {
       const uint32_t lo_hi = lo0 + j * ((2 * MN_LBO) >> 4), lo_lo = lo_hi + (HP_BYTES >> 4);
       const uint64_t b_hi = ((uint64_t)DESC_HI << 32) | lo_hi, b_lo = ((uint64_t)DESC_HI << 32) | lo_lo;
-      tc_mma_ts(d_tmem, tW + 64 + j * 8, b_hi, IDESC, j ? 1u : 0u);            // W_lo . h_hi   (small terms first)
-      tc_mma_ts(d_tmem, tW + j * 8, b_lo, IDESC, 1u);                          // W_hi . h_lo
-      tc_mma_ts(d_tmem, tW + j * 8, b_hi, IDESC, 1u);                          // W_hi . h_hi
+      tc_mma_ts_pred(d_tmem, tW + 64 + j * 8, b_hi, IDESC, j ? 1u : 0u, leader);    // W_lo . h_hi   (small terms first)
+      tc_mma_ts_pred(d_tmem, tW + j * 8, b_lo, IDESC, 1u, leader);                  // W_hi . h_lo
+      tc_mma_ts_pred(d_tmem, tW + j * 8, b_hi, IDESC, 1u, leader);                  // W_hi . h_hi
     }
   };
   // this thread's row of a weight matrix (row-major bf16 [hi 32 KB | lo 32 KB] in global memory) -> tensor memory
@@ -255,6 +260,29 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         tc_st32(tW + lane_sel + part * 64 + hh * 32, r);
       }
     }
+  };
+  // x boxes of tile t that overlap the point range: a box that starts at or past N is neither loaded nor stored
+  auto n_boxes = [&](int t) { return (g.N - t * TP > TS) ? 2 : 1; };
+  auto load_tile = [&](const CUtensorMap* tm, int t, int s, int p) {
+    const int nb = n_boxes(t);
+    mbar_expect_tx(XFULL(s), nb * XS_BYTES);
+    for (int b = 0; b < nb; ++b) tma_load_3d(sX + s * X_BYTES + b * XS_BYTES, tm, t * TP + b * TS, 0, p, XFULL(s));
+  };
+  auto prefetch_tile = [&](const CUtensorMap* tm, int t, int p) {
+    for (int b = 0; b < n_boxes(t); ++b) tma_prefetch_3d(tm, t * TP + b * TS, 0, p);
+  };
+  // producer step: box `sub` of tile t (slot s) -> f1 -> h1[t & 1]
+  auto produce = [&](int t, int s, int sub, float sc1, float sh1) {
+    float v[TS];
+    if (g.N - t * TP - sub * TS > 0) {
+      load_x_row(smem + OFF_X + s * X_BYTES + sub * XS_BYTES, ch, v);
+#pragma unroll
+      for (int i = 0; i < TS; ++i) v[i] = fmaxf(fmaf(v[i], sc1, sh1), 0.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < TS; ++i) v[i] = 0.f;           // box past the end of the pair: finite operand values, columns never stored
+    }
+    return store_h_row(smem + OFF_H1 + (t & 1) * H_BYTES, ch, sub, v);
   };
 
   float sc1 = 1.f, sh1 = 0.f;      // producers: f1 of the current layer for channel `ch`
@@ -280,185 +308,187 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
       tc_fence_after();
       if (warp == 0) {
         if (lane == 0) {
-          for (int t = 0; t < PF_DIST && t < n_tiles; ++t) tma_prefetch_3d(tm_src, t * TP, 0, p);
-          for (int t = 0; t < n_tiles; ++t) {
+          for (int t = 0; t < n_tiles; ++t) {              // NX tiles (128 KB) in flight: no L2 prefetch needed in this pass
             const int s = t % NX;
-            PROF(1);
-            if (t >= NX) mbar_wait_fast(XREAD(s), ((t / NX) - 1) & 1);
             PROF(0);
-            mbar_expect_tx(XFULL(s), X_BYTES);
-            tma_load_3d(sX + s * X_BYTES, tm_src, t * TP, 0, p, XFULL(s));
-            if (t + PF_DIST < n_tiles) tma_prefetch_3d(tm_src, (t + PF_DIST) * TP, 0, p);
+            if (t >= NX) mbar_wait_fast(XREAD(s), ((t / NX) - 1) & 1);
+            PROF(1);
+            load_tile(tm_src, t, s, p);
           }
         }
       } else if (warp == 1) {
-        if (lane == 0) {
-          for (int t = 0; t < n_tiles; ++t) {
-            const int a = t & 1, ph = (t >> 1) & 1;
-            PROF(7);
-            mbar_wait_fast(H1FULL(a), ph);
-            PROF(5);
-            mbar_wait_fast(YEMPTY(a), ph ^ 1);
-            PROF(6);
-            tc_fence_after();
-            issue_gemm(tmW1, sH1 + a * H_BYTES, tmY + a * TP);
-            tc_commit(H1EMPTY(a));
-            tc_commit(YFULL(a));
-          }
-          for (int b = 0; b < 2; ++b) {                    // every commit of this pass has arrived before the barriers are re-initialised
-            const int uses = (n_tiles + 1 - b) >> 1;
-            if (uses > 0) mbar_wait_fast(H1EMPTY(b), (uses - 1) & 1);
-          }
+        // the whole warp runs this loop converged; one elected lane issues the MMAs and commits (tc_ptx.cuh: elect_one)
+        for (int t = 0; t < n_tiles; ++t) {
+          const int a = t & 1, ph = (t >> 1) & 1;
+          PROF(2);
+          mbar_wait_fast(H1FULL(a), ph);
+          PROF(3);
+          mbar_wait_fast(YEMPTY(a), ph ^ 1);
+          PROF(4);
+          tc_fence_after();
+          const uint32_t leader = elect_one();
+          issue_gemm(tmW1, sH1 + a * H_BYTES, tmY + a * TP, leader);
+          tc_commit_pred(H1EMPTY(a), leader);
+          tc_commit_pred(YFULL(a), leader);
+          __syncwarp();
+        }
+        for (int b = 0; b < 2; ++b) {                    // every commit of this pass has arrived before the barriers are re-initialised
+          const int uses = (n_tiles + 1 - b) >> 1;
+          if (uses > 0) mbar_wait_fast(H1EMPTY(b), (uses - 1) & 1);
         }
       } else if (warp < 6) {
-        rs.reset();
-        const float b1 = __ldg(L.b1 + ch);
+        rs.reset();                          // statistics of the raw accumulator: the bias only shifts the mean
         for (int t = 0; t < n_tiles; ++t) {
           const int a = t & 1;
-          PROF(12);
+          PROF(5);
           mbar_wait_fast(YFULL(a), (t >> 1) & 1);
-          PROF(11);
+          PROF(6);
           tc_fence_after();
-          float v[TP];
-          tc_ld32(tmY + lane_sel + a * TP, v);
-          tc_fence_before();
-          mbar_arrive(YEMPTY(a));
 #pragma unroll
-          for (int i = 0; i < TP; ++i) v[i] += b1;
-          rs.add_tile(v, g.N - t * TP);
+          for (int sub = 0; sub < NSUB; ++sub) {
+            float v[TS];
+            tc_ld32(tmY + lane_sel + a * TP + sub * TS, v);
+            if (sub == NSUB - 1) { tc_fence_before(); mbar_arrive(YEMPTY(a)); }
+            rs.add_tile(v, g.N - t * TP - sub * TS);
+          }
         }
+        const float b1 = __ldg(L.b1 + ch);
         float mean, var;
         rs.finish(g.N, mean, var);
-        fold_affine(mean, var, 1e-5f, L.bn2, ch, sc2, sh2);
+        fold_affine(mean + b1, var, 1e-5f, L.bn2, ch, sc2, sh2);
         sh2 = fmaf(b1, sc2, sh2);            // f2(acc + b1) = relu(acc * sc2 + (b1 * sc2 + sh2))
       } else if (warp >= 10) {
+        const int sub = (warp >= 14) ? 1 : 0;
         for (int t = 0; t < n_tiles; ++t) {
           const int s = t % NX;
-          PROF(23);
+          PROF(7);
           mbar_wait_fast(XFULL(s), (t / NX) & 1);
-          PROF(20);
-          float v[TP];
-          load_x_row(smem + OFF_X + s * X_BYTES, ch, v);
-#pragma unroll
-          for (int i = 0; i < TP; ++i) v[i] = fmaxf(fmaf(v[i], sc1, sh1), 0.f);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(XREAD(s));        // the tile is in registers: the slot may be refilled
-          PROF(21);
+          PROF(8);
           mbar_wait_fast(H1EMPTY(t & 1), ((t >> 1) & 1) ^ 1);
-          PROF(22);
-          store_h_row(smem + OFF_H1 + (t & 1) * H_BYTES, ch, v);
+          PROF(9);
+          produce(t, s, sub, sc1, sh1);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(H1FULL(t & 1));
+          if (lane == 0) { mbar_arrive(XREAD(s)); mbar_arrive(H1FULL(t & 1)); }
         }
       }
       pass_end();
-      if (warp != 0) tp = clock64(); else PROF(28);     // 28: rest of pass A as seen by the loader thread (drain)
+      if (warp != 0) tp = clock64(); else PROF(10);     // 28: rest of pass A as seen by the loader thread (drain)
       // ======================================================== pass B: z = x + W2 f2(W1 f1(x) + b1) + b2
       const CUtensorMap* tm_dst = &tm_out;
       pass_begin();
       if (warp == 0) {
         if (lane == 0) {
-          for (int t = 0; t < PF_DIST && t < n_tiles; ++t) tma_prefetch_3d(tm_src, t * TP, 0, p);
+          auto store_tile = [&](int u, int s) {
+            for (int b = 0; b < n_boxes(u); ++b) tma_store_3d(tm_dst, sX + s * X_BYTES + b * XS_BYTES, u * TP + b * TS, 0, p);
+            bulk_commit();
+          };
+          for (int t = 0; t < PF_DIST && t < n_tiles; ++t) prefetch_tile(tm_src, t, p);
           for (int t = 0; t < n_tiles; ++t) {
             const int s = t % NX;
-            PROF(4);
+            PROF(16);
             if (t >= NX) {
               const int u = t - NX;
               mbar_wait_fast(OUTRDY(s), (u / NX) & 1);
-              PROF(2);
-              tma_store_3d(tm_dst, sX + s * X_BYTES, u * TP, 0, p);
-              bulk_commit();
+              PROF(17);
+              store_tile(u, s);
               bulk_wait_read0();
-              PROF(3);
+              PROF(18);
             }
-            mbar_expect_tx(XFULL(s), X_BYTES);
-            tma_load_3d(sX + s * X_BYTES, tm_src, t * TP, 0, p, XFULL(s));
-            if (t + PF_DIST < n_tiles) tma_prefetch_3d(tm_src, (t + PF_DIST) * TP, 0, p);
+            load_tile(tm_src, t, s, p);
+            if (t + PF_DIST < n_tiles) prefetch_tile(tm_src, t + PF_DIST, p);
           }
           for (int u = (n_tiles > NX ? n_tiles - NX : 0); u < n_tiles; ++u) {
             const int s = u % NX;
             mbar_wait_fast(OUTRDY(s), (u / NX) & 1);
-            tma_store_3d(tm_dst, sX + s * X_BYTES, u * TP, 0, p);
-            bulk_commit();
+            store_tile(u, s);
           }
           bulk_wait0();                                   // the pair's new activations are in global memory before the next pass reads them
         }
       } else if (warp == 1) {
-        if (lane == 0) {
-          for (int t = 0; t <= n_tiles; ++t) {
-            if (t < n_tiles) {
-              const int a = t & 1, ph = (t >> 1) & 1;
-              PROF(10);
-              mbar_wait_fast(H1FULL(a), ph);
-              PROF(5);
-              mbar_wait_fast(YEMPTY(a), ph ^ 1);
-              PROF(6);
-              tc_fence_after();
-              issue_gemm(tmW1, sH1 + a * H_BYTES, tmY + a * TP);
-              tc_commit(H1EMPTY(a));
-              tc_commit(YFULL(a));
-            }
-            if (t >= 1) {
-              const int u = t - 1, a = u & 1, ph = (u >> 1) & 1;
-              PROF(7);
-              mbar_wait_fast(H2FULL(a), ph);
-              PROF(8);
-              mbar_wait_fast(ZEMPTY(a), ph ^ 1);
-              PROF(9);
-              tc_fence_after();
-              issue_gemm(tmW2, sH2 + a * H_BYTES, tmZ + a * TP);
-              tc_commit(H2EMPTY(a));
-              tc_commit(ZFULL(a));
-            }
+        for (int t = 0; t <= n_tiles; ++t) {
+          if (t < n_tiles) {
+            const int a = t & 1, ph = (t >> 1) & 1;
+            PROF(19);
+            mbar_wait_fast(H1FULL(a), ph);
+            PROF(20);
+            mbar_wait_fast(YEMPTY(a), ph ^ 1);
+            PROF(21);
+            tc_fence_after();
+            const uint32_t leader = elect_one();
+            issue_gemm(tmW1, sH1 + a * H_BYTES, tmY + a * TP, leader);
+            tc_commit_pred(H1EMPTY(a), leader);
+            tc_commit_pred(YFULL(a), leader);
+            __syncwarp();
           }
-          for (int b = 0; b < 2; ++b) {
-            const int uses = (n_tiles + 1 - b) >> 1;
-            if (uses > 0) { mbar_wait_fast(H1EMPTY(b), (uses - 1) & 1); mbar_wait_fast(H2EMPTY(b), (uses - 1) & 1); }
+          if (t >= 1) {
+            const int u = t - 1, a = u & 1, ph = (u >> 1) & 1;
+            PROF(22);
+            mbar_wait_fast(H2FULL(0), u & 1);
+            PROF(23);
+            mbar_wait_fast(ZEMPTY(a), ph ^ 1);
+            PROF(24);
+            tc_fence_after();
+            const uint32_t leader = elect_one();
+            issue_gemm(tmW2, sH2, tmZ + a * TP, leader);
+            tc_commit_pred(H2EMPTY(0), leader);
+            tc_commit_pred(ZFULL(a), leader);
+            __syncwarp();
           }
         }
+        for (int b = 0; b < 2; ++b) {
+          const int uses = (n_tiles + 1 - b) >> 1;
+          if (uses > 0) mbar_wait_fast(H1EMPTY(b), (uses - 1) & 1);
+        }
+        mbar_wait_fast(H2EMPTY(0), (n_tiles - 1) & 1);
       } else if (warp < 6) {
         for (int t = 0; t < n_tiles; ++t) {
           const int a = t & 1;
-          PROF(16);
+          PROF(25);
           mbar_wait_fast(YFULL(a), (t >> 1) & 1);
-          PROF(13);
+          PROF(26);
           tc_fence_after();
-          float v[TP];
-          tc_ld32(tmY + lane_sel + a * TP, v);
-          tc_fence_before();
-          mbar_arrive(YEMPTY(a));
+          mbar_wait_fast(H2EMPTY(0), (t & 1) ^ 1);
+          PROF(27);
 #pragma unroll
-          for (int i = 0; i < TP; ++i) v[i] = fmaxf(fmaf(v[i], sc2, sh2), 0.f);
-          PROF(14);
-          mbar_wait_fast(H2EMPTY(a), ((t >> 1) & 1) ^ 1);
-          PROF(15);
-          store_h_row(smem + OFF_H2 + a * H_BYTES, ch, v);
+          for (int sub = 0; sub < NSUB; ++sub) {
+            float v[TS];
+            tc_ld32(tmY + lane_sel + a * TP + sub * TS, v);
+            if (sub == NSUB - 1) { tc_fence_before(); mbar_arrive(YEMPTY(a)); }
+#pragma unroll
+            for (int i = 0; i < TS; ++i) v[i] = fmaxf(fmaf(v[i], sc2, sh2), 0.f);
+            store_h_row(smem + OFF_H2, ch, sub, v);
+          }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(H2FULL(a));
+          if (lane == 0) mbar_arrive(H2FULL(0));
         }
       } else if (warp < 10) {
         rs.reset();
         const float b2 = __ldg(L.b2 + ch);
         for (int t = 0; t < n_tiles; ++t) {
           const int a = t & 1, s = t % NX;
-          PROF(19);
+          PROF(28);
           mbar_wait_fast(ZFULL(a), (t >> 1) & 1);
-          PROF(17);
+          PROF(29);
           tc_fence_after();
-          float v[TP];
-          tc_ld32(tmZ + lane_sel + a * TP, v);
-          tc_fence_before();
-          mbar_arrive(ZEMPTY(a));
           mbar_wait_fast(XFULL(s), (t / NX) & 1);              // completed long ago (the producers consumed the tile): orders our reads after the TMA write
-          uint8_t* xt = smem + OFF_X + s * X_BYTES;
-          float x[TP];
-          load_x_row(xt, ch, x);
 #pragma unroll
-          for (int i = 0; i < TP; ++i) v[i] = (v[i] + b2) + x[i];
-          rs.add_tile(v, g.N - t * TP);
-          store_x_row(xt, ch, v);
+          for (int sub = 0; sub < NSUB; ++sub) {
+            float v[TS];
+            tc_ld32(tmZ + lane_sel + a * TP + sub * TS, v);
+            if (sub == NSUB - 1) { tc_fence_before(); mbar_arrive(ZEMPTY(a)); }
+            const int ncv = g.N - t * TP - sub * TS;
+            if (ncv > 0) {
+              uint8_t* xt = smem + OFF_X + s * X_BYTES + sub * XS_BYTES;
+              float x[TS];
+              load_x_row(xt, ch, x);
+#pragma unroll
+              for (int i = 0; i < TS; ++i) v[i] = (v[i] + b2) + x[i];
+              rs.add_tile(v, ncv);
+              store_x_row(xt, ch, v);
+            }
+          }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(OUTRDY(s));
@@ -473,26 +503,22 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           *reinterpret_cast<float2*>(g.stats_out + ((size_t)p * C + ch) * 2) = make_float2(mean, var * (float)g.N);
         }
       } else {
+        const int sub = (warp >= 14) ? 1 : 0;
         for (int t = 0; t < n_tiles; ++t) {
           const int s = t % NX;
-          PROF(27);
+          PROF(30);
           mbar_wait_fast(XFULL(s), (t / NX) & 1);
-          PROF(24);
-          float v[TP];
-          load_x_row(smem + OFF_X + s * X_BYTES, ch, v);
-#pragma unroll
-          for (int i = 0; i < TP; ++i) v[i] = fmaxf(fmaf(v[i], sc1, sh1), 0.f);
-          PROF(25);
+          PROF(31);
           mbar_wait_fast(H1EMPTY(t & 1), ((t >> 1) & 1) ^ 1);
-          PROF(26);
-          store_h_row(smem + OFF_H1 + (t & 1) * H_BYTES, ch, v);
+          PROF(32);
+          produce(t, s, sub, sc1, sh1);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(H1FULL(t & 1));
         }
       }
       pass_end();
-      if (warp != 0) tp = clock64(); else PROF(29);
+      if (warp != 0) tp = clock64(); else PROF(33);
     }
   }
   tc_fence_before();
@@ -543,7 +569,7 @@ int make_act_map(CUtensorMap* tm, const float* base, int N, long long batch, int
   LMPCR_REQUIRE(fn, LMPCR_ERR_UNSUPPORTED, "pcn: cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)C, (cuuint64_t)P};
   const cuuint64_t strides[2] = {(cuuint64_t)N * 4, (cuuint64_t)batch * 4};
-  const cuuint32_t box[3] = {TP, C, 1}, estr[3] = {1, 1, 1};
+  const cuuint32_t box[3] = {TS, C, 1}, estr[3] = {1, 1, 1};
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LMPCR_REQUIRE(r == CUDA_SUCCESS, LMPCR_ERR_LAUNCH, "pcn: cuTensorMapEncodeTiled failed (%d) for N=%d batch=%lld P=%d", (int)r, N, batch, P);

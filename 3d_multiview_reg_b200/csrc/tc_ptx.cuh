@@ -71,6 +71,30 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Converged-warp issue: the WHOLE warp executes these, one elected lane issues (elect.sync + predication, no divergent branch).  A
+// tcgen05 instruction inside `if (lane == 0)` makes ptxas wrap every single one in an ELECT / BRA.U.ANY retry loop (~8 instructions
+// and a branch per MMA), which costs more than the MMA itself at small N.
+__device__ __forceinline__ uint32_t elect_one() {          // 1 in exactly one lane of the (converged) warp
+  uint32_t is_leader;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(is_leader));
+  return is_leader;
+}
+__device__ __forceinline__ void tc_mma_ts_pred(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nsetp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pred(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nsetp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pred(uint32_t bar, uint32_t leader) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}"
+               ::"r"(bar), "r"(leader) : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t of the warp = TMEM lane base+t)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];

@@ -286,7 +286,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs this loop converged and ONE ELECTED lane issues (elect.sync + predication).  Inside `if (lane == 0)` ptxas
+    // wraps every tcgen05.mma in an ELECT / BRA.U.ANY retry loop: measured 50 clocks per M128 x N64 x K16 MMA instead of the 32 the
+    // tensor core needs (profiles/r2_mma_rate_elect_issue.txt).
+    {
       constexpr uint32_t IDESC = make_idesc(1, 0, B_KMAJOR ? 0 : 1, TM, TN);
       constexpr uint32_t B_LBO = B_KMAJOR ? K_LBO : MN_LBO, B_SBO = B_KMAJOR ? K_SBO : MN_SBO;
       int stage = 0, acc = 0; uint32_t phase = 0, acc_phase = 0;
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
           mbar_wait(FULL(stage), phase);
           tc_fence_after();
           TC_PROF(1, tp);
+          const uint32_t leader = elect_one();
           const uint32_t sA = smem_u32(smem + (size_t)stage * STAGE_BYTES), sB = sA + 2 * A_OP_BYTES;
 #pragma unroll
           for (int ks = 0; ks < KC / 16; ++ks) {
@@ -310,18 +314,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
             const uint64_t a_lo = make_desc(sA + A_OP_BYTES + ks * 2 * K_LBO, K_LBO, K_SBO);
             const uint64_t b_hi = make_desc(sB + ks * 2 * B_LBO, B_LBO, B_SBO);
             const uint64_t b_lo = make_desc(sB + B_OP_BYTES + ks * 2 * B_LBO, B_LBO, B_SBO);
-            tc_mma_f16(d_tmem, a_lo, b_hi, IDESC, (kf | ks) ? 1u : 0u);   // small terms first
-            tc_mma_f16(d_tmem, a_hi, b_lo, IDESC, 1u);
-            tc_mma_f16(d_tmem, a_hi, b_hi, IDESC, 1u);
+            tc_mma_f16_pred(d_tmem, a_lo, b_hi, IDESC, (kf | ks) ? 1u : 0u, leader);   // small terms first
+            tc_mma_f16_pred(d_tmem, a_hi, b_lo, IDESC, 1u, leader);
+            tc_mma_f16_pred(d_tmem, a_hi, b_hi, IDESC, 1u, leader);
           }
-          tc_commit(EMPTY(stage));
+          tc_commit_pred(EMPTY(stage), leader);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           TC_PROF(2, tp);
           if (++kf == FL || kc == n_kc - 1) {    // segment complete: hand the accumulator to the epilogue warps
-            tc_commit(T_FULL(acc));
+            tc_commit_pred(T_FULL(acc), leader);
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
             kf = 0;
           }
+          __syncwarp();
         }
       }
     }

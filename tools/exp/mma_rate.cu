@@ -11,7 +11,7 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
                ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
 template <int N, int NACC, bool SS>
-__global__ void __launch_bounds__(128) k(long long* out, int reps) {
+__global__ void __launch_bounds__(128) k(long long* out, int reps, int mode) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t slot;
@@ -24,7 +24,19 @@ __global__ void __launch_bounds__(128) k(long long* out, int reps) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tb = slot;
-  if (threadIdx.x == 0) {
+  if (mode == 1 && warp == 0) {          // converged warp, elected lane issues (predication instead of a divergent branch)
+    const uint32_t idesc = make_idesc(1, 0, 1, 128, N);
+    const uint64_t bdesc = make_desc(smem_u32(sm), (N / 8) * 128, 128);
+    const uint32_t leader = elect_one();
+    const long long t0 = clock64();
+#pragma unroll 8
+    for (int r = 0; r < reps; ++r) tc_mma_ts_pred(tb + (r % NACC) * N, tb + 448 + (r & 7) * 8, bdesc, idesc, 1u, leader);
+    const long long t1 = clock64();
+    tc_commit_pred(smem_u32(&bar), leader);
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t2 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  } else if (mode == 0 && threadIdx.x == 0) {
     const uint32_t idesc = make_idesc(1, 0, 1, 128, N);
     const uint64_t bdesc = make_desc(smem_u32(sm), (N / 8) * 128, 128);
     const uint64_t adesc = make_desc(smem_u32(sm) + 8192, 128, 256);      // SS variant: K-major A, 128 rows x 16 k
@@ -45,15 +57,15 @@ __global__ void __launch_bounds__(128) k(long long* out, int reps) {
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
 }
-template <int N, int NACC, bool SS> void run(long long* d, int grid) {
+template <int N, int NACC, bool SS> void run(long long* d, int grid, int mode = 0) {
   const int reps = 480;
   cudaFuncSetAttribute(k<N, NACC, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
-  k<N, NACC, SS><<<grid, 128, 32768>>>(d, reps);
-  k<N, NACC, SS><<<grid, 128, 32768>>>(d, reps);
+  k<N, NACC, SS><<<grid, 128, 32768>>>(d, reps, mode);
+  k<N, NACC, SS><<<grid, 128, 32768>>>(d, reps, mode);
   cudaDeviceSynchronize();
   long long h[2];
   cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-  printf("%s N=%3d accumulators=%d grid=%3d: issue %.1f clk/MMA, issue+complete %.1f clk/MMA (ideal %.0f)  %s\n", SS ? "SS" : "TS", N, NACC, grid,
+  printf("%s %s N=%3d accumulators=%d grid=%3d: issue %.1f clk/MMA, issue+complete %.1f clk/MMA (ideal %.0f)  %s\n", mode ? "elect" : "lane0", SS ? "SS" : "TS", N, NACC, grid,
          (double)h[0] / reps, (double)h[1] / reps, 128.0 * N / 256, cudaGetErrorString(cudaGetLastError()));
 }
 int main() {
@@ -64,6 +76,7 @@ int main() {
     run<128, 1, false>(d, grid); run<128, 2, false>(d, grid);
     run<256, 1, false>(d, grid);
     run<32, 1, true>(d, grid); run<64, 1, true>(d, grid); run<128, 1, true>(d, grid); run<256, 1, true>(d, grid);
+    run<32, 1, false>(d, grid, 1); run<64, 1, false>(d, grid, 1); run<64, 2, false>(d, grid, 1); run<128, 1, false>(d, grid, 1);
   }
   return 0;
 }

@@ -37,11 +37,12 @@ if int(os.environ.get("LMPCR_PCN_DEBUG", "0")):
     cabi.load().lmpcr_debug_pcn_profile(buf, 1)
     cabi.pointcn_stack(bufs[0][0], layers, out=bufs[0][1])
     cabi.load().lmpcr_debug_pcn_profile(buf, 1)
-    names = {0: "loadA wait XREAD", 1: "loadA issue", 2: "loadB wait OUTRDY", 3: "loadB store+wait_read", 4: "loadB issue", 5: "mma wait H1FULL", 6: "mma wait YEMPTY",
-             7: "mma issue1(A) / after-issue1(B)", 8: "mma wait H2FULL", 9: "mma wait ZEMPTY", 10: "mma issue2", 11: "statsA wait YFULL", 12: "statsA work",
-             13: "cvtB wait YFULL", 14: "cvtB ld+f2", 15: "cvtB wait H2EMPTY", 16: "cvtB split+store+fence", 17: "epiB wait ZFULL", 19: "epiB work",
-             20: "prodA wait XFULL", 21: "prodA ld+f1", 22: "prodA wait H1EMPTY", 23: "prodA split+store+fence", 24: "prodB wait XFULL", 25: "prodB ld+f1",
-             26: "prodB wait H1EMPTY", 27: "prodB split+store+fence", 28: "loader: pass A tail", 29: "loader: pass B tail"}
-    tiles = ((a.points + 31) // 32) * a.layers * ((a.pairs + 147) // 148)
+    names = {0: "A load: issue", 1: "A load: wait XREAD", 2: "A mma: issue", 3: "A mma: wait H1FULL", 4: "A mma: wait YEMPTY", 5: "A stats: work",
+             6: "A stats: wait YFULL", 7: "A prod(w10): produce+fence", 8: "A prod: wait XFULL", 9: "A prod: wait H1EMPTY", 10: "A loader tail (drain)",
+             16: "B load: issue", 17: "B load: wait OUTRDY", 18: "B load: store+wait_read", 19: "B mma: issue GEMM2", 20: "B mma: wait H1FULL",
+             21: "B mma: wait YEMPTY", 22: "B mma: issue GEMM1", 23: "B mma: wait H2FULL", 24: "B mma: wait ZEMPTY", 25: "B cvt: work", 26: "B cvt: wait YFULL",
+             27: "B cvt: wait H2EMPTY", 28: "B epi(w7): work", 29: "B epi: wait ZFULL", 30: "B prod: produce+fence", 31: "B prod: wait XFULL",
+             32: "B prod: wait H1EMPTY", 33: "B loader tail (drain)"}
+    tiles = ((a.points + 63) // 64) * a.layers * ((a.pairs + 147) // 148)
     for i in sorted(names):
-        print("%-34s %9.1f cycles per tile" % (names[i], buf[i] / tiles))
+        print("%-34s %9.1f cycles per 64-point tile" % (names[i], buf[i] / tiles))
