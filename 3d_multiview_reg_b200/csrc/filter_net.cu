@@ -1217,17 +1217,21 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         cur_in = o; cur_out = W.T0;
       }
       int i_first = 1;
-      if (use_pcn && half >= 3) {
-        // the middle layers (all but the last, which carries the fused output head) in place on the buffer l1_2.0 has just written
+      if (use_pcn && half >= 2) {
+        // all layers after the first in ONE launch, in place on the buffer l1_2.0 has just written; the last one carries the network's
+        // output conv + weights in its epilogue and stores its tile only when the caller wants the latent features
         LMPCR_TRY(norm_affine(cur_in, CN, C, N, g, 1e-5f, blk.l1_2[1].bn1));
         PcnArgs pa{};
-        for (int i = 1; i < half - 1; ++i) pa.layer[i - 1] = pcn_layer(blk.l1_2[i]);
-        pa.n_layers = half - 2; pa.scale0 = W.scale; pa.shift0 = W.shift; pa.P = g; pa.N = N; pa.store_out = 1;
-        const int oi = part_index(cur_in);
-        pa.stats_out = oi >= 0 ? part_buf[oi] : nullptr;
-        LMPCR_TRY(launch_pcn_stack(cur_in, CN, cur_in, CN, pa, st));
-        if (oi >= 0) { part_valid[oi] = true; part_whole[oi] = true; }
-        i_first = half - 1;
+        for (int i = 1; i < half; ++i) pa.layer[i - 1] = pcn_layer(blk.l1_2[i]);
+        pa.n_layers = half - 1; pa.scale0 = W.scale; pa.shift0 = W.shift; pa.P = g; pa.N = N;
+        pa.lg_w = blk.output.w; pa.lg_b = blk.output.b; pa.lg_logits = logits_it + (size_t)p0 * N; pa.lg_scores = scores_it + (size_t)p0 * N;
+        pa.lg_anypos = anypos + p0;
+        pa.store_out = lat_dst != nullptr;
+        float* dst = lat_dst ? lat_dst : cur_in;      // first layer cur_in -> dst, the others in place on dst
+        LMPCR_TRY(launch_pcn_stack(cur_in, CN, dst, CN, pa, st));
+        { const int oi = part_index(cur_in); if (oi >= 0) { part_valid[oi] = false; part_whole[oi] = false; } }
+        head.done = true;
+        i_first = half;
       }
       for (int i = i_first; i < half; ++i) {
         float* o = (i == half - 1 && lat_dst) ? lat_dst : cur_out;

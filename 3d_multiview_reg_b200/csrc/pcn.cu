@@ -14,12 +14,12 @@
 // and writes its 128-byte row conflict-free) -- no per-element address arithmetic, no register-staged global loads.
 // Products are split-bf16 (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, fp32 accumulation in TMEM) exactly as in tcgemm.cu.
 //
-// Warp roles (576 threads, one CTA per SM):
+// Warp roles (704 threads, one CTA per SM):
 //   warp 0       TMA: x tile loads (+ L2 prefetch a few tiles ahead), output tile stores
 //   warp 1       tcgen05.mma issue (M128 x N64 x K16, 24 per GEMM tile of 64 points)
 //   warps 2-5    TMEM readers A: pass A statistics of y; pass B f2 + hi/lo split -> h2
-//   warps 6-9    TMEM readers B: pass B epilogue (z + b2 + x, statistics, tile written back over the x tile)
-//   warps 10-17  producers: x tile (smem, fp32) -> f1 -> hi/lo split -> h1 (warps 10-13 the first box of a tile, 14-17 the second)
+//   warps 6-13   TMEM readers B: pass B epilogue (z + b2 + x, statistics, tile written back over the x tile); 6-9 first box, 10-13 second
+//   warps 14-21  producers: x tile (smem, fp32) -> f1 -> hi/lo split -> h1 (warps 14-17 the first box of a tile, 18-21 the second)
 // Thread t of every 4-warp role owns channel ((warp & 3) << 5) | lane = the TMEM lane its warp may read.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -52,7 +52,7 @@ constexpr int N_BARS = 3 * NX + 16;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr size_t SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
-constexpr int NTHREADS = 18 * 32;
+constexpr int NTHREADS = 22 * 32;
 // Tensor memory (512 columns): both weight matrices of the layer as bf16 hi | lo, row = TMEM lane, two elements per 32-bit column
 // (the A operand of tcgen05.mma read from TMEM: per MMA only the activation operand crosses shared memory -- with the weights in
 // shared memory the tensor core's operand reads took 52 % of the shared-memory bandwidth), then the accumulators y[2] | z[2]
@@ -164,18 +164,34 @@ __device__ __forceinline__ void fold_affine(float mean, float var, float eps_in,
   sh = (-mean * rstd - __ldg(bn.rm + c)) * gsc + __ldg(bn.b + c);
 }
 
+// Barrier waits of this kernel.  -DPCN_WAIT_HINT_NS=<ns> selects mbarrier.try_wait with a suspend-time hint (the warp sleeps instead of
+// spinning through issue slots); default: hint-free try_wait in a loop.
+#ifdef PCN_WAIT_HINT_NS
+__device__ __forceinline__ void pcn_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity), "r"(PCN_WAIT_HINT_NS) : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
+#else
+__device__ __forceinline__ void pcn_wait(uint32_t bar, uint32_t parity) { mbar_wait_fast(bar, parity); }
+#endif
+
 // cycle counters for timing experiments (LMPCR_PCN_DEBUG=1): lane 0 of the first warp of every role in CTA 0 accumulates the time
 // between consecutive PROF() marks into the slot named at the later mark (lmpcr_debug_pcn_profile reads them)
 __device__ unsigned long long g_pcn_prof[40];
 #define PROF(slot)                                                                      \
   do {                                                                                  \
-    if (prof_me) {                                                                      \
+    if (PROFILE && prof_me) {                                                                      \
       const long long _t = clock64();                                                   \
       atomicAdd(&g_pcn_prof[slot], (unsigned long long)(_t - tp));                      \
       tp = _t;                                                                          \
     }                                                                                   \
   } while (0)
 
+template <bool PROFILE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const PcnArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -200,7 +216,7 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   const int ch = ((warp & 3) << 5) | lane;                 // channel row / TMEM lane owned by this thread in the 4-warp roles
   const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
   const int n_tiles = (g.N + TP - 1) / TP;
-  const bool prof_me = g.debug && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6 || warp == 10);
+  const bool prof_me = PROFILE && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6 || warp == 14);
   long long tp = clock64();
   const uint32_t sX = smem_u32(smem + OFF_X), sH1 = smem_u32(smem + OFF_H1), sH2 = smem_u32(smem + OFF_H2);
 
@@ -215,10 +231,10 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   // arithmetic of every role is local to a pass: use k of a ring slot / of a single barrier completes phase k
   auto pass_begin = [&]() {
     if (threadIdx.x == 0) {
-      for (int s = 0; s < NX; ++s) { mbar_init(XFULL(s), 1); mbar_init(XREAD(s), 8); mbar_init(OUTRDY(s), 4); }
+      for (int s = 0; s < NX; ++s) { mbar_init(XFULL(s), 1); mbar_init(XREAD(s), 8); mbar_init(OUTRDY(s), 8); }
       for (int a = 0; a < 2; ++a) {
         mbar_init(H1FULL(a), 8); mbar_init(H1EMPTY(a), 1); mbar_init(H2FULL(a), 4); mbar_init(H2EMPTY(a), 1);
-        mbar_init(YFULL(a), 1); mbar_init(YEMPTY(a), 128); mbar_init(ZFULL(a), 1); mbar_init(ZEMPTY(a), 128);
+        mbar_init(YFULL(a), 1); mbar_init(YEMPTY(a), 128); mbar_init(ZFULL(a), 1); mbar_init(ZEMPTY(a), 256);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -293,7 +309,7 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     for (int l = 0; l < g.n_layers; ++l) {
       const PcnLayer& L = g.layer[l];
       const CUtensorMap* tm_src = (l == 0) ? &tm_in : &tm_out;
-      if (warp >= 10) {
+      if (warp >= 14) {
         if (l == 0) { sc1 = __ldg(g.scale0 + (size_t)p * C + ch); sh1 = __ldg(g.shift0 + (size_t)p * C + ch); }
         else { sc1 = sc1_s[ch]; sh1 = sh1_s[ch]; }
       }
@@ -311,7 +327,7 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           for (int t = 0; t < n_tiles; ++t) {              // NX tiles (128 KB) in flight: no L2 prefetch needed in this pass
             const int s = t % NX;
             PROF(0);
-            if (t >= NX) mbar_wait_fast(XREAD(s), ((t / NX) - 1) & 1);
+            if (t >= NX) pcn_wait(XREAD(s), ((t / NX) - 1) & 1);
             PROF(1);
             load_tile(tm_src, t, s, p);
           }
@@ -321,9 +337,9 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         for (int t = 0; t < n_tiles; ++t) {
           const int a = t & 1, ph = (t >> 1) & 1;
           PROF(2);
-          mbar_wait_fast(H1FULL(a), ph);
+          pcn_wait(H1FULL(a), ph);
           PROF(3);
-          mbar_wait_fast(YEMPTY(a), ph ^ 1);
+          pcn_wait(YEMPTY(a), ph ^ 1);
           PROF(4);
           tc_fence_after();
           const uint32_t leader = elect_one();
@@ -334,14 +350,14 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         }
         for (int b = 0; b < 2; ++b) {                    // every commit of this pass has arrived before the barriers are re-initialised
           const int uses = (n_tiles + 1 - b) >> 1;
-          if (uses > 0) mbar_wait_fast(H1EMPTY(b), (uses - 1) & 1);
+          if (uses > 0) pcn_wait(H1EMPTY(b), (uses - 1) & 1);
         }
       } else if (warp < 6) {
         rs.reset();                          // statistics of the raw accumulator: the bias only shifts the mean
         for (int t = 0; t < n_tiles; ++t) {
           const int a = t & 1;
           PROF(5);
-          mbar_wait_fast(YFULL(a), (t >> 1) & 1);
+          pcn_wait(YFULL(a), (t >> 1) & 1);
           PROF(6);
           tc_fence_after();
 #pragma unroll
@@ -357,14 +373,14 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         rs.finish(g.N, mean, var);
         fold_affine(mean + b1, var, 1e-5f, L.bn2, ch, sc2, sh2);
         sh2 = fmaf(b1, sc2, sh2);            // f2(acc + b1) = relu(acc * sc2 + (b1 * sc2 + sh2))
-      } else if (warp >= 10) {
-        const int sub = (warp >= 14) ? 1 : 0;
+      } else if (warp >= 14) {
+        const int sub = (warp >= 18) ? 1 : 0;
         for (int t = 0; t < n_tiles; ++t) {
           const int s = t % NX;
           PROF(7);
-          mbar_wait_fast(XFULL(s), (t / NX) & 1);
+          pcn_wait(XFULL(s), (t / NX) & 1);
           PROF(8);
-          mbar_wait_fast(H1EMPTY(t & 1), ((t >> 1) & 1) ^ 1);
+          pcn_wait(H1EMPTY(t & 1), ((t >> 1) & 1) ^ 1);
           PROF(9);
           produce(t, s, sub, sc1, sh1);
           fence_proxy_async();
@@ -379,7 +395,9 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
       pass_begin();
       if (warp == 0) {
         if (lane == 0) {
+          const bool do_store = g.store_out || l + 1 < g.n_layers;      // with the fused head the last layer's tiles may stay on chip
           auto store_tile = [&](int u, int s) {
+            if (!do_store) return;
             for (int b = 0; b < n_boxes(u); ++b) tma_store_3d(tm_dst, sX + s * X_BYTES + b * XS_BYTES, u * TP + b * TS, 0, p);
             bulk_commit();
           };
@@ -389,7 +407,7 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
             PROF(16);
             if (t >= NX) {
               const int u = t - NX;
-              mbar_wait_fast(OUTRDY(s), (u / NX) & 1);
+              pcn_wait(OUTRDY(s), (u / NX) & 1);
               PROF(17);
               store_tile(u, s);
               bulk_wait_read0();
@@ -400,7 +418,7 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           }
           for (int u = (n_tiles > NX ? n_tiles - NX : 0); u < n_tiles; ++u) {
             const int s = u % NX;
-            mbar_wait_fast(OUTRDY(s), (u / NX) & 1);
+            pcn_wait(OUTRDY(s), (u / NX) & 1);
             store_tile(u, s);
           }
           bulk_wait0();                                   // the pair's new activations are in global memory before the next pass reads them
@@ -410,9 +428,9 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           if (t < n_tiles) {
             const int a = t & 1, ph = (t >> 1) & 1;
             PROF(19);
-            mbar_wait_fast(H1FULL(a), ph);
+            pcn_wait(H1FULL(a), ph);
             PROF(20);
-            mbar_wait_fast(YEMPTY(a), ph ^ 1);
+            pcn_wait(YEMPTY(a), ph ^ 1);
             PROF(21);
             tc_fence_after();
             const uint32_t leader = elect_one();
@@ -424,9 +442,9 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           if (t >= 1) {
             const int u = t - 1, a = u & 1, ph = (u >> 1) & 1;
             PROF(22);
-            mbar_wait_fast(H2FULL(0), u & 1);
+            pcn_wait(H2FULL(0), u & 1);
             PROF(23);
-            mbar_wait_fast(ZEMPTY(a), ph ^ 1);
+            pcn_wait(ZEMPTY(a), ph ^ 1);
             PROF(24);
             tc_fence_after();
             const uint32_t leader = elect_one();
@@ -438,17 +456,17 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         }
         for (int b = 0; b < 2; ++b) {
           const int uses = (n_tiles + 1 - b) >> 1;
-          if (uses > 0) mbar_wait_fast(H1EMPTY(b), (uses - 1) & 1);
+          if (uses > 0) pcn_wait(H1EMPTY(b), (uses - 1) & 1);
         }
-        mbar_wait_fast(H2EMPTY(0), (n_tiles - 1) & 1);
+        pcn_wait(H2EMPTY(0), (n_tiles - 1) & 1);
       } else if (warp < 6) {
         for (int t = 0; t < n_tiles; ++t) {
           const int a = t & 1;
           PROF(25);
-          mbar_wait_fast(YFULL(a), (t >> 1) & 1);
+          pcn_wait(YFULL(a), (t >> 1) & 1);
           PROF(26);
           tc_fence_after();
-          mbar_wait_fast(H2EMPTY(0), (t & 1) ^ 1);
+          pcn_wait(H2EMPTY(0), (t & 1) ^ 1);
           PROF(27);
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub) {
@@ -463,53 +481,94 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(H2FULL(0));
         }
-      } else if (warp < 10) {
+      } else if (warp < 14) {
+        const int sub = (warp >= 10) ? 1 : 0;           // warps 6-9: first box of every tile, warps 10-13: second box
+        const bool head = g.lg_w != nullptr && l + 1 == g.n_layers;
         rs.reset();
+        int n_seen = 0;
         const float b2 = __ldg(L.b2 + ch);
         for (int t = 0; t < n_tiles; ++t) {
           const int a = t & 1, s = t % NX;
           PROF(28);
-          mbar_wait_fast(ZFULL(a), (t >> 1) & 1);
+          pcn_wait(ZFULL(a), (t >> 1) & 1);
           PROF(29);
           tc_fence_after();
-          mbar_wait_fast(XFULL(s), (t / NX) & 1);              // completed long ago (the producers consumed the tile): orders our reads after the TMA write
+          float v[TS];
+          tc_ld32(tmZ + lane_sel + a * TP + sub * TS, v);
+          tc_fence_before();
+          mbar_arrive(ZEMPTY(a));
+          pcn_wait(XFULL(s), (t / NX) & 1);              // completed long ago (the producers consumed the tile): orders our reads after the TMA write
+          const int ncv = g.N - t * TP - sub * TS;
+          if (ncv > 0) {
+            uint8_t* xt = smem + OFF_X + s * X_BYTES + sub * XS_BYTES;
+            float x[TS];
+            load_x_row(xt, ch, x);
 #pragma unroll
-          for (int sub = 0; sub < NSUB; ++sub) {
-            float v[TS];
-            tc_ld32(tmZ + lane_sel + a * TP + sub * TS, v);
-            if (sub == NSUB - 1) { tc_fence_before(); mbar_arrive(ZEMPTY(a)); }
-            const int ncv = g.N - t * TP - sub * TS;
+            for (int i = 0; i < TS; ++i) v[i] = (v[i] + b2) + x[i];
+            rs.add_tile(v, ncv);
+            n_seen += ncv < TS ? ncv : TS;
+            store_x_row(xt, ch, v);
+          }
+          if (head) {
+            // fused 1-channel head (oanet.py:173-175) on the finished tile: logit[n] = sum_c w[c] z[c,n] + b.  Every epilogue warp takes
+            // its box and a quarter of the channels (lane = point: conflict-free column reads of the swizzled tile), the four partial
+            // sums meet in shared memory (the sc1 / sh1 area, unused in the last layer), fixed order => deterministic
+            asm volatile("bar.sync 1, 256;" ::: "memory");              // the whole tile is written
+            const uint8_t* xt = smem + OFF_X + s * X_BYTES + sub * XS_BYTES;
+            const int q = warp & 3;
+            float acc = 0.f;
             if (ncv > 0) {
-              uint8_t* xt = smem + OFF_X + s * X_BYTES + sub * XS_BYTES;
-              float x[TS];
-              load_x_row(xt, ch, x);
-#pragma unroll
-              for (int i = 0; i < TS; ++i) v[i] = (v[i] + b2) + x[i];
-              rs.add_tile(v, ncv);
-              store_x_row(xt, ch, v);
+#pragma unroll 8
+              for (int r = 32 * q; r < 32 * q + 32; ++r)
+                acc = fmaf(__ldg(g.lg_w + r), *reinterpret_cast<const float*>(xt + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2))), acc);
+            }
+            sc1_s[q * TP + sub * TS + lane] = acc;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (q == 0 && lane < ncv) {
+              const int o = sub * TS + lane;
+              const float lg = ((sc1_s[o] + sc1_s[TP + o]) + (sc1_s[2 * TP + o] + sc1_s[3 * TP + o])) + __ldg(g.lg_b);
+              const float sc = fmaxf(tanhf(lg), 0.f);
+              const size_t go = (size_t)p * g.N + (size_t)t * TP + o;
+              g.lg_logits[go] = lg;
+              g.lg_scores[go] = sc;
+              if (sc > 0.f) g.lg_anypos[p] = 1;
             }
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(OUTRDY(s));
         }
-        float mean, var;
-        rs.finish(g.N, mean, var);
-        if (l + 1 < g.n_layers) {
-          float sc, sh;
-          fold_affine(mean, var, 1e-5f, g.layer[l + 1].bn1, ch, sc, sh);
-          sc1_s[ch] = sc; sh1_s[ch] = sh;
-        } else if (g.stats_out) {
-          *reinterpret_cast<float2*>(g.stats_out + ((size_t)p * C + ch) * 2) = make_float2(mean, var * (float)g.N);
+        // the two boxes' statistics of every channel are merged (Chan) by the first group; scratch = the h2 tile, free by now
+        float mean_p = 0.f, m2_p = 0.f;
+        if (n_seen > 0) {
+          const float inv = 1.0f / (float)n_seen, m = rs.s1 * inv;
+          mean_p = rs.c0 + m;
+          m2_p = fmaxf(rs.s2 - rs.s1 * m, 0.f);
+        }
+        float* mg = reinterpret_cast<float*>(smem + OFF_H2);
+        if (sub == 1) { mg[ch] = mean_p; mg[C + ch] = m2_p; mg[2 * C + ch] = (float)n_seen; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (sub == 0) {
+          const float mb = mg[ch], m2b = mg[C + ch], nb = mg[2 * C + ch], na = (float)n_seen, n = na + nb;
+          const float delta = mb - mean_p;
+          const float mean = mean_p + delta * (nb / n);
+          const float var = fmaxf((m2_p + m2b + delta * delta * (na * nb / n)) / n, 0.f);
+          if (l + 1 < g.n_layers) {
+            float sc, sh;
+            fold_affine(mean, var, 1e-5f, g.layer[l + 1].bn1, ch, sc, sh);
+            sc1_s[ch] = sc; sh1_s[ch] = sh;
+          } else if (g.stats_out) {
+            *reinterpret_cast<float2*>(g.stats_out + ((size_t)p * C + ch) * 2) = make_float2(mean, var * (float)g.N);
+          }
         }
       } else {
-        const int sub = (warp >= 14) ? 1 : 0;
+        const int sub = (warp >= 18) ? 1 : 0;
         for (int t = 0; t < n_tiles; ++t) {
           const int s = t % NX;
           PROF(30);
-          mbar_wait_fast(XFULL(s), (t / NX) & 1);
+          pcn_wait(XFULL(s), (t / NX) & 1);
           PROF(31);
-          mbar_wait_fast(H1EMPTY(t & 1), ((t >> 1) & 1) ^ 1);
+          pcn_wait(H1EMPTY(t & 1), ((t >> 1) & 1) ^ 1);
           PROF(32);
           produce(t, s, sub, sc1, sh1);
           fence_proxy_async();
@@ -603,7 +662,8 @@ int launch_pcn_stack(const float* x_in, long long in_batch, float* x_out, long l
                 "pcn_stack: bad arguments");
   LMPCR_REQUIRE(pcn_supported(C, a.N, x_in, in_batch, x_out, out_batch), LMPCR_ERR_UNSUPPORTED,
                 "pcn_stack: needs 128 channels, N %% 4 == 0, 16-byte aligned activations and a driver with tensor maps");
-  LMPCR_REQUIRE(!a.lg_w, LMPCR_ERR_UNSUPPORTED, "pcn_stack: fused head not built");
+  LMPCR_REQUIRE(!a.lg_w || (a.lg_b && a.lg_logits && a.lg_scores && a.lg_anypos), LMPCR_ERR_ARG, "pcn_stack: the fused head needs bias, logits, scores and the any-positive flags");
+  LMPCR_REQUIRE(a.lg_w || a.store_out, LMPCR_ERR_ARG, "pcn_stack: no output");
   for (int l = 0; l < a.n_layers; ++l) {
     const PcnLayer& L = a.layer[l];
     LMPCR_REQUIRE(L.w1 && L.w2 && L.b1 && L.b2 && L.bn2.g && L.bn2.b && L.bn2.rm && L.bn2.rv && (l == 0 || (L.bn1.g && L.bn1.b && L.bn1.rm && L.bn1.rv)) &&
@@ -616,7 +676,8 @@ int launch_pcn_stack(const float* x_in, long long in_batch, float* x_out, long l
     static unsigned char attr_set[64];
     const int dev = device_ordinal();
     if (!attr_set[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(pcn_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      cudaError_t e = cudaFuncSetAttribute(pcn_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(pcn_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
       LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "pcn_stack: cannot reserve %zu bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
       attr_set[dev] = 1;
     }
@@ -624,7 +685,8 @@ int launch_pcn_stack(const float* x_in, long long in_batch, float* x_out, long l
   const int grid = a.P < sm_count() ? a.P : sm_count();
   PcnArgs b = a;
   b.debug = getenv("LMPCR_PCN_DEBUG") ? atoi(getenv("LMPCR_PCN_DEBUG")) : 0;      // timing experiments only
-  pcn_stack_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_out, b);
+  if (b.debug) pcn_stack_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_out, b);
+  else pcn_stack_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_out, b);
   return check_launch("pcn_stack_kernel");
 }
 

@@ -63,7 +63,7 @@ def test_network_takes_the_stack_kernel_and_agrees_with_the_layer_path():
     x = cu(xs)
     n0 = cabi.launch_count_named("pcn_stack_kernel")
     out = net({"xs": x})
-    assert cabi.launch_count_named("pcn_stack_kernel") - n0 == 4          # 2 blocks x (l1_1 stack + l1_2 middle layer)
+    assert cabi.launch_count_named("pcn_stack_kernel") - n0 == 4          # 2 blocks x (l1_1 stack + l1_2 tail with the fused head)
     os.environ["LMPCR_PCN"] = "0"
     try:
         n1 = cabi.launch_count_named("pcn_stack_kernel")
