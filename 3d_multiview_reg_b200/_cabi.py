@@ -20,7 +20,7 @@ GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
 EXPORTS = [
-    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_launch_count_named", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_debug_pcn_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_launch_count_named", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_debug_pcn_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_softmax_unpool", "lmpcr_softmax_unpool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
     "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
     "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
     "lmpcr_filter_pack_bytes", "lmpcr_filter_pack_weights", "lmpcr_filter_forward_packed",
@@ -65,6 +65,9 @@ def load():
     lib.lmpcr_softmax_pool_workspace_bytes.restype = _sz
     lib.lmpcr_softmax_pool_workspace_bytes.argtypes = [_i, _i, _i, _i]
     lib.lmpcr_softmax_pool.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]
+    lib.lmpcr_softmax_unpool_workspace_bytes.restype = _sz
+    lib.lmpcr_softmax_unpool_workspace_bytes.argtypes = [_i, _i, _i, _i]
+    lib.lmpcr_softmax_unpool.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]
     lib.lmpcr_nn_soft.argtypes = [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _sz, _vp]
     lib.lmpcr_launch_count.restype = ctypes.c_longlong
     lib.lmpcr_launch_count_named.restype = ctypes.c_longlong
@@ -455,6 +458,19 @@ def softmax_pool(x, embed, mode=1):
         out = torch.empty((P, C, K), dtype=torch.float32, device=x.device)
         ws = _ws(lib.lmpcr_softmax_pool_workspace_bytes(P, C, K, N), x.device)
         _check(lib.lmpcr_softmax_pool(_p(x), _p(e), P, C, K, N, int(mode), _p(out), _p(ws), ws.numel(), _stream(x)))
+    return out
+
+
+def softmax_unpool(x_down, embed, mode=1):
+    """diff_unpool's weighted sum (oanet.py:126-128): x_down [P,C,K], embed [P,K,N] -> [P,C,N]; softmax over the cluster axis."""
+    lib = load()
+    x, e = _dev(x_down, name="x_down"), _dev(embed, name="embed")
+    P, C, K = x.shape
+    N = e.shape[2]
+    with torch.cuda.device(x.device):
+        out = torch.empty((P, C, N), dtype=torch.float32, device=x.device)
+        ws = _ws(lib.lmpcr_softmax_unpool_workspace_bytes(P, C, K, N), x.device)
+        _check(lib.lmpcr_softmax_unpool(_p(x), _p(e), P, C, K, N, int(mode), _p(out), _p(ws), ws.numel(), _stream(x)))
     return out
 
 

@@ -154,6 +154,15 @@ int lmpcr_softmax_pool(const float* x, const float* embed, int n_pairs, int chan
   return launch_softmax_pool(x, embed, n_pairs, channels, clusters, n_pts, mode, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t lmpcr_softmax_unpool_workspace_bytes(int n_pairs, int channels, int clusters, int n_pts) {
+  return softmax_unpool_workspace_bytes(n_pairs, channels, clusters, n_pts);
+}
+int lmpcr_softmax_unpool(const float* x_down, const float* embed, int n_pairs, int channels, int clusters, int n_pts, int mode, float* out,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_softmax_unpool(x_down, embed, n_pairs, channels, clusters, n_pts, mode, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 size_t lmpcr_overlap_workspace_bytes(int n_points) { return overlap_workspace_bytes(n_points); }
 
 int lmpcr_overlap_count(const double* query, int n_query, const double* target, int n_target, const double* T, double radius, int32_t* count_out,

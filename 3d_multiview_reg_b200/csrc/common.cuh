@@ -77,6 +77,8 @@ int launch_mutual_xs(const float* xyz, int n_pts, const int32_t* pairs, int n_pa
 int launch_knn3d(const float* pos1, int n, const float* pos2, int m, int batch, int32_t* idx, float* sq, cudaStream_t st);
 size_t softmax_pool_workspace_bytes(int P, int C, int K, int N);
 int launch_softmax_pool(const float* x, const float* E, int P, int C, int K, int N, int mode, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t softmax_unpool_workspace_bytes(int P, int C, int K, int N);
+int launch_softmax_unpool(const float* x_down, const float* E, int P, int C, int K, int N, int mode, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 // overlap.cu
 size_t overlap_workspace_bytes(int n);
 int launch_overlap_count(const double* q, int n_q, const double* b, int n_b, const double* T, double radius, int32_t* count_out, int32_t* flag_out,

@@ -785,6 +785,39 @@ int launch_pointcn_stack(const float* x, int P, int N, const float* const* param
   return launch_pcn_stack(x, CN, out, CN, pa, st);
 }
 
+// diff_unpool's weighted sum alone (oanet.py:126-128): out[p,c,n] = sum_k x_down[p,c,k] * softmax_k(E[p,:,n])[k]; tensor-core path.
+// mode 0: softmax max / sum by a separate pass, normalised weights as the B operand; mode 1: deferred normalisation.
+size_t softmax_unpool_workspace_bytes(int P, int C, int K, int N) {
+  return align_up((size_t)P * tc_weight_blob_bytes(C, K), 256) + 2 * align_up((size_t)P * N * 4, 256) + 256;
+}
+
+int launch_softmax_unpool(const float* x_down, const float* E, int P, int C, int K, int N, int mode, float* out, void* ws, size_t ws_bytes,
+                          cudaStream_t st) {
+  LMPCR_REQUIRE(x_down && E && out && P >= 0 && C > 0 && K > 0 && N > 0, LMPCR_ERR_ARG, "lmpcr_softmax_unpool: bad arguments");
+  LMPCR_REQUIRE(mode == 0 || (mode == 1 && K >= TC_DEFER_MIN_K && (N & 3) == 0), LMPCR_ERR_ARG, "lmpcr_softmax_unpool: mode 1 needs clusters >= %d and n_pts %% 4 == 0", TC_DEFER_MIN_K);
+  LMPCR_REQUIRE(ws && ws_bytes >= softmax_unpool_workspace_bytes(P, C, K, N) && ((uintptr_t)ws & 255) == 0, LMPCR_ERR_WORKSPACE, "lmpcr_softmax_unpool: workspace");
+  if (P == 0) return LMPCR_OK;
+  char* w = reinterpret_cast<char*>(ws);
+  uint8_t* blob = reinterpret_cast<uint8_t*>(w); w += align_up((size_t)P * tc_weight_blob_bytes(C, K), 256);
+  float* cmax = reinterpret_cast<float*>(w); w += align_up((size_t)P * N * 4, 256);
+  float* cinv = reinterpret_cast<float*>(w);
+  const size_t tot = (size_t)P * N;
+  softmax_colstats_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(E, K, N, P, cmax, cinv);
+  LMPCR_TRY(check_launch("softmax_colstats_kernel"));
+  if (mode == 1) {
+    scale_inplace_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cmax, tot, 1.4426950408889634f);
+    LMPCR_TRY(check_launch("scale_inplace_kernel"));
+  }
+  LMPCR_TRY(launch_split_weights(x_down, C, K, blob, st, P, (long long)C * K, K));
+  TcGemmArgs a{};
+  a.a_blob = blob; a.a_blob_batch = (long long)tc_weight_blob_bytes(C, K);
+  a.B = E; a.b_batch = (long long)K * N; a.b_ld = N; a.b_kmajor = 0;
+  a.C = out; a.c_batch = (long long)C * N; a.c_i = N; a.c_j = 1;
+  a.prologue = mode ? TC_PRO_SOFTMAX_DEFER : TC_PRO_SOFTMAX; a.p0 = cmax; a.p1 = mode ? nullptr : cinv; a.p_batch = N;
+  a.M = C; a.N = N; a.K = K;
+  return launch_tcgemm(a, P, st);
+}
+
 int filter_num_params(const lmpcr_filter_cfg* cfg) {
   const int half = (cfg->net_depth / (cfg->iter_num + 1)) / 2;
   return block_num_params(half) * (cfg->iter_num + 1);

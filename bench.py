@@ -10,9 +10,12 @@ rank holds the scene, registers its contiguous slice of the lexicographic pair l
 scaling) and the step ends with the NCCL all-gather of the 16-float pose records.  Synthetic data
 (synthdata.synth_scene, seed 41) and seeded random weights -- there is no network for datasets.
 
---impl reference: the reference's CPU implementation of the same path.  The reference is pure Python/torch and
-cannot travel to the GPU box, so the arm runs the oracle port (oracle/: C for the NN arithmetic, numpy for the
-network and Kabsch) on the host cores, on a bounded sample of the same workload.
+--impl reference: the reference's CPU implementation of the same path on the host cores, on a bounded sample of the same
+workload: the UNMODIFIED reference code (Soft_NN('hard') x 2 -> construct_filtering_input_data -> OANet.forward)
+when oracle/make_ref.sh has copied it to the git-ignored oracle/_ref (kind "reference"), else the oracle port (kind "port").
+
+--workload dense50k: BASELINE configs[2] (50k x 50k keypoints per pair).  --scaling strong --scans 200: BASELINE configs[3]
+(19,900 pairs split over the ranks in contiguous, padded shards; total work fixed).
 """
 import argparse
 import importlib
@@ -107,27 +110,86 @@ def cpu_port_pairs(feats, xyz, sd, pairs):
     return time.perf_counter() - t0
 
 
+WORKLOAD = "configs[1]: %d scans -> %d pairs x %d keypoints x 32-d per GPU"
+
+
+def ref_dir():
+    d = os.path.join(ROOT, "oracle", "_ref")
+    return d if os.path.isdir(os.path.join(d, "lib")) else None
+
+
+class ReferencePath:
+    """The reference's own functions for the path (imported from oracle/_ref, never from the product package)."""
+
+    def __init__(self, sd):
+        import torch
+        import warnings
+        warnings.filterwarnings("ignore", category=SyntaxWarning)          # the reference's docstrings carry "\m" escapes
+        os.environ["LMPCR_REFERENCE_ROOT"] = ref_dir()
+        from oracle import refimport
+        import importlib
+        importlib.reload(refimport)
+        self.lib = refimport.import_reference()
+        self.torch = torch
+        torch.set_num_threads(os.cpu_count())
+        cfg = self.lib.utils.load_config(os.path.join(ref_dir(), "configs", "pairwise_registration", "eval", "RegBlock.yaml"))
+        cfg["misc"]["use_gpu"] = False
+        self.net = self.lib.filtering.filtering_dict["oanet"](cfg).eval()
+        self.net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            self.hard = self.lib.layers.Soft_NN(corr_type="hard", device="cpu")
+        self.threads = torch.get_num_threads()
+
+    def pairs(self, feats, xyz, pairs):
+        torch = self.torch
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a))[None]
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for a, b in pairs:
+                c_st = self.hard(t(feats[a]), t(feats[b]), t(xyz[b]))        # lib/pairwise/__init__.py:110
+                self.hard(t(feats[b]), t(feats[a]), t(xyz[a]))               # :111
+                fd = self.lib.utils.construct_filtering_input_data(t(xyz[a]), c_st, {}, False)   # :120
+                self.net(fd)                                                 # lib/filtering/oanet.py:218 (both blocks + Kabsch)
+        return time.perf_counter() - t0
+
+
+def cpu_arm(sd):
+    """(callable(feats, xyz, pairs) -> seconds, kind, threads, description)"""
+    if ref_dir():
+        try:
+            r = ReferencePath(sd)
+            return r.pairs, "reference", r.threads, "unmodified reference code from oracle/_ref (torch CPU, %d threads)" % r.threads
+        except Exception as e:                                            # the copy is broken: say so and use the port
+            sys.stderr.write("reference import failed (%s); using the oracle port\n" % e)
+    from oracle import nn_c
+    return (lambda f, x, p: cpu_port_pairs(f, x, sd, p)), "port", nn_c.threads(), "oracle port: C NN on %d threads + numpy network" % nn_c.threads()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import lmpcr_oracle as O
-    from oracle import nn_c
     S, n = args.scans, args.points
-    feats, xyz, sd = make_workload(min(S, 8), n)         # a bounded sample only touches the first scans
-    pairs = lex_pairs(min(S, 8))[: args.ref_pairs]
-    for _ in range(args.warmup):
-        cpu_port_pairs(feats, xyz, sd, pairs[:1])
-    t = [cpu_port_pairs(feats, xyz, sd, pairs) for _ in range(args.steps)]
+    feats, xyz, sd = make_workload(S, n)
+    all_pairs = lex_pairs(S)
+    fn, kind, threads, how = cpu_arm(sd)
+    t_pair = fn(feats, xyz, all_pairs[:1])                 # also the first warm-up
+    budget = 150.0                                         # seconds for the whole --steps / --warmup run
+    m = int(max(2, min(24, budget / ((args.steps + args.warmup) * max(t_pair, 1e-3)))))
+    if args.ref_pairs > 0:
+        m = args.ref_pairs
+    for w in range(args.warmup):
+        fn(feats, xyz, all_pairs[w * m % len(all_pairs):][:m])
+    t = [fn(feats, xyz, all_pairs[(k * m) % (len(all_pairs) - m):][:m]) for k in range(args.steps)]
     sec = float(np.mean(t))
-    val = len(pairs) / sec
-    cores = os.cpu_count()
-    sample = "%d pairs of the %d-scan x %d-point scene per step (oracle port: C NN on %d threads + numpy network)" % (len(pairs), S, n, nn_c.threads())
+    val = m / sec
+    sample = "%d consecutive pairs of the %d-scan x %d-point scene per step, %d steps (%s)" % (m, S, n, args.steps, how)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: %d scans -> %d pairs x %d keypoints x 32-d per GPU" % (S, S * (S - 1) // 2, n), "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD % (S, S * (S - 1) // 2, n), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -148,14 +210,29 @@ def run_ours(args):
     oanet = importlib.import_module("3d_multiview_reg_b200.lib.filtering.oanet")
 
     S, n = args.scans, args.points
-    per_rank = S * (S - 1) // 2                          # weak scaling: every rank registers this many pairs
-    # the scene grows with the number of ranks so that the global lexicographic pair list has world*per_rank pairs
-    S_glob = S
-    while S_glob * (S_glob - 1) // 2 < world * per_rank:
-        S_glob += 1
-    feats, xyz, sd = make_workload(S_glob, n)
-    all_pairs = lex_pairs(S_glob)[: world * per_rank]
-    my_pairs = all_pairs[rank * per_rank:(rank + 1) * per_rank]
+    if args.workload == "dense50k":                      # BASELINE configs[2]: a few pairs of full voxelised fragments
+        S, n = max(2, min(S, 4)) if args.scans != 60 else 3, (50000 if args.points == 5000 else args.points)
+    strong = args.scaling == "strong"
+    if strong:
+        # BASELINE configs[3]: the scene's S(S-1)/2 pairs are FIXED and split over the ranks in contiguous, equally sized shards
+        # (scene.partition_pairs: the last shard is short and padded in the all-gather)
+        S_glob = S
+        feats, xyz, sd = make_workload(S_glob, n)
+        all_pairs = lex_pairs(S_glob)
+        per_rank, ranges = scene.partition_pairs(len(all_pairs), world)
+        my_pairs = all_pairs[ranges[rank][0]:ranges[rank][1]]
+        pairs_total = len(all_pairs)
+    else:
+        per_rank = S * (S - 1) // 2                      # weak scaling: every rank registers this many pairs
+        # the scene grows with the number of ranks so that the global lexicographic pair list has world*per_rank pairs
+        S_glob = S
+        while S_glob * (S_glob - 1) // 2 < world * per_rank:
+            S_glob += 1
+        feats, xyz, sd = make_workload(S_glob, n)
+        all_pairs = lex_pairs(S_glob)[: world * per_rank]
+        my_pairs = all_pairs[rank * per_rank:(rank + 1) * per_rank]
+        pairs_total = world * per_rank
+    n_mine = len(my_pairs)
 
     net = oanet.OANet({"misc": dict(iter_num=1, net_depth=12, net_channel=128, clusters=500, normalize_weights=True, use_gpu=True,
                                     gemm_algo=args.gemm_algo), "data": {"use_mutuals": 0}}).eval()
@@ -166,14 +243,14 @@ def run_ours(args):
     f_host = torch.from_numpy(feats).pin_memory()
     x_host = torch.from_numpy(xyz).pin_memory()
     p_host = torch.from_numpy(np.ascontiguousarray(my_pairs)).pin_memory()
-    rec_host = torch.empty((world * per_rank, 16), dtype=torch.float32).pin_memory()
+    rec_host = torch.empty((pairs_total, 16), dtype=torch.float32).pin_memory()
     f_dev, x_dev, p_dev = f_host.to(dev), x_host.to(dev), p_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def step_resident():
         mine, _ = reg.register_pairs(f_dev, x_dev, p_dev)
         if world > 1:
-            return scene.all_gather_records(mine, per_rank, world * per_rank, world)
+            return scene.all_gather_records(mine, per_rank, pairs_total, world)
         return mine
 
     def step_e2e():
@@ -181,7 +258,7 @@ def run_ours(args):
         x = x_host.to(dev, non_blocking=True)
         p = p_host.to(dev, non_blocking=True)
         mine, _ = reg.register_pairs(f, x, p)
-        full = scene.all_gather_records(mine, per_rank, world * per_rank, world) if world > 1 else mine
+        full = scene.all_gather_records(mine, per_rank, pairs_total, world) if world > 1 else mine
         rec_host.copy_(full, non_blocking=True)
         return full
 
@@ -229,51 +306,95 @@ def run_ours(args):
 
     if rank == 0:
         pk = peaks()
-        pairs_total = world * per_rank
         value = pairs_total / (ms_step * 1e-3)
-        n_chunks = (per_rank + args.pair_chunk - 1) // args.pair_chunk
         nn_ms = stages["nn"]
         filt_ms = stages["filter"]
-        nn_tf = per_rank * NN_FLOP_PER_PAIR(n, 32) / (nn_ms * 1e-3) / 1e12
-        filt_tf = per_rank * FILTER_FLOP_PER_PAIR(n) / (filt_ms * 1e-3) / 1e12
-        dom = dominant_kernel_roofline(cabi, dev, n, pk)
+        nn_tf = n_mine * NN_FLOP_PER_PAIR(n, 32) / (nn_ms * 1e-3) / 1e12
+        filt_tf = n_mine * FILTER_FLOP_PER_PAIR(n) / (filt_ms * 1e-3) / 1e12
+        dom = dominant_kernel_roofline(cabi, dev, n if n <= 8192 else 5000, pk)
+        if args.workload == "dense50k":
+            workload = "configs[2]: dense keypoints, %d scans -> %d pairs x %d keypoints x 32-d" % (S, pairs_total, n)
+        elif strong:
+            workload = "configs[3]: %d scans -> %d pairs x %d keypoints x 32-d, split over %d GPU(s) (shard %d, last shard %d)" % (
+                S, pairs_total, n, world, per_rank, ranges[-1][1] - ranges[-1][0])
+        else:
+            workload = WORKLOAD % (S, per_rank, n)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: %d scans -> %d pairs x %d keypoints x 32-d per GPU (rank-0 scene of %d scans, %d pairs total)"
-                                   % (S, per_rank, n, S_glob, pairs_total),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload, "scene": "rank-0 scene of %d scans, %d pairs in total over %d rank(s)" % (S_glob, pairs_total, world),
                        "nn_algo": "tcgen05+rescore" if args.nn_algo == 1 else "exact_simt", "gemm_algo": "tcgen05 split-bf16" if args.gemm_algo == 1 else "fp32 simt",
                        "pair_chunk": args.pair_chunk, "arithmetic": "results in f32; NN screening fp16 operands -> f32 TMEM accumulators + exact f32 rescoring; GEMMs split-bf16 (hi+lo) -> f32", "l2": "256 MiB flush buffer written between timed iterations",
                        "parallelism": "pairs x%d" % world},
-            # dominant kernel = tcgemm_kernel (the fused 1x1-conv layer; ~77 % of the step in the ncu launch list under
-            # profiles/): timed alone, live, with CUDA events on a 128->128-channel layer with residual over 148 pairs.
+            # dominant kernel family = the fused 1x1-conv layers of the network: the per-layer tcgemm_kernel instance (128->128 with residual,
+            # 148 pairs) timed alone, live, with CUDA events; the pair-resident PointCN stack that replaces most of these layers is
+            # reported beside it (roofline_pcn)
             "roofline": dom,
+            "roofline_pcn": pcn_roofline(cabi, dev, n if n <= 8192 else 5000, pk),
             "roofline_filter_stage": {"bound": "tensor", "achieved": filt_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": filt_tf / pk["tf_sustained"],
                                       "algorithmic_flop_per_pair": FILTER_FLOP_PER_PAIR(n), "ms_per_step": filt_ms, "peak_source": pk["src"] + " bf16 sustained"},
             "roofline_nn": {"bound": "tensor", "achieved": nn_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": nn_tf / pk["tf_sustained"],
                             "frac_of_burst": nn_tf / pk["tf_burst"], "traffic": None, "kernel": "nn stage (both directions)",
                             "algorithmic_flop_per_pair": NN_FLOP_PER_PAIR(n, 32), "ms_per_step": nn_ms, "peak_source": pk["src"] + " bf16 sustained"},
             "stages_ms": stages,
+            "us_per_pair": {"nn": 1e3 * nn_ms / max(n_mine, 1), "filter": 1e3 * filt_ms / max(n_mine, 1), "total": 1e3 * ms_step / max(n_mine, 1)},
             "e2e": {"value": pairs_total / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(f_host.numel() * 4 + x_host.numel() * 4 + p_host.numel() * 4),
                     "d2h_bytes_per_step": int(rec_host.numel() * 4), "ms_per_step": ms_e2e},
-            "gpu_launches": None,
+            "gpu_launches": int(launches_per_step * args.steps),        # kernels of liblmpcr_b200 launched in the timed region (library counter)
             "clocks": clocks,
         }
-        # launches of OUR kernels per step (counted from the call structure: see DESIGN.md "launch count")
-        line["gpu_launches"] = int(launches_per_step * args.steps)
         if world == 1 and not args.no_cpu_baseline:
-            cf, cx, csd = feats[:8], xyz[:8], sd
-            cp = lex_pairs(8)[: args.cpu_pairs]
-            cpu_port_pairs(cf, cx, csd, cp[:1])
-            sec = cpu_port_pairs(cf, cx, csd, cp)
-            from oracle import nn_c
-            line["cpu_baseline"] = {"value": len(cp) / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "%d pairs of the same scene (oracle port: C NN on %d threads + numpy network), %.1f s"
-                                              % (len(cp), nn_c.threads(), sec)}
+            fn, kind, threads, how = cpu_arm(sd)
+            cs = min(S_glob, 8)
+            cp = lex_pairs(cs)[: args.cpu_pairs if n <= 8192 else 1]
+            if n > 8192:                                   # the CPU paths materialise N x N matrices: bounded to a 5000-point subsample there
+                cf, cx = feats[:cs, :5000], xyz[:cs, :5000]
+            else:
+                cf, cx = feats[:cs], xyz[:cs]
+            fn(cf, cx, cp[:1])
+            sec = fn(cf, cx, cp)
+            line["cpu_baseline"] = {"value": len(cp) / sec, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": "%d pairs of the first %d scans of the same scene%s (%s), %.1f s"
+                                              % (len(cp), cs, " at 5000 of the %d points" % n if n > 8192 else "", how, sec)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def pcn_roofline(cabi, dev, n, pk, P=148, C=128, layers=2, iters=6):
+    """The pair-resident PointCN stack (pcn_stack_kernel) alone: `layers` layers over P pairs per launch; algorithmic bytes per layer =
+    3 passes (statistics pass reads x, main pass reads x and writes the output) x P*C*n*4."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(7)
+    def lp():
+        bn = lambda: [torch.rand(C, generator=g) + 0.5, 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5]
+        w = lambda: torch.randn(C, C, generator=g) / C ** 0.5
+        return [t.to(dev) for t in bn() + [w(), 0.1 * torch.randn(C, generator=g)] + bn() + [w(), 0.1 * torch.randn(C, generator=g)]]
+    lps = [lp() for _ in range(layers)]
+    bufs = [(torch.randn(P, C, n, device=dev), torch.empty(P, C, n, device=dev)) for _ in range(3)]
+    for x, o in bufs:
+        cabi.pointcn_stack(x, lps, out=o)
+    torch.cuda.synchronize()
+    n0 = cabi.launch_count_named("pcn_stack_kernel")
+    evs = []
+    for i in range(iters):
+        x, o = bufs[i % 3]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cabi.pointcn_stack(x, lps, out=o)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    # the call also runs the weight packing and a two-pass statistics kernel over the input (~3 more passes): subtract nothing, say so
+    ms = float(np.mean([a.elapsed_time(b_) for a, b_ in evs]))
+    byts = 3.0 * layers * P * C * n * 4
+    del bufs
+    return {"bound": "hbm", "achieved": byts / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": byts / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "traffic": None, "kernel": "pcn_stack_kernel (%d fused PointCN layers, %d pairs x %d pts) incl. its input-statistics pre-pass" % (layers, P, n),
+            "algorithmic_bytes_per_launch": byts, "ms_per_launch": ms, "launches": cabi.launch_count_named("pcn_stack_kernel") - n0,
+            "peak_source": pk["src"] + " hbm copy"}
 
 
 def dominant_kernel_roofline(cabi, dev, n, pk, P=148, C=128, sets=3, iters=12):
@@ -316,15 +437,6 @@ def dominant_kernel_roofline(cabi, dev, n, pk, P=148, C=128, sets=3, iters=12):
             "tensor_frac_of_sustained": flops / (ms * 1e-3) / 1e12 / pk["tf_sustained"], "peak_source": pk["src"] + " hbm copy"}
 
 
-def launches_per_chunk(args, per_rank):
-    """Kernel launches of liblmpcr_b200 per pair chunk (one register_pairs iteration)."""
-    nn = 2 * (2 if args.nn_algo == 0 else 4)           # per direction: sqnorm + argmin | prep + sweep + rescore (+memset)
-    half = 3
-    per_block = 1 + 1 + half * 4 + 2 + 1 + 1 + half * 6 + 2 + 1 + 1 + (5 + (half - 1) * 4) + 1   # see filter_net.cu
-    filt = 2 * per_block + 2 * 2                        # + guard/kabsch per block
-    return nn + 1 + filt + 1
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -336,7 +448,9 @@ def main():
     ap.add_argument("--pair-chunk", type=int, default=296)
     ap.add_argument("--nn-algo", type=int, default=int(os.environ.get("LMPCR_NN_ALGO", "1")))
     ap.add_argument("--gemm-algo", type=int, default=int(os.environ.get("LMPCR_GEMM_ALGO", "1")))
-    ap.add_argument("--ref-pairs", type=int, default=12)
+    ap.add_argument("--ref-pairs", type=int, default=0, help="pairs per step of the reference arm (0: sized to a ~150 s run)")
+    ap.add_argument("--workload", default="scene", choices=["scene", "dense50k"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-pairs", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
