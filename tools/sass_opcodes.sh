@@ -9,4 +9,4 @@ cuobjdump -sass "$LIB" | awk '
   /Function :/ { fn=$3; next }
   { for (i=1;i<=NF;i++) { op=$i; sub(/\..*/,"",op);
       if (op=="UTCHMMA"||op=="LDTM"||op=="STTM"||op=="UBLKCP"||op=="UTMALDG"||op=="UTMASTG"||op=="UTMAPF"||op=="LDGSTS"||op=="FMNMX3"||op=="UTCBAR"||op=="ELECT") c[fn" "op]++ } }
-  END { for (k in c) print k, c[k] }' | sort | c++filt 2>/dev/null | awk '{ n=$NF; op=$(NF-1); $NF=""; $(NF-1)=""; name=$0; sub(/\(.*/,"",name); printf "%-12s %6d  %s\n", op, n, name }' | sort -k3,3 -k1,1
+  END { for (k in c) print k, c[k] }' | sort | c++filt 2>/dev/null | sed 's/(anonymous namespace):://g; s/lmpcr:://g; s/^void //' | awk '{ n=$NF; op=$(NF-1); $NF=""; $(NF-1)=""; name=$0; sub(/\(.*/,"",name); printf "%-44s %-8s %6d\n", name, op, n }' | sort
