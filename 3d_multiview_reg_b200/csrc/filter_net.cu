@@ -1127,9 +1127,10 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         pa.n_layers = half; pa.scale0 = W.scale; pa.shift0 = W.shift; pa.P = g; pa.N = N; pa.store_out = 1;
         const int oi = part_index(W.CAT);
         pa.stats_out = part_buf[oi];
+        pa.a_blob_out = blob_x11; pa.a_blob_out_batch = (long long)tc_weight_blob_bytes(C, N);
         LMPCR_TRY(launch_pcn_stack(W.T0, CN, W.CAT, 2 * CN, pa, st));
         part_valid[oi] = true; part_whole[oi] = true;
-        x11_blob_ready = false;
+        x11_blob_ready = true;
       } else {
         for (int i = 0; i < half; ++i) {
           const bool fin = (i == half - 1);

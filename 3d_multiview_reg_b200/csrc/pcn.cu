@@ -484,6 +484,7 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
       } else if (warp < 14) {
         const int sub = (warp >= 10) ? 1 : 0;           // warps 6-9: first box of every tile, warps 10-13: second box
         const bool head = g.lg_w != nullptr && l + 1 == g.n_layers;
+        const bool blob = g.a_blob_out != nullptr && l + 1 == g.n_layers;
         rs.reset();
         int n_seen = 0;
         const float b2 = __ldg(L.b2 + ch);
@@ -508,6 +509,28 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
             rs.add_tile(v, ncv);
             n_seen += ncv < TS ? ncv : TS;
             store_x_row(xt, ch, v);
+            if (blob) {
+              // second copy of the finished tile as the pre-split A operand of the pooling GEMM (tcgemm.cu: K = the point axis, one
+              // K chunk = this box): [hi 8 KB | lo 8 KB], 8-channel groups 512 B apart, 8-point groups 128 B apart; points past N are
+              // written as zeros so that the consumer's K padding multiplies finite values
+              uint8_t* bb = g.a_blob_out + (size_t)p * g.a_blob_out_batch + (size_t)(t * NSUB + sub) * (2 * 8192) + (ch >> 3) * 512 + (ch & 7) * 16;
+#pragma unroll
+              for (int gq = 0; gq < TS / 8; ++gq) {
+                uint32_t h[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int i0 = 8 * gq + 2 * q;
+                  const float a = (i0 < ncv) ? v[i0] : 0.f, b = (i0 + 1 < ncv) ? v[i0 + 1] : 0.f;
+                  const __nv_bfloat162 hv = __floats2bfloat162_rn(a, b);
+                  const float2 hf = __bfloat1622float2(hv);
+                  const __nv_bfloat162 lv = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+                  h[q] = *reinterpret_cast<const uint32_t*>(&hv);
+                  lo[q] = *reinterpret_cast<const uint32_t*>(&lv);
+                }
+                *reinterpret_cast<uint4*>(bb + gq * 128) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(bb + gq * 128 + 8192) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+            }
           }
           if (head) {
             // fused 1-channel head (oanet.py:173-175) on the finished tile: logit[n] = sum_c w[c] z[c,n] + b.  Every epilogue warp takes

@@ -22,6 +22,9 @@ struct PcnArgs {
   float* stats_out;                           // optional [P,128,2] = (mean, M2 over the N points) of the stack's output
   // optional fused 1-channel head on the stack's output (the network's `output` conv + weights, oanet.py:173-175)
   const float* lg_w; const float* lg_b; float* lg_logits; float* lg_scores; int32_t* lg_anypos;
+  // optional second copy of the OUTPUT as the pre-split K-major A-operand blob of tcgemm.cu (launch_split_weights(out, 128, N) layout),
+  // batch stride a_blob_out_batch bytes: the pooling GEMM that follows l1_1 reads its x1_1 operand from it
+  uint8_t* a_blob_out; long long a_blob_out_batch;
   int store_out;                              // 0: with the head present the output tiles themselves are not stored
   int P, N;
   int debug;                                  // timing experiments only (LMPCR_PCN_DEBUG); 0 in production

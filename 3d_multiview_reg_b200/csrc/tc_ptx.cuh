@@ -23,6 +23,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 #ifndef LMPCR_MBAR_HINT_NS
 #define LMPCR_MBAR_HINT_NS 20000
 #endif
+#ifndef LMPCR_MBAR_FAST
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spin = 0; !done; ++spin) {
@@ -34,6 +35,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 20)) __trap();   // a lost arrival becomes an error instead of a hung GPU (2^20 x 20 us = 21 s)
   }
 }
+#endif
 // Low-latency wait: mbarrier.try_wait WITHOUT a suspend-time hint (SASS SYNCS.PHASECHK...TRYWAIT: the hardware parks the warp for a
 // bounded time and wakes it when the phase flips).  For hand-offs on the critical path of short pipelines: the hinted form above
 // compiles to a phase check + NANOSLEEP.SYNCS 20 us, whose wake-up cost ~0.5 us per hand-off in pcn.cu (55 % of its stall samples).
@@ -48,6 +50,9 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 24)) __trap();   // a lost arrival becomes an error instead of a hung GPU
   }
 }
+#ifdef LMPCR_MBAR_FAST
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_fast(bar, parity); }
+#endif
 // kept as a separate name for the waits that are off the critical path
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
