@@ -20,11 +20,13 @@ GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
 EXPORTS = [
-    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_launch_count_named", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_debug_pcn_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_softmax_unpool", "lmpcr_softmax_unpool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_launch_count_named", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_debug_pcn_profile", "lmpcr_debug_pool_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_softmax_unpool", "lmpcr_softmax_unpool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
     "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
     "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
     "lmpcr_filter_pack_bytes", "lmpcr_filter_pack_weights", "lmpcr_filter_forward_packed",
     "lmpcr_pointcn_stack", "lmpcr_pointcn_stack_workspace_bytes",
+    "lmpcr_sample_workspace_bytes", "lmpcr_sample_keypoints",
+    "lmpcr_diff_pool_fused_workspace_bytes", "lmpcr_diff_pool_fused",
 ]
 
 
@@ -57,6 +59,9 @@ def load():
     lib.lmpcr_nn_workspace_bytes.restype = _sz
     lib.lmpcr_nn_workspace_bytes.argtypes = [_i] * 7
     lib.lmpcr_nn_argmin.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]
+    lib.lmpcr_sample_workspace_bytes.restype = _sz
+    lib.lmpcr_sample_workspace_bytes.argtypes = [_i, _i]
+    lib.lmpcr_sample_keypoints.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_uint64, _vp, _vp, _vp, _vp, _sz, _vp]
     lib.lmpcr_nn_top2.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]
     lib.lmpcr_overlap_workspace_bytes.restype = _sz
     lib.lmpcr_overlap_workspace_bytes.argtypes = [_i]
@@ -91,6 +96,9 @@ def load():
     lib.lmpcr_pointcn_stack_workspace_bytes.restype = _sz
     lib.lmpcr_pointcn_stack_workspace_bytes.argtypes = [_i, _i]
     lib.lmpcr_pointcn_stack.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _sz, _vp]
+    lib.lmpcr_diff_pool_fused_workspace_bytes.restype = _sz
+    lib.lmpcr_diff_pool_fused_workspace_bytes.argtypes = [_i, _i]
+    lib.lmpcr_diff_pool_fused.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]
     lib.lmpcr_filter_pack_bytes.restype = _sz
     lib.lmpcr_filter_pack_bytes.argtypes = [ctypes.POINTER(FilterCfg)]
     lib.lmpcr_filter_pack_weights.argtypes = [ctypes.POINTER(_vp), _i, ctypes.POINTER(FilterCfg), _vp, _sz, _vp]
@@ -199,6 +207,31 @@ def voxel_downsample(points, voxel_size):
     if flag:
         raise LmpcrError("lmpcr_voxel_downsample: extent exceeds 2^20 voxels per axis")
     return out[:n]
+
+
+def sample_keypoints(coords, feats, pts_list, n_samples, replace, seed):
+    """Device keypoint sampler (lib/layers.py:90-154, 'rand'): coords [total,3], feats [total,dim] fp32 CUDA = the concatenated
+    clouds of a batch, pts_list = points per cloud.  Returns (idx [b,m] int32 global rows, coords [b,m,3], feats [b,m,dim])."""
+    lib = load()
+    c = _dev(coords, torch.float32, "coords")
+    f = _dev(feats, torch.float32, "feats")
+    pts = [int(v) for v in pts_list]
+    b, total = len(pts), int(sum(pts))
+    if c.shape[0] != total or f.shape[0] != total:
+        raise LmpcrError("sample_keypoints: pts_list sums to %d but coords / feats have %d / %d rows" % (total, c.shape[0], f.shape[0]))
+    off = [0]
+    for v in pts:
+        off.append(off[-1] + v)
+    off_h = (ctypes.c_int32 * (b + 1))(*off)
+    with torch.cuda.device(c.device):
+        off_d = torch.tensor(off, dtype=torch.int32, device=c.device)
+        idx = torch.empty((b, n_samples), dtype=torch.int32, device=c.device)
+        co = torch.empty((b, n_samples, 3), dtype=torch.float32, device=c.device)
+        fo = torch.empty((b, n_samples, f.shape[1]), dtype=torch.float32, device=c.device)
+        ws = _ws(lib.lmpcr_sample_workspace_bytes(total, b), c.device)
+        _check(lib.lmpcr_sample_keypoints(_p(c), _p(f), _p(off_d), ctypes.cast(off_h, _vp), b, f.shape[1], int(n_samples), 1 if replace else 0,
+                                          ctypes.c_uint64(int(seed) & (2**64 - 1)), _p(idx), _p(co), _p(fo), _p(ws), ws.numel(), _stream(c)))
+    return idx, co, fo
 
 
 def nn_soft(q_feat, b_feat, b_xyz, jobs, temperature):
@@ -446,6 +479,20 @@ def pointcn_stack(x, layer_params, out=None, want_stats=False):
         ws = _ws(lib.lmpcr_pointcn_stack_workspace_bytes(P, len(layer_params)), x.device)
         _check(lib.lmpcr_pointcn_stack(_p(x), P, N, table, len(layer_params), _p(out), _p(stats), _p(ws), ws.numel(), _stream(x)))
     return (out, stats) if want_stats else out
+
+
+def diff_pool_fused(x, scale, shift, weight, mode=0):
+    """diff_pool in one launch (lmpcr_diff_pool_fused): x [P,128,N], scale / shift [P,128], weight [K,128] -> [P,128,K].
+    mode 0: single pass + fallback launch (production); 1: two passes for every item."""
+    lib = load()
+    x, sc, sh, w = _dev(x, name="x"), _dev(scale, name="scale"), _dev(shift, name="shift"), _dev(weight, name="weight")
+    P, C, N = x.shape
+    K = w.shape[0]
+    with torch.cuda.device(x.device):
+        out = torch.empty((P, C, K), dtype=torch.float32, device=x.device)
+        ws = _ws(lib.lmpcr_diff_pool_fused_workspace_bytes(P, K), x.device)
+        _check(lib.lmpcr_diff_pool_fused(_p(x), P, N, _p(sc), _p(sh), _p(w), K, int(mode), _p(out), _p(ws), ws.numel(), _stream(x)))
+    return out
 
 
 def softmax_pool(x, embed, mode=1):

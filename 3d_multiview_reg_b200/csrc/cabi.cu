@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "pool_fused.cuh"
 #include "tcgemm.cuh"
 #include "pcn.cuh"
 
@@ -138,6 +139,7 @@ int lmpcr_nn_tensor_debug(const float* q_feat, int n_q_sets, int n_q, const floa
 
 int lmpcr_debug_tc_profile(unsigned long long* out16, int reset) { return tc_profile_read(out16, reset); }
 int lmpcr_debug_pcn_profile(unsigned long long* out40, int reset) { return pcn_profile_read(out40, reset); }
+int lmpcr_debug_pool_profile(unsigned long long* out32, int reset) { return pool_fused_profile_read(out32, reset); }
 
 int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, int dim, int batch, float* out, void* workspace,
                             size_t workspace_bytes, void* stream) {
@@ -175,6 +177,16 @@ int lmpcr_voxel_downsample(const double* points, int n_points, double voxel_size
                            void* workspace, size_t workspace_bytes, void* stream) {
   LMPCR_TRY(check_device());
   return launch_voxel_downsample(points, n_points, voxel_size, out, n_out, range_flag, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t lmpcr_sample_workspace_bytes(int total_points, int n_clouds) { return sample_workspace_bytes(total_points, n_clouds); }
+
+int lmpcr_sample_keypoints(const float* coords, const float* feats, const int32_t* offsets, const int32_t* offsets_host, int n_clouds, int dim,
+                           int n_samples, int with_replacement, uint64_t seed, int32_t* idx_out, float* coords_out, float* feats_out,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_sample_keypoints(coords, feats, offsets, offsets_host, n_clouds, dim, n_samples, with_replacement, seed, idx_out, coords_out,
+                                 feats_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int lmpcr_nn_top2(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim, const int32_t* jobs,
@@ -240,6 +252,28 @@ int lmpcr_pointcn_stack(const float* x, int n_pairs, int n_pts, const float* con
                         void* workspace, size_t workspace_bytes, void* stream) {
   LMPCR_TRY(check_device());
   return launch_pointcn_stack(x, n_pairs, n_pts, params, n_layers, out, stats_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t lmpcr_diff_pool_fused_workspace_bytes(int n_pairs, int clusters) {
+  return align_up(pool_fused_weight_bytes(clusters), 256) + align_up((size_t)(n_pairs > 0 ? n_pairs : 1) * ((clusters + 127) / 128) * 4, 256) + 256;
+}
+
+int lmpcr_diff_pool_fused(const float* x, int n_pairs, int n_pts, const float* scale, const float* shift, const float* weight, int clusters,
+                          int mode, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  LMPCR_REQUIRE(x && scale && shift && weight && out && n_pairs >= 0 && n_pts > 0 && clusters > 0, LMPCR_ERR_ARG, "lmpcr_diff_pool_fused: bad arguments");
+  LMPCR_REQUIRE(workspace && workspace_bytes >= lmpcr_diff_pool_fused_workspace_bytes(n_pairs, clusters) && ((uintptr_t)workspace & 255) == 0, LMPCR_ERR_WORKSPACE,
+                "lmpcr_diff_pool_fused: workspace too small or not 256-byte aligned");
+  if (n_pairs == 0) return LMPCR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* blob = reinterpret_cast<uint8_t*>(workspace);
+  LMPCR_TRY(launch_pool_fused_pack_weights(weight, clusters, blob, st));
+  PoolFusedArgs a{};
+  a.w_blob = blob; a.scale = scale; a.shift = shift; a.out = out; a.out_batch = (long long)128 * clusters; a.out_ld = clusters;
+  a.P = n_pairs; a.N = n_pts; a.K = clusters;
+  LMPCR_REQUIRE(mode == 0 || mode == 1, LMPCR_ERR_ARG, "lmpcr_diff_pool_fused: mode must be 0 (single pass + fallback) or 1 (two passes)");
+  a.flags = mode == 0 ? reinterpret_cast<int32_t*>(blob + align_up(pool_fused_weight_bytes(clusters), 256)) : nullptr;
+  return launch_pool_fused(x, (long long)128 * n_pts, a, st);
 }
 
 int lmpcr_filter_num_params(const lmpcr_filter_cfg* cfg) {

@@ -85,6 +85,11 @@ int launch_overlap_count(const double* q, int n_q, const double* b, int n_b, con
                          void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_voxel_downsample(const double* pts, int n, double voxel, double* out, int32_t* n_out, int32_t* flag_out, void* ws, size_t ws_bytes,
                             cudaStream_t st);
+// sampler.cu
+size_t sample_workspace_bytes(int total, int n_clouds);
+int launch_sample_keypoints(const float* coords, const float* feats, const int32_t* offsets, const int32_t* offsets_host, int n_clouds, int dim, int m,
+                            int replace, uint64_t seed, int32_t* idx_out, float* coords_out, float* feats_out, void* ws, size_t ws_bytes,
+                            cudaStream_t st);
 // nn_tensor.cu (tcgen05 path)
 size_t nn_tensor_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, int dim, int n_jobs);
 int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,

@@ -16,6 +16,7 @@
 
 #include "tcgemm.cuh"
 #include "pcn.cuh"
+#include "pool_fused.cuh"
 
 namespace lmpcr {
 namespace {
@@ -635,6 +636,7 @@ size_t block_blob_bytes(int C, int K, int half) {
   b += (size_t)(half - 1) * 2 * tc_weight_blob_bytes(C, C);                       // l1_2.1..
   b += (size_t)half * (2 * tc_weight_blob_bytes(C, C) + tc_weight_blob_bytes(K, K));   // l2
   if (C == PCN_C) b += (size_t)(2 * half + 2 * (half - 1)) * pcn_weight_bytes();       // second image of the plain PointCN weights (pcn.cu)
+  if (C == PCN_C) b += pool_fused_weight_bytes(K);                                       // second image of the down embedding conv (pool_fused.cu)
   return align_up(b, 256);
 }
 
@@ -662,6 +664,9 @@ int block_blobs(BlockP& blk, int C, int K, int half, uint8_t* bp, bool do_split,
     };
     for (int i = 0; i < half; ++i) { LMPCR_TRY(prep_rm(blk.l1_1[i].c1)); LMPCR_TRY(prep_rm(blk.l1_1[i].c2)); }
     for (int i = 1; i < half; ++i) { LMPCR_TRY(prep_rm(blk.l1_2[i].c1)); LMPCR_TRY(prep_rm(blk.l1_2[i].c2)); }
+    blk.down_conv.blob_rm = bp;
+    if (do_split) LMPCR_TRY(launch_pool_fused_pack_weights(blk.down_conv.w, K, bp, st));
+    bp += pool_fused_weight_bytes(K);
   }
   return LMPCR_OK;
 }
@@ -891,6 +896,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   static const int no_defer = getenv("LMPCR_NO_DEFER") ? atoi(getenv("LMPCR_NO_DEFER")) : 0;   // debug aid: softmax statistics by separate passes
   // read per call (two getenv look-ups) so that a test can switch paths inside one process
   const int pcn_on = getenv("LMPCR_PCN") ? atoi(getenv("LMPCR_PCN")) : 1;                       // 0: PointCN layers on the per-layer GEMM path (A/B runs)
+  const int pool_on = getenv("LMPCR_POOL_FUSED") ? atoi(getenv("LMPCR_POOL_FUSED")) : 1;         // 0: diff_pool as embedding GEMM + pooling GEMM (A/B runs)
   const int pcn_min_pairs = getenv("LMPCR_PCN_MIN_PAIRS") ? atoi(getenv("LMPCR_PCN_MIN_PAIRS")) : 64;
   LMPCR_REQUIRE(n_params == filter_num_params(cfg), LMPCR_ERR_ARG, "lmpcr_filter_forward: expected %d parameter tensors, got %d", filter_num_params(cfg), n_params);
   for (int i = 0; i < n_params; ++i) LMPCR_REQUIRE(params[i], LMPCR_ERR_ARG, "lmpcr_filter_forward: params[%d] is null", i);
@@ -1112,6 +1118,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       float* cur_in = W.T0; float* cur_out = W.T1;
       // PointCN layers of plain shape (128 -> 128, no shot_cut) run as ONE pair-resident launch when the group is large enough to
       // give every SM a pair (pcn.cu): 3 HBM passes per layer instead of 5, the intermediate W1 f1(x) never leaves the SM
+      const bool use_pool_fused = pool_on && tc && !bn_train && g >= pcn_min_pairs && blk.down_conv.blob_rm && pool_fused_supported(C, K, N, W.CAT, 2 * CN);
       const bool use_pcn = pcn_on && tc && !bn_train && g >= pcn_min_pairs && half <= PCN_MAX_LAYERS && pcn_supported(C, N, W.T0, CN, W.CAT, 2 * CN);
       auto pcn_layer = [&](const PointCNP& q) {
         PcnLayer L{};
@@ -1127,15 +1134,15 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         pa.n_layers = half; pa.scale0 = W.scale; pa.shift0 = W.shift; pa.P = g; pa.N = N; pa.store_out = 1;
         const int oi = part_index(W.CAT);
         pa.stats_out = part_buf[oi];
-        pa.a_blob_out = blob_x11; pa.a_blob_out_batch = (long long)tc_weight_blob_bytes(C, N);
+        if (!use_pool_fused) { pa.a_blob_out = blob_x11; pa.a_blob_out_batch = (long long)tc_weight_blob_bytes(C, N); }   // A operand of the pooling GEMM
         LMPCR_TRY(launch_pcn_stack(W.T0, CN, W.CAT, 2 * CN, pa, st));
         part_valid[oi] = true; part_whole[oi] = true;
-        x11_blob_ready = true;
+        x11_blob_ready = !use_pool_fused;
       } else {
         for (int i = 0; i < half; ++i) {
           const bool fin = (i == half - 1);
           float* o = fin ? W.CAT : cur_out;
-          if (fin) { blob_out_for = W.CAT; x11_blob_ready = false; }
+          if (fin) { blob_out_for = use_pool_fused ? nullptr : W.CAT; x11_blob_ready = false; }
           LMPCR_TRY(pointcn(blk.l1_1[i], cur_in, CN, C, g, W.T2, nullptr, o, fin ? 2 * CN : CN));
           blob_out_for = nullptr;
           if (!fin) { float* t = cur_in; cur_in = cur_out; cur_out = t; }
@@ -1143,10 +1150,22 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       }
       const float* x11 = W.CAT; const long long x11b = 2 * CN;
       // diff_pool (oanet.py:106-110)
+      if (use_pool_fused) {
+        // embedding conv + softmax over the points + weighted sum in ONE launch: the [K, N] embedding stays on chip (pool_fused.cu)
+        LMPCR_TRY(norm_affine(x11, x11b, C, N, g, 1e-3f, blk.down_bn));
+        PoolFusedArgs pa{};
+        pa.w_blob = blk.down_conv.blob_rm; pa.scale = W.scale; pa.shift = W.shift;
+        pa.out = W.XD0; pa.out_batch = CK; pa.out_ld = K; pa.P = g; pa.N = N; pa.K = K;
+        pa.flags = reinterpret_cast<int32_t*>(sm_max);      // [g * 4] ints of a scratch row buffer that is idle until diff_unpool
+        LMPCR_TRY(launch_pool_fused(x11, x11b, pa, st));
+        part_valid[part_index(W.XD0)] = false; part_whole[part_index(W.XD0)] = false;
+      } else {
       want_sm = true;
       LMPCR_TRY(conv_norm(x11, x11b, C, N, g, 1e-3f, blk.down_bn, blk.down_conv, K, W.E, (long long)K * N, nullptr, 0));
       want_sm = false;
-      if (tc) {
+      }
+      if (use_pool_fused) {
+      } else if (tc) {
         TcGemmArgs a{};   // x_down[c,k] = sum_n x11[c,n] * softmax_n(E[k,:])[n]
         a.B = W.E; a.b_batch = (long long)K * N; a.b_ld = N; a.b_kmajor = 1;
         a.C = W.XD0; a.c_batch = CK; a.c_i = K; a.c_j = 1;

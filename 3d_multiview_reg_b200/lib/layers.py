@@ -58,24 +58,37 @@ def set_default_nn_algo(algo):
 
 
 class Sampler(torch.nn.Module):
-    """lib/layers.py:90-154, 'rand' mode (host-side np.random.choice exactly as the reference; 'fps' depends on
-    pointnet2_ops whose import is commented out in the reference, lib/layers.py:7)."""
+    """lib/layers.py:90-154, samp_type 'rand'.  Same constructor, arguments and outputs ([b,m,3], [b,m,c]) as the reference.
 
-    def __init__(self, samp_type="fps", targeted_num_points=2000):
+    rng='device' (default): one `lmpcr_sample_keypoints` call for the whole batch -- Philox keys + a segmented sort on the GPU, no
+    host round trip; the seed is drawn from torch's CPU generator, so `torch.manual_seed` makes the sample reproducible.  The draw
+    is a uniformly random ordered subset like `np.random.choice(..., replace=False)`, but not numpy's number sequence.
+    rng='numpy': the reference's own host stream (`np.random.choice` per cloud, lib/layers.py:141-145), for runs that must
+    reproduce a numpy-seeded reference experiment index for index; the gather still runs on the device.
+    'fps' depends on pointnet2_ops, whose import is commented out in the reference (lib/layers.py:7): it raises there, too."""
+
+    def __init__(self, samp_type="fps", targeted_num_points=2000, rng="device"):
         super().__init__()
         assert samp_type in ["fps", "rand"], "Wrong sampling type selected. Must be one of [fps, rand]"
+        assert rng in ["device", "numpy"]
         self.samp_type = samp_type
         self.targeted_num_points = targeted_num_points
+        self.rng = rng
 
     def forward(self, input_C, input_F, pts_list):
         if self.samp_type != "rand":
             raise NotImplementedError("fps sampling needs pointnet2_ops (dead code in the reference)")
         pts = [int(v) for v in pts_list]
-        num_points = min(self.targeted_num_points, min(pts))
+        # lib/layers.py:126,142-145: without replacement only if EVERY cloud of the batch has the targeted number of points
+        replace = not (min(self.targeted_num_points, min(pts)) >= self.targeted_num_points)
+        if self.rng == "device":
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            _, sampled_C, sampled_F = _cabi.sample_keypoints(input_C, input_F, pts, self.targeted_num_points, replace, seed)
+            return sampled_C.to(input_C.dtype), sampled_F.to(input_F.dtype)
         sampled_C, sampled_F, start = [], [], 0
         for n in pts:
             rng = np.arange(start, start + n)
-            idxs = np.random.choice(rng, self.targeted_num_points, replace=not (num_points >= self.targeted_num_points))
+            idxs = np.random.choice(rng, self.targeted_num_points, replace=replace)
             idxs = torch.from_numpy(idxs).to(input_C.device).long()
             sampled_F.append(torch.index_select(input_F, 0, idxs))
             sampled_C.append(torch.index_select(input_C, 0, idxs))

@@ -95,6 +95,8 @@ int lmpcr_nn_tensor_debug(const float* q_feat, int n_q_sets, int n_q, const floa
 int lmpcr_debug_tc_profile(unsigned long long* out16, int reset);
 /* The same for the pair-resident PointCN kernel (LMPCR_PCN_DEBUG=1): 40 counters, see csrc/pcn.cu. */
 int lmpcr_debug_pcn_profile(unsigned long long* out40, int reset);
+/* The same for the fused diff_pool kernel (LMPCR_POOL_DEBUG=1): 32 counters, see csrc/pool_fused.cu. */
+int lmpcr_debug_pool_profile(unsigned long long* out32, int reset);
 
 /* lib/utils.py:968-992 `pairwise_distance` itself, materialised: src [B,n,dim], dst [B,m,dim] -> out [B,n,m] fp32,
  * bit-identical to the reference's CPU evaluation.  Not on the hot path (which never stores the matrix); kept so
@@ -174,6 +176,26 @@ int lmpcr_voxel_downsample(const double* points, int n_points, double voxel_size
                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Keypoint sampler in front of stage 1 (lib/layers.py:90-154 `Sampler`, samp_type = 'rand'; called by
+ * lib/pairwise/__init__.py and scripts/benchmark_pairwise_registration.py on the FCGF output of a batch of clouds).
+ * Replaces the per-cloud host `np.random.choice` + two `index_select`s with one device call for the whole batch.
+ * ---------------------------------------------------------------------------------------------------- */
+
+size_t lmpcr_sample_workspace_bytes(int total_points, int n_clouds);
+
+/* coords [total,3], feats [total,dim] fp32: the concatenated clouds of a batch; cloud s owns rows offsets[s]..offsets[s+1]-1
+ * (`offsets` on the device for the kernels, `offsets_host` the same n_clouds+1 values on the host for validation).
+ * with_replacement = 0: a uniformly random ORDERED n_samples-subset per cloud (np.random.choice(range, m, replace=False),
+ * lib/layers.py:143); every cloud needs >= n_samples points, else LMPCR_ERR_ARG like numpy's ValueError.
+ * with_replacement = 1: n_samples independent uniform draws per cloud (lib/layers.py:145).
+ * The stream is Philox4x32-10 keyed by `seed` (counter = point / slot index): deterministic per seed, independent of launch
+ * geometry; it is NOT numpy's MT19937 sequence.  idx_out [n_clouds,n_samples] holds global row indices; coords_out
+ * [n_clouds,n_samples,3] and feats_out [n_clouds,n_samples,dim] (either may be NULL) are the gathered rows. */
+int lmpcr_sample_keypoints(const float* coords, const float* feats, const int32_t* offsets, const int32_t* offsets_host, int n_clouds, int dim,
+                           int n_samples, int with_replacement, uint64_t seed, int32_t* idx_out, float* coords_out, float* feats_out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * Stage 3 -- weighted Kabsch + residuals + confidence.
  * Replaces lib/utils.py:164-237 `kabsch_transformation_estimation` (normalize_w=True, best_k=0,
  * w_threshold=0) and lib/utils.py:240-256 `transformation_residuals`.
@@ -237,6 +259,18 @@ int lmpcr_conv1x1(const float* x, int n_pairs, int cin, int n_pts, const float* 
 size_t lmpcr_pointcn_stack_workspace_bytes(int n_pairs, int n_layers);
 int lmpcr_pointcn_stack(const float* x, int n_pairs, int n_pts, const float* const* params, int n_layers, float* out, float* stats_out,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused diff_pool (lib/filtering/oanet.py:96-110) in one launch -- embedding conv, softmax over the points and the weighted sum;
+ * the [K, N] embedding never reaches memory (csrc/pool_fused.cu).  This is what lmpcr_filter_forward runs for 128 channels.
+ *   out[p,c,k] = sum_n x[p,c,n] * softmax_n( weight . relu(x[p] * scale[p] + shift[p]) )[k,n]
+ *   x [P,128,N] fp32 (n_pts % 4 == 0, n_pts <= 8192), scale / shift [P,128] (the folded InstanceNorm + BatchNorm in front of the
+ *   conv), weight [K,128]; the conv bias cancels in the softmax and is not an argument.  out [P,128,K] fp32.
+ *   mode 0 (what the network runs): one pass over the points with the first tile's row maxima as the softmax shift, and a
+ *   second launch that redoes the rare (pair, cluster block) whose row sums overflowed under that shift; mode 1: two passes for
+ *   every item (row maxima first). */
+size_t lmpcr_diff_pool_fused_workspace_bytes(int n_pairs, int clusters);
+int lmpcr_diff_pool_fused(const float* x, int n_pairs, int n_pts, const float* scale, const float* shift, const float* weight, int clusters,
+                          int mode, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of tensors of OANet(cfg).state_dict() excluding `num_batches_tracked` entries; `params` below is
  * a HOST array of that many DEVICE pointers (fp32, contiguous), in state_dict order. */

@@ -465,3 +465,38 @@ import sys as _sys
 
 _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 from synthdata import oanet_param_schema, random_rotation, synth_cloud_pair, synth_scene, synth_state_dict, synth_xs  # noqa: E402,F401
+
+
+# ----------------------------------------------------------------------------- keypoint sampler (lib/layers.py:90-154)
+def sampler_rand(coords, feats, pts, m, rng=np.random):
+    """Restatement of Sampler('rand').forward: per cloud `choice(range, m, replace=False)` when EVERY cloud of the batch has at
+    least m points, else `choice(range, m, replace=True)` (lib/layers.py:126,141-145); then the two index_selects.  `rng` is
+    numpy's global stream by default, exactly what the reference consumes.  Returns (idx [b,m], coords [b,m,3], feats [b,m,c])."""
+    pts = [int(v) for v in pts]
+    replace = not (min(m, min(pts)) >= m)
+    idx, start = [], 0
+    for n in pts:
+        idx.append(rng.choice(np.arange(start, start + n), m, replace=replace))
+        start += n
+    idx = np.stack(idx, 0)
+    return idx, coords[idx], feats[idx]
+
+
+def sampler_contract(idx, pts, m):
+    """What any 'rand' sample must satisfy, whatever the random stream: shape [b,m], every index inside its own cloud, and no
+    repeats unless the batch took the with-replacement branch.  Returns the list of violations (empty = valid)."""
+    pts = [int(v) for v in pts]
+    idx = np.asarray(idx)
+    bad = []
+    if idx.shape != (len(pts), m):
+        return ["shape %s != %s" % (idx.shape, (len(pts), m))]
+    replace = not (min(m, min(pts)) >= m)
+    start = 0
+    for s, n in enumerate(pts):
+        row = idx[s]
+        if row.min() < start or row.max() >= start + n:
+            bad.append("cloud %d: index outside [%d, %d)" % (s, start, start + n))
+        if not replace and len(np.unique(row)) != m:
+            bad.append("cloud %d: repeated index without replacement" % s)
+        start += n
+    return bad

@@ -133,10 +133,11 @@ def test_grouping_invariance_at_bench_size():
     full = cabi.filter_forward(x, params, cfg, want_latent=False, packed=packed)
     for p in (0, 36, 73):
         one = cabi.filter_forward(x[p:p + 1].contiguous(), params, cfg, want_latent=False, packed=packed)
-        # the group took pcn_stack_kernel, the single pair the per-layer GEMMs: equal within the two evaluations' fp32 noise
+        # the group took pcn_stack_kernel and pool_fused_kernel, the single pair the per-layer GEMMs: equal within the two evaluations' fp32 noise
         assert (one["logits"][0][0] - full["logits"][0][p]).abs().max().item() < 5e-4
         assert O.chordal_angle(one["R"][-1].cpu().numpy(), full["R"][-1][p:p + 1].cpu().numpy()).max() < 1e-3
     os.environ["LMPCR_PCN"] = "0"
+    os.environ["LMPCR_POOL_FUSED"] = "0"
     try:
         full_l = cabi.filter_forward(x, params, cfg, want_latent=False, packed=packed)
         for p in (0, 36, 73):
@@ -145,6 +146,7 @@ def test_grouping_invariance_at_bench_size():
                 assert torch.equal(one[k][:, 0], full_l[k][:, p]), (k, p)      # same kernels: bit-identical
     finally:
         del os.environ["LMPCR_PCN"]
+        del os.environ["LMPCR_POOL_FUSED"]
     # the latent-feature variant of the pair-resident tail (tiles stored) gives the same logits as the on-chip variant
     lat = cabi.filter_forward(x, params, cfg, want_latent=True, packed=packed)
     assert torch.equal(lat["logits"], full["logits"]) and torch.equal(lat["R"], full["R"])

@@ -1,0 +1,109 @@
+"""GPU: the fused diff_pool kernel (csrc/pool_fused.cu: embedding conv + softmax over the points + weighted sum in one launch)
+against an fp64 numpy restatement of lib/filtering/oanet.py:96-110, alone (lmpcr_diff_pool_fused) and inside lmpcr_filter_forward
+(groups of >= 64 pairs take it; LMPCR_POOL_FUSED=0 switches it off)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lmpcr_oracle as O
+from util import cabi, cu, load_oanet
+
+pytestmark = pytest.mark.gpu
+
+
+def _diff_pool_ref(x, sc, sh, w, b):
+    """out[p,c,k] = sum_n x[p,c,n] softmax_n(w relu(x*sc+sh) + b)[k,n]  in fp64 (the bias is kept here: it must cancel)"""
+    x64 = x.astype(np.float64)
+    h = np.maximum(x64 * sc.astype(np.float64)[:, :, None] + sh.astype(np.float64)[:, :, None], 0)
+    E = np.einsum("kc,pcn->pkn", w.astype(np.float64), h) + b.astype(np.float64)[None, :, None]
+    S = np.exp(E - E.max(2, keepdims=True))
+    S /= S.sum(2, keepdims=True)
+    return np.matmul(x64, S.transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["single_pass", "two_pass"])
+@pytest.mark.parametrize("P,N,K", [(3, 200, 500), (2, 2000, 500), (2, 5000, 500), (75, 264, 500), (3, 64, 16), (2, 1000, 130), (2, 8192, 300), (1, 28, 500)])
+def test_diff_pool_fused_against_fp64(P, N, K, mode):
+    rng = np.random.default_rng(P * 100000 + N * 10 + K)
+    x = (rng.standard_normal((P, 128, N)) * 2 + 0.5).astype(np.float32)
+    sc = rng.uniform(0.3, 1.2, (P, 128)).astype(np.float32)
+    sh = (0.5 * rng.standard_normal((P, 128))).astype(np.float32)
+    w = (rng.standard_normal((K, 128)) * 3 / np.sqrt(128)).astype(np.float32)          # logits of a few units: a peaked softmax
+    b = rng.standard_normal(K).astype(np.float32)
+    ref = _diff_pool_ref(x, sc, sh, w, b)
+    got = cabi.diff_pool_fused(cu(x), cu(sc), cu(sh), cu(w), mode).cpu().numpy()
+    assert got.shape == (P, 128, K)
+    err = np.abs(got - ref).max()
+    # 5e-5 relative to the largest output, the gate of lmpcr_softmax_pool (split-bf16 products, fp32 accumulation)
+    assert err < 5e-5 * np.abs(ref).max(), (err, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["single_pass", "two_pass"])
+def test_diff_pool_fused_extreme_logits(mode):
+    """Rows whose maximum is far from zero (both signs) and one dominating point in the first tile: exp(E - shift) stays in range."""
+    rng = np.random.default_rng(7)
+    P, N, K = 2, 1000, 500
+    x = (rng.standard_normal((P, 128, N))).astype(np.float32)
+    x[:, :, 17] *= 6.0                                        # one point with large features
+    sc = np.ones((P, 128), np.float32)
+    sh = np.zeros((P, 128), np.float32)
+    w = (rng.standard_normal((K, 128)) * 8 / np.sqrt(128)).astype(np.float32)
+    ref = _diff_pool_ref(x, sc, sh, w, np.zeros(K, np.float32))
+    got = cabi.diff_pool_fused(cu(x), cu(sc), cu(sh), cu(w), mode).cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() < 1e-4 * np.abs(ref).max()
+
+
+def test_diff_pool_fused_single_pass_overflow_takes_the_fallback():
+    """A point far behind the first tile whose logits exceed every first-tile logit by hundreds: under the first tile's shift
+    exp() overflows, the row sums reveal it, and the second launch redoes those (pair, cluster block) items with row maxima over
+    all points.  Pair 1 is tame and must come out of the single pass untouched by the fallback (bit-identical to a tame-only call)."""
+    rng = np.random.default_rng(11)
+    P, N, K = 2, 1500, 500
+    x = rng.standard_normal((P, 128, N)).astype(np.float32)
+    x[0, :, 900] *= 30.0
+    sc = np.ones((P, 128), np.float32)
+    sh = np.zeros((P, 128), np.float32)
+    w = (rng.standard_normal((K, 128)) * 8 / np.sqrt(128)).astype(np.float32)
+    ref = _diff_pool_ref(x, sc, sh, w, np.zeros(K, np.float32))
+    E0 = w.astype(np.float64) @ np.maximum(x[0].astype(np.float64), 0)
+    assert (E0[:, 900] - E0[:, :64].max(1)).max() > 100, "the case must overflow the single pass"
+    got = cabi.diff_pool_fused(cu(x), cu(sc), cu(sh), cu(w), 0).cpu().numpy()
+    two = cabi.diff_pool_fused(cu(x), cu(sc), cu(sh), cu(w), 1).cpu().numpy()
+    assert np.isfinite(got).all()
+    # logits of several hundred carry an absolute fp32 error of ~1e-2, which rows where the outlier ties with ordinary points turn into
+    # a relative output error of that size: the gate against fp64 is loose here, the one against the two-pass mode (same arithmetic,
+    # same maxima for the redone items) is tight
+    assert np.abs(got - ref).max() < 1e-3 * np.abs(ref).max()
+    assert np.array_equal(got[0], two[0]), "flagged items are redone by exactly the two-pass code"
+    assert np.abs(got[1] - two[1]).max() < 2e-5 * np.abs(ref[1]).max()
+    tame = cabi.diff_pool_fused(cu(x[1:]), cu(sc[1:]), cu(sh[1:]), cu(w), 0).cpu().numpy()
+    assert np.array_equal(tame[0], got[1])
+
+
+def test_network_takes_the_fused_pool_and_agrees_with_the_gemm_path():
+    """74 pairs in one call: both blocks run diff_pool through pool_fused_kernel; same logits as the embedding-GEMM + pooling-GEMM
+    path (LMPCR_POOL_FUSED=0) within the tensor-path noise, and the first block within the 5e-4 gate of the fp64 oracle."""
+    sd = O.synth_state_dict(5)
+    xs, _, _ = O.synth_xs(74, 500, seed=5)
+    net = load_oanet(sd, gemm_algo=1)
+    x = cu(xs)
+    n0 = cabi.launch_count_named("pool_fused_kernel")
+    out = net({"xs": x})
+    assert cabi.launch_count_named("pool_fused_kernel") - n0 == 2
+    os.environ["LMPCR_POOL_FUSED"] = "0"
+    try:
+        n1 = cabi.launch_count_named("pool_fused_kernel")
+        ref = net({"xs": x})
+        assert cabi.launch_count_named("pool_fused_kernel") == n1
+    finally:
+        del os.environ["LMPCR_POOL_FUSED"]
+    o64 = O.oanet_forward(xs, sd, dtype=np.float64)
+    err = {name: [np.abs(res["logits"][it].cpu().numpy() - o64["logits"][it]).max() for it in range(2)] for name, res in (("fused", out), ("gemm", ref))}
+    print("max |logit - fp64| per block:", err)
+    for it in range(2):
+        assert err["fused"][it] < max(5e-4, 1.5 * err["gemm"][it]), err
+    assert err["fused"][0] < 5e-4 and err["gemm"][0] < 5e-4, err
+    assert O.chordal_angle(out["rot_est"][-1].cpu().numpy(), o64["rot_est"][-1]).max() < 1e-3
+    assert (out["logits"][0] - ref["logits"][0]).abs().max().item() < 5e-4
