@@ -20,7 +20,7 @@ GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
 EXPORTS = [
-    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_launch_count_named", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_debug_pcn_profile", "lmpcr_debug_pool_profile", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_softmax_unpool", "lmpcr_softmax_unpool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_launch_count_named", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_debug_pcn_profile", "lmpcr_debug_pool_profile", "lmpcr_debug_ktime_enable", "lmpcr_debug_ktime_read", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_softmax_unpool", "lmpcr_softmax_unpool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
     "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
     "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
     "lmpcr_filter_pack_bytes", "lmpcr_filter_pack_weights", "lmpcr_filter_forward_packed",
@@ -252,6 +252,20 @@ def nn_soft(q_feat, b_feat, b_xyz, jobs, temperature):
 
 def launch_count():
     return int(load().lmpcr_launch_count())
+
+
+def ktime_enable(on=True):
+    """Start (and reset) / stop the per-kernel device timers (lmpcr_debug_ktime_enable)."""
+    load().lmpcr_debug_ktime_enable(1 if on else 0)
+
+
+def ktime_read(kernel_name):
+    """(launches, total milliseconds) of `kernel_name` since ktime_enable(True); synchronises on the recorded events."""
+    n, ms = ctypes.c_int(0), ctypes.c_float(0.0)
+    lib = load()
+    lib.lmpcr_debug_ktime_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)]
+    _check(lib.lmpcr_debug_ktime_read(kernel_name.encode(), ctypes.byref(n), ctypes.byref(ms)))
+    return n.value, ms.value
 
 
 def launch_count_named(kernel_name):

@@ -46,6 +46,26 @@ int check_launch(const char* what) {
   return LMPCR_OK;
 }
 
+// Optional device timing of selected kernels (bench.py's live roofline): while enabled, the launchers that bracket their kernel with
+// ktime_begin / ktime_end record a CUDA event pair on the launching stream; lmpcr_debug_ktime_read synchronises and sums the pairs of
+// one kernel.  Off by default (no events are created or recorded); single-threaded use (the bench), bounded ring.
+struct KtPair { const char* name; cudaEvent_t e0, e1; };
+static KtPair g_kt[16384];
+static int g_kt_n = 0;
+static int g_kt_on = 0;
+void ktime_begin(const char* name, cudaStream_t st) {
+  if (!g_kt_on || g_kt_n >= 16384) return;
+  KtPair& k = g_kt[g_kt_n];
+  k.name = name;
+  if (!k.e0) { cudaEventCreate(&k.e0); cudaEventCreate(&k.e1); }
+  cudaEventRecord(k.e0, st);
+}
+void ktime_end(const char* name, cudaStream_t st) {
+  if (!g_kt_on || g_kt_n >= 16384 || g_kt[g_kt_n].name != name) return;
+  cudaEventRecord(g_kt[g_kt_n].e1, st);
+  ++g_kt_n;
+}
+
 static int g_cc_major[64], g_sms[64];
 static bool g_seen[64];
 
@@ -93,6 +113,22 @@ extern "C" {
 int lmpcr_abi_version(void) { return LMPCR_ABI_VERSION; }
 long long lmpcr_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 const char* lmpcr_last_error(void) { return g_err; }
+void lmpcr_debug_ktime_enable(int on) { g_kt_on = on ? 1 : 0; if (on) g_kt_n = 0; }
+
+int lmpcr_debug_ktime_read(const char* kernel_name, int* count_out, float* total_ms_out) {
+  int n = 0; float tot = 0.f;
+  for (int i = 0; i < g_kt_n; ++i) {
+    if (strcmp(g_kt[i].name, kernel_name) != 0) continue;
+    if (cudaEventSynchronize(g_kt[i].e1) != cudaSuccess) { cudaGetLastError(); return LMPCR_ERR_LAUNCH; }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_kt[i].e0, g_kt[i].e1) != cudaSuccess) { cudaGetLastError(); return LMPCR_ERR_LAUNCH; }
+    tot += ms; ++n;
+  }
+  if (count_out) *count_out = n;
+  if (total_ms_out) *total_ms_out = tot;
+  return LMPCR_OK;
+}
+
 long long lmpcr_launch_count_named(const char* kernel_name) {
   long long c = 0;
   const int n = __atomic_load_n(&g_n_names, __ATOMIC_ACQUIRE);

@@ -15,6 +15,9 @@ int check_launch(const char* what);
 int sm_count();
 int device_ordinal();    // current device clamped to [0, 63] (index of the per-device caches)
 void count_launches(int n);   // bookkeeping behind lmpcr_launch_count()
+// device timing of one kernel launch (CUDA events on `st`), recorded only while lmpcr_debug_ktime_enable(1) is in effect
+void ktime_begin(const char* name, cudaStream_t st);
+void ktime_end(const char* name, cudaStream_t st);
 
 #define LMPCR_REQUIRE(cond, code, ...)   \
   do {                                   \

@@ -288,7 +288,7 @@ int gemm(const GemmArgs& g, int batch, cudaStream_t st) {
 __global__ void in_affine_kernel(const float* __restrict__ x, long long x_batch, int C, int L, int use_in, float eps_in,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ rmean, const float* __restrict__ rvar,
-                                 float* __restrict__ scale, float* __restrict__ shift, int n_rows, int bn_train) {
+                                 float* __restrict__ scale, float* __restrict__ shift, int n_rows, int bn_train, int ld = 0) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -297,7 +297,7 @@ __global__ void in_affine_kernel(const float* __restrict__ x, long long x_batch,
   const float gsc = bn_train ? 1.f : __ldg(gamma + c) / sqrtf(__ldg(rvar + c) + 1e-5f);
   float mean = 0.f, rstd = 1.f;
   if (use_in) {
-    const float* r = x + (long long)p * x_batch + (long long)c * L;
+    const float* r = x + (long long)p * x_batch + (long long)c * (ld ? ld : L);     // rows ld floats apart (0: contiguous)
     float s = 0.f;
     for (int i = lane; i < L; i += 32) s += __ldg(r + i);
     mean = warp_sum(s) / (float)L;
@@ -616,11 +616,16 @@ struct Work {   // per-group scratch, all fp32
 constexpr int N_PART = 7;   // activation buffers whose producer can emit InstanceNorm partials (T0,T1,T2,CAT.lo,CAT.hi,XD0,XD1)
 
 inline size_t r64(size_t n) { return (n + 63) / 64 * 64; }   // every per-pair buffer is a multiple of 256 bytes (TMA alignment)
+// leading dimension of the cluster-level matrices [C, K] on the tensor path: rows padded to whole 8-element groups (K = 500 -> 504 floats
+// = 63 x 32 bytes) so that every row starts 32-byte aligned and the GEMMs on them take tcgemm's lean producer loop (256-bit loads;
+// TcGemmArgs::b_pad_ok).  The pad columns are never written and never reach a result: k-major reads mask them, j-major reads turn
+// them into output columns >= N that are not stored.
+inline int kpad(int K) { return (K + 7) / 8 * 8; }
 
 // per-pair workspace, in floats: the carve in launch_filter_forward takes the same terms in the same order
 size_t per_pair_floats(int C, int K, int N) {
   const size_t L = (size_t)(N > K ? N : K), tmax = (L + TC_TILE_N - 1) / TC_TILE_N;
-  size_t f = r64((size_t)12 * N) + 3 * r64((size_t)C * N) + r64((size_t)2 * C * N) + r64((size_t)K * N) + 4 * r64((size_t)C * K) + 2 * r64(1024) + 2 * r64(L);
+  size_t f = r64((size_t)12 * N) + 3 * r64((size_t)C * N) + r64((size_t)2 * C * N) + r64((size_t)K * N) + 4 * r64((size_t)C * kpad(K)) + 2 * r64(1024) + 2 * r64(L);
   f += (size_t)N_PART * r64((size_t)C * tmax * 2) + r64((size_t)K * tmax * 2);            // norm / softmax partials
   f += r64((size_t)N * 4 * ((K + 127) / 128) * 2);                                        // column-softmax partials (diff_unpool)
   f += r64(tc_weight_blob_bytes(C, K) / 4) + r64(tc_weight_blob_bytes(C, N) / 4);        // pre-split x2 / x1_1 (pool, unpool A operands)
@@ -932,7 +937,8 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   W.T0 = take((size_t)C * N); W.T1 = take((size_t)C * N); W.T2 = take((size_t)C * N);
   W.CAT = take((size_t)2 * C * N);
   W.E = take((size_t)K * N);
-  W.XD0 = take((size_t)C * K); W.XD1 = take((size_t)C * K); W.Y = take((size_t)C * K); W.Z = take((size_t)C * K);
+  const int KP = (tc && cfg->bn_mode != LMPCR_BN_BATCH) ? kpad(K) : K;      // row stride of the cluster-level matrices
+  W.XD0 = take((size_t)C * kpad(K)); W.XD1 = take((size_t)C * kpad(K)); W.Y = take((size_t)C * kpad(K)); W.Z = take((size_t)C * kpad(K));
   W.scale = take(1024); W.shift = take(1024);
   float* sm_max = take((size_t)(N > K ? N : K));
   float* sm_inv = take((size_t)(N > K ? N : K));
@@ -960,7 +966,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   if (status) cudaMemsetAsync(status, 0, (size_t)P * 4, st);
 
   Cursor cur{params, 0, n_params};
-  const long long CN = (long long)C * N, CK = (long long)C * K;
+  const long long CN = (long long)C * N, CK = (long long)C * KP;
 
   // Training-mode BatchNorm (cfg->bn_mode == LMPCR_BN_BATCH): the kernels above emit the InstanceNorm-only affine and
   // bn_train_finalize_kernel folds in the statistics of the batch (= all pairs of the call) and updates the running buffers.
@@ -970,7 +976,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
                                                           const_cast<float*>(bn.rm) + bn_off, const_cast<float*>(bn.rv) + bn_off, L, 0.1f);
     return check_launch("bn_train_finalize_kernel");
   };
-  auto affine = [&](const float* x, long long xb, int ch, int L, int g, bool use_in, float eps, const BNP& bn) -> int {
+  auto affine = [&](const float* x, long long xb, int ch, int L, int g, bool use_in, float eps, const BNP& bn, int ld = 0) -> int {
     if (!use_in && bn_train) {        // BatchNorm over the cluster axis of x [g, C, ch]: batch statistics over (pairs, C)
       bn_train_cols_kernel<<<(ch + 127) / 128, 128, 0, st>>>(x, xb, C, ch, g, bn.g, bn.b, const_cast<float*>(bn.rm), const_cast<float*>(bn.rv),
                                                             W.scale, W.shift, 0.1f);
@@ -978,7 +984,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     }
     const int rows = use_in ? g * ch : ch;
     in_affine_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, xb, ch, L, use_in ? 1 : 0, eps, bn.g, bn.b, bn.rm, bn.rv, W.scale, W.shift, rows,
-                                                    bn_train ? 1 : 0);
+                                                    bn_train ? 1 : 0, ld);
     LMPCR_TRY(check_launch("in_affine_kernel"));
     return use_in ? bn_finalize(ch, L, g, eps, bn, 0, ch, 0) : LMPCR_OK;
   };
@@ -991,7 +997,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     return bn_finalize(ch, L, g, eps, bn, bn_off, out_stride, out_off);
   };
   // W.scale / W.shift [g, cin] <- InstanceNorm (+ BatchNorm) of x: from the producer's fused partials when available, else a pass over x
-  auto norm_affine = [&](const float* x, long long xb, int cin, int L, int g, float eps, const BNP& bn) -> int {
+  auto norm_affine = [&](const float* x, long long xb, int cin, int L, int g, float eps, const BNP& bn, int ld = 0) -> int {
     const int xi = part_index(x);
     const int xi_hi = (cin == 2 * C) ? part_index(x + (size_t)C * L) : -1;
     if (tc && cin == C && xi >= 0 && part_valid[xi]) return aff_part(part_buf[xi], part_whole[xi], C, L, g, eps, bn, 0, C, 0);
@@ -999,18 +1005,19 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       LMPCR_TRY(aff_part(part_buf[xi], part_whole[xi], C, L, g, eps, bn, 0, 2 * C, 0));
       return aff_part(part_buf[xi_hi], part_whole[xi_hi], C, L, g, eps, bn, C, 2 * C, C);
     }
-    return affine(x, xb, cin, L, g, true, eps, bn);
+    return affine(x, xb, cin, L, g, true, eps, bn, ld);
   };
   // out[p, :, :] = conv(relu(bn(in(x))))  (+ residual), x [g, cin, L] with batch stride xb
   auto conv_norm = [&](const float* x, long long xb, int cin, int L, int g, float eps, const BNP& bn, const ConvP& cv, int cout,
-                       float* out, long long ob, const float* res, long long rb) -> int {
-    LMPCR_TRY(norm_affine(x, xb, cin, L, g, eps, bn));
+                       float* out, long long ob, const float* res, long long rb, int ld = 0) -> int {
+    if (ld == 0) ld = L;                 // row stride of x / out / res (the cluster-level matrices are stored KP apart)
+    LMPCR_TRY(norm_affine(x, xb, cin, L, g, eps, bn, ld));
     const int oi = part_index(out);
     if (tc) {
       TcGemmArgs a{};
       a.a_blob = cv.blob;
-      a.B = x; a.b_batch = xb; a.b_ld = L; a.b_kmajor = 0;
-      a.C = out; a.c_batch = ob; a.c_i = L; a.c_j = 1;
+      a.B = x; a.b_batch = xb; a.b_ld = ld; a.b_kmajor = 0; a.b_pad_ok = (ld >= ((L + 7) & ~7)) ? 1 : 0;
+      a.C = out; a.c_batch = ob; a.c_i = ld; a.c_j = 1;
       a.Res = res; a.r_batch = rb; a.bias = cv.b;
       a.prologue = TC_PRO_AFFINE_RELU; a.p0 = W.scale; a.p1 = W.shift; a.p_batch = cin;
       a.M = cout; a.N = L; a.K = cin;
@@ -1045,8 +1052,8 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
     if (oi >= 0) { part_valid[oi] = false; part_whole[oi] = false; }
     GemmArgs a{};
     a.A = cv.w; a.a_batch = 0; a.a_i = cin;
-    a.B = x; a.b_batch = xb; a.b_k = L; a.b_j = 1;
-    a.C = out; a.c_batch = ob; a.c_i = L; a.c_j = 1;
+    a.B = x; a.b_batch = xb; a.b_k = ld; a.b_j = 1;
+    a.C = out; a.c_batch = ob; a.c_i = ld; a.c_j = 1;
     a.Res = res; a.r_batch = rb; a.bias = cv.b;
     a.scale = W.scale; a.shift = W.shift; a.aff_batch = cin;
     a.M = cout; a.N = L; a.K = cin;
@@ -1155,7 +1162,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         LMPCR_TRY(norm_affine(x11, x11b, C, N, g, 1e-3f, blk.down_bn));
         PoolFusedArgs pa{};
         pa.w_blob = blk.down_conv.blob_rm; pa.scale = W.scale; pa.shift = W.shift;
-        pa.out = W.XD0; pa.out_batch = CK; pa.out_ld = K; pa.P = g; pa.N = N; pa.K = K;
+        pa.out = W.XD0; pa.out_batch = CK; pa.out_ld = KP; pa.P = g; pa.N = N; pa.K = K;
         pa.flags = reinterpret_cast<int32_t*>(sm_max);      // [g * 4] ints of a scratch row buffer that is idle until diff_unpool
         LMPCR_TRY(launch_pool_fused(x11, x11b, pa, st));
         part_valid[part_index(W.XD0)] = false; part_whole[part_index(W.XD0)] = false;
@@ -1168,7 +1175,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       } else if (tc) {
         TcGemmArgs a{};   // x_down[c,k] = sum_n x11[c,n] * softmax_n(E[k,:])[n]
         a.B = W.E; a.b_batch = (long long)K * N; a.b_ld = N; a.b_kmajor = 1;
-        a.C = W.XD0; a.c_batch = CK; a.c_i = K; a.c_j = 1;
+        a.C = W.XD0; a.c_batch = CK; a.c_i = KP; a.c_j = 1;
         a.prologue = TC_PRO_SOFTMAX; a.p0 = sm_max; a.p1 = sm_inv; a.p_batch = K;
         a.M = C; a.N = K; a.K = N;
         if ((N & 3) == 0 && N >= TC_DEFER_MIN_K && !(no_defer & 1)) {   // row maxima came fused out of the embedding conv's epilogue; the GEMM accumulates the sums itself
@@ -1191,7 +1198,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         GemmArgs a{};   // x_down[c,k] = sum_n x11[c,n] * S[k,n]
         a.A = x11; a.a_batch = x11b; a.a_i = N;
         a.B = W.E; a.b_batch = (long long)K * N; a.b_k = 1; a.b_j = N;
-        a.C = W.XD0; a.c_batch = CK; a.c_i = K; a.c_j = 1;
+        a.C = W.XD0; a.c_batch = CK; a.c_i = KP; a.c_j = 1;
         a.M = C; a.N = K; a.K = N;
         LMPCR_TRY(gemm(a, g, st));
         part_valid[part_index(W.XD0)] = false; part_whole[part_index(W.XD0)] = false;
@@ -1200,13 +1207,13 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       float* xd_in = W.XD0; float* xd_out = W.XD1;
       for (int i = 0; i < half; ++i) {
         const OAFilterP& q = blk.l2[i];
-        LMPCR_TRY(conv_norm(xd_in, CK, C, K, g, 1e-3f, q.bn1, q.c1, C, W.Y, CK, nullptr, 0));     // conv1 -> Y [g,C,K]
+        LMPCR_TRY(conv_norm(xd_in, CK, C, K, g, 1e-3f, q.bn1, q.c1, C, W.Y, CK, nullptr, 0, KP));     // conv1 -> Y [g,C,K]
         LMPCR_TRY(affine(W.Y, CK, K, 0, g, false, 0.f, q.bn2));                                    // BN over the cluster axis
         if (tc) {
           TcGemmArgs a{};   // Z[c,k'] = Y[c,k'] + b2[k'] + sum_k W2[k',k] relu(bn_k(Y[c,k]))   (trans(1,2) via strides)
           a.a_blob = q.c2.blob;
-          a.B = W.Y; a.b_batch = CK; a.b_ld = K; a.b_kmajor = 1;
-          a.C = W.Z; a.c_batch = CK; a.c_i = 1; a.c_j = K;
+          a.B = W.Y; a.b_batch = CK; a.b_ld = KP; a.b_kmajor = 1; a.b_pad_ok = (KP >= ((K + 7) & ~7)) ? 1 : 0;
+          a.C = W.Z; a.c_batch = CK; a.c_i = 1; a.c_j = KP;
           a.Res = W.Y; a.r_batch = CK; a.bias = q.c2.b;
           a.prologue = TC_PRO_AFFINE_RELU; a.p0 = W.scale; a.p1 = W.shift; a.p_batch = 0;
           a.M = K; a.N = C; a.K = K;
@@ -1214,14 +1221,14 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         } else {
           GemmArgs a{};   // Z[c,k'] = Y[c,k'] + b2[k'] + sum_k W2[k',k] relu(bn_k(Y[c,k]))   (trans(1,2) via strides)
           a.A = q.c2.w; a.a_batch = 0; a.a_i = K;
-          a.B = W.Y; a.b_batch = CK; a.b_k = 1; a.b_j = K;
-          a.C = W.Z; a.c_batch = CK; a.c_i = 1; a.c_j = K;
+          a.B = W.Y; a.b_batch = CK; a.b_k = 1; a.b_j = KP;
+          a.C = W.Z; a.c_batch = CK; a.c_i = 1; a.c_j = KP;
           a.Res = W.Y; a.r_batch = CK; a.bias = q.c2.b;
           a.scale = W.scale; a.shift = W.shift; a.aff_batch = 0;
           a.M = K; a.N = C; a.K = K;
           LMPCR_TRY(gemm(a, g, st));
         }
-        LMPCR_TRY(conv_norm(W.Z, CK, C, K, g, 1e-3f, q.bn3, q.c3, C, xd_out, CK, xd_in, CK));      // conv3 + x
+        LMPCR_TRY(conv_norm(W.Z, CK, C, K, g, 1e-3f, q.bn3, q.c3, C, xd_out, CK, xd_in, CK, KP));      // conv3 + x
         float* t = xd_in; xd_in = xd_out; xd_out = t;
       }
       // diff_unpool (oanet.py:122-129): x_up -> upper half of the concat buffer
@@ -1238,7 +1245,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
           LMPCR_TRY(check_launch("softmax_colstats_kernel"));
         }
         TcGemmArgs a{};   // x_up[c,n] = sum_k x2[c,k] * softmax_k(E[:,n])[k]
-        LMPCR_TRY(launch_split_weights(xd_in, C, K, blob_x2, st, g, CK, K));   // A operand (x2) shared by all point tiles of a pair
+        LMPCR_TRY(launch_split_weights(xd_in, C, K, blob_x2, st, g, CK, KP));   // A operand (x2) shared by all point tiles of a pair
         a.a_blob = blob_x2; a.a_blob_batch = (long long)tc_weight_blob_bytes(C, K);
         a.B = W.E; a.b_batch = (long long)K * N; a.b_ld = N; a.b_kmajor = 0;
         a.C = W.CAT + CN; a.c_batch = 2 * CN; a.c_i = N; a.c_j = 1;
@@ -1250,7 +1257,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         softmax_cols_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g);
         LMPCR_TRY(check_launch("softmax_cols_kernel"));
         GemmArgs a{};   // x_up[c,n] = sum_k x2[c,k] * S[k,n]
-        a.A = xd_in; a.a_batch = CK; a.a_i = K;
+        a.A = xd_in; a.a_batch = CK; a.a_i = KP;
         a.B = W.E; a.b_batch = (long long)K * N; a.b_k = N; a.b_j = 1;
         a.C = W.CAT + CN; a.c_batch = 2 * CN; a.c_i = N; a.c_j = 1;
         a.M = C; a.N = N; a.K = K;

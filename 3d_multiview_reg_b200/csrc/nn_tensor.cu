@@ -42,6 +42,14 @@ constexpr int B_BYTES = TN * KP * 2;   // 24576
 constexpr uint32_t OVERFLOW = 0xFFFFu;
 constexpr float PAD_NORM = 60000.0f;   // |b|^2 stand-in of padding rows: never a minimum
 
+// Barrier waits of the sweep.  A tile lasts ~0.4 us, so the hinted try_wait of tc_ptx.cuh (TRYWAIT + NANOSLEEP.SYNCS: the wake-up alone costs
+// ~0.5 us per hand-off, measured in pcn.cu) is the wrong tool here: hint-free try_wait in a loop.  -DLMPCR_NN_WAIT_HINT restores the old form (A/B runs).
+#ifdef LMPCR_NN_WAIT_HINT
+__device__ __forceinline__ void nn_wait(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+#else
+__device__ __forceinline__ void nn_wait(uint32_t bar, uint32_t parity) { mbar_wait_fast(bar, parity); }
+#endif
+
 struct RowStat { float u, v, na; };    // u = 2|da|, v = 2|a_hat|, na = |a|  (all rounded up)
 
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = 256
@@ -182,12 +190,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int job = (int)(item / n_stripes), stripe = (int)(item - (long long)job * n_stripes);
         const int qs = __ldg(g.jobs + 2 * job), bs = __ldg(g.jobs + 2 * job + 1);
-        mbar_wait(A_EMPTY, a_phase ^ 1);
+        nn_wait(A_EMPTY, a_phase ^ 1);
         mbar_expect_tx(A_FULL, A_BYTES);
         bulk_g2s(smem_u32(sA), g.form_q + ((size_t)qs * g.rows_pad_q + (size_t)stripe * TM) / 8 * RG_BYTES, A_BYTES, A_FULL);
         const uint8_t* bsrc = g.form_b + (size_t)bs * g.rows_pad_b / 8 * RG_BYTES;
         for (int t = 0; t < n_tiles; ++t) {
-          mbar_wait(EMPTY(stage), phase ^ 1);
+          nn_wait(EMPTY(stage), phase ^ 1);
           mbar_expect_tx(FULL(stage), B_BYTES);
           bulk_g2s(smem_u32(sB + stage * B_BYTES), bsrc + (size_t)t * B_BYTES, B_BYTES, FULL(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -201,10 +209,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
       int stage = 0, acc = 0; uint32_t phase = 0, acc_phase = 0, a_phase = 0;
       const uint32_t sA_u = smem_u32(sA);
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        mbar_wait(A_FULL, a_phase);
+        nn_wait(A_FULL, a_phase);
         for (int t = 0; t < n_tiles; ++t) {
-          mbar_wait(T_EMPTY(acc), acc_phase ^ 1);
-          mbar_wait(FULL(stage), phase);
+          nn_wait(T_EMPTY(acc), acc_phase ^ 1);
+          nn_wait(FULL(stage), phase);
           tc_fence_after();
           const uint32_t sB_u = smem_u32(sB + stage * B_BYTES);
 #pragma unroll
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
       float run = INFINITY;
       uint32_t cnt = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait(T_FULL(acc), acc_phase);
+        nn_wait(T_FULL(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN + half * 128;
         // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is reduced
@@ -496,13 +504,17 @@ int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float*
   a.cand = cand; a.dbg_scores = dbg_scores; a.approx_min = approx_min;
   const long long items = (long long)n_jobs * ((n_q + TM - 1) / TM);
   const int grid = (int)(items < sm_count() ? items : sm_count());
+  ktime_begin("nn_sweep_kernel", st);
   nn_sweep_kernel<<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
+  ktime_end("nn_sweep_kernel", st);
   LMPCR_TRY(check_launch("nn_sweep_kernel"));
+  ktime_begin("nn_rescore_kernel", st);
   const long long warps = (long long)n_jobs * n_q;
   const long long max_blocks = (long long)LMPCR_RESCORE_BLOCKS * sm_count();            // resident blocks of 8 persistent warps per SM
   const long long want_blocks = (warps + 7) / 8;
   nn_rescore_kernel<<<(unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks), 256, 0, st>>>(q_feat, PQ.sqn, n_q, PQ.rows_pad, PB.feat_t, PB.sqn, n_b, PB.rows_pad, jobs,
                                                                          n_jobs, cand, unsupported, idx_out, dist_out);
+  ktime_end("nn_rescore_kernel", st);
   return check_launch("nn_rescore_kernel");
 }
 

@@ -602,8 +602,10 @@ int launch_pcn_stack(const float* x_in, long long in_batch, float* x_out, long l
   const int grid = a.P < sm_count() ? a.P : sm_count();
   PcnArgs b = a;
   b.debug = getenv("LMPCR_PCN_DEBUG") ? atoi(getenv("LMPCR_PCN_DEBUG")) : 0;      // timing experiments only
+  ktime_begin("pcn_stack_kernel", st);
   if (b.debug) pcn_stack_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_out, b);
   else pcn_stack_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_out, b);
+  ktime_end("pcn_stack_kernel", st);
   return check_launch("pcn_stack_kernel");
 }
 

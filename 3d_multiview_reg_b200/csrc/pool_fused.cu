@@ -527,8 +527,11 @@ int launch_pool_fused(const float* x, long long x_batch, const PoolFusedArgs& a,
   b.debug = getenv("LMPCR_POOL_DEBUG") ? atoi(getenv("LMPCR_POOL_DEBUG")) : 0;      // timing experiments only
   auto launch = [&](int mode) -> int {
     b.mode = mode;
+    const char* tname = mode == POOL_FALLBACK ? "pool_fused_kernel(fallback)" : "pool_fused_kernel";
+    ktime_begin(tname, st);
     if (b.debug) pool_fused_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, b, np, rpp);
     else pool_fused_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, b, np, rpp);
+    ktime_end(tname, st);
     return check_launch("pool_fused_kernel");
   };
   if (!a.flags) return launch(POOL_TWO_PASS);

@@ -183,9 +183,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
   // the lean producer loop (see the producer warps below) hands a stage over with four warp arrivals instead of eight
   const bool lean_shape = a_blob && !b_blob && !(g.debug & 512) && ((reinterpret_cast<uintptr_t>(g.B) & 31) == 0) && ((g.b_ld & 7) == 0) &&
                           ((g.b_batch & 7) == 0);
-  const bool lean = lean_shape && (B_KMAJOR ? (g.prologue == TC_PRO_SOFTMAX_DEFER && (g.K & 7) == 0)
+  // b_pad_ok: every row of B is readable (and, along K, finite) up to the next multiple of 8 elements, so whole 8-element groups can be
+  // fetched although N (j-major) / K (k-major) is not a multiple of 8 -- the 500-cluster matrices of the network, stored 504 apart
+  const bool kmaj_affine = g.prologue == TC_PRO_AFFINE_RELU && g.p_batch == 0 && ((reinterpret_cast<uintptr_t>(g.p0) | reinterpret_cast<uintptr_t>(g.p1)) & 31) == 0;
+  const bool lean = lean_shape && (B_KMAJOR ? ((g.prologue == TC_PRO_SOFTMAX_DEFER || kmaj_affine) && ((g.K & 7) == 0 || g.b_pad_ok))
                                             : ((g.prologue == TC_PRO_NONE || g.prologue == TC_PRO_AFFINE_RELU || g.prologue == TC_PRO_SOFTMAX_DEFER) &&
-                                               (g.N & 7) == 0 && (g.prologue != TC_PRO_SOFTMAX_DEFER || ((reinterpret_cast<uintptr_t>(g.p0) & 31) == 0 && (g.p_batch & 7) == 0))));
+                                               ((g.N & 7) == 0 || g.b_pad_ok) && (g.prologue != TC_PRO_SOFTMAX_DEFER || ((reinterpret_cast<uintptr_t>(g.p0) & 31) == 0 && (g.p_batch & 7) == 0))));
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), b_blob ? 1 : (lean ? N_PROD_WARPS / 2 : N_PROD_WARPS) + (a_blob ? 1 : 0)); mbar_init(EMPTY(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(T_FULL(a), 1); mbar_init(T_EMPTY(a), 128); }
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
         valid1 = f_ok1 && (kb + (B_KMAJOR ? col_l : row_l + ROW_U) < g.K);
         if (valid0) ldg256(f_src, x0);
         if (valid1) ldg256(f_src + ustride, x1);
-        if (affine) {
+        if (affine && !B_KMAJOR) {
           const long long dq = g.p1 - g.p0;
           if (valid0) { sc0 = __ldg(f_q); sh0 = __ldg(f_q + dq); }
           if (valid1) { sc1 = __ldg(f_q + ROW_U); sh1 = __ldg(f_q + ROW_U + dq); }
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
         const unsigned t_old = f_tile;
         advance(f_tile, f_kc);
         if (f_tile != t_old) { if (f_tile < nt32) f_setup(); }
-        else { f_src += cstride2; if (affine) f_q += 2 * KC; }
+        else { f_src += cstride2; if (affine && !B_KMAJOR) f_q += 2 * KC; }
       };
       if (f_tile < nt32) f_setup();
       fetch();
@@ -447,6 +450,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) tcgemm_kernel(TcGemmArgs g, int b
             if (valid1) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) { x1[e] = exp2f_fast(fmaf(x1[e], LOG2E, -mm[e])); zacc[e] += x1[e]; }
+            }
+          }
+        } else if (affine && B_KMAJOR) {
+          // per-k constants shared by all pairs (p_batch == 0: BatchNorm over the cluster axis, oanet.py:73): 8 consecutive k per lane,
+          // fetched here (L1 hits) instead of being carried in registers across the pipeline wait
+          const int k0 = kc * KC + col_l;
+          if (k0 < g.K) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(g.p0 + k0)), s1 = __ldg(reinterpret_cast<const float4*>(g.p0 + k0) + 1);
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(g.p1 + k0)), t1 = __ldg(reinterpret_cast<const float4*>(g.p1 + k0) + 1);
+            const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            const int nvk = g.K - k0;                    // < 8 only in the last group of a padded row: the tail must not reach the MMA
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              x0[e] = (e < nvk) ? fmaxf(fmaf(x0[e], ss[e], tt[e]), 0.f) : 0.f;
+              x1[e] = (e < nvk) ? fmaxf(fmaf(x1[e], ss[e], tt[e]), 0.f) : 0.f;
             }
           }
         } else if (affine) {

@@ -24,6 +24,7 @@ struct TcGemmArgs {
   // B: fp32; b_kmajor = 0: B[p,k,j] at B + p*b_batch + k*b_ld + j (j contiguous)
   //          b_kmajor = 1: B[p,k,j] at B + p*b_batch + j*b_ld + k (k contiguous)
   const float* B; long long b_batch; int b_ld; int b_kmajor;
+  int b_pad_ok;   // rows of B are readable up to the next multiple of 8 elements (k-major: and finite there): lets N / K that are not multiples of 8 take the lean producer loop
   // ... or an already converted B (launch_convert_b): per (batch, n-tile, k-chunk) [hi 4 KB | lo 4 KB] in the UMMA j-major layout,
   // prologue already applied.  Both operands then arrive by TMA and the producer warps stay idle (used when M spans several
   // m-tiles, e.g. the 500-cluster embedding convs, so that the conversion is not repeated per m-tile).

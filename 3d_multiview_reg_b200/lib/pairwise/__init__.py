@@ -22,7 +22,7 @@ class PairwiseReg(nn.Module):
 
     def __init__(self, descriptor_module, filtering_module, device, samp_type="fps", corr_type="soft",
                  mutuals_flag=False, connectivity_info=None, tgt_num_points=2000,
-                 straight_through_gradient=True, train_descriptor=False):
+                 straight_through_gradient=True, train_descriptor=False, sampler_rng="device"):
         super().__init__()
         self.device = device
         self.samp_type = samp_type
@@ -32,7 +32,8 @@ class PairwiseReg(nn.Module):
         self.train_descriptor = train_descriptor
         self.descriptor_module = descriptor_module
         if self.descriptor_module:
-            self.sampler = Sampler(samp_type=self.samp_type, targeted_num_points=tgt_num_points)
+            # sampler_rng (not in the reference): 'device' = keypoints drawn on the GPU, 'numpy' = the reference's host stream
+            self.sampler = Sampler(samp_type=self.samp_type, targeted_num_points=tgt_num_points, rng=sampler_rng)
             self.feature_matching = Soft_NN(corr_type=self.corr_type, st=straight_through_gradient, device=device)
             self.precomputed_desc = False
         else:

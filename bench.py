@@ -299,7 +299,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    cabi.ktime_enable(True)          # CUDA event pairs around the dominant kernels' launches, on the launching stream, inside the timed region
     ms_step, stages = timed(step_resident, args.steps, with_timers=True)
+    ktimes = {k: cabi.ktime_read(k) for k in ("pcn_stack_kernel", "pool_fused_kernel", "nn_sweep_kernel", "nn_rescore_kernel")}
+    cabi.ktime_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     step_e2e()
     ms_e2e, _ = timed(step_e2e, max(1, args.steps))
@@ -311,7 +314,9 @@ def run_ours(args):
         filt_ms = stages["filter"]
         nn_tf = n_mine * NN_FLOP_PER_PAIR(n, 32) / (nn_ms * 1e-3) / 1e12
         filt_tf = n_mine * FILTER_FLOP_PER_PAIR(n) / (filt_ms * 1e-3) / 1e12
-        dom = dominant_kernel_roofline(cabi, dev, n if n <= 8192 else 5000, pk)
+        dom = live_pcn_roofline(ktimes["pcn_stack_kernel"], n_mine, n, args.steps, pk)
+        if dom is None:              # the pair-resident kernels did not run (point count / group size outside their range): the per-layer GEMM instead
+            dom = tcgemm_roofline(cabi, dev, n if n <= 8192 else 5000, pk)
         if args.workload == "dense50k":
             workload = "configs[2]: dense keypoints, %d scans -> %d pairs x %d keypoints x 32-d" % (S, pairs_total, n)
         elif strong:
@@ -327,16 +332,19 @@ def run_ours(args):
                        "nn_algo": "tcgen05+rescore" if args.nn_algo == 1 else "exact_simt", "gemm_algo": "tcgen05 split-bf16" if args.gemm_algo == 1 else "fp32 simt",
                        "pair_chunk": args.pair_chunk, "arithmetic": "results in f32; NN screening fp16 operands -> f32 TMEM accumulators + exact f32 rescoring; GEMMs split-bf16 (hi+lo) -> f32", "l2": "256 MiB flush buffer written between timed iterations",
                        "parallelism": "pairs x%d" % world},
-            # dominant kernel family = the fused 1x1-conv layers of the network: the per-layer tcgemm_kernel instance (128->128 with residual,
-            # 148 pairs) timed alone, live, with CUDA events; the pair-resident PointCN stack that replaces most of these layers is
-            # reported beside it (roofline_pcn)
+            # dominant kernel = pcn_stack_kernel (the pair-resident PointCN stacks, ~23 % of a step): every launch inside the timed steps
+            # is bracketed by a CUDA event pair on the launching stream (lmpcr_debug_ktime_*); the per-layer GEMM it replaced is timed
+            # alone beside it (roofline_tcgemm), the fused diff_pool kernel live like the dominant one (roofline_pool_fused)
             "roofline": dom,
-            "roofline_pcn": pcn_roofline(cabi, dev, n if n <= 8192 else 5000, pk),
+            "roofline_tcgemm": tcgemm_roofline(cabi, dev, n if n <= 8192 else 5000, pk),
+            "roofline_pool_fused": live_pool_roofline(ktimes["pool_fused_kernel"], n_mine, n, args.steps, pk),
             "roofline_filter_stage": {"bound": "tensor", "achieved": filt_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": filt_tf / pk["tf_sustained"],
                                       "algorithmic_flop_per_pair": FILTER_FLOP_PER_PAIR(n), "ms_per_step": filt_ms, "peak_source": pk["src"] + " bf16 sustained"},
             "roofline_nn": {"bound": "tensor", "achieved": nn_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": nn_tf / pk["tf_sustained"],
                             "frac_of_burst": nn_tf / pk["tf_burst"], "traffic": None, "kernel": "nn stage (both directions)",
-                            "algorithmic_flop_per_pair": NN_FLOP_PER_PAIR(n, 32), "ms_per_step": nn_ms, "peak_source": pk["src"] + " bf16 sustained"},
+                            "algorithmic_flop_per_pair": NN_FLOP_PER_PAIR(n, 32), "ms_per_step": nn_ms, "peak_source": pk["src"] + " bf16 sustained",
+                            "sweep_ms_per_step": ktimes["nn_sweep_kernel"][1] / args.steps, "rescore_ms_per_step": ktimes["nn_rescore_kernel"][1] / args.steps,
+                            "sweep_frac_of_sustained": (n_mine * NN_FLOP_PER_PAIR(n, 32) / max(ktimes["nn_sweep_kernel"][1] / args.steps, 1e-9) / 1e9) / pk["tf_sustained"]},
             "stages_ms": stages,
             "us_per_pair": {"nn": 1e3 * nn_ms / max(n_mine, 1), "filter": 1e3 * filt_ms / max(n_mine, 1), "total": 1e3 * ms_step / max(n_mine, 1)},
             "e2e": {"value": pairs_total / (ms_e2e * 1e-3), "unit": UNIT,
@@ -363,41 +371,49 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def pcn_roofline(cabi, dev, n, pk, P=148, C=128, layers=2, iters=6):
-    """The pair-resident PointCN stack (pcn_stack_kernel) alone: `layers` layers over P pairs per launch; algorithmic bytes per layer =
-    3 passes (statistics pass reads x, main pass reads x and writes the output) x P*C*n*4."""
-    import torch
-    g = torch.Generator(device="cpu").manual_seed(7)
-    def lp():
-        bn = lambda: [torch.rand(C, generator=g) + 0.5, 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5]
-        w = lambda: torch.randn(C, C, generator=g) / C ** 0.5
-        return [t.to(dev) for t in bn() + [w(), 0.1 * torch.randn(C, generator=g)] + bn() + [w(), 0.1 * torch.randn(C, generator=g)]]
-    lps = [lp() for _ in range(layers)]
-    bufs = [(torch.randn(P, C, n, device=dev), torch.empty(P, C, n, device=dev)) for _ in range(3)]
-    for x, o in bufs:
-        cabi.pointcn_stack(x, lps, out=o)
-    torch.cuda.synchronize()
-    n0 = cabi.launch_count_named("pcn_stack_kernel")
-    evs = []
-    for i in range(iters):
-        x, o = bufs[i % 3]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        cabi.pointcn_stack(x, lps, out=o)
-        e1.record()
-        evs.append((e0, e1))
-    torch.cuda.synchronize()
-    # the call also runs the weight packing and a two-pass statistics kernel over the input (~3 more passes): subtract nothing, say so
-    ms = float(np.mean([a.elapsed_time(b_) for a, b_ in evs]))
-    byts = 3.0 * layers * P * C * n * 4
-    del bufs
-    return {"bound": "hbm", "achieved": byts / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": byts / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-            "traffic": None, "kernel": "pcn_stack_kernel (%d fused PointCN layers, %d pairs x %d pts) incl. its input-statistics pre-pass" % (layers, P, n),
-            "algorithmic_bytes_per_launch": byts, "ms_per_launch": ms, "launches": cabi.launch_count_named("pcn_stack_kernel") - n0,
-            "peak_source": pk["src"] + " hbm copy"}
+PCN_PASSES_PER_PAIR = 2 * (3 * 3 + (3 * 2 - 1))      # per pair: 2 blocks x (l1_1: 3 layers x 3 passes + l1_2 tail: 2 layers, the last one's tile is not stored)
 
 
-def dominant_kernel_roofline(cabi, dev, n, pk, P=148, C=128, sets=3, iters=12):
+def live_pcn_roofline(kt, pairs, n, steps, pk, C=128):
+    """pcn_stack_kernel as it ran inside the timed steps: kt = (launches, summed device milliseconds) from the event pairs around every
+    launch.  HBM-bound: a layer streams its pair three times (statistics pass reads x; main pass reads x and writes the output), so the
+    algorithmic bytes of a step are PCN_PASSES_PER_PAIR x pairs x C x n x 4 -- DESIGN.md 4.3.  `traffic` scales the ncu DRAM counters of
+    one captured launch (profiles/r2_traffic.json: bytes moved / algorithmic bytes of that launch) to the average launch."""
+    launches, ms = kt
+    if launches == 0:
+        return None
+    byts = float(PCN_PASSES_PER_PAIR) * pairs * C * n * 4 * steps
+    per_launch = byts / launches
+    ms_launch = ms / launches
+    gbs = byts / (ms * 1e-3) / 1e9
+    traffic, note = None, None
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp)).get("pcn_stack_kernel")
+        if t:
+            traffic = per_launch * t["dram_bytes"] / t["algorithmic_bytes"]
+            note = "ncu dram bytes / algorithmic bytes = %.3f on the captured launch (%s)" % (t["dram_bytes"] / t["algorithmic_bytes"], t["shape"])
+    return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": traffic, "traffic_note": note,
+            "kernel": "pcn_stack_kernel (pair-resident PointCN stacks: 3 fused layers after conv1, 2 + output head before the pose), timed live in the step",
+            "algorithmic_bytes_per_launch": per_launch, "ms_per_launch": ms_launch, "launches_per_step": launches / steps,
+            "ms_per_step": ms / steps, "peak_source": pk["src"] + " hbm copy"}
+
+
+def live_pool_roofline(kt, pairs, n, steps, pk, C=128, K=500):
+    """pool_fused_kernel (embedding conv + softmax + weighted sum of diff_pool) as it ran inside the timed steps.  Tensor-bound by its
+    own arithmetic: 2 GEMMs of 2*K*C*n FLOP per pair and block, each executed as three bf16 products."""
+    launches, ms = kt
+    if launches == 0:
+        return None
+    flop = 2.0 * (2.0 * K * C * n) * 2 * pairs * steps          # algorithmic: 2 GEMMs x 2 blocks per pair
+    tf = flop / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
+            "executed_frac": 3.0 * tf / pk["tf_sustained"], "kernel": "pool_fused_kernel, timed live in the step",
+            "ms_per_launch": ms / launches, "launches_per_step": launches / steps, "ms_per_step": ms / steps,
+            "note": "executed tensor work is 3x the algorithmic FLOPs (split-bf16: hi.hi + hi.lo + lo.hi)", "peak_source": pk["src"] + " bf16 sustained"}
+
+
+def tcgemm_roofline(cabi, dev, n, pk, P=148, C=128, sets=3, iters=12):
     """The fused conv layer (tcgemm_kernel) alone: out = W * relu(x*scale+shift) + bias + residual over P pairs.
     Buffer sets are rotated (3 x 1.1 GB, far larger than L2) so that every launch streams from HBM.
     Algorithmic bytes per launch: read x + read residual + write out = 3 * P*C*n*4 (+ weights);

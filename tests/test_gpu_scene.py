@@ -50,7 +50,7 @@ def test_pairwise_reg_module_surface():
     sd = O.synth_state_dict(5)
     net = load_oanet(sd)
     model = pw.PairwiseReg(descriptor_module=lambda d: d["feat_in"], filtering_module=net, device=torch.device("cuda"),
-                           samp_type="rand", corr_type="hard", tgt_num_points=n).eval()
+                           samp_type="rand", corr_type="hard", tgt_num_points=n, sampler_rng="numpy").eval()
     np.random.seed(41)
     data = {"pcd0": torch.from_numpy(xyz.reshape(-1, 3)), "feat_in": torch.from_numpy(feats.reshape(-1, 32)),
             "pts_list": torch.tensor([n] * S)}
@@ -64,6 +64,19 @@ def test_pairwise_reg_module_surface():
     fa, fb = feats[0][sel[0]], feats[1][sel[1]]
     i_st, _ = nn_c.nn_argmin(fa, fb)
     assert np.array_equal(xs[0, 0, :, :3], xyz[0][sel[0]]) and np.array_equal(xs[0, 0, :, 3:], xyz[1][sel[1]][i_st])
+    # default sampler: keypoints drawn on the device -- every sampled row is a row of its own scan, no repeats, correspondences
+    # consistent with the oracle on exactly those rows
+    model_d = pw.PairwiseReg(descriptor_module=lambda d: d["feat_in"], filtering_module=net, device=torch.device("cuda"),
+                             samp_type="rand", corr_type="hard", tgt_num_points=n).eval()
+    torch.manual_seed(9)
+    fin_d, _, _, out_d = model_d(data)
+    xd = fin_d["xs"].cpu().numpy()
+    rows = {tuple(r): i for i, r in enumerate(xyz[0])}
+    sel0 = np.array([rows[tuple(r)] for r in xd[0, 0, :, :3]])
+    assert len(np.unique(sel0)) == n and not np.array_equal(sel0, np.arange(n))
+    rows1 = {tuple(r): i for i, r in enumerate(xyz[1])}
+    assert all(tuple(r) in rows1 for r in xd[0, 0, :, 3:])
+    assert tuple(out_d["rot_est"][-1].shape) == (3, 3, 3)
     # precomputed mode passes the dict straight through (lib/pairwise/__init__.py:122-125)
     m2 = pw.PairwiseReg(None, net, torch.device("cuda"))
     d, a, b = m2.compute_descriptors({"xs": filt_in["xs"]})
@@ -79,7 +92,7 @@ def test_pairwise_reg_demo_config_soft_correspondences():
     net = load_oanet(sd)
     model = pw.PairwiseReg(descriptor_module=lambda d: d["feat_in"], filtering_module=net, device=torch.device("cuda"),
                            samp_type="rand", corr_type="soft", mutuals_flag=True, tgt_num_points=n,
-                           straight_through_gradient=False).eval().cuda()
+                           straight_through_gradient=False, sampler_rng="numpy").eval().cuda()
     np.random.seed(41)
     data = {"pcd0": torch.from_numpy(xyz.reshape(-1, 3)), "feat_in": torch.from_numpy(feats.reshape(-1, 32)), "pts_list": torch.tensor([n] * S)}
     filt_in, F0, F1, out = model(data)
