@@ -20,6 +20,7 @@
 // The N x M matrix never exists in memory; HBM traffic per pair is the operands (2 x 0.5 MB, L2-resident per scene).
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -35,7 +36,12 @@ constexpr int TN = 256;                // target rows per tile   (UMMA N)
 constexpr int STAGES = 4;              // TMA ring depth for target tiles
 constexpr int CHUNK = 32;              // columns per bookkeeping chunk (= one tcgen05.ld.32x32b.x32)
 constexpr int CAP = 16;                // ring of candidate chunks per (row, column half)
-constexpr int EPI_THREADS = 256;
+constexpr int SET_THREADS = 256;       // one epilogue set: 8 warps, thread = (row, column half)
+constexpr int N_SETS = 2;              // a work item is TWO query stripes (256 rows): every target tile that arrives in shared memory feeds two MMAs, one per
+                                       // stripe, each with its own 256-column accumulator and its own set of 8 epilogue warps.  The sweep was bound by
+                                       // the L2 -> SM traffic of the target tiles (24 KB per 128 x 256 tile: 8.9 TB/s over 148 SMs, measured with the
+                                       // epilogue switched off, LMPCR_NN_DEBUG=2); two stripes per tile halve it
+constexpr int EPI_THREADS = N_SETS * SET_THREADS;
 constexpr int NTHREADS = 128 + EPI_THREADS;
 constexpr int A_BYTES = TM * KP * 2;   // 12288
 constexpr int B_BYTES = TN * KP * 2;   // 24576
@@ -147,15 +153,19 @@ struct SweepArgs {
   uint2* cand;             // [n_jobs, n_q, 2]  packed candidate chunks per (row, column half)
   float* dbg_scores;       // optional [n_jobs, n_q, rows_pad_b] raw screening scores (tests)
   float* approx_min;       // optional [n_jobs, n_q]
+  int debug;               // timing experiments only (LMPCR_NN_DEBUG): 1 = epilogue reads the accumulators but skips the minima, 2 = skips the reads too
 };
 
+// DBG: the instantiation that can store the raw scores (tests) and run the timing experiments; the production instantiation carries neither
+// (the address arithmetic of the score dump alone was 9 % of the epilogue's instructions although the dump was off)
+template <bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
-  uint8_t* sB = smem + A_BYTES;
+  uint8_t* sB = smem + N_SETS * A_BYTES;
   uint2* ring = reinterpret_cast<uint2*>(sB + STAGES * B_BYTES);            // [CAP][EPI_THREADS]
-  float* rowmin = reinterpret_cast<float*>(ring + CAP * EPI_THREADS);       // [2][TM]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rowmin + 2 * TM);
+  float* rowmin = reinterpret_cast<float*>(ring + CAP * EPI_THREADS);       // [N_SETS][2][TM]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowmin + N_SETS * 2 * TM);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const uint32_t bar0 = smem_u32(bars);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -165,14 +175,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
   auto T_EMPTY = [&](int a) { return bar0 + 8u * (2 * STAGES + 4 + a); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_stripes = (g.n_q + TM - 1) / TM;
+  const int n_stripes = (g.n_q + N_SETS * TM - 1) / (N_SETS * TM);       // stripe PAIRS (rows_pad_q is a multiple of 256: the second stripe always exists)
   const int n_tiles = g.rows_pad_b / TN;
   const long long n_items = (long long)g.n_jobs * n_stripes;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
     mbar_init(A_FULL, 1); mbar_init(A_EMPTY, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(T_FULL(a), 1); mbar_init(T_EMPTY(a), EPI_THREADS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(T_FULL(a), 1); mbar_init(T_EMPTY(a), SET_THREADS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM: all 512 columns = two 256-column accumulator stages
@@ -191,8 +201,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
         const int job = (int)(item / n_stripes), stripe = (int)(item - (long long)job * n_stripes);
         const int qs = __ldg(g.jobs + 2 * job), bs = __ldg(g.jobs + 2 * job + 1);
         nn_wait(A_EMPTY, a_phase ^ 1);
-        mbar_expect_tx(A_FULL, A_BYTES);
-        bulk_g2s(smem_u32(sA), g.form_q + ((size_t)qs * g.rows_pad_q + (size_t)stripe * TM) / 8 * RG_BYTES, A_BYTES, A_FULL);
+        mbar_expect_tx(A_FULL, N_SETS * A_BYTES);
+        bulk_g2s(smem_u32(sA), g.form_q + ((size_t)qs * g.rows_pad_q + (size_t)stripe * N_SETS * TM) / 8 * RG_BYTES, N_SETS * A_BYTES, A_FULL);
         const uint8_t* bsrc = g.form_b + (size_t)bs * g.rows_pad_b / 8 * RG_BYTES;
         for (int t = 0; t < n_tiles; ++t) {
           nn_wait(EMPTY(stage), phase ^ 1);
@@ -206,39 +216,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      int stage = 0, acc = 0; uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+      int stage = 0; uint32_t phase = 0, acc_phase = 0, a_phase = 0;
       const uint32_t sA_u = smem_u32(sA);
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         nn_wait(A_FULL, a_phase);
         for (int t = 0; t < n_tiles; ++t) {
-          nn_wait(T_EMPTY(acc), acc_phase ^ 1);
           nn_wait(FULL(stage), phase);
-          tc_fence_after();
           const uint32_t sB_u = smem_u32(sB + stage * B_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < KP / 16; ++kk)   // one K=16 step = two core matrices = 256 B further along K
-            tc_mma_f16(tmem_base + acc * TN, make_desc(sA_u + kk * 256, 128, RG_BYTES), make_desc(sB_u + kk * 256, 128, RG_BYTES),
-                       IDESC, kk > 0 ? 1u : 0u);
+          for (int st = 0; st < N_SETS; ++st) {          // the same target tile against both query stripes
+            nn_wait(T_EMPTY(st), acc_phase ^ 1);         // set st has read the previous tile out of its accumulator
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < KP / 16; ++kk)         // one K=16 step = two core matrices = 256 B further along K
+              tc_mma_f16(tmem_base + st * TN, make_desc(sA_u + st * A_BYTES + kk * 256, 128, RG_BYTES), make_desc(sB_u + kk * 256, 128, RG_BYTES),
+                         IDESC, kk > 0 ? 1u : 0u);
+            tc_commit(T_FULL(st));                       // accumulator complete
+          }
           tc_commit(EMPTY(stage));     // smem slot reusable once these MMAs have read it
-          tc_commit(T_FULL(acc));      // accumulator complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          acc ^= 1; if (acc == 0) acc_phase ^= 1;
+          acc_phase ^= 1;
         }
         tc_commit(A_EMPTY);
         a_phase ^= 1;
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: 8 warps, thread = (row, column half) =====================
-    const int te = threadIdx.x - 128;
-    const int half = te >> 7;                 // 0: columns 0..127 of a tile, 1: columns 128..255
+    // ===================== epilogue: two sets of 8 warps, thread = (set = query stripe of the pair, row, column half) =====================
+    const int te = threadIdx.x - 128;         // ring column
+    const int set = te >> 8;
+    const int half = (te >> 7) & 1;           // 0: columns 0..127 of a tile, 1: columns 128..255
     const int quarter = warp & 3;             // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;
-    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t uses = 0;                        // completed uses of this set's accumulator
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int job = (int)(item / n_stripes), stripe = (int)(item - (long long)job * n_stripes);
       const int qs = __ldg(g.jobs + 2 * job), bs = __ldg(g.jobs + 2 * job + 1);
-      const int grow = stripe * TM + row;
+      const int grow = (stripe * N_SETS + set) * TM + row;
       float margin = 0.f;
       if (grow < g.n_q) {
         const RowStat rs = g.rstat_q[(size_t)qs * g.rows_pad_q + grow];
@@ -249,13 +263,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
       float run = INFINITY;
       uint32_t cnt = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        nn_wait(T_FULL(acc), acc_phase);
+        nn_wait(T_FULL(set), uses & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TN + half * 128;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + set * TN + half * 128;
         // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is reduced
         uint32_t va[32], vb[32];
         auto reduce_chunk = [&](const uint32_t (&cur)[32], int c) {
-          if (g.dbg_scores && grow < g.n_q) {
+          if (DBG && g.dbg_scores && grow < g.n_q) {
             float* o = g.dbg_scores + ((size_t)job * g.n_q + grow) * g.rows_pad_b + (size_t)t * TN + half * 128 + c * CHUNK;
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(cur[i]);
@@ -277,6 +291,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
             ++cnt;
           }
         };
+        if (DBG && g.debug) {   // timing experiments: results are meaningless in these modes
+          if (g.debug == 1) {
+            tc_ld32_issue(taddr, va); tc_ld32_issue(taddr + CHUNK, vb); tc_ld_wait();
+            run = fminf(run, __uint_as_float(va[0] ^ vb[31]));
+            tc_ld32_issue(taddr + 2 * CHUNK, va); tc_ld32_issue(taddr + 3 * CHUNK, vb); tc_ld_wait();
+            run = fminf(run, __uint_as_float(va[0] ^ vb[31]));
+          }
+          tc_fence_before();
+          mbar_arrive(T_EMPTY(set));
+          ++uses;
+          continue;
+        }
         tc_ld32_issue(taddr, va);
         tc_ld_wait();
         tc_ld32_issue(taddr + CHUNK, vb);
@@ -290,18 +316,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
         tc_ld_wait();
         reduce_chunk(vb, 3);
         tc_fence_before();
-        mbar_arrive(T_EMPTY(acc));
-        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        mbar_arrive(T_EMPTY(set));
+        ++uses;
       }
-      // combine the two column halves of every row, then keep the chunks within `margin` of the row minimum
-      rowmin[half * TM + row] = run;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float fin = fminf(rowmin[row], rowmin[TM + row]);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // combine the two column halves of every row (the 256 threads of this set), then keep the chunks within `margin` of the row minimum
+      rowmin[(set * 2 + half) * TM + row] = run;
+      if (set == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float fin = fminf(rowmin[(set * 2) * TM + row], rowmin[(set * 2 + 1) * TM + row]);
+      if (set == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
+      uint32_t ids[3] = {0, 0, 0}, k = 0;
+      bool over = cnt > CAP;
       if (grow < g.n_q) {
         const float thr = fin + margin;
-        uint32_t ids[3] = {0, 0, 0}, k = 0;
-        bool over = cnt > CAP;
         if (!over) {
           for (uint32_t e = 0; e < cnt; ++e) {
             const uint2 en = ring[e * EPI_THREADS + te];
@@ -312,6 +338,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
           }
           over = k > 3;
         }
+      }
+      if (grow < g.n_q) {
         const uint32_t c16 = over ? OVERFLOW : k;
         g.cand[((size_t)job * g.n_q + grow) * 2 + half] = make_uint2(c16 | (ids[0] << 16), ids[1] | (ids[2] << 16));
         if (g.approx_min && half == 0) g.approx_min[(size_t)job * g.n_q + grow] = fin;
@@ -457,7 +485,7 @@ int run_prep(const float* feat, int n_sets, int n, const Prep& P, int* unsupport
   return check_launch("nn_prep_kernel");
 }
 
-constexpr size_t SWEEP_SMEM = A_BYTES + (size_t)STAGES * B_BYTES + (size_t)CAP * EPI_THREADS * 8 + 2 * TM * 4 + 16 * 8 + 16;
+constexpr size_t SWEEP_SMEM = (size_t)N_SETS * A_BYTES + (size_t)STAGES * B_BYTES + (size_t)CAP * EPI_THREADS * 8 + (size_t)N_SETS * 2 * TM * 4 + 16 * 8 + 16;
 
 }  // namespace
 
@@ -493,7 +521,8 @@ int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float*
     static unsigned char attr_set[64];
     const int dev = device_ordinal();
     if (!attr_set[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(nn_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
+      cudaError_t e = cudaFuncSetAttribute(nn_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
       LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "nn_sweep_kernel: cannot reserve %zu bytes of shared memory: %s", SWEEP_SMEM, cudaGetErrorString(e));
       attr_set[dev] = 1;
     }
@@ -502,10 +531,12 @@ int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float*
   a.form_q = PQ.form_q; a.form_b = PB.form_b; a.rstat_q = PQ.rstat; a.set_bmax = PB.bmax; a.set_dbmax = PB.dbmax;
   a.jobs = jobs; a.n_jobs = n_jobs; a.n_q = n_q; a.rows_pad_q = PQ.rows_pad; a.n_b = n_b; a.rows_pad_b = PB.rows_pad;
   a.cand = cand; a.dbg_scores = dbg_scores; a.approx_min = approx_min;
-  const long long items = (long long)n_jobs * ((n_q + TM - 1) / TM);
+  a.debug = getenv("LMPCR_NN_DEBUG") ? atoi(getenv("LMPCR_NN_DEBUG")) : 0;
+  const long long items = (long long)n_jobs * ((n_q + 2 * TM - 1) / (2 * TM));
   const int grid = (int)(items < sm_count() ? items : sm_count());
   ktime_begin("nn_sweep_kernel", st);
-  nn_sweep_kernel<<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
+  if (a.dbg_scores || a.debug) nn_sweep_kernel<true><<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
+  else nn_sweep_kernel<false><<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
   ktime_end("nn_sweep_kernel", st);
   LMPCR_TRY(check_launch("nn_sweep_kernel"));
   ktime_begin("nn_rescore_kernel", st);

@@ -18,9 +18,16 @@ for _ in range(2):
     cabi.nn_argmin(f, f, jobs, algo=a.algo)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+cabi.ktime_enable(True)
 e0.record()
 for _ in range(a.iters):
     idx = cabi.nn_argmin(f, f, jobs, algo=a.algo)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
+kt = {k: cabi.ktime_read(k) for k in ("nn_sweep_kernel", "nn_rescore_kernel")}
+cabi.ktime_enable(False)
+if kt["nn_sweep_kernel"][0]:
+    tiles = 2.0 * a.pairs * ((a.points + 127) // 128) * ((a.points + 255) // 256) / 148
+    sw = kt["nn_sweep_kernel"][1] / kt["nn_sweep_kernel"][0]
+    print("  sweep %.3f ms per launch (%.0f ns per 128x256 tile and SM), rescore %.3f ms" % (sw, 1e6 * sw / tiles, kt["nn_rescore_kernel"][1] / max(kt["nn_rescore_kernel"][0], 1)))
 print("algo %d: %.3f ms per call, %.2f us/pair, %.1f TFLOP/s algorithmic" % (a.algo, ms, 1e3 * ms / a.pairs, a.pairs * 2.0 * a.points ** 2 * 32 / ms / 1e9))
