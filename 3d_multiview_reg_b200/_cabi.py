@@ -27,6 +27,7 @@ EXPORTS = [
     "lmpcr_pointcn_stack", "lmpcr_pointcn_stack_workspace_bytes",
     "lmpcr_sample_workspace_bytes", "lmpcr_sample_keypoints",
     "lmpcr_diff_pool_fused_workspace_bytes", "lmpcr_diff_pool_fused",
+    "lmpcr_embed_fused_workspace_bytes", "lmpcr_embed_fused",
 ]
 
 
@@ -96,6 +97,9 @@ def load():
     lib.lmpcr_pointcn_stack_workspace_bytes.restype = _sz
     lib.lmpcr_pointcn_stack_workspace_bytes.argtypes = [_i, _i]
     lib.lmpcr_pointcn_stack.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _sz, _vp]
+    lib.lmpcr_embed_fused_workspace_bytes.restype = _sz
+    lib.lmpcr_embed_fused_workspace_bytes.argtypes = [_i, _i, _i]
+    lib.lmpcr_embed_fused.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]
     lib.lmpcr_diff_pool_fused_workspace_bytes.restype = _sz
     lib.lmpcr_diff_pool_fused_workspace_bytes.argtypes = [_i, _i]
     lib.lmpcr_diff_pool_fused.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]
@@ -507,6 +511,22 @@ def diff_pool_fused(x, scale, shift, weight, mode=0):
         ws = _ws(lib.lmpcr_diff_pool_fused_workspace_bytes(P, K), x.device)
         _check(lib.lmpcr_diff_pool_fused(_p(x), P, N, _p(sc), _p(sh), _p(w), K, int(mode), _p(out), _p(ws), ws.numel(), _stream(x)))
     return out
+
+
+def embed_fused(x, scale, shift, weight, bias=None, want_colmax=False):
+    """The embedding conv of diff_unpool on the pair-resident kernel (lmpcr_embed_fused): x [P,128,N], scale / shift [P,128], weight [K,128],
+    bias [K] -> embed [P,K,N] (and colmax [P,N] = log2(e) * max over the clusters)."""
+    lib = load()
+    x, sc, sh, w = _dev(x, name="x"), _dev(scale, name="scale"), _dev(shift, name="shift"), _dev(weight, name="weight")
+    b = _dev(bias, name="bias") if bias is not None else None
+    P, C, N = x.shape
+    K = w.shape[0]
+    with torch.cuda.device(x.device):
+        E = torch.empty((P, K, N), dtype=torch.float32, device=x.device)
+        cm = torch.empty((P, N), dtype=torch.float32, device=x.device) if want_colmax else None
+        ws = _ws(lib.lmpcr_embed_fused_workspace_bytes(P, N, K), x.device)
+        _check(lib.lmpcr_embed_fused(_p(x), P, N, _p(sc), _p(sh), _p(w), _p(b), K, _p(E), _p(cm), _p(ws), ws.numel(), _stream(x)))
+    return (E, cm) if want_colmax else E
 
 
 def softmax_pool(x, embed, mode=1):

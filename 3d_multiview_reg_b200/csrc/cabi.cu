@@ -312,6 +312,29 @@ int lmpcr_diff_pool_fused(const float* x, int n_pairs, int n_pts, const float* s
   return launch_pool_fused(x, (long long)128 * n_pts, a, st);
 }
 
+size_t lmpcr_embed_fused_workspace_bytes(int n_pairs, int n_pts, int clusters) {
+  return align_up(pool_fused_weight_bytes(clusters), 256) + align_up((size_t)(n_pairs > 0 ? n_pairs : 1) * 4 * ((clusters + 127) / 128) * n_pts * 4, 256) + 256;
+}
+
+int lmpcr_embed_fused(const float* x, int n_pairs, int n_pts, const float* scale, const float* shift, const float* weight, const float* bias,
+                      int clusters, float* embed, float* colmax, void* workspace, size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  LMPCR_REQUIRE(x && scale && shift && weight && embed && n_pairs >= 0 && n_pts > 0 && clusters > 0, LMPCR_ERR_ARG, "lmpcr_embed_fused: bad arguments");
+  LMPCR_REQUIRE(workspace && workspace_bytes >= lmpcr_embed_fused_workspace_bytes(n_pairs, n_pts, clusters) && ((uintptr_t)workspace & 255) == 0,
+                LMPCR_ERR_WORKSPACE, "lmpcr_embed_fused: workspace too small or not 256-byte aligned");
+  if (n_pairs == 0) return LMPCR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* blob = reinterpret_cast<uint8_t*>(workspace);
+  float* slabs = reinterpret_cast<float*>(blob + align_up(pool_fused_weight_bytes(clusters), 256));
+  LMPCR_TRY(launch_pool_fused_pack_weights(weight, clusters, blob, st));
+  PoolFusedArgs a{};
+  a.w_blob = blob; a.scale = scale; a.shift = shift; a.bias = bias; a.colmax_slabs = colmax ? slabs : nullptr;
+  a.P = n_pairs; a.N = n_pts; a.K = clusters;
+  LMPCR_TRY(launch_embed_fused(x, (long long)128 * n_pts, embed, (long long)clusters * n_pts, a, st));
+  if (colmax) LMPCR_TRY(launch_colmax_from_slabs(slabs, 4 * ((clusters + 127) / 128), n_pairs, n_pts, colmax, st));
+  return LMPCR_OK;
+}
+
 int lmpcr_filter_num_params(const lmpcr_filter_cfg* cfg) {
   if (!cfg) return LMPCR_ERR_ARG;
   return filter_num_params(cfg);

@@ -641,7 +641,7 @@ size_t block_blob_bytes(int C, int K, int half) {
   b += (size_t)(half - 1) * 2 * tc_weight_blob_bytes(C, C);                       // l1_2.1..
   b += (size_t)half * (2 * tc_weight_blob_bytes(C, C) + tc_weight_blob_bytes(K, K));   // l2
   if (C == PCN_C) b += (size_t)(2 * half + 2 * (half - 1)) * pcn_weight_bytes();       // second image of the plain PointCN weights (pcn.cu)
-  if (C == PCN_C) b += pool_fused_weight_bytes(K);                                       // second image of the down embedding conv (pool_fused.cu)
+  if (C == PCN_C) b += 2 * pool_fused_weight_bytes(K);                                   // second image of the down / up embedding convs (pool_fused.cu)
   return align_up(b, 256);
 }
 
@@ -671,6 +671,9 @@ int block_blobs(BlockP& blk, int C, int K, int half, uint8_t* bp, bool do_split,
     for (int i = 1; i < half; ++i) { LMPCR_TRY(prep_rm(blk.l1_2[i].c1)); LMPCR_TRY(prep_rm(blk.l1_2[i].c2)); }
     blk.down_conv.blob_rm = bp;
     if (do_split) LMPCR_TRY(launch_pool_fused_pack_weights(blk.down_conv.w, K, bp, st));
+    bp += pool_fused_weight_bytes(K);
+    blk.up_conv.blob_rm = bp;
+    if (do_split) LMPCR_TRY(launch_pool_fused_pack_weights(blk.up_conv.w, K, bp, st));
     bp += pool_fused_weight_bytes(K);
   }
   return LMPCR_OK;
@@ -901,6 +904,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   static const int no_defer = getenv("LMPCR_NO_DEFER") ? atoi(getenv("LMPCR_NO_DEFER")) : 0;   // debug aid: softmax statistics by separate passes
   // read per call (two getenv look-ups) so that a test can switch paths inside one process
   const int pcn_on = getenv("LMPCR_PCN") ? atoi(getenv("LMPCR_PCN")) : 1;                       // 0: PointCN layers on the per-layer GEMM path (A/B runs)
+  const int embed_on = getenv("LMPCR_EMBED_FUSED") ? atoi(getenv("LMPCR_EMBED_FUSED")) : 1;       // 0: the `up` embedding conv as convert_b + GEMM (A/B runs)
   const int pool_on = getenv("LMPCR_POOL_FUSED") ? atoi(getenv("LMPCR_POOL_FUSED")) : 1;         // 0: diff_pool as embedding GEMM + pooling GEMM (A/B runs)
   const int pcn_min_pairs = getenv("LMPCR_PCN_MIN_PAIRS") ? atoi(getenv("LMPCR_PCN_MIN_PAIRS")) : 64;
   LMPCR_REQUIRE(n_params == filter_num_params(cfg), LMPCR_ERR_ARG, "lmpcr_filter_forward: expected %d parameter tensors, got %d", filter_num_params(cfg), n_params);
@@ -1232,12 +1236,25 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         float* t = xd_in; xd_in = xd_out; xd_out = t;
       }
       // diff_unpool (oanet.py:122-129): x_up -> upper half of the concat buffer
+      const bool defer_up = tc && (N & 3) == 0 && K >= TC_DEFER_MIN_K && !(no_defer & 2);
+      const bool use_embed_fused = embed_on && defer_up && !bn_train && g >= pcn_min_pairs && blk.up_conv.blob_rm && pool_fused_supported(C, K, N, x11, x11b);
+      if (use_embed_fused) {
+        // the embedding conv on the pair-resident kernel: weights in tensor memory, one pass over the pair's tiles, no operand conversion
+        // pass and no per-tile weight traffic; its readers emit the per-slab column maxima the softmax over the clusters needs
+        LMPCR_TRY(norm_affine(x11, x11b, C, N, g, 1e-3f, blk.up_bn));
+        PoolFusedArgs pa{};
+        pa.w_blob = blk.up_conv.blob_rm; pa.scale = W.scale; pa.shift = W.shift; pa.bias = blk.up_conv.b; pa.colmax_slabs = col_part;
+        pa.P = g; pa.N = N; pa.K = K;
+        LMPCR_TRY(launch_embed_fused(x11, x11b, W.E, (long long)K * N, pa, st));
+      } else {
       want_col = true;
       LMPCR_TRY(conv_norm(x11, x11b, C, N, g, 1e-3f, blk.up_bn, blk.up_conv, K, W.E, (long long)K * N, nullptr, 0));
       want_col = false;
+      }
       if (tc) {
-        const bool defer_up = (N & 3) == 0 && K >= TC_DEFER_MIN_K && !(no_defer & 2);
-        if (defer_up) {   // column maxima came fused out of the embedding conv's epilogue; the GEMM accumulates the sums itself
+        if (use_embed_fused) {
+          LMPCR_TRY(launch_colmax_from_slabs(col_part, 4 * ((K + 127) / 128), g, N, sm_max, st));
+        } else if (defer_up) {   // column maxima came fused out of the embedding conv's epilogue; the GEMM accumulates the sums itself
           colmax_from_partials_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(col_part, 4 * ((K + 127) / 128), tot, sm_max);
           LMPCR_TRY(check_launch("colmax_from_partials_kernel"));
         } else {

@@ -65,6 +65,34 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// maximum of every column of a 32 x 32 block held one row per lane (v[i] = element (lane, i)): lane l returns the maximum of column l.
+// Butterfly transpose-reduce: 31 shuffles + 31 maxima + the selects (the price of a reduction ACROSS tensor-memory lanes).
+__device__ __forceinline__ float warp_col_max(const float (&v)[32], int lane) {
+  float w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float mine = (lane & 16) ? v[i + 16] : v[i], send = (lane & 16) ? v[i] : v[i + 16];
+    w[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float mine = (lane & 8) ? w[i + 8] : w[i], send = (lane & 8) ? w[i] : w[i + 8];
+    w[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float mine = (lane & 4) ? w[i + 4] : w[i], send = (lane & 4) ? w[i] : w[i + 4];
+    w[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 4));
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float mine = (lane & 2) ? w[i + 2] : w[i], send = (lane & 2) ? w[i] : w[i + 2];
+    w[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 2));
+  }
+  const float mine = (lane & 1) ? w[1] : w[0], send = (lane & 1) ? w[0] : w[1];
+  return fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 1));
+}
+
 // cycle counters for timing experiments (LMPCR_POOL_DEBUG=1): lane 0 of the first warp of every role in CTA 0
 __device__ unsigned long long g_pool_prof[32];
 #define PROF(slot)                                                                      \
@@ -78,7 +106,7 @@ __device__ unsigned long long g_pool_prof[32];
 
 template <bool PROFILE>
 __global__ void __launch_bounds__(NTHREADS, 1)
-pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const PoolFusedArgs g, int n_parts, int rpp) {
+pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_e, const PoolFusedArgs g, int n_parts, int rpp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* red = reinterpret_cast<float*>(smem + OFF_RED);          // [2][128]: the two boxes' row maxima / row sums
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
@@ -219,7 +247,7 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const PoolFusedArgs
     }
     // ======================================================== pass A: approximate row maxima of E (not in the single-pass mode)
     float mx = -INFINITY;
-    if (g.mode != POOL_SINGLE) {
+    if (g.mode != POOL_SINGLE && g.mode != POOL_EMBED) {
     pass_begin();
     tc_fence_after();
     if (warp == 0) {
@@ -297,6 +325,22 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const PoolFusedArgs
     tc_fence_after();
     if (warp == 0) {
       if (lane == 0) loader(p, NX);
+    } else if (warp == 1 && g.mode == POOL_EMBED) {
+      for (int t = 0; t < n_tiles; ++t) {                // embedding conv only: one E tile per x tile, all three products
+        const int a = t & 1, ph = (t >> 1) & 1;
+        mbar_wait_fast(HFULL(a), ph);
+        mbar_wait_fast(EEMPTY(a), ph ^ 1);
+        tc_fence_after();
+        const uint32_t leader = elect_one();
+        issue_gemm1(sH + a * H_BYTES, tmE + a * TP, leader, true);
+        tc_commit_pred(HEMPTY(a), leader);
+        tc_commit_pred(EFULL(a), leader);
+        __syncwarp();
+      }
+      for (int b = 0; b < 2; ++b) {
+        const int uses = (n_tiles + 1 - b) >> 1;
+        if (uses > 0) mbar_wait_fast(HEMPTY(b), (uses - 1) & 1);
+      }
     } else if (warp == 1) {
       for (int t = 0; t <= n_tiles; ++t) {
         if (t < n_tiles) {
@@ -335,6 +379,42 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const PoolFusedArgs
         if (uses > 0) mbar_wait_fast(XBEMPTY(b), (uses - 1) & 1);
       }
       mbar_wait_fast(ACCFULL, 0);
+    } else if (warp < 10 && g.mode == POOL_EMBED) {
+      // E tile -> + bias -> (column maxima over this warp's 32 rows) -> staged in shared memory (the idle xb ring, SWIZZLE_128B rows) -> TMA store
+      const int sub = (warp >= 6) ? 1 : 0;
+      const bool valid_row = row < rows_valid;
+      const float bk = (valid_row && g.bias) ? __ldg(g.bias + q * rpp + row) : 0.f;
+      const bool t0 = (warp == 2 && lane == 0);          // the thread that issues the stores
+      const int n_slabs = 4 * n_parts;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int a = t & 1, ph = (t >> 1) & 1;
+        mbar_wait_fast(EFULL(a), ph);
+        tc_fence_after();
+        float v[TS];
+        tc_ld32(tmE + lane_sel + a * TP + sub * TS, v);
+        tc_fence_before();
+        mbar_arrive(EEMPTY(a));
+        const int ncv = g.N - t * TP - sub * TS;
+#pragma unroll
+        for (int i = 0; i < TS; ++i) v[i] += bk;
+        if (g.colmax_slabs) {
+          float m[TS];
+#pragma unroll
+          for (int i = 0; i < TS; ++i) m[i] = valid_row ? v[i] : -INFINITY;          // the zero-weight rows of the block are not clusters
+          const float cm = warp_col_max(m, lane);
+          if (lane < ncv) g.colmax_slabs[((size_t)p * n_slabs + q * 4 + (warp & 3)) * g.N + (size_t)t * TP + sub * TS + lane] = cm;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // staging buffer t % 3 is free: the store of tile t - 3 has read it (t0 waited below)
+        if (ncv > 0) store_x_row(smem + OFF_XB + (t % NXB) * H_BYTES + sub * XS_BYTES, row, v);
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the tile is staged
+        if (t0) {
+          for (int b = 0; b < n_boxes(t); ++b) tma_store_3d(&tm_e, sXB + (t % NXB) * H_BYTES + b * XS_BYTES, t * TP + b * TS, q * rpp, p);
+          bulk_commit();
+          bulk_wait_read<NXB - 1>();                     // at most two stores still reading: the buffer of tile t - 2 ... is free at the next barrier
+        }
+      }
+      if (t0) bulk_wait0();                              // the item's rows are in global memory
     } else if (warp < 10) {
       const int sub = (warp >= 6) ? 1 : 0;
       float negm = -mx * LOG2E;
@@ -416,7 +496,7 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const PoolFusedArgs
         mbar_wait_fast(XFULL(s), (t / NX) & 1);
         PROF(21);
         mbar_wait_fast(HEMPTY(b), ph ^ 1);
-        mbar_wait_fast(XBEMPTY(xb), ((t / NXB) & 1) ^ 1);
+        if (g.mode != POOL_EMBED) mbar_wait_fast(XBEMPTY(xb), ((t / NXB) & 1) ^ 1);
         PROF(22);
         float v[TS];
         if (g.N - t * TP - sub * TS > 0) {
@@ -425,7 +505,7 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const PoolFusedArgs
 #pragma unroll
           for (int i = 0; i < TS; ++i) v[i] = 0.f;           // box past the end of the pair: finite operand values (e is zero there)
         }
-        store_h_row(smem + OFF_XB + xb * H_BYTES, row, sub, v);
+        if (g.mode != POOL_EMBED) store_h_row(smem + OFF_XB + xb * H_BYTES, row, sub, v);       // raw tile: the pooling operand
         if (g.N - t * TP - sub * TS > 0) {
 #pragma unroll
           for (int i = 0; i < TS; ++i) v[i] = fmaxf(fmaf(v[i], sc, sh), 0.f);
@@ -525,12 +605,13 @@ int launch_pool_fused(const float* x, long long x_batch, const PoolFusedArgs& a,
   if (items < grid) grid = (int)items;
   PoolFusedArgs b = a;
   b.debug = getenv("LMPCR_POOL_DEBUG") ? atoi(getenv("LMPCR_POOL_DEBUG")) : 0;      // timing experiments only
+  const CUtensorMap tm_e = tm_in;                 // unused in the pooling modes
   auto launch = [&](int mode) -> int {
     b.mode = mode;
     const char* tname = mode == POOL_FALLBACK ? "pool_fused_kernel(fallback)" : "pool_fused_kernel";
     ktime_begin(tname, st);
-    if (b.debug) pool_fused_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, b, np, rpp);
-    else pool_fused_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, b, np, rpp);
+    if (b.debug) pool_fused_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_e, b, np, rpp);
+    else pool_fused_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_e, b, np, rpp);
     ktime_end(tname, st);
     return check_launch("pool_fused_kernel");
   };
@@ -540,6 +621,55 @@ int launch_pool_fused(const float* x, long long x_batch, const PoolFusedArgs& a,
   cudaMemsetAsync(a.flags, 0, (size_t)items * 4, st);
   LMPCR_TRY(launch(POOL_SINGLE));
   return launch(POOL_FALLBACK);
+}
+
+
+namespace {
+__global__ void colmax_from_slabs_kernel(const float* __restrict__ slabs, int n_slabs, int P, int N, float* __restrict__ cmax) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)P * N) return;
+  const int p = (int)(gid / N), n = (int)(gid - (size_t)p * N);
+  const float* q = slabs + (size_t)p * n_slabs * N + n;
+  float m = -INFINITY;
+  for (int t = 0; t < n_slabs; ++t) m = fmaxf(m, __ldg(q + (size_t)t * N));
+  cmax[gid] = m * LOG2E;
+}
+}  // namespace
+
+int launch_colmax_from_slabs(const float* slabs, int n_slabs, int P, int N, float* cmax, cudaStream_t st) {
+  const size_t tot = (size_t)P * N;
+  colmax_from_slabs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(slabs, n_slabs, P, N, cmax);
+  return check_launch("colmax_from_slabs_kernel");
+}
+
+int launch_embed_fused(const float* x, long long x_batch, float* E, long long e_batch, const PoolFusedArgs& a, cudaStream_t st) {
+  LMPCR_REQUIRE(x && E && a.w_blob && a.scale && a.shift && a.P > 0, LMPCR_ERR_ARG, "embed_fused: bad arguments");
+  LMPCR_REQUIRE(pool_fused_supported(C, a.K, a.N, x, x_batch) && (e_batch & 3) == 0 && ((reinterpret_cast<uintptr_t>(E) & 15) == 0), LMPCR_ERR_UNSUPPORTED,
+                "embed_fused: needs 128 channels, N %% 4 == 0, 16-byte aligned tensors and a driver with tensor maps");
+  const int np = parts_of(a.K), rpp = rows_per_part(a.K);
+  CUtensorMap tm_in, tm_e;
+  LMPCR_TRY(make_act_map(&tm_in, x, a.N, x_batch, a.P));
+  LMPCR_TRY(make_rows_map(&tm_e, E, a.N, a.K, e_batch, a.P, rpp));
+  {
+    static unsigned char attr_set[64];
+    const int dev = device_ordinal();
+    if (!attr_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(pool_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(pool_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "embed_fused: cannot reserve %zu bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
+      attr_set[dev] = 1;
+    }
+  }
+  const long long items = (long long)a.P * np;
+  int grid = sm_count() / np * np;
+  if (grid < np) grid = np;
+  if (items < grid) grid = (int)items;
+  PoolFusedArgs b = a;
+  b.mode = POOL_EMBED; b.flags = nullptr; b.debug = 0;
+  ktime_begin("embed_fused_kernel", st);
+  pool_fused_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_e, b, np, rpp);
+  ktime_end("embed_fused_kernel", st);
+  return check_launch("embed_fused_kernel");
 }
 
 }  // namespace lmpcr

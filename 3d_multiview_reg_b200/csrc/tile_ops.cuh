@@ -56,6 +56,8 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, i
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N_PENDING>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_PENDING) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // 32 fp32 values of one channel row (box `sub` of the tile) -> bf16 hi/lo in the MN-major operand image: channel-group (k>>3) at
@@ -123,6 +125,19 @@ int make_act_map(CUtensorMap* tm, const float* base, int N, long long batch, int
   return LMPCR_OK;
 }
 
+
+// fp32 matrices [P, rows, N] with batch stride `batch` floats -> 3-D tensor map (N, rows, P), box 32 columns x box_rows rows, SWIZZLE_128B
+int make_rows_map(CUtensorMap* tm, const float* base, int N, int rows, long long batch, int P, int box_rows) {
+  PFN_cuTensorMapEncodeTiled_v12000 fn = encode_fn();
+  LMPCR_REQUIRE(fn, LMPCR_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)rows, (cuuint64_t)P};
+  const cuuint64_t strides[2] = {(cuuint64_t)N * 4, (cuuint64_t)batch * 4};
+  const cuuint32_t box[3] = {TS, (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LMPCR_REQUIRE(r == CUDA_SUCCESS, LMPCR_ERR_LAUNCH, "cuTensorMapEncodeTiled failed (%d) for N=%d rows=%d batch=%lld P=%d box_rows=%d", (int)r, N, rows, batch, P, box_rows);
+  return LMPCR_OK;
+}
 
 }  // namespace
 }  // namespace lmpcr

@@ -278,6 +278,16 @@ size_t lmpcr_diff_pool_fused_workspace_bytes(int n_pairs, int clusters);
 int lmpcr_diff_pool_fused(const float* x, int n_pairs, int n_pts, const float* scale, const float* shift, const float* weight, int clusters,
                           int mode, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The embedding conv of diff_unpool (lib/filtering/oanet.py:113-125, `self.conv`) on the pair-resident machinery of
+ * lmpcr_diff_pool_fused (weights in tensor memory, one pass over the pair's tiles; csrc/pool_fused.cu, POOL_EMBED):
+ *   embed[p,k,n] = sum_c weight[k,c] * relu(x[p,c,n] * scale[p,c] + shift[p,c]) + bias[k]          embed [P,K,N] fp32
+ *   colmax[p,n]  = log2(e) * max_k embed[p,k,n]   (optional; the shift of the softmax over the clusters, in the form
+ *                  lmpcr_softmax_unpool's deferred mode consumes)
+ * x [P,128,N] (n_pts % 4 == 0, n_pts <= 8192), weight [K,128], bias [K] (may be NULL). */
+size_t lmpcr_embed_fused_workspace_bytes(int n_pairs, int n_pts, int clusters);
+int lmpcr_embed_fused(const float* x, int n_pairs, int n_pts, const float* scale, const float* shift, const float* weight, const float* bias,
+                      int clusters, float* embed, float* colmax, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of tensors of OANet(cfg).state_dict() excluding `num_batches_tracked` entries; `params` below is
  * a HOST array of that many DEVICE pointers (fp32, contiguous), in state_dict order. */
 int lmpcr_filter_num_params(const lmpcr_filter_cfg* cfg);

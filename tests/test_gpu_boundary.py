@@ -138,6 +138,7 @@ def test_grouping_invariance_at_bench_size():
         assert O.chordal_angle(one["R"][-1].cpu().numpy(), full["R"][-1][p:p + 1].cpu().numpy()).max() < 1e-3
     os.environ["LMPCR_PCN"] = "0"
     os.environ["LMPCR_POOL_FUSED"] = "0"
+    os.environ["LMPCR_EMBED_FUSED"] = "0"
     try:
         full_l = cabi.filter_forward(x, params, cfg, want_latent=False, packed=packed)
         for p in (0, 36, 73):
@@ -147,6 +148,7 @@ def test_grouping_invariance_at_bench_size():
     finally:
         del os.environ["LMPCR_PCN"]
         del os.environ["LMPCR_POOL_FUSED"]
+        del os.environ["LMPCR_EMBED_FUSED"]
     # the latent-feature variant of the pair-resident tail (tiles stored) gives the same logits as the on-chip variant
     lat = cabi.filter_forward(x, params, cfg, want_latent=True, packed=packed)
     assert torch.equal(lat["logits"], full["logits"]) and torch.equal(lat["R"], full["R"])

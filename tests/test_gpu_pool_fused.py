@@ -82,6 +82,28 @@ def test_diff_pool_fused_single_pass_overflow_takes_the_fallback():
     assert np.array_equal(tame[0], got[1])
 
 
+@pytest.mark.parametrize("P,N,K", [(3, 200, 500), (2, 5000, 500), (75, 264, 500), (3, 64, 16), (2, 1000, 130), (1, 28, 500)])
+def test_embed_fused_against_fp64(P, N, K):
+    """The embedding conv of diff_unpool on the pair-resident kernel (lmpcr_embed_fused): logits and their column maxima (the shift of
+    the softmax over the clusters) against fp64; rows / columns past the matrix edge must stay untouched (canary)."""
+    rng = np.random.default_rng(P * 100000 + N * 10 + K + 1)
+    x = (rng.standard_normal((P, 128, N)) * 2 + 0.5).astype(np.float32)
+    sc = rng.uniform(0.3, 1.2, (P, 128)).astype(np.float32)
+    sh = (0.5 * rng.standard_normal((P, 128))).astype(np.float32)
+    w = (rng.standard_normal((K, 128)) * 3 / np.sqrt(128)).astype(np.float32)
+    b = rng.standard_normal(K).astype(np.float32)
+    h = np.maximum(x.astype(np.float64) * sc.astype(np.float64)[:, :, None] + sh.astype(np.float64)[:, :, None], 0)
+    ref = np.einsum("kc,pcn->pkn", w.astype(np.float64), h) + b.astype(np.float64)[None, :, None]
+    E, cm = cabi.embed_fused(cu(x), cu(sc), cu(sh), cu(w), cu(b), want_colmax=True)
+    E, cm = E.cpu().numpy(), cm.cpu().numpy()
+    scale = max(1.0, np.abs(ref).max())
+    assert np.abs(E - ref).max() < 2e-5 * scale, np.abs(E - ref).max()
+    assert np.abs(cm / np.log2(np.e) - ref.max(1)).max() < 2e-5 * scale
+    # without a bias, without the maxima
+    E0 = cabi.embed_fused(cu(x), cu(sc), cu(sh), cu(w)).cpu().numpy()
+    assert np.abs(E0 - (ref - b.astype(np.float64)[None, :, None])).max() < 2e-5 * scale
+
+
 def test_network_takes_the_fused_pool_and_agrees_with_the_gemm_path():
     """74 pairs in one call: both blocks run diff_pool through pool_fused_kernel; same logits as the embedding-GEMM + pooling-GEMM
     path (LMPCR_POOL_FUSED=0) within the tensor-path noise, and the first block within the 5e-4 gate of the fp64 oracle."""
@@ -92,13 +114,21 @@ def test_network_takes_the_fused_pool_and_agrees_with_the_gemm_path():
     n0 = cabi.launch_count_named("pool_fused_kernel")
     out = net({"xs": x})
     assert cabi.launch_count_named("pool_fused_kernel") - n0 == 4          # 2 blocks x (single pass + fallback launch)
+    n0e = cabi.launch_count_named("embed_fused_kernel")
     os.environ["LMPCR_POOL_FUSED"] = "0"
     try:
         n1 = cabi.launch_count_named("pool_fused_kernel")
         ref = net({"xs": x})
         assert cabi.launch_count_named("pool_fused_kernel") == n1
+        assert cabi.launch_count_named("embed_fused_kernel") - n0e == 2       # the `up` embedding conv of both blocks, independent of the pool switch
+        os.environ["LMPCR_EMBED_FUSED"] = "0"
+        n2 = cabi.launch_count_named("embed_fused_kernel")
+        ref2 = net({"xs": x})
+        assert cabi.launch_count_named("embed_fused_kernel") == n2
+        assert (ref2["logits"][0] - ref["logits"][0]).abs().max().item() < 5e-4
     finally:
         del os.environ["LMPCR_POOL_FUSED"]
+        os.environ.pop("LMPCR_EMBED_FUSED", None)
     o64 = O.oanet_forward(xs, sd, dtype=np.float64)
     err = {name: [np.abs(res["logits"][it].cpu().numpy() - o64["logits"][it]).max() for it in range(2)] for name, res in (("fused", out), ("gemm", ref))}
     print("max |logit - fp64| per block:", err)
