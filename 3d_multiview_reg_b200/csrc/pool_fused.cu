@@ -21,6 +21,7 @@
 //   warps 2-9     TMEM readers: pass A maxima; pass B exp + split + tcgen05.st of the e tile; final read-out of the accumulator
 //                 (2-5 first box of a tile, 6-9 second box); thread = cluster row (TMEM lane) ((warp & 3) << 5) | lane
 //   warps 10-17   producers: x tile (smem, fp32) -> h and xb operand images (10-13 first box, 14-17 second); thread = channel
+//   warp 18       embedding-conv mode only: TMA stores of the staged output tiles
 #include <math.h>
 #include <stdlib.h>
 
@@ -34,16 +35,18 @@ constexpr int C = TILE_C;
 constexpr int NX = 2;                        // x-tile ring of pass B (tiles of NSUB boxes)
 constexpr int NXB = 3;                       // xb operand ring: an xb tile is held until the pooling MMAs of its tile have run, two tiles later than h
 constexpr int NXA = NX + NXB;                // x-tile ring of pass A: the idle xb buffers serve as x slots (short tiles: the loads must run far ahead)
+constexpr int NXE = NX + 1;                  // x-tile ring of the embedding-conv mode: the third xb buffer (two are enough to stage the output tiles)
+constexpr int NSTG = NXB - 1;                // staging buffers of the embedding-conv mode
 constexpr int PF_DIST = 3;                   // L2 prefetch distance in tiles
 constexpr int WP_BYTES = C * C * 2;          // one bf16 part of a 128 x 128 weight block, row-major [cluster][channel]: 32 KB
 constexpr int OFF_X = 0, OFF_H = OFF_X + NX * X_BYTES, OFF_XB = OFF_H + 2 * H_BYTES, OFF_RED = OFF_XB + NXB * H_BYTES;
 constexpr int OFF_BAR = OFF_RED + 2 * C * 4;
-constexpr int N_BARS = 2 * NXA + 16;
+constexpr int N_BARS = 2 * NXA + 16 + 2 * (NXB - 1);
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr size_t SMEM_BYTES = OFF_TMEM + 16;
 static_assert(X_BYTES == H_BYTES, "an xb buffer doubles as an x slot in pass A");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
-constexpr int NTHREADS = 18 * 32;
+constexpr int NTHREADS = 19 * 32;                // warp 18: TMA stores of the embedding-conv mode
 // Tensor memory (512 columns): weights (bf16 hi 64 | lo 64 columns, two elements per column), E tiles [2][64], e tiles [2][hi 32 | lo 32],
 // the pooling accumulator [128 cluster rows x 128 channels]
 constexpr int TMEM_COLS = 512;
@@ -122,7 +125,10 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   auto PFULL = [&](int a) { return barB + 88 + 8u * a; };
   auto PEMPTY = [&](int a) { return barB + 104 + 8u * a; };
   const uint32_t ACCFULL = barB + 120;
-  auto x_off = [&](int s) { return s < NX ? OFF_X + s * X_BYTES : OFF_XB + (s - NX) * H_BYTES; };      // byte offset of x slot s
+  auto STAGED = [&](int u) { return barB + 128 + 8u * u; };         // embedding-conv mode: output tile staged / staging buffer free
+  auto SFREE = [&](int u) { return barB + 128 + 8u * (NSTG + u); };
+  // byte offset of x slot s: the x ring proper, then xb buffers counted from the LAST one (the embedding-conv mode stages its output in the first two)
+  auto x_off = [&](int s) { return s < NX ? OFF_X + s * X_BYTES : OFF_XB + (NXB - 1 - (s - NX)) * H_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = ((warp & 3) << 5) | lane;                 // cluster row (readers) / channel (producers): the TMEM lane / tile row owned
@@ -150,6 +156,7 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         mbar_init(EFULL(a), 1); mbar_init(EEMPTY(a), 256); mbar_init(PFULL(a), 8); mbar_init(PEMPTY(a), 1);
       }
       mbar_init(ACCFULL, 1);
+      for (int u = 0; u < NSTG; ++u) { mbar_init(STAGED(u), 8); mbar_init(SFREE(u), 1); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -236,7 +243,7 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     const int p = (int)(item / n_parts), q = (int)(item - (long long)p * n_parts);
     const int rows_valid = min(rpp, g.K - q * rpp);           // cluster rows of this block (the rest of the 128 are zero weights)
     float sc = 1.f, sh = 0.f;
-    if (warp >= 10) { sc = __ldg(g.scale + (size_t)p * C + row); sh = __ldg(g.shift + (size_t)p * C + row); }
+    if (warp >= 10 && warp < 18) { sc = __ldg(g.scale + (size_t)p * C + row); sh = __ldg(g.shift + (size_t)p * C + row); }
     if (q != q_loaded) {
       if (warp >= 2 && warp < 6) {          // every MMA of the previous item has completed (pass_end)
         load_w_row(g.w_blob + (size_t)q * 2 * WP_BYTES);
@@ -295,7 +302,7 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mx = fmaxf(red[row], red[C + row]);
       asm volatile("bar.sync 1, 256;" ::: "memory");      // red is reused for the row sums
-    } else {
+    } else if (warp < 18) {
       const int sub = (warp >= 14) ? 1 : 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int s = t % NXA, b = t & 1;
@@ -323,13 +330,17 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     // ======================================================== pass B: e = exp(E - max), acc += e . x, Z += e
     pass_begin();
     tc_fence_after();
+    const int nxb = (g.mode == POOL_EMBED) ? NXE : NX;     // x ring depth of this pass
     if (warp == 0) {
-      if (lane == 0) loader(p, NX);
+      if (lane == 0) loader(p, nxb);
     } else if (warp == 1 && g.mode == POOL_EMBED) {
       for (int t = 0; t < n_tiles; ++t) {                // embedding conv only: one E tile per x tile, all three products
         const int a = t & 1, ph = (t >> 1) & 1;
+        PROF(24);                                        // 24: issue
         mbar_wait_fast(HFULL(a), ph);
+        PROF(25);                                        // 25: wait HFULL
         mbar_wait_fast(EEMPTY(a), ph ^ 1);
+        PROF(26);                                        // 26: wait EEMPTY
         tc_fence_after();
         const uint32_t leader = elect_one();
         issue_gemm1(sH + a * H_BYTES, tmE + a * TP, leader, true);
@@ -384,11 +395,12 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       const int sub = (warp >= 6) ? 1 : 0;
       const bool valid_row = row < rows_valid;
       const float bk = (valid_row && g.bias) ? __ldg(g.bias + q * rpp + row) : 0.f;
-      const bool t0 = (warp == 2 && lane == 0);          // the thread that issues the stores
       const int n_slabs = 4 * n_parts;
       for (int t = 0; t < n_tiles; ++t) {
         const int a = t & 1, ph = (t >> 1) & 1;
+        PROF(27);                                        // 27: TMA store issue + wait_read (t0's warp) / loop tail
         mbar_wait_fast(EFULL(a), ph);
+        PROF(28);                                        // 28: wait EFULL
         tc_fence_after();
         float v[TS];
         tc_ld32(tmE + lane_sel + a * TP + sub * TS, v);
@@ -404,17 +416,27 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           const float cm = warp_col_max(m, lane);
           if (lane < ncv) g.colmax_slabs[((size_t)p * n_slabs + q * 4 + (warp & 3)) * g.N + (size_t)t * TP + sub * TS + lane] = cm;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // staging buffer t % 3 is free: the store of tile t - 3 has read it (t0 waited below)
-        if (ncv > 0) store_x_row(smem + OFF_XB + (t % NXB) * H_BYTES + sub * XS_BYTES, row, v);
+        PROF(29);                                        // 29: ld + bias + column maxima
+        const int u = t % NSTG;
+        mbar_wait_fast(SFREE(u), ((t / NSTG) & 1) ^ 1);  // the store of tile t - 2 has read this staging buffer
+        PROF(30);                                        // 30: wait SFREE
+        if (ncv > 0) store_x_row(smem + OFF_XB + u * H_BYTES + sub * XS_BYTES, row, v);
         fence_proxy_async();
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // the tile is staged
-        if (t0) {
-          for (int b = 0; b < n_boxes(t); ++b) tma_store_3d(&tm_e, sXB + (t % NXB) * H_BYTES + b * XS_BYTES, t * TP + b * TS, q * rpp, p);
-          bulk_commit();
-          bulk_wait_read<NXB - 1>();                     // at most two stores still reading: the buffer of tile t - 2 ... is free at the next barrier
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(STAGED(u));
+        PROF(31);                                        // 31: stage + fence
       }
-      if (t0) bulk_wait0();                              // the item's rows are in global memory
+    } else if (warp == 18 && g.mode == POOL_EMBED) {
+      if (lane == 0) {
+        for (int t = 0; t < n_tiles; ++t) {
+          const int u = t % NSTG;
+          mbar_wait_fast(STAGED(u), (t / NSTG) & 1);
+          for (int b = 0; b < n_boxes(t); ++b) tma_store_3d(&tm_e, sXB + u * H_BYTES + b * XS_BYTES, t * TP + b * TS, q * rpp, p);
+          bulk_commit();
+          if (t >= 1) { bulk_wait_read<1>(); mbar_arrive(SFREE((t - 1) % NSTG)); }      // the previous tile's store has read its buffer
+        }
+        bulk_wait0();                                    // the item's rows are in global memory
+      }
     } else if (warp < 10) {
       const int sub = (warp >= 6) ? 1 : 0;
       float negm = -mx * LOG2E;
@@ -488,19 +510,19 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         }
       }
       tc_fence_before();
-    } else {
+    } else if (warp < 18) {
       const int sub = (warp >= 14) ? 1 : 0;
       for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % NX, b = t & 1, ph = (t >> 1) & 1, xb = t % NXB;
+        const int s = t % nxb, b = t & 1, ph = (t >> 1) & 1, xb = t % NXB;
         PROF(20);
-        mbar_wait_fast(XFULL(s), (t / NX) & 1);
+        mbar_wait_fast(XFULL(s), (t / nxb) & 1);
         PROF(21);
         mbar_wait_fast(HEMPTY(b), ph ^ 1);
         if (g.mode != POOL_EMBED) mbar_wait_fast(XBEMPTY(xb), ((t / NXB) & 1) ^ 1);
         PROF(22);
         float v[TS];
         if (g.N - t * TP - sub * TS > 0) {
-          load_x_row(smem + OFF_X + s * X_BYTES + sub * XS_BYTES, row, v);
+          load_x_row(smem + x_off(s) + sub * XS_BYTES, row, v);
         } else {
 #pragma unroll
           for (int i = 0; i < TS; ++i) v[i] = 0.f;           // box past the end of the pair: finite operand values (e is zero there)
@@ -665,9 +687,11 @@ int launch_embed_fused(const float* x, long long x_batch, float* E, long long e_
   if (grid < np) grid = np;
   if (items < grid) grid = (int)items;
   PoolFusedArgs b = a;
-  b.mode = POOL_EMBED; b.flags = nullptr; b.debug = 0;
+  b.mode = POOL_EMBED; b.flags = nullptr;
+  b.debug = getenv("LMPCR_POOL_DEBUG") ? atoi(getenv("LMPCR_POOL_DEBUG")) : 0;      // timing experiments only
   ktime_begin("embed_fused_kernel", st);
-  pool_fused_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_e, b, np, rpp);
+  if (b.debug) pool_fused_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_e, b, np, rpp);
+  else pool_fused_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_in, tm_e, b, np, rpp);
   ktime_end("embed_fused_kernel", st);
   return check_launch("embed_fused_kernel");
 }

@@ -51,6 +51,22 @@ if int(os.environ.get("LMPCR_POOL_DEBUG", "0")):
     tiles = ((N + 63) // 64) * items
     for i in sorted(names):
         print("%-34s %9.1f cycles per 64-point tile" % (names[i], buf[i] / tiles))
+bias = torch.randn(K, device="cuda", generator=g)
+ms_e = timed(lambda x: cabi.embed_fused(x, sc, sh, w, bias, want_colmax=True))
+print("embedding conv on the same kernel (E written, column maxima): %.3f ms per launch, E written at %.0f GB/s" % (ms_e, 1.0 * P * K * N * 4 / ms_e / 1e6))
+if int(os.environ.get("LMPCR_POOL_DEBUG", "0")):
+    import ctypes
+    buf = (ctypes.c_ulonglong * 32)()
+    cabi.load().lmpcr_debug_pool_profile(buf, 1)
+    cabi.embed_fused(xs[0], sc, sh, w, bias, want_colmax=True)
+    cabi.load().lmpcr_debug_pool_profile(buf, 1)
+    names = {0: "load: issue", 1: "load: wait XFREE", 20: "prod: produce", 21: "prod: wait XFULL", 22: "prod: wait HEMPTY", 24: "mma: issue", 25: "mma: wait HFULL",
+             26: "mma: wait EEMPTY", 27: "rd: loop tail", 28: "rd: wait EFULL", 29: "rd: ld + bias + colmax", 30: "rd: wait SFREE", 31: "rd: stage + fence"}
+    items = -(-(P * ((K + 127) // 128)) // 148)
+    tiles = ((N + 63) // 64) * items
+    print("embedding-conv mode:")
+    for i in sorted(names):
+        print("%-34s %9.1f cycles per 64-point tile" % (names[i], buf[i] / tiles))
 if os.environ.get("POOL_BENCH_REF", "1") == "1":
     # the path it replaces, through the stand-alone entry points: fused conv (affine + ReLU prologue) -> E, then the deferred-softmax pooling GEMM
     ms_conv = timed(lambda x: cabi.conv1x1(x, w, None, scale=sc, shift=sh, gemm_algo=1))
