@@ -301,7 +301,7 @@ def run_ours(args):
         sampler.start()
     cabi.ktime_enable(True)          # CUDA event pairs around the dominant kernels' launches, on the launching stream, inside the timed region
     ms_step, stages = timed(step_resident, args.steps, with_timers=True)
-    ktimes = {k: cabi.ktime_read(k) for k in ("pcn_stack_kernel", "pool_fused_kernel", "nn_sweep_kernel", "nn_rescore_kernel")}
+    ktimes = {k: cabi.ktime_read(k) for k in ("pcn_stack_kernel", "pool_fused_kernel", "embed_fused_kernel", "nn_sweep_kernel", "nn_rescore_kernel")}
     cabi.ktime_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     step_e2e()
@@ -338,6 +338,7 @@ def run_ours(args):
             "roofline": dom,
             "roofline_tcgemm": tcgemm_roofline(cabi, dev, n if n <= 8192 else 5000, pk),
             "roofline_pool_fused": live_pool_roofline(ktimes["pool_fused_kernel"], n_mine, n, args.steps, pk),
+            "roofline_embed_fused": live_embed_roofline(ktimes["embed_fused_kernel"], n_mine, n, args.steps, pk),
             "roofline_filter_stage": {"bound": "tensor", "achieved": filt_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": filt_tf / pk["tf_sustained"],
                                       "algorithmic_flop_per_pair": FILTER_FLOP_PER_PAIR(n), "ms_per_step": filt_ms, "peak_source": pk["src"] + " bf16 sustained"},
             "roofline_nn": {"bound": "tensor", "achieved": nn_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": nn_tf / pk["tf_sustained"],
@@ -411,6 +412,22 @@ def live_pool_roofline(kt, pairs, n, steps, pk, C=128, K=500):
             "executed_frac": 3.0 * tf / pk["tf_sustained"], "kernel": "pool_fused_kernel, timed live in the step",
             "ms_per_launch": ms / launches, "launches_per_step": launches / steps, "ms_per_step": ms / steps,
             "note": "executed tensor work is 3x the algorithmic FLOPs (split-bf16: hi.hi + hi.lo + lo.hi)", "peak_source": pk["src"] + " bf16 sustained"}
+
+
+def live_embed_roofline(kt, pairs, n, steps, pk, C=128, K=500):
+    """The `up` embedding conv on the pair-resident kernel (pool_fused.cu, POOL_EMBED) as it ran inside the timed steps.  HBM-bound by its
+    output: it writes the [K, n] logits of every pair (K*n*4 bytes per pair and block) and reads the pair's tiles once from HBM."""
+    launches, ms = kt
+    if launches == 0:
+        return None
+    byts = (float(K) * n * 4 + float(C) * n * 4) * 2 * pairs * steps
+    gbs = byts / (ms * 1e-3) / 1e9
+    flop = 2.0 * K * C * n * 2 * pairs * steps
+    return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+            "kernel": "pool_fused_kernel in embedding-conv mode, timed live in the step", "ms_per_launch": ms / launches,
+            "launches_per_step": launches / steps, "ms_per_step": ms / steps, "tensor_tflops_algorithmic": flop / (ms * 1e-3) / 1e12,
+            "note": "shared-memory bandwidth is the nearer bound: ~208 KB cross an SM's shared memory per 64-point tile (DESIGN.md 4.4)",
+            "peak_source": pk["src"] + " hbm copy"}
 
 
 def tcgemm_roofline(cabi, dev, n, pk, P=148, C=128, sets=3, iters=12):
