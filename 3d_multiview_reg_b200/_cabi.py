@@ -28,6 +28,7 @@ EXPORTS = [
     "lmpcr_sample_workspace_bytes", "lmpcr_sample_keypoints",
     "lmpcr_diff_pool_fused_workspace_bytes", "lmpcr_diff_pool_fused",
     "lmpcr_embed_fused_workspace_bytes", "lmpcr_embed_fused",
+    "lmpcr_conv_wide_workspace_bytes", "lmpcr_conv_wide",
 ]
 
 
@@ -97,6 +98,9 @@ def load():
     lib.lmpcr_pointcn_stack_workspace_bytes.restype = _sz
     lib.lmpcr_pointcn_stack_workspace_bytes.argtypes = [_i, _i]
     lib.lmpcr_pointcn_stack.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _sz, _vp]
+    lib.lmpcr_conv_wide_workspace_bytes.restype = _sz
+    lib.lmpcr_conv_wide_workspace_bytes.argtypes = []
+    lib.lmpcr_conv_wide.argtypes = [_vp, _i, _i] + [_vp] * 12 + [_vp, _sz, _vp]
     lib.lmpcr_embed_fused_workspace_bytes.restype = _sz
     lib.lmpcr_embed_fused_workspace_bytes.argtypes = [_i, _i, _i]
     lib.lmpcr_embed_fused.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]
@@ -511,6 +515,31 @@ def diff_pool_fused(x, scale, shift, weight, mode=0):
         ws = _ws(lib.lmpcr_diff_pool_fused_workspace_bytes(P, K), x.device)
         _check(lib.lmpcr_diff_pool_fused(_p(x), P, N, _p(sc), _p(sh), _p(w), K, int(mode), _p(out), _p(ws), ws.numel(), _stream(x)))
     return out
+
+
+def conv_wide(x, convs, want_stats=False):
+    """One or two 256 -> 128 convolutions over the same input in one launch (lmpcr_conv_wide).  x [P,256,N]; convs: list of 1-2 dicts with
+    weight [128,256] and optional bias [128], scale / shift [P,256].  Returns a list of outputs [P,128,N] (and of [P,128,2] statistics)."""
+    lib = load()
+    x = _dev(x, name="x")
+    P, C, N = x.shape
+    opt = lambda t, n: _dev(t, name=n) if t is not None else None
+    with torch.cuda.device(x.device):
+        args, outs, stats, keep = [], [], [], []
+        for i in range(2):
+            if i < len(convs):
+                c = convs[i]
+                w, b, sc, sh = _dev(c["weight"], name="weight"), opt(c.get("bias"), "bias"), opt(c.get("scale"), "scale"), opt(c.get("shift"), "shift")
+                o = torch.empty((P, 128, N), dtype=torch.float32, device=x.device)
+                s = torch.empty((P, 128, 2), dtype=torch.float32, device=x.device) if want_stats else None
+                keep += [w, b, sc, sh]
+                outs.append(o); stats.append(s)
+                args += [_p(w), _p(b), _p(sc), _p(sh), _p(o), _p(s)]
+            else:
+                args += [_p(None)] * 6
+        ws = _ws(lib.lmpcr_conv_wide_workspace_bytes(), x.device)
+        _check(lib.lmpcr_conv_wide(_p(x), P, N, *args, _p(ws), ws.numel(), _stream(x)))
+    return (outs, stats) if want_stats else outs
 
 
 def embed_fused(x, scale, shift, weight, bias=None, want_colmax=False):

@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include "pool_fused.cuh"
+#include "conv_wide.cuh"
 #include "tcgemm.cuh"
 #include "pcn.cuh"
 
@@ -333,6 +334,30 @@ int lmpcr_embed_fused(const float* x, int n_pairs, int n_pts, const float* scale
   LMPCR_TRY(launch_embed_fused(x, (long long)128 * n_pts, embed, (long long)clusters * n_pts, a, st));
   if (colmax) LMPCR_TRY(launch_colmax_from_slabs(slabs, 4 * ((clusters + 127) / 128), n_pairs, n_pts, colmax, st));
   return LMPCR_OK;
+}
+
+size_t lmpcr_conv_wide_workspace_bytes(void) { return 2 * align_up(conv_wide_weight_bytes(), 256) + 256; }
+
+int lmpcr_conv_wide(const float* x, int n_pairs, int n_pts, const float* weight0, const float* bias0, const float* scale0, const float* shift0,
+                    float* out0, float* stats0, const float* weight1, const float* bias1, const float* scale1, const float* shift1, float* out1,
+                    float* stats1, void* workspace, size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  LMPCR_REQUIRE(x && weight0 && out0 && n_pairs >= 0 && n_pts > 0 && (!weight1 || out1), LMPCR_ERR_ARG, "lmpcr_conv_wide: bad arguments");
+  LMPCR_REQUIRE(workspace && workspace_bytes >= lmpcr_conv_wide_workspace_bytes() && ((uintptr_t)workspace & 255) == 0, LMPCR_ERR_WORKSPACE,
+                "lmpcr_conv_wide: workspace too small or not 256-byte aligned");
+  if (n_pairs == 0) return LMPCR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* blob0 = reinterpret_cast<uint8_t*>(workspace);
+  uint8_t* blob1 = blob0 + align_up(conv_wide_weight_bytes(), 256);
+  ConvWideArgs a{};
+  a.P = n_pairs; a.N = n_pts; a.n_convs = weight1 ? 2 : 1;
+  LMPCR_TRY(launch_conv_wide_pack_weights(weight0, blob0, st));
+  a.conv[0] = ConvWideOne{blob0, bias0, scale0, shift0, out0, (long long)128 * n_pts, stats0};
+  if (weight1) {
+    LMPCR_TRY(launch_conv_wide_pack_weights(weight1, blob1, st));
+    a.conv[1] = ConvWideOne{blob1, bias1, scale1, shift1, out1, (long long)128 * n_pts, stats1};
+  }
+  return launch_conv_wide(x, (long long)256 * n_pts, a, st);
 }
 
 int lmpcr_filter_num_params(const lmpcr_filter_cfg* cfg) {

@@ -17,6 +17,7 @@
 #include "tcgemm.cuh"
 #include "pcn.cuh"
 #include "pool_fused.cuh"
+#include "conv_wide.cuh"
 
 namespace lmpcr {
 namespace {
@@ -572,7 +573,7 @@ __global__ void guard_flag_kernel(const int32_t* __restrict__ anypos, int P, int
 // ------------------------------------------------------------------------------------------------
 // parameter table (state_dict order)
 // ------------------------------------------------------------------------------------------------
-struct ConvP { const float* w; const float* b; const uint8_t* blob; const uint8_t* blob_rm; };   // blob_rm: pcn.cu's tensor-memory image (plain 128 -> 128 layers)
+struct ConvP { const float* w; const float* b; const uint8_t* blob; const uint8_t* blob_rm; };   // blob_rm: the row-major tensor-memory image (pcn.cu, pool_fused.cu, conv_wide.cu)
 struct BNP { const float* g; const float* b; const float* rm; const float* rv; };
 struct PointCNP { bool has_sc; ConvP sc; BNP bn1; ConvP c1; BNP bn2; ConvP c2; };
 struct OAFilterP { BNP bn1; ConvP c1; BNP bn2; ConvP c2; BNP bn3; ConvP c3; };
@@ -642,6 +643,7 @@ size_t block_blob_bytes(int C, int K, int half) {
   b += (size_t)half * (2 * tc_weight_blob_bytes(C, C) + tc_weight_blob_bytes(K, K));   // l2
   if (C == PCN_C) b += (size_t)(2 * half + 2 * (half - 1)) * pcn_weight_bytes();       // second image of the plain PointCN weights (pcn.cu)
   if (C == PCN_C) b += 2 * pool_fused_weight_bytes(K);                                   // second image of the down / up embedding convs (pool_fused.cu)
+  if (C == PCN_C) b += 2 * conv_wide_weight_bytes();                                     // second image of l1_2.0's shot_cut and conv.3 (conv_wide.cu)
   return align_up(b, 256);
 }
 
@@ -675,6 +677,12 @@ int block_blobs(BlockP& blk, int C, int K, int half, uint8_t* bp, bool do_split,
     blk.up_conv.blob_rm = bp;
     if (do_split) LMPCR_TRY(launch_pool_fused_pack_weights(blk.up_conv.w, K, bp, st));
     bp += pool_fused_weight_bytes(K);
+    blk.l1_2[0].sc.blob_rm = bp;
+    if (do_split) LMPCR_TRY(launch_conv_wide_pack_weights(blk.l1_2[0].sc.w, bp, st));
+    bp += conv_wide_weight_bytes();
+    blk.l1_2[0].c1.blob_rm = bp;
+    if (do_split) LMPCR_TRY(launch_conv_wide_pack_weights(blk.l1_2[0].c1.w, bp, st));
+    bp += conv_wide_weight_bytes();
   }
   return LMPCR_OK;
 }
@@ -904,6 +912,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   static const int no_defer = getenv("LMPCR_NO_DEFER") ? atoi(getenv("LMPCR_NO_DEFER")) : 0;   // debug aid: softmax statistics by separate passes
   // read per call (two getenv look-ups) so that a test can switch paths inside one process
   const int pcn_on = getenv("LMPCR_PCN") ? atoi(getenv("LMPCR_PCN")) : 1;                       // 0: PointCN layers on the per-layer GEMM path (A/B runs)
+  const int wide_on = getenv("LMPCR_CONV_WIDE") ? atoi(getenv("LMPCR_CONV_WIDE")) : 1;            // 0: l1_2.0's shot_cut / conv.3 as two GEMM launches (A/B runs)
   const int embed_on = getenv("LMPCR_EMBED_FUSED") ? atoi(getenv("LMPCR_EMBED_FUSED")) : 1;       // 0: the `up` embedding conv as convert_b + GEMM (A/B runs)
   const int pool_on = getenv("LMPCR_POOL_FUSED") ? atoi(getenv("LMPCR_POOL_FUSED")) : 1;         // 0: diff_pool as embedding GEMM + pooling GEMM (A/B runs)
   const int pcn_min_pairs = getenv("LMPCR_PCN_MIN_PAIRS") ? atoi(getenv("LMPCR_PCN_MIN_PAIRS")) : 64;
@@ -1094,6 +1103,20 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   // PointCN (oanet.py:18-43): out = conv2(f(conv1(f(x)))) + (shot_cut(x) | x)
   auto pointcn = [&](const PointCNP& q, const float* x, long long xb, int cin, int g, float* tmp, float* sc_buf, float* out, long long ob) -> int {
     const float* res = x; long long rb = xb;
+    if (q.has_sc && wide_on && tc && !bn_train && cin == 2 * C && g >= pcn_min_pairs && q.sc.blob_rm && q.c1.blob_rm && conv_wide_supported(C, N, x, xb)) {
+      // shot_cut (raw input) and conv.3 (normalised input) of the layer in ONE launch, side by side on neighbouring CTAs: the 256-channel
+      // concat buffer comes from HBM once, both weight matrices sit in tensor memory (conv_wide.cu)
+      LMPCR_TRY(norm_affine(x, xb, cin, N, g, 1e-5f, q.bn1));
+      ConvWideArgs wa{};
+      wa.P = g; wa.N = N; wa.n_convs = 2;
+      const int ti = part_index(tmp);
+      wa.conv[0] = ConvWideOne{q.sc.blob_rm, q.sc.b, nullptr, nullptr, sc_buf, CN, nullptr};
+      wa.conv[1] = ConvWideOne{q.c1.blob_rm, q.c1.b, W.scale, W.shift, tmp, CN, ti >= 0 ? part_buf[ti] : nullptr};
+      { const int si = part_index(sc_buf); if (si >= 0) { part_valid[si] = false; part_whole[si] = false; } }
+      LMPCR_TRY(launch_conv_wide(x, xb, wa, st));
+      if (ti >= 0) { part_valid[ti] = true; part_whole[ti] = true; }
+      return conv_norm(tmp, CN, C, N, g, 1e-5f, q.bn2, q.c2, C, out, ob, sc_buf, CN);
+    }
     if (q.has_sc) {
       LMPCR_TRY(conv_plain(x, xb, cin, N, g, q.sc, C, sc_buf, CN));
       res = sc_buf; rb = CN;

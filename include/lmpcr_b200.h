@@ -288,6 +288,16 @@ size_t lmpcr_embed_fused_workspace_bytes(int n_pairs, int n_pts, int clusters);
 int lmpcr_embed_fused(const float* x, int n_pairs, int n_pts, const float* scale, const float* shift, const float* weight, const float* bias,
                       int clusters, float* embed, float* colmax, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One or two 256 -> 128 convolutions over the same input in one launch (csrc/conv_wide.cu): the shot_cut conv and conv.3 of the
+ * first PointCN of l1_2 (lib/filtering/oanet.py:22-23,27-30,171), which both read the 256-channel concat buffer.
+ *   out_i[p,o,n] = sum_c weight_i[o,c] * f_i(x[p,c,n]) + bias_i[o],   f_i(v) = relu(v * scale_i[p,c] + shift_i[p,c]) or v (scale_i NULL)
+ *   x [P,256,N] fp32 (n_pts % 4 == 0), weight_i [128,256], bias_i [128] or NULL, out_i [P,128,N];
+ *   stats_i (optional) [P,128,2] = (mean, M2 over the points) of every output row.  The second convolution is skipped when weight1 is NULL. */
+size_t lmpcr_conv_wide_workspace_bytes(void);
+int lmpcr_conv_wide(const float* x, int n_pairs, int n_pts, const float* weight0, const float* bias0, const float* scale0, const float* shift0,
+                    float* out0, float* stats0, const float* weight1, const float* bias1, const float* scale1, const float* shift1, float* out1,
+                    float* stats1, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of tensors of OANet(cfg).state_dict() excluding `num_batches_tracked` entries; `params` below is
  * a HOST array of that many DEVICE pointers (fp32, contiguous), in state_dict order. */
 int lmpcr_filter_num_params(const lmpcr_filter_cfg* cfg);

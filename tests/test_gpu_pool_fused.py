@@ -137,3 +137,30 @@ def test_network_takes_the_fused_pool_and_agrees_with_the_gemm_path():
     assert err["fused"][0] < 5e-4 and err["gemm"][0] < 5e-4, err
     assert O.chordal_angle(out["rot_est"][-1].cpu().numpy(), o64["rot_est"][-1]).max() < 1e-3
     assert (out["logits"][0] - ref["logits"][0]).abs().max().item() < 5e-4
+
+
+@pytest.mark.parametrize("P,N", [(3, 200), (2, 5000), (75, 264), (1, 28), (2, 1332)])
+def test_conv_wide_against_fp64(P, N):
+    """The two 256 -> 128 convolutions of l1_2's first PointCN in one launch (lmpcr_conv_wide, csrc/conv_wide.cu): shot_cut on the raw
+    input, conv.3 behind the folded norm affine + ReLU; outputs and the fused row statistics against fp64."""
+    rng = np.random.default_rng(P * 10000 + N)
+    x = (rng.standard_normal((P, 256, N)) * 2 + 0.5).astype(np.float32)
+    w0 = (rng.standard_normal((128, 256)) / 16).astype(np.float32)
+    w1 = (rng.standard_normal((128, 256)) / 16).astype(np.float32)
+    b0, b1 = rng.standard_normal(128).astype(np.float32), rng.standard_normal(128).astype(np.float32)
+    sc = rng.uniform(0.3, 1.2, (P, 256)).astype(np.float32)
+    sh = (0.5 * rng.standard_normal((P, 256))).astype(np.float32)
+    x64 = x.astype(np.float64)
+    ref0 = np.einsum("oc,pcn->pon", w0.astype(np.float64), x64) + b0.astype(np.float64)[None, :, None]
+    h = np.maximum(x64 * sc.astype(np.float64)[:, :, None] + sh.astype(np.float64)[:, :, None], 0)
+    ref1 = np.einsum("oc,pcn->pon", w1.astype(np.float64), h) + b1.astype(np.float64)[None, :, None]
+    outs, stats = cabi.conv_wide(cu(x), [dict(weight=cu(w0), bias=cu(b0)), dict(weight=cu(w1), bias=cu(b1), scale=cu(sc), shift=cu(sh))], want_stats=True)
+    for o, st, ref in zip(outs, stats, (ref0, ref1)):
+        o, st = o.cpu().numpy(), st.cpu().numpy()
+        scale = max(1.0, np.abs(ref).max())
+        assert np.abs(o - ref).max() < 2e-5 * scale, np.abs(o - ref).max()
+        assert np.abs(st[..., 0] - ref.mean(2)).max() < 1e-4 * scale
+        assert np.abs(st[..., 1] / N - ref.var(2)).max() < 2e-4 * max(1.0, ref.var(2).max())
+    # a single convolution, no bias
+    one = cabi.conv_wide(cu(x), [dict(weight=cu(w1), scale=cu(sc), shift=cu(sh))])[0].cpu().numpy()
+    assert np.abs(one - (ref1 - b1.astype(np.float64)[None, :, None])).max() < 2e-5 * max(1.0, np.abs(ref1).max())
