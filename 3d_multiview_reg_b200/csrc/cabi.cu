@@ -332,7 +332,7 @@ int lmpcr_embed_fused(const float* x, int n_pairs, int n_pts, const float* scale
   a.w_blob = blob; a.scale = scale; a.shift = shift; a.bias = bias; a.colmax_slabs = colmax ? slabs : nullptr;
   a.P = n_pairs; a.N = n_pts; a.K = clusters;
   LMPCR_TRY(launch_embed_fused(x, (long long)128 * n_pts, embed, (long long)clusters * n_pts, a, st));
-  if (colmax) LMPCR_TRY(launch_colmax_from_slabs(slabs, 4 * ((clusters + 127) / 128), n_pairs, n_pts, colmax, st));
+  if (colmax) LMPCR_TRY(launch_colmax_from_slabs(slabs, 2 * ((clusters + 127) / 128), n_pairs, n_pts, colmax, st));
   return LMPCR_OK;
 }
 

@@ -224,7 +224,8 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           mbar_wait_fast(STAGED(u), (t >> 1) & 1);
           tma_store_3d(tm_out, sSTG + u * STG_BYTES, t * TW, 0, p);
           bulk_commit();
-          if (t >= 1) { bulk_wait_read<1>(); mbar_arrive(SFREE((t - 1) & 1)); }      // the previous tile's store has read its buffer
+          bulk_wait_read<0>();                             // this store has read its buffer: hand it back at once
+          mbar_arrive(SFREE(u));
         }
         bulk_wait0();                                      // the item's rows are in global memory
       }

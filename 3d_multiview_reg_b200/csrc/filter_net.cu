@@ -299,15 +299,39 @@ __global__ void in_affine_kernel(const float* __restrict__ x, long long x_batch,
   float mean = 0.f, rstd = 1.f;
   if (use_in) {
     const float* r = x + (long long)p * x_batch + (long long)c * (ld ? ld : L);     // rows ld floats apart (0: contiguous)
-    float s = 0.f;
-    for (int i = lane; i < L; i += 32) s += __ldg(r + i);
-    mean = warp_sum(s) / (float)L;
-    float v = 0.f;
-    for (int i = lane; i < L; i += 32) {
-      const float d = __ldg(r + i) - mean;
-      v = fmaf(d, d, v);
+    if (L <= 1024 && (L & 3) == 0 && (reinterpret_cast<uintptr_t>(r) & 15) == 0) {
+      // short rows (the 500-cluster matrices of the OAFilter stage): the whole row in registers, one trip to memory
+      const float4* r4 = reinterpret_cast<const float4*>(r);
+      const int cnt = L >> 2;
+      float4 q[8];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = lane + 32 * i;
+        q[i] = idx < cnt ? __ldg(r4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (q[i].x + q[i].y) + (q[i].z + q[i].w);
+      }
+      mean = warp_sum(s) / (float)L;
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (lane + 32 * i < cnt) {
+          const float d0 = q[i].x - mean, d1 = q[i].y - mean, d2 = q[i].z - mean, d3 = q[i].w - mean;
+          v = fmaf(d0, d0, v); v = fmaf(d1, d1, v); v = fmaf(d2, d2, v); v = fmaf(d3, d3, v);
+        }
+      }
+      rstd = 1.0f / sqrtf(warp_sum(v) / (float)L + eps_in);
+    } else {
+      float s = 0.f;
+      for (int i = lane; i < L; i += 32) s += __ldg(r + i);
+      mean = warp_sum(s) / (float)L;
+      float v = 0.f;
+      for (int i = lane; i < L; i += 32) {
+        const float d = __ldg(r + i) - mean;
+        v = fmaf(d, d, v);
+      }
+      rstd = 1.0f / sqrtf(warp_sum(v) / (float)L + eps_in);
     }
-    rstd = 1.0f / sqrtf(warp_sum(v) / (float)L + eps_in);
   }
   if (lane == 0) {
     scale[row] = rstd * gsc;
@@ -1276,7 +1300,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       }
       if (tc) {
         if (use_embed_fused) {
-          LMPCR_TRY(launch_colmax_from_slabs(col_part, 4 * ((K + 127) / 128), g, N, sm_max, st));
+          LMPCR_TRY(launch_colmax_from_slabs(col_part, 2 * ((K + 127) / 128), g, N, sm_max, st));
         } else if (defer_up) {   // column maxima came fused out of the embedding conv's epilogue; the GEMM accumulates the sums itself
           colmax_from_partials_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(col_part, 4 * ((K + 127) / 128), tot, sm_max);
           LMPCR_TRY(check_launch("colmax_from_partials_kernel"));

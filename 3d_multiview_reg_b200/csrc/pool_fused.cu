@@ -22,6 +22,7 @@
 //                 (2-5 first box of a tile, 6-9 second box); thread = cluster row (TMEM lane) ((warp & 3) << 5) | lane
 //   warps 10-17   producers: x tile (smem, fp32) -> h and xb operand images (10-13 first box, 14-17 second); thread = channel
 //   warp 18       embedding-conv mode only: TMA stores of the staged output tiles
+//   warps 19-22   embedding-conv mode only: column maxima of the staged tiles (two warps per box: upper / lower rows; thread = point)
 #include <math.h>
 #include <stdlib.h>
 
@@ -46,7 +47,7 @@ constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr size_t SMEM_BYTES = OFF_TMEM + 16;
 static_assert(X_BYTES == H_BYTES, "an xb buffer doubles as an x slot in pass A");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
-constexpr int NTHREADS = 19 * 32;                // warp 18: TMA stores of the embedding-conv mode
+constexpr int NTHREADS = 23 * 32;                // warp 18: TMA stores, warps 19-22: column maxima (embedding-conv mode)
 // Tensor memory (512 columns): weights (bf16 hi 64 | lo 64 columns, two elements per column), E tiles [2][64], e tiles [2][hi 32 | lo 32],
 // the pooling accumulator [128 cluster rows x 128 channels]
 constexpr int TMEM_COLS = 512;
@@ -66,34 +67,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-// maximum of every column of a 32 x 32 block held one row per lane (v[i] = element (lane, i)): lane l returns the maximum of column l.
-// Butterfly transpose-reduce: 31 shuffles + 31 maxima + the selects (the price of a reduction ACROSS tensor-memory lanes).
-__device__ __forceinline__ float warp_col_max(const float (&v)[32], int lane) {
-  float w[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float mine = (lane & 16) ? v[i + 16] : v[i], send = (lane & 16) ? v[i] : v[i + 16];
-    w[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 16));
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float mine = (lane & 8) ? w[i + 8] : w[i], send = (lane & 8) ? w[i] : w[i + 8];
-    w[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 8));
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float mine = (lane & 4) ? w[i + 4] : w[i], send = (lane & 4) ? w[i] : w[i + 4];
-    w[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 4));
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float mine = (lane & 2) ? w[i + 2] : w[i], send = (lane & 2) ? w[i] : w[i + 2];
-    w[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 2));
-  }
-  const float mine = (lane & 1) ? w[1] : w[0], send = (lane & 1) ? w[0] : w[1];
-  return fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 1));
 }
 
 // cycle counters for timing experiments (LMPCR_POOL_DEBUG=1): lane 0 of the first warp of every role in CTA 0
@@ -156,7 +129,7 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         mbar_init(EFULL(a), 1); mbar_init(EEMPTY(a), 256); mbar_init(PFULL(a), 8); mbar_init(PEMPTY(a), 1);
       }
       mbar_init(ACCFULL, 1);
-      for (int u = 0; u < NSTG; ++u) { mbar_init(STAGED(u), 8); mbar_init(SFREE(u), 1); }
+      for (int u = 0; u < NSTG; ++u) { mbar_init(STAGED(u), 8); mbar_init(SFREE(u), 5); }      // freed by the store warp and the four column-maximum warps
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -169,21 +142,22 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
 
   constexpr uint32_t DESC_HI1 = (MN_SBO >> 4) | (1u << 14);                    // SBO, descriptor version
   // E tile: D[128 x TP] = W (bf16 hi | lo in tensor memory) . h (operand image at sHt); all three products, or W_hi . h_hi only
-  auto issue_gemm1 = [&](uint32_t sHt, uint32_t d_tmem, uint32_t leader, bool full) {
+  auto issue_gemm1w = [&](uint32_t tW, uint32_t sHt, uint32_t d_tmem, uint32_t leader, bool full) {
     const uint32_t lo0 = ((sHt >> 4) & 0x3FFFu) | ((MN_LBO >> 4) << 16);
 #pragma unroll
     for (int j = 0; j < C / 16; ++j) {
       const uint32_t lo_hi = lo0 + j * ((2 * MN_LBO) >> 4), lo_lo = lo_hi + (HP_BYTES >> 4);
       const uint64_t b_hi = ((uint64_t)DESC_HI1 << 32) | lo_hi, b_lo = ((uint64_t)DESC_HI1 << 32) | lo_lo;
       if (full) {
-        tc_mma_ts_pred(d_tmem, tmW + 64 + j * 8, b_hi, IDESC1, j ? 1u : 0u, leader);    // W_lo . h_hi   (small terms first)
-        tc_mma_ts_pred(d_tmem, tmW + j * 8, b_lo, IDESC1, 1u, leader);                  // W_hi . h_lo
-        tc_mma_ts_pred(d_tmem, tmW + j * 8, b_hi, IDESC1, 1u, leader);                  // W_hi . h_hi
+        tc_mma_ts_pred(d_tmem, tW + 64 + j * 8, b_hi, IDESC1, j ? 1u : 0u, leader);     // W_lo . h_hi   (small terms first)
+        tc_mma_ts_pred(d_tmem, tW + j * 8, b_lo, IDESC1, 1u, leader);                   // W_hi . h_lo
+        tc_mma_ts_pred(d_tmem, tW + j * 8, b_hi, IDESC1, 1u, leader);                   // W_hi . h_hi
       } else {
-        tc_mma_ts_pred(d_tmem, tmW + j * 8, b_hi, IDESC1, j ? 1u : 0u, leader);
+        tc_mma_ts_pred(d_tmem, tW + j * 8, b_hi, IDESC1, j ? 1u : 0u, leader);
       }
     }
   };
+  auto issue_gemm1 = [&](uint32_t sHt, uint32_t d_tmem, uint32_t leader, bool full) { issue_gemm1w(tmW, sHt, d_tmem, leader, full); };
   // pooling step: acc[128 x 128] (+)= e (bf16 hi | lo in tensor memory at tP: K = the TP points of the tile) . xb (the raw tile's
   // operand image read K-major: point-groups 128 B apart along K, channel-groups 1 KB apart along N)
   constexpr uint32_t DESC_HI2 = (MN_LBO >> 4) | (1u << 14);                    // SBO = 1024 (channel groups)
@@ -199,7 +173,7 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     }
   };
   // this thread's row of the weight block (row-major bf16 [hi 32 KB | lo 32 KB] in global memory) -> tensor memory
-  auto load_w_row = [&](const uint8_t* wg) {
+  auto load_w_row = [&](const uint8_t* wg, uint32_t tW) {
 #pragma unroll 1
     for (int part = 0; part < 2; ++part) {
 #pragma unroll 1
@@ -211,7 +185,7 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           const uint4 v = __ldg(src + q);
           r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
         }
-        tc_st32(tmW + lane_sel + part * 64 + hh * 32, r);
+        tc_st32(tW + lane_sel + part * 64 + hh * 32, r);
       }
     }
   };
@@ -236,17 +210,24 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     }
   };
 
+  // Embedding-conv mode: no pooling accumulator, so tensor memory holds the weights of TWO cluster blocks (columns 0-127 and 128-255) and four E
+  // tiles (256 + (buffer * 2 + block) * 64): every x tile / h image serves two blocks -- half the producer work, L2 reads and operand traffic per E tile
+  const int nq = (g.mode == POOL_EMBED && (n_parts & 1) == 0) ? 2 : 1;      // cluster blocks per item
+  const int ipp = n_parts / nq;                                             // items per pair
+  auto tmWe = [&](int j) { return tmem_base + j * 128; };
+  auto tmEe = [&](int a, int j) { return tmem_base + 256 + (a * 2 + j) * TP; };
   int q_loaded = -1;
-  const long long n_items = (long long)g.P * n_parts;
+  const long long n_items = (long long)g.P * ipp;
   for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
     if (g.mode == POOL_FALLBACK && g.flags[item] == 0) continue;          // uniform over the CTA: only the items the single pass gave up on
-    const int p = (int)(item / n_parts), q = (int)(item - (long long)p * n_parts);
+    const int p = (int)(item / ipp), q = (int)(item - (long long)p * ipp) * nq;      // q: first cluster block of the item
     const int rows_valid = min(rpp, g.K - q * rpp);           // cluster rows of this block (the rest of the 128 are zero weights)
     float sc = 1.f, sh = 0.f;
     if (warp >= 10 && warp < 18) { sc = __ldg(g.scale + (size_t)p * C + row); sh = __ldg(g.shift + (size_t)p * C + row); }
     if (q != q_loaded) {
       if (warp >= 2 && warp < 6) {          // every MMA of the previous item has completed (pass_end)
-        load_w_row(g.w_blob + (size_t)q * 2 * WP_BYTES);
+        if (g.mode == POOL_EMBED) { for (int j = 0; j < nq; ++j) load_w_row(g.w_blob + (size_t)(q + j) * 2 * WP_BYTES, tmWe(j)); }
+        else load_w_row(g.w_blob + (size_t)q * 2 * WP_BYTES, tmW);
         tc_st_wait();
         tc_fence_before();
       }
@@ -343,7 +324,7 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         PROF(26);                                        // 26: wait EEMPTY
         tc_fence_after();
         const uint32_t leader = elect_one();
-        issue_gemm1(sH + a * H_BYTES, tmE + a * TP, leader, true);
+        for (int j = 0; j < nq; ++j) issue_gemm1w(tmWe(j), sH + a * H_BYTES, tmEe(a, j), leader, true);
         tc_commit_pred(HEMPTY(a), leader);
         tc_commit_pred(EFULL(a), leader);
         __syncwarp();
@@ -393,49 +374,79 @@ pool_fused_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     } else if (warp < 10 && g.mode == POOL_EMBED) {
       // E tile -> + bias -> (column maxima over this warp's 32 rows) -> staged in shared memory (the idle xb ring, SWIZZLE_128B rows) -> TMA store
       const int sub = (warp >= 6) ? 1 : 0;
-      const bool valid_row = row < rows_valid;
-      const float bk = (valid_row && g.bias) ? __ldg(g.bias + q * rpp + row) : 0.f;
-      const int n_slabs = 4 * n_parts;
+      bool valid_row[2]; float bk[2];
+      for (int j = 0; j < 2; ++j) {
+        valid_row[j] = j < nq && row < min(rpp, g.K - (q + j) * rpp);
+        bk[j] = (valid_row[j] && g.bias) ? __ldg(g.bias + (q + j) * rpp + row) : 0.f;
+      }
       for (int t = 0; t < n_tiles; ++t) {
         const int a = t & 1, ph = (t >> 1) & 1;
-        PROF(27);                                        // 27: TMA store issue + wait_read (t0's warp) / loop tail
+        PROF(27);                                        // 27: loop tail
         mbar_wait_fast(EFULL(a), ph);
         PROF(28);                                        // 28: wait EFULL
         tc_fence_after();
-        float v[TS];
-        tc_ld32(tmE + lane_sel + a * TP + sub * TS, v);
-        tc_fence_before();
-        mbar_arrive(EEMPTY(a));
         const int ncv = g.N - t * TP - sub * TS;
 #pragma unroll
-        for (int i = 0; i < TS; ++i) v[i] += bk;
-        if (g.colmax_slabs) {
-          float m[TS];
+        for (int j = 0; j < 2; ++j) {
+          if (j < nq) {
+            float v[TS];
+            tc_ld32(tmEe(a, j) + lane_sel + sub * TS, v);
+            if (j == nq - 1) { tc_fence_before(); mbar_arrive(EEMPTY(a)); }
 #pragma unroll
-          for (int i = 0; i < TS; ++i) m[i] = valid_row ? v[i] : -INFINITY;          // the zero-weight rows of the block are not clusters
-          const float cm = warp_col_max(m, lane);
-          if (lane < ncv) g.colmax_slabs[((size_t)p * n_slabs + q * 4 + (warp & 3)) * g.N + (size_t)t * TP + sub * TS + lane] = cm;
+            for (int i = 0; i < TS; ++i) v[i] += bk[j];
+            PROF(29);                                    // 29: ld + bias
+            const int e = t * nq + j, u = e % NSTG;      // staged tiles are numbered through the item
+            mbar_wait_fast(SFREE(u), ((e / NSTG) & 1) ^ 1);      // the store of staged tile e - 2 has read this buffer
+            PROF(30);                                    // 30: wait SFREE
+            if (ncv > 0) store_x_row(smem + OFF_XB + u * H_BYTES + sub * XS_BYTES, row, v);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(STAGED(u));
+            PROF(31);                                    // 31: stage + fence
+          }
         }
-        PROF(29);                                        // 29: ld + bias + column maxima
-        const int u = t % NSTG;
-        mbar_wait_fast(SFREE(u), ((t / NSTG) & 1) ^ 1);  // the store of tile t - 2 has read this staging buffer
-        PROF(30);                                        // 30: wait SFREE
-        if (ncv > 0) store_x_row(smem + OFF_XB + u * H_BYTES + sub * XS_BYTES, row, v);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(STAGED(u));
-        PROF(31);                                        // 31: stage + fence
       }
     } else if (warp == 18 && g.mode == POOL_EMBED) {
       if (lane == 0) {
-        for (int t = 0; t < n_tiles; ++t) {
-          const int u = t % NSTG;
-          mbar_wait_fast(STAGED(u), (t / NSTG) & 1);
-          for (int b = 0; b < n_boxes(t); ++b) tma_store_3d(&tm_e, sXB + u * H_BYTES + b * XS_BYTES, t * TP + b * TS, q * rpp, p);
+        for (int e = 0; e < n_tiles * nq; ++e) {
+          const int t = e / nq, j = e - t * nq, u = e % NSTG;
+          mbar_wait_fast(STAGED(u), (e / NSTG) & 1);
+          for (int b = 0; b < n_boxes(t); ++b) tma_store_3d(&tm_e, sXB + u * H_BYTES + b * XS_BYTES, t * TP + b * TS, (q + j) * rpp, p);
           bulk_commit();
-          if (t >= 1) { bulk_wait_read<1>(); mbar_arrive(SFREE((t - 1) % NSTG)); }      // the previous tile's store has read its buffer
+          bulk_wait_read<0>();                           // this store has read its buffer: hand it back at once (waiting for the NEXT staged tile first
+          mbar_arrive(SFREE(u));                         // would stall the readers, who need this buffer for the tile after the next)
         }
         bulk_wait0();                                    // the item's rows are in global memory
+      }
+    } else if (warp >= 19 && g.mode == POOL_EMBED) {
+      // Column maxima (the softmax of diff_unpool runs over the clusters) from the STAGED tile: thread = point reads its column of the swizzled
+      // box conflict-free, 125 LDS + FMNMX -- a reduction across tensor-memory lanes in the readers' registers costs 31 shuffles + 31 maxima +
+      // 62 selects per 32 x 32 block and warp (it was 40 % of the reader loop).  Two slabs per cluster block (rows 0-63 / 64-...): colmax_slabs [P][2 n_parts][N].
+      const int sub = (warp - 19) & 1, rh = (warp - 19) >> 1;
+      for (int e = 0; e < n_tiles * nq; ++e) {
+        const int t = e / nq, j = e - t * nq, u = e % NSTG;
+        mbar_wait_fast(STAGED(u), (e / NSTG) & 1);
+        const int ncv = g.N - t * TP - sub * TS;
+        if (g.colmax_slabs && lane < ncv) {
+          const uint8_t* box = smem + OFF_XB + u * H_BYTES + sub * XS_BYTES;
+          const int rv_all = min(rpp, g.K - (q + j) * rpp);    // the zero-weight rows of the block are not clusters
+          const int r_lo = rh ? 64 : 0, rv = rh ? rv_all : min(rv_all, 64);
+          // eight rows per step (one swizzle period: row r0 + i sits at chunk cq ^ i), eight independent maxima: the loads of a step are in flight together
+          float m[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+          const uint32_t cq = (uint32_t)lane >> 2, cw = ((uint32_t)lane & 3u) << 2;
+          int r0 = r_lo;
+          for (; r0 + 8 <= rv; r0 += 8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], *reinterpret_cast<const float*>(box + (r0 + i) * 128 + (((cq ^ i) << 4) | cw)));
+          }
+          for (int r = r0; r < rv; ++r) m[0] = fmaxf(m[0], *reinterpret_cast<const float*>(box + r * 128 + (((cq ^ (r & 7)) << 4) | cw)));
+          g.colmax_slabs[((size_t)p * 2 * n_parts + 2 * (q + j) + rh) * g.N + (size_t)t * TP + sub * TS + lane] =
+              fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(SFREE(u));
       }
     } else if (warp < 10) {
       const int sub = (warp >= 6) ? 1 : 0;
@@ -682,9 +693,10 @@ int launch_embed_fused(const float* x, long long x_batch, float* E, long long e_
       attr_set[dev] = 1;
     }
   }
-  const long long items = (long long)a.P * np;
-  int grid = sm_count() / np * np;
-  if (grid < np) grid = np;
+  const int ipp = (np & 1) == 0 ? np / 2 : np;          // items per pair: two cluster blocks per CTA when the block count is even
+  const long long items = (long long)a.P * ipp;
+  int grid = sm_count() / ipp * ipp;
+  if (grid < ipp) grid = ipp;
   if (items < grid) grid = (int)items;
   PoolFusedArgs b = a;
   b.mode = POOL_EMBED; b.flags = nullptr;

@@ -15,7 +15,7 @@ struct PoolFusedArgs {
   int mode;                       // kernel-internal: launch_pool_fused sets it (POOL_SINGLE, then POOL_FALLBACK over the flagged items)
   int32_t* flags;                 // [P * ceil(K / 128)] scratch of the single-pass mode; NULL: two passes for every item
   // embedding-conv mode (launch_embed_fused): E = W f(x) + bias is the output, [P][K][N] fp32; colmax_slabs (optional)
-  // [P][4 * ceil(K/128)][N] = maximum of every column over each 32-row slab (diff_unpool's softmax runs over the clusters)
+  // [P][2 ceil(K/128)][N] = maximum of every column over each half cluster block (diff_unpool's softmax runs over the clusters)
   const float* bias; float* colmax_slabs;
   int debug;
 };

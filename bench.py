@@ -426,7 +426,7 @@ def live_embed_roofline(kt, pairs, n, steps, pk, C=128, K=500):
     return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
             "kernel": "pool_fused_kernel in embedding-conv mode, timed live in the step", "ms_per_launch": ms / launches,
             "launches_per_step": launches / steps, "ms_per_step": ms / steps, "tensor_tflops_algorithmic": flop / (ms * 1e-3) / 1e12,
-            "note": "shared-memory bandwidth is the nearer bound: ~208 KB cross an SM's shared memory per 64-point tile (DESIGN.md 4.4)",
+            "note": "algorithmic bytes = the logits written + the pair's tiles read once (the other cluster blocks of a pair find them in L2)",
             "peak_source": pk["src"] + " hbm copy"}
 
 
