@@ -20,7 +20,7 @@ GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
 EXPORTS = [
-    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_launch_count_named", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_debug_pcn_profile", "lmpcr_debug_pool_profile", "lmpcr_debug_ktime_enable", "lmpcr_debug_ktime_read", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_softmax_unpool", "lmpcr_softmax_unpool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_launch_count_named", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_debug_pcn_profile", "lmpcr_debug_pool_profile", "lmpcr_debug_ktime_enable", "lmpcr_debug_ktime_read", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_nn_top2_algo", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_softmax_unpool", "lmpcr_softmax_unpool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
     "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
     "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
     "lmpcr_filter_pack_bytes", "lmpcr_filter_pack_weights", "lmpcr_filter_forward_packed",
@@ -65,6 +65,7 @@ def load():
     lib.lmpcr_sample_workspace_bytes.argtypes = [_i, _i]
     lib.lmpcr_sample_keypoints.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_uint64, _vp, _vp, _vp, _vp, _sz, _vp]
     lib.lmpcr_nn_top2.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]
+    lib.lmpcr_nn_top2_algo.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]
     lib.lmpcr_overlap_workspace_bytes.restype = _sz
     lib.lmpcr_overlap_workspace_bytes.argtypes = [_i]
     lib.lmpcr_overlap_count.argtypes = [_vp, _i, _vp, _i, _vp, ctypes.c_double, _vp, _vp, _vp, _sz, _vp]
@@ -168,19 +169,22 @@ def nn_argmin(q_feat, b_feat, jobs, algo=NN_EXACT_SIMT, return_dist=False):
     return (idx, dist) if return_dist else idx
 
 
-def nn_top2(q_feat, b_feat, jobs):
-    """Two nearest neighbours: (idx [J,n,2] int32, squared fp32 distances [J,n,2])  (scripts/extract_data.py:178-184)."""
+def nn_top2(q_feat, b_feat, jobs, algo=None):
+    """Two nearest neighbours: (idx [J,n,2] int32, squared fp32 distances [J,n,2])  (scripts/extract_data.py:178-184).
+    algo None: the tcgen05 path for 32-d features (bit-identical to the exact CUDA-core kernel), else NN_EXACT_SIMT."""
     lib = load()
     q = _dev(q_feat, name="q_feat")
     b = q if b_feat is q_feat else _dev(b_feat, name="b_feat")
     jobs = _dev(jobs, torch.int32, "jobs")
     J, n = jobs.shape[0], q.shape[1]
+    if algo is None:
+        algo = NN_TENSOR if (q.shape[2] == 32 and b.shape[1] >= 2) else NN_EXACT_SIMT
     with torch.cuda.device(q.device):
         idx = torch.empty((J, n, 2), dtype=torch.int32, device=q.device)
         dist = torch.empty((J, n, 2), dtype=torch.float32, device=q.device)
-        ws = _ws(lib.lmpcr_nn_workspace_bytes(q.shape[0], n, b.shape[0], b.shape[1], q.shape[2], J, NN_EXACT_SIMT), q.device)
-        _check(lib.lmpcr_nn_top2(_p(q), q.shape[0], n, _p(b), b.shape[0], b.shape[1], q.shape[2], _p(jobs), J, _p(idx), _p(dist), _p(ws),
-                                 ws.numel(), _stream(q)))
+        ws = _ws(lib.lmpcr_nn_workspace_bytes(q.shape[0], n, b.shape[0], b.shape[1], q.shape[2], J, int(algo)), q.device)
+        _check(lib.lmpcr_nn_top2_algo(_p(q), q.shape[0], n, _p(b), b.shape[0], b.shape[1], q.shape[2], _p(jobs), J, _p(idx), _p(dist), int(algo),
+                                      _p(ws), ws.numel(), _stream(q)))
     return idx, dist
 
 

@@ -233,6 +233,22 @@ int lmpcr_nn_top2(const float* q_feat, int n_q_sets, int n_q, const float* b_fea
                         (cudaStream_t)stream);
 }
 
+int lmpcr_nn_top2_algo(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim, const int32_t* jobs,
+                       int n_jobs, int32_t* idx_out, float* dist_out, int algo, void* workspace, size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  if (algo == LMPCR_NN_TENSOR) {
+    LMPCR_REQUIRE(n_jobs >= 0, LMPCR_ERR_ARG, "lmpcr_nn_top2: n_jobs < 0");
+    if (n_jobs == 0) return LMPCR_OK;
+    LMPCR_REQUIRE(q_feat && b_feat && jobs && idx_out && dist_out, LMPCR_ERR_ARG, "lmpcr_nn_top2: null pointer");
+    LMPCR_REQUIRE(n_b >= 2, LMPCR_ERR_ARG, "lmpcr_nn_top2: needs at least two target rows");
+    return launch_nn_tensor_top2(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, dim, jobs, n_jobs, idx_out, dist_out, workspace, workspace_bytes,
+                                 (cudaStream_t)stream);
+  }
+  LMPCR_REQUIRE(algo == LMPCR_NN_EXACT_SIMT, LMPCR_ERR_ARG, "lmpcr_nn_top2: unknown algo %d", algo);
+  return launch_nn_top2(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, dim, jobs, n_jobs, idx_out, dist_out, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
+}
+
 int lmpcr_nn_soft(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, const float* b_xyz, int n_b_sets, int n_b, int dim,
                   const int32_t* jobs, int n_jobs, float temperature, float* out, void* workspace, size_t workspace_bytes, void* stream) {
   LMPCR_TRY(check_device());

@@ -97,7 +97,9 @@ int launch_sample_keypoints(const float* coords, const float* feats, const int32
 size_t nn_tensor_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, int dim, int n_jobs);
 int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
                         const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, float* dbg_scores, float* approx_min,
-                        void* ws, size_t ws_bytes, cudaStream_t st);
+                        void* ws, size_t ws_bytes, cudaStream_t st, int top2 = 0);
+int launch_nn_tensor_top2(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
+                          const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_nn_tensor(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
                      const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, void* ws, size_t ws_bytes,
                      cudaStream_t st);

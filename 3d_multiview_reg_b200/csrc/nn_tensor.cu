@@ -158,14 +158,18 @@ struct SweepArgs {
 
 // DBG: the instantiation that can store the raw scores (tests) and run the timing experiments; the production instantiation carries neither
 // (the address arithmetic of the score dump alone was 9 % of the epilogue's instructions although the dump was off)
-template <bool DBG>
+// TOP2: the candidates of the TWO nearest neighbours (scripts/extract_data.py:178-184): a chunk is recorded when its minimum is within the margin of
+// the second smallest chunk minimum.  Why that is enough: every chunk other than the one holding the nearest neighbour has a true minimum >= d(2), so
+// its screened minimum is >= d(2) - E and the second smallest screened chunk minimum c(2) >= d(2) - E; the chunk holding d(2) screens at <= d(2) + E <=
+// c(2) + 2E.  (When both neighbours share a chunk that chunk is the smallest and is recorded anyway.)
+template <bool DBG, bool TOP2>
 __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + N_SETS * A_BYTES;
   uint2* ring = reinterpret_cast<uint2*>(sB + STAGES * B_BYTES);            // [CAP][EPI_THREADS]
-  float* rowmin = reinterpret_cast<float*>(ring + CAP * EPI_THREADS);       // [N_SETS][2][TM]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rowmin + N_SETS * 2 * TM);
+  float* rowmin = reinterpret_cast<float*>(ring + CAP * EPI_THREADS);       // [2][N_SETS][2][TM]: smallest / second smallest chunk minimum
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowmin + 2 * N_SETS * 2 * TM);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const uint32_t bar0 = smem_u32(bars);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
         const float E = rs.u * bmax + rs.v * dbmax + 2e-5f * (rs.na * rs.na + rs.na * bmax + bmax * bmax) + 1e-30f;
         margin = 2.02f * E;
       }
-      float run = INFINITY;
+      float run = INFINITY, run2 = INFINITY;
       uint32_t cnt = 0;
       for (int t = 0; t < n_tiles; ++t) {
         nn_wait(T_FULL(set), uses & 1);
@@ -285,8 +289,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
             mq[q] = fminf(t, __uint_as_float(cur[b + 7]));
           }
           const float m = fminf(min3(mq[0], mq[1], mq[2]), mq[3]);
-          run = fminf(run, m);
-          if (m <= run + margin) {
+          if (TOP2) {
+            if (m < run) { run2 = run; run = m; } else run2 = fminf(run2, m);
+          } else {
+            run = fminf(run, m);
+          }
+          if (m <= (TOP2 ? run2 : run) + margin) {
             ring[(cnt & (CAP - 1)) * EPI_THREADS + te] = make_uint2(__float_as_uint(m), (uint32_t)(t * 8 + half * 4 + c));
             ++cnt;
           }
@@ -321,8 +329,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) nn_sweep_kernel(SweepArgs g) {
       }
       // combine the two column halves of every row (the 256 threads of this set), then keep the chunks within `margin` of the row minimum
       rowmin[(set * 2 + half) * TM + row] = run;
+      if (TOP2) rowmin[(N_SETS * 2 + set * 2 + half) * TM + row] = run2;
       if (set == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
-      const float fin = fminf(rowmin[(set * 2) * TM + row], rowmin[(set * 2 + 1) * TM + row]);
+      float fin = fminf(rowmin[(set * 2) * TM + row], rowmin[(set * 2 + 1) * TM + row]);
+      if (TOP2) {          // second smallest of the two halves' (smallest, second smallest)
+        const float a1 = rowmin[(set * 2) * TM + row], b1 = rowmin[(set * 2 + 1) * TM + row];
+        const float a2 = rowmin[(N_SETS * 2 + set * 2) * TM + row], b2 = rowmin[(N_SETS * 2 + set * 2 + 1) * TM + row];
+        fin = fmaxf(fminf(a1, b1), fminf(fmaxf(a1, b1), fminf(a2, b2)));
+      }
       if (set == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
       uint32_t ids[3] = {0, 0, 0}, k = 0;
       bool over = cnt > CAP;
@@ -452,6 +466,87 @@ nn_rescore_kernel(const float* __restrict__ q_feat, const float* __restrict__ sq
   }
 }
 
+// The same for the two nearest neighbours (scripts/extract_data.py:178-184): every lane keeps its two best candidates in (distance, index) order, the
+// warp merges them with REDUX minima; idx_out / dist_out [rows, 2].  Identical arithmetic and tie rule as nn_top2_kernel (nn_search.cu).
+__global__ void __launch_bounds__(256, LMPCR_RESCORE_BLOCKS)
+nn_rescore_top2_kernel(const float* __restrict__ q_feat, const float* __restrict__ sqn_q, int n_q, int rows_pad_q,
+                       const float4* __restrict__ featT_b, const float* __restrict__ sqn_b, int n_b, int rows_pad_b,
+                       const int32_t* __restrict__ jobs, int n_jobs, const uint2* __restrict__ cand, const int* __restrict__ unsupported,
+                       int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+  const long long total = (long long)n_jobs * n_q;
+  const long long W = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool scan_all = (*unsupported != 0);
+  const int n_chunks = (n_b + CHUNK - 1) / CHUNK;
+  __shared__ __align__(16) float q_sm[8][D];
+  float* qrow = q_sm[threadIdx.x >> 5];
+  const float4* qa = reinterpret_cast<const float4*>(qrow);
+  for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += W) {
+    const int job = (int)(w / n_q), row = (int)(w - (long long)job * n_q);
+    const int qs = __ldg(jobs + 2 * job), bs = __ldg(jobs + 2 * job + 1);
+    const uint4 cd = __ldg(reinterpret_cast<const uint4*>(cand) + w);
+    const float an = __ldg(sqn_q + (size_t)qs * rows_pad_q + row);
+    __syncwarp();
+    qrow[lane] = __ldg(q_feat + ((size_t)qs * n_q + row) * D + lane);
+    __syncwarp();
+    const float4* tb = featT_b + (size_t)bs * rows_pad_b * 8;
+    const float* nb = sqn_b + (size_t)bs * rows_pad_b;
+    float d1 = INFINITY, d2 = INFINITY;
+    int j1 = 0x7fffffff, j2 = 0x7fffffff;
+    auto score_chunk = [&](int ch) {
+      const int j = ch * CHUNK + lane;
+      const float4* src = tb + (size_t)ch * 256 + lane;
+      float4 v[8];
+#pragma unroll
+      for (int kq = 0; kq < 8; ++kq) v[kq] = __ldg(src + kq * 32);
+      const float bnj = __ldg(nb + j);
+      float c = 0.f;
+#pragma unroll
+      for (int kq = 0; kq < 8; ++kq) {
+        const float4 a4 = qa[kq];
+        c = fmaf(a4.x, v[kq].x, c);
+        c = fmaf(a4.y, v[kq].y, c);
+        c = fmaf(a4.z, v[kq].z, c);
+        c = fmaf(a4.w, v[kq].w, c);
+      }
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(2.0f, -c), an), bnj);
+      if (j < n_b) {
+        if (d < d1 || (d == d1 && j < j1)) { d2 = d1; j2 = j1; d1 = d; j1 = j; }
+        else if (d < d2 || (d == d2 && j < j2)) { d2 = d; j2 = j; }
+      }
+    };
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const uint32_t ex = half ? cd.z : cd.x, ey = half ? cd.w : cd.y;
+      const uint32_t c16 = ex & 0xFFFFu;
+      if (scan_all || c16 == OVERFLOW) {
+        for (int ch = 0; ch < n_chunks; ++ch)
+          if (((ch >> 2) & 1) == half) score_chunk(ch);
+      } else {
+        if (c16 > 0) score_chunk((int)(ex >> 16));
+        if (c16 > 1) score_chunk((int)(ey & 0xFFFFu));
+        if (c16 > 2) score_chunk((int)(ey >> 16));
+      }
+    }
+    // two rounds of (REDUX minimum of the monotone distance image, REDUX minimum of the index among its holders); the lane that owned the
+    // winner of round one promotes its runner-up
+    auto keyof = [](float d) { uint32_t k = __float_as_uint(d); return k ^ ((k >> 31) ? 0xffffffffu : 0x80000000u); };
+    auto unkey = [](uint32_t k) { return __uint_as_float((k >> 31) ? (k ^ 0x80000000u) : ~k); };
+    uint32_t k1 = keyof(d1);
+    const uint32_t g1 = __reduce_min_sync(0xffffffffu, k1);
+    const uint32_t i1 = __reduce_min_sync(0xffffffffu, k1 == g1 ? (uint32_t)j1 : 0x7fffffffu);
+    if (k1 == g1 && (uint32_t)j1 == i1) { d1 = d2; j1 = j2; k1 = keyof(d1); }
+    const uint32_t g2 = __reduce_min_sync(0xffffffffu, k1);
+    const uint32_t i2 = __reduce_min_sync(0xffffffffu, k1 == g2 ? (uint32_t)j1 : 0x7fffffffu);
+    if (lane == 0) {
+      idx_out[2 * w] = ((int)i1 < n_b) ? (int)i1 : 0;
+      idx_out[2 * w + 1] = ((int)i2 < n_b) ? (int)i2 : 0;
+      dist_out[2 * w] = unkey(g1);
+      dist_out[2 * w + 1] = unkey(g2);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- host side
 struct Prep {
   uint8_t *form_q, *form_b; float4* feat_t; float* sqn; RowStat* rstat; int *bmax, *dbmax;
@@ -487,7 +582,7 @@ int run_prep(const float* feat, int n_sets, int n, const Prep& P, int* unsupport
   return check_launch("nn_prep_kernel");
 }
 
-constexpr size_t SWEEP_SMEM = (size_t)N_SETS * A_BYTES + (size_t)STAGES * B_BYTES + (size_t)CAP * EPI_THREADS * 8 + (size_t)N_SETS * 2 * TM * 4 + 16 * 8 + 16;
+constexpr size_t SWEEP_SMEM = (size_t)N_SETS * A_BYTES + (size_t)STAGES * B_BYTES + (size_t)CAP * EPI_THREADS * 8 + (size_t)2 * N_SETS * 2 * TM * 4 + 16 * 8 + 16;
 
 }  // namespace
 
@@ -498,7 +593,7 @@ size_t nn_tensor_workspace_bytes(int n_q_sets, int n_q, int n_b_sets, int n_b, i
 
 int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
                         const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, float* dbg_scores, float* approx_min,
-                        void* ws, size_t ws_bytes, cudaStream_t st) {
+                        void* ws, size_t ws_bytes, cudaStream_t st, int top2) {
   LMPCR_REQUIRE(dim == D, LMPCR_ERR_UNSUPPORTED, "lmpcr_nn_argmin: LMPCR_NN_TENSOR needs dim == 32 (got %d)", dim);
   LMPCR_REQUIRE(n_b <= 65535 * CHUNK, LMPCR_ERR_UNSUPPORTED, "lmpcr_nn_argmin: too many target rows for the tensor path");
   LMPCR_REQUIRE(ws_bytes >= nn_tensor_workspace_bytes(n_q_sets, n_q, n_b_sets, n_b, dim, n_jobs), LMPCR_ERR_WORKSPACE, "lmpcr_nn_argmin: workspace too small");
@@ -523,8 +618,9 @@ int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float*
     static unsigned char attr_set[64];
     const int dev = device_ordinal();
     if (!attr_set[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(nn_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
+      cudaError_t e = cudaFuncSetAttribute(nn_sweep_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_sweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_sweep_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
       LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "nn_sweep_kernel: cannot reserve %zu bytes of shared memory: %s", SWEEP_SMEM, cudaGetErrorString(e));
       attr_set[dev] = 1;
     }
@@ -537,14 +633,22 @@ int launch_nn_tensor_ex(const float* q_feat, int n_q_sets, int n_q, const float*
   const long long items = (long long)n_jobs * ((n_q + 2 * TM - 1) / (2 * TM));
   const int grid = (int)(items < sm_count() ? items : sm_count());
   ktime_begin("nn_sweep_kernel", st);
-  if (a.dbg_scores || a.debug) nn_sweep_kernel<true><<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
-  else nn_sweep_kernel<false><<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
+  if (top2) nn_sweep_kernel<false, true><<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
+  else if (a.dbg_scores || a.debug) nn_sweep_kernel<true, false><<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
+  else nn_sweep_kernel<false, false><<<grid, NTHREADS, SWEEP_SMEM, st>>>(a);
   ktime_end("nn_sweep_kernel", st);
   LMPCR_TRY(check_launch("nn_sweep_kernel"));
   ktime_begin("nn_rescore_kernel", st);
   const long long warps = (long long)n_jobs * n_q;
   const long long max_blocks = (long long)LMPCR_RESCORE_BLOCKS * sm_count();            // resident blocks of 8 persistent warps per SM
   const long long want_blocks = (warps + 7) / 8;
+  if (top2) {
+    LMPCR_REQUIRE(dist_out, LMPCR_ERR_ARG, "lmpcr_nn_top2: dist_out is required");
+    nn_rescore_top2_kernel<<<(unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks), 256, 0, st>>>(q_feat, PQ.sqn, n_q, PQ.rows_pad, PB.feat_t, PB.sqn, n_b,
+                                                                                PB.rows_pad, jobs, n_jobs, cand, unsupported, idx_out, dist_out);
+    ktime_end("nn_rescore_kernel", st);
+    return check_launch("nn_rescore_top2_kernel");
+  }
   nn_rescore_kernel<<<(unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks), 256, 0, st>>>(q_feat, PQ.sqn, n_q, PQ.rows_pad, PB.feat_t, PB.sqn, n_b, PB.rows_pad, jobs,
                                                                          n_jobs, cand, unsupported, idx_out, dist_out);
   ktime_end("nn_rescore_kernel", st);
@@ -555,7 +659,13 @@ int launch_nn_tensor(const float* q_feat, int n_q_sets, int n_q, const float* b_
                      const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, void* ws, size_t ws_bytes,
                      cudaStream_t st) {
   return launch_nn_tensor_ex(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, dim, jobs, n_jobs, idx_out, dist_out, nullptr, nullptr, ws,
-                             ws_bytes, st);
+                             ws_bytes, st, 0);
+}
+
+int launch_nn_tensor_top2(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim,
+                          const int32_t* jobs, int n_jobs, int32_t* idx_out, float* dist_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return launch_nn_tensor_ex(q_feat, n_q_sets, n_q, b_feat, n_b_sets, n_b, dim, jobs, n_jobs, idx_out, dist_out, nullptr, nullptr, ws,
+                             ws_bytes, st, 1);
 }
 
 }  // namespace lmpcr

@@ -6,7 +6,8 @@ pairs of a scene on the CPU (sklearn brute-force 2-NN in both directions) and wr
     mutuals [n,1]  float64, 1 where nn_12[nn_21[j,0],0] == j                                             (:186-190)
     ratios  [n]    float64, d1/d2 of the 1->2 search (Lowe ratio; indexed by points of the FIRST fragment) (:191)
 
-Here all pairs of a scene go through `lmpcr_nn_top2` (exact fp32 CUDA kernel) in batched launches and the three arrays
+Here all pairs of a scene go through `lmpcr_nn_top2_algo` (tcgen05 screening + exact fp32 rescoring for 32-d features, bit-identical to the exact
+fp32 CUDA-core kernel `lmpcr_nn_top2`) in batched launches and the three arrays
 are assembled on the GPU.  File naming and keys follow the reference so that its PrecomputedPairwiseDataset-style readers
 (lib/data.py) consume the files unchanged.  The random subsampling of :160-168 stays with the caller (pass the rows you
 want); see `sample_indices` for the same with/without-replacement rule.

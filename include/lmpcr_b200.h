@@ -115,6 +115,11 @@ int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, in
  * reference's torch formula (the ratio of Euclidean distances is sqrt(d1/d2)).  fp32 CUDA cores, dim == 32. */
 int lmpcr_nn_top2(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim, const int32_t* jobs,
                   int n_jobs, int32_t* idx_out, float* dist_out, void* workspace, size_t workspace_bytes, void* stream);
+/* The same with the algorithm chosen by the caller: LMPCR_NN_EXACT_SIMT as above, LMPCR_NN_TENSOR = tcgen05 screening (the chunks within the
+ * margin of the SECOND smallest chunk minimum are recorded) + exact fp32 evaluation of the recorded chunks -- indices and distances bit-identical
+ * to the CUDA-core kernel, ~10x its throughput.  workspace from lmpcr_nn_workspace_bytes(..., algo). */
+int lmpcr_nn_top2_algo(const float* q_feat, int n_q_sets, int n_q, const float* b_feat, int n_b_sets, int n_b, int dim, const int32_t* jobs,
+                       int n_jobs, int32_t* idx_out, float* dist_out, int algo, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Soft (non straight-through) correspondences, lib/layers.py:59-70,86 `Soft_NN(corr_type='soft', st=False)` -- the demo
  * configuration (configs/pairwise_registration/demo/config.yaml):

@@ -81,9 +81,33 @@ def test_gpu_top2_exact_on_ties_and_ragged_sizes():
     q = torch.from_numpy(feats[0][None, :515].copy()).cuda()
     b = torch.from_numpy(fb[None]).cuda()
     jobs = torch.tensor([[0, 0]], dtype=torch.int32, device="cuda")
-    idx, dist = cabi.nn_top2(q, b, jobs)
     oi, od = O.nn_top2_f32(feats[0][:515], fb)
-    assert np.array_equal(idx[0].cpu().numpy(), oi) and np.array_equal(dist[0].cpu().numpy(), od)
+    for algo in (None, cabi.NN_EXACT_SIMT):            # tcgen05 screening + exact rescoring (default for 32-d) and the exact CUDA-core kernel
+        idx, dist = cabi.nn_top2(q, b, jobs, algo=algo)
+        assert np.array_equal(idx[0].cpu().numpy(), oi) and np.array_equal(dist[0].cpu().numpy(), od), algo
     assert np.array_equal(oi[:, 1], oi[:, 0] + 300)
     with pytest.raises(cabi.LmpcrError):
         cabi.nn_top2(q, b[:, :1].contiguous(), jobs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m", [(5000, 5000), (2049, 777), (130, 4100)])
+def test_gpu_top2_tensor_path_is_bit_identical_to_the_exact_kernel(n, m):
+    """Two nearest neighbours on the tcgen05 path (chunks within the margin of the SECOND smallest chunk minimum, exact rescoring) against the
+    exact CUDA-core kernel: indices and squared distances identical, both directions of a pair, un-normalised features included."""
+    import importlib
+    import torch
+    cabi = importlib.import_module("3d_multiview_reg_b200._cabi")
+    rng = np.random.default_rng(n * 7 + m)
+    fa = rng.standard_normal((1, n, 32)).astype(np.float32)
+    fb = rng.standard_normal((1, m, 32)).astype(np.float32)
+    fa /= np.linalg.norm(fa, axis=2, keepdims=True)
+    fb *= (0.5 + rng.random((1, m, 1))).astype(np.float32) / np.linalg.norm(fb, axis=2, keepdims=True)      # norms between 0.5 and 1.5
+    q, b = torch.from_numpy(fa).cuda(), torch.from_numpy(fb).cuda()
+    jobs = torch.tensor([[0, 0]], dtype=torch.int32, device="cuda")
+    it, dt = cabi.nn_top2(q, b, jobs, algo=cabi.NN_TENSOR)
+    ie, de = cabi.nn_top2(q, b, jobs, algo=cabi.NN_EXACT_SIMT)
+    assert torch.equal(it, ie) and torch.equal(dt, de)
+    it2, dt2 = cabi.nn_top2(b, q, jobs, algo=cabi.NN_TENSOR)
+    ie2, de2 = cabi.nn_top2(b, q, jobs, algo=cabi.NN_EXACT_SIMT)
+    assert torch.equal(it2, ie2) and torch.equal(dt2, de2)

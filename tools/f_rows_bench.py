@@ -31,7 +31,8 @@ def timed(fn):
 P = len(allp)
 for name, fn in (("hard NN, tcgen05 screening + exact rescoring (both directions)", lambda: cabi.nn_argmin(f, f, jobs, algo=cabi.NN_TENSOR)),
                  ("hard NN, exact CUDA-core kernel (both directions)", lambda: cabi.nn_argmin(f, f, jobs, algo=cabi.NN_EXACT_SIMT)),
-                 ("2-NN + distances for the Lowe ratio, exact CUDA-core kernel (both directions)", lambda: cabi.nn_top2(f, f, jobs)),
+                 ("2-NN + distances for the Lowe ratio, tcgen05 screening + exact rescoring (both directions)", lambda: cabi.nn_top2(f, f, jobs)),
+                 ("2-NN + distances for the Lowe ratio, exact CUDA-core kernel (both directions)", lambda: cabi.nn_top2(f, f, jobs, algo=cabi.NN_EXACT_SIMT)),
                  ("soft correspondences, exact CUDA-core online softmax (both directions)", lambda: cabi.nn_soft(f, f, x, jobs, 0.09))):
     ms = timed(fn)
     print("%-84s %8.2f ms per %d pairs x %d pts = %7.1f us/pair, %8.0f pairs/s" % (name, ms, P, a.points, 1e3 * ms / P, P / ms * 1e3))
