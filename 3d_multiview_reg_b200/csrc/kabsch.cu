@@ -1,10 +1,12 @@
-// Stage 3: weighted Kabsch / Procrustes + residuals + per-pair confidence, ONE WARP PER SCAN PAIR.
+// Stage 3: weighted Kabsch / Procrustes + residuals + per-pair confidence, ONE CTA (8 WARPS) PER SCAN PAIR.
 //
 // Replaces lib/utils.py:164-237 (kabsch_transformation_estimation) and :240-256 (transformation_residuals).
 // The reference builds a [P,N,N] diag_embed weight matrix (100 MB per pair at N=5000) and calls cuSOLVER /
-// LAPACK for a 3x3 SVD; here a warp streams the N correspondences three times (weighted sums, centred
-// 3x3 covariance, residuals -- the 140 KB of a pair stay in L1/L2 between sweeps), reduces with shuffles
-// and lane 0 solves the 3x3 problem in registers.  HBM-bound: 28 B per correspondence of compulsory traffic.
+// LAPACK for a 3x3 SVD; here a CTA streams the N correspondences three times (weighted sums, centred
+// 3x3 covariance, residuals -- the 140 KB of a pair stay in L1/L2 between sweeps), reduces with shuffles and a
+// fixed-order sum over its warps (deterministic), and thread 0 solves the 3x3 problem in registers.
+// HBM-bound: 28 B per correspondence of compulsory traffic.  (Round 1 ran one warp per pair: at 296 pairs per
+// call that left two warps per SM and 158 us per launch of pure latency.)
 #include <math.h>
 
 #include "common.cuh"
@@ -12,7 +14,7 @@
 namespace lmpcr {
 namespace {
 
-constexpr int KB_WARPS = 4;  // warps (= pairs) per CTA
+constexpr int KB_WARPS = 8;  // warps of the CTA that owns a pair (one warp per pair left 2 warps per SM at 296 pairs: 158 us per launch, latency-bound)
 
 struct Sym3 {
   double a[3][3];
@@ -106,12 +108,35 @@ __device__ bool rotation_from_cov(const float H[9], float Rout[9]) {
   return true;
 }
 
+// Deterministic block sums: every warp reduces its K values by shuffles, lane 0 parks them in shared memory, and EVERY thread adds the warps'
+// partials in the same fixed order, so all threads hold bit-identical totals (no broadcast needed, no atomics).
+template <int K>
+__device__ __forceinline__ void block_sum(float (&v)[K], float (*scratch)[16]) {
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();                                   // the previous use of the scratch has been read
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) scratch[wp][k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float t = scratch[0][k];
+    for (int w2 = 1; w2 < KB_WARPS; ++w2) t += scratch[w2][k];
+    v[k] = t;
+  }
+}
+
 __global__ void __launch_bounds__(KB_WARPS * 32)
 kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int ld, const float* wg, int P,
               int N, int guard_mode, const int32_t* __restrict__ guard_flag, float* w_out, float* __restrict__ Rg,
               float* __restrict__ tg, float* __restrict__ resg, float* __restrict__ confg, uint32_t* statusg) {
-  const int lane = threadIdx.x & 31;
-  const int p = blockIdx.x * KB_WARPS + (threadIdx.x >> 5);
+  __shared__ float scratch[KB_WARPS][16];
+  __shared__ float pose[16];
+  const int tid = threadIdx.x, nth = KB_WARPS * 32;
+  const int p = blockIdx.x;                          // one CTA per pair
   if (p >= P) return;
   const float* x1 = x1g + (size_t)p * N * ld;
   const float* x2 = x2g + (size_t)p * N * ld;
@@ -127,7 +152,7 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
     const float add = guard ? invN : 0.0f;
     float s0 = 0.f, sraw = 0.f, b1[3] = {0.f, 0.f, 0.f}, b2[3] = {0.f, 0.f, 0.f};
 #pragma unroll 4
-    for (int i = lane; i < N; i += 32) {
+    for (int i = tid; i < N; i += nth) {
       const float wraw = w[i];
       const float wi = wraw + add;
       const float* r1 = x1 + (size_t)i * ld;
@@ -140,13 +165,15 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
         b2[c] = fmaf(wi, __ldg(r2 + c), b2[c]);
       }
     }
-    S0 = warp_sum(s0);
+    float red[8] = {s0, sraw, b1[0], b1[1], b1[2], b2[0], b2[1], b2[2]};
+    block_sum<8>(red, scratch);
+    S0 = red[0];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      a1[c] = warp_sum(b1[c]);
-      a2[c] = warp_sum(b2[c]);
+      a1[c] = red[2 + c];
+      a2[c] = red[5 + c];
     }
-    if (warp_sum(sraw) == 0.0f) st |= LMPCR_STATUS_ZERO_WEIGHT;   // all weights of this pair are zero
+    if (red[1] == 0.0f) st |= LMPCR_STATUS_ZERO_WEIGHT;   // all weights of this pair are zero
     if (S0 == 0.0f && !guard) {
       if (guard_mode == LMPCR_GUARD_PAIR) {
         guard = true;
@@ -171,7 +198,7 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
 #pragma unroll
   for (int k = 0; k < 9; ++k) h[k] = 0.f;
 #pragma unroll 2
-  for (int i = lane; i < N; i += 32) {
+  for (int i = tid; i < N; i += nth) {
     const float wi = (w[i] + add) / denom;
     const float* r1 = x1 + (size_t)i * ld;
     const float* r2 = x2 + (size_t)i * ld;
@@ -186,13 +213,12 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
 #pragma unroll
       for (int b = 0; b < 3; ++b) h[3 * a + b] = fmaf(c1[a], c2[b], h[3 * a + b]);
   }
-#pragma unroll
-  for (int k = 0; k < 9; ++k) h[k] = warp_sum(h[k]);
+  block_sum<9>(h, scratch);
 
-  // ---- 3x3 SVD + rotation (lane 0), broadcast ----
+  // ---- 3x3 SVD + rotation (thread 0), broadcast through shared memory ----
   float R[9], T[3];
   int ok = 1;
-  if (lane == 0) {
+  if (tid == 0) {
     ok = rotation_from_cov(h, R) ? 1 : 0;
     if (!ok) {
 #pragma unroll
@@ -206,11 +232,19 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
       for (int a = 0; a < 3; ++a) T[a] = m2[a] - (R[3 * a] * m1[0] + R[3 * a + 1] * m1[1] + R[3 * a + 2] * m1[2]);  // :232
     }
   }
-  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (tid == 0) {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = __shfl_sync(0xffffffffu, R[k], 0);
+    for (int k = 0; k < 9; ++k) pose[k] = R[k];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) T[k] = __shfl_sync(0xffffffffu, T[k], 0);
+    for (int k = 0; k < 3; ++k) pose[9 + k] = T[k];
+    pose[12] = (float)ok;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = pose[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) T[k] = pose[9 + k];
+  ok = pose[12] != 0.f;
   if (!ok) st |= LMPCR_STATUS_DEGENERATE;
 
   // ---- sweep 3: residuals (:252-254) + confidence ----
@@ -219,7 +253,7 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
   int n_inl = 0, n_close = 0;
   float wr2 = 0.f;
 #pragma unroll 2
-  for (int i = lane; i < N; i += 32) {
+  for (int i = tid; i < N; i += nth) {
     const float wi = w[i] + add;
     const float* r1 = x1 + (size_t)i * ld;
     const float* r2 = x2 + (size_t)i * ld;
@@ -235,10 +269,10 @@ kabsch_kernel(const float* __restrict__ x1g, const float* __restrict__ x2g, int 
     n_close += (r < 0.05f);
     wr2 = fmaf(wi / denom, r2n, wr2);
   }
-  n_inl = warp_sum_i(n_inl);
-  n_close = warp_sum_i(n_close);
-  wr2 = warp_sum(wr2);
-  if (lane == 0) {
+  float fin[3] = {(float)n_inl, (float)n_close, wr2};          // counts <= N < 2^24: exact in fp32
+  block_sum<3>(fin, scratch);
+  n_inl = (int)fin[0]; n_close = (int)fin[1]; wr2 = fin[2];
+  if (tid == 0) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) Rg[(size_t)p * 9 + k] = R[k];
 #pragma unroll
@@ -294,8 +328,7 @@ int launch_kabsch(const float* x1, const float* x2, int ld, const float* w, int 
   LMPCR_REQUIRE(x1 && x2 && w && R && t, LMPCR_ERR_ARG, "lmpcr_kabsch: null pointer");
   LMPCR_REQUIRE(P >= 0 && N >= 1 && ld >= 3, LMPCR_ERR_ARG, "lmpcr_kabsch: bad sizes P=%d N=%d ld=%d", P, N, ld);
   if (P == 0) return LMPCR_OK;
-  const int grid = (P + KB_WARPS - 1) / KB_WARPS;
-  kabsch_kernel<<<grid, KB_WARPS * 32, 0, st>>>(x1, x2, ld, w, P, N, guard_mode, guard_flag, w_out, R, t, res, conf, status);
+  kabsch_kernel<<<P, KB_WARPS * 32, 0, st>>>(x1, x2, ld, w, P, N, guard_mode, guard_flag, w_out, R, t, res, conf, status);
   return check_launch("kabsch_kernel");
 }
 
