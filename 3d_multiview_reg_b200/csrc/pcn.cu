@@ -17,9 +17,10 @@
 // Warp roles (704 threads, one CTA per SM):
 //   warp 0       TMA: x tile loads (+ L2 prefetch a few tiles ahead), output tile stores
 //   warp 1       tcgen05.mma issue (M128 x N64 x K16, 24 per GEMM tile of 64 points)
-//   warps 2-5    TMEM readers A: pass A statistics of y; pass B f2 + hi/lo split -> h2
+//   warps 2-5    TMEM readers A: pass A statistics of y (first box; warps 6-9 take the second box in pass A); pass B f2 + hi/lo split -> h2
 //   warps 6-13   TMEM readers B: pass B epilogue (z + b2 + x, statistics, tile written back over the x tile); 6-9 first box, 10-13 second
-//   warps 14-21  producers: x tile (smem, fp32) -> f1 -> hi/lo split -> h1 (warps 14-17 the first box of a tile, 18-21 the second)
+//   warps 14-21  producers: x tile (smem, fp32) -> f1 -> hi/lo split -> h1 (warps 14-17 the first box of a tile, 18-21 the second; in pass A
+//                warps 10-13 join as a third group and the boxes go round-robin)
 // Thread t of every 4-warp role owns channel ((warp & 3) << 5) | lane = the TMEM lane its warp may read.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -138,7 +139,7 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   const int ch = ((warp & 3) << 5) | lane;                 // channel row / TMEM lane owned by this thread in the 4-warp roles
   const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
   const int n_tiles = (g.N + TP - 1) / TP;
-  const bool prof_me = PROFILE && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6 || warp == 14);
+  const bool prof_me = PROFILE && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 7 || warp == 14);
   long long tp = clock64();
   const uint32_t sX = smem_u32(smem + OFF_X), sH1 = smem_u32(smem + OFF_H1), sH2 = smem_u32(smem + OFF_H2);
 
@@ -151,12 +152,12 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
 
   // all barriers are re-initialised at the start of every pass (the pipeline is fully drained at a pass boundary), so the phase
   // arithmetic of every role is local to a pass: use k of a ring slot / of a single barrier completes phase k
-  auto pass_begin = [&]() {
+  auto pass_begin = [&](int y_readers) {
     if (threadIdx.x == 0) {
       for (int s = 0; s < NX; ++s) { mbar_init(XFULL(s), 1); mbar_init(XREAD(s), 8); mbar_init(OUTRDY(s), 8); }
       for (int a = 0; a < 2; ++a) {
         mbar_init(H1FULL(a), 8); mbar_init(H1EMPTY(a), 1); mbar_init(H2FULL(a), 4); mbar_init(H2EMPTY(a), 1);
-        mbar_init(YFULL(a), 1); mbar_init(YEMPTY(a), 128); mbar_init(ZFULL(a), 1); mbar_init(ZEMPTY(a), 256);
+        mbar_init(YFULL(a), 1); mbar_init(YEMPTY(a), y_readers); mbar_init(ZFULL(a), 1); mbar_init(ZEMPTY(a), 256);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -235,7 +236,7 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     for (int l = 0; l < g.n_layers; ++l) {
       const PcnLayer& L = g.layer[l];
       const CUtensorMap* tm_src = (l == 0) ? &tm_in : &tm_out;
-      if (warp >= 14) {
+      if (warp >= 10) {                     // producers (warps 10-13 produce in pass A only)
         if (l == 0) { sc1 = __ldg(g.scale0 + (size_t)p * C + ch); sh1 = __ldg(g.shift0 + (size_t)p * C + ch); }
         else { sc1 = sc1_s[ch]; sh1 = sh1_s[ch]; }
       }
@@ -246,7 +247,7 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         tc_fence_before();
       }
       // ======================================================== pass A: statistics of y = W1 f1(x) + b1
-      pass_begin();
+      pass_begin(256);                       // pass A: both 4-warp reader groups read Y (one box each)
       tc_fence_after();
       if (warp == 0) {
         if (lane == 0) {
@@ -278,31 +279,50 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           const int uses = (n_tiles + 1 - b) >> 1;
           if (uses > 0) pcn_wait(H1EMPTY(b), (uses - 1) & 1);
         }
-      } else if (warp < 6) {
-        rs.reset();                          // statistics of the raw accumulator: the bias only shifts the mean
+      } else if (warp < 10) {
+        // statistics of the raw accumulator (the bias only shifts the mean): warps 2-5 take the first box of every tile, warps 6-9 (pass-B
+        // epilogue warps, idle here otherwise) the second; the two partial (mean, M2) of every channel are merged (Chan) by the first group
+        const int sub = (warp >= 6) ? 1 : 0;
+        rs.reset();
+        int n_seen = 0;
         for (int t = 0; t < n_tiles; ++t) {
           const int a = t & 1;
           PROF(5);
           pcn_wait(YFULL(a), (t >> 1) & 1);
           PROF(6);
           tc_fence_after();
-#pragma unroll
-          for (int sub = 0; sub < NSUB; ++sub) {
-            float v[TS];
-            tc_ld32(tmY + lane_sel + a * TP + sub * TS, v);
-            if (sub == NSUB - 1) { tc_fence_before(); mbar_arrive(YEMPTY(a)); }
-            rs.add_tile(v, g.N - t * TP - sub * TS);
-          }
+          float v[TS];
+          tc_ld32(tmY + lane_sel + a * TP + sub * TS, v);
+          tc_fence_before();
+          mbar_arrive(YEMPTY(a));
+          const int ncv = g.N - t * TP - sub * TS;
+          rs.add_tile(v, ncv);
+          if (ncv > 0) n_seen += ncv < TS ? ncv : TS;
         }
-        const float b1 = __ldg(L.b1 + ch);
-        float mean, var;
-        rs.finish(g.N, mean, var);
-        fold_affine(mean + b1, var, 1e-5f, L.bn2, ch, sc2, sh2);
-        sh2 = fmaf(b1, sc2, sh2);            // f2(acc + b1) = relu(acc * sc2 + (b1 * sc2 + sh2))
-      } else if (warp >= 14) {
-        const int sub = (warp >= 18) ? 1 : 0;
-        for (int t = 0; t < n_tiles; ++t) {
-          const int s = t % NX;
+        float mean_p = 0.f, m2_p = 0.f;
+        if (n_seen > 0) {
+          const float inv = 1.0f / (float)n_seen, m = rs.s1 * inv;
+          mean_p = rs.c0 + m;
+          m2_p = fmaxf(rs.s2 - rs.s1 * m, 0.f);
+        }
+        float* mg = reinterpret_cast<float*>(smem + OFF_H2);          // the h2 tile is unused in this pass
+        if (sub == 1) { mg[ch] = mean_p; mg[C + ch] = m2_p; mg[2 * C + ch] = (float)n_seen; }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (sub == 0) {
+          const float mb = mg[ch], m2b = mg[C + ch], nb = mg[2 * C + ch], na = (float)n_seen, n = na + nb;
+          const float delta = mb - mean_p;
+          const float mean = mean_p + delta * (nb / n);
+          const float var = fmaxf((m2_p + m2b + delta * delta * (na * nb / n)) / n, 0.f);
+          const float b1 = __ldg(L.b1 + ch);
+          fold_affine(mean + b1, var, 1e-5f, L.bn2, ch, sc2, sh2);
+          sh2 = fmaf(b1, sc2, sh2);            // f2(acc + b1) = relu(acc * sc2 + (b1 * sc2 + sh2))
+        }
+      } else if (warp >= 10) {
+        // THREE producer groups in this pass (warps 10-13, idle as epilogue warps here, join 14-17 and 18-21): the boxes of the tile sequence
+        // (box u = 2 t + sub) go round-robin to the groups, every tile still collects its eight warp arrivals
+        const int grp = (warp - 10) >> 2;
+        for (int u = grp; u < 2 * n_tiles; u += 3) {
+          const int t = u >> 1, sub = u & 1, s = t % NX;
           PROF(7);
           pcn_wait(XFULL(s), (t / NX) & 1);
           PROF(8);
@@ -318,7 +338,7 @@ pcn_stack_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
       if (warp != 0) tp = clock64(); else PROF(10);     // 28: rest of pass A as seen by the loader thread (drain)
       // ======================================================== pass B: z = x + W2 f2(W1 f1(x) + b1) + b2
       const CUtensorMap* tm_dst = &tm_out;
-      pass_begin();
+      pass_begin(128);
       if (warp == 0) {
         if (lane == 0) {
           const bool do_store = g.store_out || l + 1 < g.n_layers;      // with the fused head the last layer's tiles may stay on chip
