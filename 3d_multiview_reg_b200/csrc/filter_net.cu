@@ -18,6 +18,7 @@
 #include "pcn.cuh"
 #include "pool_fused.cuh"
 #include "conv_wide.cuh"
+#include "unpool_fused.cuh"
 
 namespace lmpcr {
 namespace {
@@ -831,7 +832,8 @@ int launch_pointcn_stack(const float* x, int P, int N, const float* const* param
 }
 
 // diff_unpool's weighted sum alone (oanet.py:126-128): out[p,c,n] = sum_k x_down[p,c,k] * softmax_k(E[p,:,n])[k]; tensor-core path.
-// mode 0: softmax max / sum by a separate pass, normalised weights as the B operand; mode 1: deferred normalisation.
+// mode 0: softmax max / sum by a separate pass, normalised weights as the B operand; mode 1: deferred normalisation; mode 2: the
+// pair-resident kernel of unpool_fused.cu (what the network runs for groups of 64 pairs and more).
 size_t softmax_unpool_workspace_bytes(int P, int C, int K, int N) {
   return align_up((size_t)P * tc_weight_blob_bytes(C, K), 256) + 2 * align_up((size_t)P * N * 4, 256) + 256;
 }
@@ -839,7 +841,7 @@ size_t softmax_unpool_workspace_bytes(int P, int C, int K, int N) {
 int launch_softmax_unpool(const float* x_down, const float* E, int P, int C, int K, int N, int mode, float* out, void* ws, size_t ws_bytes,
                           cudaStream_t st) {
   LMPCR_REQUIRE(x_down && E && out && P >= 0 && C > 0 && K > 0 && N > 0, LMPCR_ERR_ARG, "lmpcr_softmax_unpool: bad arguments");
-  LMPCR_REQUIRE(mode == 0 || (mode == 1 && K >= TC_DEFER_MIN_K && (N & 3) == 0), LMPCR_ERR_ARG, "lmpcr_softmax_unpool: mode 1 needs clusters >= %d and n_pts %% 4 == 0", TC_DEFER_MIN_K);
+  LMPCR_REQUIRE(mode == 0 || ((mode == 1 || mode == 2) && K >= TC_DEFER_MIN_K && (N & 3) == 0), LMPCR_ERR_ARG, "lmpcr_softmax_unpool: modes 1 and 2 need clusters >= %d and n_pts %% 4 == 0", TC_DEFER_MIN_K);
   LMPCR_REQUIRE(ws && ws_bytes >= softmax_unpool_workspace_bytes(P, C, K, N) && ((uintptr_t)ws & 255) == 0, LMPCR_ERR_WORKSPACE, "lmpcr_softmax_unpool: workspace");
   if (P == 0) return LMPCR_OK;
   char* w = reinterpret_cast<char*>(ws);
@@ -849,9 +851,16 @@ int launch_softmax_unpool(const float* x_down, const float* E, int P, int C, int
   const size_t tot = (size_t)P * N;
   softmax_colstats_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(E, K, N, P, cmax, cinv);
   LMPCR_TRY(check_launch("softmax_colstats_kernel"));
-  if (mode == 1) {
+  if (mode >= 1) {
     scale_inplace_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cmax, tot, 1.4426950408889634f);
     LMPCR_TRY(check_launch("scale_inplace_kernel"));
+  }
+  if (mode == 2) {   // the pair-resident kernel (unpool_fused.cu)
+    LMPCR_REQUIRE(unpool_fused_supported(C, K, N, x_down, (long long)C * K, K, E, (long long)K * N, out, (long long)C * N), LMPCR_ERR_UNSUPPORTED,
+                  "lmpcr_softmax_unpool: mode 2 needs 128 channels, 256 < clusters <= 512, clusters %% 4 == 0 and 16-byte aligned tensors");
+    UnpoolFusedArgs ua{};
+    ua.cmax = cmax; ua.stats_out = nullptr; ua.P = P; ua.N = N; ua.K = K;
+    return launch_unpool_fused(x_down, (long long)C * K, K, E, (long long)K * N, out, (long long)C * N, ua, st);
   }
   LMPCR_TRY(launch_split_weights(x_down, C, K, blob, st, P, (long long)C * K, K));
   TcGemmArgs a{};
@@ -939,6 +948,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   const int wide_on = getenv("LMPCR_CONV_WIDE") ? atoi(getenv("LMPCR_CONV_WIDE")) : 1;            // 0: l1_2.0's shot_cut / conv.3 as two GEMM launches (A/B runs)
   const int embed_on = getenv("LMPCR_EMBED_FUSED") ? atoi(getenv("LMPCR_EMBED_FUSED")) : 1;       // 0: the `up` embedding conv as convert_b + GEMM (A/B runs)
   const int pool_on = getenv("LMPCR_POOL_FUSED") ? atoi(getenv("LMPCR_POOL_FUSED")) : 1;         // 0: diff_pool as embedding GEMM + pooling GEMM (A/B runs)
+  const int unpool_on = getenv("LMPCR_UNPOOL_FUSED") ? atoi(getenv("LMPCR_UNPOOL_FUSED")) : 1;   // 0: diff_unpool's product on the generic GEMM (A/B runs)
   const int pcn_min_pairs = getenv("LMPCR_PCN_MIN_PAIRS") ? atoi(getenv("LMPCR_PCN_MIN_PAIRS")) : 64;
   LMPCR_REQUIRE(n_params == filter_num_params(cfg), LMPCR_ERR_ARG, "lmpcr_filter_forward: expected %d parameter tensors, got %d", filter_num_params(cfg), n_params);
   for (int i = 0; i < n_params; ++i) LMPCR_REQUIRE(params[i], LMPCR_ERR_ARG, "lmpcr_filter_forward: params[%d] is null", i);
@@ -1308,6 +1318,15 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
           softmax_colstats_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g, sm_max, sm_inv);
           LMPCR_TRY(check_launch("softmax_colstats_kernel"));
         }
+        const int oi_up = part_index(W.CAT + CN);
+        if (unpool_on && defer_up && g >= pcn_min_pairs &&
+            unpool_fused_supported(C, K, N, xd_in, CK, KP, W.E, (long long)K * N, W.CAT + CN, 2 * CN)) {
+          // pair-resident product: x2 on chip (tensor memory + shared memory) for all point tiles of the pair, E by TMA, sums in the producers
+          UnpoolFusedArgs ua{};
+          ua.cmax = sm_max; ua.stats_out = part_buf[oi_up]; ua.P = g; ua.N = N; ua.K = K;
+          part_valid[oi_up] = true; part_whole[oi_up] = false;
+          LMPCR_TRY(launch_unpool_fused(xd_in, CK, KP, W.E, (long long)K * N, W.CAT + CN, 2 * CN, ua, st));
+        } else {
         TcGemmArgs a{};   // x_up[c,n] = sum_k x2[c,k] * softmax_k(E[:,n])[k]
         LMPCR_TRY(launch_split_weights(xd_in, C, K, blob_x2, st, g, CK, KP));   // A operand (x2) shared by all point tiles of a pair
         a.a_blob = blob_x2; a.a_blob_batch = (long long)tc_weight_blob_bytes(C, K);
@@ -1317,6 +1336,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
         a.M = C; a.N = N; a.K = K;
         { const int oi = part_index(W.CAT + CN); part_valid[oi] = tc_fast_epilogue(a); part_whole[oi] = false; a.stats_out = part_valid[oi] ? part_buf[oi] : nullptr; }
         LMPCR_TRY(launch_tcgemm(a, g, st));
+        }
       } else {
         softmax_cols_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(W.E, K, N, g);
         LMPCR_TRY(check_launch("softmax_cols_kernel"));

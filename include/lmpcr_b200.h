@@ -160,7 +160,9 @@ int lmpcr_softmax_pool(const float* x, const float* embed, int n_pairs, int chan
 /* The un-pooling step of diff_unpool alone (lib/filtering/oanet.py:126-128), the twin of lmpcr_softmax_pool:
  *   out[p,c,n] = sum_k x_down[p,c,k] * softmax_k(embed[p,:,n])[k].   x_down [P,C,K], embed [P,K,N], out [P,C,N] fp32.
  * The softmax runs over the CLUSTER axis here (over the points in diff_pool).  mode 0: separate statistics pass; mode 1: deferred
- * normalisation (needs clusters >= 97, n_pts % 4 == 0) -- the way lmpcr_filter_forward runs it. */
+ * normalisation on the generic GEMM (needs clusters >= 97, n_pts % 4 == 0); mode 2: the pair-resident kernel (x_down stays in tensor /
+ * shared memory for all point tiles of a pair, embed streams by TMA; needs channels == 128, 256 < clusters <= 512, clusters % 4 == 0,
+ * n_pts % 4 == 0) -- the way lmpcr_filter_forward runs it for groups of 64 pairs and more. */
 size_t lmpcr_softmax_unpool_workspace_bytes(int n_pairs, int channels, int clusters, int n_pts);
 int lmpcr_softmax_unpool(const float* x_down, const float* embed, int n_pairs, int channels, int clusters, int n_pts, int mode, float* out,
                          void* workspace, size_t workspace_bytes, void* stream);
