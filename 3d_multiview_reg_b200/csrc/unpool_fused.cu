@@ -17,7 +17,8 @@
 // and stores the tile by TMA.  Products are split-bf16 (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, fp32 accumulation) exactly as in tcgemm.cu.
 //
 // Warp roles (14 warps):
-//   warp 0      TMA: x_down boxes (32 clusters x 128 channels) then E boxes, L2 prefetch a few boxes ahead
+//   warp 0      TMA: x_down boxes (32 clusters x 128 channels) then E boxes (+ the tile's column maxima with its first box); no L2 prefetch:
+//               measured 378 / 380 / 386 / 461 us per 296 pairs at prefetch distances of 0 / 6 / 12 / 24 boxes
 //   warp 1      tcgen05.mma issue (M128 x N64 x K16; 24 per chunk of 128 clusters)
 //   warps 2-5   epilogue: TMEM -> 1/sum -> statistics -> staging box -> TMA store
 //   warps 6-13  producers: two groups of four warps, group g takes box g of every chunk (thread = cluster row = TMEM lane)
@@ -38,7 +39,6 @@ constexpr int KCH = 128;                     // clusters per K chunk (= rows of 
 constexpr int MAX_KC = 4;                    // K <= 512
 constexpr int NPG = 2;                       // producer groups of four warps: group g takes box g of every chunk
 constexpr int NXB = 5;                       // box ring
-constexpr int PFD = 6;                       // L2 prefetch distance in boxes
 constexpr int ALO_BYTES = C * KCH * 2;       // x_down lo of one chunk as a K-major operand image: 32 KB
 constexpr uint32_t A_LBO = 128, A_SBO = (KCH / 8) * 128;     // cluster-groups adjacent, 8-channel groups 2 KB apart
 constexpr int OFF_X = 0;
@@ -48,7 +48,8 @@ constexpr int OFF_STG = OFF_ALO + 2 * ALO_BYTES;
 constexpr int OFF_ZP = OFF_STG + XS_BYTES;   // column-sum partials [tile parity][NPG / 2][4 warps][64 columns]
 constexpr int ZP_FLOATS = 2 * (NPG / 2) * 4 * TP;
 constexpr int OFF_IZ = OFF_ZP + ZP_FLOATS * 4;
-constexpr int OFF_BAR = OFF_IZ + TP * 4;
+constexpr int OFF_CM = OFF_IZ + TP * 4;      // column maxima (times log2 e) of the tile in flight: [tile parity][64]
+constexpr int OFF_BAR = OFF_CM + 2 * TP * 4;
 constexpr int N_BARS = 2 * NXB + 9;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr size_t SMEM_BYTES = OFF_TMEM + 16;
@@ -135,6 +136,7 @@ unpool_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const int nA = (g.K + TS - 1) / TS;                      // x_down boxes of 32 clusters
   const int tpp = (n_tiles + g.n_parts - 1) / g.n_parts;   // point tiles per part
   const uint32_t sX = smem_u32(smem + OFF_X), sH = smem_u32(smem + OFF_H), sALO = smem_u32(smem + OFF_ALO), sSTG = smem_u32(smem + OFF_STG);
+  const uint32_t sCM = smem_u32(smem + OFF_CM);
 
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
@@ -161,30 +163,37 @@ unpool_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
     if (warp == 0) {
       if (lane == 0) {
-        const int n_box = nA + 2 * nQ;
-        // box u of the item's stream: x_down boxes first, then (tile, chunk, half) in the order the producers consume them
-        auto coords = [&](int u, int& c0, int& c1) {       // false: a box that starts at or past N (neither loaded nor prefetched)
-          if (u < nA) { c0 = u * TS; c1 = 0; return true; }
-          const int e = u - nA, q = e >> 1;
-          c0 = (t0 + q / n_kc) * TP + (e & 1) * TS; c1 = (q % n_kc) * KCH;
-          return c0 < g.N;
-        };
-        auto prefetch = [&](int u) {
-          int c0, c1;
-          if (u < n_box && coords(u, c0, c1)) tma_prefetch_3d(u < nA ? &tm_a : &tm_e, c0, c1, p);
-        };
-        for (int u = 0; u < PFD; ++u) prefetch(u);
-        for (int u = 0; u < n_box; ++u) {
-          const int s = u % NXB;
-          if (u >= NXB) up_wait(XREAD(s), ((u / NXB) - 1) & 1);
-          int c0, c1;
-          if (coords(u, c0, c1)) {
-            mbar_expect_tx(XFULL(s), XS_BYTES);
-            tma_load_3d(sX + s * XS_BYTES, u < nA ? &tm_a : &tm_e, c0, c1, p, XFULL(s));
-          } else {
-            mbar_arrive(XFULL(s));                         // the producers write zeros for this half tile
+        // the item's box stream: x_down boxes first, then (tile, chunk, half) in the order the producers consume them.  Ring slot and
+        // phase are carried incrementally (this thread feeds eight producer warps: no divisions on its path)
+        int s = 0, ph = 0;                                 // slot of box u, parity of the XREAD phase that frees it (valid once u >= NXB)
+        bool wrapped = false;
+        auto next_slot = [&]() { if (++s == NXB) { s = 0; if (wrapped) ph ^= 1; wrapped = true; } };
+        for (int u = 0; u < nA; ++u) {
+          if (wrapped) up_wait(XREAD(s), ph);
+          mbar_expect_tx(XFULL(s), XS_BYTES);
+          tma_load_3d(sX + s * XS_BYTES, &tm_a, u * TS, 0, p, XFULL(s));
+          next_slot();
+        }
+        const float* cm_p = g.cmax + (size_t)p * g.N;
+        for (int tl = 0; tl < nT; ++tl) {
+          const int col = (t0 + tl) * TP;
+          for (int kc = 0; kc < n_kc; ++kc) {
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+              if (wrapped) up_wait(XREAD(s), ph);
+              const int c0 = col + sub * TS;
+              if (c0 < g.N) {
+                // the tile's column maxima travel with its first box (same barrier): 64 floats, fewer in the last tile
+                const uint32_t cm_bytes = (kc == 0 && sub == 0) ? (uint32_t)min(TP, g.N - col) * 4u : 0u;
+                mbar_expect_tx(XFULL(s), XS_BYTES + cm_bytes);
+                if (cm_bytes) bulk_g2s(sCM + (tl & 1) * TP * 4, cm_p + col, cm_bytes, XFULL(s));
+                tma_load_3d(sX + s * XS_BYTES, &tm_e, c0, kc * KCH, p, XFULL(s));
+              } else {
+                mbar_arrive(XFULL(s));                     // a box that starts at or past N: the producers write zeros for this half tile
+              }
+              next_slot();
+            }
           }
-          prefetch(u + PFD);
         }
       }
     } else if (warp == 1) {
@@ -232,7 +241,7 @@ unpool_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       const int et = threadIdx.x - 64;                     // 0..127
       for (int tl = 0; tl < nT; ++tl) {
         const int acc = tl & 1, t = t0 + tl;
-        up_wait(ACCFULL(acc), (tl >> 1) & 1);
+        up_wait(ACCFULL(acc), (tl >> 1) & 1);             // a sleeping (hinted) wait for these mostly idle warps measured the same: 340.7 vs 340.8 us
         tc_fence_after();
         if (et < TP) {                                     // 1 / column sum: the producers' partials in a fixed order
           const float* zp = zp_s + (tl & 1) * (NPG / 2) * 4 * TP + et;
@@ -325,7 +334,8 @@ unpool_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       for (int tl = 0; tl < nT; ++tl) {
         const int t = t0 + tl;
         const int col0 = t * TP + sub * TS, ncv = g.N - col0;
-        const float4* cm = reinterpret_cast<const float4*>(g.cmax + (size_t)p * g.N + col0);
+        // the tile's column maxima arrived with its first box (every producer warp waits for that box: own or seen)
+        const float4* cm = reinterpret_cast<const float4*>(smem + OFF_CM) + (tl & 1) * (TP / 4) + sub * (TS / 4);
         float zacc[TS];
 #pragma unroll
         for (int i = 0; i < TS; ++i) zacc[i] = 0.f;
@@ -339,7 +349,7 @@ unpool_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             load_x_row(smem + OFF_X + s * XS_BYTES, ch, v);
 #pragma unroll
             for (int c4 = 0; c4 < TS / 4; ++c4) {
-              const float4 m = (4 * c4 < ncv) ? __ldg(cm + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 m = (4 * c4 < ncv) ? cm[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
               v[4 * c4] = ex2_approx(fmaf(v[4 * c4], LOG2E, -m.x));
               v[4 * c4 + 1] = ex2_approx(fmaf(v[4 * c4 + 1], LOG2E, -m.y));
               v[4 * c4 + 2] = ex2_approx(fmaf(v[4 * c4 + 2], LOG2E, -m.z));
