@@ -301,7 +301,7 @@ def run_ours(args):
         sampler.start()
     cabi.ktime_enable(True)          # CUDA event pairs around the dominant kernels' launches, on the launching stream, inside the timed region
     ms_step, stages = timed(step_resident, args.steps, with_timers=True)
-    ktimes = {k: cabi.ktime_read(k) for k in ("pcn_stack_kernel", "pool_fused_kernel", "embed_fused_kernel", "nn_sweep_kernel", "nn_rescore_kernel")}
+    ktimes = {k: cabi.ktime_read(k) for k in ("pcn_stack_kernel", "pool_fused_kernel", "embed_fused_kernel", "unpool_fused_kernel", "nn_sweep_kernel", "nn_rescore_kernel")}
     cabi.ktime_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     step_e2e()
@@ -339,6 +339,7 @@ def run_ours(args):
             "roofline_tcgemm": tcgemm_roofline(cabi, dev, n if n <= 8192 else 5000, pk),
             "roofline_pool_fused": live_pool_roofline(ktimes["pool_fused_kernel"], n_mine, n, args.steps, pk),
             "roofline_embed_fused": live_embed_roofline(ktimes["embed_fused_kernel"], n_mine, n, args.steps, pk),
+            "roofline_unpool_fused": live_unpool_roofline(ktimes["unpool_fused_kernel"], n_mine, n, args.steps, pk),
             "roofline_filter_stage": {"bound": "tensor", "achieved": filt_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": filt_tf / pk["tf_sustained"],
                                       "algorithmic_flop_per_pair": FILTER_FLOP_PER_PAIR(n), "ms_per_step": filt_ms, "peak_source": pk["src"] + " bf16 sustained"},
             "roofline_nn": {"bound": "tensor", "achieved": nn_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": nn_tf / pk["tf_sustained"],
@@ -428,6 +429,21 @@ def live_embed_roofline(kt, pairs, n, steps, pk, C=128, K=500):
             "launches_per_step": launches / steps, "ms_per_step": ms / steps, "tensor_tflops_algorithmic": flop / (ms * 1e-3) / 1e12,
             "note": "algorithmic bytes = the logits written + the pair's tiles read once (the other cluster blocks of a pair find them in L2)",
             "peak_source": pk["src"] + " hbm copy"}
+
+
+def live_unpool_roofline(kt, pairs, n, steps, pk, C=128, K=500):
+    """diff_unpool's product on the pair-resident kernel (unpool_fused.cu) as it ran inside the timed steps.  HBM-bound by its input: it
+    reads the [K, n] logits of every pair once, x_down [C, K] once, and writes the [C, n] output."""
+    launches, ms = kt
+    if launches == 0:
+        return None
+    byts = (float(K) * n + float(C) * K + float(C) * n + n) * 4 * 2 * pairs * steps
+    gbs = byts / (ms * 1e-3) / 1e9
+    flop = 2.0 * K * C * n * 2 * pairs * steps
+    return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+            "kernel": "unpool_fused_kernel, timed live in the step", "ms_per_launch": ms / launches,
+            "launches_per_step": launches / steps, "ms_per_step": ms / steps, "tensor_tflops_algorithmic": flop / (ms * 1e-3) / 1e12,
+            "note": "algorithmic bytes = logits + x_down + column maxima read, output written; 2 blocks per pair", "peak_source": pk["src"] + " hbm copy"}
 
 
 def tcgemm_roofline(cabi, dev, n, pk, P=148, C=128, sets=3, iters=12):
