@@ -967,7 +967,9 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   // training-mode BatchNorm couples all pairs of the call: they must form ONE group
   LMPCR_REQUIRE(!bn_train || G >= P, LMPCR_ERR_WORKSPACE,
                 "lmpcr_filter_forward: batch-statistics BatchNorm needs all %d pairs in one group, the workspace holds %d", P, G);
-  if (!bn_train) {  // groups whose tile counts are whole waves: the pooling GEMM has 4 tiles per pair, so G % (SMs/4) == 0
+  if (!bn_train && G < P) {  // several groups: whole waves for the per-pair kernels (4 tiles / CTAs per pair in the pooling stage, so G % (SMs/4) == 0).
+    // A call that fits ONE group keeps all its pairs together: splitting 290 pairs into 259 + 31 would send the tail below the
+    // pair-resident kernels' group-size threshold
     const int q = sm_count() / 4;
     if (q > 0 && G > q) G = G / q * q;
   }
