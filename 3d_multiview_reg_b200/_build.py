@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblmpcr_b200.so")
-SOURCES = ["cabi.cu", "kabsch.cu", "nn_search.cu", "nn_tensor.cu", "tcgemm.cu", "filter_net.cu", "overlap.cu", "pcn.cu", "sampler.cu", "pool_fused.cu", "conv_wide.cu", "unpool_fused.cu"]
+SOURCES = ["cabi.cu", "kabsch.cu", "nn_search.cu", "nn_tensor.cu", "tcgemm.cu", "filter_net.cu", "overlap.cu", "pcn.cu", "sampler.cu", "pool_fused.cu", "conv_wide.cu", "unpool_fused.cu", "oaf.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

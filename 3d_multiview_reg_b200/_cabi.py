@@ -29,6 +29,7 @@ EXPORTS = [
     "lmpcr_diff_pool_fused_workspace_bytes", "lmpcr_diff_pool_fused",
     "lmpcr_embed_fused_workspace_bytes", "lmpcr_embed_fused",
     "lmpcr_conv_wide_workspace_bytes", "lmpcr_conv_wide",
+    "lmpcr_oafilter_stack_workspace_bytes", "lmpcr_oafilter_stack",
 ]
 
 
@@ -99,6 +100,9 @@ def load():
     lib.lmpcr_pointcn_stack_workspace_bytes.restype = _sz
     lib.lmpcr_pointcn_stack_workspace_bytes.argtypes = [_i, _i]
     lib.lmpcr_pointcn_stack.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _sz, _vp]
+    lib.lmpcr_oafilter_stack_workspace_bytes.restype = _sz
+    lib.lmpcr_oafilter_stack_workspace_bytes.argtypes = [_i, _i, _i]
+    lib.lmpcr_oafilter_stack.argtypes = [_vp, _i, _i, ctypes.POINTER(_vp), _i, _vp, _vp, _sz, _vp]
     lib.lmpcr_conv_wide_workspace_bytes.restype = _sz
     lib.lmpcr_conv_wide_workspace_bytes.argtypes = []
     lib.lmpcr_conv_wide.argtypes = [_vp, _i, _i] + [_vp] * 12 + [_vp, _sz, _vp]
@@ -505,6 +509,26 @@ def pointcn_stack(x, layer_params, out=None, want_stats=False):
         ws = _ws(lib.lmpcr_pointcn_stack_workspace_bytes(P, len(layer_params)), x.device)
         _check(lib.lmpcr_pointcn_stack(_p(x), P, N, table, len(layer_params), _p(out), _p(stats), _p(ws), ws.numel(), _stream(x)))
     return (out, stats) if want_stats else out
+
+
+def oafilter_stack(x, layer_params):
+    """The OAFilter stack of an OANBlock in one pair-resident launch (lmpcr_oafilter_stack).  x [P,128,K]; layer_params: list (one entry per
+    layer) of 18 tensors in state_dict order: BN conv1.1 (w, b, rm, rv), conv1.3 (w, b), BN conv2.0 (x4, K channels), conv2.2 (w [K,K], b),
+    BN conv3.2 (x4), conv3.4 (w, b).  Returns [P,128,K]."""
+    lib = load()
+    x = _dev(x, name="x")
+    P, C, K = x.shape
+    if C != 128:
+        raise LmpcrError("oafilter_stack: x must be [P,128,K]")
+    flat = [_dev(t, name="parameter") for lp in layer_params for t in lp]
+    if len(flat) != 18 * len(layer_params):
+        raise LmpcrError("oafilter_stack: 18 tensors per layer expected")
+    table = (ctypes.c_void_p * len(flat))(*[t.data_ptr() for t in flat])
+    with torch.cuda.device(x.device):
+        out = torch.empty_like(x)
+        ws = _ws(lib.lmpcr_oafilter_stack_workspace_bytes(P, K, len(layer_params)), x.device)
+        _check(lib.lmpcr_oafilter_stack(_p(x), P, K, table, len(layer_params), _p(out), _p(ws), ws.numel(), _stream(x)))
+    return out
 
 
 def diff_pool_fused(x, scale, shift, weight, mode=0):

@@ -307,6 +307,14 @@ int lmpcr_pointcn_stack(const float* x, int n_pairs, int n_pts, const float* con
   return launch_pointcn_stack(x, n_pairs, n_pts, params, n_layers, out, stats_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t lmpcr_oafilter_stack_workspace_bytes(int n_pairs, int clusters, int n_layers) { return oafilter_stack_workspace_bytes(n_pairs, clusters, n_layers); }
+
+int lmpcr_oafilter_stack(const float* x, int n_pairs, int clusters, const float* const* params, int n_layers, float* out, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  LMPCR_TRY(check_device());
+  return launch_oafilter_stack(x, n_pairs, clusters, params, n_layers, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 size_t lmpcr_diff_pool_fused_workspace_bytes(int n_pairs, int clusters) {
   return align_up(pool_fused_weight_bytes(clusters), 256) + align_up((size_t)(n_pairs > 0 ? n_pairs : 1) * ((clusters + 127) / 128) * 4, 256) + 256;
 }

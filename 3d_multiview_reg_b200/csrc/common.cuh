@@ -108,6 +108,8 @@ int launch_nn_tensor(const float* q_feat, int n_q_sets, int n_q, const float* b_
 size_t conv1x1_workspace_bytes(int cout, int cin);
 int launch_conv1x1(const float* x, int P, int cin, int N, const float* weight, const float* bias, const float* scale, const float* shift,
                    const float* residual, int cout, float* out, int algo, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t oafilter_stack_workspace_bytes(int P, int K, int n_layers);
+int launch_oafilter_stack(const float* x, int P, int K, const float* const* params, int n_layers, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t pointcn_stack_workspace_bytes(int P, int n_layers);
 int launch_pointcn_stack(const float* x, int P, int N, const float* const* params, int n_layers, float* out, float* stats_out, void* ws,
                          size_t ws_bytes, cudaStream_t st);

@@ -19,6 +19,7 @@
 #include "pool_fused.cuh"
 #include "conv_wide.cuh"
 #include "unpool_fused.cuh"
+#include "oaf.cuh"
 
 namespace lmpcr {
 namespace {
@@ -798,6 +799,56 @@ int launch_softmax_pool(const float* x, const float* E, int P, int C, int K, int
 // kernel of pcn.cu; exported like lmpcr_conv1x1 so that it can be tested and timed by itself.
 // params: 12 tensors per layer in state_dict order: conv.1 (BN weight, bias, running_mean, running_var), conv.3 (weight, bias),
 // conv.5 (BN x 4), conv.7 (weight, bias).
+// Stand-alone OAFilter stack (lmpcr_oafilter_stack): x [P,128,K] -> out [P,128,K]; params per layer in state_dict order (18 tensors):
+// conv1.1 (BN x4), conv1.3 (weight [128,128], bias), conv2.0 (BN over the clusters x4), conv2.2 (weight [K,K], bias), conv3.2 (BN x4), conv3.4 (weight, bias)
+size_t oafilter_stack_workspace_bytes(int P, int K, int n_layers) {
+  const size_t pp = P > 0 ? P : 1, mat = align_up(pp * OAF_C * (size_t)kpad(K) * 4, 256);
+  return (size_t)n_layers * (2 * tc_weight_blob_bytes(OAF_C, OAF_C) + tc_weight_blob_bytes(K, K)) + 4 * mat + 2 * align_up(pp * OAF_C * 4, 256) +
+         align_up((size_t)OAF_MAX_LAYERS * 3 * OAF_KMAX * 4, 256) + 256;
+}
+int launch_oafilter_stack(const float* x, int P, int K, const float* const* params, int n_layers, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  LMPCR_REQUIRE(x && out && params && P >= 0 && K > 0 && n_layers >= 1 && n_layers <= OAF_MAX_LAYERS, LMPCR_ERR_ARG, "lmpcr_oafilter_stack: bad arguments");
+  LMPCR_REQUIRE(ws && ws_bytes >= oafilter_stack_workspace_bytes(P, K, n_layers) && ((uintptr_t)ws & 255) == 0, LMPCR_ERR_WORKSPACE, "lmpcr_oafilter_stack: workspace");
+  if (P == 0) return LMPCR_OK;
+  const int KP = kpad(K);
+  const long long CK = (long long)OAF_C * KP;
+  uint8_t* bp = reinterpret_cast<uint8_t*>(ws);
+  OafArgs oa{};
+  OafBN bn2[OAF_MAX_LAYERS]; const float* bias2[OAF_MAX_LAYERS];
+  for (int l = 0; l < n_layers; ++l) {
+    const float* const* q = params + 18 * l;
+    for (int i = 0; i < 18; ++i) LMPCR_REQUIRE(q[i], LMPCR_ERR_ARG, "lmpcr_oafilter_stack: params[%d] is null", 18 * l + i);
+    OafLayer& L = oa.layer[l];
+    L.bn1 = OafBN{q[0], q[1], q[2], q[3]}; L.b1 = q[5];
+    bn2[l] = OafBN{q[6], q[7], q[8], q[9]}; bias2[l] = q[11];
+    L.bn3 = OafBN{q[12], q[13], q[14], q[15]}; L.b3 = q[17];
+    L.w1 = bp; LMPCR_TRY(launch_split_weights(q[4], OAF_C, OAF_C, bp, st)); bp += tc_weight_blob_bytes(OAF_C, OAF_C);
+    L.w2 = bp; LMPCR_TRY(launch_split_weights(q[10], K, K, bp, st)); bp += tc_weight_blob_bytes(K, K);
+    L.w3 = bp; LMPCR_TRY(launch_split_weights(q[16], OAF_C, OAF_C, bp, st)); bp += tc_weight_blob_bytes(OAF_C, OAF_C);
+  }
+  bp = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(bp), 256));
+  const size_t mat = align_up((size_t)P * OAF_C * KP * 4, 256);
+  float* xd0 = reinterpret_cast<float*>(bp); float* xd1 = reinterpret_cast<float*>(bp + mat);
+  float* y = reinterpret_cast<float*>(bp + 2 * mat); float* z = reinterpret_cast<float*>(bp + 3 * mat);
+  bp += 4 * mat;
+  float* scale = reinterpret_cast<float*>(bp); bp += align_up((size_t)P * OAF_C * 4, 256);
+  float* shift = reinterpret_cast<float*>(bp); bp += align_up((size_t)P * OAF_C * 4, 256);
+  float* tab = reinterpret_cast<float*>(bp);
+  LMPCR_REQUIRE(oaf_supported(OAF_C, K, KP, CK, xd0, xd1, y, z), LMPCR_ERR_UNSUPPORTED, "lmpcr_oafilter_stack: needs 480 < clusters <= 512 and a driver with tensor maps");
+  LMPCR_REQUIRE(cudaMemcpy2DAsync(xd0, (size_t)KP * 4, x, (size_t)K * 4, (size_t)K * 4, (size_t)P * OAF_C, cudaMemcpyDeviceToDevice, st) == cudaSuccess,
+                LMPCR_ERR_LAUNCH, "lmpcr_oafilter_stack: copy of the input failed");
+  const int rows = P * OAF_C;
+  in_affine_kernel<<<(rows + 7) / 8, 256, 0, st>>>(xd0, CK, OAF_C, K, 1, 1e-3f, params[0], params[1], params[2], params[3], scale, shift, rows, 0, KP);
+  LMPCR_TRY(check_launch("in_affine_kernel"));
+  LMPCR_TRY(launch_oaf_tables(bn2, bias2, n_layers, K, tab, st));
+  oa.n_layers = n_layers; oa.scale0 = scale; oa.shift0 = shift; oa.tab = tab; oa.P = P; oa.K = K;
+  LMPCR_TRY(launch_oaf_stack(xd0, xd1, y, z, KP, CK, oa, st));
+  const float* res = (n_layers & 1) ? xd1 : xd0;
+  LMPCR_REQUIRE(cudaMemcpy2DAsync(out, (size_t)K * 4, res, (size_t)KP * 4, (size_t)K * 4, (size_t)P * OAF_C, cudaMemcpyDeviceToDevice, st) == cudaSuccess,
+                LMPCR_ERR_LAUNCH, "lmpcr_oafilter_stack: copy of the output failed");
+  return LMPCR_OK;
+}
+
 size_t pointcn_stack_workspace_bytes(int P, int n_layers) {
   return (size_t)n_layers * 2 * pcn_weight_bytes() + 2 * align_up((size_t)(P > 0 ? P : 1) * PCN_C * 4, 256) + 256;
 }
@@ -949,6 +1000,7 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
   const int embed_on = getenv("LMPCR_EMBED_FUSED") ? atoi(getenv("LMPCR_EMBED_FUSED")) : 1;       // 0: the `up` embedding conv as convert_b + GEMM (A/B runs)
   const int pool_on = getenv("LMPCR_POOL_FUSED") ? atoi(getenv("LMPCR_POOL_FUSED")) : 1;         // 0: diff_pool as embedding GEMM + pooling GEMM (A/B runs)
   const int unpool_on = getenv("LMPCR_UNPOOL_FUSED") ? atoi(getenv("LMPCR_UNPOOL_FUSED")) : 1;   // 0: diff_unpool's product on the generic GEMM (A/B runs)
+  const int oaf_on = getenv("LMPCR_OAF") ? atoi(getenv("LMPCR_OAF")) : 1;                        // 0: the OAFilter stage as nine GEMM launches per block (A/B runs)
   const int pcn_min_pairs = getenv("LMPCR_PCN_MIN_PAIRS") ? atoi(getenv("LMPCR_PCN_MIN_PAIRS")) : 64;
   LMPCR_REQUIRE(n_params == filter_num_params(cfg), LMPCR_ERR_ARG, "lmpcr_filter_forward: expected %d parameter tensors, got %d", filter_num_params(cfg), n_params);
   for (int i = 0; i < n_params; ++i) LMPCR_REQUIRE(params[i], LMPCR_ERR_ARG, "lmpcr_filter_forward: params[%d] is null", i);
@@ -1268,7 +1320,31 @@ int launch_filter_forward(const float* xs, int P, int N, const float* const* par
       }
       // l2: OAFilter x half (oanet.py:85-93)
       float* xd_in = W.XD0; float* xd_out = W.XD1;
-      for (int i = 0; i < half; ++i) {
+      bool use_oaf = oaf_on && tc && !bn_train && g >= pcn_min_pairs && half >= 1 && half <= OAF_MAX_LAYERS &&
+                     oaf_supported(C, K, KP, CK, W.XD0, W.XD1, W.Y, W.Z) && (size_t)G * r64((size_t)(N > K ? N : K)) >= (size_t)OAF_MAX_LAYERS * 3 * OAF_KMAX;
+      for (int i = 0; i < half && use_oaf; ++i) use_oaf = blk.l2[i].c1.blob && blk.l2[i].c2.blob && blk.l2[i].c3.blob && blk.l2[i].c1.b && blk.l2[i].c3.b;
+      if (use_oaf) {
+        // the whole OAFilter stack of the block in ONE pair-resident launch (oaf.cu): relu(bn_k(y)) stays on chip as conv2's A operand, W2
+        // streams once per pair and layer, all InstanceNorm statistics are thread-local sums of the epilogues
+        LMPCR_TRY(norm_affine(xd_in, CK, C, K, g, 1e-3f, blk.l2[0].bn1, KP));
+        OafArgs oa{};
+        OafBN bn2[OAF_MAX_LAYERS]; const float* bias2[OAF_MAX_LAYERS];
+        for (int i = 0; i < half; ++i) {
+          const OAFilterP& q = blk.l2[i];
+          OafLayer& L = oa.layer[i];
+          L.w1 = q.c1.blob; L.w2 = q.c2.blob; L.w3 = q.c3.blob; L.b1 = q.c1.b; L.b3 = q.c3.b;
+          L.bn1 = OafBN{q.bn1.g, q.bn1.b, q.bn1.rm, q.bn1.rv};
+          L.bn3 = OafBN{q.bn3.g, q.bn3.b, q.bn3.rm, q.bn3.rv};
+          bn2[i] = OafBN{q.bn2.g, q.bn2.b, q.bn2.rm, q.bn2.rv}; bias2[i] = q.c2.b;
+        }
+        float* tab = sm_inv;                  // idle between diff_pool and diff_unpool
+        LMPCR_TRY(launch_oaf_tables(bn2, bias2, half, K, tab, st));
+        oa.n_layers = half; oa.scale0 = W.scale; oa.shift0 = W.shift; oa.tab = tab; oa.P = g; oa.K = K;
+        LMPCR_TRY(launch_oaf_stack(W.XD0, W.XD1, W.Y, W.Z, KP, CK, oa, st));
+        if (half & 1) { xd_in = W.XD1; xd_out = W.XD0; }
+        part_valid[part_index(W.XD0)] = false; part_valid[part_index(W.XD1)] = false;
+      }
+      for (int i = 0; i < half && !use_oaf; ++i) {
         const OAFilterP& q = blk.l2[i];
         LMPCR_TRY(conv_norm(xd_in, CK, C, K, g, 1e-3f, q.bn1, q.c1, C, W.Y, CK, nullptr, 0, KP));     // conv1 -> Y [g,C,K]
         LMPCR_TRY(affine(W.Y, CK, K, 0, g, false, 0.f, q.bn2));                                    // BN over the cluster axis

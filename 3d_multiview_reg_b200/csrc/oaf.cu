@@ -1,0 +1,499 @@
+// Pair-resident OAFilter stack of the filtering network (tcgen05 / TMEM / TMA tensor maps), sm_100a.
+//
+// The cluster-level stage of an OANBlock (lib/filtering/oanet.py:85-93,170: `l2` = OAFilter x depth/2) works on x_down [128 channels x
+// K = 500 clusters] per pair.  One OAFilter (oanet.py:56-83) is
+//   y   = W1 . relu(bn(in(x))) + b1                                  conv1: InstanceNorm over the clusters, 128 -> 128 channels
+//   z   = y + b2 + relu(bn_k(y)) . W2^T                              conv2 on the transposed matrix: BatchNorm per cluster, K -> K clusters
+//   out = W3 . relu(bn(in(z))) + b3 + x                              conv3 + shortcut
+// On the per-layer GEMM path that is nine launches of tcgemm.cu plus nine statistics kernels per block and group: every 128 x 64 output tile
+// of conv2 re-fetches a 256 KB slab of W2 from L2 (606 MB per 296 pairs and layer) and the small problems are dominated by fixed costs
+// (1.04 ms per 296 pairs for 0.26 ms of tensor work).
+//
+// Here ONE CTA OWNS A PAIR for the whole stack.  The 128 channels are the MMA's M (= TMEM lanes), so every InstanceNorm statistic is a
+// thread-local running sum of the epilogue (thread = channel row), and conv2 needs no transposition: relu(bn_k(y)) is its A operand.
+//   conv1 / conv3: 64-cluster tiles; weights [128 x 128] bf16 hi | lo resident in tensor memory (A operand from TMEM), the activation tile as
+//                  a bf16 hi/lo MN-major operand image in shared memory (tile_ops.cuh), double-buffered 64-column accumulators
+//   conv2:         A = relu(bn_k(y)) for ALL clusters stays on chip: hi as a K-major operand image in shared memory (128 KB), lo in tensor
+//                  memory (256 columns); W2 streams ONCE per pair and layer through a ring of six 16 KB TMA bulk copies of the tcgemm.cu blob
+//                  tiles (128 output clusters x 32 input clusters, hi | lo); two passes of 256 output clusters (256 accumulator columns)
+//   y and z go through per-pair scratch matrices that stay in L2 (TMA stores / loads of 32-cluster x 128-channel boxes, SWIZZLE_128B).
+// Products are split-bf16 (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, fp32 accumulation) exactly as in tcgemm.cu.
+//
+// Warp roles (288 threads, one CTA per SM): warps 0-7 are "row" warps -- thread = channel row (TMEM lane (warp & 3) * 32 + lane), set s = warp >> 2
+// takes the 32-cluster boxes of parity s; they are producers (box -> affine + ReLU -> operand image) and epilogue (TMEM -> bias / residual ->
+// statistics -> staged box -> TMA store) in turn.  Warp 8 issues the MMAs and the W2 ring's bulk copies.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "oaf.cuh"
+#include "tile_ops.cuh"
+
+namespace lmpcr {
+namespace {
+
+constexpr int C = TILE_C;                       // channels = M
+constexpr int NCHK = OAF_KMAX / TS;             // 16 chunks of 32 clusters
+constexpr int NT = OAF_KMAX / TP;               // 8 MMA tiles of 64 clusters (conv1 / conv3)
+constexpr int ACH_BYTES = C * TS * 2;           // one bf16 part of a 128 x 32 K-major operand tile: 8 KB
+constexpr uint32_t K_LBO = 128, K_SBO = (TS / 8) * 128;   // K-major image: k-groups adjacent, 8-row groups 512 B apart (= tcgemm.cu's blob tiles)
+constexpr int WT_BYTES = 2 * ACH_BYTES;         // one blob tile of tcgemm.cu: [hi 8 KB | lo 8 KB]
+constexpr int NRING = 6;                        // W2 ring
+constexpr int OFF_AHI = 0;                      // relu(bn_k(y)) hi: 16 chunks x 8 KB (conv3: the residual boxes)
+constexpr int OFF_R = NCHK * ACH_BYTES;         // 96 KB region: conv1 / conv3: [H 32 KB | IN0 | IN1 | OUT0 | OUT1]; conv2: the W2 ring (its epilogue: IN / OUT boxes)
+constexpr int OFF_H = OFF_R;
+constexpr int OFF_BOX = OFF_R + H_BYTES;
+constexpr int OFF_EX = OFF_R + NRING * WT_BYTES;          // row statistics of the two sets: [2][128] x (mean, M2)
+constexpr int OFF_BAR = OFF_EX + 2 * C * 2 * 4;
+enum { B_XIN = 0, B_XRES = 2, B_HFULL = 6, B_MMADONE = 7, B_WFULL = 9, B_WEMPTY = 15, B_D2FULL = 21, B_EPIDONE = 22, N_BARS = 23 };
+constexpr int OFF_TMEM = OFF_BAR + 24 * 8;
+constexpr size_t SMEM_BYTES = OFF_TMEM + 16;
+static_assert(H_BYTES + 4 * XS_BYTES == NRING * WT_BYTES, "the 96 KB region is carved the same way in all phases");
+static_assert(OFF_BOX % 1024 == 0 && XS_BYTES % 1024 == 0, "SWIZZLE_128B boxes need 1024-byte aligned slots");
+static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
+constexpr int NTHREADS = 9 * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int TM_ALO = 0, TM_W = 256, TM_D = 384, TM_D2 = 256;
+constexpr uint32_t IDESC13 = make_idesc(1, 0, 1, 128, TP);      // W (TMEM, K-major) . h (MN-major): M128 x N64
+constexpr uint32_t IDESC2 = make_idesc(1, 0, 0, 128, 128);      // a (K-major) . W2 tile (K-major):  M128 x N128
+
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void set_sync(int s) { asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory"); }
+
+// shifted running sums of one row over the boxes a thread sees (pcn.cu: RunStat)
+struct RowStat {
+  float c0, s1, s2; bool have;
+  __device__ __forceinline__ void reset() { c0 = 0.f; s1 = 0.f; s2 = 0.f; have = false; }
+  __device__ __forceinline__ void add(const float (&v)[TS], int ncv) {
+    if (ncv <= 0) return;
+    if (!have) { c0 = v[0]; have = true; }
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < TS; ++i) if (ncv >= TS || i < ncv) { const float d = v[i] - c0; a += d; b = fmaf(d, d, b); }
+    s1 += a; s2 += b;
+  }
+  __device__ __forceinline__ float2 mean_m2(int n) const {      // n > 0
+    const float m = s1 / (float)n;
+    return make_float2(c0 + m, fmaxf(s2 - s1 * m, 0.f));
+  }
+};
+
+// InstanceNorm (biased variance, eps) + eval BatchNorm -> relu(x * sc + sh)       (oanet.py:60-62,77-79)
+__device__ __forceinline__ void fold_affine(float mean, float var, float eps_in, const OafBN& bn, int c, float& sc, float& sh) {
+  const float rstd = 1.0f / sqrtf(var + eps_in);
+  const float gsc = __ldg(bn.g + c) / sqrtf(__ldg(bn.rv + c) + 1e-5f);
+  sc = rstd * gsc;
+  sh = (-mean * rstd - __ldg(bn.rm + c)) * gsc + __ldg(bn.b + c);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_y,
+                 const __grid_constant__ CUtensorMap tm_z, const OafArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* ex_s = reinterpret_cast<float*>(smem + OFF_EX);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  const uint32_t bar0 = smem_u32(smem + OFF_BAR);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool row_warp = warp < 8;
+  const int s = (warp >> 2) & 1;                            // box parity this thread's set works on
+  const int ch = ((warp & 3) << 5) | lane;                  // channel row = TMEM lane
+  const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+  const bool set_leader = row_warp && (warp & 3) == 0 && lane == 0;
+  const uint32_t sAHI = smem_u32(smem + OFF_AHI), sR = smem_u32(smem + OFF_R), sH = smem_u32(smem + OFF_H);
+  uint8_t* in_box = smem + OFF_BOX + s * XS_BYTES;
+  uint8_t* out_box = smem + OFF_BOX + (2 + s) * XS_BYTES;
+  const uint32_t sIN = smem_u32(in_box), sOUT = smem_u32(out_box);
+  const int K = g.K;
+  // valid clusters in the boxes of each set (a row's statistics are merged from the two sets' partial sums)
+  int nv0 = 0, nv1 = 0;
+  for (int c = 0; c < NCHK; ++c) { const int v = min(TS, max(0, K - c * TS)); if (c & 1) nv1 += v; else nv0 += v; }
+
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // every phase (conv1 / conv2 / conv3 of a layer) starts with drained pipelines and freshly initialised barriers: use k of a barrier
+  // completes its phase k
+  auto phase_sync = [&]() {
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 6; ++i) mbar_init(BAR(B_XIN + i), 1);             // XIN[2], XRES[4]
+      mbar_init(BAR(B_HFULL), 8);
+      mbar_init(BAR(B_MMADONE), 1); mbar_init(BAR(B_MMADONE + 1), 1);
+      for (int i = 0; i < 2 * NRING; ++i) mbar_init(BAR(B_WFULL + i), 1);   // WFULL[6], WEMPTY[6]
+      mbar_init(BAR(B_D2FULL), 1);
+      mbar_init(BAR(B_EPIDONE), 8);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  };
+  // this thread's row of a [128 x 128] weight matrix (tcgemm.cu blob: per 32-k chunk [hi 8 KB | lo 8 KB], K-major) -> tensor memory [hi 64 | lo 64]
+  auto load_w_row = [&](const uint8_t* blob) {
+#pragma unroll 1
+    for (int kc = 0; kc < C / TS; ++kc) {
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        const uint8_t* src = blob + (size_t)kc * WT_BYTES + part * ACH_BYTES + (ch >> 3) * K_SBO + (ch & 7) * 16;
+        uint32_t r[16];
+#pragma unroll
+        for (int kg = 0; kg < 4; ++kg) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + kg * K_LBO));
+          r[4 * kg] = v.x; r[4 * kg + 1] = v.y; r[4 * kg + 2] = v.z; r[4 * kg + 3] = v.w;
+        }
+        tc_st16(tmem_base + lane_sel + TM_W + part * 64 + kc * 16, r);
+      }
+    }
+    tc_st_wait();
+  };
+  // control warp, conv1 / conv3: one 64-cluster tile per HFULL
+  constexpr uint32_t DESC_HI = (MN_SBO >> 4) | (1u << 14);                     // SBO, descriptor version
+  auto mma_tiles_13 = [&]() {
+    const uint32_t tW = tmem_base + TM_W;
+    const uint32_t lo0 = ((sH >> 4) & 0x3FFFu) | ((MN_LBO >> 4) << 16);
+    for (int t = 0; t < NT; ++t) {
+      mbar_wait_fast(BAR(B_HFULL), t & 1);
+      tc_fence_after();
+      const uint32_t leader = elect_one();
+      const uint32_t d_tmem = tmem_base + TM_D + (t & 1) * TP;
+#pragma unroll
+      for (int j = 0; j < C / 16; ++j) {
+        const uint32_t lo_hi = lo0 + j * ((2 * MN_LBO) >> 4), lo_lo = lo_hi + (HP_BYTES >> 4);
+        const uint64_t b_hi = ((uint64_t)DESC_HI << 32) | lo_hi, b_lo = ((uint64_t)DESC_HI << 32) | lo_lo;
+        tc_mma_ts_pred(d_tmem, tW + 64 + j * 8, b_hi, IDESC13, j ? 1u : 0u, leader);    // W_lo . h_hi   (small terms first)
+        tc_mma_ts_pred(d_tmem, tW + j * 8, b_lo, IDESC13, 1u, leader);                  // W_hi . h_lo
+        tc_mma_ts_pred(d_tmem, tW + j * 8, b_hi, IDESC13, 1u, leader);                  // W_hi . h_hi
+      }
+      tc_commit_pred(BAR(B_MMADONE + (t & 1)), leader);
+      __syncwarp();
+    }
+  };
+  // row warps: stage a box of 32 clusters and store it by TMA (two set-wide barriers; the leader's previous store has read the box)
+  auto emit_box = [&](const CUtensorMap* tm, const float (&v)[TS], int col0, int p) {
+    store_x_row(out_box, ch, v);
+    fence_proxy_async();
+    set_sync(s);
+    if (set_leader) { tma_store_3d(tm, sOUT, col0, 0, p); bulk_commit(); }
+  };
+
+  float sc = 1.f, sh = 0.f;        // row warps: the folded InstanceNorm + BatchNorm in front of the next 128 -> 128 convolution, for channel `ch`
+  RowStat rs;
+
+  for (int p = blockIdx.x; p < g.P; p += gridDim.x) {
+    for (int l = 0; l < g.n_layers; ++l) {
+      const OafLayer& L = g.layer[l];
+      const CUtensorMap* tm_in = (l & 1) ? &tm_x1 : &tm_x0;
+      const CUtensorMap* tm_out = (l & 1) ? &tm_x0 : &tm_x1;
+      const float* tab = g.tab + (size_t)l * 3 * OAF_KMAX;
+      if (row_warp && l == 0) { sc = __ldg(g.scale0 + (size_t)p * C + ch); sh = __ldg(g.shift0 + (size_t)p * C + ch); }
+
+      // ============================================================ conv1: y = W1 . relu(x*sc + sh) + b1;  a = relu(bn_k(y)) stays on chip
+      phase_sync();
+      if (row_warp) {
+        if (set_leader) { mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, tm_in, s * TS, 0, p, BAR(B_XIN + s)); }
+        if (warp < 4) load_w_row(L.w1);
+        const float b1 = __ldg(L.b1 + ch);
+        auto epilogue1 = [&](int tt) {
+          const int cidx = 2 * tt + s, col0 = cidx * TS;
+          float v[TS];
+          tc_ld32(tmem_base + lane_sel + TM_D + (tt & 1) * TP + s * TS, v);
+#pragma unroll
+          for (int i = 0; i < TS; ++i) v[i] += b1;
+          // a = relu(y * s2[k] + t2[k]) -> bf16 hi (K-major image in shared memory) / lo (tensor memory); exact zeros for k >= K (s2 = t2 = 0)
+          uint32_t lo[16];
+          uint8_t* adst = smem + OFF_AHI + cidx * ACH_BYTES + (ch >> 3) * K_SBO + (ch & 7) * 16;
+#pragma unroll
+          for (int kg = 0; kg < 4; ++kg) {
+            uint32_t hi[4];
+#pragma unroll
+            for (int h4 = 0; h4 < 2; ++h4) {
+              const float4 s2 = __ldg(reinterpret_cast<const float4*>(tab + col0 + 8 * kg + 4 * h4));
+              const float4 t2 = __ldg(reinterpret_cast<const float4*>(tab + OAF_KMAX + col0 + 8 * kg + 4 * h4));
+              const int i0 = 8 * kg + 4 * h4;
+              const float a0 = fmaxf(fmaf(v[i0], s2.x, t2.x), 0.f), a1 = fmaxf(fmaf(v[i0 + 1], s2.y, t2.y), 0.f);
+              const float a2 = fmaxf(fmaf(v[i0 + 2], s2.z, t2.z), 0.f), a3 = fmaxf(fmaf(v[i0 + 3], s2.w, t2.w), 0.f);
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+              const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+              const __nv_bfloat162 l01 = __floats2bfloat162_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2bfloat162_rn(a2 - f23.x, a3 - f23.y);
+              hi[2 * h4] = *reinterpret_cast<const uint32_t*>(&h01); hi[2 * h4 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+              lo[4 * kg + 2 * h4] = *reinterpret_cast<const uint32_t*>(&l01); lo[4 * kg + 2 * h4 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+            }
+            *reinterpret_cast<uint4*>(adst + kg * K_LBO) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          }
+          tc_st16(tmem_base + lane_sel + TM_ALO + cidx * 16, lo);
+          if (set_leader) bulk_wait_read0();
+          set_sync(s);
+          emit_box(&tm_y, v, col0, p);
+        };
+        for (int t = 0; t < NT; ++t) {
+          mbar_wait_fast(BAR(B_XIN + s), t & 1);
+          if (t >= 1) { mbar_wait_fast(BAR(B_MMADONE + ((t - 1) & 1)), ((t - 1) >> 1) & 1); tc_fence_after(); }   // H is free, accumulator t-1 is full
+          float v[TS];
+          load_x_row(in_box, ch, v);
+#pragma unroll
+          for (int i = 0; i < TS; ++i) v[i] = fmaxf(fmaf(v[i], sc, sh), 0.f);
+          store_h_row(smem + OFF_H, ch, s, v);
+          fence_proxy_async();
+          tc_fence_before();
+          set_sync(s);                                       // every row of the set's box has been read
+          if (set_leader && t + 1 < NT) { mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, tm_in, (t + 1) * TP + s * TS, 0, p, BAR(B_XIN + s)); }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_HFULL));
+          if (t >= 1) epilogue1(t - 1);
+        }
+        mbar_wait_fast(BAR(B_MMADONE + ((NT - 1) & 1)), ((NT - 1) >> 1) & 1);
+        tc_fence_after();
+        epilogue1(NT - 1);
+        tc_st_wait();
+        fence_proxy_async();
+        if (set_leader) bulk_wait0();                        // y is in global memory (L2) before conv2's epilogue loads it
+      } else {
+        mma_tiles_13();
+      }
+
+      // ============================================================ conv2: z = y + b2 + a . W2^T, two passes of 256 output clusters
+      phase_sync();
+      if (row_warp) {
+        rs.reset();
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait_fast(BAR(B_D2FULL), h);
+          tc_fence_after();
+          if (set_leader) { mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, &tm_y, (h * 8 + s) * TS, 0, p, BAR(B_XIN + s)); }
+          for (int ii = 0; ii < 4; ++ii) {
+            const int i = h * 4 + ii, cidx = h * 8 + 2 * ii + s, col0 = cidx * TS;
+            mbar_wait_fast(BAR(B_XIN + s), i & 1);
+            float y[TS], v[TS];
+            load_x_row(in_box, ch, y);
+            tc_ld32(tmem_base + lane_sel + TM_D2 + (cidx - h * 8) * TS, v);
+#pragma unroll
+            for (int q = 0; q < TS / 4; ++q) {
+              const float4 b2 = __ldg(reinterpret_cast<const float4*>(tab + 2 * OAF_KMAX + col0 + 4 * q));
+              v[4 * q] += y[4 * q] + b2.x; v[4 * q + 1] += y[4 * q + 1] + b2.y; v[4 * q + 2] += y[4 * q + 2] + b2.z; v[4 * q + 3] += y[4 * q + 3] + b2.w;
+            }
+            rs.add(v, K - col0);
+            if (set_leader) bulk_wait_read0();
+            set_sync(s);                                     // the set has read its y box; the staging box is free
+            if (set_leader && ii + 1 < 4) { mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, &tm_y, (cidx + 2) * TS, 0, p, BAR(B_XIN + s)); }
+            emit_box(&tm_z, v, col0, p);
+          }
+          if (set_leader) bulk_wait_read0();                 // the boxes alias the W2 ring: the last store has read its box
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_EPIDONE));
+        }
+        if (set_leader) bulk_wait0();                        // z is in global memory (L2) before conv3 loads it
+        const float2 mm = rs.mean_m2(s ? nv1 : nv0);
+        *reinterpret_cast<float2*>(ex_s + (s * C + ch) * 2) = mm;
+      } else {
+        auto issue_load = [&](int Lq) {
+          const int st = Lq % NRING, h = Lq >> 5, r = Lq & 31, kc = r >> 1, qd = r & 1;
+          mbar_expect_tx(BAR(B_WFULL + st), WT_BYTES);
+          bulk_g2s(sR + st * WT_BYTES, L.w2 + ((size_t)(2 * h + qd) * NCHK + kc) * WT_BYTES, WT_BYTES, BAR(B_WFULL + st));
+        };
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1) { mbar_wait_fast(BAR(B_EPIDONE), 0); tc_fence_after(); }       // accumulators read, boxes (= ring slots 2..5) free
+          const int base = h * 32;
+          if (lane == 0) for (int q = 0; q < NRING - 1; ++q) issue_load(base + q);
+          __syncwarp();
+          for (int r = 0; r < 32; ++r) {
+            const int it = base + r, st = it % NRING, kc = r >> 1, qd = r & 1;
+            mbar_wait_fast(BAR(B_WFULL + st), (it / NRING) & 1);
+            tc_fence_after();
+            const uint32_t leader = elect_one();
+            const uint32_t d_tmem = tmem_base + TM_D2 + qd * 128;
+            const uint32_t sB = sR + st * WT_BYTES;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t a_hi = make_desc(sAHI + kc * ACH_BYTES + j * 2 * K_LBO, K_LBO, K_SBO);
+              const uint64_t b_hi = make_desc(sB + j * 2 * K_LBO, K_LBO, K_SBO), b_lo = make_desc(sB + ACH_BYTES + j * 2 * K_LBO, K_LBO, K_SBO);
+              tc_mma_ts_pred(d_tmem, tmem_base + TM_ALO + kc * 16 + j * 8, b_hi, IDESC2, (kc | j) ? 1u : 0u, leader);   // a_lo . W_hi (small terms first)
+              tc_mma_f16_pred(d_tmem, a_hi, b_lo, IDESC2, 1u, leader);                                                  // a_hi . W_lo
+              tc_mma_f16_pred(d_tmem, a_hi, b_hi, IDESC2, 1u, leader);                                                  // a_hi . W_hi
+            }
+            tc_commit_pred(BAR(B_WEMPTY + st), leader);
+            if (r == 31) tc_commit_pred(BAR(B_D2FULL), leader);
+            __syncwarp();
+            if (r + NRING - 1 < 32) {                        // refill the slot of the PREVIOUS tile (its MMAs have had a tile's time to finish)
+              if (r >= 1) mbar_wait_fast(BAR(B_WEMPTY + (it - 1) % NRING), ((it - 1) / NRING) & 1);
+              if (lane == 0) issue_load(it + NRING - 1);
+              __syncwarp();
+            }
+          }
+        }
+        // every commit of this phase has arrived before the barriers are re-initialised
+        for (int it = 64 - NRING; it < 64; ++it) mbar_wait_fast(BAR(B_WEMPTY + it % NRING), (it / NRING) & 1);
+      }
+
+      // ============================================================ conv3: out = W3 . relu(z*sc + sh) + b3 + x
+      phase_sync();
+      if (row_warp) {
+        {
+          const float2 m0 = *reinterpret_cast<const float2*>(ex_s + ch * 2), m1 = *reinterpret_cast<const float2*>(ex_s + (C + ch) * 2);
+          const float n0 = (float)nv0, n1 = (float)nv1, n = n0 + n1, d = m1.x - m0.x;
+          const float mean = m0.x + d * (n1 / n), m2 = m0.y + m1.y + d * d * (n0 * n1 / n);
+          fold_affine(mean, m2 / n, 1e-3f, L.bn3, ch, sc, sh);
+        }
+        uint8_t* res_box = smem + OFF_AHI + (s * 2) * XS_BYTES;       // + (t & 1) * XS_BYTES: the layer input x (residual), double-buffered
+        const uint32_t sRES = smem_u32(res_box);
+        if (set_leader) {
+          mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, &tm_z, s * TS, 0, p, BAR(B_XIN + s));
+          for (int b = 0; b < 2; ++b) {
+            mbar_expect_tx(BAR(B_XRES + 2 * s + b), XS_BYTES);
+            tma_load_3d(sRES + b * XS_BYTES, tm_in, b * TP + s * TS, 0, p, BAR(B_XRES + 2 * s + b));
+          }
+        }
+        if (warp < 4) load_w_row(L.w3);
+        const float b3 = __ldg(L.b3 + ch);
+        rs.reset();
+        auto epilogue3 = [&](int tt) {
+          const int cidx = 2 * tt + s, col0 = cidx * TS, b = tt & 1;
+          mbar_wait_fast(BAR(B_XRES + 2 * s + b), (tt >> 1) & 1);
+          float x[TS], v[TS];
+          load_x_row(res_box + b * XS_BYTES, ch, x);
+          tc_ld32(tmem_base + lane_sel + TM_D + (tt & 1) * TP + s * TS, v);
+#pragma unroll
+          for (int i = 0; i < TS; ++i) v[i] += b3 + x[i];
+          rs.add(v, K - col0);
+          if (set_leader) bulk_wait_read0();
+          set_sync(s);                                       // the set has read its residual box; the staging box is free
+          if (set_leader && tt + 2 < NT) {
+            mbar_expect_tx(BAR(B_XRES + 2 * s + b), XS_BYTES);
+            tma_load_3d(sRES + b * XS_BYTES, tm_in, (tt + 2) * TP + s * TS, 0, p, BAR(B_XRES + 2 * s + b));
+          }
+          emit_box(tm_out, v, col0, p);
+        };
+        for (int t = 0; t < NT; ++t) {
+          mbar_wait_fast(BAR(B_XIN + s), t & 1);
+          if (t >= 1) { mbar_wait_fast(BAR(B_MMADONE + ((t - 1) & 1)), ((t - 1) >> 1) & 1); tc_fence_after(); }
+          float v[TS];
+          load_x_row(in_box, ch, v);
+#pragma unroll
+          for (int i = 0; i < TS; ++i) v[i] = fmaxf(fmaf(v[i], sc, sh), 0.f);
+          store_h_row(smem + OFF_H, ch, s, v);
+          fence_proxy_async();
+          tc_fence_before();
+          set_sync(s);
+          if (set_leader && t + 1 < NT) { mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, &tm_z, (t + 1) * TP + s * TS, 0, p, BAR(B_XIN + s)); }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_HFULL));
+          if (t >= 1) epilogue3(t - 1);
+        }
+        mbar_wait_fast(BAR(B_MMADONE + ((NT - 1) & 1)), ((NT - 1) >> 1) & 1);
+        tc_fence_after();
+        epilogue3(NT - 1);
+        if (set_leader) bulk_wait0();                        // the layer's output is in global memory before the next layer (or kernel) loads it
+        const float2 mm = rs.mean_m2(s ? nv1 : nv0);
+        *reinterpret_cast<float2*>(ex_s + (s * C + ch) * 2) = mm;
+      } else {
+        mma_tiles_13();
+      }
+      // the next layer's InstanceNorm + BatchNorm from the statistics of this layer's output
+      if (l + 1 < g.n_layers) {
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (row_warp) {
+          const float2 m0 = *reinterpret_cast<const float2*>(ex_s + ch * 2), m1 = *reinterpret_cast<const float2*>(ex_s + (C + ch) * 2);
+          const float n0 = (float)nv0, n1 = (float)nv1, n = n0 + n1, d = m1.x - m0.x;
+          const float mean = m0.x + d * (n1 / n), m2 = m0.y + m1.y + d * d * (n0 * n1 / n);
+          fold_affine(mean, m2 / n, 1e-3f, g.layer[l + 1].bn1, ch, sc, sh);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+__global__ void oaf_tables_kernel(OafBN bn0, OafBN bn1, OafBN bn2, OafBN bn3, const float* c0, const float* c1, const float* c2, const float* c3, int K,
+                                  float* __restrict__ tab) {
+  const OafBN bn = blockIdx.x == 0 ? bn0 : blockIdx.x == 1 ? bn1 : blockIdx.x == 2 ? bn2 : bn3;
+  const float* bias = blockIdx.x == 0 ? c0 : blockIdx.x == 1 ? c1 : blockIdx.x == 2 ? c2 : c3;
+  float* t = tab + (size_t)blockIdx.x * 3 * OAF_KMAX;
+  const int k = threadIdx.x;
+  float s2 = 0.f, t2 = 0.f, b2 = 0.f;
+  if (k < K) {
+    s2 = __ldg(bn.g + k) / sqrtf(__ldg(bn.rv + k) + 1e-5f);
+    t2 = -__ldg(bn.rm + k) * s2 + __ldg(bn.b + k);
+    b2 = bias ? __ldg(bias + k) : 0.f;
+  }
+  t[k] = s2; t[OAF_KMAX + k] = t2; t[2 * OAF_KMAX + k] = b2;
+}
+
+// [P][128][ld] fp32 -> 3-D tensor map (K, 128, P), box 32 clusters x 128 channels, SWIZZLE_128B; clusters >= K read as zeros and are not stored
+int make_oaf_map(CUtensorMap* tm, const float* base, int K, int ld, long long batch, int P) {
+  PFN_cuTensorMapEncodeTiled_v12000 fn = encode_fn();
+  LMPCR_REQUIRE(fn, LMPCR_ERR_UNSUPPORTED, "oaf: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)C, (cuuint64_t)P};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)batch * 4};
+  const cuuint32_t box[3] = {TS, C, 1}, estr[3] = {1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LMPCR_REQUIRE(r == CUDA_SUCCESS, LMPCR_ERR_LAUNCH, "oaf: cuTensorMapEncodeTiled failed (%d) for K=%d ld=%d batch=%lld P=%d", (int)r, K, ld, batch, P);
+  return LMPCR_OK;
+}
+
+}  // namespace
+
+int launch_oaf_tables(const OafBN* bn2, const float* const* bias2, int n_layers, int K, float* tab, cudaStream_t st) {
+  LMPCR_REQUIRE(bn2 && bias2 && tab && n_layers >= 1 && n_layers <= OAF_MAX_LAYERS && K >= 1 && K <= OAF_KMAX, LMPCR_ERR_ARG, "oaf_tables: bad arguments");
+  OafBN b[OAF_MAX_LAYERS]; const float* c[OAF_MAX_LAYERS];
+  for (int i = 0; i < OAF_MAX_LAYERS; ++i) { b[i] = bn2[i < n_layers ? i : 0]; c[i] = bias2[i < n_layers ? i : 0]; }
+  oaf_tables_kernel<<<n_layers, OAF_KMAX, 0, st>>>(b[0], b[1], b[2], b[3], c[0], c[1], c[2], c[3], K, tab);
+  return check_launch("oaf_tables_kernel");
+}
+
+bool oaf_supported(int Cc, int K, int ld, long long batch, const float* xd0, const float* xd1, const float* y, const float* z) {
+  const uintptr_t al = reinterpret_cast<uintptr_t>(xd0) | reinterpret_cast<uintptr_t>(xd1) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z);
+  return Cc == C && K > OAF_KMAX - TS && K <= OAF_KMAX && ld >= K && (ld & 3) == 0 && (batch & 3) == 0 && (al & 15) == 0 && encode_fn() != nullptr;
+}
+
+int launch_oaf_stack(float* xd0, float* xd1, float* y, float* z, int ld, long long batch, const OafArgs& a, cudaStream_t st) {
+  LMPCR_REQUIRE(xd0 && xd1 && y && z && a.P > 0 && a.n_layers >= 1 && a.n_layers <= OAF_MAX_LAYERS && a.scale0 && a.shift0 && a.tab, LMPCR_ERR_ARG,
+                "oaf_stack: bad arguments");
+  LMPCR_REQUIRE(oaf_supported(C, a.K, ld, batch, xd0, xd1, y, z), LMPCR_ERR_UNSUPPORTED,
+                "oaf_stack: needs 128 channels, 480 < K <= 512 clusters, 16-byte aligned rows and a driver with tensor maps");
+  for (int i = 0; i < a.n_layers; ++i) {
+    const OafLayer& L = a.layer[i];
+    LMPCR_REQUIRE(L.w1 && L.w2 && L.w3 && L.b1 && L.b3 && L.bn3.g && (i == 0 || L.bn1.g), LMPCR_ERR_ARG, "oaf_stack: layer %d arguments", i);
+    LMPCR_REQUIRE(((reinterpret_cast<uintptr_t>(L.w1) | reinterpret_cast<uintptr_t>(L.w2) | reinterpret_cast<uintptr_t>(L.w3)) & 15) == 0, LMPCR_ERR_ARG,
+                  "oaf_stack: layer %d weight blobs must be 16-byte aligned", i);
+  }
+  CUtensorMap tm[4];
+  float* bases[4] = {xd0, xd1, y, z};
+  for (int i = 0; i < 4; ++i) LMPCR_TRY(make_oaf_map(&tm[i], bases[i], a.K, ld, batch, a.P));
+  {
+    static unsigned char attr_set[64];
+    const int dev = device_ordinal();
+    if (!attr_set[dev]) {
+      const cudaError_t e = cudaFuncSetAttribute(oaf_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "oaf_stack: cannot reserve %zu bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
+      attr_set[dev] = 1;
+    }
+  }
+  int grid = sm_count();
+  if (a.P < grid) grid = a.P;
+  ktime_begin("oaf_stack_kernel", st);
+  oaf_stack_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], a);
+  ktime_end("oaf_stack_kernel", st);
+  return check_launch("oaf_stack_kernel");
+}
+
+}  // namespace lmpcr

@@ -273,6 +273,17 @@ size_t lmpcr_pointcn_stack_workspace_bytes(int n_pairs, int n_layers);
 int lmpcr_pointcn_stack(const float* x, int n_pairs, int n_pts, const float* const* params, int n_layers, float* out, float* stats_out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* The OAFilter stack of an OANBlock (lib/filtering/oanet.py:56-93,170: `l2`) in ONE pair-resident launch (csrc/oaf.cu) -- what
+ * lmpcr_filter_forward runs for 128 channels and 480 < clusters <= 512 in eval mode.  Per layer
+ *   y = W1 . relu(bn(in(x))) + b1;   z = y + b2 + relu(bn_k(y)) . W2^T;   out = W3 . relu(bn(in(z))) + b3 + x
+ * (InstanceNorm eps 1e-3 over the clusters, eval BatchNorm; bn_k = BatchNorm over the cluster axis of the transposed matrix).
+ *   x, out [P,128,K] fp32 contiguous (out may alias x); params: HOST array of 18 * n_layers DEVICE pointers, per layer in state_dict
+ *   order: conv1.1 (weight, bias, running_mean, running_var), conv1.3 (weight [128,128], bias), conv2.0 (x4, K channels), conv2.2
+ *   (weight [K,K], bias), conv3.2 (x4), conv3.4 (weight [128,128], bias); n_layers <= 4. */
+size_t lmpcr_oafilter_stack_workspace_bytes(int n_pairs, int clusters, int n_layers);
+int lmpcr_oafilter_stack(const float* x, int n_pairs, int clusters, const float* const* params, int n_layers, float* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* Fused diff_pool (lib/filtering/oanet.py:96-110) in one launch -- embedding conv, softmax over the points and the weighted sum;
  * the [K, N] embedding never reaches memory (csrc/pool_fused.cu).  This is what lmpcr_filter_forward runs for 128 channels.
  *   out[p,c,k] = sum_n x[p,c,n] * softmax_n( weight . relu(x[p] * scale[p] + shift[p]) )[k,n]
