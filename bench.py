@@ -301,7 +301,7 @@ def run_ours(args):
         sampler.start()
     cabi.ktime_enable(True)          # CUDA event pairs around the dominant kernels' launches, on the launching stream, inside the timed region
     ms_step, stages = timed(step_resident, args.steps, with_timers=True)
-    ktimes = {k: cabi.ktime_read(k) for k in ("pcn_stack_kernel", "pool_fused_kernel", "embed_fused_kernel", "unpool_fused_kernel", "nn_sweep_kernel", "nn_rescore_kernel")}
+    ktimes = {k: cabi.ktime_read(k) for k in ("pcn_stack_kernel", "pool_fused_kernel", "embed_fused_kernel", "unpool_fused_kernel", "oaf_stack_kernel", "nn_sweep_kernel", "nn_rescore_kernel")}
     cabi.ktime_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     step_e2e()
@@ -340,6 +340,7 @@ def run_ours(args):
             "roofline_pool_fused": live_pool_roofline(ktimes["pool_fused_kernel"], n_mine, n, args.steps, pk),
             "roofline_embed_fused": live_embed_roofline(ktimes["embed_fused_kernel"], n_mine, n, args.steps, pk),
             "roofline_unpool_fused": live_unpool_roofline(ktimes["unpool_fused_kernel"], n_mine, n, args.steps, pk),
+            "roofline_oaf": live_oaf_roofline(ktimes["oaf_stack_kernel"], n_mine, args.steps, pk),
             "roofline_filter_stage": {"bound": "tensor", "achieved": filt_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": filt_tf / pk["tf_sustained"],
                                       "algorithmic_flop_per_pair": FILTER_FLOP_PER_PAIR(n), "ms_per_step": filt_ms, "peak_source": pk["src"] + " bf16 sustained"},
             "roofline_nn": {"bound": "tensor", "achieved": nn_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": nn_tf / pk["tf_sustained"],
@@ -444,6 +445,24 @@ def live_unpool_roofline(kt, pairs, n, steps, pk, C=128, K=500):
             "kernel": "unpool_fused_kernel, timed live in the step", "ms_per_launch": ms / launches,
             "launches_per_step": launches / steps, "ms_per_step": ms / steps, "tensor_tflops_algorithmic": flop / (ms * 1e-3) / 1e12,
             "note": "algorithmic bytes = logits + x_down + column maxima read, output written; 2 blocks per pair", "peak_source": pk["src"] + " hbm copy"}
+
+
+def live_oaf_roofline(kt, pairs, steps, pk, C=128, K=500, layers=3):
+    """The OAFilter stage on the pair-resident kernel (oaf.cu) as it ran inside the timed steps: per pair, block and layer two
+    128 x 128 x K convolutions and one 128 x K x K cluster-mixing product.  Tensor-bound by executed work (three bf16
+    products per fp32 product); its operands live in L2 / on chip, HBM sees the stack's input and output only."""
+    launches, ms = kt
+    if launches == 0:
+        return None
+    flop = (2.0 * 2 * C * C * K + 2.0 * C * K * K) * layers * 2 * pairs * steps
+    tf = flop / (ms * 1e-3) / 1e12
+    w2_bytes = float(512 * 512 * 4) * layers * 2 * pairs * steps
+    return {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
+            "executed_frac": 3 * tf / pk["tf_sustained"], "kernel": "oaf_stack_kernel, timed live in the step",
+            "ms_per_launch": ms / launches, "launches_per_step": launches / steps, "ms_per_step": ms / steps,
+            "l2_w2_stream_gbs": w2_bytes / (ms * 1e-3) / 1e9,
+            "note": "executed tensor work is 3x the algorithmic FLOPs (split-bf16); l2_w2_stream_gbs = the bf16 hi/lo image of W2 (1 MB) streamed L2 -> SM once per pair and layer",
+            "peak_source": pk["src"] + " bf16 sustained"}
 
 
 def tcgemm_roofline(cabi, dev, n, pk, P=148, C=128, sets=3, iters=12):

@@ -141,6 +141,7 @@ def test_grouping_invariance_at_bench_size():
     os.environ["LMPCR_EMBED_FUSED"] = "0"
     os.environ["LMPCR_CONV_WIDE"] = "0"
     os.environ["LMPCR_UNPOOL_FUSED"] = "0"
+    os.environ["LMPCR_OAF"] = "0"
     try:
         full_l = cabi.filter_forward(x, params, cfg, want_latent=False, packed=packed)
         for p in (0, 36, 73):
@@ -153,6 +154,7 @@ def test_grouping_invariance_at_bench_size():
         del os.environ["LMPCR_EMBED_FUSED"]
         del os.environ["LMPCR_CONV_WIDE"]
         del os.environ["LMPCR_UNPOOL_FUSED"]
+        del os.environ["LMPCR_OAF"]
     # the latent-feature variant of the pair-resident tail (tiles stored) gives the same logits as the on-chip variant
     lat = cabi.filter_forward(x, params, cfg, want_latent=True, packed=packed)
     assert torch.equal(lat["logits"], full["logits"]) and torch.equal(lat["R"], full["R"])
