@@ -449,7 +449,7 @@ def live_unpool_roofline(kt, pairs, n, steps, pk, C=128, K=500):
 
 def live_oaf_roofline(kt, pairs, steps, pk, C=128, K=500, layers=3):
     """The OAFilter stage on the pair-resident kernel (oaf.cu) as it ran inside the timed steps: per pair, block and layer two
-    128 x 128 x K convolutions and one 128 x K x K cluster-mixing product (DESIGN.md 4.9).  Tensor-bound by executed work (three bf16
+    128 x 128 x K convolutions and one 128 x K x K cluster-mixing product (DESIGN.md 4.8).  Tensor-bound by executed work (three bf16
     products per fp32 product); its operands live in L2 / on chip, HBM sees the stack's input and output only."""
     launches, ms = kt
     if launches == 0:
