@@ -20,7 +20,7 @@ GUARD_BATCH, GUARD_PAIR = 0, 1
 STATUS_ZERO_WEIGHT, STATUS_DEGENERATE = 1, 2
 
 EXPORTS = [
-    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_launch_count_named", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_debug_pcn_profile", "lmpcr_debug_pool_profile", "lmpcr_debug_ktime_enable", "lmpcr_debug_ktime_read", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_nn_top2_algo", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_softmax_unpool", "lmpcr_softmax_unpool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
+    "lmpcr_abi_version", "lmpcr_launch_count", "lmpcr_launch_count_named", "lmpcr_last_error", "lmpcr_nn_tensor_debug", "lmpcr_debug_tc_profile", "lmpcr_debug_pcn_profile", "lmpcr_debug_oaf_profile", "lmpcr_debug_pool_profile", "lmpcr_debug_ktime_enable", "lmpcr_debug_ktime_read", "lmpcr_conv1x1", "lmpcr_conv1x1_workspace_bytes", "lmpcr_nn_soft", "lmpcr_nn_top2", "lmpcr_nn_top2_algo", "lmpcr_softmax_pool", "lmpcr_softmax_pool_workspace_bytes", "lmpcr_softmax_unpool", "lmpcr_softmax_unpool_workspace_bytes", "lmpcr_overlap_workspace_bytes", "lmpcr_overlap_count", "lmpcr_voxel_downsample", "lmpcr_device_info", "lmpcr_nn_workspace_bytes", "lmpcr_nn_argmin",
     "lmpcr_pairwise_distance", "lmpcr_gather_xyz", "lmpcr_mutual_xs", "lmpcr_knn3d_1", "lmpcr_kabsch", "lmpcr_residuals",
     "lmpcr_filter_num_params", "lmpcr_filter_workspace_bytes", "lmpcr_filter_forward", "lmpcr_pack_pose_records",
     "lmpcr_filter_pack_bytes", "lmpcr_filter_pack_weights", "lmpcr_filter_forward_packed",

@@ -7,6 +7,7 @@
 #include "conv_wide.cuh"
 #include "tcgemm.cuh"
 #include "pcn.cuh"
+#include "oaf.cuh"
 
 namespace lmpcr {
 
@@ -176,6 +177,7 @@ int lmpcr_nn_tensor_debug(const float* q_feat, int n_q_sets, int n_q, const floa
 
 int lmpcr_debug_tc_profile(unsigned long long* out16, int reset) { return tc_profile_read(out16, reset); }
 int lmpcr_debug_pcn_profile(unsigned long long* out40, int reset) { return pcn_profile_read(out40, reset); }
+int lmpcr_debug_oaf_profile(unsigned long long* out40, int reset) { return oaf_profile_read(out40, reset); }
 int lmpcr_debug_pool_profile(unsigned long long* out32, int reset) { return pool_fused_profile_read(out32, reset); }
 
 int lmpcr_pairwise_distance(const float* src, int n, const float* dst, int m, int dim, int batch, float* out, void* workspace,

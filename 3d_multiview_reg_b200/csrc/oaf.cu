@@ -19,9 +19,11 @@
 //   y and z go through per-pair scratch matrices that stay in L2 (TMA stores / loads of 32-cluster x 128-channel boxes, SWIZZLE_128B).
 // Products are split-bf16 (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, fp32 accumulation) exactly as in tcgemm.cu.
 //
-// Warp roles (288 threads, one CTA per SM): warps 0-7 are "row" warps -- thread = channel row (TMEM lane (warp & 3) * 32 + lane), set s = warp >> 2
-// takes the 32-cluster boxes of parity s; they are producers (box -> affine + ReLU -> operand image) and epilogue (TMEM -> bias / residual ->
-// statistics -> staged box -> TMA store) in turn.  Warp 8 issues the MMAs and the W2 ring's bulk copies.
+// Warp roles (576 threads, one CTA per SM): warps 0-15 are "row" warps -- thread = channel row (TMEM lane (warp & 3) * 32 + lane), set
+// s = (warp >> 2) & 1 takes the 32-cluster boxes of parity s, half hs = warp >> 3 the first or last 16 clusters of a box row; they are producers
+// (box -> affine + ReLU -> operand image) and epilogue (TMEM -> bias / residual -> statistics -> staged box -> TMA store) in turn.  Warp 16
+// issues the MMAs, warp 17 the W2 ring's bulk copies.  (Eight row warps on whole box rows: 496 us per 296 pairs x 3 layers; the dependent chains
+// of two warps per scheduler were the bound, profiles/r6_ncu_oaf_stack.txt.)
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
@@ -53,7 +55,9 @@ constexpr size_t SMEM_BYTES = OFF_TMEM + 16;
 static_assert(H_BYTES + 4 * XS_BYTES == NRING * WT_BYTES, "the 96 KB region is carved the same way in all phases");
 static_assert(OFF_BOX % 1024 == 0 && XS_BYTES % 1024 == 0, "SWIZZLE_128B boxes need 1024-byte aligned slots");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
-constexpr int NTHREADS = 9 * 32;
+constexpr int HW = TS / 2;                      // clusters per row thread and box: two warps share a box row-wise (16 row warps)
+constexpr int N_ROW_WARPS = 16;
+constexpr int NTHREADS = (N_ROW_WARPS + 2) * 32;      // + the MMA warp + the W2 ring's loader warp
 constexpr int TMEM_COLS = 512;
 constexpr int TM_ALO = 0, TM_W = 256, TM_D = 384, TM_D2 = 256;
 constexpr uint32_t IDESC13 = make_idesc(1, 0, 1, 128, TP);      // W (TMEM, K-major) . h (MN-major): M128 x N64
@@ -66,25 +70,83 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
         "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
-__device__ __forceinline__ void set_sync(int s) { asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory"); }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[HW]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < HW; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void set_sync(int s) { asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); }
+// half `hs` (16 clusters = four 16-byte chunks) of one channel row of a SWIZZLE_128B box: chunk c of row r sits at chunk position c ^ (r & 7)
+__device__ __forceinline__ void load_x_half(const uint8_t* xt, int r, int hs, float (&v)[HW]) {
+  const uint8_t* row = xt + r * 128;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 q = *reinterpret_cast<const float4*>(row + (((4 * hs + c) ^ (r & 7)) << 4));
+    v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+  }
+}
+__device__ __forceinline__ void store_x_half(uint8_t* xt, int r, int hs, const float (&v)[HW]) {
+  uint8_t* row = xt + r * 128;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<float4*>(row + (((4 * hs + c) ^ (r & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+// 16 fp32 values of one channel row (half `hs` of box `sub` of the tile) -> bf16 hi/lo in the MN-major operand image (tile_ops.cuh: store_h_row)
+__device__ __forceinline__ void store_h_half(uint8_t* hbase, int k, int sub, int hs, const float (&v)[HW]) {
+  uint8_t* row = hbase + (k >> 3) * MN_LBO + (k & 7) * 16 + (sub * (TS / 8) + 2 * hs) * MN_SBO;
+#pragma unroll
+  for (int gq = 0; gq < 2; ++gq) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float a = v[8 * gq + 2 * q], b = v[8 * gq + 2 * q + 1];
+      const __nv_bfloat162 hv = __floats2bfloat162_rn(a, b);
+      const float2 hf = __bfloat1622float2(hv);
+      const __nv_bfloat162 lv = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+      h[q] = *reinterpret_cast<const uint32_t*>(&hv);
+      l[q] = *reinterpret_cast<const uint32_t*>(&lv);
+    }
+    *reinterpret_cast<uint4*>(row + gq * MN_SBO) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(row + gq * MN_SBO + HP_BYTES) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
 
 // shifted running sums of one row over the boxes a thread sees (pcn.cu: RunStat)
 struct RowStat {
   float c0, s1, s2; bool have;
   __device__ __forceinline__ void reset() { c0 = 0.f; s1 = 0.f; s2 = 0.f; have = false; }
-  __device__ __forceinline__ void add(const float (&v)[TS], int ncv) {
+  __device__ __forceinline__ void add(const float (&v)[HW], int ncv) {
     if (ncv <= 0) return;
     if (!have) { c0 = v[0]; have = true; }
     float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int i = 0; i < TS; ++i) if (ncv >= TS || i < ncv) { const float d = v[i] - c0; a += d; b = fmaf(d, d, b); }
+    for (int i = 0; i < HW; ++i) if (ncv >= HW || i < ncv) { const float d = v[i] - c0; a += d; b = fmaf(d, d, b); }
     s1 += a; s2 += b;
   }
-  __device__ __forceinline__ float2 mean_m2(int n) const {      // n > 0
+  __device__ __forceinline__ float2 mean_m2(int n) const {      // (mean, M2) of the n values seen; n == 0: (0, 0)
+    if (n <= 0) return make_float2(0.f, 0.f);
     const float m = s1 / (float)n;
     return make_float2(c0 + m, fmaxf(s2 - s1 * m, 0.f));
   }
 };
+// Chan's merge of two (mean, M2) partials over na and nb values (nb may be 0)
+__device__ __forceinline__ float2 merge_stats(float2 a, int na, float2 b, int nb) {
+  if (nb <= 0) return a;
+  if (na <= 0) return b;
+  const float fa = (float)na, fb = (float)nb, n = fa + fb, d = b.x - a.x;
+  return make_float2(a.x + d * (fb / n), a.y + b.y + d * d * (fa * fb / n));
+}
 
 // InstanceNorm (biased variance, eps) + eval BatchNorm -> relu(x * sc + sh)       (oanet.py:60-62,77-79)
 __device__ __forceinline__ void fold_affine(float mean, float var, float eps_in, const OafBN& bn, int c, float& sc, float& sh) {
@@ -94,6 +156,19 @@ __device__ __forceinline__ void fold_affine(float mean, float var, float eps_in,
   sh = (-mean * rstd - __ldg(bn.rm + c)) * gsc + __ldg(bn.b + c);
 }
 
+// cycle counters for timing experiments (LMPCR_OAF_DEBUG=1): in CTA 0, lane 0 of row warp 0 (the leader of set 0) and of the control warp
+// accumulate the time between consecutive PROF() marks into the slot named at the later mark (lmpcr_debug_oaf_profile reads them)
+__device__ unsigned long long g_oaf_prof[40];
+#define PROF(slot)                                                                      \
+  do {                                                                                  \
+    if (PROFILE && prof_me) {                                                           \
+      const long long _t = clock64();                                                   \
+      atomicAdd(&g_oaf_prof[slot], (unsigned long long)(_t - tp));                      \
+      tp = _t;                                                                          \
+    }                                                                                   \
+  } while (0)
+
+template <bool PROFILE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_y,
                  const __grid_constant__ CUtensorMap tm_z, const OafArgs g) {
@@ -104,21 +179,29 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool row_warp = warp < 8;
+  const bool row_warp = warp < N_ROW_WARPS, mma_warp = warp == N_ROW_WARPS;
   const int s = (warp >> 2) & 1;                            // box parity this thread's set works on
+  const int hs = (warp >> 3) & 1;                           // which 16 clusters of a box row this thread takes
   const int ch = ((warp & 3) << 5) | lane;                  // channel row = TMEM lane
   const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-  const bool set_leader = row_warp && (warp & 3) == 0 && lane == 0;
+  const bool set_leader = row_warp && (warp & 3) == 0 && hs == 0 && lane == 0;
   const uint32_t sAHI = smem_u32(smem + OFF_AHI), sR = smem_u32(smem + OFF_R), sH = smem_u32(smem + OFF_H);
   uint8_t* in_box = smem + OFF_BOX + s * XS_BYTES;
   uint8_t* out_box = smem + OFF_BOX + (2 + s) * XS_BYTES;
   const uint32_t sIN = smem_u32(in_box), sOUT = smem_u32(out_box);
   const int K = g.K;
-  // valid clusters in the boxes of each set (a row's statistics are merged from the two sets' partial sums)
-  int nv0 = 0, nv1 = 0;
-  for (int c = 0; c < NCHK; ++c) { const int v = min(TS, max(0, K - c * TS)); if (c & 1) nv1 += v; else nv0 += v; }
+  // all CTAs stream the same W2 tiles: the order of the two passes (hx) and of the two 128-cluster tiles of a K step (qx) differs from CTA to
+  // CTA so that they do not all ask L2 for the same lines at the same time.  Every output element still sees the same accumulation order.
+  const int hx = blockIdx.x & 1, qx = (blockIdx.x >> 1) & 1;
+  const bool prof_me = PROFILE && blockIdx.x == 0 && lane == 0 && (warp == 0 || mma_warp);
+  long long tp = PROFILE ? clock64() : 0;
+  // valid clusters this thread sees per layer matrix, and the ones its partner half / the other set see (a row's statistics are merged from
+  // the four partial sums in a fixed order)
+  int nv[2][2] = {{0, 0}, {0, 0}};
+  for (int c = 0; c < NCHK; ++c)
+    for (int h = 0; h < 2; ++h) nv[c & 1][h] += min(HW, max(0, K - c * TS - h * HW));
 
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == N_ROW_WARPS) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -132,11 +215,11 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
     tc_fence_after();
     if (threadIdx.x == 0) {
       for (int i = 0; i < 6; ++i) mbar_init(BAR(B_XIN + i), 1);             // XIN[2], XRES[4]
-      mbar_init(BAR(B_HFULL), 8);
+      mbar_init(BAR(B_HFULL), N_ROW_WARPS);
       mbar_init(BAR(B_MMADONE), 1); mbar_init(BAR(B_MMADONE + 1), 1);
       for (int i = 0; i < 2 * NRING; ++i) mbar_init(BAR(B_WFULL + i), 1);   // WFULL[6], WEMPTY[6]
       mbar_init(BAR(B_D2FULL), 1);
-      mbar_init(BAR(B_EPIDONE), 8);
+      mbar_init(BAR(B_EPIDONE), N_ROW_WARPS);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -167,6 +250,7 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
     for (int t = 0; t < NT; ++t) {
       mbar_wait_fast(BAR(B_HFULL), t & 1);
       tc_fence_after();
+      PROF(32);
       const uint32_t leader = elect_one();
       const uint32_t d_tmem = tmem_base + TM_D + (t & 1) * TP;
 #pragma unroll
@@ -179,14 +263,28 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
       }
       tc_commit_pred(BAR(B_MMADONE + (t & 1)), leader);
       __syncwarp();
+      PROF(33);
     }
   };
-  // row warps: stage a box of 32 clusters and store it by TMA (two set-wide barriers; the leader's previous store has read the box)
-  auto emit_box = [&](const CUtensorMap* tm, const float (&v)[TS], int col0, int p) {
-    store_x_row(out_box, ch, v);
+  // row warps: stage this thread's 16 clusters of a box row; the set's leader stores the box by TMA once all 256 threads have written
+  auto emit_box = [&](const CUtensorMap* tm, const float (&v)[HW], int col0, int p) {
+    store_x_half(out_box, ch, hs, v);
     fence_proxy_async();
     set_sync(s);
     if (set_leader) { tma_store_3d(tm, sOUT, col0, 0, p); bulk_commit(); }
+  };
+  // (mean, M2) of this thread's row over all K clusters: the four partial sums (set x half) are merged half-first, then set 0 with set 1.
+  // Called by all row warps right before a phase boundary; the result is read after the boundary's __syncthreads (read_row_stats).
+  auto publish_row_stats = [&](const float2 mine) {
+    float2* slot = reinterpret_cast<float2*>(ex_s) + s * C + ch;
+    if (hs == 1) *slot = mine;
+    set_sync(s);
+    if (hs == 0) *slot = merge_stats(mine, nv[s][0], *slot, nv[s][1]);
+  };
+  auto read_row_stats = [&](float& mean, float& var) {
+    const float2* e = reinterpret_cast<const float2*>(ex_s);
+    const float2 m = merge_stats(e[ch], nv[0][0] + nv[0][1], e[C + ch], nv[1][0] + nv[1][1]);
+    mean = m.x; var = m.y / (float)K;
   };
 
   float sc = 1.f, sh = 0.f;        // row warps: the folded InstanceNorm + BatchNorm in front of the next 128 -> 128 convolution, for channel `ch`
@@ -202,26 +300,28 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
 
       // ============================================================ conv1: y = W1 . relu(x*sc + sh) + b1;  a = relu(bn_k(y)) stays on chip
       phase_sync();
+      PROF(30);
       if (row_warp) {
         if (set_leader) { mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, tm_in, s * TS, 0, p, BAR(B_XIN + s)); }
         if (warp < 4) load_w_row(L.w1);
+        PROF(9);
         const float b1 = __ldg(L.b1 + ch);
         auto epilogue1 = [&](int tt) {
-          const int cidx = 2 * tt + s, col0 = cidx * TS;
-          float v[TS];
-          tc_ld32(tmem_base + lane_sel + TM_D + (tt & 1) * TP + s * TS, v);
+          const int cidx = 2 * tt + s, col0 = cidx * TS, colh = col0 + hs * HW;
+          float v[HW];
+          tc_ld16(tmem_base + lane_sel + TM_D + (tt & 1) * TP + s * TS + hs * HW, v);
 #pragma unroll
-          for (int i = 0; i < TS; ++i) v[i] += b1;
+          for (int i = 0; i < HW; ++i) v[i] += b1;
           // a = relu(y * s2[k] + t2[k]) -> bf16 hi (K-major image in shared memory) / lo (tensor memory); exact zeros for k >= K (s2 = t2 = 0)
-          uint32_t lo[16];
-          uint8_t* adst = smem + OFF_AHI + cidx * ACH_BYTES + (ch >> 3) * K_SBO + (ch & 7) * 16;
+          uint32_t lo[8];
+          uint8_t* adst = smem + OFF_AHI + cidx * ACH_BYTES + (ch >> 3) * K_SBO + (ch & 7) * 16 + 2 * hs * K_LBO;
 #pragma unroll
-          for (int kg = 0; kg < 4; ++kg) {
+          for (int kg = 0; kg < 2; ++kg) {
             uint32_t hi[4];
 #pragma unroll
             for (int h4 = 0; h4 < 2; ++h4) {
-              const float4 s2 = __ldg(reinterpret_cast<const float4*>(tab + col0 + 8 * kg + 4 * h4));
-              const float4 t2 = __ldg(reinterpret_cast<const float4*>(tab + OAF_KMAX + col0 + 8 * kg + 4 * h4));
+              const float4 s2 = __ldg(reinterpret_cast<const float4*>(tab + colh + 8 * kg + 4 * h4));
+              const float4 t2 = __ldg(reinterpret_cast<const float4*>(tab + OAF_KMAX + colh + 8 * kg + 4 * h4));
               const int i0 = 8 * kg + 4 * h4;
               const float a0 = fmaxf(fmaf(v[i0], s2.x, t2.x), 0.f), a1 = fmaxf(fmaf(v[i0 + 1], s2.y, t2.y), 0.f);
               const float a2 = fmaxf(fmaf(v[i0 + 2], s2.z, t2.z), 0.f), a3 = fmaxf(fmaf(v[i0 + 3], s2.w, t2.w), 0.f);
@@ -233,85 +333,112 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
             }
             *reinterpret_cast<uint4*>(adst + kg * K_LBO) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           }
-          tc_st16(tmem_base + lane_sel + TM_ALO + cidx * 16, lo);
+          tc_st8(tmem_base + lane_sel + TM_ALO + cidx * 16 + hs * 8, lo);
+          PROF(5);
           if (set_leader) bulk_wait_read0();
           set_sync(s);
+          PROF(6);
           emit_box(&tm_y, v, col0, p);
+          PROF(7);
         };
         for (int t = 0; t < NT; ++t) {
           mbar_wait_fast(BAR(B_XIN + s), t & 1);
-          if (t >= 1) { mbar_wait_fast(BAR(B_MMADONE + ((t - 1) & 1)), ((t - 1) >> 1) & 1); tc_fence_after(); }   // H is free, accumulator t-1 is full
-          float v[TS];
-          load_x_row(in_box, ch, v);
+          PROF(0);
+          float v[HW];
+          load_x_half(in_box, ch, hs, v);
 #pragma unroll
-          for (int i = 0; i < TS; ++i) v[i] = fmaxf(fmaf(v[i], sc, sh), 0.f);
-          store_h_row(smem + OFF_H, ch, s, v);
+          for (int i = 0; i < HW; ++i) v[i] = fmaxf(fmaf(v[i], sc, sh), 0.f);
+          PROF(1);
+          if (t >= 1) { mbar_wait_fast(BAR(B_MMADONE + ((t - 1) & 1)), ((t - 1) >> 1) & 1); tc_fence_after(); }   // H is free, accumulator t-1 is full
+          PROF(2);
+          store_h_half(smem + OFF_H, ch, s, hs, v);
           fence_proxy_async();
           tc_fence_before();
+          PROF(3);
           set_sync(s);                                       // every row of the set's box has been read
           if (set_leader && t + 1 < NT) { mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, tm_in, (t + 1) * TP + s * TS, 0, p, BAR(B_XIN + s)); }
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_HFULL));
+          PROF(4);
           if (t >= 1) epilogue1(t - 1);
         }
         mbar_wait_fast(BAR(B_MMADONE + ((NT - 1) & 1)), ((NT - 1) >> 1) & 1);
         tc_fence_after();
+        PROF(2);
         epilogue1(NT - 1);
         tc_st_wait();
         fence_proxy_async();
         if (set_leader) bulk_wait0();                        // y is in global memory (L2) before conv2's epilogue loads it
-      } else {
+        PROF(8);
+      } else if (mma_warp) {
         mma_tiles_13();
       }
 
       // ============================================================ conv2: z = y + b2 + a . W2^T, two passes of 256 output clusters
       phase_sync();
+      PROF(30);
       if (row_warp) {
-        rs.reset();
+        // y boxes: two per set (this phase only: ring slots 2 + s and s, idle while the accumulator is read), so the load of box ii + 1 is in
+        // flight while box ii is consumed.  The halves are visited in the CTA's ring order (hx); their statistics are kept apart and merged in
+        // a fixed order, so a pair's result does not depend on the CTA it ran on
+        uint8_t* ybox[2] = {in_box, smem + OFF_R + s * XS_BYTES};
+        const uint32_t sY[2] = {sIN, sR + (uint32_t)s * XS_BYTES};
+        const uint32_t ybar[2] = {BAR(B_XIN + s), BAR(B_XRES + 2 * s)};
+        RowStat rsh[2];
+        rsh[0].reset(); rsh[1].reset();
         for (int h = 0; h < 2; ++h) {
+          const int hh = h ^ hx;                             // which 256 output clusters this pass produced
           mbar_wait_fast(BAR(B_D2FULL), h);
           tc_fence_after();
-          if (set_leader) { mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, &tm_y, (h * 8 + s) * TS, 0, p, BAR(B_XIN + s)); }
-          for (int ii = 0; ii < 4; ++ii) {
-            const int i = h * 4 + ii, cidx = h * 8 + 2 * ii + s, col0 = cidx * TS;
-            mbar_wait_fast(BAR(B_XIN + s), i & 1);
-            float y[TS], v[TS];
-            load_x_row(in_box, ch, y);
-            tc_ld32(tmem_base + lane_sel + TM_D2 + (cidx - h * 8) * TS, v);
+          PROF(10);
+          if (set_leader) {
+            for (int b = 0; b < 2; ++b) { mbar_expect_tx(ybar[b], XS_BYTES); tma_load_3d(sY[b], &tm_y, (hh * 8 + 2 * b + s) * TS, 0, p, ybar[b]); }
+          }
 #pragma unroll
-            for (int q = 0; q < TS / 4; ++q) {
-              const float4 b2 = __ldg(reinterpret_cast<const float4*>(tab + 2 * OAF_KMAX + col0 + 4 * q));
+          for (int ii = 0; ii < 4; ++ii) {
+            const int b = ii & 1, cidx = hh * 8 + 2 * ii + s, col0 = cidx * TS, colh = col0 + hs * HW;
+            mbar_wait_fast(ybar[b], (h * 2 + (ii >> 1)) & 1);
+            PROF(11);
+            float y[HW], v[HW];
+            load_x_half(ybox[b], ch, hs, y);
+            tc_ld16(tmem_base + lane_sel + TM_D2 + (cidx - hh * 8) * TS + hs * HW, v);
+#pragma unroll
+            for (int q = 0; q < HW / 4; ++q) {
+              const float4 b2 = __ldg(reinterpret_cast<const float4*>(tab + 2 * OAF_KMAX + colh + 4 * q));
               v[4 * q] += y[4 * q] + b2.x; v[4 * q + 1] += y[4 * q + 1] + b2.y; v[4 * q + 2] += y[4 * q + 2] + b2.z; v[4 * q + 3] += y[4 * q + 3] + b2.w;
             }
-            rs.add(v, K - col0);
+            rsh[hh].add(v, K - colh);
+            PROF(12);
             if (set_leader) bulk_wait_read0();
             set_sync(s);                                     // the set has read its y box; the staging box is free
-            if (set_leader && ii + 1 < 4) { mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, &tm_y, (cidx + 2) * TS, 0, p, BAR(B_XIN + s)); }
+            if (set_leader && ii + 2 < 4) { mbar_expect_tx(ybar[b], XS_BYTES); tma_load_3d(sY[b], &tm_y, (cidx + 4) * TS, 0, p, ybar[b]); }
+            PROF(13);
             emit_box(&tm_z, v, col0, p);
+            PROF(14);
           }
           if (set_leader) bulk_wait_read0();                 // the boxes alias the W2 ring: the last store has read its box
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_EPIDONE));
+          PROF(15);
         }
         if (set_leader) bulk_wait0();                        // z is in global memory (L2) before conv3 loads it
-        const float2 mm = rs.mean_m2(s ? nv1 : nv0);
-        *reinterpret_cast<float2*>(ex_s + (s * C + ch) * 2) = mm;
-      } else {
-        auto issue_load = [&](int Lq) {
-          const int st = Lq % NRING, h = Lq >> 5, r = Lq & 31, kc = r >> 1, qd = r & 1;
-          mbar_expect_tx(BAR(B_WFULL + st), WT_BYTES);
-          bulk_g2s(sR + st * WT_BYTES, L.w2 + ((size_t)(2 * h + qd) * NCHK + kc) * WT_BYTES, WT_BYTES, BAR(B_WFULL + st));
-        };
+        {
+          // this thread's clusters of half 0 and half 1, merged in that order whatever the order they were produced in
+          int n0 = 0, n1 = 0;
+          for (int c = s; c < NCHK; c += 2) { const int nn = min(HW, max(0, K - c * TS - hs * HW)); if (c < NCHK / 2) n0 += nn; else n1 += nn; }
+          publish_row_stats(merge_stats(rsh[0].mean_m2(n0), n0, rsh[1].mean_m2(n1), n1));
+        }
+        PROF(15);
+      } else if (mma_warp) {
         for (int h = 0; h < 2; ++h) {
-          if (h == 1) { mbar_wait_fast(BAR(B_EPIDONE), 0); tc_fence_after(); }       // accumulators read, boxes (= ring slots 2..5) free
-          const int base = h * 32;
-          if (lane == 0) for (int q = 0; q < NRING - 1; ++q) issue_load(base + q);
-          __syncwarp();
+          if (h == 1) { mbar_wait_fast(BAR(B_EPIDONE), 0); tc_fence_after(); }       // the accumulator of the first pass has been read
+          PROF(19);
           for (int r = 0; r < 32; ++r) {
-            const int it = base + r, st = it % NRING, kc = r >> 1, qd = r & 1;
+            const int it = h * 32 + r, st = it % NRING, kc = r >> 1, qd = (r & 1) ^ qx;
             mbar_wait_fast(BAR(B_WFULL + st), (it / NRING) & 1);
             tc_fence_after();
+            PROF(16);
             const uint32_t leader = elect_one();
             const uint32_t d_tmem = tmem_base + TM_D2 + qd * 128;
             const uint32_t sB = sR + st * WT_BYTES;
@@ -326,25 +453,35 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
             tc_commit_pred(BAR(B_WEMPTY + st), leader);
             if (r == 31) tc_commit_pred(BAR(B_D2FULL), leader);
             __syncwarp();
-            if (r + NRING - 1 < 32) {                        // refill the slot of the PREVIOUS tile (its MMAs have had a tile's time to finish)
-              if (r >= 1) mbar_wait_fast(BAR(B_WEMPTY + (it - 1) % NRING), ((it - 1) / NRING) & 1);
-              if (lane == 0) issue_load(it + NRING - 1);
-              __syncwarp();
-            }
+            PROF(17);
           }
         }
         // every commit of this phase has arrived before the barriers are re-initialised
         for (int it = 64 - NRING; it < 64; ++it) mbar_wait_fast(BAR(B_WEMPTY + it % NRING), (it / NRING) & 1);
+        PROF(18);
+      } else {
+        // the W2 ring's loader: tile Lq = (pass, K step, 128-cluster tile) in the order the MMA warp consumes them, six 16 KB slots; a slot is
+        // refilled as soon as the MMAs of its previous tile have completed
+        if (lane == 0) {
+          for (int Lq = 0; Lq < 64; ++Lq) {
+            const int st = Lq % NRING, h = (Lq >> 5) ^ hx, r = Lq & 31, kc = r >> 1, qd = (r & 1) ^ qx;
+            if (Lq == 32) mbar_wait_fast(BAR(B_EPIDONE), 0);                         // slots 2..5 are the epilogue's boxes between the passes
+            if (Lq >= NRING) mbar_wait_fast(BAR(B_WEMPTY + st), ((Lq - NRING) / NRING) & 1);
+            mbar_expect_tx(BAR(B_WFULL + st), WT_BYTES);
+            bulk_g2s(sR + st * WT_BYTES, L.w2 + ((size_t)(2 * h + qd) * NCHK + kc) * WT_BYTES, WT_BYTES, BAR(B_WFULL + st));
+          }
+        }
+        __syncwarp();
       }
 
       // ============================================================ conv3: out = W3 . relu(z*sc + sh) + b3 + x
       phase_sync();
+      PROF(30);
       if (row_warp) {
         {
-          const float2 m0 = *reinterpret_cast<const float2*>(ex_s + ch * 2), m1 = *reinterpret_cast<const float2*>(ex_s + (C + ch) * 2);
-          const float n0 = (float)nv0, n1 = (float)nv1, n = n0 + n1, d = m1.x - m0.x;
-          const float mean = m0.x + d * (n1 / n), m2 = m0.y + m1.y + d * d * (n0 * n1 / n);
-          fold_affine(mean, m2 / n, 1e-3f, L.bn3, ch, sc, sh);
+          float mean, var;
+          read_row_stats(mean, var);
+          fold_affine(mean, var, 1e-3f, L.bn3, ch, sc, sh);
         }
         uint8_t* res_box = smem + OFF_AHI + (s * 2) * XS_BYTES;       // + (t & 1) * XS_BYTES: the layer input x (residual), double-buffered
         const uint32_t sRES = smem_u32(res_box);
@@ -358,46 +495,57 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
         if (warp < 4) load_w_row(L.w3);
         const float b3 = __ldg(L.b3 + ch);
         rs.reset();
+        PROF(29);
         auto epilogue3 = [&](int tt) {
           const int cidx = 2 * tt + s, col0 = cidx * TS, b = tt & 1;
           mbar_wait_fast(BAR(B_XRES + 2 * s + b), (tt >> 1) & 1);
-          float x[TS], v[TS];
-          load_x_row(res_box + b * XS_BYTES, ch, x);
-          tc_ld32(tmem_base + lane_sel + TM_D + (tt & 1) * TP + s * TS, v);
+          PROF(28);
+          float x[HW], v[HW];
+          load_x_half(res_box + b * XS_BYTES, ch, hs, x);
+          tc_ld16(tmem_base + lane_sel + TM_D + (tt & 1) * TP + s * TS + hs * HW, v);
 #pragma unroll
-          for (int i = 0; i < TS; ++i) v[i] += b3 + x[i];
-          rs.add(v, K - col0);
+          for (int i = 0; i < HW; ++i) v[i] += b3 + x[i];
+          rs.add(v, K - col0 - hs * HW);
+          PROF(25);
           if (set_leader) bulk_wait_read0();
           set_sync(s);                                       // the set has read its residual box; the staging box is free
           if (set_leader && tt + 2 < NT) {
             mbar_expect_tx(BAR(B_XRES + 2 * s + b), XS_BYTES);
             tma_load_3d(sRES + b * XS_BYTES, tm_in, (tt + 2) * TP + s * TS, 0, p, BAR(B_XRES + 2 * s + b));
           }
+          PROF(26);
           emit_box(tm_out, v, col0, p);
+          PROF(27);
         };
         for (int t = 0; t < NT; ++t) {
           mbar_wait_fast(BAR(B_XIN + s), t & 1);
-          if (t >= 1) { mbar_wait_fast(BAR(B_MMADONE + ((t - 1) & 1)), ((t - 1) >> 1) & 1); tc_fence_after(); }
-          float v[TS];
-          load_x_row(in_box, ch, v);
+          PROF(20);
+          float v[HW];
+          load_x_half(in_box, ch, hs, v);
 #pragma unroll
-          for (int i = 0; i < TS; ++i) v[i] = fmaxf(fmaf(v[i], sc, sh), 0.f);
-          store_h_row(smem + OFF_H, ch, s, v);
+          for (int i = 0; i < HW; ++i) v[i] = fmaxf(fmaf(v[i], sc, sh), 0.f);
+          PROF(21);
+          if (t >= 1) { mbar_wait_fast(BAR(B_MMADONE + ((t - 1) & 1)), ((t - 1) >> 1) & 1); tc_fence_after(); }
+          PROF(22);
+          store_h_half(smem + OFF_H, ch, s, hs, v);
           fence_proxy_async();
           tc_fence_before();
+          PROF(23);
           set_sync(s);
           if (set_leader && t + 1 < NT) { mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, &tm_z, (t + 1) * TP + s * TS, 0, p, BAR(B_XIN + s)); }
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_HFULL));
+          PROF(24);
           if (t >= 1) epilogue3(t - 1);
         }
         mbar_wait_fast(BAR(B_MMADONE + ((NT - 1) & 1)), ((NT - 1) >> 1) & 1);
         tc_fence_after();
+        PROF(22);
         epilogue3(NT - 1);
         if (set_leader) bulk_wait0();                        // the layer's output is in global memory before the next layer (or kernel) loads it
-        const float2 mm = rs.mean_m2(s ? nv1 : nv0);
-        *reinterpret_cast<float2*>(ex_s + (s * C + ch) * 2) = mm;
-      } else {
+        publish_row_stats(rs.mean_m2(nv[s][hs]));
+        PROF(31);
+      } else if (mma_warp) {
         mma_tiles_13();
       }
       // the next layer's InstanceNorm + BatchNorm from the statistics of this layer's output
@@ -406,17 +554,16 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
         __syncthreads();
         tc_fence_after();
         if (row_warp) {
-          const float2 m0 = *reinterpret_cast<const float2*>(ex_s + ch * 2), m1 = *reinterpret_cast<const float2*>(ex_s + (C + ch) * 2);
-          const float n0 = (float)nv0, n1 = (float)nv1, n = n0 + n1, d = m1.x - m0.x;
-          const float mean = m0.x + d * (n1 / n), m2 = m0.y + m1.y + d * d * (n0 * n1 / n);
-          fold_affine(mean, m2 / n, 1e-3f, g.layer[l + 1].bn1, ch, sc, sh);
+          float mean, var;
+          read_row_stats(mean, var);
+          fold_affine(mean, var, 1e-3f, g.layer[l + 1].bn1, ch, sc, sh);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == N_ROW_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -452,6 +599,13 @@ int make_oaf_map(CUtensorMap* tm, const float* base, int K, int ld, long long ba
 
 }  // namespace
 
+int oaf_profile_read(unsigned long long* out40, int reset) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out40, g_oaf_prof, sizeof(unsigned long long) * 40);
+  if (reset) { unsigned long long z[40] = {0}; cudaMemcpyToSymbol(g_oaf_prof, z, sizeof(z)); }
+  return e == cudaSuccess ? 0 : -1;
+}
+
 int launch_oaf_tables(const OafBN* bn2, const float* const* bias2, int n_layers, int K, float* tab, cudaStream_t st) {
   LMPCR_REQUIRE(bn2 && bias2 && tab && n_layers >= 1 && n_layers <= OAF_MAX_LAYERS && K >= 1 && K <= OAF_KMAX, LMPCR_ERR_ARG, "oaf_tables: bad arguments");
   OafBN b[OAF_MAX_LAYERS]; const float* c[OAF_MAX_LAYERS];
@@ -483,7 +637,8 @@ int launch_oaf_stack(float* xd0, float* xd1, float* y, float* z, int ld, long lo
     static unsigned char attr_set[64];
     const int dev = device_ordinal();
     if (!attr_set[dev]) {
-      const cudaError_t e = cudaFuncSetAttribute(oaf_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      cudaError_t e = cudaFuncSetAttribute(oaf_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(oaf_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
       LMPCR_REQUIRE(e == cudaSuccess, LMPCR_ERR_LAUNCH, "oaf_stack: cannot reserve %zu bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
       attr_set[dev] = 1;
     }
@@ -491,7 +646,9 @@ int launch_oaf_stack(float* xd0, float* xd1, float* y, float* z, int ld, long lo
   int grid = sm_count();
   if (a.P < grid) grid = a.P;
   ktime_begin("oaf_stack_kernel", st);
-  oaf_stack_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], a);
+  const char* dbg = getenv("LMPCR_OAF_DEBUG");
+  if (dbg && atoi(dbg) == 1) oaf_stack_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], a);
+  else oaf_stack_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], a);
   ktime_end("oaf_stack_kernel", st);
   return check_launch("oaf_stack_kernel");
 }

@@ -27,6 +27,7 @@ struct OafArgs {
 
 // per layer: s2[k] = gamma/sqrt(rv + 1e-5), t2[k] = beta - rm*s2[k], b2[k]; zeros for k >= K (oanet.py:73-75, eval mode)
 int launch_oaf_tables(const OafBN* bn2, const float* const* bias2, int n_layers, int K, float* tab, cudaStream_t st);
+int oaf_profile_read(unsigned long long* out40, int reset);                      // timing experiments (LMPCR_OAF_DEBUG=1)
 bool oaf_supported(int C, int K, int ld, long long batch, const float* xd0, const float* xd1, const float* y, const float* z);
 // x (layer input) ping-pongs between xd0 and xd1: layer i reads xd[i & 1] and writes xd[(i + 1) & 1]; y, z are per-pair scratch of the same
 // shape [P][128][ld] fp32 with batch stride `batch` floats.  The stack's output is xd[n_layers & 1].

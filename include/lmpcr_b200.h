@@ -95,6 +95,7 @@ int lmpcr_nn_tensor_debug(const float* q_feat, int n_q_sets, int n_q, const floa
 int lmpcr_debug_tc_profile(unsigned long long* out16, int reset);
 /* The same for the pair-resident PointCN kernel (LMPCR_PCN_DEBUG=1): 40 counters, see csrc/pcn.cu. */
 int lmpcr_debug_pcn_profile(unsigned long long* out40, int reset);
+int lmpcr_debug_oaf_profile(unsigned long long* out40, int reset);   /* oaf_stack_kernel, LMPCR_OAF_DEBUG=1 */
 /* Diagnostic: device time of individual kernels inside a larger call.  While enabled, the launchers of pcn_stack_kernel,
  * pool_fused_kernel, nn_sweep_kernel and nn_rescore_kernel bracket their launch with a CUDA event pair on the launching stream;
  * lmpcr_debug_ktime_read synchronises on them and returns the number of launches of `kernel_name` since the enable and their summed

@@ -32,3 +32,23 @@ cabi.ktime_enable(False)
 flop = (2.0 * 2 * 128 * 128 * K + 2.0 * 128 * K * K) * layers * P
 print("oaf_stack_kernel: %d pairs x %d layers: %.1f us per launch (%d launches), %.1f us per pair and layer, %.1f TFLOP/s algorithmic"
       % (P, layers, 1e3 * ms / n, n, 1e3 * ms / n / layers / ((P + 147) // 148), flop / (ms / n * 1e-3) / 1e12))
+
+if int(os.environ.get("LMPCR_OAF_DEBUG", "0")):
+    import ctypes
+    buf = (ctypes.c_ulonglong * 40)()
+    cabi.load().lmpcr_debug_oaf_profile(buf, 1)
+    cabi.oafilter_stack(x, params)
+    cabi.load().lmpcr_debug_oaf_profile(buf, 1)
+    names = {30: "phase_sync", 9: "conv1 start (first load, W1 -> TMEM)", 0: "conv1 wait x box", 1: "conv1 load + affine", 2: "conv1 wait MMADONE", 3: "conv1 operand image + fences",
+             4: "conv1 set barrier + next load + arrive", 5: "conv1 epi: tc_ld + a = relu(bn_k(y)) -> smem / TMEM", 6: "conv1 epi: store drained + set barrier",
+             7: "conv1 epi: stage + set barrier + TMA store", 8: "conv1 tail", 10: "conv2 wait D2FULL (= MMA phase)", 11: "conv2 epi: wait y box", 12: "conv2 epi: box + tc_ld + z + stats",
+             13: "conv2 epi: store drained + set barrier + next load", 14: "conv2 epi: stage + set barrier + TMA store", 15: "conv2 epi: half end / stats",
+             16: "conv2 ctl: wait WFULL", 17: "conv2 ctl: MMA issue + commit", 18: "conv2 ctl: wait WEMPTY + refill", 19: "conv2 ctl: wait EPIDONE",
+             29: "conv3 start", 20: "conv3 wait z box", 21: "conv3 load + affine", 22: "conv3 wait MMADONE", 23: "conv3 operand image + fences", 24: "conv3 set barrier + next load + arrive",
+             28: "conv3 epi: wait residual box", 25: "conv3 epi: box + tc_ld + out + stats", 26: "conv3 epi: store drained + set barrier + next load",
+             27: "conv3 epi: stage + set barrier + TMA store", 31: "conv3 tail / stats", 32: "conv1/3 ctl: wait HFULL", 33: "conv1/3 ctl: MMA issue + commit"}
+    per = layers * ((P + 147) // 148)
+    tot_row = sum(buf[i] for i in names if i not in (16, 17, 18, 19, 32, 33))
+    for i in names:
+        print("%-58s %9.0f cycles per pair and layer" % (names[i], buf[i] / per))
+    print("row thread total %.0f cycles per pair and layer" % (tot_row / per))
