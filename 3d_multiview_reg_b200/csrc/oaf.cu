@@ -49,8 +49,8 @@ constexpr int OFF_H = OFF_R;
 constexpr int OFF_BOX = OFF_R + H_BYTES;
 constexpr int OFF_EX = OFF_R + NRING * WT_BYTES;          // row statistics of the two sets: [2][128] x (mean, M2)
 constexpr int OFF_BAR = OFF_EX + 2 * C * 2 * 4;
-enum { B_XIN = 0, B_XRES = 2, B_HFULL = 6, B_MMADONE = 7, B_WFULL = 9, B_WEMPTY = 15, B_D2FULL = 21, B_EPIDONE = 22, N_BARS = 23 };
-constexpr int OFF_TMEM = OFF_BAR + 24 * 8;
+enum { B_XIN = 0, B_XRES = 2, B_HFULL = 6, B_MMADONE = 7, B_WFULL = 9, B_WEMPTY = 15, B_D2FULL = 21, B_EPIDONE = 22, B_ZIN2 = 23, N_BARS = 25 };
+constexpr int OFF_TMEM = OFF_BAR + 26 * 8;
 constexpr size_t SMEM_BYTES = OFF_TMEM + 16;
 static_assert(H_BYTES + 4 * XS_BYTES == NRING * WT_BYTES, "the 96 KB region is carved the same way in all phases");
 static_assert(OFF_BOX % 1024 == 0 && XS_BYTES % 1024 == 0, "SWIZZLE_128B boxes need 1024-byte aligned slots");
@@ -220,6 +220,7 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
       for (int i = 0; i < 2 * NRING; ++i) mbar_init(BAR(B_WFULL + i), 1);   // WFULL[6], WEMPTY[6]
       mbar_init(BAR(B_D2FULL), 1);
       mbar_init(BAR(B_EPIDONE), N_ROW_WARPS);
+      mbar_init(BAR(B_ZIN2), 1); mbar_init(BAR(B_ZIN2 + 1), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -308,6 +309,13 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
         const float b1 = __ldg(L.b1 + ch);
         auto epilogue1 = [&](int tt) {
           const int cidx = 2 * tt + s, col0 = cidx * TS, colh = col0 + hs * HW;
+          // the BatchNorm-over-clusters constants of this thread's 16 clusters first: their loads are in flight while the accumulator arrives
+          float4 s2[4], t2[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            s2[q] = __ldg(reinterpret_cast<const float4*>(tab + colh + 4 * q));
+            t2[q] = __ldg(reinterpret_cast<const float4*>(tab + OAF_KMAX + colh + 4 * q));
+          }
           float v[HW];
           tc_ld16(tmem_base + lane_sel + TM_D + (tt & 1) * TP + s * TS + hs * HW, v);
 #pragma unroll
@@ -320,11 +328,10 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
             uint32_t hi[4];
 #pragma unroll
             for (int h4 = 0; h4 < 2; ++h4) {
-              const float4 s2 = __ldg(reinterpret_cast<const float4*>(tab + colh + 8 * kg + 4 * h4));
-              const float4 t2 = __ldg(reinterpret_cast<const float4*>(tab + OAF_KMAX + colh + 8 * kg + 4 * h4));
+              const float4 sq = s2[2 * kg + h4], tq = t2[2 * kg + h4];
               const int i0 = 8 * kg + 4 * h4;
-              const float a0 = fmaxf(fmaf(v[i0], s2.x, t2.x), 0.f), a1 = fmaxf(fmaf(v[i0 + 1], s2.y, t2.y), 0.f);
-              const float a2 = fmaxf(fmaf(v[i0 + 2], s2.z, t2.z), 0.f), a3 = fmaxf(fmaf(v[i0 + 3], s2.w, t2.w), 0.f);
+              const float a0 = fmaxf(fmaf(v[i0], sq.x, tq.x), 0.f), a1 = fmaxf(fmaf(v[i0 + 1], sq.y, tq.y), 0.f);
+              const float a2 = fmaxf(fmaf(v[i0 + 2], sq.z, tq.z), 0.f), a3 = fmaxf(fmaf(v[i0 + 3], sq.w, tq.w), 0.f);
               const __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
               const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
               const __nv_bfloat162 l01 = __floats2bfloat162_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2bfloat162_rn(a2 - f23.x, a3 - f23.y);
@@ -399,13 +406,15 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
             const int b = ii & 1, cidx = hh * 8 + 2 * ii + s, col0 = cidx * TS, colh = col0 + hs * HW;
             mbar_wait_fast(ybar[b], (h * 2 + (ii >> 1)) & 1);
             PROF(11);
+            float4 b2[HW / 4];                               // conv2's bias of this thread's 16 clusters: in flight while the accumulator arrives
+#pragma unroll
+            for (int q = 0; q < HW / 4; ++q) b2[q] = __ldg(reinterpret_cast<const float4*>(tab + 2 * OAF_KMAX + colh + 4 * q));
             float y[HW], v[HW];
             load_x_half(ybox[b], ch, hs, y);
             tc_ld16(tmem_base + lane_sel + TM_D2 + (cidx - hh * 8) * TS + hs * HW, v);
 #pragma unroll
             for (int q = 0; q < HW / 4; ++q) {
-              const float4 b2 = __ldg(reinterpret_cast<const float4*>(tab + 2 * OAF_KMAX + colh + 4 * q));
-              v[4 * q] += y[4 * q] + b2.x; v[4 * q + 1] += y[4 * q + 1] + b2.y; v[4 * q + 2] += y[4 * q + 2] + b2.z; v[4 * q + 3] += y[4 * q + 3] + b2.w;
+              v[4 * q] += y[4 * q] + b2[q].x; v[4 * q + 1] += y[4 * q + 1] + b2[q].y; v[4 * q + 2] += y[4 * q + 2] + b2[q].z; v[4 * q + 3] += y[4 * q + 3] + b2[q].w;
             }
             rsh[hh].add(v, K - colh);
             PROF(12);
@@ -485,9 +494,14 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
         }
         uint8_t* res_box = smem + OFF_AHI + (s * 2) * XS_BYTES;       // + (t & 1) * XS_BYTES: the layer input x (residual), double-buffered
         const uint32_t sRES = smem_u32(res_box);
+        // z boxes: double-buffered too in this phase (the second one in the idle half of the a_hi region), so that the load of tile t + 2 has a
+        // whole tile's time: with one box the TMA latency was exposed on every tile (9.9k clocks per pair and layer)
+        uint8_t* zbox[2] = {in_box, smem + OFF_AHI + (4 + s) * XS_BYTES};
+        const uint32_t sZ[2] = {sIN, smem_u32(zbox[1])};
+        const uint32_t zbar[2] = {BAR(B_XIN + s), BAR(B_ZIN2 + s)};
         if (set_leader) {
-          mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, &tm_z, s * TS, 0, p, BAR(B_XIN + s));
           for (int b = 0; b < 2; ++b) {
+            mbar_expect_tx(zbar[b], XS_BYTES); tma_load_3d(sZ[b], &tm_z, b * TP + s * TS, 0, p, zbar[b]);
             mbar_expect_tx(BAR(B_XRES + 2 * s + b), XS_BYTES);
             tma_load_3d(sRES + b * XS_BYTES, tm_in, b * TP + s * TS, 0, p, BAR(B_XRES + 2 * s + b));
           }
@@ -518,10 +532,10 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
           PROF(27);
         };
         for (int t = 0; t < NT; ++t) {
-          mbar_wait_fast(BAR(B_XIN + s), t & 1);
+          mbar_wait_fast(zbar[t & 1], (t >> 1) & 1);
           PROF(20);
           float v[HW];
-          load_x_half(in_box, ch, hs, v);
+          load_x_half(zbox[t & 1], ch, hs, v);
 #pragma unroll
           for (int i = 0; i < HW; ++i) v[i] = fmaxf(fmaf(v[i], sc, sh), 0.f);
           PROF(21);
@@ -532,7 +546,7 @@ oaf_stack_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constan
           tc_fence_before();
           PROF(23);
           set_sync(s);
-          if (set_leader && t + 1 < NT) { mbar_expect_tx(BAR(B_XIN + s), XS_BYTES); tma_load_3d(sIN, &tm_z, (t + 1) * TP + s * TS, 0, p, BAR(B_XIN + s)); }
+          if (set_leader && t + 2 < NT) { mbar_expect_tx(zbar[t & 1], XS_BYTES); tma_load_3d(sZ[t & 1], &tm_z, (t + 2) * TP + s * TS, 0, p, zbar[t & 1]); }
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_HFULL));
           PROF(24);
