@@ -22,8 +22,9 @@
 // Warp roles (576 threads, one CTA per SM): warps 0-15 are "row" warps -- thread = channel row (TMEM lane (warp & 3) * 32 + lane), set
 // s = (warp >> 2) & 1 takes the 32-cluster boxes of parity s, half hs = warp >> 3 the first or last 16 clusters of a box row; they are producers
 // (box -> affine + ReLU -> operand image) and epilogue (TMEM -> bias / residual -> statistics -> staged box -> TMA store) in turn.  Warp 16
-// issues the MMAs, warp 17 the W2 ring's bulk copies.  (Eight row warps on whole box rows: 496 us per 296 pairs x 3 layers; the dependent chains
-// of two warps per scheduler were the bound, profiles/r6_ncu_oaf_stack.txt.)
+// issues the MMAs, warp 17 the W2 ring's bulk copies.  (History, DESIGN.md 4.8: with ONE warp issuing MMAs and refilling the ring conv2's tensor
+// phase took 69k instead of 41k clocks per pair and layer; eight row warps on whole box rows were as fast as sixteen on half rows -- the row
+// warps' time is the chain of hand-offs per tile, not instruction throughput.)
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
@@ -52,7 +53,7 @@ constexpr int OFF_BAR = OFF_EX + 2 * C * 2 * 4;
 enum { B_XIN = 0, B_XRES = 2, B_HFULL = 6, B_MMADONE = 7, B_WFULL = 9, B_WEMPTY = 15, B_D2FULL = 21, B_EPIDONE = 22, B_ZIN2 = 23, N_BARS = 25 };
 constexpr int OFF_TMEM = OFF_BAR + 26 * 8;
 constexpr size_t SMEM_BYTES = OFF_TMEM + 16;
-static_assert(H_BYTES + 4 * XS_BYTES == NRING * WT_BYTES, "the 96 KB region is carved the same way in all phases");
+static_assert(N_BARS <= 26 && H_BYTES + 4 * XS_BYTES == NRING * WT_BYTES, "the 96 KB region is carved the same way in all phases");
 static_assert(OFF_BOX % 1024 == 0 && XS_BYTES % 1024 == 0, "SWIZZLE_128B boxes need 1024-byte aligned slots");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
 constexpr int HW = TS / 2;                      // clusters per row thread and box: two warps share a box row-wise (16 row warps)
